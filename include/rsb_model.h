@@ -1,0 +1,122 @@
+/*
+ * rsb_model.h -- flat, host-side description of one compiled scene ("model") and of the
+ * robosuite task wrapped around it ("task").  This is the data format that crosses the
+ * C-ABI once, at rsb_create(); the CUDA library converts it to fp32 and uploads it.
+ *
+ * It stands where the reference reaches `suite.make(...)` -> robosuite builds MJCF ->
+ * mujoco-py compiles `MjSim` (reference call site: util/rlkit_utils.py:49-56).  Field names
+ * follow MuJoCo's mjModel so that a maintainer holding a real
+ * mjModel can fill the struct field by field.  All arrays are host pointers owned by the
+ * caller and only read during rsb_create()/oracle calls.  Quaternions are (w,x,y,z).
+ */
+#ifndef RSB_MODEL_H
+#define RSB_MODEL_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { RSB_JNT_FREE = 0, RSB_JNT_SLIDE = 2, RSB_JNT_HINGE = 3 };           /* mjtJoint values */
+enum { RSB_GEOM_PLANE = 0, RSB_GEOM_SPHERE = 2, RSB_GEOM_CAPSULE = 3,
+       RSB_GEOM_CYLINDER = 5, RSB_GEOM_BOX = 6 };                          /* mjtGeom values  */
+enum { RSB_CONE_PYRAMIDAL = 0, RSB_CONE_ELLIPTIC = 1 };
+enum { RSB_TASK_LIFT = 0, RSB_TASK_DOOR = 1, RSB_TASK_STACK = 2, RSB_TASK_TWOARMLIFT = 3 };
+enum { RSB_CTRL_OSC_POSE = 0, RSB_CTRL_OSC_POSITION = 1, RSB_CTRL_JOINT_VELOCITY = 2,
+       RSB_CTRL_JOINT_TORQUE = 3 };
+
+#define RSB_MAX_ROBOTS 2
+#define RSB_ARM_DOF 7
+#define RSB_MAX_FINGER_GEOMS 4
+#define RSB_MAX_OBJ 4
+
+typedef struct rsb_model {
+  /* sizes */
+  int nq, nv, nu, nbody, njnt, ngeom, nsite, npair, nM;
+  /* <option> */
+  double timestep, gravity[3], impratio, tolerance, ls_tolerance, meaninertia;
+  int cone, iterations, ls_iterations;
+  /* bodies (tree order, body 0 = world) */
+  const int *body_parentid, *body_rootid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum;
+  const double *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia;
+  const double *body_invweight0;          /* [nbody][2] (translation, rotation) */
+  /* joints */
+  const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_bodyid, *jnt_limited;
+  const double *jnt_pos, *jnt_axis, *jnt_range, *jnt_stiffness, *jnt_margin;
+  const double *jnt_solref, *jnt_solimp;  /* limit rows: [njnt][2], [njnt][5] */
+  /* dofs */
+  const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr;
+  const double *dof_armature, *dof_damping, *dof_frictionloss, *dof_invweight0;
+  const double *dof_solref, *dof_solimp;  /* frictionloss rows */
+  const double *qpos0, *qpos_spring;
+  /* geoms */
+  const int *geom_type, *geom_bodyid;
+  const double *geom_size, *geom_pos, *geom_quat, *geom_rbound;
+  /* sites */
+  const int *site_bodyid;
+  const double *site_pos, *site_quat;
+  /* statically filtered candidate geom pairs, in MuJoCo contact order
+     (body pair ascending, then geom ids), with the mixed contact parameters */
+  const int *pair_geom1, *pair_geom2, *pair_condim;
+  const double *pair_friction;            /* [npair][5] */
+  const double *pair_solref, *pair_solimp;/* [npair][2], [npair][5] */
+  const double *pair_margin, *pair_gap;
+  /* actuators (joint transmission only) */
+  const int *act_dofid, *act_ctrllimited, *act_forcelimited;
+  const double *act_gain, *act_bias;      /* gainprm[0]; biasprm[0..2] -> [nu][3] */
+  const double *act_ctrlrange, *act_forcerange, *act_gear;
+} rsb_model;
+
+/* One robot arm + gripper + its controller, as robosuite's SingleArm/Controller hold them
+   (SURVEY.md A.2).  Index arrays are into the model's dof/qpos/actuator spaces. */
+typedef struct rsb_robot {
+  int arm_qposadr[RSB_ARM_DOF], arm_dofadr[RSB_ARM_DOF], arm_act[RSB_ARM_DOF];
+  int grip_ndof;                           /* gripper joints/actuators (2 for Panda/Rethink) */
+  int grip_qposadr[2], grip_dofadr[2], grip_act[2];
+  int grip_action_dim;                     /* 1 */
+  double grip_sign[2];                     /* Panda (-1,+1); Rethink (+1,-1) */
+  double grip_speed;                       /* 0.01 */
+  double grip_init_qpos[2];
+  int eef_site, eef_body;                  /* grip_site, hand body (for eef_quat) */
+  double init_qpos[RSB_ARM_DOF];
+  int left_finger_geoms[RSB_MAX_FINGER_GEOMS], n_left_finger_geoms;
+  int right_finger_geoms[RSB_MAX_FINGER_GEOMS], n_right_finger_geoms;
+  /* controller */
+  int ctrl_type, control_dim;              /* 6 / 3 / 7 */
+  double input_max[RSB_ARM_DOF], input_min[RSB_ARM_DOF];
+  double output_max[RSB_ARM_DOF], output_min[RSB_ARM_DOF];
+  double kp[RSB_ARM_DOF], kd[RSB_ARM_DOF]; /* OSC: 6 used (kd = 2 sqrt(kp) damping); JV: PID kp, kd per joint */
+  double ki[RSB_ARM_DOF];                  /* JV integral gain (0 -> pure P law of robosuite v1.0) */
+  double nullspace_kp;                     /* 10 */
+  int uncouple_pos_ori;
+  double torque_limit_lo[RSB_ARM_DOF], torque_limit_hi[RSB_ARM_DOF];
+  double velocity_limit_lo[RSB_ARM_DOF], velocity_limit_hi[RSB_ARM_DOF];
+  int has_velocity_limits;
+} rsb_robot;
+
+typedef struct rsb_task {
+  int task_id, nrobot;
+  rsb_robot robot[RSB_MAX_ROBOTS];
+  int horizon, substeps, ignore_done, reward_shaping;
+  double reward_scale;
+  double init_noise;                       /* gaussian std on arm init qpos (0.02) */
+  double table_height;                     /* table_offset z (0.8) */
+  int obs_dim, act_dim;
+  /* task objects: meaning depends on task_id
+     LIFT:  obj_body[0]=cube, obj_geom[0]=cube geom, obj_qposadr[0]=free joint
+     DOOR:  obj_body[0]=door, [1]=latch(handle), obj_site[0]=handle site,
+            obj_qposadr[0]=hinge, [1]=latch hinge, obj_body[2]=door frame root (placed)
+     STACK: cubeA=0, cubeB=1
+     TWOARMLIFT: obj_body[0]=pot, obj_site[0..1]=handle sites, obj_geom[0..1]=handle geoms */
+  int obj_body[RSB_MAX_OBJ], obj_geom[RSB_MAX_OBJ], obj_site[RSB_MAX_OBJ];
+  int obj_qposadr[RSB_MAX_OBJ], obj_dofadr[RSB_MAX_OBJ];
+  double obj_half[RSB_MAX_OBJ][3];         /* box half sizes for placement z / overlap tests */
+  /* placement sampler: uniform ranges (robosuite UniformRandomSampler) */
+  double place_x[RSB_MAX_OBJ][2], place_y[RSB_MAX_OBJ][2], place_yaw[RSB_MAX_OBJ][2];
+  double place_z[RSB_MAX_OBJ];             /* absolute z written to the free joint */
+  double place_ref[3];                     /* reference point added to sampled xy */
+} rsb_task;
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSB_MODEL_H */

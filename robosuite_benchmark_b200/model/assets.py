@@ -1,0 +1,188 @@
+"""Authored MJCF for the benchmark scenes (robots, grippers, arena, task objects).
+
+robosuite's own XML/mesh assets are not available in the build environment (SURVEY.md §0.3,
+A.5), so these are written from public kinematic data (Franka Panda / Rethink Sawyer link
+frames, robosuite's table arena and object conventions) with PRIMITIVE collision geoms only.
+Everything robosuite would take from its asset files is data here: a maintainer with the real
+assets can feed their compiled mjModel through include/rsb_model.h instead.
+
+Deviations from robosuite v1.0 (documented in DESIGN.md): arm links carry no collision geoms
+(meshes upstream); gripper hand/fingers/pads are boxes; the Lift cube half-size is the mean
+(0.021) of robosuite's U(0.020, 0.022) build-time draw.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+PI = np.pi
+
+BASE_OPTION = ('<compiler angle="radian"/>'
+               '<option timestep="0.002" cone="elliptic" impratio="20" integrator="Euler" solver="Newton" '
+               'iterations="100" tolerance="1e-8" gravity="0 0 -9.81"/>')
+
+# collision classes: robot parts hit objects/arena (contype 1) but not each other
+ROBOT_COL = 'contype="0" conaffinity="1"'
+WORLD_COL = 'contype="1" conaffinity="1"'
+NO_COL = 'contype="0" conaffinity="0"'
+
+
+def _f(v):
+    return " ".join(f"{float(x):.10g}" for x in np.atleast_1d(v))
+
+
+# ----------------------------------------------------------------------------- grippers
+def panda_gripper(pf: str) -> str:
+    """Franka hand: two slide fingers (±y), box pads with high friction."""
+    pad = f'{ROBOT_COL} condim="4" friction="2 0.05 0.0001" solref="0.01 0.5"'
+    return f'''
+<body name="{pf}right_hand" pos="0 0 0.107" quat="0.9238795 0 0 -0.3826834">
+  <inertial pos="0 0 0.03" mass="0.5" diaginertia="0.002 0.002 0.002"/>
+  <geom name="{pf}hand_col" type="box" pos="0 0 0.0333" size="0.0315 0.102 0.0333" {ROBOT_COL}/>
+  <site name="{pf}grip_site" pos="0 0 0.1025"/>
+  <body name="{pf}leftfinger" pos="0 0 0.0584">
+    <inertial pos="0 0.01 0.02" mass="0.1" diaginertia="0.0001 0.0001 0.0001"/>
+    <joint name="{pf}finger_joint1" type="slide" axis="0 1 0" range="0 0.04" damping="100" armature="1.0" frictionloss="1.0"/>
+    <geom name="{pf}finger1_col" type="box" pos="0 0.0115 0.027" size="0.0105 0.0075 0.027" {ROBOT_COL}/>
+    <geom name="{pf}finger1_pad" type="box" pos="0 0.0025 0.044" size="0.008 0.0015 0.008" {pad}/>
+  </body>
+  <body name="{pf}rightfinger" pos="0 0 0.0584">
+    <inertial pos="0 -0.01 0.02" mass="0.1" diaginertia="0.0001 0.0001 0.0001"/>
+    <joint name="{pf}finger_joint2" type="slide" axis="0 1 0" range="-0.04 0" damping="100" armature="1.0" frictionloss="1.0"/>
+    <geom name="{pf}finger2_col" type="box" pos="0 -0.0115 0.027" size="0.0105 0.0075 0.027" {ROBOT_COL}/>
+    <geom name="{pf}finger2_pad" type="box" pos="0 -0.0025 0.044" size="0.008 0.0015 0.008" {pad}/>
+  </body>
+</body>'''
+
+
+def panda_gripper_actuators(pf: str) -> str:
+    return (f'<position name="{pf}gripper_finger_joint1" joint="{pf}finger_joint1" kp="1000" ctrlrange="0 0.04" forcerange="-20 20"/>'
+            f'<position name="{pf}gripper_finger_joint2" joint="{pf}finger_joint2" kp="1000" ctrlrange="-0.04 0" forcerange="-20 20"/>')
+
+
+def rethink_gripper(pf: str) -> str:
+    """Rethink two-finger gripper for Sawyer: slide fingers along ±y."""
+    pad = f'{ROBOT_COL} condim="4" friction="2 0.05 0.0001" solref="0.01 0.5"'
+    return f'''
+<body name="{pf}right_hand" pos="0 0 0.0245" quat="0.7071068 0 0 0.7071068">
+  <inertial pos="0 0 0.03" mass="0.3" diaginertia="0.001 0.001 0.001"/>
+  <geom name="{pf}hand_col" type="box" pos="0 0 0.03" size="0.03 0.06 0.03" {ROBOT_COL}/>
+  <site name="{pf}grip_site" pos="0 0 0.109"/>
+  <body name="{pf}leftfinger" pos="0 0.01 0.0444">
+    <inertial pos="0 0 0.03" mass="0.02" diaginertia="0.00001 0.00001 0.00001"/>
+    <joint name="{pf}finger_joint1" type="slide" axis="0 1 0" range="-0.0115 0.020833" damping="100" armature="1.0" frictionloss="1.0"/>
+    <geom name="{pf}finger1_col" type="box" pos="0 0.009 0.035" size="0.008 0.006 0.035" {ROBOT_COL}/>
+    <geom name="{pf}finger1_pad" type="box" pos="0 0.002 0.062" size="0.008 0.0015 0.008" {pad}/>
+  </body>
+  <body name="{pf}rightfinger" pos="0 -0.01 0.0444">
+    <inertial pos="0 0 0.03" mass="0.02" diaginertia="0.00001 0.00001 0.00001"/>
+    <joint name="{pf}finger_joint2" type="slide" axis="0 1 0" range="-0.020833 0.0115" damping="100" armature="1.0" frictionloss="1.0"/>
+    <geom name="{pf}finger2_col" type="box" pos="0 -0.009 0.035" size="0.008 0.006 0.035" {ROBOT_COL}/>
+    <geom name="{pf}finger2_pad" type="box" pos="0 -0.002 0.062" size="0.008 0.0015 0.008" {pad}/>
+  </body>
+</body>'''
+
+
+def rethink_gripper_actuators(pf: str) -> str:
+    return (f'<position name="{pf}gripper_finger_joint1" joint="{pf}finger_joint1" kp="1000" ctrlrange="-0.0115 0.020833" forcerange="-20 20"/>'
+            f'<position name="{pf}gripper_finger_joint2" joint="{pf}finger_joint2" kp="1000" ctrlrange="-0.020833 0.0115" forcerange="-20 20"/>')
+
+
+# ----------------------------------------------------------------------------- robots
+def panda(pf: str, base_pos, base_quat=(1, 0, 0, 0)) -> str:
+    """Franka Emika Panda, 7 hinge joints about local z (link frames: SURVEY.md A.5)."""
+    lim = [(-2.8973, 2.8973), (-1.7628, 1.7628), (-2.8973, 2.8973), (-3.0718, -0.0698),
+           (-2.8973, 2.8973), (-0.0175, 3.7525), (-2.8973, 2.8973)]
+    frames = [("0 0 0.333", "1 0 0 0"), ("0 0 0", "0.7071068 -0.7071068 0 0"),
+              ("0 -0.316 0", "0.7071068 0.7071068 0 0"), ("0.0825 0 0", "0.7071068 0.7071068 0 0"),
+              ("-0.0825 0.384 0", "0.7071068 -0.7071068 0 0"), ("0 0 0", "0.7071068 0.7071068 0 0"),
+              ("0.088 0 0", "0.7071068 0.7071068 0 0")]
+    inert = [("0 0 -0.07", 3, 0.3), ("0 -0.1 0", 3, 0.3), ("0.04 0 -0.05", 2, 0.2), ("-0.04 0.05 0", 2, 0.2),
+             ("0 0 -0.15", 2, 0.2), ("0.06 0 0", 1.5, 0.1), ("0 0 0.08", 0.5, 0.05)]
+    damp = [0.1, 0.1, 0.1, 0.1, 0.1, 0.01, 0.01]
+    s = f'<body name="{pf}base" pos="{_f(base_pos)}" quat="{_f(base_quat)}">'
+    s += f'<inertial pos="0 0 0.05" mass="4" diaginertia="0.4 0.4 0.4"/>'
+    for i in range(7):
+        s += (f'<body name="{pf}link{i + 1}" pos="{frames[i][0]}" quat="{frames[i][1]}">'
+              f'<inertial pos="{inert[i][0]}" mass="{inert[i][1]}" diaginertia="{inert[i][2]} {inert[i][2]} {inert[i][2]}"/>'
+              f'<joint name="{pf}joint{i + 1}" type="hinge" axis="0 0 1" range="{lim[i][0]} {lim[i][1]}" damping="{damp[i]}"/>')
+    s += panda_gripper(pf)
+    s += "</body>" * 8
+    return s
+
+
+def panda_actuators(pf: str) -> str:
+    tl = [80, 80, 80, 80, 12, 12, 12]
+    s = "".join(f'<motor name="{pf}torq_j{i + 1}" joint="{pf}joint{i + 1}" ctrlrange="{-tl[i]} {tl[i]}" ctrllimited="true"/>'
+                for i in range(7))
+    return s + panda_gripper_actuators(pf)
+
+
+PANDA_INIT_QPOS = [0, PI / 16.0, 0.00, -PI / 2.0 - PI / 3.0, 0.00, PI - 0.2, PI / 4]
+PANDA_GRIP_INIT = [0.020833, -0.020833]
+PANDA_GRIP_SIGN = [-1.0, 1.0]
+
+
+def sawyer(pf: str, base_pos, base_quat=(1, 0, 0, 0)) -> str:
+    """Rethink Sawyer, 7 hinge joints about local z (public URDF link frames)."""
+    lim = [(-3.0503, 3.0503), (-3.8095, 2.2736), (-3.0426, 3.0426), (-3.0439, 3.0439),
+           (-2.9761, 2.9761), (-2.9761, 2.9761), (-4.7124, 4.7124)]
+    frames = [("0 0 0.08", "1 0 0 0"), ("0.081 0.05 0.237", "0.5 -0.5 0.5 0.5"),
+              ("0 -0.14 0.1425", "0.7071068 0.7071068 0 0"), ("0 -0.042 0.26", "0.7071068 -0.7071068 0 0"),
+              ("0 -0.125 -0.1265", "0.7071068 0.7071068 0 0"), ("0 0.031 0.275", "0.7071068 -0.7071068 0 0"),
+              ("0 -0.11 0.1053", "0.0616248 0.06163 -0.704416 0.704416")]
+    inert = [("0.024 0.014 0.136", 5.32, 0.05), ("-0.003 -0.002 0.035", 4.51, 0.03), ("-0.002 -0.03 0.087", 1.75, 0.02),
+             ("-0.002 0.0013 0.0018", 2.51, 0.01), ("0.0026 -0.02 0.09", 1.12, 0.01), ("-0.00005 0.003 0.02", 1.56, 0.004),
+             ("0.008 0.005 -0.003", 0.33, 0.0003)]
+    s = f'<body name="{pf}base" pos="{_f(base_pos)}" quat="{_f(base_quat)}">'
+    s += f'<inertial pos="0 0 0.04" mass="2" diaginertia="0.02 0.02 0.02"/>'
+    for i in range(7):
+        s += (f'<body name="{pf}link{i + 1}" pos="{frames[i][0]}" quat="{frames[i][1]}">'
+              f'<inertial pos="{inert[i][0]}" mass="{inert[i][1]}" diaginertia="{inert[i][2]} {inert[i][2]} {inert[i][2]}"/>'
+              f'<joint name="{pf}joint{i + 1}" type="hinge" axis="0 0 1" range="{lim[i][0]} {lim[i][1]}" damping="0.1"/>')
+    s += rethink_gripper(pf)
+    s += "</body>" * 8
+    return s
+
+
+def sawyer_actuators(pf: str) -> str:
+    tl = [80, 80, 40, 40, 9, 9, 9]
+    s = "".join(f'<motor name="{pf}torq_j{i + 1}" joint="{pf}joint{i + 1}" ctrlrange="{-tl[i]} {tl[i]}" ctrllimited="true"/>'
+                for i in range(7))
+    return s + rethink_gripper_actuators(pf)
+
+
+SAWYER_INIT_QPOS = [0, -1.18, 0.00, 2.18, 0.00, 0.57, 3.3161]
+SAWYER_GRIP_INIT = [0.020833, -0.020833]
+SAWYER_GRIP_SIGN = [1.0, -1.0]
+
+ROBOTS = {
+    "Panda": dict(body=panda, act=panda_actuators, init_qpos=PANDA_INIT_QPOS, grip_init=PANDA_GRIP_INIT,
+                  grip_sign=PANDA_GRIP_SIGN),
+    "Sawyer": dict(body=sawyer, act=sawyer_actuators, init_qpos=SAWYER_INIT_QPOS, grip_init=SAWYER_GRIP_INIT,
+                   grip_sign=SAWYER_GRIP_SIGN),
+}
+
+
+# ----------------------------------------------------------------------------- arena / objects
+TABLE_HEIGHT = 0.8
+TABLE_FULL = (0.8, 0.8, 0.05)
+ROBOT_BASE_Z = 0.912
+
+
+def table_arena(full=TABLE_FULL, friction=(1, 0.005, 0.0001)) -> str:
+    hx, hy, hz = full[0] / 2, full[1] / 2, full[2] / 2
+    return (f'<geom name="floor" type="plane" pos="0 0 0" size="3 3 0.125" {WORLD_COL}/>'
+            f'<body name="table" pos="0 0 {TABLE_HEIGHT - hz}">'
+            f'<geom name="table_collision" type="box" size="{hx} {hy} {hz}" friction="{_f(friction)}" {WORLD_COL}/>'
+            f'</body>')
+
+
+def box_object(name, half, pos, density=1000, friction=(1, 0.005, 0.0001), solref=(0.02, 1.0),
+               solimp=(0.9, 0.95, 0.001)) -> str:
+    return (f'<body name="{name}" pos="{_f(pos)}"><freejoint name="{name}_joint"/>'
+            f'<geom name="{name}_g0" type="box" size="{_f(half)}" density="{density}" friction="{_f(friction)}" '
+            f'solref="{_f(solref)}" solimp="{_f(solimp)}" {WORLD_COL}/></body>')
+
+
+def scene(world: str, actuators: str, extra: str = "") -> str:
+    return f'<mujoco model="rsb">{BASE_OPTION}<worldbody>{world}</worldbody><actuator>{actuators}</actuator>{extra}</mujoco>'

@@ -1,0 +1,148 @@
+"""Task scenes: MJCF composition + the task descriptor (include/rsb_model.h `rsb_task`).
+
+Mirrors what robosuite's env constructors do at `suite.make` time (reference call site
+util/rlkit_utils.py:49-56; behaviour per SURVEY.md A.1, A.5, A.6): arena + robot(s) + gripper(s)
++ task objects are merged into one MJCF, compiled, and the ids the env logic needs (arm dofs,
+actuators, eef site, finger geoms, object bodies) are resolved by name.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import numpy as np
+
+from . import assets as A
+from .mjcf import Model, compile_mjcf
+
+TASK_IDS = {"Lift": 0, "Door": 1, "Stack": 2, "TwoArmLift": 3}
+CTRL_IDS = {"OSC_POSE": 0, "OSC_POSITION": 1, "JOINT_VELOCITY": 2, "JOINT_TORQUE": 3}
+
+OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89}
+
+
+def _robot_desc(m: Model, pf: str, robot: str, cc: dict) -> dict:
+    R = A.ROBOTS[robot]
+    jn = [m.id("joint", f"{pf}joint{i + 1}") for i in range(7)]
+    fj = [m.id("joint", f"{pf}finger_joint{i + 1}") for i in range(2)]
+    act = [m.id("actuator", f"{pf}torq_j{i + 1}") for i in range(7)]
+    gact = [m.id("actuator", f"{pf}gripper_finger_joint{i + 1}") for i in range(2)]
+    ctype = cc["type"]
+    ndim = {"OSC_POSE": 6, "OSC_POSITION": 3, "JOINT_VELOCITY": 7, "JOINT_TORQUE": 7}[ctype]
+
+    def vec(x, n, fill=0.0):
+        v = np.full(7, fill, float)
+        x = np.atleast_1d(np.asarray(x, float))
+        v[:n] = x if x.size == n else np.full(n, x[0])
+        return v
+
+    tl_lo = np.array([float(m.act_ctrlrange[a, 0]) for a in act])
+    tl_hi = np.array([float(m.act_ctrlrange[a, 1]) for a in act])
+    ki = np.zeros(7)
+    if ctype.startswith("OSC"):
+        kp = vec(cc.get("kp", 150.0), 6)
+        damping = vec(cc.get("damping_ratio", cc.get("damping", 1.0)), 6)
+        kd = 2.0 * np.sqrt(kp) * damping
+    elif ctype == "JOINT_VELOCITY":
+        kp_in = cc.get("kp", 3.0)
+        kp = vec(kp_in, 7)
+        if np.isscalar(kp_in) and cc.get("kp_scale_by_actuator_range", True):
+            kp = float(kp_in) * (tl_hi - tl_lo)        # robosuite: kp * (high - low) of the actuator range
+        ki = kp * float(cc.get("ki_ratio", 0.005))
+        kd = kp * float(cc.get("kd_ratio", 0.001))
+    else:
+        kp, kd = np.zeros(7), np.zeros(7)
+    vl = cc.get("velocity_limits")
+    d = dict(
+        arm_qposadr=[int(m.jnt_qposadr[j]) for j in jn], arm_dofadr=[int(m.jnt_dofadr[j]) for j in jn],
+        arm_act=act, grip_ndof=2, grip_qposadr=[int(m.jnt_qposadr[j]) for j in fj],
+        grip_dofadr=[int(m.jnt_dofadr[j]) for j in fj], grip_act=gact, grip_action_dim=1,
+        grip_sign=list(R["grip_sign"]), grip_speed=0.01, grip_init_qpos=list(R["grip_init"]),
+        eef_site=m.id("site", f"{pf}grip_site"), eef_body=m.id("body", f"{pf}right_hand"),
+        init_qpos=list(R["init_qpos"]),
+        left_finger_geoms=[m.id("geom", f"{pf}finger1_col"), m.id("geom", f"{pf}finger1_pad")],
+        right_finger_geoms=[m.id("geom", f"{pf}finger2_col"), m.id("geom", f"{pf}finger2_pad")],
+        ctrl_type=CTRL_IDS[ctype], control_dim=ndim,
+        input_max=vec(cc.get("input_max", 1.0), ndim), input_min=vec(cc.get("input_min", -1.0), ndim),
+        output_max=vec(cc.get("output_max", 1.0), ndim), output_min=vec(cc.get("output_min", -1.0), ndim),
+        kp=kp, kd=kd, ki=ki, nullspace_kp=10.0, uncouple_pos_ori=int(bool(cc.get("uncouple_pos_ori", True))),
+        torque_limit_lo=tl_lo, torque_limit_hi=tl_hi,
+        velocity_limit_lo=vec(vl[0], 7) if vl is not None else np.zeros(7),
+        velocity_limit_hi=vec(vl[1], 7) if vl is not None else np.zeros(7),
+        has_velocity_limits=int(vl is not None),
+    )
+    return d
+
+
+def build_task(env_name: str, robots: Sequence[str], controller_config: dict, horizon: int = 500,
+               control_freq: float = 20, reward_scale: float = 1.0, reward_shaping: bool = True,
+               ignore_done: bool = False, env_configuration: str = "single-arm-opposed"):
+    """-> (Model, task dict).  `controller_config` is the dict from load_controller_config."""
+    if isinstance(robots, str):
+        robots = [robots]
+    if env_name not in TASK_IDS:
+        raise NotImplementedError(f"environment {env_name!r} is not on the batched hot path "
+                                  f"(supported: {sorted(TASK_IDS)})")
+    for r in robots:
+        if r not in A.ROBOTS:
+            raise NotImplementedError(f"robot {r!r} not supported (have {sorted(A.ROBOTS)})")
+    builder = {"Lift": _lift}[env_name] if env_name == "Lift" else _BUILDERS[env_name]
+    xml, objs = builder(robots, env_configuration)
+    m = compile_mjcf(xml)
+    substeps = int((1.0 / control_freq) / m.timestep)
+    n_rob = len(robots)
+    rdesc = [_robot_desc(m, f"robot{i}_", r, controller_config) for i, r in enumerate(robots)]
+    act_dim = sum(r["control_dim"] + r["grip_action_dim"] for r in rdesc)
+    task = dict(task_id=TASK_IDS[env_name], nrobot=n_rob, robot=rdesc, horizon=int(horizon), substeps=substeps,
+                ignore_done=int(bool(ignore_done)), reward_shaping=int(bool(reward_shaping)),
+                reward_scale=float(reward_scale), init_noise=0.02, table_height=A.TABLE_HEIGHT,
+                obs_dim=OBS_DIMS[env_name] if n_rob == (2 if env_name == "TwoArmLift" else 1) else None,
+                act_dim=act_dim, env_name=env_name, robots=list(robots), xml=xml)
+    task.update(objs(m))
+    return m, task
+
+
+def empty_task():
+    """Task descriptor with no robots/objects: lets the physics stages run on an arbitrary compiled model."""
+    t = dict(task_id=-1, nrobot=0, robot=[], horizon=1 << 30, substeps=1, ignore_done=1, reward_shaping=0,
+             reward_scale=1.0, init_noise=0.0, table_height=0.0, obs_dim=0, act_dim=0)
+    t.update(_empty_objs())
+    return t
+
+
+def _empty_objs():
+    return dict(obj_body=[-1] * 4, obj_geom=[-1] * 4, obj_site=[-1] * 4, obj_qposadr=[-1] * 4, obj_dofadr=[-1] * 4,
+                obj_half=np.zeros((4, 3)), place_x=np.zeros((4, 2)), place_y=np.zeros((4, 2)),
+                place_yaw=np.zeros((4, 2)), place_z=np.zeros(4), place_ref=np.zeros(3))
+
+
+def _single_arm_world(robot: str):
+    R = A.ROBOTS[robot]
+    base = (-0.16 - A.TABLE_FULL[0] / 2, 0.0, A.ROBOT_BASE_Z)
+    return R["body"]("robot0_", base), R["act"]("robot0_")
+
+
+def _lift(robots, env_configuration):
+    """Lift: one cube on the table."""
+    assert len(robots) == 1, "Lift takes one robot"
+    body, act = _single_arm_world(robots[0])
+    half = 0.021
+    world = A.table_arena() + body + A.box_object("cube", [half] * 3, [0, 0, A.TABLE_HEIGHT + half])
+    xml = A.scene(world, act)
+
+    def objs(m: Model):
+        o = _empty_objs()
+        j = m.id("joint", "cube_joint")
+        o["obj_body"][0] = m.id("body", "cube")
+        o["obj_geom"][0] = m.id("geom", "cube_g0")
+        o["obj_qposadr"][0], o["obj_dofadr"][0] = int(m.jnt_qposadr[j]), int(m.jnt_dofadr[j])
+        o["obj_half"][0] = half
+        o["place_x"][0], o["place_y"][0] = [-0.03, 0.03], [-0.03, 0.03]
+        o["place_yaw"][0] = [0.0, 2 * np.pi]
+        o["place_z"][0] = A.TABLE_HEIGHT + half + 0.01  # robosuite drops objects from 1 cm
+        o["place_ref"] = np.array([0.0, 0.0, A.TABLE_HEIGHT])
+        return o
+
+    return xml, objs
+
+
+_BUILDERS: Dict[str, callable] = {"Lift": _lift}
