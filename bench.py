@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- env control-steps/s of the batched env.step hot path (BASELINE.json metric), one process per GPU.
+
+Workload at N GPUs (weak scaling): BASELINE.json configs[1] on every GPU -- Lift-Panda-OSC_POSE, 4096 batched envs,
+synthetic tanh(N(0,1)) actions from the Philox stream shared with the oracle, horizon 500 with a batch reset at the
+horizon.  One bench "step" = one 20 Hz control step (25 physics substeps + controller + reward + observation) of every
+env of the batch.  `value` is measured with states/actions resident in HBM (CUDA events around each step, L2 flushed
+between steps); `e2e` goes through the host-buffer C-ABI call (pinned host actions in, obs/reward/done out) each step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl ours|reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENV_NAME, ROBOT, CONTROLLER, SEED, HORIZON = "Lift", "Panda", "OSC_POSE", 17, 500
+METRIC, UNIT = "Lift-Panda-OSC env control-steps/s", "control-steps/s"
+
+
+def algorithmic_bytes_per_step(task, model) -> int:
+    """bytes = 4*(2*S + 2*A + O + 2) with S = nq + 2*nv + C + 1 (OSC: C = 21 per arm)."""
+    C = sum(21 if r["ctrl_type"] in (0, 1) else 9 for r in task["robot"])
+    S = model.nq + 2 * model.nv + C + 1
+    return 4 * (2 * S + 2 * task["act_dim"] + task["obs_dim"] + 2)
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port, test infra)
+def _cpu_worker(args):
+    wid, steps, seed = args
+    import numpy as np  # noqa: F401
+    from oracle.oracle import OracleEnv
+    from robosuite_benchmark_b200.controllers import load_controller_config
+    from robosuite_benchmark_b200.model.tasks import build_task
+    m, t = build_task(ENV_NAME, ROBOT, load_controller_config(default_controller=CONTROLLER), horizon=HORIZON,
+                      control_freq=20, reward_shaping=True, ignore_done=True)
+    env = OracleEnv(m, t, ncon_max=16, nefc_max=64)
+    env.reset(seed=seed, env_id=wid, episode=0)
+    for k in range(5):
+        env.step(env.random_action(seed, wid, k))
+    t0 = time.perf_counter()
+    for k in range(5, 5 + steps):
+        env.step(env.random_action(seed, wid, k))
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(steps_per_worker=300):
+    """The fp64 C oracle (a PORT of the reference's CPU path; the real robosuite+mujoco cannot be installed here) as one
+    process per host core, same workload; steps/s summed over workers."""
+    import multiprocessing as mp
+    from oracle import oracle as _o
+    _o.build()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = max(1, min(cores, 64))
+    with mp.get_context("fork").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        times = pool.map(_cpu_worker, [(w, steps_per_worker, SEED) for w in range(cores)])
+        wall = time.perf_counter() - t0
+    value = sum(steps_per_worker / t for t in times)
+    return dict(value=value, unit=UNIT, cores=cores, kind="port",
+                sample=f"{cores} processes x {steps_per_worker} control steps of {ENV_NAME}-{ROBOT}-{CONTROLLER} (single env each, fp64 C oracle), wall {wall:.1f}s")
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.samples, self.reasons, self.proc, self.th = [], set(), None, None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.th = threading.Thread(target=self._read, daemon=True)
+        self.th.start()
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            p = [x.strip() for x in line.split(",")]
+            try:
+                self.samples.append((float(p[0]), float(p[1])))
+                for nm, v in zip(names, p[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        sm = sorted(s[0] for s in self.samples)
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(s[1] for s in self.samples), reasons=sorted(self.reasons))
+
+
+# ----------------------------------------------------------------------------- arms
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: every --steps "step" is `per` control steps on each host core
+    per = 40
+    t_warm = max(1, args.warmup)
+    import multiprocessing as mp
+    from oracle import oracle as _o
+    _o.build()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    total = per * (t_warm + args.steps)
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_worker, [(w, per * t_warm, SEED) for w in range(cores)])          # warm-up
+        t0 = time.perf_counter()
+        times = pool.map(_cpu_worker, [(w, per * args.steps, SEED) for w in range(cores)])
+        wall = time.perf_counter() - t0
+    value = sum(per * args.steps / t for t in times)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{ENV_NAME}-{ROBOT}-{CONTROLLER}, one env per host core, tanh-Gaussian random actions, horizon {HORIZON}",
+                       "note": "robosuite+mujoco are not installable here (no network, no wheels): this arm times the fp64 C oracle port of the reference CPU path"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{cores} processes x {per * args.steps} control steps ({total} incl. warm-up)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import robosuite_benchmark_b200 as suite
+    from robosuite_benchmark_b200 import backend
+
+    E = args.envs
+    cfg = suite.load_controller_config(default_controller=CONTROLLER)
+    env = suite.make(ENV_NAME, ROBOT, controller_configs=cfg, num_envs=E, batched=True, device=dev, seed=SEED, env_id_base=rank * E,
+                     horizon=HORIZON, control_freq=20, reward_shaping=True, ignore_done=True)
+    sim = env.sim
+    obs = torch.zeros(E, sim.obs_dim, device=dev)
+    rew = torch.zeros(E, device=dev)
+    done = torch.zeros(E, dtype=torch.uint8, device=dev)
+    act = torch.zeros(E, sim.act_dim, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    sim.reset(obs=obs)
+    step_idx = 0
+
+    def one_step():
+        nonlocal step_idx
+        sim.random_actions(step_idx, out=act)
+        sim.step(act, obs, rew, done)
+        step_idx += 1
+        if step_idx % HORIZON == 0:
+            sim.reset(obs=obs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = sim.info("launches")
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    rsum = 0.0
+    for k in range(args.steps):
+        flush.zero_()                                   # L2 flush between timed iterations (outside the event pair)
+        ev[k][0].record()
+        sim.random_actions(step_idx, out=act)
+        kev[k][0].record()
+        sim.step(act, obs, rew, done)
+        kev[k][1].record()
+        step_idx += 1
+        if step_idx % HORIZON == 0:
+            sim.reset(obs=obs)
+        ev[k][1].record()
+    barrier()
+    launches = sim.info("launches") - l0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    kms = sum(a.elapsed_time(b) for a, b in kev)
+    rsum = float(rew.mean().item())
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * E * args.steps / (ms_total / 1000.0)
+
+    # ---- end-to-end through the host-buffer C-ABI call (pinned host actions in; obs/reward/done out), every step
+    h_act = torch.empty(E, sim.act_dim, pin_memory=True)
+    h_act.copy_(act)
+    e2e_steps = max(5, min(args.steps, 50))
+    for _ in range(3):
+        sim.step_host(h_act.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        o_h, r_h, d_h = sim.step_host(h_act.numpy())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * e2e_steps / float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        bps = algorithmic_bytes_per_step(env.task, env.model)
+        kernel_ms = kms / args.steps
+        achieved = bps * E / (kernel_ms / 1000.0) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_baseline()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{ENV_NAME}-{ROBOT}-{CONTROLLER}, {E} batched envs per GPU, tanh-Gaussian random actions (Philox), "
+                                       f"horizon {HORIZON}, 25 substeps/control step, physics + controller + reward + obs",
+                           "envs_per_gpu": E, "l2": "flushed between timed steps (256 MiB write)",
+                           "mean_reward_last_step": rsum},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * sim.act_dim * 4,
+                        "d2h_bytes_per_step": E * (sim.obs_dim * 4 + 4 + 1)},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "k_step", "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": bps,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                             "note": "state stays in shared memory for the 25 substeps: the kernel is issue/latency-bound, not HBM-bound (DESIGN.md)"},
+                "kernel_info": {"regs": sim.info("regs_step"), "smem_bytes_per_env": sim.info("smem_bytes"),
+                                "envs_per_block": sim.info("envs_per_block"), "blocks_per_sm": sim.info("blocks_per_sm")},
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -45,7 +45,7 @@ def _p(a):
 class OracleEnv:
     """One scalar environment stepping in float64."""
 
-    def __init__(self, model, task, ncon_max: int = 0):
+    def __init__(self, model, task, ncon_max: int = 0, nefc_max: int = 0):
         from robosuite_benchmark_b200.model.cstruct import model_to_c, task_to_c
         self.L = lib()
         self.model, self.task = model, task
@@ -56,6 +56,8 @@ class OracleEnv:
         self.h = self.L.orc_create(C.byref(self._cm), C.byref(self._ct), ncon_max)
         if not self.h:
             raise RuntimeError("orc_create failed (model exceeds oracle limits)")
+        if nefc_max:
+            self.L.orc_set_nefc_max(C.c_void_p(self.h), int(nefc_max))
         self.nq, self.nv, self.nu = model.nq, model.nv, model.nu
         self.obs_dim, self.act_dim, self.nrobot = task["obs_dim"], task["act_dim"], task["nrobot"]
 

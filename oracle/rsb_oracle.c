@@ -59,7 +59,7 @@ typedef struct {
 typedef struct orc_env {
   rsb_model m;
   rsb_task t;
-  int ncon_max;
+  int ncon_max, nefc_max;
   /* state */
   real qpos[MAXQ], qvel[MAXV], qacc_warmstart[MAXV], ctrl[MAXU];
   orc_ctrl rc[RSB_MAX_ROBOTS];
@@ -142,6 +142,7 @@ orc_env *orc_create(const rsb_model *src, const rsb_task *task, int ncon_max) {
   orc_env *e = (orc_env *)calloc(1, sizeof(orc_env));
   e->m = *src; e->t = *task;
   e->ncon_max = ncon_max > 0 && ncon_max < MAXCON ? ncon_max : MAXCON;
+  e->nefc_max = MAXEFC;
   int nb = src->nbody, nj = src->njnt, nv = src->nv, ng = src->ngeom, ns = src->nsite, np = src->npair, nu = src->nu;
   DUPI(body_parentid, nb); DUPI(body_rootid, nb); DUPI(body_jntadr, nb); DUPI(body_jntnum, nb); DUPI(body_dofadr, nb); DUPI(body_dofnum, nb);
   DUPD(body_pos, 3 * nb); DUPD(body_quat, 4 * nb); DUPD(body_ipos, 3 * nb); DUPD(body_iquat, 4 * nb); DUPD(body_mass, nb); DUPD(body_inertia, 3 * nb);
@@ -162,6 +163,8 @@ orc_env *orc_create(const rsb_model *src, const rsb_task *task, int ncon_max) {
   for (int i = 0; i < src->nq; i++) e->qpos[i] = src->qpos0[i];
   return e;
 }
+/* same row cap as the CUDA library's nefc_max (contacts that do not fit are skipped, scalar rows are clipped) */
+void orc_set_nefc_max(orc_env *e, int n) { e->nefc_max = n > 0 && n < MAXEFC ? n : MAXEFC; }
 void orc_destroy(orc_env *e) { if (e) { free(e->efc_J); free(e); } /* model arrays leak by design: test helper */ }
 
 /* ------------------------------------------------------------------ A.3.1 kinematics */
@@ -586,7 +589,7 @@ static void make_constraint(orc_env *e) {
   /* contacts (elliptic cones: dim rows each; pyramidal handled as frictionless+note) */
   static real jp1[3 * MAXV], jr1[3 * MAXV], jp2[3 * MAXV], jr2[3 * MAXV];
   for (int c = 0; c < e->ncon; c++) {
-    orc_contact *k = &e->con[c]; if (e->nefc + k->dim > MAXEFC) { k->efc_address = -1; continue; }
+    orc_contact *k = &e->con[c]; if (e->nefc + k->dim > e->nefc_max) { k->efc_address = -1; continue; }
     int b1 = m->geom_bodyid[k->geom1], b2 = m->geom_bodyid[k->geom2];
     jac_point(e, b1, k->pos, jp1, jr1); jac_point(e, b2, k->pos, jp2, jr2);
     k->efc_address = e->nefc;

@@ -1,0 +1,1342 @@
+/*
+ * rsb_dev.h -- the batched env.step hot path as lane-cooperative device code (fp32).
+ *
+ * One "group" of RSB_LANES lanes (a warp by default) owns one environment; all per-env data of the 25 physics
+ * substeps of a control step live in that group's slice of shared memory (layout: DevModel::o_*).  The stages follow
+ * MuJoCo's mj_step / robosuite's controllers as restated in SURVEY.md Appendix A (cited per function); the CPU
+ * oracle (oracle/rsb_oracle.c) restates the same path in fp64 with different formulations.
+ *
+ * Differences in formulation from the oracle (deliberate, so parity is a real check):
+ *   - spatial algebra about a per-tree reference point (the root body's frame origin), not the world origin;
+ *   - Featherstone-style chain walks (parallel over bodies/dofs) instead of serial recursions;
+ *   - Cholesky solves instead of explicit inverses / eigen pseudo-inverses in the OSC law;
+ *   - Newton solver state in shared memory, reductions by lane shuffles.
+ *
+ * The same source compiles for the host (RSB_EMU) where lanes are fibers; that build is TEST infrastructure only.
+ */
+#ifndef RSB_DEV_H
+#define RSB_DEV_H
+
+#include "rsb_devmodel.h"
+
+#ifndef RSB_LANES
+#define RSB_LANES 32
+#endif
+
+typedef float real;
+
+#ifdef RSB_EMU
+/* ---- host emulation of a lane group (tests/emu): provided by the harness */
+#include <math.h>
+#include <stdint.h>
+struct Grp { int lane; unsigned mask; };
+void emu_sync();
+float emu_shfl_f(float v, int src);
+int emu_shfl_i(int v, int src);
+#define RSB_D static inline
+#define RSB_DN static
+#define RSB_DNOINL static
+RSB_D void gsync(Grp) { emu_sync(); }
+RSB_D real gshfl(Grp, real v, int src) { return emu_shfl_f(v, src); }
+RSB_D int gshfl_i(Grp, int v, int src) { return emu_shfl_i(v, src); }
+RSB_D real gshfl_xor(Grp g, real v, int x) { return emu_shfl_f(v, g.lane ^ x); }
+RSB_D int gshfl_xor_i(Grp g, int v, int x) { return emu_shfl_i(v, g.lane ^ x); }
+RSB_D real gshfl_up(Grp g, real v, int d) { return emu_shfl_f(v, g.lane >= d ? g.lane - d : g.lane); }
+RSB_D int gshfl_up_i(Grp g, int v, int d) { return emu_shfl_i(v, g.lane >= d ? g.lane - d : g.lane); }
+RSB_D void rsb_sincos(real x, real *s, real *c) { *s = sinf(x); *c = cosf(x); }
+RSB_D real rsb_rsqrt(real x) { return 1.0f / sqrtf(x); }
+RSB_D int f2i(real f) { int i; memcpy(&i, &f, 4); return i; }
+RSB_D real i2f(int i) { real f; memcpy(&f, &i, 4); return f; }
+RSB_D uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+#else
+#include <stdint.h>
+struct Grp { int lane; unsigned mask; };
+#define RSB_D __device__ __forceinline__
+#define RSB_DN __device__ __forceinline__
+#define RSB_DNOINL __device__ __noinline__
+RSB_D void gsync(Grp g) { __syncwarp(g.mask); }
+RSB_D real gshfl(Grp g, real v, int src) { return __shfl_sync(g.mask, v, src, RSB_LANES); }
+RSB_D int gshfl_i(Grp g, int v, int src) { return __shfl_sync(g.mask, v, src, RSB_LANES); }
+RSB_D real gshfl_xor(Grp g, real v, int x) { return __shfl_xor_sync(g.mask, v, x, RSB_LANES); }
+RSB_D int gshfl_xor_i(Grp g, int v, int x) { return __shfl_xor_sync(g.mask, v, x, RSB_LANES); }
+RSB_D real gshfl_up(Grp g, real v, int d) { return __shfl_up_sync(g.mask, v, d, RSB_LANES); }
+RSB_D int gshfl_up_i(Grp g, int v, int d) { return __shfl_up_sync(g.mask, v, d, RSB_LANES); }
+RSB_D void rsb_sincos(real x, real *s, real *c) { sincosf(x, s, c); }
+RSB_D real rsb_rsqrt(real x) { return rsqrtf(x); }
+RSB_D int f2i(real f) { return __float_as_int(f); }
+RSB_D real i2f(int i) { return __int_as_float(i); }
+RSB_D uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+#endif
+
+#define RSB_MINVAL 1e-15f
+#define RSB_PI 3.14159265358979323846f
+
+/* ------------------------------------------------------------------ group reductions */
+RSB_D real gsum(Grp g, real v) {
+#pragma unroll
+  for (int o = RSB_LANES / 2; o > 0; o >>= 1) v += gshfl_xor(g, v, o);
+  return v;
+}
+RSB_D real gmaxf(Grp g, real v) {
+#pragma unroll
+  for (int o = RSB_LANES / 2; o > 0; o >>= 1) v = fmaxf(v, gshfl_xor(g, v, o));
+  return v;
+}
+RSB_D int gsum_i(Grp g, int v) {
+#pragma unroll
+  for (int o = RSB_LANES / 2; o > 0; o >>= 1) v += gshfl_xor_i(g, v, o);
+  return v;
+}
+/* inclusive prefix sum over lanes */
+RSB_D int gscan_incl(Grp g, int v) {
+#pragma unroll
+  for (int o = 1; o < RSB_LANES; o <<= 1) { int t = gshfl_up_i(g, v, o); if (g.lane >= o) v += t; }
+  return v;
+}
+
+/* ------------------------------------------------------------------ small vector helpers */
+RSB_D real dot3(const real *a, const real *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+RSB_D void cross3(real *o, const real *a, const real *b) {
+  real x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+RSB_D real dot6(const real *a, const real *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5]; }
+RSB_D void matvec3(real *o, const real *R, const real *v) {
+  real x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2], y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2], z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+RSB_D void matTvec3(real *o, const real *R, const real *v) {
+  real x = R[0] * v[0] + R[3] * v[1] + R[6] * v[2], y = R[1] * v[0] + R[4] * v[1] + R[7] * v[2], z = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+RSB_D void matmul3(real *o, const real *A, const real *B) {
+  real t[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) t[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+#pragma unroll
+  for (int k = 0; k < 9; k++) o[k] = t[k];
+}
+RSB_D void quatmul(real *o, const real *a, const real *b) {
+  real w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  real x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  real y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  real z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  o[0] = w; o[1] = x; o[2] = y; o[3] = z;
+}
+RSB_D void quatnorm(real *q) {
+  real n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  if (n2 < 1e-30f) { q[0] = 1; q[1] = q[2] = q[3] = 0; } else { real r = 1.0f / sqrtf(n2); q[0] *= r; q[1] *= r; q[2] *= r; q[3] *= r; }
+}
+RSB_D void quat2mat(real *R, const real *q) {
+  real w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = 1 - 2 * (x * x + y * y);
+}
+/* v' = q v q*  without forming the matrix */
+RSB_D void quatrot(real *o, const real *q, const real *v) {
+  real t[3], u[3]; cross3(t, q + 1, v); t[0] *= 2; t[1] *= 2; t[2] *= 2; cross3(u, q + 1, t);
+  o[0] = v[0] + q[0] * t[0] + u[0]; o[1] = v[1] + q[0] * t[1] + u[1]; o[2] = v[2] + q[0] * t[2] + u[2];
+}
+RSB_D real clampf(real x, real lo, real hi) { return fminf(fmaxf(x, lo), hi); }
+
+/* ------------------------------------------------------------------ Philox4x32-10 (same counters/keys as the oracle) */
+RSB_D void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t h0 = mulhi32(0xD2511F53u, c[0]), l0 = 0xD2511F53u * c[0], h1 = mulhi32(0xCD9E8D57u, c[2]), l1 = 0xCD9E8D57u * c[2];
+    uint32_t n0 = h1 ^ c[1] ^ k0, n1 = l1, n2 = h0 ^ c[3] ^ k1, n3 = l0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+RSB_D void rsb_philox(uint64_t seed, uint64_t env_id, uint32_t stream, uint32_t index, uint32_t out[4]) {
+  out[0] = (uint32_t)env_id; out[1] = (uint32_t)(env_id >> 32); out[2] = stream; out[3] = index;
+  philox4x32(out, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+/* fp32 Box-Muller on the oracle's uniforms needs the full 32 bits for u1 near 0; use double for the two transcendental
+   arguments only (8 values per reset, 8 per synthetic action -- negligible) */
+RSB_D void box_muller(uint32_t a, uint32_t b, real *z0, real *z1) {
+  double u1 = ((double)a + 0.5) * (1.0 / 4294967296.0), u2 = ((double)b + 0.5) * (1.0 / 4294967296.0);
+  double rad = sqrt(-2.0 * log(u1)), ang = 2.0 * 3.14159265358979323846 * u2;
+  *z0 = (real)(rad * cos(ang)); *z1 = (real)(rad * sin(ang));
+}
+
+/* ================================================================== A.3.1 kinematics */
+RSB_DN void st_kinematics(const DevModel &m, real *s, Grp g) {
+  real *qpos = s + m.o_qpos, *jq = s + m.o_jq;
+  real *xpos = s + m.o_xpos, *xquat = s + m.o_xquat, *xmat = s + m.o_xmat, *xanchor = s + m.o_xanchor, *xaxis = s + m.o_xaxis;
+  /* per-joint local motion, lane-parallel (the transcendental part) */
+  for (int j = g.lane; j < m.njnt; j += RSB_LANES) {
+    int t = m.jnt_type[j], a = m.jnt_qadr[j];
+    if (t == RSB_JNT_HINGE) {
+      real sn, cs; rsb_sincos(0.5f * (qpos[a] - m.qpos0[a]), &sn, &cs);
+      jq[4 * j] = cs; jq[4 * j + 1] = sn * m.jnt_axis[3 * j]; jq[4 * j + 2] = sn * m.jnt_axis[3 * j + 1]; jq[4 * j + 3] = sn * m.jnt_axis[3 * j + 2];
+    } else if (t == RSB_JNT_SLIDE) jq[4 * j] = qpos[a] - m.qpos0[a];
+    else quatnorm(qpos + a + 3);                   /* mj_kinematics normalises free-joint quaternions in place */
+  }
+  gsync(g);
+  /* tree composition: serial in tree order (one lane; the chain is inherently sequential) */
+  if (g.lane == 0) {
+    xpos[0] = xpos[1] = xpos[2] = 0; xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
+    for (int k = 0; k < 9; k++) xmat[k] = (k % 4 == 0) ? 1.0f : 0.0f;
+    for (int b = 1; b < m.nbody; b++) {
+      int p = m.body_parent[b], jn = m.body_jntnum[b], ja = m.body_jntadr[b];
+      real pos[3], quat[4];
+      if (jn == 1 && m.jnt_type[ja] == RSB_JNT_FREE) {
+        int a = m.jnt_qadr[ja];
+        pos[0] = qpos[a]; pos[1] = qpos[a + 1]; pos[2] = qpos[a + 2]; quat[0] = qpos[a + 3]; quat[1] = qpos[a + 4]; quat[2] = qpos[a + 5]; quat[3] = qpos[a + 6];
+        xanchor[3 * ja] = pos[0]; xanchor[3 * ja + 1] = pos[1]; xanchor[3 * ja + 2] = pos[2]; xaxis[3 * ja] = 0; xaxis[3 * ja + 1] = 0; xaxis[3 * ja + 2] = 1;
+      } else {
+        real t3[3]; matvec3(t3, xmat + 9 * p, m.body_pos + 3 * b);
+        pos[0] = xpos[3 * p] + t3[0]; pos[1] = xpos[3 * p + 1] + t3[1]; pos[2] = xpos[3 * p + 2] + t3[2];
+        quatmul(quat, xquat + 4 * p, m.body_quat + 4 * b);
+        for (int k = 0; k < jn; k++) {
+          int j = ja + k; real anchor[3], axis[3];
+          quatrot(t3, quat, m.jnt_pos + 3 * j); anchor[0] = pos[0] + t3[0]; anchor[1] = pos[1] + t3[1]; anchor[2] = pos[2] + t3[2];
+          quatrot(axis, quat, m.jnt_axis + 3 * j);
+          if (m.jnt_type[j] == RSB_JNT_SLIDE) { real dq = jq[4 * j]; pos[0] += axis[0] * dq; pos[1] += axis[1] * dq; pos[2] += axis[2] * dq; }
+          else {
+            real qn[4]; quatmul(qn, quat, jq + 4 * j); quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
+            quatrot(t3, quat, m.jnt_pos + 3 * j); pos[0] = anchor[0] - t3[0]; pos[1] = anchor[1] - t3[1]; pos[2] = anchor[2] - t3[2];
+          }
+          xanchor[3 * j] = anchor[0]; xanchor[3 * j + 1] = anchor[1]; xanchor[3 * j + 2] = anchor[2];
+          xaxis[3 * j] = axis[0]; xaxis[3 * j + 1] = axis[1]; xaxis[3 * j + 2] = axis[2];
+        }
+      }
+      quatnorm(quat);
+      xpos[3 * b] = pos[0]; xpos[3 * b + 1] = pos[1]; xpos[3 * b + 2] = pos[2];
+      xquat[4 * b] = quat[0]; xquat[4 * b + 1] = quat[1]; xquat[4 * b + 2] = quat[2]; xquat[4 * b + 3] = quat[3];
+      real R[9]; quat2mat(R, quat);
+#pragma unroll
+      for (int k = 0; k < 9; k++) xmat[9 * b + k] = R[k];
+    }
+  }
+  gsync(g);
+  /* geoms and sites, lane-parallel */
+  real *gxpos = s + m.o_gxpos, *gxmat = s + m.o_gxmat, *sxpos = s + m.o_sxpos, *sxmat = s + m.o_sxmat;
+  for (int i = g.lane; i < m.ngeom + m.nsite; i += RSB_LANES) {
+    bool isg = i < m.ngeom; int k = isg ? i : i - m.ngeom; int b = isg ? m.geom_body[k] : m.site_body[k];
+    const real *lp = isg ? m.geom_pos + 3 * k : m.site_pos + 3 * k, *lm = isg ? m.geom_mat + 9 * k : m.site_mat + 9 * k;
+    real t3[3], R[9]; matvec3(t3, xmat + 9 * b, lp); matmul3(R, xmat + 9 * b, lm);
+    real *op = isg ? gxpos + 3 * k : sxpos + 3 * k, *om = isg ? gxmat + 9 * k : sxmat + 9 * k;
+    op[0] = xpos[3 * b] + t3[0]; op[1] = xpos[3 * b + 1] + t3[1]; op[2] = xpos[3 * b + 2] + t3[2];
+#pragma unroll
+    for (int q = 0; q < 9; q++) om[q] = R[q];
+  }
+}
+
+/* ================================================================== A.3.2 inertias + motion subspaces about the tree reference point */
+/* spatial inertia record: [Ixx Iyy Izz Ixy Ixz Iyz hx hy hz m], h = m c, about the reference point */
+RSB_D void inert_mul(real *f, const real *I, const real *v) {
+  const real *w = v, *l = v + 3; const real *h = I + 6; real t[3];
+  f[0] = I[0] * w[0] + I[3] * w[1] + I[4] * w[2]; f[1] = I[3] * w[0] + I[1] * w[1] + I[5] * w[2]; f[2] = I[4] * w[0] + I[5] * w[1] + I[2] * w[2];
+  cross3(t, h, l); f[0] += t[0]; f[1] += t[1]; f[2] += t[2];
+  cross3(t, h, w); f[3] = I[9] * l[0] - t[0]; f[4] = I[9] * l[1] - t[1]; f[5] = I[9] * l[2] - t[2];
+}
+
+RSB_DN void st_inertia(const DevModel &m, real *s, Grp g) {
+  const real *xpos = s + m.o_xpos, *xmat = s + m.o_xmat, *xanchor = s + m.o_xanchor, *xaxis = s + m.o_xaxis;
+  real *cinert = s + m.o_cinert, *crb = s + m.o_crb, *cdof = s + m.o_cdof, *M = s + m.o_M;
+  for (int b = g.lane; b < m.nbody; b += RSB_LANES) {
+    real I[10];
+    real ms = m.body_mass[b];
+    if (b == 0 || ms <= 0) { for (int k = 0; k < 10; k++) I[k] = 0; }
+    else {
+      int r = m.body_root[b]; real Rw[9], c[3], t3[3];
+      matmul3(Rw, xmat + 9 * b, m.body_imat + 9 * b); matvec3(t3, xmat + 9 * b, m.body_ipos + 3 * b);
+      c[0] = xpos[3 * b] + t3[0] - xpos[3 * r]; c[1] = xpos[3 * b + 1] + t3[1] - xpos[3 * r + 1]; c[2] = xpos[3 * b + 2] + t3[2] - xpos[3 * r + 2];
+      real d0 = m.body_inertia[3 * b], d1 = m.body_inertia[3 * b + 1], d2 = m.body_inertia[3 * b + 2], cc = dot3(c, c);
+      I[0] = Rw[0] * Rw[0] * d0 + Rw[1] * Rw[1] * d1 + Rw[2] * Rw[2] * d2 + ms * (cc - c[0] * c[0]);
+      I[1] = Rw[3] * Rw[3] * d0 + Rw[4] * Rw[4] * d1 + Rw[5] * Rw[5] * d2 + ms * (cc - c[1] * c[1]);
+      I[2] = Rw[6] * Rw[6] * d0 + Rw[7] * Rw[7] * d1 + Rw[8] * Rw[8] * d2 + ms * (cc - c[2] * c[2]);
+      I[3] = Rw[0] * Rw[3] * d0 + Rw[1] * Rw[4] * d1 + Rw[2] * Rw[5] * d2 - ms * c[0] * c[1];
+      I[4] = Rw[0] * Rw[6] * d0 + Rw[1] * Rw[7] * d1 + Rw[2] * Rw[8] * d2 - ms * c[0] * c[2];
+      I[5] = Rw[3] * Rw[6] * d0 + Rw[4] * Rw[7] * d1 + Rw[5] * Rw[8] * d2 - ms * c[1] * c[2];
+      I[6] = ms * c[0]; I[7] = ms * c[1]; I[8] = ms * c[2]; I[9] = ms;
+    }
+#pragma unroll
+    for (int k = 0; k < 10; k++) { cinert[10 * b + k] = I[k]; crb[10 * b + k] = I[k]; }
+  }
+  for (int d = g.lane; d < m.nv; d += RSB_LANES) {
+    int kind = m.dof_kind[d], j = m.dof_jnt[d], b = m.dof_body[d], r = m.dof_root[d]; real w[3] = {0, 0, 0}, v[3] = {0, 0, 0};
+    if (kind == RSB_DOF_SLIDE) { v[0] = xaxis[3 * j]; v[1] = xaxis[3 * j + 1]; v[2] = xaxis[3 * j + 2]; }
+    else if (kind == RSB_DOF_FREE_T) { v[d - m.jnt_dadr[j]] = 1; }
+    else {
+      real off[3];
+      if (kind == RSB_DOF_HINGE) {
+        w[0] = xaxis[3 * j]; w[1] = xaxis[3 * j + 1]; w[2] = xaxis[3 * j + 2];
+        off[0] = xpos[3 * r] - xanchor[3 * j]; off[1] = xpos[3 * r + 1] - xanchor[3 * j + 1]; off[2] = xpos[3 * r + 2] - xanchor[3 * j + 2];
+      } else {                                      /* free rotation: body-local axis k expressed in the world */
+        int k = d - m.jnt_dadr[j] - 3; w[0] = xmat[9 * b + k]; w[1] = xmat[9 * b + 3 + k]; w[2] = xmat[9 * b + 6 + k];
+        off[0] = xpos[3 * r] - xpos[3 * b]; off[1] = xpos[3 * r + 1] - xpos[3 * b + 1]; off[2] = xpos[3 * r + 2] - xpos[3 * b + 2];
+      }
+      cross3(v, w, off);                            /* velocity of the reference point under unit rotation */
+    }
+    cdof[6 * d] = w[0]; cdof[6 * d + 1] = w[1]; cdof[6 * d + 2] = w[2]; cdof[6 * d + 3] = v[0]; cdof[6 * d + 4] = v[1]; cdof[6 * d + 5] = v[2];
+  }
+  for (int i = g.lane; i < m.nv * m.ldm; i += RSB_LANES) M[i] = 0;
+  gsync(g);
+}
+
+/* ================================================================== A.3.3 composite rigid bodies -> dense symmetric M (+ armature) */
+RSB_DN void st_crb(const DevModel &m, real *s, Grp g) {
+  real *crb = s + m.o_crb, *cdof = s + m.o_cdof, *fi = s + m.o_fi, *M = s + m.o_M;
+  if (g.lane < 10) for (int b = m.nbody - 1; b > 0; b--) crb[10 * m.body_parent[b] + g.lane] += crb[10 * b + g.lane];
+  gsync(g);
+  for (int d = g.lane; d < m.nv; d += RSB_LANES) { real f[6]; inert_mul(f, crb + 10 * m.dof_body[d], cdof + 6 * d);
+#pragma unroll
+    for (int k = 0; k < 6; k++) fi[6 * d + k] = f[k]; }
+  gsync(g);
+  for (int p = g.lane; p < m.nmpair; p += RSB_LANES) {
+    int i = m.mpair_i[p], j = m.mpair_j[p]; real v = dot6(cdof + 6 * j, fi + 6 * i);
+    if (i == j) v += m.dof_armature[i];
+    M[i * m.ldm + j] = v; M[j * m.ldm + i] = v;
+  }
+  gsync(g);
+}
+
+/* ================================================================== A.3.7 RNE(acc = 0) with gravity -> qfrc_bias; passive forces */
+RSB_D void crossm(real *o, const real *v, const real *c) {          /* motion cross: v x c */
+  real a[3], b[3], d[3]; cross3(a, v, c); cross3(b, v, c + 3); cross3(d, v + 3, c);
+  o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = b[0] + d[0]; o[4] = b[1] + d[1]; o[5] = b[2] + d[2];
+}
+RSB_D void crossf(real *o, const real *v, const real *f) {          /* force cross: v x* f */
+  real a[3], b[3], d[3]; cross3(a, v, f); cross3(b, v + 3, f + 3); cross3(d, v, f + 3);
+  o[0] = a[0] + b[0]; o[1] = a[1] + b[1]; o[2] = a[2] + b[2]; o[3] = d[0]; o[4] = d[1]; o[5] = d[2];
+}
+
+RSB_DN void st_bias(const DevModel &m, real *s, Grp g) {
+  const real *qvel = s + m.o_qvel, *qpos = s + m.o_qpos, *cdof = s + m.o_cdof, *cinert = s + m.o_cinert;
+  real *cvel = s + m.o_cvel, *cacc = s + m.o_cacc, *cdd = s + m.o_cdofdot, *bias = s + m.o_bias, *passive = s + m.o_passive;
+  /* body velocities: sum over the dof chain (all dofs of a tree share the reference point) */
+  for (int b = g.lane; b < m.nbody; b += RSB_LANES) {
+    real v[6] = {0, 0, 0, 0, 0, 0};
+    for (int d = m.body_lastdof[b]; d >= 0; d = m.dof_parent[d]) { real q = qvel[d];
+#pragma unroll
+      for (int k = 0; k < 6; k++) v[k] += cdof[6 * d + k] * q; }
+#pragma unroll
+    for (int k = 0; k < 6; k++) cvel[6 * b + k] = v[k];
+  }
+  /* cdof_dot = (velocity accumulated before this dof) x cdof */
+  for (int d = g.lane; d < m.nv; d += RSB_LANES) {
+    real o[6] = {0, 0, 0, 0, 0, 0}; int st = m.dof_velstart[d];
+    if (st != -2) {
+      real v[6] = {0, 0, 0, 0, 0, 0};
+      for (int e = st; e >= 0; e = m.dof_parent[e]) { real q = qvel[e];
+#pragma unroll
+        for (int k = 0; k < 6; k++) v[k] += cdof[6 * e + k] * q; }
+      crossm(o, v, cdof + 6 * d);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) cdd[6 * d + k] = o[k];
+  }
+  gsync(g);
+  /* body accelerations (acc = 0, gravity as base acceleration) and body forces */
+  for (int b = g.lane; b < m.nbody; b += RSB_LANES) {
+    real a[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
+    for (int d = m.body_lastdof[b]; d >= 0; d = m.dof_parent[d]) { real q = qvel[d];
+#pragma unroll
+      for (int k = 0; k < 6; k++) a[k] += cdd[6 * d + k] * q; }
+    real f[6] = {0, 0, 0, 0, 0, 0};
+    if (b > 0) { real Ia[6], Iv[6], t[6]; inert_mul(Ia, cinert + 10 * b, a); inert_mul(Iv, cinert + 10 * b, cvel + 6 * b); crossf(t, cvel + 6 * b, Iv);
+#pragma unroll
+      for (int k = 0; k < 6; k++) f[k] = Ia[k] + t[k]; }
+#pragma unroll
+    for (int k = 0; k < 6; k++) cacc[6 * b + k] = f[k];          /* cacc now holds cfrc_body */
+  }
+  gsync(g);
+  if (g.lane < 6) for (int b = m.nbody - 1; b > 0; b--) cacc[6 * m.body_parent[b] + g.lane] += cacc[6 * b + g.lane];
+  gsync(g);
+  for (int d = g.lane; d < m.nv; d += RSB_LANES) {
+    bias[d] = dot6(cdof + 6 * d, cacc + 6 * m.dof_body[d]);
+    real p = -m.dof_damping[d] * qvel[d]; int j = m.dof_jnt[d];
+    if (m.dof_kind[d] <= RSB_DOF_SLIDE && m.jnt_stiffness[j] != 0) p -= m.jnt_stiffness[j] * (qpos[m.jnt_qadr[j]] - m.qpos_spring[m.jnt_qadr[j]]);
+    passive[d] = p;
+  }
+  gsync(g);
+}
+
+/* ================================================================== A.3.5 collision */
+struct RawCon { real pos[3], normal[3], dist; };
+
+RSB_D void make_frame(real *frame) {              /* frame[0..2] = normal; fills the two tangents (mju_makeFrame) */
+  real *x = frame, *y = frame + 3, *z = frame + 6;
+  if (x[1] < 0.5f && x[1] > -0.5f) { y[0] = 0; y[1] = 1; y[2] = 0; } else { y[0] = 0; y[1] = 0; y[2] = 1; }
+  real d = dot3(x, y); y[0] -= x[0] * d; y[1] -= x[1] * d; y[2] -= x[2] * d;
+  real n = sqrtf(dot3(y, y)); if (n < RSB_MINVAL) { y[0] = 1; y[1] = 0; y[2] = 0; } else { y[0] /= n; y[1] /= n; y[2] /= n; }
+  cross3(z, x, y);
+}
+
+RSB_D int col_plane_sphere(const real *ppos, const real *pmat, const real *spos, real r, real margin, RawCon *out) {
+  real n[3] = {pmat[2], pmat[5], pmat[8]}, dif[3] = {spos[0] - ppos[0], spos[1] - ppos[1], spos[2] - ppos[2]};
+  real d = dot3(dif, n) - r; if (d > margin) return 0;
+  out->dist = d;
+  for (int k = 0; k < 3; k++) { out->normal[k] = n[k]; out->pos[k] = spos[k] - n[k] * (r + 0.5f * d); }
+  return 1;
+}
+RSB_D int col_plane_box(const real *ppos, const real *pmat, const real *bpos, const real *bmat, const real *size, real margin, RawCon *out) {
+  real n[3] = {pmat[2], pmat[5], pmat[8]}; int cnt = 0;
+  real dif[3] = {bpos[0] - ppos[0], bpos[1] - ppos[1], bpos[2] - ppos[2]}; real d0 = dot3(dif, n);
+  for (int i = 0; i < 8 && cnt < 4; i++) {
+    real loc[3] = {(i & 1 ? size[0] : -size[0]), (i & 2 ? size[1] : -size[1]), (i & 4 ? size[2] : -size[2])}, w[3];
+    matvec3(w, bmat, loc);
+    real ld = d0 + dot3(w, n);
+    if (ld > margin) continue;
+    RawCon *c = &out[cnt++]; c->dist = ld;
+    for (int k = 0; k < 3; k++) { c->normal[k] = n[k]; c->pos[k] = bpos[k] + w[k] - n[k] * ld * 0.5f; }
+  }
+  return cnt;
+}
+RSB_D int col_plane_capsule(const real *ppos, const real *pmat, const real *cpos, const real *cmat, const real *size, real margin, RawCon *out) {
+  real ax[3] = {cmat[2], cmat[5], cmat[8]}; int cnt = 0;
+  for (int sg = -1; sg <= 1; sg += 2) { real p[3] = {cpos[0] + ax[0] * sg * size[1], cpos[1] + ax[1] * sg * size[1], cpos[2] + ax[2] * sg * size[1]}; cnt += col_plane_sphere(ppos, pmat, p, size[0], margin, out + cnt); }
+  return cnt;
+}
+RSB_D int col_sphere_sphere(const real *p1, real r1, const real *p2, real r2, real margin, RawCon *out) {
+  real d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]}; real len = sqrtf(dot3(d, d)), dist = len - r1 - r2;
+  if (dist > margin) return 0;
+  if (len < RSB_MINVAL) { d[0] = 1; d[1] = 0; d[2] = 0; } else { d[0] /= len; d[1] /= len; d[2] /= len; }
+  out->dist = dist;
+  for (int k = 0; k < 3; k++) { out->normal[k] = d[k]; out->pos[k] = p1[k] + d[k] * (r1 + 0.5f * dist); }
+  return 1;
+}
+RSB_D int col_capsule_capsule(const real *p1, const real *m1, const real *s1, const real *p2, const real *m2, const real *s2, real margin, RawCon *out) {
+  real a1[3] = {m1[2], m1[5], m1[8]}, a2[3] = {m2[2], m2[5], m2[8]}, d[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+  real b = dot3(a1, a2), c1 = dot3(a1, d), c2 = dot3(a2, d), den = 1 - b * b, t1, t2;
+  if (den < 1e-12f) { t1 = 0; t2 = c2; } else { t1 = (b * c2 - c1) / den; t2 = (c2 - b * c1) / den; }
+  t1 = clampf(t1, -s1[1], s1[1]);
+  t2 = clampf(c2 + b * t1, -s2[1], s2[1]);
+  t1 = clampf(-c1 + b * t2, -s1[1], s1[1]);
+  real q1[3] = {p1[0] + a1[0] * t1, p1[1] + a1[1] * t1, p1[2] + a1[2] * t1}, q2[3] = {p2[0] + a2[0] * t2, p2[1] + a2[1] * t2, p2[2] + a2[2] * t2};
+  return col_sphere_sphere(q1, s1[0], q2, s2[0], margin, out);
+}
+RSB_D int col_sphere_box(const real *sp, real r, const real *bp, const real *bm, const real *size, real margin, RawCon *out) {
+  real d[3] = {sp[0] - bp[0], sp[1] - bp[1], sp[2] - bp[2]}, loc[3], cl[3]; matTvec3(loc, bm, d); int inside = 1;
+  for (int k = 0; k < 3; k++) { cl[k] = loc[k]; if (cl[k] > size[k]) { cl[k] = size[k]; inside = 0; } if (cl[k] < -size[k]) { cl[k] = -size[k]; inside = 0; } }
+  real nl[3], dist;
+  if (!inside) { nl[0] = loc[0] - cl[0]; nl[1] = loc[1] - cl[1]; nl[2] = loc[2] - cl[2]; real len = sqrtf(dot3(nl, nl));
+    if (len < RSB_MINVAL) { nl[0] = 1; nl[1] = 0; nl[2] = 0; } else { nl[0] /= len; nl[1] /= len; nl[2] /= len; } dist = len - r; }
+  else {
+    int bk = 0; real best = 1e30f;
+    for (int k = 0; k < 3; k++) { real f = size[k] - fabsf(loc[k]); if (f < best) { best = f; bk = k; } }
+    nl[0] = nl[1] = nl[2] = 0; nl[bk] = loc[bk] >= 0 ? 1.0f : -1.0f; cl[bk] = nl[bk] * size[bk]; dist = -best - r;
+  }
+  if (dist > margin) return 0;
+  real nw[3], cw[3]; matvec3(nw, bm, nl); matvec3(cw, bm, cl);
+  out->dist = dist;
+  for (int k = 0; k < 3; k++) { out->normal[k] = -nw[k]; out->pos[k] = bp[k] + cw[k] + nw[k] * 0.5f * dist; }
+  return 1;
+}
+RSB_D int col_capsule_box(const real *cp, const real *cm, const real *cs, const real *bp, const real *bm, const real *size, real margin, RawCon *out) {
+  real ax[3] = {cm[2], cm[5], cm[8]}; int cnt = 0;
+  for (int sg = -1; sg <= 1; sg++) { real p[3] = {cp[0] + ax[0] * sg * cs[1], cp[1] + ax[1] * sg * cs[1], cp[2] + ax[2] * sg * cs[1]}; cnt += col_sphere_box(p, cs[0], bp, bm, size, margin, out + cnt); }
+  return cnt;
+}
+
+/* box-box: separating-axis test over 15 axes, then reference-face clipping (face case, <= 8 contacts) or the closest
+   points of the two supporting edges (edge case, 1 contact).  Same contact generation rules as DESIGN.md "box-box". */
+RSB_DNOINL int col_box_box(const real *pa, const real *Ra, const real *ha, const real *pb, const real *Rb, const real *hb, real margin, RawCon *out) {
+  real R[9], Q[9], t[3], d[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { real v = Ra[i] * Rb[j] + Ra[3 + i] * Rb[3 + j] + Ra[6 + i] * Rb[6 + j]; R[3 * i + j] = v; Q[3 * i + j] = fabsf(v) + 1e-9f; }
+  matTvec3(t, Ra, d);
+  real best = -1e30f; int code = -1; real bsign = 1;
+  for (int i = 0; i < 3; i++) {
+    real sp = fabsf(t[i]) - (ha[i] + hb[0] * Q[3 * i] + hb[1] * Q[3 * i + 1] + hb[2] * Q[3 * i + 2]);
+    if (sp > margin) return 0;
+    if (sp > best + 1e-6f) { best = sp; code = i; bsign = t[i] >= 0 ? 1.0f : -1.0f; }
+  }
+  for (int j = 0; j < 3; j++) {
+    real tb = t[0] * R[j] + t[1] * R[3 + j] + t[2] * R[6 + j];
+    real sp = fabsf(tb) - (hb[j] + ha[0] * Q[j] + ha[1] * Q[3 + j] + ha[2] * Q[6 + j]);
+    if (sp > margin) return 0;
+    if (sp > best + 1e-6f) { best = sp; code = 3 + j; bsign = tb >= 0 ? 1.0f : -1.0f; }
+  }
+  real en[3] = {0, 0, 0};
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    real L[3] = {0, 0, 0}; L[i1] = -R[3 * i2 + j]; L[i2] = R[3 * i1 + j];
+    real len = sqrtf(L[i1] * L[i1] + L[i2] * L[i2]);
+    if (len < 1e-6f) continue;
+    real tl = (t[i1] * L[i1] + t[i2] * L[i2]) / len;
+    real ra = (ha[i1] * Q[3 * i2 + j] + ha[i2] * Q[3 * i1 + j]) / len;
+    real rb = (hb[j1] * Q[3 * i + j2] + hb[j2] * Q[3 * i + j1]) / len;
+    real sp = fabsf(tl) - (ra + rb);
+    if (sp > margin) return 0;
+    if (sp > best + 1e-4f) { best = sp; code = 6 + 3 * i + j; bsign = tl >= 0 ? 1.0f : -1.0f; en[0] = L[0] / len; en[1] = L[1] / len; en[2] = L[2] / len; }
+  }
+  if (code < 0) return 0;
+  if (code >= 6) {
+    int i = (code - 6) / 3, j = (code - 6) % 3;
+    real nA[3] = {en[0] * bsign, en[1] * bsign, en[2] * bsign}, n[3]; matvec3(n, Ra, nA);
+    real ca[3] = {pa[0], pa[1], pa[2]}, cb[3] = {pb[0], pb[1], pb[2]};
+    for (int k = 0; k < 3; k++) if (k != i) { real sg = nA[k] > 0 ? 1.0f : -1.0f; for (int c = 0; c < 3; c++) ca[c] += sg * ha[k] * Ra[3 * c + k]; }
+    real nB[3]; matTvec3(nB, Rb, n);
+    for (int k = 0; k < 3; k++) if (k != j) { real sg = nB[k] > 0 ? -1.0f : 1.0f; for (int c = 0; c < 3; c++) cb[c] += sg * hb[k] * Rb[3 * c + k]; }
+    real ua[3] = {Ra[i], Ra[3 + i], Ra[6 + i]}, ub[3] = {Rb[j], Rb[3 + j], Rb[6 + j]}, w[3] = {ca[0] - cb[0], ca[1] - cb[1], ca[2] - cb[2]};
+    real bb = dot3(ua, ub), dd = dot3(ua, w), ee = dot3(ub, w), den = 1 - bb * bb;
+    real sa = den > 1e-12f ? (bb * ee - dd) / den : 0, sb = den > 1e-12f ? (ee - bb * dd) / den : 0;
+    sa = clampf(sa, -ha[i], ha[i]); sb = clampf(sb, -hb[j], hb[j]);
+    out->dist = best;
+    for (int k = 0; k < 3; k++) { out->normal[k] = n[k]; out->pos[k] = 0.5f * ((ca[k] + ua[k] * sa) + (cb[k] + ub[k] * sb)); }
+    return 1;
+  }
+  const real *pr, *Rr, *hr, *pi, *Ri, *hi; int ax; real nsign;
+  if (code < 3) { pr = pa; Rr = Ra; hr = ha; pi = pb; Ri = Rb; hi = hb; ax = code; nsign = bsign; }
+  else { pr = pb; Rr = Rb; hr = hb; pi = pa; Ri = Ra; hi = ha; ax = code - 3; nsign = -bsign; }
+  real nr[3] = {Rr[ax] * nsign, Rr[3 + ax] * nsign, Rr[6 + ax] * nsign};
+  real nl[3]; matTvec3(nl, Ri, nr); int ia = 0; real am = fabsf(nl[0]);
+  for (int k = 1; k < 3; k++) if (fabsf(nl[k]) > am) { am = fabsf(nl[k]); ia = k; }
+  real isg = nl[ia] > 0 ? -1.0f : 1.0f; int u = (ia + 1) % 3, v = (ia + 2) % 3;
+  real poly[16][3], tmp[16][3]; int np = 4;
+  for (int c = 0; c < 4; c++) {
+    real su = (c == 0 || c == 3) ? -1.0f : 1.0f, sv = (c < 2) ? -1.0f : 1.0f; real wv[3];
+    for (int k = 0; k < 3; k++) wv[k] = pi[k] + isg * hi[ia] * Ri[3 * k + ia] + su * hi[u] * Ri[3 * k + u] + sv * hi[v] * Ri[3 * k + v] - pr[k];
+    matTvec3(poly[c], Rr, wv);
+  }
+  int ru = (ax + 1) % 3, rv = (ax + 2) % 3;
+  for (int side = 0; side < 4; side++) {
+    int k = side < 2 ? ru : rv; real sg = (side & 1) ? -1.0f : 1.0f, lim = hr[k];
+    int nn = 0;
+    for (int c = 0; c < np; c++) {
+      const real *P = poly[c], *Qp = poly[(c + 1) % np];
+      real dp = sg * P[k] - lim, dq = sg * Qp[k] - lim;
+      if (dp <= 0) { tmp[nn][0] = P[0]; tmp[nn][1] = P[1]; tmp[nn][2] = P[2]; nn++; }
+      if ((dp < 0 && dq > 0) || (dp > 0 && dq < 0)) { real f = dp / (dp - dq); for (int x = 0; x < 3; x++) tmp[nn][x] = P[x] + f * (Qp[x] - P[x]); nn++; }
+    }
+    np = nn; for (int c = 0; c < np; c++) { poly[c][0] = tmp[c][0]; poly[c][1] = tmp[c][1]; poly[c][2] = tmp[c][2]; }
+    if (np == 0) return 0;
+  }
+  int cnt = 0;
+  real nout[3]; for (int k = 0; k < 3; k++) nout[k] = (code < 3) ? nr[k] : -nr[k];
+  for (int c = 0; c < np && cnt < 8; c++) {
+    real depth = nsign * poly[c][ax] - hr[ax];
+    if (depth > margin) continue;
+    real pl[3] = {poly[c][0], poly[c][1], poly[c][2]}; pl[ax] -= nsign * 0.5f * depth;
+    RawCon *o = &out[cnt++]; real w[3]; matvec3(w, Rr, pl);
+    o->dist = depth; for (int k = 0; k < 3; k++) { o->pos[k] = pr[k] + w[k]; o->normal[k] = nout[k]; }
+  }
+  return cnt;
+}
+
+/* contact record in shared memory (RSB_CONW words): pos3 frame9 dist includemargin mu | pair dim efc_address geom1 geom2 */
+#define CON_DIST 12
+#define CON_INC 13
+#define CON_MU 14
+#define CON_PAIR 15
+#define CON_DIM 16
+#define CON_ADR 17
+#define CON_G1 18
+#define CON_G2 19
+#define MISC_NCON 0
+#define MISC_NEFC 1
+#define MISC_ITER 2
+#define MISC_NLIMROW 3
+
+RSB_DN void st_collision(const DevModel &m, real *s, Grp g) {
+  const real *gxpos = s + m.o_gxpos, *gxmat = s + m.o_gxmat; real *con = s + m.o_con; int *misc = (int *)(s + m.o_misc);
+  int base = 0;
+  for (int p0 = 0; p0 < m.npair; p0 += RSB_LANES) {
+    int p = p0 + g.lane; RawCon rc[9]; int n = 0; real inc = 0;
+    if (p < m.npair) {
+      int g1 = m.pair_g1[p], g2 = m.pair_g2[p], t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+      real margin = m.pair_margin[p]; const real *p1 = gxpos + 3 * g1, *p2 = gxpos + 3 * g2, *R1 = gxmat + 9 * g1, *R2 = gxmat + 9 * g2;
+      const real *s1 = m.geom_size + 3 * g1, *s2 = m.geom_size + 3 * g2;
+      bool reject;
+      real dv[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+      if (t1 == RSB_GEOM_PLANE) { real nn[3] = {R1[2], R1[5], R1[8]}; reject = dot3(dv, nn) > m.geom_rbound[g2] + margin; }
+      else { real bound = m.geom_rbound[g1] + m.geom_rbound[g2] + margin; reject = dot3(dv, dv) > bound * bound; }
+      if (!reject) {
+        if (t1 == RSB_GEOM_PLANE && t2 == RSB_GEOM_BOX) n = col_plane_box(p1, R1, p2, R2, s2, margin, rc);
+        else if (t1 == RSB_GEOM_PLANE && t2 == RSB_GEOM_SPHERE) n = col_plane_sphere(p1, R1, p2, s2[0], margin, rc);
+        else if (t1 == RSB_GEOM_PLANE && t2 == RSB_GEOM_CAPSULE) n = col_plane_capsule(p1, R1, p2, R2, s2, margin, rc);
+        else if (t1 == RSB_GEOM_SPHERE && t2 == RSB_GEOM_SPHERE) n = col_sphere_sphere(p1, s1[0], p2, s2[0], margin, rc);
+        else if (t1 == RSB_GEOM_SPHERE && t2 == RSB_GEOM_BOX) n = col_sphere_box(p1, s1[0], p2, R2, s2, margin, rc);
+        else if (t1 == RSB_GEOM_CAPSULE && t2 == RSB_GEOM_CAPSULE) n = col_capsule_capsule(p1, R1, s1, p2, R2, s2, margin, rc);
+        else if (t1 == RSB_GEOM_CAPSULE && t2 == RSB_GEOM_BOX) n = col_capsule_box(p1, R1, s1, p2, R2, s2, margin, rc);
+        else if (t1 == RSB_GEOM_BOX && t2 == RSB_GEOM_BOX) n = col_box_box(p1, R1, s1, p2, R2, s2, margin, rc);
+      }
+      inc = margin - m.pair_gap[p];
+      int keep = 0;                                 /* active contacts only: dist < includemargin; compact in place */
+      for (int k = 0; k < n; k++) if (rc[k].dist < inc) { if (keep != k) rc[keep] = rc[k]; keep++; }
+      n = keep;
+    }
+    int incl = gscan_incl(g, n), off = base + incl - n;
+    for (int k = 0; k < n; k++) {
+      int c = off + k; if (c >= m.ncon_max) break;
+      real *o = con + c * RSB_CONW; int *oi = (int *)o;
+      o[0] = rc[k].pos[0]; o[1] = rc[k].pos[1]; o[2] = rc[k].pos[2];
+      real fr[9]; fr[0] = rc[k].normal[0]; fr[1] = rc[k].normal[1]; fr[2] = rc[k].normal[2]; make_frame(fr);
+#pragma unroll
+      for (int q = 0; q < 9; q++) o[3 + q] = fr[q];
+      o[CON_DIST] = rc[k].dist; o[CON_INC] = inc; o[CON_MU] = 0;
+      oi[CON_PAIR] = p; oi[CON_DIM] = m.pair_dim[p]; oi[CON_ADR] = -1; oi[CON_G1] = m.pair_g1[p]; oi[CON_G2] = m.pair_g2[p];
+    }
+    base += gshfl_i(g, incl, RSB_LANES - 1);
+  }
+  if (base > m.ncon_max) base = m.ncon_max;
+  if (g.lane == 0) misc[MISC_NCON] = base;
+  gsync(g);
+}
+
+/* ================================================================== A.3.6 constraint rows */
+enum { EFC_FRICTION = 0, EFC_LIMIT = 1, EFC_CONTACT_NORMAL = 2, EFC_CONTACT_FRICTION = 3 };
+
+RSB_D real impedance_fn(const real *si, real pos, real margin) {
+  real d0 = si[0], d1 = si[1], w = si[2], mid = si[3], pw = si[4];
+  if (d0 == d1 || w <= RSB_MINVAL) return 0.5f * (d0 + d1);
+  real x = fabsf(pos - margin) / w, y;
+  if (x >= 1) return d1;
+  if (x <= 0) return d0;
+  if (pw == 1) y = x;
+  else if (pw == 2) y = (x <= mid) ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
+  else if (x <= mid) y = powf(x, pw) / powf(mid, pw - 1);
+  else y = 1 - powf(1 - x, pw) / powf(1 - mid, pw - 1);
+  return d0 + y * (d1 - d0);
+}
+RSB_D void kb_fn(const DevModel &m, const real *solref, const real *solimp, real *K, real *B) {
+  real dmax = solimp[1];
+  if (solref[0] > 0) {
+    real tc = fmaxf(solref[0], 2 * m.timestep), dr = solref[1];
+    real k = dmax * dmax * tc * tc * dr * dr; *K = 1 / fmaxf(k, RSB_MINVAL);
+    *B = 2 / fmaxf(dmax * tc, RSB_MINVAL);
+  } else { *K = -solref[0] / fmaxf(dmax * dmax, RSB_MINVAL); *B = -solref[1] / fmaxf(dmax, RSB_MINVAL); }
+}
+
+RSB_DN void st_constraint(const DevModel &m, real *s, Grp g) {
+  const real *qpos = s + m.o_qpos, *qvel = s + m.o_qvel, *cdof = s + m.o_cdof, *xpos = s + m.o_xpos;
+  real *con = s + m.o_con, *J = s + m.o_J; int *misc = (int *)(s + m.o_misc);
+  real *epos = s + m.o_epos, *emargin = s + m.o_emargin, *eR = s + m.o_eR, *eD = s + m.o_eD, *earef = s + m.o_earef, *efloss = s + m.o_efloss;
+  int *etype = (int *)(s + m.o_etype), *eid = (int *)(s + m.o_eid);
+  const int ncon = misc[MISC_NCON], nv = m.nv, ldj = m.ldj;
+  /* rows 0..nfl-1: dof friction loss (static) */
+  for (int k = g.lane; k < m.nfl; k += RSB_LANES) { etype[k] = EFC_FRICTION; eid[k] = m.fl_dof[k]; epos[k] = 0; emargin[k] = 0; efloss[k] = m.dof_floss[m.fl_dof[k]]; }
+  /* joint limits: ordered compaction (joint order, lower side before upper side) */
+  int nrow = m.nfl;
+  for (int k0 = 0; k0 < m.nlimj; k0 += RSB_LANES) {
+    int k = k0 + g.lane, cnt = 0; real dlo = 0, dhi = 0, mg = 0; int j = 0;
+    if (k < m.nlimj) { j = m.lim_jnt[k]; real q = qpos[m.jnt_qadr[j]]; mg = m.jnt_margin[j]; dlo = q - m.jnt_range[2 * j]; dhi = m.jnt_range[2 * j + 1] - q; cnt = (dlo < mg) + (dhi < mg); }
+    int incl = gscan_incl(g, cnt), r = nrow + incl - cnt;
+    if (cnt && dlo < mg && r < m.nefc_max) { etype[r] = EFC_LIMIT; eid[r] = j; epos[r] = dlo; emargin[r] = mg; efloss[r] = 1.0f; r++; }   /* efloss doubles as the sign of J */
+    if (cnt && dhi < mg && r < m.nefc_max) { etype[r] = EFC_LIMIT; eid[r] = j; epos[r] = dhi; emargin[r] = mg; efloss[r] = -1.0f; }
+    nrow += gshfl_i(g, incl, RSB_LANES - 1);
+  }
+  if (nrow > m.nefc_max) nrow = m.nefc_max;
+  const int nscalar = nrow;
+  /* contact row addresses: serial rule of the reference (a contact that does not fit is skipped, later ones may fit) */
+  gsync(g);
+  if (g.lane == 0) {
+    int n = nscalar;
+    for (int c = 0; c < ncon; c++) { int *ci = (int *)(con + c * RSB_CONW); int dim = ci[CON_DIM];
+      if (n + dim > m.nefc_max) ci[CON_ADR] = -1; else { ci[CON_ADR] = n; n += dim; } }
+    misc[MISC_NEFC] = n;
+  }
+  gsync(g);
+  const int nefc = misc[MISC_NEFC];
+  /* scalar rows of J */
+  for (int i = g.lane; i < nscalar * nv; i += RSB_LANES) {
+    int r = i / nv, d = i - r * nv; real v = 0;
+    if (etype[r] == EFC_FRICTION) v = (eid[r] == d) ? 1.0f : 0.0f;
+    else v = (m.jnt_dadr[eid[r]] == d) ? efloss[r] : 0.0f;
+    J[r * ldj + d] = v;
+  }
+  /* contact rows of J: item = (contact, dof) */
+  for (int i = g.lane; i < ncon * nv; i += RSB_LANES) {
+    int c = i / nv, d = i - c * nv; const real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr;
+    int adr = ci[CON_ADR]; if (adr < 0) continue;
+    int dim = ci[CON_DIM], b1 = m.geom_body[ci[CON_G1]], b2 = m.geom_body[ci[CON_G2]];
+    int sgn = ((m.body_dofmask[b2] >> d) & 1) - ((m.body_dofmask[b1] >> d) & 1);
+    real jp[3] = {0, 0, 0}, jr[3] = {0, 0, 0};
+    if (sgn != 0) {
+      int r = m.dof_root[d]; real off[3] = {cr[0] - xpos[3 * r], cr[1] - xpos[3 * r + 1], cr[2] - xpos[3 * r + 2]}, t[3];
+      cross3(t, cdof + 6 * d, off); real sg = (real)sgn;
+      jp[0] = sg * (cdof[6 * d + 3] + t[0]); jp[1] = sg * (cdof[6 * d + 4] + t[1]); jp[2] = sg * (cdof[6 * d + 5] + t[2]);
+      jr[0] = sg * cdof[6 * d]; jr[1] = sg * cdof[6 * d + 1]; jr[2] = sg * cdof[6 * d + 2];
+    }
+    J[adr * ldj + d] = dot3(cr + 3, jp);
+    if (dim >= 3) { J[(adr + 1) * ldj + d] = dot3(cr + 6, jp); J[(adr + 2) * ldj + d] = dot3(cr + 9, jp); }
+    if (dim >= 4) J[(adr + 3) * ldj + d] = dot3(cr + 3, jr);
+  }
+  /* contact row bookkeeping */
+  for (int c = g.lane; c < ncon; c += RSB_LANES) {
+    const real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr; int adr = ci[CON_ADR]; if (adr < 0) continue;
+    for (int r = 0; r < ci[CON_DIM]; r++) { etype[adr + r] = r == 0 ? EFC_CONTACT_NORMAL : EFC_CONTACT_FRICTION; eid[adr + r] = c; efloss[adr + r] = 0;
+      epos[adr + r] = r == 0 ? cr[CON_DIST] : 0; emargin[adr + r] = r == 0 ? cr[CON_INC] : 0; }
+  }
+  gsync(g);
+  /* impedance, regulariser, reference acceleration (mj_makeImpedance), lane per row */
+  for (int r = g.lane; r < nefc; r += RSB_LANES) {
+    const real *solref, *solimp; real diag; int type = etype[r], id = eid[r];
+    if (type == EFC_FRICTION) { solref = m.dof_solref + 2 * id; solimp = m.dof_solimp + 5 * id; diag = m.dof_invw[id]; }
+    else if (type == EFC_LIMIT) { solref = m.jnt_solref + 2 * id; solimp = m.jnt_solimp + 5 * id; diag = m.dof_invw[m.jnt_dadr[id]]; }
+    else {
+      const int *ci = (const int *)(con + id * RSB_CONW); int p = ci[CON_PAIR], rr = r - ci[CON_ADR];
+      solref = m.pair_solref + 2 * p; solimp = m.pair_solimp + 5 * p; int o = rr < 3 ? 0 : 1;
+      diag = m.body_invw[2 * m.geom_body[ci[CON_G1]] + o] + m.body_invw[2 * m.geom_body[ci[CON_G2]] + o];
+    }
+    real K, B; kb_fn(m, solref, solimp, &K, &B);
+    if (type == EFC_FRICTION || type == EFC_CONTACT_FRICTION) K = 0;
+    real imp = impedance_fn(solimp, epos[r], emargin[r]);
+    real Rr = fmaxf((1 - imp) / imp * diag, RSB_MINVAL); eR[r] = Rr;
+    real vel = 0; for (int d = 0; d < nv; d++) vel += J[r * ldj + d] * qvel[d];
+    earef[r] = -B * vel - K * imp * (epos[r] - emargin[r]);
+  }
+  gsync(g);
+  /* elliptic friction rows: R from the normal row and impratio; regularised cone slope mu */
+  for (int c = g.lane; c < ncon; c += RSB_LANES) {
+    real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr; int i = ci[CON_ADR], dim = ci[CON_DIM]; const real *fr = m.pair_friction + 5 * ci[CON_PAIR];
+    if (i < 0) continue;
+    if (dim < 2) { cr[CON_MU] = fr[0]; continue; }
+    real ir = fmaxf(m.impratio, RSB_MINVAL);
+    eR[i + 1] = eR[i] / ir; cr[CON_MU] = fr[0] * sqrtf(eR[i + 1] / eR[i]);
+    for (int j = 1; j < dim - 1; j++) eR[i + 1 + j] = eR[i + 1] * fr[0] * fr[0] / (fr[j] * fr[j]);
+  }
+  gsync(g);
+  for (int r = g.lane; r < nefc; r += RSB_LANES) eD[r] = 1.0f / eR[r];
+  gsync(g);
+}
+
+/* ================================================================== dense Cholesky, lane per row (n <= 2*RSB_LANES) */
+/* In-place lower factor of the symmetric matrix A (only the lower triangle is read).  Pivots below `floor_` are treated as
+   dropped directions (pinv-like): the column is zeroed and the pivot set to +inf so solves return 0 along it. */
+RSB_DN void chol_factor(real *A, int n, int ld, Grp g) {
+  for (int j = 0; j < n; j++) {
+    real sj = 0, s0 = 0, s1 = 0; int i0 = g.lane, i1 = g.lane + RSB_LANES;
+    if (i0 >= j && i0 < n) { s0 = A[i0 * ld + j]; for (int k = 0; k < j; k++) s0 -= A[i0 * ld + k] * A[j * ld + k]; }
+    if (i1 >= j && i1 < n) { s1 = A[i1 * ld + j]; for (int k = 0; k < j; k++) s1 -= A[i1 * ld + k] * A[j * ld + k]; }
+    sj = gshfl(g, (j < RSB_LANES) ? s0 : s1, j % RSB_LANES);
+    real inv = sj > 1e-30f ? rsb_rsqrt(sj) : 0.0f, diag = sj > 1e-30f ? sj * inv : 1e30f;
+    if (i0 >= j && i0 < n) A[i0 * ld + j] = (i0 == j) ? diag : s0 * inv;
+    if (i1 >= j && i1 < n) A[i1 * ld + j] = (i1 == j) ? diag : s1 * inv;
+    gsync(g);
+  }
+}
+/* x <- A^-1 x with A = L L^T; x is a shared-memory vector of length n; result visible to all lanes on return */
+RSB_DN void chol_solve(const real *L, int n, int ld, real *x, Grp g) {
+  int i0 = g.lane, i1 = g.lane + RSB_LANES;
+  real b0 = i0 < n ? x[i0] : 0, b1 = i1 < n ? x[i1] : 0;
+  for (int k = 0; k < n; k++) {
+    real mine = (k < RSB_LANES) ? b0 : b1; real xk = gshfl(g, mine, k % RSB_LANES) / L[k * ld + k];
+    if (i0 == k) b0 = xk; if (i1 == k) b1 = xk;
+    if (i0 > k && i0 < n) b0 -= L[i0 * ld + k] * xk;
+    if (i1 > k && i1 < n) b1 -= L[i1 * ld + k] * xk;
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    real mine = (k < RSB_LANES) ? b0 : b1; real xk = gshfl(g, mine, k % RSB_LANES) / L[k * ld + k];
+    if (i0 == k) b0 = xk; if (i1 == k) b1 = xk;
+    if (i0 < k) b0 -= L[k * ld + i0] * xk;
+    if (i1 < k) b1 -= L[k * ld + i1] * xk;
+  }
+  if (i0 < n) x[i0] = b0; if (i1 < n) x[i1] = b1;
+  gsync(g);
+}
+
+/* ================================================================== A.2 controllers */
+/* controller state words per robot (RSB_CS_WORDS): goal_pos3 goal_ori9 initial_joint7 grip_cur2 goal_vel7 summed_err7 last_err7
+   derr_buf35 derr_n derr_ptr saturated */
+#define CS_GOALPOS 0
+#define CS_GOALORI 3
+#define CS_INITJ 12
+#define CS_GRIP 19
+#define CS_GOALVEL 21
+#define CS_SUMERR 28
+#define CS_LASTERR 35
+#define CS_DERR 42
+#define CS_DERRN 77
+#define CS_DERRPTR 78
+#define CS_SAT 79
+
+RSB_D real scale_action(const DevRobot &rb, int k, real a) {
+  real lo = rb.in_min[k], hi = rb.in_max[k]; a = clampf(a, lo, hi);
+  real sc = fabsf(rb.out_max[k] - rb.out_min[k]) / fabsf(hi - lo);
+  return (a - 0.5f * (hi + lo)) * sc + 0.5f * (rb.out_max[k] + rb.out_min[k]);
+}
+
+RSB_DN void ctrl_reset(const DevModel &m, real *s, Grp g) {
+  const real *qpos = s + m.o_qpos, *sxpos = s + m.o_sxpos, *sxmat = s + m.o_sxmat;
+  for (int ri = 0; ri < m.nrobot; ri++) {
+    const DevRobot &rb = m.robot[ri]; real *cs = s + m.o_cs + ri * RSB_CS_WORDS;
+    for (int k = g.lane; k < RSB_CS_WORDS; k += RSB_LANES) {
+      real v = 0;
+      if (k < 3) v = sxpos[3 * rb.eef_site + k];
+      else if (k < 12) v = sxmat[9 * rb.eef_site + k - 3];
+      else if (k < 19) v = qpos[rb.arm_qadr[k - 12]];
+      cs[k] = v;
+    }
+  }
+  gsync(g);
+}
+
+RSB_DN void ctrl_set_goal(const DevModel &m, real *s, Grp g) {
+  const real *act = s + m.o_act, *sxpos = s + m.o_sxpos, *sxmat = s + m.o_sxmat;
+  if (g.lane < m.nrobot) {
+    int ri = g.lane; const DevRobot &rb = m.robot[ri]; real *cs = s + m.o_cs + ri * RSB_CS_WORDS; const real *a = act + rb.act_off;
+    if (rb.ctrl_type == RSB_CTRL_OSC_POSE || rb.ctrl_type == RSB_CTRL_OSC_POSITION) {
+      real d[6] = {0, 0, 0, 0, 0, 0}; for (int k = 0; k < rb.control_dim; k++) d[k] = scale_action(rb, k, a[k]);
+      if (rb.ctrl_type == RSB_CTRL_OSC_POSE && (d[3] != 0 || d[4] != 0 || d[5] != 0)) {
+        real ang = sqrtf(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]), q[4], Rm[9], Rg[9];
+        if (ang < RSB_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
+        else { real sn, c; rsb_sincos(0.5f * ang, &sn, &c); real f = sn / ang; q[0] = c; q[1] = f * d[3]; q[2] = f * d[4]; q[3] = f * d[5]; }
+        quat2mat(Rm, q); matmul3(Rg, Rm, sxmat + 9 * rb.eef_site);
+        for (int k = 0; k < 9; k++) cs[CS_GOALORI + k] = Rg[k];
+      }
+      for (int k = 0; k < 3; k++) cs[CS_GOALPOS + k] = sxpos[3 * rb.eef_site + k] + d[k];
+    } else if (rb.ctrl_type == RSB_CTRL_JOINT_VELOCITY) {
+      for (int k = 0; k < RSB_ARM_DOF; k++) { real v = scale_action(rb, k, a[k]); if (rb.has_vl) v = clampf(v, rb.vl_lo[k], rb.vl_hi[k]); cs[CS_GOALVEL + k] = v; }
+    } else { for (int k = 0; k < RSB_ARM_DOF; k++) cs[CS_GOALVEL + k] = scale_action(rb, k, a[k]); }
+  }
+  gsync(g);
+}
+
+/* serial 7x7 triangular solves on one lane (fully unrolled: x stays in registers) */
+RSB_D void chol7_solve_reg(const real *L, real *x) {
+#pragma unroll
+  for (int i = 0; i < 7; i++) { real v = x[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) v -= L[i * 7 + k] * x[k]; x[i] = v / L[i * 7 + i]; }
+#pragma unroll
+  for (int i = 6; i >= 0; i--) { real v = x[i];
+#pragma unroll
+    for (int k = i + 1; k < 7; k++) v -= L[k * 7 + i] * x[k]; x[i] = v / L[i * 7 + i]; }
+}
+/* solve the symmetric 3x3 system A x = b (A given with leading dim ld); x = 0 when A is singular */
+RSB_D void sym3_solve(const real *A, int ld, const real *b, real *x) {
+  real a = A[0], bq = A[1], c = A[2], d = A[ld + 1], e = A[ld + 2], f = A[2 * ld + 2];
+  real c00 = d * f - e * e, c01 = c * e - bq * f, c02 = bq * e - c * d, det = a * c00 + bq * c01 + c * c02;
+  real sc = fmaxf(fmaxf(fabsf(a), fabsf(d)), fabsf(f));
+  if (fabsf(det) <= 1e-18f * sc * sc * sc || !(det == det)) { x[0] = x[1] = x[2] = 0; return; }
+  real id = 1.0f / det, c11 = a * f - c * c, c12 = bq * c - a * e, c22 = a * d - bq * bq;
+  x[0] = (c00 * b[0] + c01 * b[1] + c02 * b[2]) * id; x[1] = (c01 * b[0] + c11 * b[1] + c12 * b[2]) * id; x[2] = (c02 * b[0] + c12 * b[1] + c22 * b[2]) * id;
+}
+
+/* scratch layout for the OSC law (floats, in o_cscr): Jee[42] Lm[49] X[42] A[36](ld 6) F[6] pose[7] y[6] w[6] v6[6] tau[7] */
+RSB_DN void ctrl_run(const DevModel &m, real *s, Grp g) {
+  const real *qpos = s + m.o_qpos, *qvel = s + m.o_qvel, *cdof = s + m.o_cdof, *M = s + m.o_M, *bias = s + m.o_bias;
+  const real *sxpos = s + m.o_sxpos, *sxmat = s + m.o_sxmat, *xpos = s + m.o_xpos, *cvel = s + m.o_cvel;
+  real *ctrl = s + m.o_ctrl; real *scr = s + m.o_cscr;
+  real *Jee = scr, *Lm = scr + 42, *X = scr + 91, *A = scr + 133, *F = scr + 169, *pose = scr + 175, *y = scr + 182, *w = scr + 188, *v6 = scr + 194, *tau = scr + 200;
+  for (int ri = 0; ri < m.nrobot; ri++) {
+    const DevRobot &rb = m.robot[ri]; real *cs = s + m.o_cs + ri * RSB_CS_WORDS;
+    if (rb.ctrl_type == RSB_CTRL_OSC_POSE || rb.ctrl_type == RSB_CTRL_OSC_POSITION) {
+      int sb = m.site_body[rb.eef_site], root = m.body_root[sb]; const real *ep = sxpos + 3 * rb.eef_site;
+      real off[3] = {ep[0] - xpos[3 * root], ep[1] - xpos[3 * root + 1], ep[2] - xpos[3 * root + 2]};
+      if (g.lane < RSB_ARM_DOF) {                    /* site Jacobian, arm columns */
+        int c = g.lane, d = rb.arm_dadr[c]; real t[3] = {0, 0, 0}, wv[3] = {0, 0, 0}, lv[3] = {0, 0, 0};
+        if ((m.body_dofmask[sb] >> d) & 1) { cross3(t, cdof + 6 * d, off); wv[0] = cdof[6 * d]; wv[1] = cdof[6 * d + 1]; wv[2] = cdof[6 * d + 2];
+          lv[0] = cdof[6 * d + 3] + t[0]; lv[1] = cdof[6 * d + 4] + t[1]; lv[2] = cdof[6 * d + 5] + t[2]; }
+        for (int r = 0; r < 3; r++) { Jee[r * 7 + c] = lv[r]; Jee[(3 + r) * 7 + c] = wv[r]; }
+      }
+      for (int i = g.lane; i < 49; i += RSB_LANES) { int r = i / 7, c = i - 7 * r; Lm[i] = M[rb.arm_dadr[r] * m.ldm + rb.arm_dadr[c]]; }
+      if (g.lane == 8) {                             /* site velocity = full Jacobian x qvel = body twist moved to the site */
+        const real *cv = cvel + 6 * sb; real t[3]; cross3(t, cv, off);
+        v6[0] = cv[3] + t[0]; v6[1] = cv[4] + t[1]; v6[2] = cv[5] + t[2]; v6[3] = cv[0]; v6[4] = cv[1]; v6[5] = cv[2];
+      }
+      if (g.lane >= 9 && g.lane < 16) { int k = g.lane - 9; real kn = rb.null_kp; pose[k] = kn * (cs[CS_INITJ + k] - qpos[rb.arm_qadr[k]]) - 2 * sqrtf(kn) * qvel[rb.arm_dadr[k]]; }
+      gsync(g);
+      chol_factor(Lm, 7, 7, g);
+      if (g.lane < 6) {                              /* X[r][:] = M^-1 J[r][:]^T */
+        real x[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) x[k] = Jee[g.lane * 7 + k];
+        chol7_solve_reg(Lm, x);
+#pragma unroll
+        for (int k = 0; k < 7; k++) X[g.lane * 7 + k] = x[k];
+      } else if (g.lane == 6) {                      /* desired wrench */
+        const real *Rc = sxmat + 9 * rb.eef_site, *Rd = cs + CS_GOALORI; real eo[3] = {0, 0, 0};
+        for (int k = 0; k < 3; k++) { real a[3] = {Rc[k], Rc[3 + k], Rc[6 + k]}, b[3] = {Rd[k], Rd[3 + k], Rd[6 + k]}, x3[3]; cross3(x3, a, b); eo[0] += 0.5f * x3[0]; eo[1] += 0.5f * x3[1]; eo[2] += 0.5f * x3[2]; }
+        for (int k = 0; k < 3; k++) { F[k] = rb.kp[k] * (cs[CS_GOALPOS + k] - ep[k]) - rb.kd[k] * v6[k]; F[3 + k] = rb.kp[3 + k] * eo[k] - rb.kd[3 + k] * v6[3 + k]; }
+      } else if (g.lane == 7) {                      /* y = J pose */
+        for (int r = 0; r < 6; r++) { real acc = 0; for (int k = 0; k < 7; k++) acc += Jee[r * 7 + k] * pose[k]; y[r] = acc; }
+      }
+      gsync(g);
+      for (int i = g.lane; i < 36; i += RSB_LANES) { int r = i / 6, c = i - 6 * r; real acc = 0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) acc += X[r * 7 + k] * Jee[c * 7 + k]; A[i] = acc; }
+      gsync(g);
+      if (g.lane == 0) {                             /* decoupled task-space inertia applied to the wrench */
+        if (rb.uncouple) { sym3_solve(A, 6, F, w); sym3_solve(A + 21, 6, F + 3, w + 3); }
+      }
+      gsync(g);
+      chol_factor(A, 6, 6, g);
+      chol_solve(A, 6, 6, y, g);                     /* y = Lambda_full J pose */
+      if (!rb.uncouple) { chol_solve(A, 6, 6, F, g); if (g.lane < 6) w[g.lane] = F[g.lane]; gsync(g); }
+      if (g.lane < RSB_ARM_DOF) {
+        int c = g.lane; real t = bias[rb.arm_dadr[c]];
+        for (int r = 0; r < 6; r++) t += Jee[r * 7 + c] * (w[r] - y[r]);
+        for (int k = 0; k < 7; k++) t += M[rb.arm_dadr[c] * m.ldm + rb.arm_dadr[k]] * pose[k];
+        tau[c] = t;
+      }
+    } else if (rb.ctrl_type == RSB_CTRL_JOINT_VELOCITY) {
+      int ptr = (int)cs[CS_DERRPTR], nfill = (int)cs[CS_DERRN], satur = (int)cs[CS_SAT]; int nn = nfill < 5 ? nfill + 1 : 5;
+      real raw = 0, t = 0; int sat = 0;
+      if (g.lane < RSB_ARM_DOF) {
+        int k = g.lane; real err = cs[CS_GOALVEL + k] - qvel[rb.arm_dadr[k]];
+        cs[CS_DERR + ptr * 7 + k] = err - cs[CS_LASTERR + k]; cs[CS_LASTERR + k] = err;
+        real avg = 0; for (int i = 0; i < 5; i++) avg += cs[CS_DERR + i * 7 + k] / (real)nn;
+        real se = cs[CS_SUMERR + k]; if (!satur) { se += err; cs[CS_SUMERR + k] = se; }
+        raw = rb.kp[k] * err + rb.ki[k] * se + rb.kd[k] * avg + bias[rb.arm_dadr[k]];
+        t = clampf(raw, rb.tl_lo[k], rb.tl_hi[k]); sat = (t != raw); tau[k] = t;
+      }
+      sat = gsum_i(g, sat);
+      gsync(g);
+      if (g.lane == 0) { cs[CS_DERRPTR] = (real)((ptr + 1) % 5); cs[CS_DERRN] = (real)nn; cs[CS_SAT] = sat ? 1.0f : 0.0f; }
+    } else {
+      if (g.lane < RSB_ARM_DOF) tau[g.lane] = cs[CS_GOALVEL + g.lane] + bias[rb.arm_dadr[g.lane]];
+    }
+    gsync(g);
+    if (g.lane < RSB_ARM_DOF) { int k = g.lane; real t = clampf(tau[k], rb.tl_lo[k], rb.tl_hi[k]); tau[k] = t; ctrl[rb.arm_act[k]] = t; }
+    /* gripper: integrate the binary open/close command (robosuite Gripper.format_action) */
+    if (rb.grip_action_dim > 0 && g.lane >= 16 && g.lane < 16 + rb.grip_ndof) {
+      int k = g.lane - 16; real ga = s[m.o_act + rb.act_off + rb.control_dim]; real sg = ga > 0 ? 1.0f : (ga < 0 ? -1.0f : 0.0f);
+      real v = clampf(cs[CS_GRIP + k] + rb.grip_sign[k] * rb.grip_speed * sg, -1.0f, 1.0f); cs[CS_GRIP + k] = v;
+      int a = rb.grip_act[k]; real lo = m.act_crange[2 * a], hi = m.act_crange[2 * a + 1];
+      ctrl[a] = 0.5f * (hi + lo) + 0.5f * (hi - lo) * v;
+    }
+    gsync(g);
+    /* keep the last torques for debugging/parity: cscr[208 + 7*ri ...] */
+    if (g.lane < RSB_ARM_DOF) scr[208 + 7 * ri + g.lane] = tau[g.lane];
+    gsync(g);
+  }
+}
+
+/* ================================================================== actuation + smooth acceleration */
+RSB_DN void st_actuation(const DevModel &m, real *s, Grp g) {
+  const real *qpos = s + m.o_qpos, *qvel = s + m.o_qvel, *ctrl = s + m.o_ctrl, *bias = s + m.o_bias, *passive = s + m.o_passive, *M = s + m.o_M;
+  real *actf = s + m.o_actuator, *smooth = s + m.o_smooth, *qas = s + m.o_qacc_smooth, *L = s + m.o_L;
+  for (int d = g.lane; d < m.nv; d += RSB_LANES) {
+    real f = 0;
+    for (int a = 0; a < m.nu; a++) if (m.act_dof[a] == d) {
+      real c = ctrl[a]; if (m.act_climited[a]) c = clampf(c, m.act_crange[2 * a], m.act_crange[2 * a + 1]);
+      int qa = m.jnt_qadr[m.dof_jnt[d]]; real gear = m.act_gear[a], len = qpos[qa] * gear, vel = qvel[d] * gear;
+      real fa = m.act_gain[a] * c + m.act_bias[3 * a] + m.act_bias[3 * a + 1] * len + m.act_bias[3 * a + 2] * vel;
+      if (m.act_flimited[a]) fa = clampf(fa, m.act_frange[2 * a], m.act_frange[2 * a + 1]);
+      f += gear * fa;
+    }
+    actf[d] = f; real sm = passive[d] - bias[d] + f; smooth[d] = sm; qas[d] = sm;
+  }
+  for (int i = g.lane; i < m.nv * m.ldm; i += RSB_LANES) L[i] = M[i];
+  gsync(g);
+  chol_factor(L, m.nv, m.ldm, g);
+  chol_solve(L, m.nv, m.ldm, qas, g);
+}
+
+/* ================================================================== A.3.7 constraint solver (Newton, exact line search) */
+struct LsAcc { real cost, d1, d2; };
+
+/* Evaluate the constraint cost of this lane's rows at x = jar + alpha*Jv.
+   mode 0: cost only; mode 1: cost + force + Hessian weights (ew, Hc); mode 2: cost + line-search derivatives. */
+RSB_D void efc_eval(const DevModel &m, real *s, Grp g, int nefc, real alpha, int mode, LsAcc *acc) {
+  const real *con = s + m.o_con, *eD = s + m.o_eD, *eR = s + m.o_eR, *efloss = s + m.o_efloss, *jar = s + m.o_ejar, *Jv = s + m.o_eJv;
+  real *force = s + m.o_eforce, *ew = s + m.o_ew, *Hc = s + m.o_Hc; const int *etype = (const int *)(s + m.o_etype), *eid = (const int *)(s + m.o_eid);
+  real cost = 0, d1 = 0, d2 = 0;
+  for (int r = g.lane; r < nefc; r += RSB_LANES) {
+    int type = etype[r]; real D = eD[r];
+    if (type == EFC_CONTACT_FRICTION) continue;
+    real dx = (mode == 2) ? Jv[r] : 0, x = jar[r] + alpha * dx;
+    if (type == EFC_FRICTION) {
+      real fl = efloss[r], rf = eR[r] * fl;
+      if (x <= -rf) { cost += -0.5f * rf * fl - fl * x; d1 += -fl * dx; if (mode == 1) { force[r] = fl; ew[r] = 0; } }
+      else if (x >= rf) { cost += -0.5f * rf * fl + fl * x; d1 += fl * dx; if (mode == 1) { force[r] = -fl; ew[r] = 0; } }
+      else { cost += 0.5f * D * x * x; d1 += D * x * dx; d2 += D * dx * dx; if (mode == 1) { force[r] = -D * x; ew[r] = D; } }
+      continue;
+    }
+    const real *cr = con + eid[r] * RSB_CONW; int dim = (type == EFC_LIMIT) ? 1 : ((const int *)cr)[CON_DIM];
+    if (dim == 1) {
+      if (x < 0) { cost += 0.5f * D * x * x; d1 += D * x * dx; d2 += D * dx * dx; if (mode == 1) { force[r] = -D * x; ew[r] = D; } }
+      else if (mode == 1) { force[r] = 0; ew[r] = 0; }
+      continue;
+    }
+    /* elliptic cone, dim in {3, 4} */
+    const real *fr = m.pair_friction + 5 * ((const int *)cr)[CON_PAIR]; real mu = cr[CON_MU];
+    real sc[RSB_MAXDIM], U[RSB_MAXDIM], dU[RSB_MAXDIM], xs[RSB_MAXDIM], dxs[RSB_MAXDIM]; sc[0] = mu; real T2 = 0;
+#pragma unroll
+    for (int j = 0; j < RSB_MAXDIM; j++) if (j < dim) {
+      if (j > 0) sc[j] = fr[j - 1];
+      real dxj = (mode == 2) ? Jv[r + j] : 0; dxs[j] = dxj; xs[j] = jar[r + j] + alpha * dxj; U[j] = xs[j] * sc[j]; dU[j] = dxj * sc[j];
+      if (j > 0) T2 += U[j] * U[j];
+    }
+    real N = U[0], T = sqrtf(T2);
+    if (N >= mu * T || (T <= 0 && N >= 0)) {                         /* top zone: separated / inside the dual cone */
+      if (mode == 1) { for (int j = 0; j < dim; j++) { force[r + j] = 0; ew[r + j] = 0; } }
+    } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {              /* bottom zone: plain quadratic */
+#pragma unroll
+      for (int j = 0; j < RSB_MAXDIM; j++) if (j < dim) {
+        real Dj = eD[r + j], dxj = dxs[j]; cost += 0.5f * Dj * xs[j] * xs[j]; d1 += Dj * xs[j] * dxj; d2 += Dj * dxj * dxj;
+        if (mode == 1) { force[r + j] = -Dj * xs[j]; ew[r + j] = Dj; }
+      }
+    } else {                                                         /* middle zone: cone surface */
+      real Dm = D / (mu * mu * (1 + mu * mu)), NmT = N - mu * T;
+      cost += 0.5f * Dm * NmT * NmT;
+      real gU[RSB_MAXDIM]; gU[0] = Dm * NmT;
+#pragma unroll
+      for (int j = 1; j < RSB_MAXDIM; j++) if (j < dim) gU[j] = -Dm * mu * NmT * U[j] / T;
+      if (mode == 1) { for (int j = 0; j < dim; j++) { force[r + j] = -gU[j] * sc[j]; ew[r + j] = -1.0f; } }     /* ew < 0 marks "use the cone block" */
+      if (mode >= 1) {
+        real *hc = Hc + eid[r] * 16; real invT = 1.0f / T;
+#pragma unroll
+        for (int a = 0; a < RSB_MAXDIM; a++)
+#pragma unroll
+          for (int b = 0; b < RSB_MAXDIM; b++) if (a < dim && b < dim) {
+            real h;
+            if (a == 0 && b == 0) h = Dm;
+            else if (a == 0 || b == 0) h = -Dm * mu * U[a + b] * invT;
+            else h = Dm * mu * mu * U[a] * U[b] * invT * invT - Dm * mu * NmT * ((a == b ? invT : 0.0f) - U[a] * U[b] * invT * invT * invT);
+            if (mode == 1) hc[a * 4 + b] = h * sc[a] * sc[b];
+            else d2 += dU[a] * h * dU[b];
+          }
+        if (mode == 2) { for (int j = 0; j < dim; j++) d1 += gU[j] * dU[j]; }
+      }
+    }
+  }
+  acc->cost = cost; acc->d1 = d1; acc->d2 = d2;
+}
+
+/* jar = J qacc - aref (lane per row); returns the total cost (Gauss + constraint), identical on all lanes */
+RSB_D real solver_cost(const DevModel &m, real *s, Grp g, int nefc, const real *qacc) {
+  const real *J = s + m.o_J, *earef = s + m.o_earef, *M = s + m.o_M, *qas = s + m.o_qacc_smooth; real *jar = s + m.o_ejar;
+  for (int r = g.lane; r < nefc; r += RSB_LANES) { real a = -earef[r]; for (int d = 0; d < m.nv; d++) a += J[r * m.ldj + d] * qacc[d]; jar[r] = a; }
+  real gs = 0;
+  for (int i = g.lane; i < m.nv; i += RSB_LANES) { real md = 0; for (int j = 0; j < m.nv; j++) md += M[i * m.ldm + j] * (qacc[j] - qas[j]); gs += 0.5f * (qacc[i] - qas[i]) * md; }
+  gsync(g);
+  LsAcc a; efc_eval(m, s, g, nefc, 0.0f, 0, &a);
+  return gsum(g, gs + a.cost);
+}
+
+RSB_DN void st_solve(const DevModel &m, real *s, Grp g) {
+  int *misc = (int *)(s + m.o_misc); const int nefc = misc[MISC_NEFC], nv = m.nv, ldm = m.ldm, ldj = m.ldj;
+  real *qacc = s + m.o_qacc, *qas = s + m.o_qacc_smooth, *warm = s + m.o_warm, *qfc = s + m.o_qfc, *grad = s + m.o_grad, *search = s + m.o_search, *Mv = s + m.o_Mv, *tmpv = s + m.o_tmpv;
+  const real *M = s + m.o_M, *J = s + m.o_J; real *H = s + m.o_L, *force = s + m.o_eforce, *ew = s + m.o_ew, *Jv = s + m.o_eJv, *jar = s + m.o_ejar, *Hc = s + m.o_Hc;
+  const real *con = s + m.o_con;
+  if (nefc == 0) {
+    for (int d = g.lane; d < nv; d += RSB_LANES) { qacc[d] = qas[d]; qfc[d] = 0; }
+    if (g.lane == 0) misc[MISC_ITER] = 0;
+    gsync(g); return;
+  }
+  /* warm start: the cheaper of qacc_warmstart and qacc_smooth */
+  real cw = solver_cost(m, s, g, nefc, warm); gsync(g);
+  real cs0 = solver_cost(m, s, g, nefc, qas); gsync(g);
+  for (int d = g.lane; d < nv; d += RSB_LANES) { qacc[d] = (cw < cs0) ? warm[d] : qas[d]; tmpv[d] = 0; }
+  gsync(g);
+  const real scale = 1.0f / (m.meaninertia * (real)(nv > 1 ? nv : 1));
+  int iter = 0;
+  for (; iter < m.solver_iters; iter++) {
+    /* residual rows, forces, Hessian weights */
+    for (int r = g.lane; r < nefc; r += RSB_LANES) { real a = -(s + m.o_earef)[r]; for (int d = 0; d < nv; d++) a += J[r * ldj + d] * qacc[d]; jar[r] = a; }
+    gsync(g);
+    LsAcc acc; efc_eval(m, s, g, nefc, 0.0f, 1, &acc);
+    gsync(g);
+    /* gradient = M qacc - M qacc_smooth - J^T f  (lane per dof) */
+    real gn = 0;
+    for (int d = g.lane; d < nv; d += RSB_LANES) {
+      real a = 0; for (int j = 0; j < nv; j++) a += M[d * ldm + j] * (qacc[j] - qas[j]);    /* difference first: exact 0 on unconstrained dofs */
+      real f = 0; for (int r = 0; r < nefc; r++) f += J[r * ldj + d] * force[r];
+      a -= f; grad[d] = a; qfc[d] = f; gn += a * a;
+    }
+    gn = gsum(g, gn);
+#ifdef RSB_EMU_TRACE
+    if (g.lane == 0) printf("  it %d scaled|grad| %.3e\n", iter, scale * sqrtf(gn));
+#endif
+    if (scale * sqrtf(gn) < m.solver_tol) break;
+    /* H = M + J^T W J (+ cone blocks), lower triangle, lanes over entries */
+    for (int e = g.lane; e < nv * nv; e += RSB_LANES) {
+      int i = e / nv, j = e - i * nv; if (j > i) continue;
+      real h = M[i * ldm + j];
+      for (int r = 0; r < nefc; r++) { real wv = ew[r]; if (wv > 0) h += wv * J[r * ldj + i] * J[r * ldj + j]; }
+      H[i * ldm + j] = h;
+    }
+    gsync(g);
+    for (int c = 0; c < misc[MISC_NCON]; c++) {
+      const int *ci = (const int *)(con + c * RSB_CONW); int adr = ci[CON_ADR]; if (adr < 0 || !(ew[adr] < 0)) continue;
+      int dim = ci[CON_DIM]; const real *hc = Hc + c * 16;
+      for (int e = g.lane; e < nv * nv; e += RSB_LANES) {
+        int i = e / nv, j = e - i * nv; if (j > i) continue;
+        real h = 0;
+        for (int a = 0; a < dim; a++) { real ja = J[(adr + a) * ldj + i]; if (ja != 0) for (int b = 0; b < dim; b++) h += hc[a * 4 + b] * ja * J[(adr + b) * ldj + j]; }
+        H[i * ldm + j] += h;
+      }
+    }
+    gsync(g);
+    chol_factor(H, nv, ldm, g);
+    for (int d = g.lane; d < nv; d += RSB_LANES) search[d] = -grad[d];
+    gsync(g);
+    chol_solve(H, nv, ldm, search, g);
+    /* directional quantities */
+    real gq1 = 0, gq2 = 0;
+    for (int d = g.lane; d < nv; d += RSB_LANES) { real a = 0; for (int j = 0; j < nv; j++) a += M[d * ldm + j] * search[j]; Mv[d] = a; gq2 += search[d] * a; gq1 += search[d] * (grad[d] + qfc[d]); }
+    for (int r = g.lane; r < nefc; r += RSB_LANES) { real a = 0; for (int d = 0; d < nv; d++) a += J[r * ldj + d] * search[d]; Jv[r] = a; }
+    gq1 = gsum(g, gq1); gq2 = gsum(g, gq2);           /* gq1 = s.(M a - M a_s): slope of the Gauss term at alpha = 0 */
+    gsync(g);
+    /* exact line search on the convex 1-D cost: safeguarded Newton on its derivative */
+    real lo = 0, hi = -1, alpha = 0, d1_0 = 0;
+    for (int it = 0; it < m.ls_iters; it++) {
+      LsAcc v; efc_eval(m, s, g, nefc, alpha, 2, &v);
+      real d1 = gq1 + alpha * gq2 + gsum(g, v.d1), d2 = gq2 + gsum(g, v.d2);
+      if (it == 0) d1_0 = fabsf(d1);
+#ifdef RSB_EMU_TRACE
+      if (g.lane == 0) printf("    ls %d alpha %.6g d1 %.3e d2 %.3e\n", it, alpha, d1, d2);
+#endif
+      if (fabsf(d1) <= 1e-4f * d1_0 + 1e-30f && it > 0) break;
+      if (it == 0 && !(d1 < -1e-10f / scale)) break;  /* Newton decrement below tolerance (or fp32 noise): converged */
+      if (d1 < 0) lo = alpha; else hi = alpha;
+      real an = d2 > RSB_MINVAL ? alpha - d1 / d2 : alpha;
+      if (hi >= 0 && (an <= lo || an >= hi)) an = 0.5f * (lo + hi);
+      else if (hi < 0 && an <= lo) an = lo > 0 ? 2 * lo : 1.0f;
+      if (an == alpha) break;
+      alpha = an;
+    }
+    if (alpha == 0) break;
+    for (int d = g.lane; d < nv; d += RSB_LANES) qacc[d] += alpha * search[d];
+    gsync(g);
+  }
+  if (iter == m.solver_iters) {                       /* forces must correspond to the final qacc */
+    for (int r = g.lane; r < nefc; r += RSB_LANES) { real a = -(s + m.o_earef)[r]; for (int d = 0; d < nv; d++) a += J[r * ldj + d] * qacc[d]; jar[r] = a; }
+    gsync(g);
+    LsAcc acc; efc_eval(m, s, g, nefc, 0.0f, 1, &acc);
+    gsync(g);
+    for (int d = g.lane; d < nv; d += RSB_LANES) { real f = 0; for (int r = 0; r < nefc; r++) f += J[r * ldj + d] * force[r]; qfc[d] = f; }
+  }
+  if (g.lane == 0) misc[MISC_ITER] = iter;
+  gsync(g);
+}
+
+/* ================================================================== A.3.8 semi-implicit Euler with implicit joint damping */
+RSB_DN void st_euler(const DevModel &m, real *s, Grp g) {
+  real *qpos = s + m.o_qpos, *qvel = s + m.o_qvel, *warm = s + m.o_warm, *L = s + m.o_L, *tmpv = s + m.o_tmpv;
+  const real *M = s + m.o_M, *qacc = s + m.o_qacc, *smooth = s + m.o_smooth, *qfc = s + m.o_qfc; const real h = m.timestep;
+  if (m.any_damping) {
+    for (int i = g.lane; i < m.nv * m.ldm; i += RSB_LANES) { int r = i / m.ldm, c = i - r * m.ldm; L[i] = M[i] + ((r == c) ? h * m.dof_damping[r] : 0.0f); }
+    for (int d = g.lane; d < m.nv; d += RSB_LANES) tmpv[d] = smooth[d] + qfc[d];
+    gsync(g);
+    chol_factor(L, m.nv, m.ldm, g);
+    chol_solve(L, m.nv, m.ldm, tmpv, g);
+  } else { for (int d = g.lane; d < m.nv; d += RSB_LANES) tmpv[d] = qacc[d]; gsync(g); }
+  for (int d = g.lane; d < m.nv; d += RSB_LANES) { qvel[d] += h * tmpv[d]; warm[d] = qacc[d]; }
+  gsync(g);
+  for (int j = g.lane; j < m.njnt; j += RSB_LANES) {
+    int qa = m.jnt_qadr[j], d = m.jnt_dadr[j];
+    if (m.jnt_type[j] == RSB_JNT_FREE) {
+      for (int k = 0; k < 3; k++) qpos[qa + k] += h * qvel[d + k];
+      real w[3] = {qvel[d + 3], qvel[d + 4], qvel[d + 5]}; real wn = sqrtf(dot3(w, w)), ang = wn * h;
+      if (ang > 0) { real sn, c; rsb_sincos(0.5f * ang, &sn, &c); real f = sn / wn; real dq[4] = {c, f * w[0], f * w[1], f * w[2]}, qn[4];
+        quatmul(qn, qpos + qa + 3, dq); quatnorm(qn); qpos[qa + 3] = qn[0]; qpos[qa + 4] = qn[1]; qpos[qa + 5] = qn[2]; qpos[qa + 6] = qn[3]; }
+    } else qpos[qa] += h * qvel[d];
+  }
+  gsync(g);
+}
+
+/* ================================================================== one physics substep, the control step, reward, observation */
+RSB_D void fwd_position(const DevModel &m, real *s, Grp g) { st_kinematics(m, s, g); st_inertia(m, s, g); st_crb(m, s, g); st_collision(m, s, g); }
+
+RSB_D void substep(const DevModel &m, real *s, Grp g, bool policy_step) {
+  fwd_position(m, s, g); st_bias(m, s, g); st_constraint(m, s, g);
+  if (policy_step) ctrl_set_goal(m, s, g);
+  ctrl_run(m, s, g);
+  st_actuation(m, s, g); st_solve(m, s, g); st_euler(m, s, g);
+}
+
+RSB_D bool geom_in(const int *set, int n, int gm) { for (int i = 0; i < n; i++) if (set[i] == gm) return true; return false; }
+RSB_D bool check_grasp(const DevModel &m, const real *s, int ri, int obj_geom) {
+  const DevRobot &rb = m.robot[ri]; const real *con = s + m.o_con; int ncon = ((const int *)(s + m.o_misc))[MISC_NCON]; bool tl = false, tr = false;
+  for (int c = 0; c < ncon; c++) {
+    const int *ci = (const int *)(con + c * RSB_CONW); int g1 = ci[CON_G1], g2 = ci[CON_G2];
+    if ((geom_in(rb.lfg, rb.nlfg, g1) && g2 == obj_geom) || (geom_in(rb.lfg, rb.nlfg, g2) && g1 == obj_geom)) tl = true;
+    if ((geom_in(rb.rfg, rb.nrfg, g1) && g2 == obj_geom) || (geom_in(rb.rfg, rb.nrfg, g2) && g1 == obj_geom)) tr = true;
+  }
+  return tl && tr;
+}
+
+/* A.6 staged task rewards (evaluated by every lane identically; cheap) */
+RSB_DN real task_reward(const DevModel &m, const real *s) {
+  const real *xpos = s + m.o_xpos, *sxpos = s + m.o_sxpos, *qpos = s + m.o_qpos; real r = 0;
+  const real *eef = sxpos + 3 * m.robot[0].eef_site;
+  if (m.task_id == RSB_TASK_LIFT) {
+    const real *cube = xpos + 3 * m.obj_body[0];
+    if (cube[2] > m.table_height + 0.04f) r = 2.25f;
+    else if (m.reward_shaping) {
+      real d[3] = {eef[0] - cube[0], eef[1] - cube[1], eef[2] - cube[2]}; r += 1 - tanhf(10.0f * sqrtf(dot3(d, d)));
+      if (check_grasp(m, s, 0, m.obj_geom[0])) r += 0.25f;
+    }
+    return r * m.reward_scale / 2.25f;
+  }
+  if (m.task_id == RSB_TASK_STACK) {
+    const real *A = xpos + 3 * m.obj_body[0], *B = xpos + 3 * m.obj_body[1];
+    real d[3] = {eef[0] - A[0], eef[1] - A[1], eef[2] - A[2]}; real dist = sqrtf(dot3(d, d));
+    bool grasp = check_grasp(m, s, 0, m.obj_geom[0]);
+    real r_reach = (1 - tanhf(10.0f * dist)) * 0.25f + (grasp ? 0.25f : 0.0f);
+    bool lifted = A[2] > m.table_height + 0.04f; real r_lift = lifted ? 1.0f : 0.0f;
+    if (lifted) { real hd = sqrtf((A[0] - B[0]) * (A[0] - B[0]) + (A[1] - B[1]) * (A[1] - B[1])); r_lift += 0.5f * (1 - tanhf(hd)); }
+    bool touch = false; const real *con = s + m.o_con; int ncon = ((const int *)(s + m.o_misc))[MISC_NCON];
+    for (int c = 0; c < ncon; c++) { const int *ci = (const int *)(con + c * RSB_CONW); int g1 = ci[CON_G1], g2 = ci[CON_G2];
+      if ((g1 == m.obj_geom[0] && g2 == m.obj_geom[1]) || (g2 == m.obj_geom[0] && g1 == m.obj_geom[1])) touch = true; }
+    real r_stack = (!grasp && r_lift > 0 && touch) ? 2.0f : 0.0f;
+    if (m.reward_shaping) r = fmaxf(r_reach, fmaxf(r_lift, r_stack)); else r = r_stack > 0 ? 2.0f : 0.0f;
+    return r * m.reward_scale / 2.0f;
+  }
+  if (m.task_id == RSB_TASK_DOOR) {
+    real hinge = qpos[m.obj_qadr[0]], handle = qpos[m.obj_qadr[1]];
+    if (hinge > 0.3f) r = 1.0f;
+    else if (m.reward_shaping) {
+      const real *hs = sxpos + 3 * m.obj_site[0]; real d[3] = {eef[0] - hs[0], eef[1] - hs[1], eef[2] - hs[2]};
+      r += 0.25f * (1 - tanhf(10.0f * sqrtf(dot3(d, d))));
+      r += fminf(0.25f * fabsf(handle / (0.5f * RSB_PI)), 0.25f);
+    }
+    return r * m.reward_scale;
+  }
+  return 0;
+}
+
+/* A.1.4 observation vector, robosuite v1.0 order: per robot [sin q, cos q, qd, eef_pos, eef_quat(xyzw), grip q, grip qd], then object-state.
+   Lane-parallel: lane i produces element i (and i+LANES, ...) and writes it straight to `obs` (global memory, coalesced). */
+RSB_D real obs_element(const DevModel &m, const real *s, int i) {
+  const real *qpos = s + m.o_qpos, *qvel = s + m.o_qvel, *xpos = s + m.o_xpos, *xquat = s + m.o_xquat, *sxpos = s + m.o_sxpos;
+  for (int ri = 0; ri < m.nrobot; ri++) {
+    const DevRobot &rb = m.robot[ri]; int n = 28 + 2 * rb.grip_ndof;
+    if (i < n) {
+      if (i < 7) return sinf(qpos[rb.arm_qadr[i]]);
+      if (i < 14) return cosf(qpos[rb.arm_qadr[i - 7]]);
+      if (i < 21) return qvel[rb.arm_dadr[i - 14]];
+      if (i < 24) return sxpos[3 * rb.eef_site + i - 21];
+      if (i < 28) { int k = i - 24; return xquat[4 * rb.eef_body + (k == 3 ? 0 : k + 1)]; }
+      int k = i - 28; return k < rb.grip_ndof ? qpos[rb.grip_qadr[k]] : qvel[rb.grip_dadr[k - rb.grip_ndof]];
+    }
+    i -= n;
+  }
+  const real *eef = sxpos + 3 * m.robot[0].eef_site;
+  if (m.task_id == RSB_TASK_LIFT) {
+    const real *cube = xpos + 3 * m.obj_body[0];
+    if (i < 3) return cube[i];
+    if (i < 7) { int k = i - 3; return xquat[4 * m.obj_body[0] + (k == 3 ? 0 : k + 1)]; }
+    return eef[i - 7] - cube[i - 7];
+  }
+  if (m.task_id == RSB_TASK_STACK) {
+    const real *A = xpos + 3 * m.obj_body[0], *B = xpos + 3 * m.obj_body[1];
+    if (i < 3) return A[i];
+    if (i < 7) { int k = i - 3; return xquat[4 * m.obj_body[0] + (k == 3 ? 0 : k + 1)]; }
+    if (i < 10) return B[i - 7];
+    if (i < 14) { int k = i - 10; return xquat[4 * m.obj_body[1] + (k == 3 ? 0 : k + 1)]; }
+    if (i < 17) return eef[i - 14] - A[i - 14];
+    if (i < 20) return eef[i - 17] - B[i - 17];
+    return A[i - 20] - B[i - 20];
+  }
+  if (m.task_id == RSB_TASK_DOOR) {
+    const real *door = xpos + 3 * m.obj_body[0], *hs = sxpos + 3 * m.obj_site[0];
+    if (i < 3) return door[i];
+    if (i < 6) return hs[i - 3];
+    if (i < 9) return door[i - 6] - eef[i - 6];
+    if (i < 12) return hs[i - 9] - eef[i - 9];
+    return qpos[m.obj_qadr[i - 12]];
+  }
+  return 0;
+}
+
+/* persistent state <-> shared memory (state record layout: DevModel::st_*) */
+RSB_D void load_state(const DevModel &m, real *s, const real *st, Grp g) {
+  for (int i = g.lane; i < m.nq; i += RSB_LANES) s[m.o_qpos + i] = st[m.st_qpos + i];
+  for (int i = g.lane; i < m.nv; i += RSB_LANES) { s[m.o_qvel + i] = st[m.st_qvel + i]; s[m.o_warm + i] = st[m.st_warm + i]; }
+  for (int i = g.lane; i < m.nrobot * RSB_CS_WORDS; i += RSB_LANES) s[m.o_cs + i] = st[m.st_cs + i];
+  for (int i = g.lane; i < m.nu; i += RSB_LANES) s[m.o_ctrl + i] = 0;
+  gsync(g);
+}
+RSB_D void store_state(const DevModel &m, const real *s, real *st, Grp g) {
+  for (int i = g.lane; i < m.nq; i += RSB_LANES) st[m.st_qpos + i] = s[m.o_qpos + i];
+  for (int i = g.lane; i < m.nv; i += RSB_LANES) { st[m.st_qvel + i] = s[m.o_qvel + i]; st[m.st_warm + i] = s[m.o_warm + i]; }
+  for (int i = g.lane; i < m.nrobot * RSB_CS_WORDS; i += RSB_LANES) st[m.st_cs + i] = s[m.o_cs + i];
+}
+
+/* One control step of one env (robosuite MujocoEnv.step): 25 x (forward, controller, mj_step), then reward + observation.
+   `st` = this env's state record, `action` = [act_dim], `obs` = [obs_dim] output row.  Returns via *reward, *done.
+   Stepping a finished episode leaves the state untouched and reports done = 2 (the host raises ValueError). */
+RSB_D void env_step(const DevModel &m, real *s, Grp g, real *st, const real *action, real *obs, real *reward, unsigned char *done) {
+  int t = f2i(st[m.st_time]);
+  bool finished = (t >= m.horizon) && !m.ignore_done;
+  if (finished) { if (g.lane == 0) { *done = 2; *reward = 0; } return; }
+  load_state(m, s, st, g);
+  for (int i = g.lane; i < m.act_dim; i += RSB_LANES) s[m.o_act + i] = action[i];
+  gsync(g);
+  for (int k = 0; k < m.substeps; k++) substep(m, s, g, k == 0);
+  st_kinematics(m, s, g); gsync(g); st_collision(m, s, g);   /* observations / reward read the post-step kinematics and contacts */
+  real r = task_reward(m, s);
+  for (int i = g.lane; i < m.obs_dim; i += RSB_LANES) obs[i] = obs_element(m, s, i);
+  store_state(m, s, st, g);
+  if (g.lane == 0) { t++; st[m.st_time] = i2f(t); *reward = r; *done = ((t >= m.horizon) && !m.ignore_done) ? 1 : 0; }
+}
+
+/* robosuite MujocoEnv.reset (hard_reset = False): sim.reset, noisy arm init, object placement, new controller, forward, obs.
+   Randomness: Philox keyed (seed, env_id), stream 0, counter = episode*8 + block -- identical to the oracle's orc_reset. */
+RSB_D void env_reset(const DevModel &m, real *s, Grp g, real *st, uint64_t seed, uint64_t env_id, real *obs) {
+  int episode = f2i(st[m.st_episode]);
+  real *qpos = s + m.o_qpos;
+  for (int i = g.lane; i < m.nq; i += RSB_LANES) qpos[i] = m.qpos0[i];
+  for (int i = g.lane; i < m.nv; i += RSB_LANES) { s[m.o_qvel + i] = 0; s[m.o_warm + i] = 0; }
+  gsync(g);
+  if (g.lane < m.nrobot) {
+    const DevRobot &rb = m.robot[g.lane]; real z[8]; uint32_t r[4];
+    for (int blk = 0; blk < 2; blk++) {
+      rsb_philox(seed, env_id, 0, (uint32_t)(episode * 8 + (g.lane * 2 + blk)), r);
+      box_muller(r[0], r[1], &z[4 * blk], &z[4 * blk + 1]); box_muller(r[2], r[3], &z[4 * blk + 2], &z[4 * blk + 3]);
+    }
+    for (int k = 0; k < RSB_ARM_DOF; k++) qpos[rb.arm_qadr[k]] = rb.init_qpos[k] + m.init_noise * z[k];
+    for (int k = 0; k < rb.grip_ndof; k++) qpos[rb.grip_qadr[k]] = rb.grip_init[k];
+  }
+  if (g.lane == RSB_LANES - 1) {                      /* object placement: uniform xy + yaw, rejection on overlap (serial over objects) */
+    for (int o = 0; o < RSB_MAX_OBJ; o++) {
+      if (m.obj_qadr[o] < 0 || m.place_z[o] <= 0) continue;
+      int qa = m.obj_qadr[o]; real x = 0, y = 0, yaw = 0; uint32_t r[4];
+      for (int attempt = 0; attempt < 16; attempt++) {
+        rsb_philox(seed, env_id, 0, (uint32_t)(episode * 8 + 4 + o) + 0x10000u * (uint32_t)attempt, r);
+        double u0 = ((double)r[0] + 0.5) * (1.0 / 4294967296.0), u1 = ((double)r[1] + 0.5) * (1.0 / 4294967296.0), u2 = ((double)r[2] + 0.5) * (1.0 / 4294967296.0);
+        x = (real)(m.place_x[o][0] + (m.place_x[o][1] - m.place_x[o][0]) * u0);
+        y = (real)(m.place_y[o][0] + (m.place_y[o][1] - m.place_y[o][0]) * u1);
+        yaw = (real)(m.place_yaw[o][0] + (m.place_yaw[o][1] - m.place_yaw[o][0]) * u2);
+        bool ok = true;
+        for (int p = 0; p < o; p++) if (m.obj_qadr[p] >= 0 && m.place_z[p] > 0) {
+          real dx = x + m.place_ref[0] - qpos[m.obj_qadr[p]], dy = y + m.place_ref[1] - qpos[m.obj_qadr[p] + 1];
+          real rr = sqrtf(m.obj_half[o][0] * m.obj_half[o][0] + m.obj_half[o][1] * m.obj_half[o][1]) + sqrtf(m.obj_half[p][0] * m.obj_half[p][0] + m.obj_half[p][1] * m.obj_half[p][1]);
+          if (dx * dx + dy * dy < rr * rr) ok = false;
+        }
+        if (ok) break;
+      }
+      real sn, c; rsb_sincos(0.5f * yaw, &sn, &c);
+      qpos[qa] = m.place_ref[0] + x; qpos[qa + 1] = m.place_ref[1] + y; qpos[qa + 2] = m.place_z[o];
+      qpos[qa + 3] = c; qpos[qa + 4] = 0; qpos[qa + 5] = 0; qpos[qa + 6] = sn;
+    }
+  }
+  gsync(g);
+  st_kinematics(m, s, g); gsync(g);
+  ctrl_reset(m, s, g);
+  for (int i = g.lane; i < m.obs_dim; i += RSB_LANES) obs[i] = obs_element(m, s, i);
+  store_state(m, s, st, g);
+  if (g.lane == 0) { st[m.st_time] = i2f(0); st[m.st_episode] = i2f(episode + 1); }
+}
+
+/* synthetic action stream shared with the oracle: a = tanh(N(0,1)) keyed (seed, env, step, dim), stream 1 */
+RSB_D void random_action_block(uint64_t seed, uint64_t env_id, uint64_t step, int blk, int n, real *action) {
+  uint32_t r[4]; rsb_philox(seed, env_id, 1, (uint32_t)(step * 4 + (uint64_t)blk), r);
+  real z[4]; box_muller(r[0], r[1], &z[0], &z[1]); box_muller(r[2], r[3], &z[2], &z[3]);
+  for (int k = 0; k < 4; k++) if (4 * blk + k < n) action[4 * blk + k] = tanhf(z[k]);
+}
+
+/* debug record (floats) for parity tests; layout documented in rsb_devmodel.h / tests/emu */
+RSB_D void dump_debug(const DevModel &m, const real *s, Grp g, real *out) {
+  const int *misc = (const int *)(s + m.o_misc); int nv = m.nv, nc = m.ncon_max, ne = m.nefc_max;
+  if (g.lane == 0) { out[0] = (real)misc[MISC_NCON]; out[1] = (real)misc[MISC_NEFC]; out[2] = (real)misc[MISC_ITER]; }
+  real *o = out + 8;
+  for (int i = g.lane; i < nv * nv; i += RSB_LANES) o[i] = s[m.o_M + (i / nv) * m.ldm + i % nv];
+  o += nv * nv;
+  const int vecs[8] = {m.o_bias, m.o_passive, m.o_actuator, m.o_qacc_smooth, m.o_qacc, m.o_qfc, m.o_smooth, m.o_warm};
+  for (int k = 0; k < 8; k++) for (int i = g.lane; i < nv; i += RSB_LANES) o[k * nv + i] = s[vecs[k] + i];
+  o += 8 * nv;
+  for (int i = g.lane; i < 14; i += RSB_LANES) o[i] = s[m.o_cscr + 208 + i];
+  o += 14;
+  for (int i = g.lane; i < nc * 16; i += RSB_LANES) { int c = i / 16, k = i % 16; const real *cr = s + m.o_con + c * RSB_CONW; const int *ci = (const int *)cr;
+    real v = 0; if (c < misc[MISC_NCON]) { if (k < 13) v = cr[k]; else if (k == 13) v = (real)ci[CON_G1]; else if (k == 14) v = (real)ci[CON_G2]; else v = cr[CON_MU]; } o[i] = v; }
+  o += nc * 16;
+  const int ev[5] = {m.o_earef, m.o_eR, m.o_eforce, m.o_epos, m.o_ejar};
+  for (int k = 0; k < 5; k++) for (int i = g.lane; i < ne; i += RSB_LANES) o[k * ne + i] = i < misc[MISC_NEFC] ? s[ev[k] + i] : 0;
+  for (int i = g.lane; i < ne; i += RSB_LANES) o[5 * ne + i] = i < misc[MISC_NEFC] ? (real)((const int *)(s + m.o_etype))[i] : -1;
+  o += 6 * ne;
+  for (int i = g.lane; i < ne * nv; i += RSB_LANES) { int r = i / nv, d = i % nv; o[i] = r < misc[MISC_NEFC] ? s[m.o_J + r * m.ldj + d] : 0; }
+}
+
+#endif /* RSB_DEV_H */

@@ -1,0 +1,166 @@
+"""GPU parity: the CUDA path, called through the C-ABI (include/rsb.h), against the fp64 CPU oracle on identical inputs.
+
+Tolerances are BASELINE.json's north_star: contact-pair lists bit-exact; qpos/qvel max-abs <= 1e-4 after one control
+step from identical state (fp32 vs fp64); controller torques within 1e-5 relative; reward means within 1 %.
+(The oracle itself is PARITY UNPINNED against real MuJoCo/robosuite -- see oracle/rsb_oracle.c.)
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NCON, NEFC = 16, 64
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def sim(lift_panda_osc, torch_cuda):
+    from robosuite_benchmark_b200.backend import BatchSim
+    m, t = lift_panda_osc
+    return BatchSim(m, t, 32, device="cuda:0", seed=17, ncon_max=NCON, nefc_max=NEFC)
+
+
+def _oracle(lift_panda_osc):
+    from oracle.oracle import OracleEnv
+    m, t = lift_panda_osc
+    return OracleEnv(m, t, ncon_max=NCON, nefc_max=NEFC)
+
+
+def _rollout_states(lift_panda_osc, n_envs, steps_between=3, seed=17):
+    """States sampled from oracle rollouts under the synthetic tanh-Gaussian action stream (the reference's committed
+    runs store no states and no simulator exists here to regenerate them: SURVEY.md 8c)."""
+    out = []
+    for i in range(n_envs):
+        orc = _oracle(lift_panda_osc)
+        orc.reset(seed=seed, env_id=i, episode=0)
+        k = 0
+        for k in range((i % 8) * steps_between):
+            orc.step(orc.random_action(seed, i, k))
+        out.append((orc, k + 1))
+    return out
+
+
+def test_reset_matches_oracle(sim, lift_panda_osc, torch_cuda):
+    obs = sim.reset().cpu().numpy()
+    st = sim.unpack_state(sim.get_state().cpu().numpy())
+    for i in (0, 5, 31):
+        orc = _oracle(lift_panda_osc)
+        o = orc.reset(seed=17, env_id=i, episode=0)
+        qpos, qvel, _, cs = orc.get_state()
+        assert np.abs(o - obs[i]).max() < 2e-6
+        assert np.abs(qpos - st["qpos"][i]).max() < 1e-6 and np.abs(cs - st["cs"][i]).max() < 2e-6
+    assert (st["episode"] == 1).all() and (st["timestep"] == 0).all()
+
+
+def test_one_control_step_from_identical_state(sim, lift_panda_osc, torch_cuda):
+    torch = torch_cuda
+    n = sim.num_envs
+    envs = _rollout_states(lift_panda_osc, n)
+    rows, acts = [], []
+    for i, (orc, k) in enumerate(envs):
+        qpos, qvel, warm, cs = orc.get_state()
+        rows.append(sim.pack_state(qpos, qvel, warm, cs, timestep=k, episode=1)[0])
+        acts.append(orc.random_action(17, i, k))
+    sim.set_state(torch.as_tensor(np.stack(rows)))
+    a = torch.as_tensor(np.stack(acts), dtype=torch.float32, device=sim.device)
+    obs, rew, done = sim.step(a)
+    st = sim.unpack_state(sim.get_state().cpu().numpy())
+    obs, rew = obs.cpu().numpy(), rew.cpu().numpy()
+    dq = dv = do = dr = 0.0
+    for i, (orc, k) in enumerate(envs):
+        o, r, _ = orc.step(acts[i])
+        qpos, qvel, _, _ = orc.get_state()
+        dq = max(dq, np.abs(qpos - st["qpos"][i]).max())
+        dv = max(dv, np.abs(qvel - st["qvel"][i]).max())
+        do = max(do, np.abs(o - obs[i]).max())
+        dr = max(dr, abs(r - rew[i]))
+    assert dq <= 1e-4 and dv <= 1e-4, (dq, dv)      # north_star tolerance (fp32)
+    assert do <= 1e-4 and dr <= 1e-5, (do, dr)
+    assert (done.cpu().numpy() == 0).all()
+
+
+def test_substep_internals_contacts_bit_exact_torques_1e5(sim, lift_panda_osc, torch_cuda):
+    from tests.emu.emu import split_debug
+    torch = torch_cuda
+    m, _ = lift_panda_osc
+    n = sim.num_envs
+    envs = _rollout_states(lift_panda_osc, n, steps_between=2)
+    rows, acts = [], []
+    for i, (orc, k) in enumerate(envs):
+        qpos, qvel, warm, cs = orc.get_state()
+        rows.append(sim.pack_state(qpos, qvel, warm, cs, timestep=k, episode=1)[0])
+        acts.append(orc.random_action(17, i, k))
+    sim.set_state(torch.as_tensor(np.stack(rows)))
+    a = torch.as_tensor(np.stack(acts), dtype=torch.float32, device=sim.device)
+    dbg = sim.debug_substep(a, True).cpu().numpy()
+    ncontacts = 0
+    for i, (orc, k) in enumerate(envs):
+        orc.substep(acts[i], True)
+        d = split_debug(dbg[i], m.nv, NCON, NEFC)
+        ref_pairs = orc.get("contact_geoms").reshape(-1, 2).astype(int)
+        assert ref_pairs.tolist() == d["contact_geoms"].tolist()            # bit-exact contact-pair list
+        ncontacts += len(ref_pairs)
+        assert int(orc.get("counts")[1]) == d["nefc"]
+        tau_ref = orc.get("torques")[:7]
+        assert np.abs(tau_ref - d["torques"][:7]).max() <= 1e-5 * max(1.0, np.abs(tau_ref).max())
+        M = orc.get("M", (m.nv, m.nv))
+        assert np.abs(M - d["M"]).max() <= 2e-6 * np.abs(M).max()
+        assert np.abs(orc.get("qfrc_bias") - d["qfrc_bias"]).max() <= 1e-5 * max(1.0, np.abs(orc.get("qfrc_bias")).max())
+        assert np.abs(orc.get("qacc") - d["qacc"]).max() <= 2e-5 * max(1.0, np.abs(orc.get("qacc")).max())
+        if len(ref_pairs):
+            assert np.abs(orc.get("contact_dist") - d["contact_dist"]).max() < 1e-6
+    assert ncontacts > 0
+
+
+def test_episode_reward_mean_within_1pct(lift_panda_osc, torch_cuda):
+    """Random-action reward means: CUDA free-running vs oracle free-running over 40 control steps x 16 envs."""
+    from robosuite_benchmark_b200.backend import BatchSim
+    m, t = lift_panda_osc
+    n, steps = 16, 40
+    s = BatchSim(m, t, n, device="cuda:0", seed=59, ncon_max=NCON, nefc_max=NEFC)
+    s.reset()
+    tot = np.zeros(n)
+    for k in range(steps):
+        _, r, _ = s.step(s.random_actions(k))
+        tot += r.cpu().numpy()
+    ref = np.zeros(n)
+    for i in range(n):
+        orc = _oracle(lift_panda_osc)
+        orc.reset(seed=59, env_id=i, episode=0)
+        for k in range(steps):
+            ref[i] += orc.step(orc.random_action(59, i, k))[1]
+    assert abs(tot.mean() - ref.mean()) <= 0.01 * abs(ref.mean()), (tot.mean(), ref.mean())
+    s.close()
+
+
+def test_single_env_protocol(torch_cuda):
+    import robosuite_benchmark_b200 as suite
+    from robosuite_benchmark_b200.wrappers import GymWrapper
+    env = suite.make("Lift", "Panda", controller_configs=suite.load_controller_config(default_controller="OSC_POSE"),
+                     horizon=3, control_freq=20, reward_shaping=True, has_renderer=False, has_offscreen_renderer=False,
+                     use_object_obs=True, use_camera_obs=False)
+    g = GymWrapper(env)
+    assert g.observation_space.low.size == 42 and g.action_space.low.size == 7
+    o = g.reset()
+    assert o.shape == (42,) and o.dtype == np.float64
+    for k in range(3):
+        o, r, d, info = g.step(np.zeros(7))
+        assert isinstance(r, float) and info == {}
+    assert d is True
+    with pytest.raises(ValueError):
+        g.step(np.zeros(7))
+    with pytest.raises(AssertionError):
+        env.reset(); env.step(np.zeros(6))
+    d0 = env.reset()
+    assert list(d0.keys())[:2] == ["robot0_robot-state", "object-state"]
+    g2 = GymWrapper(env, keys=["object-state", "robot0_proprio-state"])
+    o2 = g2.reset()
+    assert o2.shape == (42,)
+    env.close()
