@@ -161,6 +161,7 @@ class BatchedEnv(_EnvBase):
 
 def make(env_name, robots, num_envs=1, **kwargs):
     """robosuite.make: single env by default; `num_envs=N` (N > 1) returns the batched GPU environment."""
-    if num_envs == 1 and not kwargs.pop("batched", False):
+    batched = kwargs.pop("batched", False)
+    if num_envs == 1 and not batched:
         return RobosuiteEnv(env_name, robots, **kwargs)
     return BatchedEnv(env_name, robots, num_envs=num_envs, **kwargs)
