@@ -8,16 +8,17 @@
  */
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/rsb.h"
-#include "rsb_dev.h"
 
-#ifndef RSB_EPB
-#define RSB_EPB 4
-#endif
+#define RSB_MAX_EPB 16         /* envs (warps) per CTA, chosen at create(): as many as fit shared memory, so that with lockstep
+                                  stages ONE CTA per SM shares a single instruction stream */
+#define RSB_LOCKSTEP 1
+#include "rsb_dev.h"
 
 static thread_local std::string g_err;
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return 1; } } while (0)
@@ -26,7 +27,7 @@ struct rsb_batch {
   DevModel dm;                 /* device pointers fixed up */
   void *d_arena = nullptr;
   float *d_state = nullptr;
-  int n = 0, device = 0;
+  int n = 0, device = 0, epb = 1;
   uint64_t seed = 0, env_id_base = 0;
   size_t smem_bytes = 0;
   int64_t launches = 0;
@@ -38,41 +39,40 @@ struct rsb_batch {
 };
 
 /* ------------------------------------------------------------------ kernels */
-__global__ void __launch_bounds__(RSB_EPB * 32)
-k_step(const __grid_constant__ DevModel m, float *__restrict__ state, const float *__restrict__ actions, float *__restrict__ obs,
+__global__ void __launch_bounds__(RSB_MAX_EPB * 32)
+k_step(float *__restrict__ state, const float *__restrict__ actions, float *__restrict__ obs,
        float *__restrict__ rew, unsigned char *__restrict__ done, int n) {
-  extern __shared__ float smem[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, env = blockIdx.x * RSB_EPB + w;
-  if (env >= n) return;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, env = blockIdx.x * (blockDim.x >> 5) + w;
+  const bool commit = env < n; const int e = commit ? env : n - 1;          /* padding warps shadow the last env (no stores) */
   Grp g{lane, 0xffffffffu};
-  env_step(m, smem + (size_t)w * m.smem_words, g, state + (size_t)env * m.st_words, actions + (size_t)env * m.act_dim,
-           obs + (size_t)env * m.obs_dim, rew + env, done + env);
+  env_step(w * c_model.smem_words, g, state + (size_t)e * c_model.st_words, actions + (size_t)e * c_model.act_dim,
+           obs + (size_t)e * c_model.obs_dim, rew + e, done + e, commit);
 }
 
-__global__ void __launch_bounds__(RSB_EPB * 32)
-k_reset(const __grid_constant__ DevModel m, float *__restrict__ state, const unsigned char *__restrict__ mask, float *__restrict__ obs,
+__global__ void __launch_bounds__(RSB_MAX_EPB * 32)
+k_reset(float *__restrict__ state, const unsigned char *__restrict__ mask, float *__restrict__ obs,
         uint64_t seed, uint64_t env_id_base, int n) {
-  extern __shared__ float smem[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, env = blockIdx.x * RSB_EPB + w;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, env = blockIdx.x * (blockDim.x >> 5) + w;
   if (env >= n) return;
   if (mask && !mask[env]) return;
   Grp g{lane, 0xffffffffu};
-  env_reset(m, smem + (size_t)w * m.smem_words, g, state + (size_t)env * m.st_words, seed, env_id_base + (uint64_t)env, obs + (size_t)env * m.obs_dim);
+  env_reset(w * c_model.smem_words, g, state + (size_t)env * c_model.st_words, seed, env_id_base + (uint64_t)env, obs + (size_t)env * c_model.obs_dim);
 }
 
-__global__ void __launch_bounds__(RSB_EPB * 32)
-k_debug_substep(const __grid_constant__ DevModel m, float *__restrict__ state, const float *__restrict__ actions, int policy_step,
+__global__ void __launch_bounds__(RSB_MAX_EPB * 32)
+k_debug_substep(float *__restrict__ state, const float *__restrict__ actions, int policy_step,
                 float *__restrict__ dbg, int dbg_words, int n) {
-  extern __shared__ float smem[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, env = blockIdx.x * RSB_EPB + w;
-  if (env >= n) return;
-  Grp g{lane, 0xffffffffu}; float *s = smem + (size_t)w * m.smem_words; float *st = state + (size_t)env * m.st_words;
-  load_state(m, s, st, g);
-  for (int i = lane; i < m.act_dim; i += 32) s[m.o_act + i] = actions[(size_t)env * m.act_dim + i];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, env = blockIdx.x * (blockDim.x >> 5) + w;
+  const bool commit = env < n; const int e = commit ? env : n - 1;
+  const DevModel &m = c_model;
+  Grp g{lane, 0xffffffffu}; const int so = w * m.smem_words; float *s = rsb_smem + so; float *st = state + (size_t)e * m.st_words;
+  load_state(so, st, g);
+  for (int i = lane; i < m.act_dim; i += 32) s[m.o_act + i] = actions[(size_t)e * m.act_dim + i];
   gsync(g);
-  substep(m, s, g, policy_step != 0);
-  dump_debug(m, s, g, dbg + (size_t)env * dbg_words);
-  store_state(m, s, st, g);
+  substep(so, g, policy_step != 0);
+  if (!commit) return;
+  dump_debug(so, g, dbg + (size_t)e * dbg_words);
+  store_state(so, st, g);
 }
 
 __global__ void k_random_actions(uint64_t seed, uint64_t env_id_base, uint64_t step, int act_dim, float *__restrict__ actions, int n) {
@@ -81,6 +81,8 @@ __global__ void k_random_actions(uint64_t seed, uint64_t env_id_base, uint64_t s
   int env = i / nblk, blk = i - env * nblk;
   random_action_block(seed, env_id_base + (uint64_t)env, step, blk, act_dim, actions + (size_t)env * act_dim);
 }
+
+static const rsb_batch *g_const_owner[64];
 
 /* ------------------------------------------------------------------ C-ABI */
 extern "C" {
@@ -92,6 +94,8 @@ int rsb_sizeof_task(void) { return (int)sizeof(rsb_task); }
 void rsb_destroy(rsb_batch *b) {
   if (!b) return;
   cudaSetDevice(b->device);
+  cudaDeviceSynchronize();
+  if (b->device < 64 && g_const_owner[b->device] == b) g_const_owner[b->device] = nullptr;
   cudaFree(b->d_arena); cudaFree(b->d_state); cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_done); cudaFree(b->d_mask);
   cudaFreeHost(b->p_act); cudaFreeHost(b->p_obs); cudaFreeHost(b->p_rew); cudaFreeHost(b->p_done);
   if (b->stream) cudaStreamDestroy(b->stream);
@@ -109,9 +113,13 @@ int rsb_create(const rsb_model *model, const rsb_task *task, int n_envs, int dev
   RsbHostModel hm;
   if (!rsb_build_host_model(model, task, ncon_max, nefc_max, hm)) { g_err = hm.error; return 4; }
   rsb_batch *b = new rsb_batch(); b->n = n_envs; b->device = device; b->seed = seed; b->env_id_base = env_id_base;
-  b->dm = hm.dm; b->smem_bytes = (size_t)hm.dm.smem_words * 4 * RSB_EPB;
+  b->dm = hm.dm;
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
-  if (b->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { g_err = "per-env working set does not fit shared memory"; delete b; return 5; }
+  size_t per_env = (size_t)hm.dm.smem_words * 4;
+  int epb = (int)((size_t)prop.sharedMemPerBlockOptin / per_env); if (epb > RSB_MAX_EPB) epb = RSB_MAX_EPB;
+  if (const char *e = getenv("RSB_EPB")) { int v = atoi(e); if (v > 0 && v < epb) epb = v; }
+  if (epb < 1) { g_err = "per-env working set does not fit shared memory"; delete b; return 5; }
+  b->epb = epb; b->smem_bytes = per_env * (size_t)epb;
   CK(cudaMalloc(&b->d_arena, hm.arena.size()));
   CK(cudaMemcpy(b->d_arena, hm.arena.data(), hm.arena.size(), cudaMemcpyHostToDevice));
   rsb_fixup_pointers(b->dm, b->d_arena);
@@ -121,7 +129,7 @@ int rsb_create(const rsb_model *model, const rsb_task *task, int n_envs, int dev
   CK(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
   CK(cudaFuncSetAttribute(k_debug_substep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_step)); b->regs_step = fa.numRegs;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->blocks_per_sm, k_step, RSB_EPB * 32, b->smem_bytes));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->blocks_per_sm, k_step, b->epb * 32, b->smem_bytes));
   CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   *out = b; return 0;
 }
@@ -131,31 +139,44 @@ int64_t rsb_info(const rsb_batch *b, int what) {
     case RSB_INFO_NENVS: return b->n; case RSB_INFO_OBS_DIM: return b->dm.obs_dim; case RSB_INFO_ACT_DIM: return b->dm.act_dim;
     case RSB_INFO_STATE_WORDS: return b->dm.st_words; case RSB_INFO_SMEM_BYTES: return (int64_t)b->dm.smem_words * 4;
     case RSB_INFO_DBG_WORDS: return RSB_DBG_WORDS(b->dm.nv, b->dm.ncon_max, b->dm.nefc_max); case RSB_INFO_NQ: return b->dm.nq; case RSB_INFO_NV: return b->dm.nv;
-    case RSB_INFO_ENVS_PER_BLOCK: return RSB_EPB; case RSB_INFO_LAUNCHES: return b->launches;
+    case RSB_INFO_ENVS_PER_BLOCK: return b->epb; case RSB_INFO_LAUNCHES: return b->launches;
     case RSB_INFO_NCON_MAX: return b->dm.ncon_max; case RSB_INFO_NEFC_MAX: return b->dm.nefc_max;
     case RSB_INFO_REGS_STEP: return b->regs_step; case RSB_INFO_BLOCKS_PER_SM: return b->blocks_per_sm;
   }
   return -1;
 }
 
-static inline int nblocks(const rsb_batch *b) { return (b->n + RSB_EPB - 1) / RSB_EPB; }
+static inline int nblocks(const rsb_batch *b) { return (b->n + b->epb - 1) / b->epb; }
+
+/* The kernels read the model from constant memory.  Several batches (e.g. exploration and evaluation envs) may coexist in
+   one process: the constant copy is re-uploaded, stream-ordered, whenever another batch used it last. */
+static int bind_model(rsb_batch *b, cudaStream_t st) {
+  if (b->device < 64 && g_const_owner[b->device] == b) return 0;
+  if (b->device < 64 && g_const_owner[b->device] != nullptr) CK(cudaDeviceSynchronize());     /* kernels of the previous owner may be in flight */
+  CK(cudaMemcpyToSymbolAsync(c_model, &b->dm, sizeof(DevModel), 0, cudaMemcpyHostToDevice, st));
+  if (b->device < 64) g_const_owner[b->device] = b;
+  return 0;
+}
 
 int rsb_reset(rsb_batch *b, const uint8_t *d_mask, float *d_obs, void *stream) {
   CK(cudaSetDevice(b->device));
-  k_reset<<<nblocks(b), RSB_EPB * 32, b->smem_bytes, (cudaStream_t)stream>>>(b->dm, b->d_state, d_mask, d_obs, b->seed, b->env_id_base, b->n);
+  if (bind_model(b, (cudaStream_t)stream)) return 1;
+  k_reset<<<nblocks(b), b->epb * 32, b->smem_bytes, (cudaStream_t)stream>>>(b->d_state, d_mask, d_obs, b->seed, b->env_id_base, b->n);
   b->launches++; CK(cudaGetLastError()); return 0;
 }
 
 int rsb_step(rsb_batch *b, const float *d_actions, float *d_obs, float *d_reward, uint8_t *d_done, void *stream) {
   CK(cudaSetDevice(b->device));
-  k_step<<<nblocks(b), RSB_EPB * 32, b->smem_bytes, (cudaStream_t)stream>>>(b->dm, b->d_state, d_actions, d_obs, d_reward, d_done, b->n);
+  if (bind_model(b, (cudaStream_t)stream)) return 1;
+  k_step<<<nblocks(b), b->epb * 32, b->smem_bytes, (cudaStream_t)stream>>>(b->d_state, d_actions, d_obs, d_reward, d_done, b->n);
   b->launches++; CK(cudaGetLastError()); return 0;
 }
 
 int rsb_debug_substep(rsb_batch *b, const float *d_actions, int policy_step, float *d_dbg, void *stream) {
   CK(cudaSetDevice(b->device));
   int words = RSB_DBG_WORDS(b->dm.nv, b->dm.ncon_max, b->dm.nefc_max);
-  k_debug_substep<<<nblocks(b), RSB_EPB * 32, b->smem_bytes, (cudaStream_t)stream>>>(b->dm, b->d_state, d_actions, policy_step, d_dbg, words, b->n);
+  if (bind_model(b, (cudaStream_t)stream)) return 1;
+  k_debug_substep<<<nblocks(b), b->epb * 32, b->smem_bytes, (cudaStream_t)stream>>>(b->d_state, d_actions, policy_step, d_dbg, words, b->n);
   b->launches++; CK(cudaGetLastError()); return 0;
 }
 

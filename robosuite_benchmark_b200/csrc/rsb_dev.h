@@ -36,6 +36,11 @@ int emu_shfl_i(int v, int src);
 #define RSB_D static inline
 #define RSB_DN static
 #define RSB_DNOINL static
+extern DevModel emu_model;                 /* the harness sets these before running a group */
+extern float *emu_smem;
+#define MDL emu_model
+#define RSB_SMEM emu_smem
+#define RSB_CTA_SYNC() ((void)0)
 RSB_D void gsync(Grp) { emu_sync(); }
 RSB_D real gshfl(Grp, real v, int src) { return emu_shfl_f(v, src); }
 RSB_D int gshfl_i(Grp, int v, int src) { return emu_shfl_i(v, src); }
@@ -52,8 +57,19 @@ RSB_D uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a 
 #include <stdint.h>
 struct Grp { int lane; unsigned mask; };
 #define RSB_D __device__ __forceinline__
-#define RSB_DN __device__ __forceinline__
+#define RSB_DN __device__ __noinline__
 #define RSB_DNOINL __device__ __noinline__
+/* the compiled model lives in constant memory (set by the host before a launch); every env's working set is a slice of
+   the CTA's dynamic shared memory, addressed by WORD OFFSET so that non-inlined stage functions still emit LDS/STS */
+__constant__ DevModel c_model;
+extern __shared__ float rsb_smem[];
+#define MDL c_model
+#define RSB_SMEM rsb_smem
+#ifdef RSB_LOCKSTEP
+#define RSB_CTA_SYNC() __syncthreads()       /* keep the CTA's warps in the same stage: they share instruction fetches */
+#else
+#define RSB_CTA_SYNC() ((void)0)
+#endif
 RSB_D void gsync(Grp g) { __syncwarp(g.mask); }
 RSB_D real gshfl(Grp g, real v, int src) { return __shfl_sync(g.mask, v, src, RSB_LANES); }
 RSB_D int gshfl_i(Grp g, int v, int src) { return __shfl_sync(g.mask, v, src, RSB_LANES); }
@@ -68,6 +84,7 @@ RSB_D real i2f(int i) { return __int_as_float(i); }
 RSB_D uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 #endif
 
+#define SOFF(p) ((int)((p) - RSB_SMEM))
 #define RSB_MINVAL 1e-15f
 #define RSB_PI 3.14159265358979323846f
 
@@ -164,16 +181,16 @@ RSB_D void box_muller(uint32_t a, uint32_t b, real *z0, real *z1) {
 }
 
 /* ================================================================== A.3.1 kinematics */
-RSB_DN void st_kinematics(const DevModel &m, real *s, Grp g) {
-  real *qpos = s + m.o_qpos, *jq = s + m.o_jq;
-  real *xpos = s + m.o_xpos, *xquat = s + m.o_xquat, *xmat = s + m.o_xmat, *xanchor = s + m.o_xanchor, *xaxis = s + m.o_xaxis;
+RSB_DN void st_kinematics(int so, Grp g) { real *s = RSB_SMEM + so;
+  real *qpos = s + MDL.o_qpos, *jq = s + MDL.o_jq;
+  real *xpos = s + MDL.o_xpos, *xquat = s + MDL.o_xquat, *xmat = s + MDL.o_xmat, *xanchor = s + MDL.o_xanchor, *xaxis = s + MDL.o_xaxis;
   /* per-joint local motion, lane-parallel (the transcendental part) */
-  for (int j = g.lane; j < m.njnt; j += RSB_LANES) {
-    int t = m.jnt_type[j], a = m.jnt_qadr[j];
+  for (int j = g.lane; j < MDL.njnt; j += RSB_LANES) {
+    int t = MDL.jnt_type[j], a = MDL.jnt_qadr[j];
     if (t == RSB_JNT_HINGE) {
-      real sn, cs; rsb_sincos(0.5f * (qpos[a] - m.qpos0[a]), &sn, &cs);
-      jq[4 * j] = cs; jq[4 * j + 1] = sn * m.jnt_axis[3 * j]; jq[4 * j + 2] = sn * m.jnt_axis[3 * j + 1]; jq[4 * j + 3] = sn * m.jnt_axis[3 * j + 2];
-    } else if (t == RSB_JNT_SLIDE) jq[4 * j] = qpos[a] - m.qpos0[a];
+      real sn, cs; rsb_sincos(0.5f * (qpos[a] - MDL.qpos0[a]), &sn, &cs);
+      jq[4 * j] = cs; jq[4 * j + 1] = sn * MDL.jnt_axis[3 * j]; jq[4 * j + 2] = sn * MDL.jnt_axis[3 * j + 1]; jq[4 * j + 3] = sn * MDL.jnt_axis[3 * j + 2];
+    } else if (t == RSB_JNT_SLIDE) jq[4 * j] = qpos[a] - MDL.qpos0[a];
     else quatnorm(qpos + a + 3);                   /* mj_kinematics normalises free-joint quaternions in place */
   }
   gsync(g);
@@ -181,25 +198,25 @@ RSB_DN void st_kinematics(const DevModel &m, real *s, Grp g) {
   if (g.lane == 0) {
     xpos[0] = xpos[1] = xpos[2] = 0; xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
     for (int k = 0; k < 9; k++) xmat[k] = (k % 4 == 0) ? 1.0f : 0.0f;
-    for (int b = 1; b < m.nbody; b++) {
-      int p = m.body_parent[b], jn = m.body_jntnum[b], ja = m.body_jntadr[b];
+    for (int b = 1; b < MDL.nbody; b++) {
+      int p = MDL.body_parent[b], jn = MDL.body_jntnum[b], ja = MDL.body_jntadr[b];
       real pos[3], quat[4];
-      if (jn == 1 && m.jnt_type[ja] == RSB_JNT_FREE) {
-        int a = m.jnt_qadr[ja];
+      if (jn == 1 && MDL.jnt_type[ja] == RSB_JNT_FREE) {
+        int a = MDL.jnt_qadr[ja];
         pos[0] = qpos[a]; pos[1] = qpos[a + 1]; pos[2] = qpos[a + 2]; quat[0] = qpos[a + 3]; quat[1] = qpos[a + 4]; quat[2] = qpos[a + 5]; quat[3] = qpos[a + 6];
         xanchor[3 * ja] = pos[0]; xanchor[3 * ja + 1] = pos[1]; xanchor[3 * ja + 2] = pos[2]; xaxis[3 * ja] = 0; xaxis[3 * ja + 1] = 0; xaxis[3 * ja + 2] = 1;
       } else {
-        real t3[3]; matvec3(t3, xmat + 9 * p, m.body_pos + 3 * b);
+        real t3[3]; matvec3(t3, xmat + 9 * p, MDL.body_pos + 3 * b);
         pos[0] = xpos[3 * p] + t3[0]; pos[1] = xpos[3 * p + 1] + t3[1]; pos[2] = xpos[3 * p + 2] + t3[2];
-        quatmul(quat, xquat + 4 * p, m.body_quat + 4 * b);
+        quatmul(quat, xquat + 4 * p, MDL.body_quat + 4 * b);
         for (int k = 0; k < jn; k++) {
           int j = ja + k; real anchor[3], axis[3];
-          quatrot(t3, quat, m.jnt_pos + 3 * j); anchor[0] = pos[0] + t3[0]; anchor[1] = pos[1] + t3[1]; anchor[2] = pos[2] + t3[2];
-          quatrot(axis, quat, m.jnt_axis + 3 * j);
-          if (m.jnt_type[j] == RSB_JNT_SLIDE) { real dq = jq[4 * j]; pos[0] += axis[0] * dq; pos[1] += axis[1] * dq; pos[2] += axis[2] * dq; }
+          quatrot(t3, quat, MDL.jnt_pos + 3 * j); anchor[0] = pos[0] + t3[0]; anchor[1] = pos[1] + t3[1]; anchor[2] = pos[2] + t3[2];
+          quatrot(axis, quat, MDL.jnt_axis + 3 * j);
+          if (MDL.jnt_type[j] == RSB_JNT_SLIDE) { real dq = jq[4 * j]; pos[0] += axis[0] * dq; pos[1] += axis[1] * dq; pos[2] += axis[2] * dq; }
           else {
             real qn[4]; quatmul(qn, quat, jq + 4 * j); quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
-            quatrot(t3, quat, m.jnt_pos + 3 * j); pos[0] = anchor[0] - t3[0]; pos[1] = anchor[1] - t3[1]; pos[2] = anchor[2] - t3[2];
+            quatrot(t3, quat, MDL.jnt_pos + 3 * j); pos[0] = anchor[0] - t3[0]; pos[1] = anchor[1] - t3[1]; pos[2] = anchor[2] - t3[2];
           }
           xanchor[3 * j] = anchor[0]; xanchor[3 * j + 1] = anchor[1]; xanchor[3 * j + 2] = anchor[2];
           xaxis[3 * j] = axis[0]; xaxis[3 * j + 1] = axis[1]; xaxis[3 * j + 2] = axis[2];
@@ -215,10 +232,10 @@ RSB_DN void st_kinematics(const DevModel &m, real *s, Grp g) {
   }
   gsync(g);
   /* geoms and sites, lane-parallel */
-  real *gxpos = s + m.o_gxpos, *gxmat = s + m.o_gxmat, *sxpos = s + m.o_sxpos, *sxmat = s + m.o_sxmat;
-  for (int i = g.lane; i < m.ngeom + m.nsite; i += RSB_LANES) {
-    bool isg = i < m.ngeom; int k = isg ? i : i - m.ngeom; int b = isg ? m.geom_body[k] : m.site_body[k];
-    const real *lp = isg ? m.geom_pos + 3 * k : m.site_pos + 3 * k, *lm = isg ? m.geom_mat + 9 * k : m.site_mat + 9 * k;
+  real *gxpos = s + MDL.o_gxpos, *gxmat = s + MDL.o_gxmat, *sxpos = s + MDL.o_sxpos, *sxmat = s + MDL.o_sxmat;
+  for (int i = g.lane; i < MDL.ngeom + MDL.nsite; i += RSB_LANES) {
+    bool isg = i < MDL.ngeom; int k = isg ? i : i - MDL.ngeom; int b = isg ? MDL.geom_body[k] : MDL.site_body[k];
+    const real *lp = isg ? MDL.geom_pos + 3 * k : MDL.site_pos + 3 * k, *lm = isg ? MDL.geom_mat + 9 * k : MDL.site_mat + 9 * k;
     real t3[3], R[9]; matvec3(t3, xmat + 9 * b, lp); matmul3(R, xmat + 9 * b, lm);
     real *op = isg ? gxpos + 3 * k : sxpos + 3 * k, *om = isg ? gxmat + 9 * k : sxmat + 9 * k;
     op[0] = xpos[3 * b] + t3[0]; op[1] = xpos[3 * b + 1] + t3[1]; op[2] = xpos[3 * b + 2] + t3[2];
@@ -236,18 +253,18 @@ RSB_D void inert_mul(real *f, const real *I, const real *v) {
   cross3(t, h, w); f[3] = I[9] * l[0] - t[0]; f[4] = I[9] * l[1] - t[1]; f[5] = I[9] * l[2] - t[2];
 }
 
-RSB_DN void st_inertia(const DevModel &m, real *s, Grp g) {
-  const real *xpos = s + m.o_xpos, *xmat = s + m.o_xmat, *xanchor = s + m.o_xanchor, *xaxis = s + m.o_xaxis;
-  real *cinert = s + m.o_cinert, *crb = s + m.o_crb, *cdof = s + m.o_cdof, *M = s + m.o_M;
-  for (int b = g.lane; b < m.nbody; b += RSB_LANES) {
+RSB_DN void st_inertia(int so, Grp g) { real *s = RSB_SMEM + so;
+  const real *xpos = s + MDL.o_xpos, *xmat = s + MDL.o_xmat, *xanchor = s + MDL.o_xanchor, *xaxis = s + MDL.o_xaxis;
+  real *cinert = s + MDL.o_cinert, *crb = s + MDL.o_crb, *cdof = s + MDL.o_cdof, *M = s + MDL.o_M;
+  for (int b = g.lane; b < MDL.nbody; b += RSB_LANES) {
     real I[10];
-    real ms = m.body_mass[b];
+    real ms = MDL.body_mass[b];
     if (b == 0 || ms <= 0) { for (int k = 0; k < 10; k++) I[k] = 0; }
     else {
-      int r = m.body_root[b]; real Rw[9], c[3], t3[3];
-      matmul3(Rw, xmat + 9 * b, m.body_imat + 9 * b); matvec3(t3, xmat + 9 * b, m.body_ipos + 3 * b);
+      int r = MDL.body_root[b]; real Rw[9], c[3], t3[3];
+      matmul3(Rw, xmat + 9 * b, MDL.body_imat + 9 * b); matvec3(t3, xmat + 9 * b, MDL.body_ipos + 3 * b);
       c[0] = xpos[3 * b] + t3[0] - xpos[3 * r]; c[1] = xpos[3 * b + 1] + t3[1] - xpos[3 * r + 1]; c[2] = xpos[3 * b + 2] + t3[2] - xpos[3 * r + 2];
-      real d0 = m.body_inertia[3 * b], d1 = m.body_inertia[3 * b + 1], d2 = m.body_inertia[3 * b + 2], cc = dot3(c, c);
+      real d0 = MDL.body_inertia[3 * b], d1 = MDL.body_inertia[3 * b + 1], d2 = MDL.body_inertia[3 * b + 2], cc = dot3(c, c);
       I[0] = Rw[0] * Rw[0] * d0 + Rw[1] * Rw[1] * d1 + Rw[2] * Rw[2] * d2 + ms * (cc - c[0] * c[0]);
       I[1] = Rw[3] * Rw[3] * d0 + Rw[4] * Rw[4] * d1 + Rw[5] * Rw[5] * d2 + ms * (cc - c[1] * c[1]);
       I[2] = Rw[6] * Rw[6] * d0 + Rw[7] * Rw[7] * d1 + Rw[8] * Rw[8] * d2 + ms * (cc - c[2] * c[2]);
@@ -259,40 +276,40 @@ RSB_DN void st_inertia(const DevModel &m, real *s, Grp g) {
 #pragma unroll
     for (int k = 0; k < 10; k++) { cinert[10 * b + k] = I[k]; crb[10 * b + k] = I[k]; }
   }
-  for (int d = g.lane; d < m.nv; d += RSB_LANES) {
-    int kind = m.dof_kind[d], j = m.dof_jnt[d], b = m.dof_body[d], r = m.dof_root[d]; real w[3] = {0, 0, 0}, v[3] = {0, 0, 0};
+  for (int d = g.lane; d < MDL.nv; d += RSB_LANES) {
+    int kind = MDL.dof_kind[d], j = MDL.dof_jnt[d], b = MDL.dof_body[d], r = MDL.dof_root[d]; real w[3] = {0, 0, 0}, v[3] = {0, 0, 0};
     if (kind == RSB_DOF_SLIDE) { v[0] = xaxis[3 * j]; v[1] = xaxis[3 * j + 1]; v[2] = xaxis[3 * j + 2]; }
-    else if (kind == RSB_DOF_FREE_T) { v[d - m.jnt_dadr[j]] = 1; }
+    else if (kind == RSB_DOF_FREE_T) { v[d - MDL.jnt_dadr[j]] = 1; }
     else {
       real off[3];
       if (kind == RSB_DOF_HINGE) {
         w[0] = xaxis[3 * j]; w[1] = xaxis[3 * j + 1]; w[2] = xaxis[3 * j + 2];
         off[0] = xpos[3 * r] - xanchor[3 * j]; off[1] = xpos[3 * r + 1] - xanchor[3 * j + 1]; off[2] = xpos[3 * r + 2] - xanchor[3 * j + 2];
       } else {                                      /* free rotation: body-local axis k expressed in the world */
-        int k = d - m.jnt_dadr[j] - 3; w[0] = xmat[9 * b + k]; w[1] = xmat[9 * b + 3 + k]; w[2] = xmat[9 * b + 6 + k];
+        int k = d - MDL.jnt_dadr[j] - 3; w[0] = xmat[9 * b + k]; w[1] = xmat[9 * b + 3 + k]; w[2] = xmat[9 * b + 6 + k];
         off[0] = xpos[3 * r] - xpos[3 * b]; off[1] = xpos[3 * r + 1] - xpos[3 * b + 1]; off[2] = xpos[3 * r + 2] - xpos[3 * b + 2];
       }
       cross3(v, w, off);                            /* velocity of the reference point under unit rotation */
     }
     cdof[6 * d] = w[0]; cdof[6 * d + 1] = w[1]; cdof[6 * d + 2] = w[2]; cdof[6 * d + 3] = v[0]; cdof[6 * d + 4] = v[1]; cdof[6 * d + 5] = v[2];
   }
-  for (int i = g.lane; i < m.nv * m.ldm; i += RSB_LANES) M[i] = 0;
+  for (int i = g.lane; i < MDL.nv * MDL.ldm; i += RSB_LANES) M[i] = 0;
   gsync(g);
 }
 
 /* ================================================================== A.3.3 composite rigid bodies -> dense symmetric M (+ armature) */
-RSB_DN void st_crb(const DevModel &m, real *s, Grp g) {
-  real *crb = s + m.o_crb, *cdof = s + m.o_cdof, *fi = s + m.o_fi, *M = s + m.o_M;
-  if (g.lane < 10) for (int b = m.nbody - 1; b > 0; b--) crb[10 * m.body_parent[b] + g.lane] += crb[10 * b + g.lane];
+RSB_DN void st_crb(int so, Grp g) { real *s = RSB_SMEM + so;
+  real *crb = s + MDL.o_crb, *cdof = s + MDL.o_cdof, *fi = s + MDL.o_fi, *M = s + MDL.o_M;
+  if (g.lane < 10) for (int b = MDL.nbody - 1; b > 0; b--) crb[10 * MDL.body_parent[b] + g.lane] += crb[10 * b + g.lane];
   gsync(g);
-  for (int d = g.lane; d < m.nv; d += RSB_LANES) { real f[6]; inert_mul(f, crb + 10 * m.dof_body[d], cdof + 6 * d);
+  for (int d = g.lane; d < MDL.nv; d += RSB_LANES) { real f[6]; inert_mul(f, crb + 10 * MDL.dof_body[d], cdof + 6 * d);
 #pragma unroll
     for (int k = 0; k < 6; k++) fi[6 * d + k] = f[k]; }
   gsync(g);
-  for (int p = g.lane; p < m.nmpair; p += RSB_LANES) {
-    int i = m.mpair_i[p], j = m.mpair_j[p]; real v = dot6(cdof + 6 * j, fi + 6 * i);
-    if (i == j) v += m.dof_armature[i];
-    M[i * m.ldm + j] = v; M[j * m.ldm + i] = v;
+  for (int p = g.lane; p < MDL.nmpair; p += RSB_LANES) {
+    int i = MDL.mpair_i[p], j = MDL.mpair_j[p]; real v = dot6(cdof + 6 * j, fi + 6 * i);
+    if (i == j) v += MDL.dof_armature[i];
+    M[i * MDL.ldm + j] = v; M[j * MDL.ldm + i] = v;
   }
   gsync(g);
 }
@@ -307,24 +324,24 @@ RSB_D void crossf(real *o, const real *v, const real *f) {          /* force cro
   o[0] = a[0] + b[0]; o[1] = a[1] + b[1]; o[2] = a[2] + b[2]; o[3] = d[0]; o[4] = d[1]; o[5] = d[2];
 }
 
-RSB_DN void st_bias(const DevModel &m, real *s, Grp g) {
-  const real *qvel = s + m.o_qvel, *qpos = s + m.o_qpos, *cdof = s + m.o_cdof, *cinert = s + m.o_cinert;
-  real *cvel = s + m.o_cvel, *cacc = s + m.o_cacc, *cdd = s + m.o_cdofdot, *bias = s + m.o_bias, *passive = s + m.o_passive;
+RSB_DN void st_bias(int so, Grp g) { real *s = RSB_SMEM + so;
+  const real *qvel = s + MDL.o_qvel, *qpos = s + MDL.o_qpos, *cdof = s + MDL.o_cdof, *cinert = s + MDL.o_cinert;
+  real *cvel = s + MDL.o_cvel, *cacc = s + MDL.o_cacc, *cdd = s + MDL.o_cdofdot, *bias = s + MDL.o_bias, *passive = s + MDL.o_passive;
   /* body velocities: sum over the dof chain (all dofs of a tree share the reference point) */
-  for (int b = g.lane; b < m.nbody; b += RSB_LANES) {
+  for (int b = g.lane; b < MDL.nbody; b += RSB_LANES) {
     real v[6] = {0, 0, 0, 0, 0, 0};
-    for (int d = m.body_lastdof[b]; d >= 0; d = m.dof_parent[d]) { real q = qvel[d];
+    for (int d = MDL.body_lastdof[b]; d >= 0; d = MDL.dof_parent[d]) { real q = qvel[d];
 #pragma unroll
       for (int k = 0; k < 6; k++) v[k] += cdof[6 * d + k] * q; }
 #pragma unroll
     for (int k = 0; k < 6; k++) cvel[6 * b + k] = v[k];
   }
   /* cdof_dot = (velocity accumulated before this dof) x cdof */
-  for (int d = g.lane; d < m.nv; d += RSB_LANES) {
-    real o[6] = {0, 0, 0, 0, 0, 0}; int st = m.dof_velstart[d];
+  for (int d = g.lane; d < MDL.nv; d += RSB_LANES) {
+    real o[6] = {0, 0, 0, 0, 0, 0}; int st = MDL.dof_velstart[d];
     if (st != -2) {
       real v[6] = {0, 0, 0, 0, 0, 0};
-      for (int e = st; e >= 0; e = m.dof_parent[e]) { real q = qvel[e];
+      for (int e = st; e >= 0; e = MDL.dof_parent[e]) { real q = qvel[e];
 #pragma unroll
         for (int k = 0; k < 6; k++) v[k] += cdof[6 * e + k] * q; }
       crossm(o, v, cdof + 6 * d);
@@ -334,9 +351,9 @@ RSB_DN void st_bias(const DevModel &m, real *s, Grp g) {
   }
   gsync(g);
   /* body accelerations (acc = 0, gravity as base acceleration) and body forces */
-  for (int b = g.lane; b < m.nbody; b += RSB_LANES) {
-    real a[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
-    for (int d = m.body_lastdof[b]; d >= 0; d = m.dof_parent[d]) { real q = qvel[d];
+  for (int b = g.lane; b < MDL.nbody; b += RSB_LANES) {
+    real a[6] = {0, 0, 0, -MDL.gravity[0], -MDL.gravity[1], -MDL.gravity[2]};
+    for (int d = MDL.body_lastdof[b]; d >= 0; d = MDL.dof_parent[d]) { real q = qvel[d];
 #pragma unroll
       for (int k = 0; k < 6; k++) a[k] += cdd[6 * d + k] * q; }
     real f[6] = {0, 0, 0, 0, 0, 0};
@@ -347,12 +364,12 @@ RSB_DN void st_bias(const DevModel &m, real *s, Grp g) {
     for (int k = 0; k < 6; k++) cacc[6 * b + k] = f[k];          /* cacc now holds cfrc_body */
   }
   gsync(g);
-  if (g.lane < 6) for (int b = m.nbody - 1; b > 0; b--) cacc[6 * m.body_parent[b] + g.lane] += cacc[6 * b + g.lane];
+  if (g.lane < 6) for (int b = MDL.nbody - 1; b > 0; b--) cacc[6 * MDL.body_parent[b] + g.lane] += cacc[6 * b + g.lane];
   gsync(g);
-  for (int d = g.lane; d < m.nv; d += RSB_LANES) {
-    bias[d] = dot6(cdof + 6 * d, cacc + 6 * m.dof_body[d]);
-    real p = -m.dof_damping[d] * qvel[d]; int j = m.dof_jnt[d];
-    if (m.dof_kind[d] <= RSB_DOF_SLIDE && m.jnt_stiffness[j] != 0) p -= m.jnt_stiffness[j] * (qpos[m.jnt_qadr[j]] - m.qpos_spring[m.jnt_qadr[j]]);
+  for (int d = g.lane; d < MDL.nv; d += RSB_LANES) {
+    bias[d] = dot6(cdof + 6 * d, cacc + 6 * MDL.dof_body[d]);
+    real p = -MDL.dof_damping[d] * qvel[d]; int j = MDL.dof_jnt[d];
+    if (MDL.dof_kind[d] <= RSB_DOF_SLIDE && MDL.jnt_stiffness[j] != 0) p -= MDL.jnt_stiffness[j] * (qpos[MDL.jnt_qadr[j]] - MDL.qpos_spring[MDL.jnt_qadr[j]]);
     passive[d] = p;
   }
   gsync(g);
@@ -534,19 +551,19 @@ RSB_DNOINL int col_box_box(const real *pa, const real *Ra, const real *ha, const
 #define MISC_ITER 2
 #define MISC_NLIMROW 3
 
-RSB_DN void st_collision(const DevModel &m, real *s, Grp g) {
-  const real *gxpos = s + m.o_gxpos, *gxmat = s + m.o_gxmat; real *con = s + m.o_con; int *misc = (int *)(s + m.o_misc);
+RSB_DN void st_collision(int so, Grp g) { real *s = RSB_SMEM + so;
+  const real *gxpos = s + MDL.o_gxpos, *gxmat = s + MDL.o_gxmat; real *con = s + MDL.o_con; int *misc = (int *)(s + MDL.o_misc);
   int base = 0;
-  for (int p0 = 0; p0 < m.npair; p0 += RSB_LANES) {
+  for (int p0 = 0; p0 < MDL.npair; p0 += RSB_LANES) {
     int p = p0 + g.lane; RawCon rc[9]; int n = 0; real inc = 0;
-    if (p < m.npair) {
-      int g1 = m.pair_g1[p], g2 = m.pair_g2[p], t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-      real margin = m.pair_margin[p]; const real *p1 = gxpos + 3 * g1, *p2 = gxpos + 3 * g2, *R1 = gxmat + 9 * g1, *R2 = gxmat + 9 * g2;
-      const real *s1 = m.geom_size + 3 * g1, *s2 = m.geom_size + 3 * g2;
+    if (p < MDL.npair) {
+      int g1 = MDL.pair_g1[p], g2 = MDL.pair_g2[p], t1 = MDL.geom_type[g1], t2 = MDL.geom_type[g2];
+      real margin = MDL.pair_margin[p]; const real *p1 = gxpos + 3 * g1, *p2 = gxpos + 3 * g2, *R1 = gxmat + 9 * g1, *R2 = gxmat + 9 * g2;
+      const real *s1 = MDL.geom_size + 3 * g1, *s2 = MDL.geom_size + 3 * g2;
       bool reject;
       real dv[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
-      if (t1 == RSB_GEOM_PLANE) { real nn[3] = {R1[2], R1[5], R1[8]}; reject = dot3(dv, nn) > m.geom_rbound[g2] + margin; }
-      else { real bound = m.geom_rbound[g1] + m.geom_rbound[g2] + margin; reject = dot3(dv, dv) > bound * bound; }
+      if (t1 == RSB_GEOM_PLANE) { real nn[3] = {R1[2], R1[5], R1[8]}; reject = dot3(dv, nn) > MDL.geom_rbound[g2] + margin; }
+      else { real bound = MDL.geom_rbound[g1] + MDL.geom_rbound[g2] + margin; reject = dot3(dv, dv) > bound * bound; }
       if (!reject) {
         if (t1 == RSB_GEOM_PLANE && t2 == RSB_GEOM_BOX) n = col_plane_box(p1, R1, p2, R2, s2, margin, rc);
         else if (t1 == RSB_GEOM_PLANE && t2 == RSB_GEOM_SPHERE) n = col_plane_sphere(p1, R1, p2, s2[0], margin, rc);
@@ -557,25 +574,25 @@ RSB_DN void st_collision(const DevModel &m, real *s, Grp g) {
         else if (t1 == RSB_GEOM_CAPSULE && t2 == RSB_GEOM_BOX) n = col_capsule_box(p1, R1, s1, p2, R2, s2, margin, rc);
         else if (t1 == RSB_GEOM_BOX && t2 == RSB_GEOM_BOX) n = col_box_box(p1, R1, s1, p2, R2, s2, margin, rc);
       }
-      inc = margin - m.pair_gap[p];
+      inc = margin - MDL.pair_gap[p];
       int keep = 0;                                 /* active contacts only: dist < includemargin; compact in place */
       for (int k = 0; k < n; k++) if (rc[k].dist < inc) { if (keep != k) rc[keep] = rc[k]; keep++; }
       n = keep;
     }
     int incl = gscan_incl(g, n), off = base + incl - n;
     for (int k = 0; k < n; k++) {
-      int c = off + k; if (c >= m.ncon_max) break;
+      int c = off + k; if (c >= MDL.ncon_max) break;
       real *o = con + c * RSB_CONW; int *oi = (int *)o;
       o[0] = rc[k].pos[0]; o[1] = rc[k].pos[1]; o[2] = rc[k].pos[2];
       real fr[9]; fr[0] = rc[k].normal[0]; fr[1] = rc[k].normal[1]; fr[2] = rc[k].normal[2]; make_frame(fr);
 #pragma unroll
       for (int q = 0; q < 9; q++) o[3 + q] = fr[q];
       o[CON_DIST] = rc[k].dist; o[CON_INC] = inc; o[CON_MU] = 0;
-      oi[CON_PAIR] = p; oi[CON_DIM] = m.pair_dim[p]; oi[CON_ADR] = -1; oi[CON_G1] = m.pair_g1[p]; oi[CON_G2] = m.pair_g2[p];
+      oi[CON_PAIR] = p; oi[CON_DIM] = MDL.pair_dim[p]; oi[CON_ADR] = -1; oi[CON_G1] = MDL.pair_g1[p]; oi[CON_G2] = MDL.pair_g2[p];
     }
     base += gshfl_i(g, incl, RSB_LANES - 1);
   }
-  if (base > m.ncon_max) base = m.ncon_max;
+  if (base > MDL.ncon_max) base = MDL.ncon_max;
   if (g.lane == 0) misc[MISC_NCON] = base;
   gsync(g);
 }
@@ -595,41 +612,41 @@ RSB_D real impedance_fn(const real *si, real pos, real margin) {
   else y = 1 - powf(1 - x, pw) / powf(1 - mid, pw - 1);
   return d0 + y * (d1 - d0);
 }
-RSB_D void kb_fn(const DevModel &m, const real *solref, const real *solimp, real *K, real *B) {
+RSB_D void kb_fn(const real *solref, const real *solimp, real *K, real *B) {
   real dmax = solimp[1];
   if (solref[0] > 0) {
-    real tc = fmaxf(solref[0], 2 * m.timestep), dr = solref[1];
+    real tc = fmaxf(solref[0], 2 * MDL.timestep), dr = solref[1];
     real k = dmax * dmax * tc * tc * dr * dr; *K = 1 / fmaxf(k, RSB_MINVAL);
     *B = 2 / fmaxf(dmax * tc, RSB_MINVAL);
   } else { *K = -solref[0] / fmaxf(dmax * dmax, RSB_MINVAL); *B = -solref[1] / fmaxf(dmax, RSB_MINVAL); }
 }
 
-RSB_DN void st_constraint(const DevModel &m, real *s, Grp g) {
-  const real *qpos = s + m.o_qpos, *qvel = s + m.o_qvel, *cdof = s + m.o_cdof, *xpos = s + m.o_xpos;
-  real *con = s + m.o_con, *J = s + m.o_J; int *misc = (int *)(s + m.o_misc);
-  real *epos = s + m.o_epos, *emargin = s + m.o_emargin, *eR = s + m.o_eR, *eD = s + m.o_eD, *earef = s + m.o_earef, *efloss = s + m.o_efloss;
-  int *etype = (int *)(s + m.o_etype), *eid = (int *)(s + m.o_eid);
-  const int ncon = misc[MISC_NCON], nv = m.nv, ldj = m.ldj;
+RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
+  const real *qpos = s + MDL.o_qpos, *qvel = s + MDL.o_qvel, *cdof = s + MDL.o_cdof, *xpos = s + MDL.o_xpos;
+  real *con = s + MDL.o_con, *J = s + MDL.o_J; int *misc = (int *)(s + MDL.o_misc);
+  real *epos = s + MDL.o_epos, *emargin = s + MDL.o_emargin, *eR = s + MDL.o_eR, *eD = s + MDL.o_eD, *earef = s + MDL.o_earef, *efloss = s + MDL.o_efloss;
+  int *etype = (int *)(s + MDL.o_etype), *eid = (int *)(s + MDL.o_eid);
+  const int ncon = misc[MISC_NCON], nv = MDL.nv, ldj = MDL.ldj;
   /* rows 0..nfl-1: dof friction loss (static) */
-  for (int k = g.lane; k < m.nfl; k += RSB_LANES) { etype[k] = EFC_FRICTION; eid[k] = m.fl_dof[k]; epos[k] = 0; emargin[k] = 0; efloss[k] = m.dof_floss[m.fl_dof[k]]; }
+  for (int k = g.lane; k < MDL.nfl; k += RSB_LANES) { etype[k] = EFC_FRICTION; eid[k] = MDL.fl_dof[k]; epos[k] = 0; emargin[k] = 0; efloss[k] = MDL.dof_floss[MDL.fl_dof[k]]; }
   /* joint limits: ordered compaction (joint order, lower side before upper side) */
-  int nrow = m.nfl;
-  for (int k0 = 0; k0 < m.nlimj; k0 += RSB_LANES) {
+  int nrow = MDL.nfl;
+  for (int k0 = 0; k0 < MDL.nlimj; k0 += RSB_LANES) {
     int k = k0 + g.lane, cnt = 0; real dlo = 0, dhi = 0, mg = 0; int j = 0;
-    if (k < m.nlimj) { j = m.lim_jnt[k]; real q = qpos[m.jnt_qadr[j]]; mg = m.jnt_margin[j]; dlo = q - m.jnt_range[2 * j]; dhi = m.jnt_range[2 * j + 1] - q; cnt = (dlo < mg) + (dhi < mg); }
+    if (k < MDL.nlimj) { j = MDL.lim_jnt[k]; real q = qpos[MDL.jnt_qadr[j]]; mg = MDL.jnt_margin[j]; dlo = q - MDL.jnt_range[2 * j]; dhi = MDL.jnt_range[2 * j + 1] - q; cnt = (dlo < mg) + (dhi < mg); }
     int incl = gscan_incl(g, cnt), r = nrow + incl - cnt;
-    if (cnt && dlo < mg && r < m.nefc_max) { etype[r] = EFC_LIMIT; eid[r] = j; epos[r] = dlo; emargin[r] = mg; efloss[r] = 1.0f; r++; }   /* efloss doubles as the sign of J */
-    if (cnt && dhi < mg && r < m.nefc_max) { etype[r] = EFC_LIMIT; eid[r] = j; epos[r] = dhi; emargin[r] = mg; efloss[r] = -1.0f; }
+    if (cnt && dlo < mg && r < MDL.nefc_max) { etype[r] = EFC_LIMIT; eid[r] = j; epos[r] = dlo; emargin[r] = mg; efloss[r] = 1.0f; r++; }   /* efloss doubles as the sign of J */
+    if (cnt && dhi < mg && r < MDL.nefc_max) { etype[r] = EFC_LIMIT; eid[r] = j; epos[r] = dhi; emargin[r] = mg; efloss[r] = -1.0f; }
     nrow += gshfl_i(g, incl, RSB_LANES - 1);
   }
-  if (nrow > m.nefc_max) nrow = m.nefc_max;
+  if (nrow > MDL.nefc_max) nrow = MDL.nefc_max;
   const int nscalar = nrow;
   /* contact row addresses: serial rule of the reference (a contact that does not fit is skipped, later ones may fit) */
   gsync(g);
   if (g.lane == 0) {
     int n = nscalar;
     for (int c = 0; c < ncon; c++) { int *ci = (int *)(con + c * RSB_CONW); int dim = ci[CON_DIM];
-      if (n + dim > m.nefc_max) ci[CON_ADR] = -1; else { ci[CON_ADR] = n; n += dim; } }
+      if (n + dim > MDL.nefc_max) ci[CON_ADR] = -1; else { ci[CON_ADR] = n; n += dim; } }
     misc[MISC_NEFC] = n;
   }
   gsync(g);
@@ -638,18 +655,18 @@ RSB_DN void st_constraint(const DevModel &m, real *s, Grp g) {
   for (int i = g.lane; i < nscalar * nv; i += RSB_LANES) {
     int r = i / nv, d = i - r * nv; real v = 0;
     if (etype[r] == EFC_FRICTION) v = (eid[r] == d) ? 1.0f : 0.0f;
-    else v = (m.jnt_dadr[eid[r]] == d) ? efloss[r] : 0.0f;
+    else v = (MDL.jnt_dadr[eid[r]] == d) ? efloss[r] : 0.0f;
     J[r * ldj + d] = v;
   }
   /* contact rows of J: item = (contact, dof) */
   for (int i = g.lane; i < ncon * nv; i += RSB_LANES) {
     int c = i / nv, d = i - c * nv; const real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr;
     int adr = ci[CON_ADR]; if (adr < 0) continue;
-    int dim = ci[CON_DIM], b1 = m.geom_body[ci[CON_G1]], b2 = m.geom_body[ci[CON_G2]];
-    int sgn = ((m.body_dofmask[b2] >> d) & 1) - ((m.body_dofmask[b1] >> d) & 1);
+    int dim = ci[CON_DIM], b1 = MDL.geom_body[ci[CON_G1]], b2 = MDL.geom_body[ci[CON_G2]];
+    int sgn = ((MDL.body_dofmask[b2] >> d) & 1) - ((MDL.body_dofmask[b1] >> d) & 1);
     real jp[3] = {0, 0, 0}, jr[3] = {0, 0, 0};
     if (sgn != 0) {
-      int r = m.dof_root[d]; real off[3] = {cr[0] - xpos[3 * r], cr[1] - xpos[3 * r + 1], cr[2] - xpos[3 * r + 2]}, t[3];
+      int r = MDL.dof_root[d]; real off[3] = {cr[0] - xpos[3 * r], cr[1] - xpos[3 * r + 1], cr[2] - xpos[3 * r + 2]}, t[3];
       cross3(t, cdof + 6 * d, off); real sg = (real)sgn;
       jp[0] = sg * (cdof[6 * d + 3] + t[0]); jp[1] = sg * (cdof[6 * d + 4] + t[1]); jp[2] = sg * (cdof[6 * d + 5] + t[2]);
       jr[0] = sg * cdof[6 * d]; jr[1] = sg * cdof[6 * d + 1]; jr[2] = sg * cdof[6 * d + 2];
@@ -668,14 +685,14 @@ RSB_DN void st_constraint(const DevModel &m, real *s, Grp g) {
   /* impedance, regulariser, reference acceleration (mj_makeImpedance), lane per row */
   for (int r = g.lane; r < nefc; r += RSB_LANES) {
     const real *solref, *solimp; real diag; int type = etype[r], id = eid[r];
-    if (type == EFC_FRICTION) { solref = m.dof_solref + 2 * id; solimp = m.dof_solimp + 5 * id; diag = m.dof_invw[id]; }
-    else if (type == EFC_LIMIT) { solref = m.jnt_solref + 2 * id; solimp = m.jnt_solimp + 5 * id; diag = m.dof_invw[m.jnt_dadr[id]]; }
+    if (type == EFC_FRICTION) { solref = MDL.dof_solref + 2 * id; solimp = MDL.dof_solimp + 5 * id; diag = MDL.dof_invw[id]; }
+    else if (type == EFC_LIMIT) { solref = MDL.jnt_solref + 2 * id; solimp = MDL.jnt_solimp + 5 * id; diag = MDL.dof_invw[MDL.jnt_dadr[id]]; }
     else {
       const int *ci = (const int *)(con + id * RSB_CONW); int p = ci[CON_PAIR], rr = r - ci[CON_ADR];
-      solref = m.pair_solref + 2 * p; solimp = m.pair_solimp + 5 * p; int o = rr < 3 ? 0 : 1;
-      diag = m.body_invw[2 * m.geom_body[ci[CON_G1]] + o] + m.body_invw[2 * m.geom_body[ci[CON_G2]] + o];
+      solref = MDL.pair_solref + 2 * p; solimp = MDL.pair_solimp + 5 * p; int o = rr < 3 ? 0 : 1;
+      diag = MDL.body_invw[2 * MDL.geom_body[ci[CON_G1]] + o] + MDL.body_invw[2 * MDL.geom_body[ci[CON_G2]] + o];
     }
-    real K, B; kb_fn(m, solref, solimp, &K, &B);
+    real K, B; kb_fn(solref, solimp, &K, &B);
     if (type == EFC_FRICTION || type == EFC_CONTACT_FRICTION) K = 0;
     real imp = impedance_fn(solimp, epos[r], emargin[r]);
     real Rr = fmaxf((1 - imp) / imp * diag, RSB_MINVAL); eR[r] = Rr;
@@ -685,10 +702,10 @@ RSB_DN void st_constraint(const DevModel &m, real *s, Grp g) {
   gsync(g);
   /* elliptic friction rows: R from the normal row and impratio; regularised cone slope mu */
   for (int c = g.lane; c < ncon; c += RSB_LANES) {
-    real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr; int i = ci[CON_ADR], dim = ci[CON_DIM]; const real *fr = m.pair_friction + 5 * ci[CON_PAIR];
+    real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr; int i = ci[CON_ADR], dim = ci[CON_DIM]; const real *fr = MDL.pair_friction + 5 * ci[CON_PAIR];
     if (i < 0) continue;
     if (dim < 2) { cr[CON_MU] = fr[0]; continue; }
-    real ir = fmaxf(m.impratio, RSB_MINVAL);
+    real ir = fmaxf(MDL.impratio, RSB_MINVAL);
     eR[i + 1] = eR[i] / ir; cr[CON_MU] = fr[0] * sqrtf(eR[i + 1] / eR[i]);
     for (int j = 1; j < dim - 1; j++) eR[i + 1 + j] = eR[i + 1] * fr[0] * fr[0] / (fr[j] * fr[j]);
   }
@@ -700,7 +717,7 @@ RSB_DN void st_constraint(const DevModel &m, real *s, Grp g) {
 /* ================================================================== dense Cholesky, lane per row (n <= 2*RSB_LANES) */
 /* In-place lower factor of the symmetric matrix A (only the lower triangle is read).  Pivots below `floor_` are treated as
    dropped directions (pinv-like): the column is zeroed and the pivot set to +inf so solves return 0 along it. */
-RSB_DN void chol_factor(real *A, int n, int ld, Grp g) {
+RSB_DN void chol_factor(int ao, int n, int ld, Grp g) { real *A = RSB_SMEM + ao;
   for (int j = 0; j < n; j++) {
     real sj = 0, s0 = 0, s1 = 0; int i0 = g.lane, i1 = g.lane + RSB_LANES;
     if (i0 >= j && i0 < n) { s0 = A[i0 * ld + j]; for (int k = 0; k < j; k++) s0 -= A[i0 * ld + k] * A[j * ld + k]; }
@@ -713,7 +730,7 @@ RSB_DN void chol_factor(real *A, int n, int ld, Grp g) {
   }
 }
 /* x <- A^-1 x with A = L L^T; x is a shared-memory vector of length n; result visible to all lanes on return */
-RSB_DN void chol_solve(const real *L, int n, int ld, real *x, Grp g) {
+RSB_DN void chol_solve(int lo_, int n, int ld, int xo, Grp g) { const real *L = RSB_SMEM + lo_; real *x = RSB_SMEM + xo;
   int i0 = g.lane, i1 = g.lane + RSB_LANES;
   real b0 = i0 < n ? x[i0] : 0, b1 = i1 < n ? x[i1] : 0;
   for (int k = 0; k < n; k++) {
@@ -753,10 +770,10 @@ RSB_D real scale_action(const DevRobot &rb, int k, real a) {
   return (a - 0.5f * (hi + lo)) * sc + 0.5f * (rb.out_max[k] + rb.out_min[k]);
 }
 
-RSB_DN void ctrl_reset(const DevModel &m, real *s, Grp g) {
-  const real *qpos = s + m.o_qpos, *sxpos = s + m.o_sxpos, *sxmat = s + m.o_sxmat;
-  for (int ri = 0; ri < m.nrobot; ri++) {
-    const DevRobot &rb = m.robot[ri]; real *cs = s + m.o_cs + ri * RSB_CS_WORDS;
+RSB_DN void ctrl_reset(int so, Grp g) { real *s = RSB_SMEM + so;
+  const real *qpos = s + MDL.o_qpos, *sxpos = s + MDL.o_sxpos, *sxmat = s + MDL.o_sxmat;
+  for (int ri = 0; ri < MDL.nrobot; ri++) {
+    const DevRobot &rb = MDL.robot[ri]; real *cs = s + MDL.o_cs + ri * RSB_CS_WORDS;
     for (int k = g.lane; k < RSB_CS_WORDS; k += RSB_LANES) {
       real v = 0;
       if (k < 3) v = sxpos[3 * rb.eef_site + k];
@@ -768,10 +785,10 @@ RSB_DN void ctrl_reset(const DevModel &m, real *s, Grp g) {
   gsync(g);
 }
 
-RSB_DN void ctrl_set_goal(const DevModel &m, real *s, Grp g) {
-  const real *act = s + m.o_act, *sxpos = s + m.o_sxpos, *sxmat = s + m.o_sxmat;
-  if (g.lane < m.nrobot) {
-    int ri = g.lane; const DevRobot &rb = m.robot[ri]; real *cs = s + m.o_cs + ri * RSB_CS_WORDS; const real *a = act + rb.act_off;
+RSB_DN void ctrl_set_goal(int so, Grp g) { real *s = RSB_SMEM + so;
+  const real *act = s + MDL.o_act, *sxpos = s + MDL.o_sxpos, *sxmat = s + MDL.o_sxmat;
+  if (g.lane < MDL.nrobot) {
+    int ri = g.lane; const DevRobot &rb = MDL.robot[ri]; real *cs = s + MDL.o_cs + ri * RSB_CS_WORDS; const real *a = act + rb.act_off;
     if (rb.ctrl_type == RSB_CTRL_OSC_POSE || rb.ctrl_type == RSB_CTRL_OSC_POSITION) {
       real d[6] = {0, 0, 0, 0, 0, 0}; for (int k = 0; k < rb.control_dim; k++) d[k] = scale_action(rb, k, a[k]);
       if (rb.ctrl_type == RSB_CTRL_OSC_POSE && (d[3] != 0 || d[4] != 0 || d[5] != 0)) {
@@ -811,30 +828,30 @@ RSB_D void sym3_solve(const real *A, int ld, const real *b, real *x) {
 }
 
 /* scratch layout for the OSC law (floats, in o_cscr): Jee[42] Lm[49] X[42] A[36](ld 6) F[6] pose[7] y[6] w[6] v6[6] tau[7] */
-RSB_DN void ctrl_run(const DevModel &m, real *s, Grp g) {
-  const real *qpos = s + m.o_qpos, *qvel = s + m.o_qvel, *cdof = s + m.o_cdof, *M = s + m.o_M, *bias = s + m.o_bias;
-  const real *sxpos = s + m.o_sxpos, *sxmat = s + m.o_sxmat, *xpos = s + m.o_xpos, *cvel = s + m.o_cvel;
-  real *ctrl = s + m.o_ctrl; real *scr = s + m.o_cscr;
+RSB_DN void ctrl_run(int so, Grp g) { real *s = RSB_SMEM + so;
+  const real *qpos = s + MDL.o_qpos, *qvel = s + MDL.o_qvel, *cdof = s + MDL.o_cdof, *M = s + MDL.o_M, *bias = s + MDL.o_bias;
+  const real *sxpos = s + MDL.o_sxpos, *sxmat = s + MDL.o_sxmat, *xpos = s + MDL.o_xpos, *cvel = s + MDL.o_cvel;
+  real *ctrl = s + MDL.o_ctrl; real *scr = s + MDL.o_cscr;
   real *Jee = scr, *Lm = scr + 42, *X = scr + 91, *A = scr + 133, *F = scr + 169, *pose = scr + 175, *y = scr + 182, *w = scr + 188, *v6 = scr + 194, *tau = scr + 200;
-  for (int ri = 0; ri < m.nrobot; ri++) {
-    const DevRobot &rb = m.robot[ri]; real *cs = s + m.o_cs + ri * RSB_CS_WORDS;
+  for (int ri = 0; ri < MDL.nrobot; ri++) {
+    const DevRobot &rb = MDL.robot[ri]; real *cs = s + MDL.o_cs + ri * RSB_CS_WORDS;
     if (rb.ctrl_type == RSB_CTRL_OSC_POSE || rb.ctrl_type == RSB_CTRL_OSC_POSITION) {
-      int sb = m.site_body[rb.eef_site], root = m.body_root[sb]; const real *ep = sxpos + 3 * rb.eef_site;
+      int sb = MDL.site_body[rb.eef_site], root = MDL.body_root[sb]; const real *ep = sxpos + 3 * rb.eef_site;
       real off[3] = {ep[0] - xpos[3 * root], ep[1] - xpos[3 * root + 1], ep[2] - xpos[3 * root + 2]};
       if (g.lane < RSB_ARM_DOF) {                    /* site Jacobian, arm columns */
         int c = g.lane, d = rb.arm_dadr[c]; real t[3] = {0, 0, 0}, wv[3] = {0, 0, 0}, lv[3] = {0, 0, 0};
-        if ((m.body_dofmask[sb] >> d) & 1) { cross3(t, cdof + 6 * d, off); wv[0] = cdof[6 * d]; wv[1] = cdof[6 * d + 1]; wv[2] = cdof[6 * d + 2];
+        if ((MDL.body_dofmask[sb] >> d) & 1) { cross3(t, cdof + 6 * d, off); wv[0] = cdof[6 * d]; wv[1] = cdof[6 * d + 1]; wv[2] = cdof[6 * d + 2];
           lv[0] = cdof[6 * d + 3] + t[0]; lv[1] = cdof[6 * d + 4] + t[1]; lv[2] = cdof[6 * d + 5] + t[2]; }
         for (int r = 0; r < 3; r++) { Jee[r * 7 + c] = lv[r]; Jee[(3 + r) * 7 + c] = wv[r]; }
       }
-      for (int i = g.lane; i < 49; i += RSB_LANES) { int r = i / 7, c = i - 7 * r; Lm[i] = M[rb.arm_dadr[r] * m.ldm + rb.arm_dadr[c]]; }
+      for (int i = g.lane; i < 49; i += RSB_LANES) { int r = i / 7, c = i - 7 * r; Lm[i] = M[rb.arm_dadr[r] * MDL.ldm + rb.arm_dadr[c]]; }
       if (g.lane == 8) {                             /* site velocity = full Jacobian x qvel = body twist moved to the site */
         const real *cv = cvel + 6 * sb; real t[3]; cross3(t, cv, off);
         v6[0] = cv[3] + t[0]; v6[1] = cv[4] + t[1]; v6[2] = cv[5] + t[2]; v6[3] = cv[0]; v6[4] = cv[1]; v6[5] = cv[2];
       }
       if (g.lane >= 9 && g.lane < 16) { int k = g.lane - 9; real kn = rb.null_kp; pose[k] = kn * (cs[CS_INITJ + k] - qpos[rb.arm_qadr[k]]) - 2 * sqrtf(kn) * qvel[rb.arm_dadr[k]]; }
       gsync(g);
-      chol_factor(Lm, 7, 7, g);
+      chol_factor(SOFF(Lm), 7, 7, g);
       if (g.lane < 6) {                              /* X[r][:] = M^-1 J[r][:]^T */
         real x[7];
 #pragma unroll
@@ -858,13 +875,13 @@ RSB_DN void ctrl_run(const DevModel &m, real *s, Grp g) {
         if (rb.uncouple) { sym3_solve(A, 6, F, w); sym3_solve(A + 21, 6, F + 3, w + 3); }
       }
       gsync(g);
-      chol_factor(A, 6, 6, g);
-      chol_solve(A, 6, 6, y, g);                     /* y = Lambda_full J pose */
-      if (!rb.uncouple) { chol_solve(A, 6, 6, F, g); if (g.lane < 6) w[g.lane] = F[g.lane]; gsync(g); }
+      chol_factor(SOFF(A), 6, 6, g);
+      chol_solve(SOFF(A), 6, 6, SOFF(y), g);                     /* y = Lambda_full J pose */
+      if (!rb.uncouple) { chol_solve(SOFF(A), 6, 6, SOFF(F), g); if (g.lane < 6) w[g.lane] = F[g.lane]; gsync(g); }
       if (g.lane < RSB_ARM_DOF) {
         int c = g.lane; real t = bias[rb.arm_dadr[c]];
         for (int r = 0; r < 6; r++) t += Jee[r * 7 + c] * (w[r] - y[r]);
-        for (int k = 0; k < 7; k++) t += M[rb.arm_dadr[c] * m.ldm + rb.arm_dadr[k]] * pose[k];
+        for (int k = 0; k < 7; k++) t += M[rb.arm_dadr[c] * MDL.ldm + rb.arm_dadr[k]] * pose[k];
         tau[c] = t;
       }
     } else if (rb.ctrl_type == RSB_CTRL_JOINT_VELOCITY) {
@@ -888,9 +905,9 @@ RSB_DN void ctrl_run(const DevModel &m, real *s, Grp g) {
     if (g.lane < RSB_ARM_DOF) { int k = g.lane; real t = clampf(tau[k], rb.tl_lo[k], rb.tl_hi[k]); tau[k] = t; ctrl[rb.arm_act[k]] = t; }
     /* gripper: integrate the binary open/close command (robosuite Gripper.format_action) */
     if (rb.grip_action_dim > 0 && g.lane >= 16 && g.lane < 16 + rb.grip_ndof) {
-      int k = g.lane - 16; real ga = s[m.o_act + rb.act_off + rb.control_dim]; real sg = ga > 0 ? 1.0f : (ga < 0 ? -1.0f : 0.0f);
+      int k = g.lane - 16; real ga = s[MDL.o_act + rb.act_off + rb.control_dim]; real sg = ga > 0 ? 1.0f : (ga < 0 ? -1.0f : 0.0f);
       real v = clampf(cs[CS_GRIP + k] + rb.grip_sign[k] * rb.grip_speed * sg, -1.0f, 1.0f); cs[CS_GRIP + k] = v;
-      int a = rb.grip_act[k]; real lo = m.act_crange[2 * a], hi = m.act_crange[2 * a + 1];
+      int a = rb.grip_act[k]; real lo = MDL.act_crange[2 * a], hi = MDL.act_crange[2 * a + 1];
       ctrl[a] = 0.5f * (hi + lo) + 0.5f * (hi - lo) * v;
     }
     gsync(g);
@@ -901,24 +918,24 @@ RSB_DN void ctrl_run(const DevModel &m, real *s, Grp g) {
 }
 
 /* ================================================================== actuation + smooth acceleration */
-RSB_DN void st_actuation(const DevModel &m, real *s, Grp g) {
-  const real *qpos = s + m.o_qpos, *qvel = s + m.o_qvel, *ctrl = s + m.o_ctrl, *bias = s + m.o_bias, *passive = s + m.o_passive, *M = s + m.o_M;
-  real *actf = s + m.o_actuator, *smooth = s + m.o_smooth, *qas = s + m.o_qacc_smooth, *L = s + m.o_L;
-  for (int d = g.lane; d < m.nv; d += RSB_LANES) {
+RSB_DN void st_actuation(int so, Grp g) { real *s = RSB_SMEM + so;
+  const real *qpos = s + MDL.o_qpos, *qvel = s + MDL.o_qvel, *ctrl = s + MDL.o_ctrl, *bias = s + MDL.o_bias, *passive = s + MDL.o_passive, *M = s + MDL.o_M;
+  real *actf = s + MDL.o_actuator, *smooth = s + MDL.o_smooth, *qas = s + MDL.o_qacc_smooth, *L = s + MDL.o_L;
+  for (int d = g.lane; d < MDL.nv; d += RSB_LANES) {
     real f = 0;
-    for (int a = 0; a < m.nu; a++) if (m.act_dof[a] == d) {
-      real c = ctrl[a]; if (m.act_climited[a]) c = clampf(c, m.act_crange[2 * a], m.act_crange[2 * a + 1]);
-      int qa = m.jnt_qadr[m.dof_jnt[d]]; real gear = m.act_gear[a], len = qpos[qa] * gear, vel = qvel[d] * gear;
-      real fa = m.act_gain[a] * c + m.act_bias[3 * a] + m.act_bias[3 * a + 1] * len + m.act_bias[3 * a + 2] * vel;
-      if (m.act_flimited[a]) fa = clampf(fa, m.act_frange[2 * a], m.act_frange[2 * a + 1]);
+    for (int a = 0; a < MDL.nu; a++) if (MDL.act_dof[a] == d) {
+      real c = ctrl[a]; if (MDL.act_climited[a]) c = clampf(c, MDL.act_crange[2 * a], MDL.act_crange[2 * a + 1]);
+      int qa = MDL.jnt_qadr[MDL.dof_jnt[d]]; real gear = MDL.act_gear[a], len = qpos[qa] * gear, vel = qvel[d] * gear;
+      real fa = MDL.act_gain[a] * c + MDL.act_bias[3 * a] + MDL.act_bias[3 * a + 1] * len + MDL.act_bias[3 * a + 2] * vel;
+      if (MDL.act_flimited[a]) fa = clampf(fa, MDL.act_frange[2 * a], MDL.act_frange[2 * a + 1]);
       f += gear * fa;
     }
     actf[d] = f; real sm = passive[d] - bias[d] + f; smooth[d] = sm; qas[d] = sm;
   }
-  for (int i = g.lane; i < m.nv * m.ldm; i += RSB_LANES) L[i] = M[i];
+  for (int i = g.lane; i < MDL.nv * MDL.ldm; i += RSB_LANES) L[i] = M[i];
   gsync(g);
-  chol_factor(L, m.nv, m.ldm, g);
-  chol_solve(L, m.nv, m.ldm, qas, g);
+  chol_factor(so + MDL.o_L, MDL.nv, MDL.ldm, g);
+  chol_solve(so + MDL.o_L, MDL.nv, MDL.ldm, so + MDL.o_qacc_smooth, g);
 }
 
 /* ================================================================== A.3.7 constraint solver (Newton, exact line search) */
@@ -926,9 +943,9 @@ struct LsAcc { real cost, d1, d2; };
 
 /* Evaluate the constraint cost of this lane's rows at x = jar + alpha*Jv.
    mode 0: cost only; mode 1: cost + force + Hessian weights (ew, Hc); mode 2: cost + line-search derivatives. */
-RSB_D void efc_eval(const DevModel &m, real *s, Grp g, int nefc, real alpha, int mode, LsAcc *acc) {
-  const real *con = s + m.o_con, *eD = s + m.o_eD, *eR = s + m.o_eR, *efloss = s + m.o_efloss, *jar = s + m.o_ejar, *Jv = s + m.o_eJv;
-  real *force = s + m.o_eforce, *ew = s + m.o_ew, *Hc = s + m.o_Hc; const int *etype = (const int *)(s + m.o_etype), *eid = (const int *)(s + m.o_eid);
+RSB_DN LsAcc efc_eval(int so, Grp g, int nefc, real alpha, int mode) { real *s = RSB_SMEM + so;
+  const real *con = s + MDL.o_con, *eD = s + MDL.o_eD, *eR = s + MDL.o_eR, *efloss = s + MDL.o_efloss, *jar = s + MDL.o_ejar, *Jv = s + MDL.o_eJv;
+  real *force = s + MDL.o_eforce, *ew = s + MDL.o_ew, *Hc = s + MDL.o_Hc; const int *etype = (const int *)(s + MDL.o_etype), *eid = (const int *)(s + MDL.o_eid);
   real cost = 0, d1 = 0, d2 = 0;
   for (int r = g.lane; r < nefc; r += RSB_LANES) {
     int type = etype[r]; real D = eD[r];
@@ -948,7 +965,7 @@ RSB_D void efc_eval(const DevModel &m, real *s, Grp g, int nefc, real alpha, int
       continue;
     }
     /* elliptic cone, dim in {3, 4} */
-    const real *fr = m.pair_friction + 5 * ((const int *)cr)[CON_PAIR]; real mu = cr[CON_MU];
+    const real *fr = MDL.pair_friction + 5 * ((const int *)cr)[CON_PAIR]; real mu = cr[CON_MU];
     real sc[RSB_MAXDIM], U[RSB_MAXDIM], dU[RSB_MAXDIM], xs[RSB_MAXDIM], dxs[RSB_MAXDIM]; sc[0] = mu; real T2 = 0;
 #pragma unroll
     for (int j = 0; j < RSB_MAXDIM; j++) if (j < dim) {
@@ -989,42 +1006,42 @@ RSB_D void efc_eval(const DevModel &m, real *s, Grp g, int nefc, real alpha, int
       }
     }
   }
-  acc->cost = cost; acc->d1 = d1; acc->d2 = d2;
+  LsAcc acc; acc.cost = cost; acc.d1 = d1; acc.d2 = d2; return acc;
 }
 
 /* jar = J qacc - aref (lane per row); returns the total cost (Gauss + constraint), identical on all lanes */
-RSB_D real solver_cost(const DevModel &m, real *s, Grp g, int nefc, const real *qacc) {
-  const real *J = s + m.o_J, *earef = s + m.o_earef, *M = s + m.o_M, *qas = s + m.o_qacc_smooth; real *jar = s + m.o_ejar;
-  for (int r = g.lane; r < nefc; r += RSB_LANES) { real a = -earef[r]; for (int d = 0; d < m.nv; d++) a += J[r * m.ldj + d] * qacc[d]; jar[r] = a; }
+RSB_DN real solver_cost(int so, Grp g, int nefc, int qo) { real *s = RSB_SMEM + so; const real *qacc = RSB_SMEM + qo;
+  const real *J = s + MDL.o_J, *earef = s + MDL.o_earef, *M = s + MDL.o_M, *qas = s + MDL.o_qacc_smooth; real *jar = s + MDL.o_ejar;
+  for (int r = g.lane; r < nefc; r += RSB_LANES) { real a = -earef[r]; for (int d = 0; d < MDL.nv; d++) a += J[r * MDL.ldj + d] * qacc[d]; jar[r] = a; }
   real gs = 0;
-  for (int i = g.lane; i < m.nv; i += RSB_LANES) { real md = 0; for (int j = 0; j < m.nv; j++) md += M[i * m.ldm + j] * (qacc[j] - qas[j]); gs += 0.5f * (qacc[i] - qas[i]) * md; }
+  for (int i = g.lane; i < MDL.nv; i += RSB_LANES) { real md = 0; for (int j = 0; j < MDL.nv; j++) md += M[i * MDL.ldm + j] * (qacc[j] - qas[j]); gs += 0.5f * (qacc[i] - qas[i]) * md; }
   gsync(g);
-  LsAcc a; efc_eval(m, s, g, nefc, 0.0f, 0, &a);
+  LsAcc a = efc_eval(so, g, nefc, 0.0f, 0);
   return gsum(g, gs + a.cost);
 }
 
-RSB_DN void st_solve(const DevModel &m, real *s, Grp g) {
-  int *misc = (int *)(s + m.o_misc); const int nefc = misc[MISC_NEFC], nv = m.nv, ldm = m.ldm, ldj = m.ldj;
-  real *qacc = s + m.o_qacc, *qas = s + m.o_qacc_smooth, *warm = s + m.o_warm, *qfc = s + m.o_qfc, *grad = s + m.o_grad, *search = s + m.o_search, *Mv = s + m.o_Mv, *tmpv = s + m.o_tmpv;
-  const real *M = s + m.o_M, *J = s + m.o_J; real *H = s + m.o_L, *force = s + m.o_eforce, *ew = s + m.o_ew, *Jv = s + m.o_eJv, *jar = s + m.o_ejar, *Hc = s + m.o_Hc;
-  const real *con = s + m.o_con;
+RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
+  int *misc = (int *)(s + MDL.o_misc); const int nefc = misc[MISC_NEFC], nv = MDL.nv, ldm = MDL.ldm, ldj = MDL.ldj;
+  real *qacc = s + MDL.o_qacc, *qas = s + MDL.o_qacc_smooth, *warm = s + MDL.o_warm, *qfc = s + MDL.o_qfc, *grad = s + MDL.o_grad, *search = s + MDL.o_search, *Mv = s + MDL.o_Mv, *tmpv = s + MDL.o_tmpv;
+  const real *M = s + MDL.o_M, *J = s + MDL.o_J; real *H = s + MDL.o_L, *force = s + MDL.o_eforce, *ew = s + MDL.o_ew, *Jv = s + MDL.o_eJv, *jar = s + MDL.o_ejar, *Hc = s + MDL.o_Hc;
+  const real *con = s + MDL.o_con;
   if (nefc == 0) {
     for (int d = g.lane; d < nv; d += RSB_LANES) { qacc[d] = qas[d]; qfc[d] = 0; }
     if (g.lane == 0) misc[MISC_ITER] = 0;
     gsync(g); return;
   }
   /* warm start: the cheaper of qacc_warmstart and qacc_smooth */
-  real cw = solver_cost(m, s, g, nefc, warm); gsync(g);
-  real cs0 = solver_cost(m, s, g, nefc, qas); gsync(g);
+  real cw = solver_cost(so, g, nefc, so + MDL.o_warm); gsync(g);
+  real cs0 = solver_cost(so, g, nefc, so + MDL.o_qacc_smooth); gsync(g);
   for (int d = g.lane; d < nv; d += RSB_LANES) { qacc[d] = (cw < cs0) ? warm[d] : qas[d]; tmpv[d] = 0; }
   gsync(g);
-  const real scale = 1.0f / (m.meaninertia * (real)(nv > 1 ? nv : 1));
+  const real scale = 1.0f / (MDL.meaninertia * (real)(nv > 1 ? nv : 1));
   int iter = 0;
-  for (; iter < m.solver_iters; iter++) {
+  for (; iter < MDL.solver_iters; iter++) {
     /* residual rows, forces, Hessian weights */
-    for (int r = g.lane; r < nefc; r += RSB_LANES) { real a = -(s + m.o_earef)[r]; for (int d = 0; d < nv; d++) a += J[r * ldj + d] * qacc[d]; jar[r] = a; }
+    for (int r = g.lane; r < nefc; r += RSB_LANES) { real a = -(s + MDL.o_earef)[r]; for (int d = 0; d < nv; d++) a += J[r * ldj + d] * qacc[d]; jar[r] = a; }
     gsync(g);
-    LsAcc acc; efc_eval(m, s, g, nefc, 0.0f, 1, &acc);
+    efc_eval(so, g, nefc, 0.0f, 1);
     gsync(g);
     /* gradient = M qacc - M qacc_smooth - J^T f  (lane per dof) */
     real gn = 0;
@@ -1037,7 +1054,7 @@ RSB_DN void st_solve(const DevModel &m, real *s, Grp g) {
 #ifdef RSB_EMU_TRACE
     if (g.lane == 0) printf("  it %d scaled|grad| %.3e\n", iter, scale * sqrtf(gn));
 #endif
-    if (scale * sqrtf(gn) < m.solver_tol) break;
+    if (scale * sqrtf(gn) < MDL.solver_tol) break;
     /* H = M + J^T W J (+ cone blocks), lower triangle, lanes over entries */
     for (int e = g.lane; e < nv * nv; e += RSB_LANES) {
       int i = e / nv, j = e - i * nv; if (j > i) continue;
@@ -1057,10 +1074,10 @@ RSB_DN void st_solve(const DevModel &m, real *s, Grp g) {
       }
     }
     gsync(g);
-    chol_factor(H, nv, ldm, g);
+    chol_factor(so + MDL.o_L, nv, ldm, g);
     for (int d = g.lane; d < nv; d += RSB_LANES) search[d] = -grad[d];
     gsync(g);
-    chol_solve(H, nv, ldm, search, g);
+    chol_solve(so + MDL.o_L, nv, ldm, so + MDL.o_search, g);
     /* directional quantities */
     real gq1 = 0, gq2 = 0;
     for (int d = g.lane; d < nv; d += RSB_LANES) { real a = 0; for (int j = 0; j < nv; j++) a += M[d * ldm + j] * search[j]; Mv[d] = a; gq2 += search[d] * a; gq1 += search[d] * (grad[d] + qfc[d]); }
@@ -1069,8 +1086,8 @@ RSB_DN void st_solve(const DevModel &m, real *s, Grp g) {
     gsync(g);
     /* exact line search on the convex 1-D cost: safeguarded Newton on its derivative */
     real lo = 0, hi = -1, alpha = 0, d1_0 = 0;
-    for (int it = 0; it < m.ls_iters; it++) {
-      LsAcc v; efc_eval(m, s, g, nefc, alpha, 2, &v);
+    for (int it = 0; it < MDL.ls_iters; it++) {
+      LsAcc v = efc_eval(so, g, nefc, alpha, 2);
       real d1 = gq1 + alpha * gq2 + gsum(g, v.d1), d2 = gq2 + gsum(g, v.d2);
       if (it == 0) d1_0 = fabsf(d1);
 #ifdef RSB_EMU_TRACE
@@ -1089,10 +1106,10 @@ RSB_DN void st_solve(const DevModel &m, real *s, Grp g) {
     for (int d = g.lane; d < nv; d += RSB_LANES) qacc[d] += alpha * search[d];
     gsync(g);
   }
-  if (iter == m.solver_iters) {                       /* forces must correspond to the final qacc */
-    for (int r = g.lane; r < nefc; r += RSB_LANES) { real a = -(s + m.o_earef)[r]; for (int d = 0; d < nv; d++) a += J[r * ldj + d] * qacc[d]; jar[r] = a; }
+  if (iter == MDL.solver_iters) {                       /* forces must correspond to the final qacc */
+    for (int r = g.lane; r < nefc; r += RSB_LANES) { real a = -(s + MDL.o_earef)[r]; for (int d = 0; d < nv; d++) a += J[r * ldj + d] * qacc[d]; jar[r] = a; }
     gsync(g);
-    LsAcc acc; efc_eval(m, s, g, nefc, 0.0f, 1, &acc);
+    efc_eval(so, g, nefc, 0.0f, 1);
     gsync(g);
     for (int d = g.lane; d < nv; d += RSB_LANES) { real f = 0; for (int r = 0; r < nefc; r++) f += J[r * ldj + d] * force[r]; qfc[d] = f; }
   }
@@ -1101,21 +1118,21 @@ RSB_DN void st_solve(const DevModel &m, real *s, Grp g) {
 }
 
 /* ================================================================== A.3.8 semi-implicit Euler with implicit joint damping */
-RSB_DN void st_euler(const DevModel &m, real *s, Grp g) {
-  real *qpos = s + m.o_qpos, *qvel = s + m.o_qvel, *warm = s + m.o_warm, *L = s + m.o_L, *tmpv = s + m.o_tmpv;
-  const real *M = s + m.o_M, *qacc = s + m.o_qacc, *smooth = s + m.o_smooth, *qfc = s + m.o_qfc; const real h = m.timestep;
-  if (m.any_damping) {
-    for (int i = g.lane; i < m.nv * m.ldm; i += RSB_LANES) { int r = i / m.ldm, c = i - r * m.ldm; L[i] = M[i] + ((r == c) ? h * m.dof_damping[r] : 0.0f); }
-    for (int d = g.lane; d < m.nv; d += RSB_LANES) tmpv[d] = smooth[d] + qfc[d];
+RSB_DN void st_euler(int so, Grp g) { real *s = RSB_SMEM + so;
+  real *qpos = s + MDL.o_qpos, *qvel = s + MDL.o_qvel, *warm = s + MDL.o_warm, *L = s + MDL.o_L, *tmpv = s + MDL.o_tmpv;
+  const real *M = s + MDL.o_M, *qacc = s + MDL.o_qacc, *smooth = s + MDL.o_smooth, *qfc = s + MDL.o_qfc; const real h = MDL.timestep;
+  if (MDL.any_damping) {
+    for (int i = g.lane; i < MDL.nv * MDL.ldm; i += RSB_LANES) { int r = i / MDL.ldm, c = i - r * MDL.ldm; L[i] = M[i] + ((r == c) ? h * MDL.dof_damping[r] : 0.0f); }
+    for (int d = g.lane; d < MDL.nv; d += RSB_LANES) tmpv[d] = smooth[d] + qfc[d];
     gsync(g);
-    chol_factor(L, m.nv, m.ldm, g);
-    chol_solve(L, m.nv, m.ldm, tmpv, g);
-  } else { for (int d = g.lane; d < m.nv; d += RSB_LANES) tmpv[d] = qacc[d]; gsync(g); }
-  for (int d = g.lane; d < m.nv; d += RSB_LANES) { qvel[d] += h * tmpv[d]; warm[d] = qacc[d]; }
+    chol_factor(so + MDL.o_L, MDL.nv, MDL.ldm, g);
+    chol_solve(so + MDL.o_L, MDL.nv, MDL.ldm, so + MDL.o_tmpv, g);
+  } else { for (int d = g.lane; d < MDL.nv; d += RSB_LANES) tmpv[d] = qacc[d]; gsync(g); }
+  for (int d = g.lane; d < MDL.nv; d += RSB_LANES) { qvel[d] += h * tmpv[d]; warm[d] = qacc[d]; }
   gsync(g);
-  for (int j = g.lane; j < m.njnt; j += RSB_LANES) {
-    int qa = m.jnt_qadr[j], d = m.jnt_dadr[j];
-    if (m.jnt_type[j] == RSB_JNT_FREE) {
+  for (int j = g.lane; j < MDL.njnt; j += RSB_LANES) {
+    int qa = MDL.jnt_qadr[j], d = MDL.jnt_dadr[j];
+    if (MDL.jnt_type[j] == RSB_JNT_FREE) {
       for (int k = 0; k < 3; k++) qpos[qa + k] += h * qvel[d + k];
       real w[3] = {qvel[d + 3], qvel[d + 4], qvel[d + 5]}; real wn = sqrtf(dot3(w, w)), ang = wn * h;
       if (ang > 0) { real sn, c; rsb_sincos(0.5f * ang, &sn, &c); real f = sn / wn; real dq[4] = {c, f * w[0], f * w[1], f * w[2]}, qn[4];
@@ -1126,18 +1143,19 @@ RSB_DN void st_euler(const DevModel &m, real *s, Grp g) {
 }
 
 /* ================================================================== one physics substep, the control step, reward, observation */
-RSB_D void fwd_position(const DevModel &m, real *s, Grp g) { st_kinematics(m, s, g); st_inertia(m, s, g); st_crb(m, s, g); st_collision(m, s, g); }
-
-RSB_D void substep(const DevModel &m, real *s, Grp g, bool policy_step) {
-  fwd_position(m, s, g); st_bias(m, s, g); st_constraint(m, s, g);
-  if (policy_step) ctrl_set_goal(m, s, g);
-  ctrl_run(m, s, g);
-  st_actuation(m, s, g); st_solve(m, s, g); st_euler(m, s, g);
+/* Stage sequence of one physics substep.  RSB_CTA_SYNC() between stages keeps all warps of the CTA in the same stage
+   (they then share instruction-cache lines: the whole step is far larger than the I-cache); it carries no data dependency. */
+RSB_D void substep(int so, Grp g, bool policy_step) {
+  st_kinematics(so, g); RSB_CTA_SYNC(); st_inertia(so, g); st_crb(so, g); RSB_CTA_SYNC(); st_collision(so, g); RSB_CTA_SYNC();
+  st_bias(so, g); RSB_CTA_SYNC(); st_constraint(so, g); RSB_CTA_SYNC();
+  if (policy_step) ctrl_set_goal(so, g);
+  ctrl_run(so, g); RSB_CTA_SYNC();
+  st_actuation(so, g); RSB_CTA_SYNC(); st_solve(so, g); RSB_CTA_SYNC(); st_euler(so, g); RSB_CTA_SYNC();
 }
 
 RSB_D bool geom_in(const int *set, int n, int gm) { for (int i = 0; i < n; i++) if (set[i] == gm) return true; return false; }
-RSB_D bool check_grasp(const DevModel &m, const real *s, int ri, int obj_geom) {
-  const DevRobot &rb = m.robot[ri]; const real *con = s + m.o_con; int ncon = ((const int *)(s + m.o_misc))[MISC_NCON]; bool tl = false, tr = false;
+RSB_D bool check_grasp(int so, int ri, int obj_geom) { const real *s = RSB_SMEM + so;
+  const DevRobot &rb = MDL.robot[ri]; const real *con = s + MDL.o_con; int ncon = ((const int *)(s + MDL.o_misc))[MISC_NCON]; bool tl = false, tr = false;
   for (int c = 0; c < ncon; c++) {
     const int *ci = (const int *)(con + c * RSB_CONW); int g1 = ci[CON_G1], g2 = ci[CON_G2];
     if ((geom_in(rb.lfg, rb.nlfg, g1) && g2 == obj_geom) || (geom_in(rb.lfg, rb.nlfg, g2) && g1 == obj_geom)) tl = true;
@@ -1147,51 +1165,51 @@ RSB_D bool check_grasp(const DevModel &m, const real *s, int ri, int obj_geom) {
 }
 
 /* A.6 staged task rewards (evaluated by every lane identically; cheap) */
-RSB_DN real task_reward(const DevModel &m, const real *s) {
-  const real *xpos = s + m.o_xpos, *sxpos = s + m.o_sxpos, *qpos = s + m.o_qpos; real r = 0;
-  const real *eef = sxpos + 3 * m.robot[0].eef_site;
-  if (m.task_id == RSB_TASK_LIFT) {
-    const real *cube = xpos + 3 * m.obj_body[0];
-    if (cube[2] > m.table_height + 0.04f) r = 2.25f;
-    else if (m.reward_shaping) {
+RSB_DN real task_reward(int so) { const real *s = RSB_SMEM + so;
+  const real *xpos = s + MDL.o_xpos, *sxpos = s + MDL.o_sxpos, *qpos = s + MDL.o_qpos; real r = 0;
+  const real *eef = sxpos + 3 * MDL.robot[0].eef_site;
+  if (MDL.task_id == RSB_TASK_LIFT) {
+    const real *cube = xpos + 3 * MDL.obj_body[0];
+    if (cube[2] > MDL.table_height + 0.04f) r = 2.25f;
+    else if (MDL.reward_shaping) {
       real d[3] = {eef[0] - cube[0], eef[1] - cube[1], eef[2] - cube[2]}; r += 1 - tanhf(10.0f * sqrtf(dot3(d, d)));
-      if (check_grasp(m, s, 0, m.obj_geom[0])) r += 0.25f;
+      if (check_grasp(so, 0, MDL.obj_geom[0])) r += 0.25f;
     }
-    return r * m.reward_scale / 2.25f;
+    return r * MDL.reward_scale / 2.25f;
   }
-  if (m.task_id == RSB_TASK_STACK) {
-    const real *A = xpos + 3 * m.obj_body[0], *B = xpos + 3 * m.obj_body[1];
+  if (MDL.task_id == RSB_TASK_STACK) {
+    const real *A = xpos + 3 * MDL.obj_body[0], *B = xpos + 3 * MDL.obj_body[1];
     real d[3] = {eef[0] - A[0], eef[1] - A[1], eef[2] - A[2]}; real dist = sqrtf(dot3(d, d));
-    bool grasp = check_grasp(m, s, 0, m.obj_geom[0]);
+    bool grasp = check_grasp(so, 0, MDL.obj_geom[0]);
     real r_reach = (1 - tanhf(10.0f * dist)) * 0.25f + (grasp ? 0.25f : 0.0f);
-    bool lifted = A[2] > m.table_height + 0.04f; real r_lift = lifted ? 1.0f : 0.0f;
+    bool lifted = A[2] > MDL.table_height + 0.04f; real r_lift = lifted ? 1.0f : 0.0f;
     if (lifted) { real hd = sqrtf((A[0] - B[0]) * (A[0] - B[0]) + (A[1] - B[1]) * (A[1] - B[1])); r_lift += 0.5f * (1 - tanhf(hd)); }
-    bool touch = false; const real *con = s + m.o_con; int ncon = ((const int *)(s + m.o_misc))[MISC_NCON];
+    bool touch = false; const real *con = s + MDL.o_con; int ncon = ((const int *)(s + MDL.o_misc))[MISC_NCON];
     for (int c = 0; c < ncon; c++) { const int *ci = (const int *)(con + c * RSB_CONW); int g1 = ci[CON_G1], g2 = ci[CON_G2];
-      if ((g1 == m.obj_geom[0] && g2 == m.obj_geom[1]) || (g2 == m.obj_geom[0] && g1 == m.obj_geom[1])) touch = true; }
+      if ((g1 == MDL.obj_geom[0] && g2 == MDL.obj_geom[1]) || (g2 == MDL.obj_geom[0] && g1 == MDL.obj_geom[1])) touch = true; }
     real r_stack = (!grasp && r_lift > 0 && touch) ? 2.0f : 0.0f;
-    if (m.reward_shaping) r = fmaxf(r_reach, fmaxf(r_lift, r_stack)); else r = r_stack > 0 ? 2.0f : 0.0f;
-    return r * m.reward_scale / 2.0f;
+    if (MDL.reward_shaping) r = fmaxf(r_reach, fmaxf(r_lift, r_stack)); else r = r_stack > 0 ? 2.0f : 0.0f;
+    return r * MDL.reward_scale / 2.0f;
   }
-  if (m.task_id == RSB_TASK_DOOR) {
-    real hinge = qpos[m.obj_qadr[0]], handle = qpos[m.obj_qadr[1]];
+  if (MDL.task_id == RSB_TASK_DOOR) {
+    real hinge = qpos[MDL.obj_qadr[0]], handle = qpos[MDL.obj_qadr[1]];
     if (hinge > 0.3f) r = 1.0f;
-    else if (m.reward_shaping) {
-      const real *hs = sxpos + 3 * m.obj_site[0]; real d[3] = {eef[0] - hs[0], eef[1] - hs[1], eef[2] - hs[2]};
+    else if (MDL.reward_shaping) {
+      const real *hs = sxpos + 3 * MDL.obj_site[0]; real d[3] = {eef[0] - hs[0], eef[1] - hs[1], eef[2] - hs[2]};
       r += 0.25f * (1 - tanhf(10.0f * sqrtf(dot3(d, d))));
       r += fminf(0.25f * fabsf(handle / (0.5f * RSB_PI)), 0.25f);
     }
-    return r * m.reward_scale;
+    return r * MDL.reward_scale;
   }
   return 0;
 }
 
 /* A.1.4 observation vector, robosuite v1.0 order: per robot [sin q, cos q, qd, eef_pos, eef_quat(xyzw), grip q, grip qd], then object-state.
    Lane-parallel: lane i produces element i (and i+LANES, ...) and writes it straight to `obs` (global memory, coalesced). */
-RSB_D real obs_element(const DevModel &m, const real *s, int i) {
-  const real *qpos = s + m.o_qpos, *qvel = s + m.o_qvel, *xpos = s + m.o_xpos, *xquat = s + m.o_xquat, *sxpos = s + m.o_sxpos;
-  for (int ri = 0; ri < m.nrobot; ri++) {
-    const DevRobot &rb = m.robot[ri]; int n = 28 + 2 * rb.grip_ndof;
+RSB_D real obs_element(int so, int i) { const real *s = RSB_SMEM + so;
+  const real *qpos = s + MDL.o_qpos, *qvel = s + MDL.o_qvel, *xpos = s + MDL.o_xpos, *xquat = s + MDL.o_xquat, *sxpos = s + MDL.o_sxpos;
+  for (int ri = 0; ri < MDL.nrobot; ri++) {
+    const DevRobot &rb = MDL.robot[ri]; int n = 28 + 2 * rb.grip_ndof;
     if (i < n) {
       if (i < 7) return sinf(qpos[rb.arm_qadr[i]]);
       if (i < 14) return cosf(qpos[rb.arm_qadr[i - 7]]);
@@ -1202,112 +1220,113 @@ RSB_D real obs_element(const DevModel &m, const real *s, int i) {
     }
     i -= n;
   }
-  const real *eef = sxpos + 3 * m.robot[0].eef_site;
-  if (m.task_id == RSB_TASK_LIFT) {
-    const real *cube = xpos + 3 * m.obj_body[0];
+  const real *eef = sxpos + 3 * MDL.robot[0].eef_site;
+  if (MDL.task_id == RSB_TASK_LIFT) {
+    const real *cube = xpos + 3 * MDL.obj_body[0];
     if (i < 3) return cube[i];
-    if (i < 7) { int k = i - 3; return xquat[4 * m.obj_body[0] + (k == 3 ? 0 : k + 1)]; }
+    if (i < 7) { int k = i - 3; return xquat[4 * MDL.obj_body[0] + (k == 3 ? 0 : k + 1)]; }
     return eef[i - 7] - cube[i - 7];
   }
-  if (m.task_id == RSB_TASK_STACK) {
-    const real *A = xpos + 3 * m.obj_body[0], *B = xpos + 3 * m.obj_body[1];
+  if (MDL.task_id == RSB_TASK_STACK) {
+    const real *A = xpos + 3 * MDL.obj_body[0], *B = xpos + 3 * MDL.obj_body[1];
     if (i < 3) return A[i];
-    if (i < 7) { int k = i - 3; return xquat[4 * m.obj_body[0] + (k == 3 ? 0 : k + 1)]; }
+    if (i < 7) { int k = i - 3; return xquat[4 * MDL.obj_body[0] + (k == 3 ? 0 : k + 1)]; }
     if (i < 10) return B[i - 7];
-    if (i < 14) { int k = i - 10; return xquat[4 * m.obj_body[1] + (k == 3 ? 0 : k + 1)]; }
+    if (i < 14) { int k = i - 10; return xquat[4 * MDL.obj_body[1] + (k == 3 ? 0 : k + 1)]; }
     if (i < 17) return eef[i - 14] - A[i - 14];
     if (i < 20) return eef[i - 17] - B[i - 17];
     return A[i - 20] - B[i - 20];
   }
-  if (m.task_id == RSB_TASK_DOOR) {
-    const real *door = xpos + 3 * m.obj_body[0], *hs = sxpos + 3 * m.obj_site[0];
+  if (MDL.task_id == RSB_TASK_DOOR) {
+    const real *door = xpos + 3 * MDL.obj_body[0], *hs = sxpos + 3 * MDL.obj_site[0];
     if (i < 3) return door[i];
     if (i < 6) return hs[i - 3];
     if (i < 9) return door[i - 6] - eef[i - 6];
     if (i < 12) return hs[i - 9] - eef[i - 9];
-    return qpos[m.obj_qadr[i - 12]];
+    return qpos[MDL.obj_qadr[i - 12]];
   }
   return 0;
 }
 
 /* persistent state <-> shared memory (state record layout: DevModel::st_*) */
-RSB_D void load_state(const DevModel &m, real *s, const real *st, Grp g) {
-  for (int i = g.lane; i < m.nq; i += RSB_LANES) s[m.o_qpos + i] = st[m.st_qpos + i];
-  for (int i = g.lane; i < m.nv; i += RSB_LANES) { s[m.o_qvel + i] = st[m.st_qvel + i]; s[m.o_warm + i] = st[m.st_warm + i]; }
-  for (int i = g.lane; i < m.nrobot * RSB_CS_WORDS; i += RSB_LANES) s[m.o_cs + i] = st[m.st_cs + i];
-  for (int i = g.lane; i < m.nu; i += RSB_LANES) s[m.o_ctrl + i] = 0;
+RSB_D void load_state(int so, const real *st, Grp g) { real *s = RSB_SMEM + so;
+  for (int i = g.lane; i < MDL.nq; i += RSB_LANES) s[MDL.o_qpos + i] = st[MDL.st_qpos + i];
+  for (int i = g.lane; i < MDL.nv; i += RSB_LANES) { s[MDL.o_qvel + i] = st[MDL.st_qvel + i]; s[MDL.o_warm + i] = st[MDL.st_warm + i]; }
+  for (int i = g.lane; i < MDL.nrobot * RSB_CS_WORDS; i += RSB_LANES) s[MDL.o_cs + i] = st[MDL.st_cs + i];
+  for (int i = g.lane; i < MDL.nu; i += RSB_LANES) s[MDL.o_ctrl + i] = 0;
   gsync(g);
 }
-RSB_D void store_state(const DevModel &m, const real *s, real *st, Grp g) {
-  for (int i = g.lane; i < m.nq; i += RSB_LANES) st[m.st_qpos + i] = s[m.o_qpos + i];
-  for (int i = g.lane; i < m.nv; i += RSB_LANES) { st[m.st_qvel + i] = s[m.o_qvel + i]; st[m.st_warm + i] = s[m.o_warm + i]; }
-  for (int i = g.lane; i < m.nrobot * RSB_CS_WORDS; i += RSB_LANES) st[m.st_cs + i] = s[m.o_cs + i];
+RSB_D void store_state(int so, real *st, Grp g) { const real *s = RSB_SMEM + so;
+  for (int i = g.lane; i < MDL.nq; i += RSB_LANES) st[MDL.st_qpos + i] = s[MDL.o_qpos + i];
+  for (int i = g.lane; i < MDL.nv; i += RSB_LANES) { st[MDL.st_qvel + i] = s[MDL.o_qvel + i]; st[MDL.st_warm + i] = s[MDL.o_warm + i]; }
+  for (int i = g.lane; i < MDL.nrobot * RSB_CS_WORDS; i += RSB_LANES) st[MDL.st_cs + i] = s[MDL.o_cs + i];
 }
 
 /* One control step of one env (robosuite MujocoEnv.step): 25 x (forward, controller, mj_step), then reward + observation.
    `st` = this env's state record, `action` = [act_dim], `obs` = [obs_dim] output row.  Returns via *reward, *done.
    Stepping a finished episode leaves the state untouched and reports done = 2 (the host raises ValueError). */
-RSB_D void env_step(const DevModel &m, real *s, Grp g, real *st, const real *action, real *obs, real *reward, unsigned char *done) {
-  int t = f2i(st[m.st_time]);
-  bool finished = (t >= m.horizon) && !m.ignore_done;
-  if (finished) { if (g.lane == 0) { *done = 2; *reward = 0; } return; }
-  load_state(m, s, st, g);
-  for (int i = g.lane; i < m.act_dim; i += RSB_LANES) s[m.o_act + i] = action[i];
+RSB_D void env_step(int so, Grp g, real *st, const real *action, real *obs, real *reward, unsigned char *done, bool commit) { real *s = RSB_SMEM + so;
+  int t = f2i(st[MDL.st_time]);
+  const bool finished = (t >= MDL.horizon) && !MDL.ignore_done;
+  load_state(so, st, g);
+  for (int i = g.lane; i < MDL.act_dim; i += RSB_LANES) s[MDL.o_act + i] = action[i];
   gsync(g);
-  for (int k = 0; k < m.substeps; k++) substep(m, s, g, k == 0);
-  st_kinematics(m, s, g); gsync(g); st_collision(m, s, g);   /* observations / reward read the post-step kinematics and contacts */
-  real r = task_reward(m, s);
-  for (int i = g.lane; i < m.obs_dim; i += RSB_LANES) obs[i] = obs_element(m, s, i);
-  store_state(m, s, st, g);
-  if (g.lane == 0) { t++; st[m.st_time] = i2f(t); *reward = r; *done = ((t >= m.horizon) && !m.ignore_done) ? 1 : 0; }
+  for (int k = 0; k < MDL.substeps; k++) substep(so, g, k == 0);
+  st_kinematics(so, g); RSB_CTA_SYNC(); st_collision(so, g);   /* observations / reward read the post-step kinematics and contacts */
+  if (!commit) return;                               /* padding warp of the last CTA: ran only to reach the barriers */
+  if (finished) { if (g.lane == 0) { *done = 2; *reward = 0; } return; }      /* state untouched; host raises ValueError */
+  real r = task_reward(so);
+  for (int i = g.lane; i < MDL.obs_dim; i += RSB_LANES) obs[i] = obs_element(so, i);
+  store_state(so, st, g);
+  if (g.lane == 0) { t++; st[MDL.st_time] = i2f(t); *reward = r; *done = ((t >= MDL.horizon) && !MDL.ignore_done) ? 1 : 0; }
 }
 
 /* robosuite MujocoEnv.reset (hard_reset = False): sim.reset, noisy arm init, object placement, new controller, forward, obs.
    Randomness: Philox keyed (seed, env_id), stream 0, counter = episode*8 + block -- identical to the oracle's orc_reset. */
-RSB_D void env_reset(const DevModel &m, real *s, Grp g, real *st, uint64_t seed, uint64_t env_id, real *obs) {
-  int episode = f2i(st[m.st_episode]);
-  real *qpos = s + m.o_qpos;
-  for (int i = g.lane; i < m.nq; i += RSB_LANES) qpos[i] = m.qpos0[i];
-  for (int i = g.lane; i < m.nv; i += RSB_LANES) { s[m.o_qvel + i] = 0; s[m.o_warm + i] = 0; }
+RSB_D void env_reset(int so, Grp g, real *st, uint64_t seed, uint64_t env_id, real *obs) { real *s = RSB_SMEM + so;
+  int episode = f2i(st[MDL.st_episode]);
+  real *qpos = s + MDL.o_qpos;
+  for (int i = g.lane; i < MDL.nq; i += RSB_LANES) qpos[i] = MDL.qpos0[i];
+  for (int i = g.lane; i < MDL.nv; i += RSB_LANES) { s[MDL.o_qvel + i] = 0; s[MDL.o_warm + i] = 0; }
   gsync(g);
-  if (g.lane < m.nrobot) {
-    const DevRobot &rb = m.robot[g.lane]; real z[8]; uint32_t r[4];
+  if (g.lane < MDL.nrobot) {
+    const DevRobot &rb = MDL.robot[g.lane]; real z[8]; uint32_t r[4];
     for (int blk = 0; blk < 2; blk++) {
       rsb_philox(seed, env_id, 0, (uint32_t)(episode * 8 + (g.lane * 2 + blk)), r);
       box_muller(r[0], r[1], &z[4 * blk], &z[4 * blk + 1]); box_muller(r[2], r[3], &z[4 * blk + 2], &z[4 * blk + 3]);
     }
-    for (int k = 0; k < RSB_ARM_DOF; k++) qpos[rb.arm_qadr[k]] = rb.init_qpos[k] + m.init_noise * z[k];
+    for (int k = 0; k < RSB_ARM_DOF; k++) qpos[rb.arm_qadr[k]] = rb.init_qpos[k] + MDL.init_noise * z[k];
     for (int k = 0; k < rb.grip_ndof; k++) qpos[rb.grip_qadr[k]] = rb.grip_init[k];
   }
   if (g.lane == RSB_LANES - 1) {                      /* object placement: uniform xy + yaw, rejection on overlap (serial over objects) */
     for (int o = 0; o < RSB_MAX_OBJ; o++) {
-      if (m.obj_qadr[o] < 0 || m.place_z[o] <= 0) continue;
-      int qa = m.obj_qadr[o]; real x = 0, y = 0, yaw = 0; uint32_t r[4];
+      if (MDL.obj_qadr[o] < 0 || MDL.place_z[o] <= 0) continue;
+      int qa = MDL.obj_qadr[o]; real x = 0, y = 0, yaw = 0; uint32_t r[4];
       for (int attempt = 0; attempt < 16; attempt++) {
         rsb_philox(seed, env_id, 0, (uint32_t)(episode * 8 + 4 + o) + 0x10000u * (uint32_t)attempt, r);
         double u0 = ((double)r[0] + 0.5) * (1.0 / 4294967296.0), u1 = ((double)r[1] + 0.5) * (1.0 / 4294967296.0), u2 = ((double)r[2] + 0.5) * (1.0 / 4294967296.0);
-        x = (real)(m.place_x[o][0] + (m.place_x[o][1] - m.place_x[o][0]) * u0);
-        y = (real)(m.place_y[o][0] + (m.place_y[o][1] - m.place_y[o][0]) * u1);
-        yaw = (real)(m.place_yaw[o][0] + (m.place_yaw[o][1] - m.place_yaw[o][0]) * u2);
+        x = (real)(MDL.place_x[o][0] + (MDL.place_x[o][1] - MDL.place_x[o][0]) * u0);
+        y = (real)(MDL.place_y[o][0] + (MDL.place_y[o][1] - MDL.place_y[o][0]) * u1);
+        yaw = (real)(MDL.place_yaw[o][0] + (MDL.place_yaw[o][1] - MDL.place_yaw[o][0]) * u2);
         bool ok = true;
-        for (int p = 0; p < o; p++) if (m.obj_qadr[p] >= 0 && m.place_z[p] > 0) {
-          real dx = x + m.place_ref[0] - qpos[m.obj_qadr[p]], dy = y + m.place_ref[1] - qpos[m.obj_qadr[p] + 1];
-          real rr = sqrtf(m.obj_half[o][0] * m.obj_half[o][0] + m.obj_half[o][1] * m.obj_half[o][1]) + sqrtf(m.obj_half[p][0] * m.obj_half[p][0] + m.obj_half[p][1] * m.obj_half[p][1]);
+        for (int p = 0; p < o; p++) if (MDL.obj_qadr[p] >= 0 && MDL.place_z[p] > 0) {
+          real dx = x + MDL.place_ref[0] - qpos[MDL.obj_qadr[p]], dy = y + MDL.place_ref[1] - qpos[MDL.obj_qadr[p] + 1];
+          real rr = sqrtf(MDL.obj_half[o][0] * MDL.obj_half[o][0] + MDL.obj_half[o][1] * MDL.obj_half[o][1]) + sqrtf(MDL.obj_half[p][0] * MDL.obj_half[p][0] + MDL.obj_half[p][1] * MDL.obj_half[p][1]);
           if (dx * dx + dy * dy < rr * rr) ok = false;
         }
         if (ok) break;
       }
       real sn, c; rsb_sincos(0.5f * yaw, &sn, &c);
-      qpos[qa] = m.place_ref[0] + x; qpos[qa + 1] = m.place_ref[1] + y; qpos[qa + 2] = m.place_z[o];
+      qpos[qa] = MDL.place_ref[0] + x; qpos[qa + 1] = MDL.place_ref[1] + y; qpos[qa + 2] = MDL.place_z[o];
       qpos[qa + 3] = c; qpos[qa + 4] = 0; qpos[qa + 5] = 0; qpos[qa + 6] = sn;
     }
   }
   gsync(g);
-  st_kinematics(m, s, g); gsync(g);
-  ctrl_reset(m, s, g);
-  for (int i = g.lane; i < m.obs_dim; i += RSB_LANES) obs[i] = obs_element(m, s, i);
-  store_state(m, s, st, g);
-  if (g.lane == 0) { st[m.st_time] = i2f(0); st[m.st_episode] = i2f(episode + 1); }
+  st_kinematics(so, g);
+  ctrl_reset(so, g);
+  for (int i = g.lane; i < MDL.obs_dim; i += RSB_LANES) obs[i] = obs_element(so, i);
+  store_state(so, st, g);
+  if (g.lane == 0) { st[MDL.st_time] = i2f(0); st[MDL.st_episode] = i2f(episode + 1); }
 }
 
 /* synthetic action stream shared with the oracle: a = tanh(N(0,1)) keyed (seed, env, step, dim), stream 1 */
@@ -1318,25 +1337,25 @@ RSB_D void random_action_block(uint64_t seed, uint64_t env_id, uint64_t step, in
 }
 
 /* debug record (floats) for parity tests; layout documented in rsb_devmodel.h / tests/emu */
-RSB_D void dump_debug(const DevModel &m, const real *s, Grp g, real *out) {
-  const int *misc = (const int *)(s + m.o_misc); int nv = m.nv, nc = m.ncon_max, ne = m.nefc_max;
+RSB_D void dump_debug(int so, Grp g, real *out) { const real *s = RSB_SMEM + so;
+  const int *misc = (const int *)(s + MDL.o_misc); int nv = MDL.nv, nc = MDL.ncon_max, ne = MDL.nefc_max;
   if (g.lane == 0) { out[0] = (real)misc[MISC_NCON]; out[1] = (real)misc[MISC_NEFC]; out[2] = (real)misc[MISC_ITER]; }
   real *o = out + 8;
-  for (int i = g.lane; i < nv * nv; i += RSB_LANES) o[i] = s[m.o_M + (i / nv) * m.ldm + i % nv];
+  for (int i = g.lane; i < nv * nv; i += RSB_LANES) o[i] = s[MDL.o_M + (i / nv) * MDL.ldm + i % nv];
   o += nv * nv;
-  const int vecs[8] = {m.o_bias, m.o_passive, m.o_actuator, m.o_qacc_smooth, m.o_qacc, m.o_qfc, m.o_smooth, m.o_warm};
+  const int vecs[8] = {MDL.o_bias, MDL.o_passive, MDL.o_actuator, MDL.o_qacc_smooth, MDL.o_qacc, MDL.o_qfc, MDL.o_smooth, MDL.o_warm};
   for (int k = 0; k < 8; k++) for (int i = g.lane; i < nv; i += RSB_LANES) o[k * nv + i] = s[vecs[k] + i];
   o += 8 * nv;
-  for (int i = g.lane; i < 14; i += RSB_LANES) o[i] = s[m.o_cscr + 208 + i];
+  for (int i = g.lane; i < 14; i += RSB_LANES) o[i] = s[MDL.o_cscr + 208 + i];
   o += 14;
-  for (int i = g.lane; i < nc * 16; i += RSB_LANES) { int c = i / 16, k = i % 16; const real *cr = s + m.o_con + c * RSB_CONW; const int *ci = (const int *)cr;
+  for (int i = g.lane; i < nc * 16; i += RSB_LANES) { int c = i / 16, k = i % 16; const real *cr = s + MDL.o_con + c * RSB_CONW; const int *ci = (const int *)cr;
     real v = 0; if (c < misc[MISC_NCON]) { if (k < 13) v = cr[k]; else if (k == 13) v = (real)ci[CON_G1]; else if (k == 14) v = (real)ci[CON_G2]; else v = cr[CON_MU]; } o[i] = v; }
   o += nc * 16;
-  const int ev[5] = {m.o_earef, m.o_eR, m.o_eforce, m.o_epos, m.o_ejar};
+  const int ev[5] = {MDL.o_earef, MDL.o_eR, MDL.o_eforce, MDL.o_epos, MDL.o_ejar};
   for (int k = 0; k < 5; k++) for (int i = g.lane; i < ne; i += RSB_LANES) o[k * ne + i] = i < misc[MISC_NEFC] ? s[ev[k] + i] : 0;
-  for (int i = g.lane; i < ne; i += RSB_LANES) o[5 * ne + i] = i < misc[MISC_NEFC] ? (real)((const int *)(s + m.o_etype))[i] : -1;
+  for (int i = g.lane; i < ne; i += RSB_LANES) o[5 * ne + i] = i < misc[MISC_NEFC] ? (real)((const int *)(s + MDL.o_etype))[i] : -1;
   o += 6 * ne;
-  for (int i = g.lane; i < ne * nv; i += RSB_LANES) { int r = i / nv, d = i % nv; o[i] = r < misc[MISC_NEFC] ? s[m.o_J + r * m.ldj + d] : 0; }
+  for (int i = g.lane; i < ne * nv; i += RSB_LANES) { int r = i / nv, d = i % nv; o[i] = r < misc[MISC_NEFC] ? s[MDL.o_J + r * MDL.ldj + d] : 0; }
 }
 
 #endif /* RSB_DEV_H */

@@ -16,6 +16,9 @@
 
 #include "../../robosuite_benchmark_b200/csrc/rsb_dev.h"
 
+DevModel emu_model;
+float *emu_smem = nullptr;
+
 namespace {
 constexpr int NL = RSB_LANES;
 constexpr size_t STACK = 1 << 18;
@@ -84,24 +87,27 @@ void emu_set_state(void *h, const float *in) { EmuEnv *e = (EmuEnv *)h; memcpy(e
 
 void emu_reset(void *h, uint64_t seed, uint64_t env_id, float *obs) {
   EmuEnv *e = (EmuEnv *)h;
-  run_group([&](int lane) { Grp g{lane, 0xffffffffu}; env_reset(e->dm, e->smem.data(), g, e->state.data(), seed, env_id, obs); });
+  emu_model = e->dm; emu_smem = e->smem.data();
+  run_group([&](int lane) { Grp g{lane, 0xffffffffu}; env_reset(0, g, e->state.data(), seed, env_id, obs); });
 }
 int emu_step(void *h, const float *action, float *obs, float *reward) {
   EmuEnv *e = (EmuEnv *)h; unsigned char done = 0;
-  run_group([&](int lane) { Grp g{lane, 0xffffffffu}; env_step(e->dm, e->smem.data(), g, e->state.data(), action, obs, reward, &done); });
+  emu_model = e->dm; emu_smem = e->smem.data();
+  run_group([&](int lane) { Grp g{lane, 0xffffffffu}; env_step(0, g, e->state.data(), action, obs, reward, &done, true); });
   return done;
 }
 /* one physics substep from the stored state, state written back, internals dumped */
 void emu_debug_substep(void *h, const float *action, int policy_step, float *dbg) {
   EmuEnv *e = (EmuEnv *)h;
+  emu_model = e->dm; emu_smem = e->smem.data();
   run_group([&](int lane) {
     Grp g{lane, 0xffffffffu}; const DevModel &m = e->dm; float *s = e->smem.data();
-    load_state(m, s, e->state.data(), g);
+    load_state(0, e->state.data(), g);
     for (int i = g.lane; i < m.act_dim; i += RSB_LANES) s[m.o_act + i] = action[i];
     gsync(g);
-    substep(m, s, g, policy_step != 0);
-    dump_debug(m, s, g, dbg);
-    store_state(m, s, e->state.data(), g);
+    substep(0, g, policy_step != 0);
+    dump_debug(0, g, dbg);
+    store_state(0, e->state.data(), g);
   });
 }
 void emu_random_action(void *h, uint64_t seed, uint64_t env_id, uint64_t step, float *action) {
