@@ -1,0 +1,36 @@
+/*
+ * rsb_sac.h -- C-ABI of the replay-sampling and SAC-update kernels (part of librsb_cuda.so).
+ *
+ * Reference interfaces replaced (un-vendored rlkit @ b7f97b2, reached from util/rlkit_custom.py:235-238):
+ *   EnvReplayBuffer.random_batch(batch_size)          -> rsb_replay_sample
+ *   TanhGaussianPolicy.forward / TanhNormal.rsample   -> rsb_normal + rsb_head_fwd / rsb_head_bwd
+ *   SACTrainer.train_from_torch (losses)              -> rsb_sac_losses
+ *   torch.optim.Adam x4 + soft_update_from_to         -> rsb_adam_polyak
+ * The dense GEMMs between these calls are issued by the host through cuBLAS.  All pointers are DEVICE pointers, `stream` is a
+ * cudaStream_t as void*; every call is stream-ordered, non-blocking and CUDA-graph capturable.  Returns 0 or an error code.
+ */
+#ifndef RSB_SAC_H
+#define RSB_SAC_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+const char *rsb_sac_last_error(void);
+/* ring arrays in rlkit's layout: obs[cap,O] act[cap,A] rew[cap] term[cap](u8) next_obs[cap,O]; `size` = filled rows.
+   Row b of the batch takes ring row idx_b = mulhi32(Philox4x32-10(key=seed, ctr=(b, step_lo, step_hi, 0xB0FFE7)).word0, size). */
+int rsb_replay_sample(const float *d_obs, const float *d_act, const float *d_rew, const uint8_t *d_term, const float *d_next, int size, int obs_dim, int act_dim,
+                      uint64_t seed, uint64_t step, int batch, float *b_obs, int ld_obs, float *b_act, float *b_rew, float *b_term, float *b_next, int ld_next, int *b_idx, void *stream);
+int rsb_normal(uint64_t seed, uint64_t step, uint32_t stream_id, int n, float *d_out, void *stream);
+int rsb_bias_relu(float *d_x, const float *d_bias, int rows, int cols, int relu, int nmat, long mat_stride, int bias_stride, void *stream);
+int rsb_relu_bwd(float *d_dy, const float *d_y, long n, void *stream);
+int rsb_colsum(const float *d_dy, int r0, int r1, int cols, float *d_db, int nmat, long mat_stride, int db_stride, void *stream);
+int rsb_head_fwd(const float *d_out, const float *d_eps, int rows, int act_dim, float *d_a, float *d_logpi, float *dst0, int ld0, int r0lo, int r0hi, float *dst1, int ld1, int r1lo, int r1hi, void *stream);
+int rsb_head_bwd(const float *d_out, const float *d_eps, const float *d_a, int rows, int batch, int act_dim, const float *d_alpha, const float *d_ga, int ld_ga, float *d_dout, void *stream);
+int rsb_sac_losses(const float *d_q, const float *d_qt, const float *d_logpi, const float *d_rew, const float *d_term, const float *d_alpha, float reward_scale, float discount,
+                   float target_entropy, int batch, float *d_dq, float *d_y, float *d_sums, float *d_galpha, void *stream);
+int rsb_adam_polyak(float *d_p, const float *d_g, float *d_m, float *d_v, long n, const float *d_lr, float b1, float b2, float eps, float *d_bc,
+                    float *d_tgt, long tgt_begin, long tgt_end, float tau, int do_soft, float *d_alpha, long log_alpha_idx, void *stream);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -25,15 +25,15 @@ INFO = dict(nenvs=0, obs_dim=1, act_dim=2, state_words=3, smem_bytes=4, dbg_word
 
 
 def sources():
-    return [os.path.join(_CSRC, f) for f in ("rsb_cuda.cu", "rsb_dev.h", "rsb_devmodel.h")] + \
-           [os.path.join(_HERE, "..", "include", f) for f in ("rsb.h", "rsb_model.h")]
+    return [os.path.join(_CSRC, f) for f in ("rsb_cuda.cu", "rsb_sac.cu", "rsb_dev.h", "rsb_devmodel.h")] + \
+           [os.path.join(_HERE, "..", "include", f) for f in ("rsb.h", "rsb_sac.h", "rsb_model.h")]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/rsb_cuda.cu for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     stale = force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in sources())
     if stale:
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(_CSRC, "rsb_cuda.cu")]
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(_CSRC, "rsb_cuda.cu"), os.path.join(_CSRC, "rsb_sac.cu")]
         subprocess.check_call(cmd)
     return LIB_PATH
 
@@ -58,13 +58,25 @@ def lib():
         L.rsb_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rsb_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rsb_debug_substep.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.rsb_sac_last_error.restype = C.c_char_p
+        V, I, F, U64, L_ = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_long
+        L.rsb_replay_sample.argtypes = [V, V, V, V, V, I, I, I, U64, U64, I, V, I, V, V, V, V, I, V, V]
+        L.rsb_normal.argtypes = [U64, U64, C.c_uint32, I, V, V]
+        L.rsb_bias_relu.argtypes = [V, V, I, I, I, I, L_, I, V]
+        L.rsb_relu_bwd.argtypes = [V, V, L_, V]
+        L.rsb_colsum.argtypes = [V, I, I, I, V, I, L_, I, V]
+        L.rsb_head_fwd.argtypes = [V, V, I, I, V, V, V, I, I, I, V, I, I, I, V]
+        L.rsb_head_bwd.argtypes = [V, V, V, I, I, I, V, V, I, V, V]
+        L.rsb_sac_losses.argtypes = [V, V, V, V, V, V, F, F, F, I, V, V, V, V, V]
+        L.rsb_adam_polyak.argtypes = [V, V, V, V, L_, V, F, F, F, V, V, L_, L_, F, I, V, L_, V]
         _LIB = L
     return _LIB
 
 
 EXPORTS = ["rsb_last_error", "rsb_sizeof_model", "rsb_sizeof_task", "rsb_create", "rsb_destroy", "rsb_info", "rsb_reset",
            "rsb_step", "rsb_step_host", "rsb_reset_host", "rsb_random_actions", "rsb_get_state", "rsb_set_state",
-           "rsb_debug_substep"]
+           "rsb_debug_substep", "rsb_sac_last_error", "rsb_replay_sample", "rsb_normal", "rsb_bias_relu", "rsb_relu_bwd",
+           "rsb_colsum", "rsb_head_fwd", "rsb_head_bwd", "rsb_sac_losses", "rsb_adam_polyak"]
 
 
 class RsbError(RuntimeError):

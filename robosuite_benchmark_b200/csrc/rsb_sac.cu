@@ -1,0 +1,208 @@
+/*
+ * rsb_sac.cu -- replay sampling/gather and the non-GEMM parts of the rlkit SAC update as sm_100a kernels (C-ABI: include/rsb_sac.h).
+ *
+ * Stands behind rlkit's EnvReplayBuffer.random_batch and SACTrainer.train_from_torch (reference call sites
+ * util/rlkit_custom.py:235-238).  The dense GEMMs of the five 256x256 MLPs are issued by the host through
+ * cuBLAS (tensor cores, TF32/FP32-accumulate); everything between them is fused here: Philox index draw + row gather,
+ * tanh-Gaussian sampling / log-prob and its backward, TD targets and loss gradients, bias+ReLU, and ONE Adam + Polyak
+ * kernel over the flat parameter buffer.  All calls are stream-ordered and capturable in a CUDA graph (no syncs, no allocs).
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/rsb_sac.h"
+
+static thread_local std::string g_sac_err;
+#define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_sac_err = std::string(#call) + ": " + cudaGetErrorString(e_); return 1; } } while (0)
+
+__device__ __forceinline__ void philox4(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t h0 = __umulhi(0xD2511F53u, c[0]), l0 = 0xD2511F53u * c[0], h1 = __umulhi(0xCD9E8D57u, c[2]), l1 = 0xCD9E8D57u * c[2];
+    uint32_t n0 = h1 ^ c[1] ^ k0, n1 = l1, n2 = h0 ^ c[3] ^ k1, n3 = l0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+/* ---------------------------------------------------------------- replay: Philox index draw (with replacement) + row gather
+   index of batch row b at update `step`: Philox(key = seed; counter = (b, step_lo, step_hi, 0xB0FFE7)) -> word0; idx = mulhi(word0, size).
+   One warp per row; obs/next_obs/actions rows are copied with coalesced 32-lane loads. */
+__global__ void k_replay_sample(const float *__restrict__ obs, const float *__restrict__ act, const float *__restrict__ rew,
+                                const unsigned char *__restrict__ term, const float *__restrict__ next_obs,
+                                int size, int O, int A, uint64_t seed, uint64_t step, int B,
+                                float *__restrict__ b_obs, float *__restrict__ b_act, float *__restrict__ b_rew, float *__restrict__ b_term,
+                                float *__restrict__ b_next, int *__restrict__ b_idx, int ld_obs, int ld_next) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= B) return;
+  uint32_t c[4] = {(uint32_t)row, (uint32_t)step, (uint32_t)(step >> 32), 0xB0FFE7u};
+  philox4(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  int idx = (int)__umulhi(c[0], (uint32_t)size);
+  const float *so = obs + (size_t)idx * O, *sn = next_obs + (size_t)idx * O, *sa = act + (size_t)idx * A;
+  for (int k = lane; k < O; k += 32) { b_obs[(size_t)row * ld_obs + k] = so[k]; b_next[(size_t)row * ld_next + k] = sn[k]; }
+  for (int k = lane; k < A; k += 32) b_act[(size_t)row * A + k] = sa[k];
+  if (lane == 0) { b_rew[row] = rew[idx]; b_term[row] = (float)term[idx]; if (b_idx) b_idx[row] = idx; }
+}
+
+/* ---------------------------------------------------------------- N(0,1) noise, Philox keyed (seed, step, stream)  */
+__global__ void k_normal(uint64_t seed, uint64_t step, uint32_t stream, int n, float *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;               /* one thread -> 4 values */
+  if (4 * i >= n) return;
+  uint32_t c[4] = {(uint32_t)i, (uint32_t)step, (uint32_t)(step >> 32), stream};
+  philox4(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  float z[4];
+#pragma unroll
+  for (int p = 0; p < 2; p++) {
+    float u1 = ((float)(c[2 * p] >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(c[2 * p + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float rad = sqrtf(-2.0f * logf(u1)), sn, cs; sincosf(6.283185307179586f * u2, &sn, &cs);
+    z[2 * p] = rad * cs; z[2 * p + 1] = rad * sn;
+  }
+  for (int k = 0; k < 4; k++) if (4 * i + k < n) out[4 * i + k] = z[k];
+}
+
+/* ---------------------------------------------------------------- bias + ReLU (in place), row-major [rows, cols] */
+__global__ void k_bias_relu(float *__restrict__ x, const float *__restrict__ bias, int rows, int cols, int relu, int nmat, long mat_stride, int bias_stride) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x; long per = (long)rows * cols;
+  if (i >= per * nmat) return;
+  int mt = (int)(i / per); long r = i - (long)mt * per; int c = (int)(r % cols);
+  float v = x[(long)mt * mat_stride + r] + bias[mt * bias_stride + c];
+  x[(long)mt * mat_stride + r] = relu ? fmaxf(v, 0.0f) : v;
+}
+/* dZ = dY * (Y > 0)  (in place on dY) */
+__global__ void k_relu_bwd(float *__restrict__ dy, const float *__restrict__ y, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dy[i] = y[i] > 0.0f ? dy[i] : 0.0f;
+}
+/* column sums of dY [rows, cols] rows in [r0, r1) -> db[cols] (one block per column group; small matrices) */
+__global__ void k_colsum(const float *__restrict__ dy, int r0, int r1, int cols, float *__restrict__ db, int nmat, long mat_stride, int db_stride) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x, mt = blockIdx.y; if (c >= cols || mt >= nmat) return;
+  float acc = 0; const float *p = dy + (long)mt * mat_stride;
+  for (int r = r0; r < r1; r++) acc += p[(long)r * cols + c];
+  db[mt * db_stride + c] = acc;
+}
+
+/* ---------------------------------------------------------------- tanh-Gaussian head (rlkit TanhGaussianPolicy / TanhNormal)
+   out [R, 2A] = (mean | raw log_std); eps [R, A].  a = tanh(mean + exp(clamp(log_std,-20,2)) eps),
+   logpi = sum_d [ -0.5 eps^2 - log_std - 0.5 log(2 pi) - log(1 - a^2 + 1e-6) ].
+   `a` is written to up to two destinations with leading dims (the action columns of the Q-network input buffers). */
+#define LOG_SIG_MAX 2.0f
+#define LOG_SIG_MIN -20.0f
+__global__ void k_head_fwd(const float *__restrict__ out, const float *__restrict__ eps, int R, int A,
+                           float *__restrict__ a_store, float *__restrict__ logpi,
+                           float *__restrict__ dst0, int ld0, int row0_lo, int row0_hi, float *__restrict__ dst1, int ld1, int row1_lo, int row1_hi) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x; if (r >= R) return;
+  float lp = 0;
+  for (int d = 0; d < A; d++) {
+    float mu = out[(size_t)r * 2 * A + d], ls = fminf(fmaxf(out[(size_t)r * 2 * A + A + d], LOG_SIG_MIN), LOG_SIG_MAX), e = eps[(size_t)r * A + d];
+    float a = tanhf(mu + expf(ls) * e);
+    lp += -0.5f * e * e - ls - 0.9189385332046727f - logf(1.0f - a * a + 1e-6f);
+    a_store[(size_t)r * A + d] = a;
+    if (dst0 && r >= row0_lo && r < row0_hi) dst0[(size_t)(r - row0_lo) * ld0 + d] = a;
+    if (dst1 && r >= row1_lo && r < row1_hi) dst1[(size_t)(r - row1_lo) * ld1 + d] = a;
+  }
+  logpi[r] = lp;
+}
+/* backward for rows [0, B): upstream g_lp (scalar, same for every row: alpha / B) and g_a [B, A] with leading dim ld_ga
+   (the action columns of d(Q input)).  d_out [R, 2A] is fully written (rows >= B get zero: next_obs rows carry no gradient). */
+__global__ void k_head_bwd(const float *__restrict__ out, const float *__restrict__ eps, const float *__restrict__ a_store, int R, int B, int A,
+                           const float *__restrict__ alpha, float inv_B, const float *__restrict__ g_a, int ld_ga, float *__restrict__ d_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= R * A) return;
+  int r = i / A, d = i - r * A; float dmu = 0, dls = 0;
+  if (r < B) {
+    float raw = out[(size_t)r * 2 * A + A + d], ls = fminf(fmaxf(raw, LOG_SIG_MIN), LOG_SIG_MAX), e = eps[i], a = a_store[i];
+    float g_lp = alpha[0] * inv_B, one = 1.0f - a * a;
+    float dz = g_a[(size_t)r * ld_ga + d] * one + g_lp * 2.0f * a * one / (one + 1e-6f);
+    dmu = dz; dls = dz * expf(ls) * e - g_lp;
+    if (raw < LOG_SIG_MIN || raw > LOG_SIG_MAX) dls = 0;
+  }
+  d_out[(size_t)r * 2 * A + d] = dmu; d_out[(size_t)r * 2 * A + A + d] = dls;
+}
+
+/* ---------------------------------------------------------------- losses: TD target, dQ, alpha gradient, loss sums
+   q [2, 2B]: rows [0,B) = Q_i(obs, a_new), rows [B,2B) = Q_i(obs, act); qt [2, B] = target nets on (next_obs, a').
+   dq [2, 2B]: rows [0,B): d policy_loss / dq_i = -1/B on the arg-min network (0 on the other); rows [B,2B): 2 (q_i - y) / B.
+   sums[0..5] += qf1_loss, qf2_loss, policy_loss, alpha_loss, mean(logpi), mean(y)   (pre-zeroed by the caller; atomics)
+   galpha[0] = d alpha_loss / d log_alpha = -mean(logpi + target_entropy). */
+__global__ void k_losses(const float *__restrict__ q, const float *__restrict__ qt, const float *__restrict__ logpi /*[2B]*/,
+                         const float *__restrict__ rew, const float *__restrict__ term, const float *__restrict__ alpha_logalpha /* [alpha, log_alpha] */,
+                         float reward_scale, float discount, float target_entropy, int B, float *__restrict__ dq, float *__restrict__ ytarget,
+                         float *__restrict__ sums, float *__restrict__ galpha) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  float l1 = 0, l2 = 0, lp = 0, la = 0, mlp = 0, my = 0, ga = 0;
+  if (b < B) {
+    float alpha = alpha_logalpha[0], log_alpha = alpha_logalpha[1], invB = 1.0f / (float)B;
+    float q1n = q[b], q2n = q[2 * B + b], lpi = logpi[b];
+    bool first = q1n <= q2n;                                        /* torch.min routes the gradient to the smaller entry */
+    dq[b] = first ? -invB : 0.0f; dq[2 * B + b] = first ? 0.0f : -invB;
+    lp = (alpha * lpi - fminf(q1n, q2n)) * invB;
+    la = -(log_alpha * (lpi + target_entropy)) * invB; ga = -(lpi + target_entropy) * invB; mlp = lpi * invB;
+    float tq = fminf(qt[b], qt[B + b]) - alpha * logpi[B + b];
+    float y = reward_scale * rew[b] + (1.0f - term[b]) * discount * tq; ytarget[b] = y; my = y * invB;
+    float e1 = q[B + b] - y, e2 = q[3 * B + b] - y;
+    dq[B + b] = 2.0f * e1 * invB; dq[3 * B + b] = 2.0f * e2 * invB; l1 = e1 * e1 * invB; l2 = e2 * e2 * invB;
+  }
+  /* warp reduce, then one atomic per warp */
+  for (int o = 16; o > 0; o >>= 1) {
+    l1 += __shfl_xor_sync(0xffffffffu, l1, o); l2 += __shfl_xor_sync(0xffffffffu, l2, o); lp += __shfl_xor_sync(0xffffffffu, lp, o);
+    la += __shfl_xor_sync(0xffffffffu, la, o); mlp += __shfl_xor_sync(0xffffffffu, mlp, o); my += __shfl_xor_sync(0xffffffffu, my, o); ga += __shfl_xor_sync(0xffffffffu, ga, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(sums + 0, l1); atomicAdd(sums + 1, l2); atomicAdd(sums + 2, lp); atomicAdd(sums + 3, la); atomicAdd(sums + 4, mlp); atomicAdd(sums + 5, my);
+    atomicAdd(galpha, ga);
+  }
+}
+
+/* ---------------------------------------------------------------- Adam (torch.optim.Adam semantics) + Polyak, one launch over the flat buffer
+   segment table seg[k] = (begin, end, lr); params/grads/m/v are flat fp32; tgt_map[i] >= 0 gives the index of the target
+   copy of parameter i (Q networks) or -1; the soft update uses the UPDATED parameter, as rlkit does (step, then soft_update). */
+__global__ void k_adam_polyak(float *__restrict__ p, const float *__restrict__ gr, float *__restrict__ m, float *__restrict__ v, long n,
+                              const float *__restrict__ lr_elem, float b1, float b2, float eps, const float *__restrict__ bias_corr /* [bc1, sqrt(bc2)] device */,
+                              float *__restrict__ tgt, long tgt_begin, long tgt_end, float tau, int do_soft,
+                              float *__restrict__ alpha_out /* [alpha, log_alpha] refreshed from p[log_alpha_idx] */, long log_alpha_idx) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  float g = gr[i], mi = b1 * m[i] + (1.0f - b1) * g, vi = b2 * v[i] + (1.0f - b2) * g * g; m[i] = mi; v[i] = vi;
+  float denom = sqrtf(vi) / bias_corr[1] + eps, pi = p[i] - (lr_elem[i] / bias_corr[0]) * (mi / denom); p[i] = pi;
+  if (do_soft && i >= tgt_begin && i < tgt_end) { long k = i - tgt_begin; tgt[k] = (1.0f - tau) * tgt[k] + tau * pi; }
+  if (i == log_alpha_idx) { alpha_out[1] = pi; alpha_out[0] = expf(pi); }
+}
+/* bias corrections advance on the device so the whole update is graph-replayable: bc[2]=beta1^t, bc[3]=beta2^t */
+__global__ void k_adam_tick(float *__restrict__ bc, float b1, float b2) {
+  float p1 = bc[2] * b1, p2 = bc[3] * b2; bc[2] = p1; bc[3] = p2; bc[0] = 1.0f - p1; bc[1] = sqrtf(1.0f - p2);
+}
+
+extern "C" {
+const char *rsb_sac_last_error(void) { return g_sac_err.c_str(); }
+
+int rsb_replay_sample(const float *d_obs, const float *d_act, const float *d_rew, const uint8_t *d_term, const float *d_next, int size, int obs_dim, int act_dim,
+                      uint64_t seed, uint64_t step, int batch, float *b_obs, int ld_obs, float *b_act, float *b_rew, float *b_term, float *b_next, int ld_next, int *b_idx, void *stream) {
+  if (size <= 0 || batch <= 0) { g_sac_err = "replay_sample: empty buffer or batch"; return 2; }
+  int threads = 128, blocks = (batch * 32 + threads - 1) / threads;
+  k_replay_sample<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_obs, d_act, d_rew, d_term, d_next, size, obs_dim, act_dim, seed, step, batch, b_obs, b_act, b_rew, b_term, b_next, b_idx, ld_obs, ld_next);
+  CKS(cudaGetLastError()); return 0;
+}
+int rsb_normal(uint64_t seed, uint64_t step, uint32_t stream_id, int n, float *d_out, void *stream) {
+  int t = (n + 3) / 4; k_normal<<<(t + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, step, stream_id, n, d_out); CKS(cudaGetLastError()); return 0;
+}
+int rsb_bias_relu(float *d_x, const float *d_bias, int rows, int cols, int relu, int nmat, long mat_stride, int bias_stride, void *stream) {
+  long n = (long)rows * cols * nmat; k_bias_relu<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_bias, rows, cols, relu, nmat, mat_stride, bias_stride); CKS(cudaGetLastError()); return 0;
+}
+int rsb_relu_bwd(float *d_dy, const float *d_y, long n, void *stream) { k_relu_bwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_dy, d_y, n); CKS(cudaGetLastError()); return 0; }
+int rsb_colsum(const float *d_dy, int r0, int r1, int cols, float *d_db, int nmat, long mat_stride, int db_stride, void *stream) {
+  dim3 grid((cols + 127) / 128, nmat); k_colsum<<<grid, 128, 0, (cudaStream_t)stream>>>(d_dy, r0, r1, cols, d_db, nmat, mat_stride, db_stride); CKS(cudaGetLastError()); return 0;
+}
+int rsb_head_fwd(const float *d_out, const float *d_eps, int rows, int act_dim, float *d_a, float *d_logpi, float *dst0, int ld0, int r0lo, int r0hi, float *dst1, int ld1, int r1lo, int r1hi, void *stream) {
+  k_head_fwd<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_out, d_eps, rows, act_dim, d_a, d_logpi, dst0, ld0, r0lo, r0hi, dst1, ld1, r1lo, r1hi); CKS(cudaGetLastError()); return 0;
+}
+int rsb_head_bwd(const float *d_out, const float *d_eps, const float *d_a, int rows, int batch, int act_dim, const float *d_alpha, const float *d_ga, int ld_ga, float *d_dout, void *stream) {
+  int n = rows * act_dim; k_head_bwd<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_out, d_eps, d_a, rows, batch, act_dim, d_alpha, 1.0f / (float)batch, d_ga, ld_ga, d_dout); CKS(cudaGetLastError()); return 0;
+}
+int rsb_sac_losses(const float *d_q, const float *d_qt, const float *d_logpi, const float *d_rew, const float *d_term, const float *d_alpha, float reward_scale, float discount,
+                   float target_entropy, int batch, float *d_dq, float *d_y, float *d_sums, float *d_galpha, void *stream) {
+  k_losses<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_q, d_qt, d_logpi, d_rew, d_term, d_alpha, reward_scale, discount, target_entropy, batch, d_dq, d_y, d_sums, d_galpha); CKS(cudaGetLastError()); return 0;
+}
+int rsb_adam_polyak(float *d_p, const float *d_g, float *d_m, float *d_v, long n, const float *d_lr, float b1, float b2, float eps, float *d_bc,
+                    float *d_tgt, long tgt_begin, long tgt_end, float tau, int do_soft, float *d_alpha, long log_alpha_idx, void *stream) {
+  k_adam_tick<<<1, 1, 0, (cudaStream_t)stream>>>(d_bc, b1, b2);
+  k_adam_polyak<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_p, d_g, d_m, d_v, n, d_lr, b1, b2, eps, d_bc, d_tgt, tgt_begin, tgt_end, tau, do_soft, d_alpha, log_alpha_idx);
+  CKS(cudaGetLastError()); return 0;
+}
+}

@@ -1,0 +1,527 @@
+"""rlkit's SAC pieces as the reference wires them (util/rlkit_utils.py:64-106,139-150; util/rlkit_custom.py:233-240),
+re-built on the CUDA library: `EnvReplayBuffer` (HBM-resident ring, Philox-indexed sampling), `FlattenMlp`,
+`TanhGaussianPolicy`, `MakeDeterministic`, `SACTrainer`.
+
+All trainable parameters live in ONE flat fp32 buffer  [policy | Q1,Q2 (stacked per layer) | log_alpha]  with a matching flat
+gradient buffer, so that (a) the twin Q networks run as batched GEMMs, (b) one kernel does the four Adam steps and the
+Polyak update, (c) data-parallel training all-reduces a single bucket.  Dense GEMMs go through cuBLAS (torch.mm / bmm with
+`out=`); everything else is the fused kernels of csrc/rsb_sac.cu.  One whole update is captured in a CUDA graph.
+There is no CPU path: constructing any of these without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+
+from .backend import RsbError, lib
+
+HID = 256
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _chk(rc):
+    if rc != 0:
+        raise RsbError(lib().rsb_sac_last_error().decode())
+
+
+def _stream(dev):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+# ----------------------------------------------------------------------------- replay ring
+class EnvReplayBuffer:
+    """rlkit EnvReplayBuffer layout (observations, actions, rewards, terminals, next_obs; ring pointer `_top`, `_size`)
+    resident in HBM.  `add_batch` appends N transitions written by the env kernels; `random_batch` draws indices with
+    replacement from Philox keyed (seed, draw counter, row) -- the same integers the numpy oracle produces."""
+
+    def __init__(self, max_replay_buffer_size, env=None, obs_dim=None, action_dim=None, device="cuda:0", seed=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise RsbError("the replay ring lives in HBM: no CUDA device visible")
+        self.torch, self.L = torch, lib()
+        self.device = torch.device(device)
+        if env is not None:
+            obs_dim = env.observation_space.low.size
+            action_dim = env.action_space.low.size
+        self.obs_dim, self.action_dim = int(obs_dim), int(action_dim)
+        self.capacity = int(max_replay_buffer_size)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self._observations = torch.zeros(self.capacity, self.obs_dim, **f32)
+        self._next_obs = torch.zeros(self.capacity, self.obs_dim, **f32)
+        self._actions = torch.zeros(self.capacity, self.action_dim, **f32)
+        self._rewards = torch.zeros(self.capacity, **f32)
+        self._terminals = torch.zeros(self.capacity, dtype=torch.uint8, device=self.device)
+        self._top, self._size, self.seed, self.draws = 0, 0, int(seed), 0
+
+    def _pieces(self, n):
+        """Ring rows for the next n transitions as (ring_slice, batch_slice) pieces (two when the pointer wraps)."""
+        n = int(n)
+        if n > self.capacity:
+            raise ValueError("batch larger than the ring")
+        first = min(n, self.capacity - self._top)
+        out = [(slice(self._top, self._top + first), slice(0, first))]
+        if first < n:
+            out.append((slice(0, n - first), slice(first, n)))
+        return out
+
+    def _advance(self, n):
+        self._top = (self._top + n) % self.capacity
+        self._size = min(self.capacity, self._size + n)
+
+    def add_batch(self, obs, actions, rewards, terminals, next_obs):
+        """Append n transitions (device tensors).  rlkit add_sample semantics applied row by row: ring pointer advances, size saturates."""
+        n = obs.shape[0]
+        rewards, terminals = rewards.reshape(-1), terminals.reshape(-1)
+        for rs, bs in self._pieces(n):
+            self._observations[rs].copy_(obs[bs])
+            self._actions[rs].copy_(actions[bs])
+            self._rewards[rs].copy_(rewards[bs])
+            self._terminals[rs].copy_(terminals[bs])
+            self._next_obs[rs].copy_(next_obs[bs])
+        self._advance(n)
+
+    def add_paths(self, paths):
+        """rlkit path dicts (numpy, [T, .]) -- the single-env protocol."""
+        t = self.torch
+        for p in paths:
+            self.add_batch(t.as_tensor(p["observations"], dtype=t.float32, device=self.device),
+                           t.as_tensor(p["actions"], dtype=t.float32, device=self.device),
+                           t.as_tensor(p["rewards"], dtype=t.float32, device=self.device),
+                           t.as_tensor(np.asarray(p["terminals"]).astype(np.uint8), device=self.device),
+                           t.as_tensor(p["next_observations"], dtype=t.float32, device=self.device))
+
+    def num_steps_can_sample(self):
+        return self._size
+
+    def sample_into(self, batch_size, step, b_obs, ld_obs, b_act, b_rew, b_term, b_next, ld_next, b_idx=None):
+        _chk(self.L.rsb_replay_sample(_ptr(self._observations), _ptr(self._actions), _ptr(self._rewards), _ptr(self._terminals),
+                                      _ptr(self._next_obs), self._size, self.obs_dim, self.action_dim, C.c_uint64(self.seed),
+                                      C.c_uint64(step), int(batch_size), _ptr(b_obs), int(ld_obs), _ptr(b_act), _ptr(b_rew), _ptr(b_term),
+                                      _ptr(b_next), int(ld_next), None if b_idx is None else _ptr(b_idx), _stream(self.device)))
+
+    def random_batch(self, batch_size):
+        t = self.torch
+        f32 = dict(dtype=t.float32, device=self.device)
+        b = dict(observations=t.empty(batch_size, self.obs_dim, **f32), actions=t.empty(batch_size, self.action_dim, **f32),
+                 rewards=t.empty(batch_size, **f32), terminals=t.empty(batch_size, **f32),
+                 next_observations=t.empty(batch_size, self.obs_dim, **f32),
+                 indices=t.empty(batch_size, dtype=t.int32, device=self.device))
+        self.sample_into(batch_size, self.draws, b["observations"], self.obs_dim, b["actions"], b["rewards"], b["terminals"],
+                         b["next_observations"], self.obs_dim, b["indices"])
+        self.draws += 1
+        b["rewards"], b["terminals"] = b["rewards"].unsqueeze(1), b["terminals"].unsqueeze(1)
+        return b
+
+    def get_diagnostics(self):
+        return OrderedDict([("size", self._size)])
+
+    def get_snapshot(self):
+        return {}
+
+    def end_epoch(self, epoch):
+        return
+
+
+def replay_indices_reference(seed, step, batch, size):
+    """Host restatement of the index rule (numpy) -- used by tests; mirrors oracle/sac_oracle.py."""
+    from .philox import philox4x32
+    out = np.empty(batch, np.int64)
+    for b in range(batch):
+        w = philox4x32([b, step & 0xFFFFFFFF, (step >> 32) & 0xFFFFFFFF, 0xB0FFE7], [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF])
+        out[b] = (int(w[0]) * int(size)) >> 32
+    return out
+
+
+# ----------------------------------------------------------------------------- parameter store + network handles
+class ParamStore:
+    """Flat fp32 parameter / gradient / Adam-moment buffers and the views the GEMMs read."""
+
+    def __init__(self, obs_dim, act_dim, device, hidden=HID, seed=0, policy_init_w=1e-3, qf_init_w=3e-3, b_init=0.1):
+        import torch
+        self.torch, self.device = torch, torch.device(device)
+        self.O, self.A, self.H = int(obs_dim), int(act_dim), int(hidden)
+        O, A, H, QI = self.O, self.A, self.H, self.O + self.A
+        shapes = OrderedDict([
+            ("p_W0", (O, H)), ("p_b0", (H,)), ("p_W1", (H, H)), ("p_b1", (H,)), ("p_W2", (H, 2 * A)), ("p_b2", (2 * A,)),
+            ("q_W0", (2, QI, H)), ("q_b0", (2, H)), ("q_W1", (2, H, H)), ("q_b1", (2, H)), ("q_W2", (2, H, 1)), ("q_b2", (2, 1)),
+            ("log_alpha", (1,))])
+        self.shapes, self.offsets, n = shapes, OrderedDict(), 0
+        for k, s in shapes.items():
+            self.offsets[k] = n
+            n += int(np.prod(s))
+        self.n = n
+        self.q_begin, self.q_end = self.offsets["q_W0"], self.offsets["log_alpha"]
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.flat, self.grad = torch.zeros(n, **f32), torch.zeros(n, **f32)
+        self.m, self.v = torch.zeros(n, **f32), torch.zeros(n, **f32)
+        self.target = torch.zeros(self.q_end - self.q_begin, **f32)
+        self.P, self.G, self.T = self._views(self.flat, 0), self._views(self.grad, 0), self._views(self.target, self.q_begin, only_q=True)
+        self.init_weights(seed, policy_init_w, qf_init_w, b_init)
+
+    def _views(self, buf, base, only_q=False):
+        v = {}
+        for k, s in self.shapes.items():
+            if only_q and not k.startswith("q_"):
+                continue
+            o = self.offsets[k] - base
+            v[k] = buf[o:o + int(np.prod(s))].view(*s)
+        return v
+
+    def init_weights(self, seed, policy_init_w, qf_init_w, b_init):
+        self.load_host(init_host_params(self.O, self.A, self.H, seed, policy_init_w, qf_init_w, b_init))
+
+    def load_host(self, host, targets=None):
+        t = self.torch
+        for k, a in host.items():
+            self.P[k].copy_(t.as_tensor(np.asarray(a, np.float32).reshape(self.shapes[k])))
+        if targets is None:
+            self.target.copy_(self.flat[self.q_begin:self.q_end])
+        else:
+            for k, a in targets.items():
+                self.T[k].copy_(t.as_tensor(np.asarray(a, np.float32).reshape(self.shapes[k])))
+
+    def to_host(self):
+        return {k: v.detach().cpu().numpy().copy() for k, v in self.P.items()}, {k: v.detach().cpu().numpy().copy() for k, v in self.T.items()}
+
+
+def init_host_params(O, A, H=HID, seed=0, policy_init_w=1e-3, qf_init_w=3e-3, b_init=0.1):
+    """rlkit Mlp init: hidden W ~ U(+-1/sqrt(fan_in)) (fanin_init), hidden b = 0.1, last layers U(+-init_w).
+    Host numpy, in the store's layout (weights [in, out], twin Q stacked on axis 0)."""
+    rng = np.random.default_rng(seed)
+    QI = O + A
+
+    def u(shape, bound):
+        return rng.uniform(-bound, bound, size=shape).astype(np.float32)
+
+    return {"p_W0": u((O, H), 1 / np.sqrt(O)), "p_b0": np.full(H, b_init, np.float32), "p_W1": u((H, H), 1 / np.sqrt(H)),
+            "p_b1": np.full(H, b_init, np.float32), "p_W2": u((H, 2 * A), policy_init_w), "p_b2": u((2 * A,), policy_init_w),
+            "q_W0": u((2, QI, H), 1 / np.sqrt(QI)), "q_b0": np.full((2, H), b_init, np.float32), "q_W1": u((2, H, H), 1 / np.sqrt(H)),
+            "q_b1": np.full((2, H), b_init, np.float32), "q_W2": u((2, H, 1), qf_init_w), "q_b2": u((2, 1), qf_init_w),
+            "log_alpha": np.zeros(1, np.float32)}
+
+
+class FlattenMlp:
+    """Handle on one Q network of the store (rlkit FlattenMlp: cat(obs, act) -> 256 -> 256 -> 1)."""
+
+    def __init__(self, store: ParamStore, index: int, target=False):
+        self.store, self.index, self.target = store, index, target
+        self.input_size, self.output_size, self.hidden_sizes = store.O + store.A, 1, [store.H, store.H]
+
+    def views(self):
+        src = self.store.T if self.target else self.store.P
+        return {k: src["q_" + k][self.index] for k in ("W0", "b0", "W1", "b1", "W2", "b2")}
+
+    def __call__(self, obs, act):
+        t = self.store.torch
+        v = self.views()
+        x = t.cat([obs, act], dim=1)
+        h = t.relu(x @ v["W0"] + v["b0"])
+        h = t.relu(h @ v["W1"] + v["b1"])
+        return h @ v["W2"] + v["b2"]
+
+    def state_dict(self):
+        v = self.views()
+        return OrderedDict([("fc0.weight", v["W0"].t().contiguous().cpu()), ("fc0.bias", v["b0"].cpu().clone()),
+                            ("fc1.weight", v["W1"].t().contiguous().cpu()), ("fc1.bias", v["b1"].cpu().clone()),
+                            ("last_fc.weight", v["W2"].t().contiguous().cpu()), ("last_fc.bias", v["b2"].cpu().clone())])
+
+
+class TanhGaussianPolicy:
+    """rlkit TanhGaussianPolicy handle: obs -> 256 -> 256 -> (mean, log_std); a = tanh(mean + std * eps)."""
+
+    def __init__(self, store: ParamStore):
+        self.store = store
+        self.input_size, self.output_size, self.hidden_sizes = store.O, store.A, [store.H, store.H]
+
+    def forward(self, obs, deterministic=False, eps=None):
+        t, P, A = self.store.torch, self.store.P, self.store.A
+        h = t.relu(obs @ P["p_W0"] + P["p_b0"])
+        h = t.relu(h @ P["p_W1"] + P["p_b1"])
+        out = h @ P["p_W2"] + P["p_b2"]
+        mean, log_std = out[:, :A], out[:, A:].clamp(-20.0, 2.0)
+        if deterministic:
+            return t.tanh(mean), mean, log_std
+        if eps is None:
+            eps = t.randn_like(mean)
+        return t.tanh(mean + log_std.exp() * eps), mean, log_std
+
+    def get_actions(self, obs, deterministic=False):
+        """obs: torch tensor [N, O] on the device -> actions [N, A] (batched collectors)."""
+        with self.store.torch.no_grad():
+            return self.forward(obs, deterministic)[0]
+
+    def get_action(self, obs_np, deterministic=False):
+        t = self.store.torch
+        o = t.as_tensor(np.asarray(obs_np, np.float32)[None], device=self.store.device)
+        return self.get_actions(o, deterministic)[0].cpu().numpy().astype(np.float64), {}
+
+    def reset(self):
+        pass
+
+    def state_dict(self):
+        P, A = self.store.P, self.store.A
+        W2, b2 = P["p_W2"], P["p_b2"]
+        return OrderedDict([("fc0.weight", P["p_W0"].t().contiguous().cpu()), ("fc0.bias", P["p_b0"].cpu().clone()),
+                            ("fc1.weight", P["p_W1"].t().contiguous().cpu()), ("fc1.bias", P["p_b1"].cpu().clone()),
+                            ("last_fc.weight", W2[:, :A].t().contiguous().cpu()), ("last_fc.bias", b2[:A].cpu().clone()),
+                            ("last_fc_log_std.weight", W2[:, A:].t().contiguous().cpu()), ("last_fc_log_std.bias", b2[A:].cpu().clone())])
+
+
+class MakeDeterministic:
+    def __init__(self, stochastic_policy):
+        self.stochastic_policy = stochastic_policy
+
+    def get_action(self, obs_np):
+        return self.stochastic_policy.get_action(obs_np, deterministic=True)
+
+    def get_actions(self, obs):
+        return self.stochastic_policy.get_actions(obs, deterministic=True)
+
+    def reset(self):
+        pass
+
+
+# ----------------------------------------------------------------------------- trainer
+class SACTrainer:
+    """rlkit SACTrainer (twin Q, no V net, automatic entropy tuning) -- update order and semantics per SURVEY.md A.4:
+    all losses are built from the pre-update weights and the PRE-update alpha; Adam on policy / Q1 / Q2 / log_alpha;
+    Polyak update when n_train_steps % target_update_period == 0 (so the very first step already updates)."""
+
+    def __init__(self, env=None, policy=None, qf1=None, qf2=None, target_qf1=None, target_qf2=None, *, store: ParamStore = None,
+                 replay_buffer: EnvReplayBuffer = None, batch_size=128, discount=0.99, reward_scale=1.0, policy_lr=1e-3, qf_lr=1e-3,
+                 soft_target_tau=1e-2, target_update_period=1, use_automatic_entropy_tuning=True, target_entropy=None,
+                 seed=0, tf32=True, use_graph=True, world_size=1):
+        import torch
+        if store is None:
+            store = policy.store
+        self.torch, self.L, self.store, self.device = torch, lib(), store, store.device
+        self.policy = policy or TanhGaussianPolicy(store)
+        self.qf1, self.qf2 = qf1 or FlattenMlp(store, 0), qf2 or FlattenMlp(store, 1)
+        self.target_qf1, self.target_qf2 = target_qf1 or FlattenMlp(store, 0, True), target_qf2 or FlattenMlp(store, 1, True)
+        self.replay, self.B = replay_buffer, int(batch_size)
+        self.discount, self.reward_scale = float(discount), float(reward_scale)
+        self.tau, self.period = float(soft_target_tau), int(target_update_period)
+        if not use_automatic_entropy_tuning:
+            raise NotImplementedError("fixed-alpha SAC is not on the benchmark path (all committed variants use automatic entropy tuning)")
+        A = store.A
+        self.target_entropy = float(-A if target_entropy is None else target_entropy)   # -prod(action_space.shape)
+        self.seed, self.tf32, self.use_graph, self.world = int(seed), bool(tf32), bool(use_graph), int(world_size)
+        self._n_train_steps_total = 0
+        self._need_to_update_eval_statistics = True
+        self.eval_statistics = OrderedDict()
+        f32 = dict(dtype=torch.float32, device=self.device)
+        n = store.n
+        lr = torch.empty(n, **f32)
+        lr[:store.q_begin] = policy_lr
+        lr[store.q_begin:store.q_end] = qf_lr
+        lr[store.q_end:] = policy_lr
+        self.lr = lr
+        self.bc = torch.tensor([0.0, 0.0, 1.0, 1.0], **f32)
+        self.alpha = torch.tensor([1.0, 0.0], **f32)                 # [alpha, log_alpha] (device copy read by the kernels)
+        self._alloc(self.B)
+        self._graphs = {}
+
+    # -- buffers
+    def _alloc(self, B):
+        t, s = self.torch, self.store
+        O, A, H, QI = s.O, s.A, s.H, s.O + s.A
+        f32 = dict(dtype=t.float32, device=self.device)
+        self.Xp = t.zeros(2 * B, O, **f32)             # policy input: obs rows, then next_obs rows
+        self.XQ = t.zeros(2 * B, QI, **f32)            # Q input: (obs, a_new) rows, then (obs, act) rows
+        self.XT = t.zeros(B, QI, **f32)                # target-Q input: (next_obs, a')
+        self.act, self.rew, self.term = t.zeros(B, A, **f32), t.zeros(B, **f32), t.zeros(B, **f32)
+        self.idx = t.zeros(B, dtype=t.int32, device=self.device)
+        self.eps = t.zeros(2 * B, A, **f32)
+        self.H1p, self.H2p, self.OUT = t.zeros(2 * B, H, **f32), t.zeros(2 * B, H, **f32), t.zeros(2 * B, 2 * A, **f32)
+        self.a_store, self.logpi = t.zeros(2 * B, A, **f32), t.zeros(2 * B, **f32)
+        self.H1q, self.H2q, self.q = t.zeros(2, 2 * B, H, **f32), t.zeros(2, 2 * B, H, **f32), t.zeros(2, 2 * B, 1, **f32)
+        self.H1t, self.H2t, self.qt = t.zeros(2, B, H, **f32), t.zeros(2, B, H, **f32), t.zeros(2, B, 1, **f32)
+        self.dq, self.y, self.sums = t.zeros(2, 2 * B, 1, **f32), t.zeros(B, **f32), t.zeros(8, **f32)
+        self.dH2q, self.dH1q = t.zeros(2, 2 * B, H, **f32), t.zeros(2, 2 * B, H, **f32)
+        self.gX = t.zeros(B, QI, **f32)
+        self.dOUT, self.dH2p, self.dH1p = t.zeros(2 * B, 2 * A, **f32), t.zeros(B, H, **f32), t.zeros(B, H, **f32)
+
+    # -- kernels
+    def _bias_relu(self, x, bias, relu, nmat=1):
+        rows, cols = x.shape[-2], x.shape[-1]
+        _chk(self.L.rsb_bias_relu(_ptr(x), _ptr(bias), rows, cols, int(relu), nmat, rows * cols, cols, _stream(self.device)))
+
+    def _relu_bwd(self, dy, y):
+        _chk(self.L.rsb_relu_bwd(_ptr(dy), _ptr(y), dy.numel(), _stream(self.device)))
+
+    def _colsum(self, dy, r0, r1, db, nmat=1):
+        rows, cols = dy.shape[-2], dy.shape[-1]
+        _chk(self.L.rsb_colsum(_ptr(dy), r0, r1, cols, _ptr(db), nmat, rows * cols, cols, _stream(self.device)))
+
+    def _sample(self, step):
+        s = self.store
+        B, O = self.B, s.O
+        self.replay.sample_into(B, step, self.Xp, O, self.act, self.rew, self.term, self.Xp[B:], O, self.idx)
+
+    def load_batch(self, batch):
+        """Use an explicit batch (dict of tensors/arrays, rlkit keys) instead of sampling -- parity tests and `train(batch)`."""
+        t, B = self.torch, self.B
+        g = lambda k: t.as_tensor(np.asarray(batch[k]) if not t.is_tensor(batch[k]) else batch[k], dtype=t.float32, device=self.device)
+        self.Xp[:B].copy_(g("observations")); self.Xp[B:].copy_(g("next_observations"))
+        self.act.copy_(g("actions")); self.rew.copy_(g("rewards").reshape(-1)); self.term.copy_(g("terminals").reshape(-1))
+
+    def _update_body(self, step_for_noise, do_soft, external_eps):
+        t, s, L, B = self.torch, self.store, self.L, self.B
+        O, A, H, QI = s.O, s.A, s.H, s.O + s.A
+        P, G, T = s.P, s.G, s.T
+        st = _stream(self.device)
+        # inputs
+        self.XQ[:B, :O].copy_(self.Xp[:B]); self.XQ[B:, :O].copy_(self.Xp[:B]); self.XQ[B:, O:].copy_(self.act)
+        self.XT[:, :O].copy_(self.Xp[B:])
+        self.sums.zero_(); G["log_alpha"].zero_()
+        if not external_eps:
+            _chk(L.rsb_normal(C.c_uint64(self.seed), C.c_uint64(step_for_noise), 7, 2 * B * A, _ptr(self.eps), st))
+        # policy forward on [obs; next_obs]
+        t.mm(self.Xp, P["p_W0"], out=self.H1p); self._bias_relu(self.H1p, P["p_b0"], 1)
+        t.mm(self.H1p, P["p_W1"], out=self.H2p); self._bias_relu(self.H2p, P["p_b1"], 1)
+        t.mm(self.H2p, P["p_W2"], out=self.OUT); self._bias_relu(self.OUT, P["p_b2"], 0)
+        _chk(L.rsb_head_fwd(_ptr(self.OUT), _ptr(self.eps), 2 * B, A, _ptr(self.a_store), _ptr(self.logpi),
+                            C.c_void_p(self.XQ.data_ptr() + 4 * O), QI, 0, B, C.c_void_p(self.XT.data_ptr() + 4 * O), QI, B, 2 * B, st))
+        # twin Q forward (batched over the two networks) on [(obs,a_new); (obs,act)] and target twin Q on (next_obs, a')
+        XQ2, XT2 = self.XQ.unsqueeze(0).expand(2, 2 * B, QI), self.XT.unsqueeze(0).expand(2, B, QI)
+        t.bmm(XQ2, P["q_W0"], out=self.H1q); self._bias_relu(self.H1q, P["q_b0"], 1, 2)
+        t.bmm(self.H1q, P["q_W1"], out=self.H2q); self._bias_relu(self.H2q, P["q_b1"], 1, 2)
+        t.bmm(self.H2q, P["q_W2"], out=self.q); self._bias_relu(self.q, P["q_b2"], 0, 2)
+        t.bmm(XT2, T["q_W0"], out=self.H1t); self._bias_relu(self.H1t, T["q_b0"], 1, 2)
+        t.bmm(self.H1t, T["q_W1"], out=self.H2t); self._bias_relu(self.H2t, T["q_b1"], 1, 2)
+        t.bmm(self.H2t, T["q_W2"], out=self.qt); self._bias_relu(self.qt, T["q_b2"], 0, 2)
+        # losses and their gradients w.r.t. the Q outputs / log_alpha
+        _chk(L.rsb_sac_losses(_ptr(self.q), _ptr(self.qt), _ptr(self.logpi), _ptr(self.rew), _ptr(self.term), _ptr(self.alpha),
+                              self.reward_scale, self.discount, self.target_entropy, B, _ptr(self.dq), _ptr(self.y), _ptr(self.sums),
+                              _ptr(G["log_alpha"]), st))
+        # twin-Q backward: weight grads from the Bellman rows [B, 2B) only, input grads for the policy rows [0, B)
+        t.bmm(self.H2q[:, B:].transpose(1, 2), self.dq[:, B:], out=G["q_W2"]); self._colsum(self.dq, B, 2 * B, G["q_b2"], 2)
+        t.bmm(self.dq, P["q_W2"].transpose(1, 2), out=self.dH2q); self._relu_bwd(self.dH2q, self.H2q)
+        t.bmm(self.H1q[:, B:].transpose(1, 2), self.dH2q[:, B:], out=G["q_W1"]); self._colsum(self.dH2q, B, 2 * B, G["q_b1"], 2)
+        t.bmm(self.dH2q, P["q_W1"].transpose(1, 2), out=self.dH1q); self._relu_bwd(self.dH1q, self.H1q)
+        t.bmm(XQ2[:, B:].transpose(1, 2), self.dH1q[:, B:], out=G["q_W0"]); self._colsum(self.dH1q, B, 2 * B, G["q_b0"], 2)
+        t.mm(self.dH1q[0, :B], P["q_W0"][0].t(), out=self.gX); self.gX.addmm_(self.dH1q[1, :B], P["q_W0"][1].t())
+        # policy backward
+        _chk(L.rsb_head_bwd(_ptr(self.OUT), _ptr(self.eps), _ptr(self.a_store), 2 * B, B, A, _ptr(self.alpha),
+                            C.c_void_p(self.gX.data_ptr() + 4 * O), QI, _ptr(self.dOUT), st))
+        t.mm(self.H2p[:B].t(), self.dOUT[:B], out=G["p_W2"]); self._colsum(self.dOUT, 0, B, G["p_b2"])
+        t.mm(self.dOUT[:B], P["p_W2"].t(), out=self.dH2p); self._relu_bwd(self.dH2p, self.H2p[:B])
+        t.mm(self.H1p[:B].t(), self.dH2p, out=G["p_W1"]); self._colsum(self.dH2p, 0, B, G["p_b1"])
+        t.mm(self.dH2p, P["p_W1"].t(), out=self.dH1p); self._relu_bwd(self.dH1p, self.H1p[:B])
+        t.mm(self.Xp[:B].t(), self.dH1p, out=G["p_W0"]); self._colsum(self.dH1p, 0, B, G["p_b0"])
+
+    def _apply(self, do_soft):
+        s = self.store
+        _chk(self.L.rsb_adam_polyak(_ptr(s.flat), _ptr(s.grad), _ptr(s.m), _ptr(s.v), s.n, _ptr(self.lr), 0.9, 0.999, 1e-8, _ptr(self.bc),
+                                    _ptr(s.target), s.q_begin, s.q_end, self.tau, int(do_soft), _ptr(self.alpha), s.offsets["log_alpha"],
+                                    _stream(self.device)))
+
+    def _allreduce(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.store.grad)                        # ONE flat bucket per update (sum), then mean
+            self.store.grad.mul_(1.0 / self.world)
+
+    # -- public
+    def train_step(self, batch=None, eps=None):
+        """One SAC update.  batch=None samples from the replay ring with the Philox rule; `eps` overrides the policy noise."""
+        t = self.torch
+        step = self._n_train_steps_total
+        do_soft = (step % self.period) == 0
+        old = t.backends.cuda.matmul.allow_tf32
+        t.backends.cuda.matmul.allow_tf32 = self.tf32
+        try:
+            if batch is not None:
+                self.load_batch(batch)
+            else:
+                self._sample(step)
+            if eps is not None:
+                self.eps.copy_(t.as_tensor(eps, dtype=t.float32, device=self.device).reshape(self.eps.shape))
+            if self.use_graph and batch is None and eps is None:
+                # the replay `size` argument is baked into a captured launch: sampling stays outside the graphs
+                key = "noise+body"
+                if key not in self._graphs:
+                    self._warm(lambda: self._update_body(step, do_soft, False))
+                    g = t.cuda.CUDAGraph()
+                    with t.cuda.graph(g):
+                        self._update_body(0, do_soft, True)            # noise generated outside (its counter changes per step)
+                    ga, gb = t.cuda.CUDAGraph(), t.cuda.CUDAGraph()
+                    with t.cuda.graph(ga):
+                        self._apply(True)
+                    with t.cuda.graph(gb):
+                        self._apply(False)
+                    self._graphs[key] = (g, ga, gb)
+                g, ga, gb = self._graphs[key]
+                _chk(self.L.rsb_normal(C.c_uint64(self.seed), C.c_uint64(step), 7, self.eps.numel(), _ptr(self.eps), _stream(self.device)))
+                g.replay()
+                self._allreduce()
+                (ga if do_soft else gb).replay()
+            else:
+                self._update_body(step, do_soft, eps is not None)
+                self._allreduce()
+                self._apply(do_soft)
+        finally:
+            t.backends.cuda.matmul.allow_tf32 = old
+        if self._need_to_update_eval_statistics:
+            self._need_to_update_eval_statistics = False
+            self._fill_statistics()
+        self._n_train_steps_total += 1
+
+    def _warm(self, fn):
+        """Graph capture must not be the first time cuBLAS sees these shapes (workspace allocation): run the body once eagerly
+        on a side stream (it only writes scratch buffers and the gradient buffer, never the parameters)."""
+        t = self.torch
+        side = t.cuda.Stream(self.device)
+        side.wait_stream(t.cuda.current_stream(self.device))
+        with t.cuda.stream(side):
+            fn()
+        t.cuda.current_stream(self.device).wait_stream(side)
+        t.cuda.synchronize(self.device)
+
+    def train(self, np_batch):
+        """rlkit TorchTrainer.train(np_batch) (util/rlkit_custom.py:238)."""
+        self.train_step(batch=np_batch)
+
+    train_from_torch = train
+
+    def _fill_statistics(self):
+        t, B, A = self.torch, self.B, self.store.A
+        s = self.sums.cpu().numpy()
+        st = OrderedDict()
+        st["QF1 Loss"], st["QF2 Loss"], st["Policy Loss"] = float(s[0]), float(s[1]), float(s[2])
+
+        def add(name, x):
+            x = x.detach().float().reshape(-1)
+            st[name + " Mean"], st[name + " Std"] = float(x.mean()), float(x.std(unbiased=False))
+            st[name + " Max"], st[name + " Min"] = float(x.max()), float(x.min())
+
+        add("Q1 Predictions", self.q[0, B:]); add("Q2 Predictions", self.q[1, B:]); add("Q Targets", self.y)
+        add("Log Pis", self.logpi[:B]); add("Policy mu", self.OUT[:B, :A]); add("Policy log std", self.OUT[:B, A:].clamp(-20, 2))
+        st["Alpha"], st["Alpha Loss"] = float(self.alpha[0].item()), float(s[3])
+        self.eval_statistics = st
+
+    def get_diagnostics(self):
+        return self.eval_statistics
+
+    def end_epoch(self, epoch):
+        self._need_to_update_eval_statistics = True
+
+    @property
+    def networks(self):
+        return [self.policy, self.qf1, self.qf2, self.target_qf1, self.target_qf2]
+
+    def get_snapshot(self):
+        return dict(policy=self.policy, qf1=self.qf1, qf2=self.qf2, target_qf1=self.target_qf1, target_qf2=self.target_qf2)
+
+
+def algorithmic_flops_per_update(obs_dim, act_dim, batch, hidden=HID):
+    """2*B*[6*MAC_Q + 2*MAC_pi (fwd) + 2*(2*MAC_Q + MAC_pi) + 4*MAC_Q (bwd)]."""
+    mq = (obs_dim + act_dim) * hidden + hidden * hidden + hidden
+    mp = obs_dim * hidden + hidden * hidden + 2 * act_dim * hidden
+    return 2 * batch * (6 * mq + 2 * mp + 2 * (2 * mq + mp) + 4 * mq)

@@ -1,0 +1,122 @@
+"""GPU parity of the replay sampling and SAC update kernels (through the C-ABI of include/rsb_sac.h) against the CPU oracle
+(oracle/sac_oracle.py, PyTorch fp32 autograd).  Replay indices: bit-exact.  Floating point: fp32 GEMM mode within 2e-5 relative
+of the oracle's gradients / 1e-6 absolute on parameters after an update; TF32 mode (the benchmarked mode) within 1e-2 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+O, A, B = 42, 7, 128
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch
+
+
+def _ring(torch, n=5800, cap=8192, seed=17):
+    from robosuite_benchmark_b200.sac import EnvReplayBuffer
+    rng = np.random.default_rng(0)
+    rb = EnvReplayBuffer(cap, obs_dim=O, action_dim=A, device="cuda:0", seed=seed)
+    data = dict(obs=rng.normal(size=(n, O)).astype(np.float32) * 0.5, act=np.tanh(rng.normal(size=(n, A))).astype(np.float32),
+                rew=rng.uniform(0, 0.03, size=n).astype(np.float32), term=(rng.uniform(size=n) < 0.01).astype(np.uint8),
+                nxt=rng.normal(size=(n, O)).astype(np.float32) * 0.5)
+    for lo in range(0, n, 1450):                  # appended in batches, like the collectors do
+        sl = slice(lo, min(n, lo + 1450))
+        rb.add_batch(*(torch.as_tensor(data[k][sl], device="cuda:0") for k in ("obs", "act", "rew", "term", "nxt")))
+    return rb, data
+
+
+def test_replay_indices_bit_exact_and_rows_gathered(torch_cuda):
+    from oracle.sac_oracle import replay_indices
+    rb, data = _ring(torch_cuda)
+    assert rb.get_diagnostics()["size"] == 5800
+    for draw in range(3):
+        b = rb.random_batch(B)
+        idx = b["indices"].cpu().numpy()
+        assert (idx == replay_indices(17, draw, B, 5800)).all()                # bit-exact sample indices
+        assert (b["observations"].cpu().numpy() == data["obs"][idx]).all() and (b["next_observations"].cpu().numpy() == data["nxt"][idx]).all()
+        assert (b["actions"].cpu().numpy() == data["act"][idx]).all() and (b["rewards"].cpu().numpy()[:, 0] == data["rew"][idx]).all()
+        assert (b["terminals"].cpu().numpy()[:, 0] == data["term"][idx]).all()
+
+
+def test_ring_wraps_like_rlkit(torch_cuda):
+    torch = torch_cuda
+    from robosuite_benchmark_b200.sac import EnvReplayBuffer
+    rb = EnvReplayBuffer(10, obs_dim=2, action_dim=1, device="cuda:0")
+    for k in range(4):
+        n = 3
+        v = torch.full((n, 2), float(k), device="cuda:0")
+        rb.add_batch(v, v[:, :1], v[:, 0], torch.zeros(n, dtype=torch.uint8, device="cuda:0"), v + 0.5)
+    assert rb._size == 10 and rb._top == 2
+    assert rb._observations[:, 0].cpu().tolist() == [3.0, 3.0, 0.0, 1.0, 1.0, 1.0, 2.0, 2.0, 2.0, 3.0]
+
+
+def _pair(torch, tf32, graph=False, period=5):
+    from oracle.sac_oracle import SacOracle
+    from robosuite_benchmark_b200.sac import ParamStore, SACTrainer
+    store = ParamStore(O, A, "cuda:0", seed=3)
+    params, targets = store.to_host()
+    kw = dict(discount=0.99, reward_scale=1.0, policy_lr=1e-3, qf_lr=5e-4, soft_target_tau=0.005, target_update_period=period)
+    tr = SACTrainer(store=store, batch_size=B, tf32=tf32, use_graph=graph, seed=5, **kw)
+    return store, tr, SacOracle(params, targets, O, A, **kw)
+
+
+def test_update_matches_oracle_fp32(torch_cuda):
+    torch = torch_cuda
+    store, tr, orc = _pair(torch, tf32=False)
+    rng = np.random.default_rng(1)
+    for step in range(6):                          # crosses a Polyak step (period 5 -> steps 0 and 5)
+        batch = dict(observations=rng.normal(size=(B, O)).astype(np.float32) * 0.5, actions=np.tanh(rng.normal(size=(B, A))).astype(np.float32),
+                     rewards=rng.uniform(0, 0.03, size=(B, 1)).astype(np.float32), terminals=(rng.uniform(size=(B, 1)) < 0.05).astype(np.float32),
+                     next_observations=rng.normal(size=(B, O)).astype(np.float32) * 0.5)
+        eps = rng.normal(size=(2 * B, A)).astype(np.float32)
+        g_ref = orc.train(batch, eps)
+        tr.train_step(batch=batch, eps=eps)
+        torch.cuda.synchronize()
+        for k, gr in g_ref.items():
+            got = store.G[k].cpu().numpy()
+            scale = max(np.abs(gr.numpy()).max(), 1e-8)
+            assert np.abs(got - gr.numpy()).max() <= 2e-5 * scale + 1e-9, (step, k)
+        p_ref, t_ref = orc.params()
+        p_got, t_got = store.to_host()
+        for k in p_ref:
+            assert np.abs(p_ref[k] - p_got[k]).max() < 2e-6, (step, k)
+        for k in t_ref:
+            assert np.abs(t_ref[k] - t_got[k]).max() < 2e-6, (step, k)
+        st = tr.get_diagnostics() if step == 0 else None
+        if st:
+            for k in ("QF1 Loss", "QF2 Loss", "Policy Loss", "Alpha", "Alpha Loss"):
+                assert abs(st[k] - orc.stats[k]) <= 1e-5 * max(1.0, abs(orc.stats[k])), k
+            assert np.float32(st["Alpha"]) == np.float32(0.9990004897117615)      # the reference's logged first-update value
+
+
+def test_tf32_graph_update_close_to_oracle_and_to_eager(torch_cuda):
+    torch = torch_cuda
+    rb, _ = _ring(torch)
+    store, tr, orc = _pair(torch, tf32=True, graph=True)
+    tr.replay = rb
+    store2, tr2, _ = _pair(torch, tf32=True, graph=False)
+    tr2.replay = rb
+    for step in range(7):
+        tr.train_step(); tr2.train_step()
+    torch.cuda.synchronize()
+    a, _ = store.to_host(); b, _ = store2.to_host()
+    for k in a:
+        assert np.abs(a[k] - b[k]).max() < 1e-6, k           # graph replay == eager launches
+    # against the fp32 oracle fed the same sampled batches and the same Philox noise
+    from oracle.sac_oracle import replay_indices
+    store3, tr3, orc3 = _pair(torch, tf32=True, graph=False)
+    tr3.replay = rb
+    tr3.train_step()
+    torch.cuda.synchronize()
+    idx = tr3.idx.cpu().numpy()
+    assert (idx == replay_indices(17, 0, B, 5800)).all()
+    batch = dict(observations=tr3.Xp[:B].cpu().numpy(), next_observations=tr3.Xp[B:].cpu().numpy(), actions=tr3.act.cpu().numpy(),
+                 rewards=tr3.rew.cpu().numpy(), terminals=tr3.term.cpu().numpy())
+    g_ref = orc3.train(batch, tr3.eps.cpu().numpy())
+    for k, gr in g_ref.items():
+        scale = max(np.abs(gr.numpy()).max(), 1e-8)
+        assert np.abs(store3.G[k].cpu().numpy() - gr.numpy()).max() <= 1e-2 * scale, k
