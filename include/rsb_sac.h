@@ -28,7 +28,7 @@ int rsb_head_fwd(const float *d_out, const float *d_eps, int rows, int act_dim, 
 int rsb_head_bwd(const float *d_out, const float *d_eps, const float *d_a, int rows, int batch, int act_dim, const float *d_alpha, const float *d_ga, int ld_ga, float *d_dout, void *stream);
 int rsb_sac_losses(const float *d_q, const float *d_qt, const float *d_logpi, const float *d_rew, const float *d_term, const float *d_alpha, float reward_scale, float discount,
                    float target_entropy, int batch, float *d_dq, float *d_y, float *d_sums, float *d_galpha, void *stream);
-int rsb_adam_polyak(float *d_p, const float *d_g, float *d_m, float *d_v, long n, const float *d_lr, float b1, float b2, float eps, float *d_bc,
+int rsb_adam_polyak(float *d_p, const float *d_g, float *d_m, float *d_v, long n, double lr_pi, double lr_q, float b1, float b2, float eps, double *d_bc /* [4] = {0,0,1,1} at start */,
                     float *d_tgt, long tgt_begin, long tgt_end, float tau, int do_soft, float *d_alpha, long log_alpha_idx, void *stream);
 #ifdef __cplusplus
 }

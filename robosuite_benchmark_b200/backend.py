@@ -68,7 +68,7 @@ def lib():
         L.rsb_head_fwd.argtypes = [V, V, I, I, V, V, V, I, I, I, V, I, I, I, V]
         L.rsb_head_bwd.argtypes = [V, V, V, I, I, I, V, V, I, V, V]
         L.rsb_sac_losses.argtypes = [V, V, V, V, V, V, F, F, F, I, V, V, V, V, V]
-        L.rsb_adam_polyak.argtypes = [V, V, V, V, L_, V, F, F, F, V, V, L_, L_, F, I, V, L_, V]
+        L.rsb_adam_polyak.argtypes = [V, V, V, V, L_, C.c_double, C.c_double, F, F, F, V, V, L_, L_, F, I, V, L_, V]
         _LIB = L
     return _LIB
 

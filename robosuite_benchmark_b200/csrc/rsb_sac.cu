@@ -152,21 +152,23 @@ __global__ void k_losses(const float *__restrict__ q, const float *__restrict__ 
 }
 
 /* ---------------------------------------------------------------- Adam (torch.optim.Adam semantics) + Polyak, one launch over the flat buffer
-   segment table seg[k] = (begin, end, lr); params/grads/m/v are flat fp32; tgt_map[i] >= 0 gives the index of the target
-   copy of parameter i (Q networks) or -1; the soft update uses the UPDATED parameter, as rlkit does (step, then soft_update). */
+   params/grads/m/v are flat fp32; the Q segment [tgt_begin, tgt_end) uses lr_q and has a target copy `tgt`, the rest uses lr_pi; the soft update uses the UPDATED parameter, as rlkit does (step, then soft_update). */
 __global__ void k_adam_polyak(float *__restrict__ p, const float *__restrict__ gr, float *__restrict__ m, float *__restrict__ v, long n,
-                              const float *__restrict__ lr_elem, float b1, float b2, float eps, const float *__restrict__ bias_corr /* [bc1, sqrt(bc2)] device */,
+                              double lr_pi, double lr_q, float b1, float b2, float eps, const double *__restrict__ bc /* [1-b1^t, sqrt(1-b2^t), b1^t, b2^t] */,
                               float *__restrict__ tgt, long tgt_begin, long tgt_end, float tau, int do_soft,
                               float *__restrict__ alpha_out /* [alpha, log_alpha] refreshed from p[log_alpha_idx] */, long log_alpha_idx) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  const bool isq = i >= tgt_begin && i < tgt_end;
+  /* torch.optim.Adam keeps step_size = lr / bias_correction1 and sqrt(bias_correction2) as Python doubles, cast to fp32 at use */
+  const float step_size = (float)((isq ? lr_q : lr_pi) / bc[0]), bc2s = (float)bc[1];
   float g = gr[i], mi = b1 * m[i] + (1.0f - b1) * g, vi = b2 * v[i] + (1.0f - b2) * g * g; m[i] = mi; v[i] = vi;
-  float denom = sqrtf(vi) / bias_corr[1] + eps, pi = p[i] - (lr_elem[i] / bias_corr[0]) * (mi / denom); p[i] = pi;
-  if (do_soft && i >= tgt_begin && i < tgt_end) { long k = i - tgt_begin; tgt[k] = (1.0f - tau) * tgt[k] + tau * pi; }
-  if (i == log_alpha_idx) { alpha_out[1] = pi; alpha_out[0] = expf(pi); }
+  float denom = sqrtf(vi) / bc2s + eps, pi = p[i] - step_size * (mi / denom); p[i] = pi;
+  if (do_soft && isq) { long k = i - tgt_begin; tgt[k] = (1.0f - tau) * tgt[k] + tau * pi; }
+  if (i == log_alpha_idx) { alpha_out[1] = pi; alpha_out[0] = (float)exp((double)pi); }      /* correctly rounded, like torch's CPU exp */
 }
-/* bias corrections advance on the device so the whole update is graph-replayable: bc[2]=beta1^t, bc[3]=beta2^t */
-__global__ void k_adam_tick(float *__restrict__ bc, float b1, float b2) {
-  float p1 = bc[2] * b1, p2 = bc[3] * b2; bc[2] = p1; bc[3] = p2; bc[0] = 1.0f - p1; bc[1] = sqrtf(1.0f - p2);
+/* bias corrections advance on the device so the whole update is graph-replayable */
+__global__ void k_adam_tick(double *__restrict__ bc, double b1, double b2) {
+  double p1 = bc[2] * b1, p2 = bc[3] * b2; bc[2] = p1; bc[3] = p2; bc[0] = 1.0 - p1; bc[1] = sqrt(1.0 - p2);
 }
 
 extern "C" {
@@ -199,10 +201,10 @@ int rsb_sac_losses(const float *d_q, const float *d_qt, const float *d_logpi, co
                    float target_entropy, int batch, float *d_dq, float *d_y, float *d_sums, float *d_galpha, void *stream) {
   k_losses<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_q, d_qt, d_logpi, d_rew, d_term, d_alpha, reward_scale, discount, target_entropy, batch, d_dq, d_y, d_sums, d_galpha); CKS(cudaGetLastError()); return 0;
 }
-int rsb_adam_polyak(float *d_p, const float *d_g, float *d_m, float *d_v, long n, const float *d_lr, float b1, float b2, float eps, float *d_bc,
+int rsb_adam_polyak(float *d_p, const float *d_g, float *d_m, float *d_v, long n, double lr_pi, double lr_q, float b1, float b2, float eps, double *d_bc,
                     float *d_tgt, long tgt_begin, long tgt_end, float tau, int do_soft, float *d_alpha, long log_alpha_idx, void *stream) {
-  k_adam_tick<<<1, 1, 0, (cudaStream_t)stream>>>(d_bc, b1, b2);
-  k_adam_polyak<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_p, d_g, d_m, d_v, n, d_lr, b1, b2, eps, d_bc, d_tgt, tgt_begin, tgt_end, tau, do_soft, d_alpha, log_alpha_idx);
+  k_adam_tick<<<1, 1, 0, (cudaStream_t)stream>>>(d_bc, (double)b1, (double)b2);
+  k_adam_polyak<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_p, d_g, d_m, d_v, n, lr_pi, lr_q, b1, b2, eps, d_bc, d_tgt, tgt_begin, tgt_end, tau, do_soft, d_alpha, log_alpha_idx);
   CKS(cudaGetLastError()); return 0;
 }
 }

@@ -317,12 +317,8 @@ class SACTrainer:
         self.eval_statistics = OrderedDict()
         f32 = dict(dtype=torch.float32, device=self.device)
         n = store.n
-        lr = torch.empty(n, **f32)
-        lr[:store.q_begin] = policy_lr
-        lr[store.q_begin:store.q_end] = qf_lr
-        lr[store.q_end:] = policy_lr
-        self.lr = lr
-        self.bc = torch.tensor([0.0, 0.0, 1.0, 1.0], **f32)
+        self.policy_lr, self.qf_lr = float(policy_lr), float(qf_lr)
+        self.bc = torch.tensor([0.0, 0.0, 1.0, 1.0], dtype=torch.float64, device=self.device)
         self.alpha = torch.tensor([1.0, 0.0], **f32)                 # [alpha, log_alpha] (device copy read by the kernels)
         self._alloc(self.B)
         self._graphs = {}
@@ -418,7 +414,7 @@ class SACTrainer:
 
     def _apply(self, do_soft):
         s = self.store
-        _chk(self.L.rsb_adam_polyak(_ptr(s.flat), _ptr(s.grad), _ptr(s.m), _ptr(s.v), s.n, _ptr(self.lr), 0.9, 0.999, 1e-8, _ptr(self.bc),
+        _chk(self.L.rsb_adam_polyak(_ptr(s.flat), _ptr(s.grad), _ptr(s.m), _ptr(s.v), s.n, self.policy_lr, self.qf_lr, 0.9, 0.999, 1e-8, _ptr(self.bc),
                                     _ptr(s.target), s.q_begin, s.q_end, self.tau, int(do_soft), _ptr(self.alpha), s.offsets["log_alpha"],
                                     _stream(self.device)))
 
