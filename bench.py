@@ -53,7 +53,7 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_baseline(steps_per_worker=300):
+def cpu_baseline(steps_per_worker=12000):
     """The fp64 C oracle (a PORT of the reference's CPU path; the real robosuite+mujoco cannot be installed here) as one
     process per host core, same workload; steps/s summed over workers."""
     import multiprocessing as mp
@@ -236,6 +236,9 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * E * e2e_steps / float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    sac = None
+    if not args.no_sac:
+        sac = sac_bench(dev, sim.obs_dim, sim.act_dim, world, rank)
 
     if rank == 0:
         peaks = {}
@@ -266,10 +269,44 @@ def run_ours(args):
                              "note": "state stays in shared memory for the 25 substeps: the kernel is issue/latency-bound, not HBM-bound (DESIGN.md)"},
                 "kernel_info": {"regs": sim.info("regs_step"), "smem_bytes_per_env": sim.info("smem_bytes"),
                                 "envs_per_block": sim.info("envs_per_block"), "blocks_per_sm": sim.info("blocks_per_sm")},
-                "cpu_baseline": cpu}
+                "sac": sac, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sac_bench(dev, obs_dim, act_dim, world, rank, updates=300):
+    """SAC updates/s (the second half of BASELINE.json's metric): replay ring pre-filled with 1e6 synthetic transitions, Philox-sampled
+    batches, 256x256 twin-Q + tanh-Gaussian policy, reference hyper-parameters; B = 128 (the reference's batch) and B = 4096."""
+    import torch
+    from robosuite_benchmark_b200.sac import EnvReplayBuffer, ParamStore, SACTrainer, algorithmic_flops_per_update
+    n = 1_000_000
+    rb = EnvReplayBuffer(n, obs_dim=obs_dim, action_dim=act_dim, device=dev, seed=SEED + rank)
+    g = torch.Generator(device=dev); g.manual_seed(SEED + rank)
+    for lo in range(0, n, 250_000):
+        m = 250_000
+        obs = torch.randn(m, obs_dim, device=dev, generator=g) * 0.5
+        rb.add_batch(obs, torch.tanh(torch.randn(m, act_dim, device=dev, generator=g)), torch.rand(m, device=dev, generator=g) * 0.1,
+                     torch.zeros(m, dtype=torch.uint8, device=dev), obs + 0.05 * torch.randn(m, obs_dim, device=dev, generator=g))
+    out = {"gemm": "cuBLAS TF32 (fp32 accumulate)", "ring_transitions": n, "world": world}
+    for B in (128, 4096):
+        store = ParamStore(obs_dim, act_dim, dev, seed=SEED)
+        tr = SACTrainer(store=store, replay_buffer=rb, batch_size=B, discount=0.99, reward_scale=1.0, policy_lr=1e-3, qf_lr=5e-4,
+                        soft_target_tau=0.005, target_update_period=5, seed=SEED, tf32=True, use_graph=True, world_size=world)
+        for _ in range(10):
+            tr.train_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(updates):
+            tr.train_step()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / updates
+        fl = algorithmic_flops_per_update(obs_dim, act_dim, B)
+        out[f"b{B}"] = {"updates_per_s": 1000.0 / ms, "samples_per_s": world * B * 1000.0 / ms, "us_per_update": 1000.0 * ms,
+                        "algorithmic_gflop_per_update": fl / 1e9, "achieved_tflops": fl / (ms / 1000.0) / 1e12}
+        del tr, store
+    return out
 
 
 def main():
@@ -280,6 +317,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sac", action="store_true", help="skip the SAC updates/s leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,47 @@
+"""End-to-end: the reference's `--variant` JSON drives the batched training loop; outputs carry the reference's schema."""
+import csv
+import glob
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _variant(tmp, n_epochs=2):
+    v = json.load(open(os.path.join(GOLDEN, "variant_Lift-Panda-OSC-POSE-SEED17.json")))      # verbatim copy of the committed run's variant.json
+    v["algorithm_kwargs"].update(num_epochs=n_epochs, num_eval_steps_per_epoch=40, num_expl_steps_per_train_loop=40,
+                                 num_trains_per_train_loop=12, min_num_steps_before_training=80, expl_max_path_length=20, eval_max_path_length=20)
+    v["replay_buffer_size"] = 4096
+    p = os.path.join(tmp, "variant.json")
+    json.dump(v, open(p, "w"))
+    return p
+
+
+@pytest.mark.parametrize("num_envs", [1, 2])
+def test_variant_json_trains_and_logs_reference_schema(tmp_path, num_envs):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from robosuite_benchmark_b200.train import build_parser, run_experiment
+    args = build_parser().parse_args(["--variant", _variant(str(tmp_path)), "--seed", "17", "--log_dir", str(tmp_path / "log"), "--num_envs", str(num_envs)])
+    algo, log_dir = run_experiment(args)
+    assert os.path.basename(os.path.dirname(log_dir)) == "Lift_Panda_OSC_POSE_SEED17"
+    rows = list(csv.DictReader(open(os.path.join(log_dir, "progress.csv"))))
+    cols = json.load(open(os.path.join(GOLDEN, "progress_columns.json")))
+    assert list(rows[0].keys()) == cols                      # the reference's 83 columns, same order
+    assert len(rows) == 2 and rows[1]["Epoch"] == "1"
+    r0 = rows[0]
+    assert float(r0["replay_buffer/size"]) == 120.0           # 80 warm-up + 40 exploration transitions
+    assert float(r0["exploration/num paths total"]) == 6.0 and float(r0["evaluation/num paths total"]) == 2.0
+    assert np.float32(float(r0["trainer/Alpha"])) == np.float32(0.9990004897117615) and float(r0["trainer/Alpha Loss"]) == 0.0
+    assert abs(float(r0["trainer/Log Pis Mean"]) + 0.67 * 7) < 0.6
+    snap = pickle.load(open(os.path.join(log_dir, "params.pkl"), "rb"))
+    assert sorted(snap) == sorted(["trainer/policy", "trainer/qf1", "trainer/qf2", "trainer/target_qf1", "trainer/target_qf2",
+                                   "exploration/policy", "evaluation/policy"])
+    assert tuple(snap["trainer/policy"]["fc0.weight"].shape) == (256, 42) and tuple(snap["trainer/qf1"]["fc0.weight"].shape) == (256, 49)
+    assert json.load(open(os.path.join(log_dir, "variant.json")))["trainer_kwargs"]["qf_lr"] == 0.0005
