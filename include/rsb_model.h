@@ -114,6 +114,9 @@ typedef struct rsb_task {
   double place_x[RSB_MAX_OBJ][2], place_y[RSB_MAX_OBJ][2], place_yaw[RSB_MAX_OBJ][2];
   double place_z[RSB_MAX_OBJ];             /* absolute z written to the free joint */
   double place_ref[3];                     /* reference point added to sampled xy */
+  /* place_body[o] >= 0: object o is a FIXED body (no free joint; robosuite writes model.body_pos/body_quat at reset, e.g. the
+     Door): the sampled pose (place_ref + xy, place_z, yaw about z) overrides that body's pos/quat for this env.  At most one. */
+  int place_body[RSB_MAX_OBJ];
 } rsb_task;
 
 #ifdef __cplusplus

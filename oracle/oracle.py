@@ -112,6 +112,15 @@ class OracleEnv:
         self.L.orc_set_state(C.c_void_p(self.h), _p(qpos), _p(qvel), None if warm is None else _p(warm),
                              None if cs is None else _p(cs))
 
+    def get_bpose(self):
+        b = np.zeros(7)
+        self.L.orc_get_bpose(C.c_void_p(self.h), _p(b))
+        return b
+
+    def set_bpose(self, b):
+        b = np.ascontiguousarray(b, np.float64)
+        self.L.orc_set_bpose(C.c_void_p(self.h), _p(b))
+
     def set_timestep(self, t):
         self.L.orc_set_timestep(C.c_void_p(self.h), int(t))
 

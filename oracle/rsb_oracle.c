@@ -62,6 +62,7 @@ typedef struct orc_env {
   int ncon_max, nefc_max;
   /* state */
   real qpos[MAXQ], qvel[MAXV], qacc_warmstart[MAXV], ctrl[MAXU];
+  real bpose[7]; int override_body;          /* per-env pose of the task's placed FIXED body (rsb_task.place_body), -1 if none */
   orc_ctrl rc[RSB_MAX_ROBOTS];
   int timestep, done;
   uint64_t episode;
@@ -160,6 +161,9 @@ orc_env *orc_create(const rsb_model *src, const rsb_task *task, int ncon_max) {
   DUPI(act_dofid, nu); DUPI(act_ctrllimited, nu); DUPI(act_forcelimited, nu);
   DUPD(act_gain, nu); DUPD(act_bias, 3 * nu); DUPD(act_ctrlrange, 2 * nu); DUPD(act_forcerange, 2 * nu); DUPD(act_gear, nu);
   e->efc_J = (real *)calloc((size_t)MAXEFC * MAXV, sizeof(real));
+  e->override_body = -1;
+  for (int o = 0; o < RSB_MAX_OBJ; o++) if (task->place_body[o] >= 0) { int b = task->place_body[o]; e->override_body = b;
+    for (int k = 0; k < 3; k++) e->bpose[k] = src->body_pos[3 * b + k]; for (int k = 0; k < 4; k++) e->bpose[3 + k] = src->body_quat[4 * b + k]; }
   for (int i = 0; i < src->nq; i++) e->qpos[i] = src->qpos0[i];
   return e;
 }
@@ -181,9 +185,9 @@ static void kinematics(orc_env *e) {
       v3copy(pos, e->qpos + a); memcpy(quat, e->qpos + a + 3, sizeof quat);
       v3copy(e->xanchor[ja], pos); v3set(e->xaxis[ja], 0, 0, 1);
     } else {
-      real t[3];
-      m3mulv(t, e->xmat[p], m->body_pos + 3 * b); v3addscl(pos, e->xpos[p], t, 1);
-      qmul(quat, e->xquat[p], m->body_quat + 4 * b);
+      real t[3]; const real *bp = b == e->override_body ? e->bpose : m->body_pos + 3 * b, *bq = b == e->override_body ? e->bpose + 3 : m->body_quat + 4 * b;
+      m3mulv(t, e->xmat[p], bp); v3addscl(pos, e->xpos[p], t, 1);
+      qmul(quat, e->xquat[p], bq);
       for (int k = 0; k < jn; k++) {
         int j = ja + k; real dq = e->qpos[m->jnt_qposadr[j]] - m->qpos0[m->jnt_qposadr[j]];
         real anchor[3], axis[3];
@@ -1021,6 +1025,22 @@ static real task_reward(const orc_env *e) {
     }
     return r * t->reward_scale / 1.0;
   }
+  if (t->task_id == RSB_TASK_TWOARMLIFT) {
+    /* A.6: tilt gate cos(angle(z_pot, z)) >= cos 30 deg; success pot bottom > table + 0.10 -> 3 * gate; else lift shaping 10 * gate *
+       clamp(elevation - 0.05, 0, 0.15) + per arm (0.25 if grasping its handle else 0.5 (1 - tanh(10 d))); scaled by 1/3 */
+    const real *pot = e->xpos[t->obj_body[0]], *Rp = e->xmat[t->obj_body[0]];
+    real cos_z = Rp[8], gate = cos_z >= cos(M_PI / 6.0) ? 1.0 : 0.0;
+    real bottom = pot[2] - t->obj_half[0][2], elev = bottom - t->table_height;
+    if (elev > 0.10) r = 3.0 * gate;
+    else if (t->reward_shaping) {
+      real lift = elev - 0.05; if (lift < 0) lift = 0; if (lift > 0.15) lift = 0.15; r += 10.0 * gate * lift;
+      for (int ri = 0; ri < 2; ri++) {
+        const real *eef = e->site_xpos[t->robot[ri].eef_site], *hs = e->site_xpos[t->obj_site[ri]]; real d[3]; v3sub(d, eef, hs);
+        if (check_grasp(e, ri, t->obj_geom[ri])) r += 0.25; else r += 0.5 * (1 - tanh(10.0 * v3norm(d)));
+      }
+    }
+    return r * t->reward_scale / 3.0;
+  }
   return 0;
 }
 
@@ -1060,6 +1080,17 @@ static void observation(const orc_env *e, real *obs) {
     for (int k = 0; k < 3; k++) obs[n++] = door[k] - eef[k];
     for (int k = 0; k < 3; k++) obs[n++] = hs[k] - eef[k];
     obs[n++] = e->qpos[t->obj_qposadr[0]]; obs[n++] = e->qpos[t->obj_qposadr[1]];
+  } else if (t->task_id == RSB_TASK_TWOARMLIFT) {
+    const real *pot = e->xpos[t->obj_body[0]], *e0 = e->site_xpos[t->robot[0].eef_site], *e1 = e->site_xpos[t->robot[1].eef_site];
+    const real *h0 = e->site_xpos[t->obj_site[0]], *h1 = e->site_xpos[t->obj_site[1]];
+    for (int k = 0; k < 3; k++) obs[n++] = pot[k];
+    put_quat_xyzw(obs + n, e->xquat[t->obj_body[0]]); n += 4;
+    for (int k = 0; k < 3; k++) obs[n++] = e0[k];
+    for (int k = 0; k < 3; k++) obs[n++] = e1[k];
+    for (int k = 0; k < 3; k++) obs[n++] = h0[k];
+    for (int k = 0; k < 3; k++) obs[n++] = h1[k];
+    for (int k = 0; k < 3; k++) obs[n++] = h0[k] - e0[k];
+    for (int k = 0; k < 3; k++) obs[n++] = h1[k] - e1[k];
   }
 }
 
@@ -1097,7 +1128,7 @@ void orc_reset(orc_env *e, uint64_t seed, uint64_t env_id, uint64_t episode) {
   }
   /* object placement: uniform xy + yaw per object (robosuite UniformRandomSampler; rejection for overlaps) */
   for (int o = 0; o < RSB_MAX_OBJ; o++) {
-    if (t->obj_qposadr[o] < 0 || t->place_z[o] <= 0) continue;
+    if ((t->obj_qposadr[o] < 0 && t->place_body[o] < 0) || t->place_z[o] <= 0) continue;
     int qa = t->obj_qposadr[o]; real x = 0, y = 0, yaw = 0;
     for (int attempt = 0; attempt < 16; attempt++) {
       orc_philox(seed, env_id, 0, (uint32_t)(episode * 8 + 4 + (uint64_t)o) + 0x10000u * (uint32_t)attempt, r);
@@ -1105,15 +1136,16 @@ void orc_reset(orc_env *e, uint64_t seed, uint64_t env_id, uint64_t episode) {
       y = t->place_y[o][0] + (t->place_y[o][1] - t->place_y[o][0]) * u01(r[1]);
       yaw = t->place_yaw[o][0] + (t->place_yaw[o][1] - t->place_yaw[o][0]) * u01(r[2]);
       int ok = 1;
-      for (int p = 0; p < o; p++) if (t->obj_qposadr[p] >= 0 && t->place_z[p] > 0) {
+      for (int p = 0; p < o; p++) if (t->obj_qposadr[p] >= 0 && t->place_body[o] < 0 && t->place_z[p] > 0) {
         real dx = x + t->place_ref[0] - e->qpos[t->obj_qposadr[p]], dy = y + t->place_ref[1] - e->qpos[t->obj_qposadr[p] + 1];
         real rr = sqrt(t->obj_half[o][0] * t->obj_half[o][0] + t->obj_half[o][1] * t->obj_half[o][1]) + sqrt(t->obj_half[p][0] * t->obj_half[p][0] + t->obj_half[p][1] * t->obj_half[p][1]);
         if (dx * dx + dy * dy < rr * rr) ok = 0;
       }
       if (ok) break;
     }
-    e->qpos[qa] = t->place_ref[0] + x; e->qpos[qa + 1] = t->place_ref[1] + y; e->qpos[qa + 2] = t->place_z[o];
-    e->qpos[qa + 3] = cos(0.5 * yaw); e->qpos[qa + 4] = 0; e->qpos[qa + 5] = 0; e->qpos[qa + 6] = sin(0.5 * yaw);
+    real *dst = t->place_body[o] >= 0 ? e->bpose : e->qpos + qa;
+    dst[0] = t->place_ref[0] + x; dst[1] = t->place_ref[1] + y; dst[2] = t->place_z[o];
+    dst[3] = cos(0.5 * yaw); dst[4] = 0; dst[5] = 0; dst[6] = sin(0.5 * yaw);
   }
   orc_forward(e);
   for (int ri = 0; ri < t->nrobot; ri++) controller_reset(e, ri);
@@ -1171,6 +1203,8 @@ void orc_set_state(orc_env *e, const real *qpos, const real *qvel, const real *w
   }
   e->done = 0;
 }
+void orc_get_bpose(const orc_env *e, real *out) { memcpy(out, e->bpose, sizeof e->bpose); }
+void orc_set_bpose(orc_env *e, const real *in) { memcpy(e->bpose, in, sizeof e->bpose); }
 void orc_set_timestep(orc_env *e, int t) { e->timestep = t; e->done = 0; }
 
 /* named getter for tests: returns element count written (doubles) or -1 */

@@ -112,6 +112,8 @@ class BatchSim:
         self._ct = task_to_c(task)
         assert self.L.rsb_sizeof_model() == C.sizeof(self._cm), "rsb_model ABI mismatch"
         assert self.L.rsb_sizeof_task() == C.sizeof(self._ct), "rsb_task ABI mismatch"
+        ncon_max = ncon_max or int(task.get("ncon_max", 0))
+        nefc_max = nefc_max or int(task.get("nefc_max", 0))
         h = C.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         _check(self.L.rsb_create(C.byref(self._cm), C.byref(self._ct), int(num_envs), int(idx), C.c_uint64(seed),
@@ -205,7 +207,7 @@ class BatchSim:
         return dbg
 
     # -- state record helpers (layout: include/rsb.h rsb_get_state)
-    def pack_state(self, qpos, qvel, warm=None, cs=None, timestep=0, episode=0) -> np.ndarray:
+    def pack_state(self, qpos, qvel, warm=None, cs=None, timestep=0, episode=0, bpose=None) -> np.ndarray:
         """numpy rows [n, state_words] from per-env arrays (float64 accepted)."""
         qpos = np.atleast_2d(qpos)
         n = qpos.shape[0]
@@ -217,6 +219,8 @@ class BatchSim:
             st[:, nq + nv:nq + 2 * nv] = np.atleast_2d(warm)
         if cs is not None:
             st[:, nq + 2 * nv:nq + 2 * nv + 80 * self.nrobot] = np.atleast_2d(cs)
+        o = nq + 2 * nv + 80 * self.nrobot
+        st[:, o:o + 7] = [0, 0, 0, 1, 0, 0, 0] if bpose is None else np.atleast_2d(bpose)
         ints = st.view(np.int32)
         ints[:, -2] = timestep
         ints[:, -1] = episode
@@ -226,4 +230,4 @@ class BatchSim:
         nq, nv = self.nq, self.nv
         ints = st.view(np.int32)
         return dict(qpos=st[:, :nq], qvel=st[:, nq:nq + nv], warm=st[:, nq + nv:nq + 2 * nv],
-                    cs=st[:, nq + 2 * nv:nq + 2 * nv + 80 * self.nrobot], timestep=ints[:, -2], episode=ints[:, -1])
+                    cs=st[:, nq + 2 * nv:nq + 2 * nv + 80 * self.nrobot], bpose=st[:, -9:-2], timestep=ints[:, -2], episode=ints[:, -1])

@@ -117,6 +117,8 @@ int rsb_create(const rsb_model *model, const rsb_task *task, int n_envs, int dev
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
   size_t per_env = (size_t)hm.dm.smem_words * 4;
   int epb = (int)((size_t)prop.sharedMemPerBlockOptin / per_env); if (epb > RSB_MAX_EPB) epb = RSB_MAX_EPB;
+  /* two CTAs per SM (each keeps its warps in lockstep) balance instruction-fetch sharing against barrier stalls and tail waves */
+  { int half = (int)(((size_t)prop.sharedMemPerMultiprocessor / 2 - 1024) / per_env); if (half >= 4 && half < epb) epb = half; }
   if (const char *e = getenv("RSB_EPB")) { int v = atoi(e); if (v > 0 && v < epb) epb = v; }
   if (epb < 1) { g_err = "per-env working set does not fit shared memory"; delete b; return 5; }
   b->epb = epb; b->smem_bytes = per_env * (size_t)epb;

@@ -206,9 +206,11 @@ RSB_DN void st_kinematics(int so, Grp g) { real *s = RSB_SMEM + so;
         pos[0] = qpos[a]; pos[1] = qpos[a + 1]; pos[2] = qpos[a + 2]; quat[0] = qpos[a + 3]; quat[1] = qpos[a + 4]; quat[2] = qpos[a + 5]; quat[3] = qpos[a + 6];
         xanchor[3 * ja] = pos[0]; xanchor[3 * ja + 1] = pos[1]; xanchor[3 * ja + 2] = pos[2]; xaxis[3 * ja] = 0; xaxis[3 * ja + 1] = 0; xaxis[3 * ja + 2] = 1;
       } else {
-        real t3[3]; matvec3(t3, xmat + 9 * p, MDL.body_pos + 3 * b);
+        const real *bp = (b == MDL.override_body) ? s + MDL.o_bpose : MDL.body_pos + 3 * b;
+        const real *bq = (b == MDL.override_body) ? s + MDL.o_bpose + 3 : MDL.body_quat + 4 * b;
+        real t3[3]; matvec3(t3, xmat + 9 * p, bp);
         pos[0] = xpos[3 * p] + t3[0]; pos[1] = xpos[3 * p + 1] + t3[1]; pos[2] = xpos[3 * p + 2] + t3[2];
-        quatmul(quat, xquat + 4 * p, MDL.body_quat + 4 * b);
+        quatmul(quat, xquat + 4 * p, bq);
         for (int k = 0; k < jn; k++) {
           int j = ja + k; real anchor[3], axis[3];
           quatrot(t3, quat, MDL.jnt_pos + 3 * j); anchor[0] = pos[0] + t3[0]; anchor[1] = pos[1] + t3[1]; anchor[2] = pos[2] + t3[2];
@@ -1201,6 +1203,19 @@ RSB_DN real task_reward(int so) { const real *s = RSB_SMEM + so;
     }
     return r * MDL.reward_scale;
   }
+  if (MDL.task_id == RSB_TASK_TWOARMLIFT) {
+    const real *pot = xpos + 3 * MDL.obj_body[0]; const real *Rp = s + MDL.o_xmat + 9 * MDL.obj_body[0];
+    real gate = Rp[8] >= 0.8660254037844387f ? 1.0f : 0.0f, elev = pot[2] - MDL.obj_half[0][2] - MDL.table_height;
+    if (elev > 0.10f) r = 3.0f * gate;
+    else if (MDL.reward_shaping) {
+      r += 10.0f * gate * clampf(elev - 0.05f, 0.0f, 0.15f);
+      for (int ri = 0; ri < 2; ri++) {
+        const real *ee = sxpos + 3 * MDL.robot[ri].eef_site, *hs = sxpos + 3 * MDL.obj_site[ri]; real d[3] = {ee[0] - hs[0], ee[1] - hs[1], ee[2] - hs[2]};
+        if (check_grasp(so, ri, MDL.obj_geom[ri])) r += 0.25f; else r += 0.5f * (1 - tanhf(10.0f * sqrtf(dot3(d, d))));
+      }
+    }
+    return r * MDL.reward_scale / 3.0f;
+  }
   return 0;
 }
 
@@ -1245,6 +1260,18 @@ RSB_D real obs_element(int so, int i) { const real *s = RSB_SMEM + so;
     if (i < 12) return hs[i - 9] - eef[i - 9];
     return qpos[MDL.obj_qadr[i - 12]];
   }
+  if (MDL.task_id == RSB_TASK_TWOARMLIFT) {
+    const real *pot = xpos + 3 * MDL.obj_body[0], *e0 = sxpos + 3 * MDL.robot[0].eef_site, *e1 = sxpos + 3 * MDL.robot[1].eef_site;
+    const real *h0 = sxpos + 3 * MDL.obj_site[0], *h1 = sxpos + 3 * MDL.obj_site[1];
+    if (i < 3) return pot[i];
+    if (i < 7) { int k = i - 3; return xquat[4 * MDL.obj_body[0] + (k == 3 ? 0 : k + 1)]; }
+    if (i < 10) return e0[i - 7];
+    if (i < 13) return e1[i - 10];
+    if (i < 16) return h0[i - 13];
+    if (i < 19) return h1[i - 16];
+    if (i < 22) return h0[i - 19] - e0[i - 19];
+    return h1[i - 22] - e1[i - 22];
+  }
   return 0;
 }
 
@@ -1254,12 +1281,14 @@ RSB_D void load_state(int so, const real *st, Grp g) { real *s = RSB_SMEM + so;
   for (int i = g.lane; i < MDL.nv; i += RSB_LANES) { s[MDL.o_qvel + i] = st[MDL.st_qvel + i]; s[MDL.o_warm + i] = st[MDL.st_warm + i]; }
   for (int i = g.lane; i < MDL.nrobot * RSB_CS_WORDS; i += RSB_LANES) s[MDL.o_cs + i] = st[MDL.st_cs + i];
   for (int i = g.lane; i < MDL.nu; i += RSB_LANES) s[MDL.o_ctrl + i] = 0;
+  if (g.lane < 7) s[MDL.o_bpose + g.lane] = st[MDL.st_bpose + g.lane];
   gsync(g);
 }
 RSB_D void store_state(int so, real *st, Grp g) { const real *s = RSB_SMEM + so;
   for (int i = g.lane; i < MDL.nq; i += RSB_LANES) st[MDL.st_qpos + i] = s[MDL.o_qpos + i];
   for (int i = g.lane; i < MDL.nv; i += RSB_LANES) { st[MDL.st_qvel + i] = s[MDL.o_qvel + i]; st[MDL.st_warm + i] = s[MDL.o_warm + i]; }
   for (int i = g.lane; i < MDL.nrobot * RSB_CS_WORDS; i += RSB_LANES) st[MDL.st_cs + i] = s[MDL.o_cs + i];
+  if (g.lane < 7) st[MDL.st_bpose + g.lane] = s[MDL.o_bpose + g.lane];
 }
 
 /* One control step of one env (robosuite MujocoEnv.step): 25 x (forward, controller, mj_step), then reward + observation.
@@ -1288,6 +1317,7 @@ RSB_D void env_reset(int so, Grp g, real *st, uint64_t seed, uint64_t env_id, re
   real *qpos = s + MDL.o_qpos;
   for (int i = g.lane; i < MDL.nq; i += RSB_LANES) qpos[i] = MDL.qpos0[i];
   for (int i = g.lane; i < MDL.nv; i += RSB_LANES) { s[MDL.o_qvel + i] = 0; s[MDL.o_warm + i] = 0; }
+  if (g.lane < 7) { int ob = MDL.override_body; s[MDL.o_bpose + g.lane] = ob < 0 ? (g.lane == 3 ? 1.0f : 0.0f) : (g.lane < 3 ? MDL.body_pos[3 * ob + g.lane] : MDL.body_quat[4 * ob + g.lane - 3]); }
   gsync(g);
   if (g.lane < MDL.nrobot) {
     const DevRobot &rb = MDL.robot[g.lane]; real z[8]; uint32_t r[4];
@@ -1300,7 +1330,7 @@ RSB_D void env_reset(int so, Grp g, real *st, uint64_t seed, uint64_t env_id, re
   }
   if (g.lane == RSB_LANES - 1) {                      /* object placement: uniform xy + yaw, rejection on overlap (serial over objects) */
     for (int o = 0; o < RSB_MAX_OBJ; o++) {
-      if (MDL.obj_qadr[o] < 0 || MDL.place_z[o] <= 0) continue;
+      if ((MDL.obj_qadr[o] < 0 && MDL.place_body[o] < 0) || MDL.place_z[o] <= 0) continue;
       int qa = MDL.obj_qadr[o]; real x = 0, y = 0, yaw = 0; uint32_t r[4];
       for (int attempt = 0; attempt < 16; attempt++) {
         rsb_philox(seed, env_id, 0, (uint32_t)(episode * 8 + 4 + o) + 0x10000u * (uint32_t)attempt, r);
@@ -1309,7 +1339,7 @@ RSB_D void env_reset(int so, Grp g, real *st, uint64_t seed, uint64_t env_id, re
         y = (real)(MDL.place_y[o][0] + (MDL.place_y[o][1] - MDL.place_y[o][0]) * u1);
         yaw = (real)(MDL.place_yaw[o][0] + (MDL.place_yaw[o][1] - MDL.place_yaw[o][0]) * u2);
         bool ok = true;
-        for (int p = 0; p < o; p++) if (MDL.obj_qadr[p] >= 0 && MDL.place_z[p] > 0) {
+        for (int p = 0; p < o; p++) if (MDL.obj_qadr[p] >= 0 && MDL.place_body[o] < 0 && MDL.place_z[p] > 0) {
           real dx = x + MDL.place_ref[0] - qpos[MDL.obj_qadr[p]], dy = y + MDL.place_ref[1] - qpos[MDL.obj_qadr[p] + 1];
           real rr = sqrtf(MDL.obj_half[o][0] * MDL.obj_half[o][0] + MDL.obj_half[o][1] * MDL.obj_half[o][1]) + sqrtf(MDL.obj_half[p][0] * MDL.obj_half[p][0] + MDL.obj_half[p][1] * MDL.obj_half[p][1]);
           if (dx * dx + dy * dy < rr * rr) ok = false;
@@ -1317,8 +1347,9 @@ RSB_D void env_reset(int so, Grp g, real *st, uint64_t seed, uint64_t env_id, re
         if (ok) break;
       }
       real sn, c; rsb_sincos(0.5f * yaw, &sn, &c);
-      qpos[qa] = MDL.place_ref[0] + x; qpos[qa + 1] = MDL.place_ref[1] + y; qpos[qa + 2] = MDL.place_z[o];
-      qpos[qa + 3] = c; qpos[qa + 4] = 0; qpos[qa + 5] = 0; qpos[qa + 6] = sn;
+      real *dst = MDL.place_body[o] >= 0 ? s + MDL.o_bpose : qpos + qa;
+      dst[0] = MDL.place_ref[0] + x; dst[1] = MDL.place_ref[1] + y; dst[2] = MDL.place_z[o];
+      dst[3] = c; dst[4] = 0; dst[5] = 0; dst[6] = sn;
     }
   }
   gsync(g);

@@ -67,11 +67,12 @@ typedef struct DevModel {
   int obj_body[RSB_MAX_OBJ], obj_geom[RSB_MAX_OBJ], obj_site[RSB_MAX_OBJ], obj_qadr[RSB_MAX_OBJ], obj_dadr[RSB_MAX_OBJ];
   float obj_half[RSB_MAX_OBJ][3], place_x[RSB_MAX_OBJ][2], place_y[RSB_MAX_OBJ][2], place_yaw[RSB_MAX_OBJ][2];
   float place_z[RSB_MAX_OBJ], place_ref[3];
+  int place_body[RSB_MAX_OBJ], override_body;       /* fixed body whose pose is a per-env quantity (Door), -1 if none */
   DevRobot robot[RSB_MAX_ROBOTS];
-  /* per-env persistent state record in HBM (words): qpos, qvel, warm, cs[nrobot*RSB_CS_WORDS], timestep, episode */
-  int st_qpos, st_qvel, st_warm, st_cs, st_time, st_episode, st_words;
+  /* per-env persistent state record in HBM (words): qpos, qvel, warm, cs[nrobot*RSB_CS_WORDS], bpose[7], timestep, episode */
+  int st_qpos, st_qvel, st_warm, st_cs, st_bpose, st_time, st_episode, st_words;
   /* per-env shared-memory layout (word offsets) */
-  int o_qpos, o_qvel, o_warm, o_ctrl, o_cs, o_act;
+  int o_qpos, o_qvel, o_warm, o_ctrl, o_cs, o_act, o_bpose;
   int o_xpos, o_xquat, o_xmat, o_xanchor, o_xaxis, o_jq;
   int o_cinert, o_crb, o_cdof, o_fi, o_M, o_L;
   int o_gxpos, o_gxmat, o_sxpos, o_sxmat;
@@ -217,12 +218,13 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
   /* task */
   d.task_id = t->task_id; d.nrobot = t->nrobot; d.horizon = t->horizon; d.substeps = t->substeps; d.ignore_done = t->ignore_done;
   d.reward_shaping = t->reward_shaping; d.obs_dim = t->obs_dim; d.act_dim = t->act_dim;
+  d.override_body = -1;
   d.reward_scale = (float)t->reward_scale; d.init_noise = (float)t->init_noise; d.table_height = (float)t->table_height;
   for (int o = 0; o < RSB_MAX_OBJ; o++) {
     d.obj_body[o] = t->obj_body[o]; d.obj_geom[o] = t->obj_geom[o]; d.obj_site[o] = t->obj_site[o]; d.obj_qadr[o] = t->obj_qposadr[o]; d.obj_dadr[o] = t->obj_dofadr[o];
     for (int k = 0; k < 3; k++) d.obj_half[o][k] = (float)t->obj_half[o][k];
     for (int k = 0; k < 2; k++) { d.place_x[o][k] = (float)t->place_x[o][k]; d.place_y[o][k] = (float)t->place_y[o][k]; d.place_yaw[o][k] = (float)t->place_yaw[o][k]; }
-    d.place_z[o] = (float)t->place_z[o];
+    d.place_z[o] = (float)t->place_z[o]; d.place_body[o] = t->place_body[o]; if (t->place_body[o] >= 0) d.override_body = t->place_body[o];
   }
   for (int k = 0; k < 3; k++) d.place_ref[k] = (float)t->place_ref[k];
   int aoff = 0;
@@ -246,12 +248,12 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
   }
   /* persistent state record */
   int w = 0;
-  d.st_qpos = w; w += d.nq; d.st_qvel = w; w += d.nv; d.st_warm = w; w += d.nv; d.st_cs = w; w += d.nrobot * RSB_CS_WORDS;
+  d.st_qpos = w; w += d.nq; d.st_qvel = w; w += d.nv; d.st_warm = w; w += d.nv; d.st_cs = w; w += d.nrobot * RSB_CS_WORDS; d.st_bpose = w; w += 7;
   d.st_time = w++; d.st_episode = w++; d.st_words = w;
   /* shared-memory layout */
   int o = 0; int nb = d.nbody, nv = d.nv, nj = d.njnt, ne = nefc_max, nc = ncon_max;
 #define L(name, n) d.name = o; o += (n)
-  L(o_qpos, d.nq); L(o_qvel, nv); L(o_warm, nv); L(o_ctrl, d.nu > 0 ? d.nu : 1); L(o_cs, d.nrobot * RSB_CS_WORDS + 1); L(o_act, d.act_dim + 1);
+  L(o_qpos, d.nq); L(o_qvel, nv); L(o_warm, nv); L(o_ctrl, d.nu > 0 ? d.nu : 1); L(o_cs, d.nrobot * RSB_CS_WORDS + 1); L(o_act, d.act_dim + 1); L(o_bpose, 7);
   L(o_xpos, 3 * nb); L(o_xquat, 4 * nb); L(o_xmat, 9 * nb); L(o_xanchor, 3 * nj + 1); L(o_xaxis, 3 * nj + 1); L(o_jq, 4 * nj + 1);
   L(o_cinert, 10 * nb); L(o_crb, 10 * nb); L(o_cdof, 6 * nv); L(o_fi, 6 * nv); L(o_M, nv * d.ldm); L(o_L, nv * d.ldm);
   L(o_gxpos, 3 * d.ngeom + 1); L(o_gxmat, 9 * d.ngeom + 1); L(o_sxpos, 3 * d.nsite + 1); L(o_sxmat, 9 * d.nsite + 1);

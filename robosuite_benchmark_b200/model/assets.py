@@ -184,5 +184,47 @@ def box_object(name, half, pos, density=1000, friction=(1, 0.005, 0.0001), solre
             f'solref="{_f(solref)}" solimp="{_f(solimp)}" {WORLD_COL}/></body>')
 
 
+def door_object(pos=(0.12, -0.2, TABLE_HEIGHT), yaw=-PI / 2, hinge_damping=0.1, hinge_frictionloss=0.0) -> str:
+    """Door with a latch handle (robosuite DoorObject with lock=True, authored from primitives).  The root body is
+    FIXED to the world; its pose is re-sampled at every reset (rsb_task.place_body).  Local frame: x = door width, y = door normal
+    (the handle sits on the -y face), z = up; hinge on the +x post, door opens towards +y (away from the robot after the -90 deg yaw)."""
+    q = f"{np.cos(yaw / 2):.10g} 0 0 {np.sin(yaw / 2):.10g}"
+    col = WORLD_COL + ' friction="1 0.005 0.0001"'
+    return f'''
+<body name="door_root" pos="{_f(pos)}" quat="{q}">
+  <geom name="door_post_l" type="box" pos="-0.165 0 0.16" size="0.015 0.015 0.16" {col}/>
+  <geom name="door_post_r" type="box" pos="0.165 0 0.16" size="0.015 0.015 0.16" {col}/>
+  <body name="door" pos="0.15 0 0.16">
+    <inertial pos="-0.15 0 0" mass="1.0" diaginertia="0.0075 0.0141 0.0066"/>
+    <joint name="door_hinge" type="hinge" axis="0 0 1" range="0 0.4" damping="{hinge_damping}" frictionloss="{hinge_frictionloss}"/>
+    <geom name="door_panel" type="box" pos="-0.15 0 0" size="0.14 0.01 0.15" {col}/>
+    <body name="latch" pos="-0.25 0 0">
+      <inertial pos="0.03 -0.04 0" mass="0.1" diaginertia="0.0001 0.0001 0.0001"/>
+      <joint name="latch_joint" type="hinge" axis="0 1 0" range="-1.57 0" damping="0.1" frictionloss="0.1" stiffness="0.5" springref="0"/>
+      <geom name="latch_stem" type="box" pos="0 -0.03 0" size="0.008 0.02 0.008" {col}/>
+      <geom name="latch_handle" type="box" pos="0.04 -0.05 0" size="0.05 0.01 0.01" {col}/>
+      <site name="door_handle" pos="0.04 -0.05 0"/>
+    </body>
+  </body>
+</body>'''
+
+
+def pot_with_handles(name="pot", pos=(0, 0, TABLE_HEIGHT + 0.07), density=1000) -> str:
+    """robosuite PotWithHandlesObject from boxes: hollow body (base + 4 walls, half size 0.07) and two handle grip bars 9 cm out along
+    -y / +y (the side bars of each handle loop are visual only)."""
+    col = WORLD_COL + f' density="{density}" friction="1 0.005 0.0001"'
+    h, t = 0.07, 0.005
+    g = [f'<geom name="{name}_base" type="box" pos="0 0 {-h + 0.01}" size="{h} {h} 0.01" {col}/>',
+         f'<geom name="{name}_wall_xp" type="box" pos="{h - t} 0 0.01" size="{t} {h} {h - 0.01}" {col}/>',
+         f'<geom name="{name}_wall_xn" type="box" pos="{-h + t} 0 0.01" size="{t} {h} {h - 0.01}" {col}/>',
+         f'<geom name="{name}_wall_yp" type="box" pos="0 {h - t} 0.01" size="{h - 2 * t} {t} {h - 0.01}" {col}/>',
+         f'<geom name="{name}_wall_yn" type="box" pos="0 {-h + t} 0.01" size="{h - 2 * t} {t} {h - 0.01}" {col}/>']
+    for k, sg in enumerate((-1, 1)):
+        y = sg * (h + 0.09)
+        g.append(f'<geom name="{name}_handle{k}" type="box" pos="0 {y} 0.05" size="0.045 0.01 0.01" {col}/>')
+        g.append(f'<site name="{name}_handle{k}" pos="0 {y} 0.05"/>')
+    return f'<body name="{name}" pos="{_f(pos)}"><freejoint name="{name}_joint"/>' + "".join(g) + "</body>"
+
+
 def scene(world: str, actuators: str, extra: str = "") -> str:
     return f'<mujoco model="rsb">{BASE_OPTION}<worldbody>{world}</worldbody><actuator>{actuators}</actuator>{extra}</mujoco>'

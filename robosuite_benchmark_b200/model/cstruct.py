@@ -84,7 +84,7 @@ class RsbTask(C.Structure):
         ("obj_body", I4), ("obj_geom", I4), ("obj_site", I4), ("obj_qposadr", I4), ("obj_dofadr", I4),
         ("obj_half", (C.c_double * 3) * 4),
         ("place_x", D2 * 4), ("place_y", D2 * 4), ("place_yaw", D2 * 4), ("place_z", C.c_double * 4),
-        ("place_ref", C.c_double * 3),
+        ("place_ref", C.c_double * 3), ("place_body", I4),
     ]
 
 
@@ -129,7 +129,7 @@ def task_to_c(task: dict) -> RsbTask:
     for k in ("reward_scale", "init_noise", "table_height"):
         setattr(t, k, float(task[k]))
     for k in ("obj_body", "obj_geom", "obj_site", "obj_qposadr", "obj_dofadr", "obj_half", "place_x", "place_y",
-              "place_yaw", "place_z", "place_ref"):
+              "place_yaw", "place_z", "place_ref", "place_body"):
         _fill(getattr(t, k), task[k])
     for ri, rd in enumerate(task["robot"]):
         r = t.robot[ri]

@@ -18,6 +18,8 @@ TASK_IDS = {"Lift": 0, "Door": 1, "Stack": 2, "TwoArmLift": 3}
 CTRL_IDS = {"OSC_POSE": 0, "OSC_POSITION": 1, "JOINT_VELOCITY": 2, "JOINT_TORQUE": 3}
 
 OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89}
+#: default bounds of the per-env contact list / constraint-row list (shared-memory sizing; rsb_create ncon_max / nefc_max)
+LIMITS = {"Lift": (16, 64), "Door": (16, 64), "Stack": (24, 96), "TwoArmLift": (32, 96)}
 
 
 def _robot_desc(m: Model, pf: str, robot: str, cc: dict) -> dict:
@@ -85,7 +87,7 @@ def build_task(env_name: str, robots: Sequence[str], controller_config: dict, ho
     for r in robots:
         if r not in A.ROBOTS:
             raise NotImplementedError(f"robot {r!r} not supported (have {sorted(A.ROBOTS)})")
-    builder = {"Lift": _lift}[env_name] if env_name == "Lift" else _BUILDERS[env_name]
+    builder = _BUILDERS[env_name]
     xml, objs = builder(robots, env_configuration)
     m = compile_mjcf(xml)
     substeps = int((1.0 / control_freq) / m.timestep)
@@ -96,7 +98,7 @@ def build_task(env_name: str, robots: Sequence[str], controller_config: dict, ho
                 ignore_done=int(bool(ignore_done)), reward_shaping=int(bool(reward_shaping)),
                 reward_scale=float(reward_scale), init_noise=0.02, table_height=A.TABLE_HEIGHT,
                 obs_dim=OBS_DIMS[env_name] if n_rob == (2 if env_name == "TwoArmLift" else 1) else None,
-                act_dim=act_dim, env_name=env_name, robots=list(robots), xml=xml)
+                act_dim=act_dim, env_name=env_name, robots=list(robots), xml=xml, ncon_max=LIMITS[env_name][0], nefc_max=LIMITS[env_name][1])
     task.update(objs(m))
     return m, task
 
@@ -112,7 +114,7 @@ def empty_task():
 def _empty_objs():
     return dict(obj_body=[-1] * 4, obj_geom=[-1] * 4, obj_site=[-1] * 4, obj_qposadr=[-1] * 4, obj_dofadr=[-1] * 4,
                 obj_half=np.zeros((4, 3)), place_x=np.zeros((4, 2)), place_y=np.zeros((4, 2)),
-                place_yaw=np.zeros((4, 2)), place_z=np.zeros(4), place_ref=np.zeros(3))
+                place_yaw=np.zeros((4, 2)), place_z=np.zeros(4), place_ref=np.zeros(3), place_body=[-1] * 4)
 
 
 def _single_arm_world(robot: str):
@@ -145,4 +147,83 @@ def _lift(robots, env_configuration):
     return xml, objs
 
 
-_BUILDERS: Dict[str, callable] = {"Lift": _lift}
+def _stack(robots, env_configuration):
+    """Stack: cubeA (half 0.02) to be put on cubeB (half 0.025); both placed uniformly in +-0.08 with overlap rejection."""
+    assert len(robots) == 1, "Stack takes one robot"
+    body, act = _single_arm_world(robots[0])
+    ha, hb = 0.02, 0.025
+    world = (A.table_arena() + body + A.box_object("cubeA", [ha] * 3, [-0.04, -0.04, A.TABLE_HEIGHT + ha])
+             + A.box_object("cubeB", [hb] * 3, [0.04, 0.04, A.TABLE_HEIGHT + hb]))
+    xml = A.scene(world, act)
+
+    def objs(m: Model):
+        o = _empty_objs()
+        for k, (nm, hh) in enumerate((("cubeA", ha), ("cubeB", hb))):
+            j = m.id("joint", nm + "_joint")
+            o["obj_body"][k], o["obj_geom"][k] = m.id("body", nm), m.id("geom", nm + "_g0")
+            o["obj_qposadr"][k], o["obj_dofadr"][k] = int(m.jnt_qposadr[j]), int(m.jnt_dofadr[j])
+            o["obj_half"][k] = hh
+            o["place_x"][k], o["place_y"][k], o["place_yaw"][k] = [-0.08, 0.08], [-0.08, 0.08], [0.0, 2 * np.pi]
+            o["place_z"][k] = A.TABLE_HEIGHT + hh + 0.01
+        o["place_ref"] = np.array([0.0, 0.0, A.TABLE_HEIGHT])
+        return o
+
+    return xml, objs
+
+
+def _door(robots, env_configuration):
+    """Door: hinged door with a latch handle standing on the table; the door root is re-placed at every reset."""
+    assert len(robots) == 1, "Door takes one robot"
+    body, act = _single_arm_world(robots[0])
+    world = A.table_arena() + body + A.door_object()
+    xml = A.scene(world, act)
+
+    def objs(m: Model):
+        o = _empty_objs()
+        jh, jl = m.id("joint", "door_hinge"), m.id("joint", "latch_joint")
+        o["obj_body"][0], o["obj_body"][1], o["obj_body"][2] = m.id("body", "door"), m.id("body", "latch"), m.id("body", "door_root")
+        o["obj_geom"][0] = m.id("geom", "latch_handle")
+        o["obj_site"][0] = m.id("site", "door_handle")
+        o["obj_qposadr"][0], o["obj_qposadr"][1] = int(m.jnt_qposadr[jh]), int(m.jnt_qposadr[jl])
+        o["obj_dofadr"][0], o["obj_dofadr"][1] = int(m.jnt_dofadr[jh]), int(m.jnt_dofadr[jl])
+        # placement slot 2 = the fixed root body: x in [0.07, 0.09], y in [-0.01, 0.01], yaw in [-pi/2 - 0.25, -pi/2] about place_ref
+        o["place_body"][2] = m.id("body", "door_root")
+        o["place_x"][2], o["place_y"][2], o["place_yaw"][2] = [0.07, 0.09], [-0.01, 0.01], [-np.pi / 2 - 0.25, -np.pi / 2]
+        o["place_z"][2] = A.TABLE_HEIGHT
+        o["place_ref"] = np.array([0.04, -0.2, A.TABLE_HEIGHT])
+        return o
+
+    return xml, objs
+
+
+def _two_arm_lift(robots, env_configuration):
+    """TwoArmLift, `single-arm-opposed`: two arms facing each other across the table, a pot with two handles between them."""
+    assert len(robots) == 2, "TwoArmLift takes two robots"
+    if env_configuration not in ("single-arm-opposed", "default", None):
+        raise NotImplementedError(f"env_configuration {env_configuration!r} is not implemented (single-arm-opposed only)")
+    bodies, acts = "", ""
+    for i, (r, yaw, y) in enumerate(zip(robots, (np.pi / 2, -np.pi / 2), (-0.69, 0.69))):
+        R = A.ROBOTS[r]
+        quat = (np.cos(yaw / 2), 0, 0, np.sin(yaw / 2))
+        bodies += R["body"](f"robot{i}_", (0.0, y, A.ROBOT_BASE_Z), quat)
+        acts += R["act"](f"robot{i}_")
+    world = A.table_arena() + bodies + A.pot_with_handles()
+    xml = A.scene(world, acts)
+
+    def objs(m: Model):
+        o = _empty_objs()
+        j = m.id("joint", "pot_joint")
+        o["obj_body"][0] = m.id("body", "pot")
+        o["obj_geom"][0], o["obj_geom"][1] = m.id("geom", "pot_handle0"), m.id("geom", "pot_handle1")
+        o["obj_site"][0], o["obj_site"][1] = m.id("site", "pot_handle0"), m.id("site", "pot_handle1")
+        o["obj_qposadr"][0], o["obj_dofadr"][0] = int(m.jnt_qposadr[j]), int(m.jnt_dofadr[j])
+        o["obj_half"][0] = [0.07, 0.07, 0.07]
+        o["place_x"][0], o["place_y"][0], o["place_yaw"][0] = [-0.03, 0.03], [-0.03, 0.03], [-np.pi / 3, np.pi / 3]
+        o["place_z"][0] = A.TABLE_HEIGHT + 0.07 + 0.01
+        o["place_ref"] = np.array([0.0, 0.0, A.TABLE_HEIGHT])
+        return o
+
+    return xml, objs
+
+
+_BUILDERS: Dict[str, callable] = {"Lift": _lift, "Stack": _stack, "Door": _door, "TwoArmLift": _two_arm_lift}

@@ -106,13 +106,15 @@ class EmuEnv:
         nq, nv = self.nq, self.nv
         return st[:nq].copy(), st[nq:nq + nv].copy(), st[nq + nv:nq + 2 * nv].copy(), st[nq + 2 * nv:nq + 2 * nv + 80 * self.nrobot].copy()
 
-    def set_state(self, qpos, qvel, warm=None, cs=None, timestep=0, episode=0):
+    def set_state(self, qpos, qvel, warm=None, cs=None, timestep=0, episode=0, bpose=None):
         nq, nv = self.nq, self.nv
         st = self.raw_state()
         st[:nq], st[nq:nq + nv] = qpos, qvel
         st[nq + nv:nq + 2 * nv] = 0 if warm is None else warm
         if cs is not None:
             st[nq + 2 * nv:nq + 2 * nv + 80 * self.nrobot] = cs
+        if bpose is not None:
+            st[-9:-2] = bpose
         ints = st.view(np.int32)
         ints[-2], ints[-1] = timestep, episode
         self.set_raw_state(st)

@@ -1,0 +1,56 @@
+"""CPU parity of the device code (compiled for the host by tests/emu, lanes = fibers) against the fp64 oracle, for every BASELINE
+config family.  This is the no-GPU guard for the logic of csrc/rsb_dev.h; the `-m gpu` tests run the same checks on the real kernels."""
+import numpy as np
+import pytest
+
+from oracle.oracle import OracleEnv
+from robosuite_benchmark_b200.controllers import load_controller_config
+from robosuite_benchmark_b200.model.tasks import build_task
+from tests.emu.emu import EmuEnv
+
+CONFIGS = [("Lift", ["Panda"], "OSC_POSE", 42, 7), ("Lift", ["Panda"], "JOINT_VELOCITY", 42, 8), ("Lift", ["Sawyer"], "OSC_POSITION", 42, 4),
+           ("Door", ["Panda"], "JOINT_VELOCITY", 46, 8), ("Stack", ["Sawyer"], "OSC_POSE", 55, 7), ("TwoArmLift", ["Panda", "Panda"], "OSC_POSE", 89, 14)]
+
+
+@pytest.mark.parametrize("env_name,robots,ctrl,obs_dim,act_dim", CONFIGS)
+def test_control_step_matches_oracle(env_name, robots, ctrl, obs_dim, act_dim):
+    m, t = build_task(env_name, robots, load_controller_config(default_controller=ctrl), ignore_done=True)
+    assert (t["obs_dim"], t["act_dim"]) == (obs_dim, act_dim)          # dims pinned by the committed networks
+    nc, ne = t["ncon_max"], t["nefc_max"]
+    orc, emu = OracleEnv(m, t, ncon_max=nc, nefc_max=ne), EmuEnv(m, t, nc, ne)
+    o1, o2 = orc.reset(seed=17, env_id=3), emu.reset(seed=17, env_id=3)
+    assert np.abs(o1 - o2).max() < 2e-6
+    for k in range(2):
+        a = orc.random_action(17, 3, k)
+        assert np.abs(a - emu.random_action(17, 3, k)).max() < 1e-6
+        qp, qv, w, cs = orc.get_state()
+        emu.set_state(qp, qv, w, cs, timestep=k, bpose=orc.get_bpose())
+        o1, r1, _ = orc.step(a)
+        o2, r2, _ = emu.step(a)
+        qp, qv, _, _ = orc.get_state()
+        qp2, qv2, _, _ = emu.get_state()
+        assert np.abs(qp - qp2).max() <= 1e-4 and np.abs(qv - qv2).max() <= 1e-4      # north_star tolerance for one control step (fp32)
+        assert np.abs(o1 - o2).max() <= 1e-4 and abs(r1 - r2) <= 1e-5
+
+
+def test_lane_order_independence():
+    """A missing gsync() would make the result depend on the order in which the emulator runs the lanes."""
+    m, t = build_task("Lift", "Panda", load_controller_config(default_controller="OSC_POSE"), ignore_done=True)
+    outs = []
+    for order in (0, 1, 2):
+        emu = EmuEnv(m, t, 16, 64)
+        emu.set_order(order)
+        emu.reset(seed=5, env_id=1)
+        outs.append(emu.step(emu.random_action(5, 1, 0))[0])
+    emu.set_order(0)
+    assert (outs[0] == outs[1]).all() and (outs[0] == outs[2]).all()
+
+
+def test_done_protocol_and_terminated_episode():
+    m, t = build_task("Lift", "Panda", load_controller_config(default_controller="OSC_POSE"), horizon=2, ignore_done=False)
+    emu = EmuEnv(m, t, 16, 64)
+    emu.reset(seed=1, env_id=0)
+    assert emu.step(np.zeros(7))[2] is False
+    assert emu.step(np.zeros(7))[2] is True
+    with pytest.raises(ValueError):
+        emu.step(np.zeros(7))

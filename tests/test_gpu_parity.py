@@ -140,6 +140,59 @@ def test_episode_reward_mean_within_1pct(lift_panda_osc, torch_cuda):
     s.close()
 
 
+FAMILIES = [("Door", ["Panda"], "JOINT_VELOCITY"), ("Stack", ["Sawyer"], "OSC_POSE"), ("TwoArmLift", ["Panda", "Panda"], "OSC_POSE"),
+            ("Lift", ["Panda"], "JOINT_VELOCITY"), ("Lift", ["Sawyer"], "OSC_POSITION")]
+
+
+@pytest.mark.parametrize("env_name,robots,ctrl", FAMILIES)
+def test_other_config_families_one_control_step(env_name, robots, ctrl, torch_cuda):
+    """BASELINE.json configs[2..4] (+ the other controllers): reset, contact-pair lists and one control step from identical state."""
+    from oracle.oracle import OracleEnv
+    from robosuite_benchmark_b200.backend import BatchSim
+    from robosuite_benchmark_b200.controllers import load_controller_config
+    from robosuite_benchmark_b200.model.tasks import build_task
+    from tests.emu.emu import split_debug
+    torch = torch_cuda
+    m, t = build_task(env_name, robots, load_controller_config(default_controller=ctrl), ignore_done=True)
+    nc, ne, n = t["ncon_max"], t["nefc_max"], 6
+    sim = BatchSim(m, t, n, device="cuda:0", seed=83)
+    obs0 = sim.reset().cpu().numpy()
+    orcs, rows, acts = [], [], []
+    for i in range(n):
+        orc = OracleEnv(m, t, ncon_max=nc, nefc_max=ne)
+        o = orc.reset(seed=83, env_id=i, episode=0)
+        assert np.abs(o - obs0[i]).max() < 2e-6
+        for k in range(i):                                         # env i is i control steps into its episode
+            orc.step(orc.random_action(83, i, k))
+        qpos, qvel, warm, cs = orc.get_state()
+        rows.append(sim.pack_state(qpos, qvel, warm, cs, timestep=i, episode=1, bpose=orc.get_bpose())[0])
+        acts.append(orc.random_action(83, i, i)); orcs.append(orc)
+    st0 = torch.as_tensor(np.stack(rows))
+    a = torch.as_tensor(np.stack(acts), dtype=torch.float32, device=sim.device)
+    sim.set_state(st0)
+    dbg = sim.debug_substep(a, True).cpu().numpy()
+    for i, orc in enumerate(orcs):
+        snap = (orc.get_state(), orc.get_bpose())
+        orc.substep(acts[i], True)
+        d = split_debug(dbg[i], m.nv, nc, ne)
+        assert orc.get("contact_geoms").reshape(-1, 2).astype(int).tolist() == d["contact_geoms"].tolist()
+        tau = orc.get("torques")[:7 * len(robots)]
+        assert np.abs(tau - d["torques"][:7 * len(robots)]).max() <= 1e-5 * max(1.0, np.abs(tau).max())
+        (qpos, qvel, warm, cs), bp = snap
+        orc.set_state(qpos, qvel, warm, cs); orc.set_bpose(bp)
+    sim.set_state(st0)
+    obs, rew, _ = sim.step(a)
+    st = sim.unpack_state(sim.get_state().cpu().numpy())
+    obs, rew = obs.cpu().numpy(), rew.cpu().numpy()
+    for i, orc in enumerate(orcs):
+        orc.set_timestep(i)
+        o, r, _ = orc.step(acts[i])
+        qpos, qvel, _, _ = orc.get_state()
+        assert np.abs(qpos - st["qpos"][i]).max() <= 1e-4 and np.abs(qvel - st["qvel"][i]).max() <= 1e-4, (i, np.abs(qvel - st["qvel"][i]).max())
+        assert np.abs(o - obs[i]).max() <= 1e-4 and abs(r - rew[i]) <= 1e-5
+    sim.close()
+
+
 def test_single_env_protocol(torch_cuda):
     import robosuite_benchmark_b200 as suite
     from robosuite_benchmark_b200.wrappers import GymWrapper
