@@ -161,9 +161,11 @@ def run_ours(args):
     import robosuite_benchmark_b200 as suite
     from robosuite_benchmark_b200 import backend
 
+    from robosuite_benchmark_b200.parallel import max_over_ranks, shard, whole_job_rate
     E = args.envs
+    env_id_base, _ = shard(rank, world, E)
     cfg = suite.load_controller_config(default_controller=CONTROLLER)
-    env = suite.make(ENV_NAME, ROBOT, controller_configs=cfg, num_envs=E, batched=True, device=dev, seed=SEED, env_id_base=rank * E,
+    env = suite.make(ENV_NAME, ROBOT, controller_configs=cfg, num_envs=E, batched=True, device=dev, seed=SEED, env_id_base=env_id_base,
                      horizon=HORIZON, control_freq=20, reward_shaping=True, ignore_done=True)
     sim = env.sim
     obs = torch.zeros(E, sim.obs_dim, device=dev)
@@ -213,11 +215,8 @@ def run_ours(args):
     ms = sum(a.elapsed_time(b) for a, b in ev)
     kms = sum(a.elapsed_time(b) for a, b in kev)
     rsum = float(rew.mean().item())
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = world * E * args.steps / (ms_total / 1000.0)
+    ms_total = max_over_ranks(ms, dev)
+    value = whole_job_rate(E * args.steps, world, ms_total / 1000.0)
 
     # ---- end-to-end through the host-buffer C-ABI call (pinned host actions in; obs/reward/done out), every step
     h_act = torch.empty(E, sim.act_dim, pin_memory=True)
@@ -231,10 +230,7 @@ def run_ours(args):
         o_h, r_h, d_h = sim.step_host(h_act.numpy())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * E * e2e_steps / float(t.item())
+    e2e_value = whole_job_rate(E * e2e_steps, world, max_over_ranks(e2e_s, dev))
     clocks = sampler.stop() if rank == 0 else None
     sac = None
     if not args.no_sac:

@@ -419,10 +419,8 @@ class SACTrainer:
                                     _stream(self.device)))
 
     def _allreduce(self):
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.store.grad)                        # ONE flat bucket per update (sum), then mean
-            self.store.grad.mul_(1.0 / self.world)
+        from .parallel import allreduce_mean_
+        allreduce_mean_(self.store.grad, self.world)                # ONE flat bucket per update
 
     # -- public
     def train_step(self, batch=None, eps=None):
