@@ -158,6 +158,22 @@ RSB_D void quatrot(real *o, const real *q, const real *v) {
   o[0] = v[0] + q[0] * t[0] + u[0]; o[1] = v[1] + q[0] * t[1] + u[1]; o[2] = v[2] + q[0] * t[2] + u[2];
 }
 RSB_D real clampf(real x, real lo, real hi) { return fminf(fmaxf(x, lo), hi); }
+/* dot products over shared memory with four independent accumulators and the loads of four terms issued together: the inner
+   loops of this kernel are latency-bound (LDS ~29 cycles, dependent FMA 4 cycles), not throughput-bound */
+RSB_D real sdot(const real *a, const real *b, int n) {
+  real s0 = 0, s1 = 0, s2 = 0, s3 = 0; int k = 0;
+  for (; k + 4 <= n; k += 4) { real a0 = a[k], a1 = a[k + 1], a2 = a[k + 2], a3 = a[k + 3], b0 = b[k], b1 = b[k + 1], b2 = b[k + 2], b3 = b[k + 3];
+    s0 += a0 * b0; s1 += a1 * b1; s2 += a2 * b2; s3 += a3 * b3; }
+  for (; k < n; k++) s0 += a[k] * b[k];
+  return (s0 + s1) + (s2 + s3);
+}
+RSB_D real sdot_strided(const real *a, int stride, const real *b, int n) {         /* sum_k a[k*stride] * b[k] */
+  real s0 = 0, s1 = 0, s2 = 0, s3 = 0; int k = 0;
+  for (; k + 4 <= n; k += 4) { real a0 = a[k * stride], a1 = a[(k + 1) * stride], a2 = a[(k + 2) * stride], a3 = a[(k + 3) * stride], b0 = b[k], b1 = b[k + 1], b2 = b[k + 2], b3 = b[k + 3];
+    s0 += a0 * b0; s1 += a1 * b1; s2 += a2 * b2; s3 += a3 * b3; }
+  for (; k < n; k++) s0 += a[k * stride] * b[k];
+  return (s0 + s1) + (s2 + s3);
+}
 
 /* ------------------------------------------------------------------ Philox4x32-10 (same counters/keys as the oracle) */
 RSB_D void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
@@ -182,55 +198,82 @@ RSB_D void box_muller(uint32_t a, uint32_t b, real *z0, real *z1) {
 
 /* ================================================================== A.3.1 kinematics */
 RSB_DN void st_kinematics(int so, Grp g) { real *s = RSB_SMEM + so;
-  real *qpos = s + MDL.o_qpos, *jq = s + MDL.o_jq;
+  real *qpos = s + MDL.o_qpos, *lt = s + MDL.o_jq;               /* lt: per-body LOCAL transform (pos3, quat4), 7 words per body */
   real *xpos = s + MDL.o_xpos, *xquat = s + MDL.o_xquat, *xmat = s + MDL.o_xmat, *xanchor = s + MDL.o_xanchor, *xaxis = s + MDL.o_xaxis;
-  /* per-joint local motion, lane-parallel (the transcendental part) */
-  for (int j = g.lane; j < MDL.njnt; j += RSB_LANES) {
-    int t = MDL.jnt_type[j], a = MDL.jnt_qadr[j];
-    if (t == RSB_JNT_HINGE) {
-      real sn, cs; rsb_sincos(0.5f * (qpos[a] - MDL.qpos0[a]), &sn, &cs);
-      jq[4 * j] = cs; jq[4 * j + 1] = sn * MDL.jnt_axis[3 * j]; jq[4 * j + 2] = sn * MDL.jnt_axis[3 * j + 1]; jq[4 * j + 3] = sn * MDL.jnt_axis[3 * j + 2];
-    } else if (t == RSB_JNT_SLIDE) jq[4 * j] = qpos[a] - MDL.qpos0[a];
-    else quatnorm(qpos + a + 3);                   /* mj_kinematics normalises free-joint quaternions in place */
-  }
-  gsync(g);
-  /* tree composition: serial in tree order (one lane; the chain is inherently sequential) */
-  if (g.lane == 0) {
-    xpos[0] = xpos[1] = xpos[2] = 0; xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
-    for (int k = 0; k < 9; k++) xmat[k] = (k % 4 == 0) ? 1.0f : 0.0f;
-    for (int b = 1; b < MDL.nbody; b++) {
-      int p = MDL.body_parent[b], jn = MDL.body_jntnum[b], ja = MDL.body_jntadr[b];
-      real pos[3], quat[4];
-      if (jn == 1 && MDL.jnt_type[ja] == RSB_JNT_FREE) {
-        int a = MDL.jnt_qadr[ja];
-        pos[0] = qpos[a]; pos[1] = qpos[a + 1]; pos[2] = qpos[a + 2]; quat[0] = qpos[a + 3]; quat[1] = qpos[a + 4]; quat[2] = qpos[a + 5]; quat[3] = qpos[a + 6];
-        xanchor[3 * ja] = pos[0]; xanchor[3 * ja + 1] = pos[1]; xanchor[3 * ja + 2] = pos[2]; xaxis[3 * ja] = 0; xaxis[3 * ja + 1] = 0; xaxis[3 * ja + 2] = 1;
-      } else {
-        const real *bp = (b == MDL.override_body) ? s + MDL.o_bpose : MDL.body_pos + 3 * b;
-        const real *bq = (b == MDL.override_body) ? s + MDL.o_bpose + 3 : MDL.body_quat + 4 * b;
-        real t3[3]; matvec3(t3, xmat + 9 * p, bp);
-        pos[0] = xpos[3 * p] + t3[0]; pos[1] = xpos[3 * p + 1] + t3[1]; pos[2] = xpos[3 * p + 2] + t3[2];
-        quatmul(quat, xquat + 4 * p, bq);
-        for (int k = 0; k < jn; k++) {
-          int j = ja + k; real anchor[3], axis[3];
-          quatrot(t3, quat, MDL.jnt_pos + 3 * j); anchor[0] = pos[0] + t3[0]; anchor[1] = pos[1] + t3[1]; anchor[2] = pos[2] + t3[2];
-          quatrot(axis, quat, MDL.jnt_axis + 3 * j);
-          if (MDL.jnt_type[j] == RSB_JNT_SLIDE) { real dq = jq[4 * j]; pos[0] += axis[0] * dq; pos[1] += axis[1] * dq; pos[2] += axis[2] * dq; }
-          else {
-            real qn[4]; quatmul(qn, quat, jq + 4 * j); quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
-            quatrot(t3, quat, MDL.jnt_pos + 3 * j); pos[0] = anchor[0] - t3[0]; pos[1] = anchor[1] - t3[1]; pos[2] = anchor[2] - t3[2];
-          }
-          xanchor[3 * j] = anchor[0]; xanchor[3 * j + 1] = anchor[1]; xanchor[3 * j + 2] = anchor[2];
-          xaxis[3 * j] = axis[0]; xaxis[3 * j + 1] = axis[1]; xaxis[3 * j + 2] = axis[2];
+  /* phase A, lane per body: fold the body's joints into its parent-relative transform (all the trigonometry happens here) */
+  for (int b = g.lane; b < MDL.nbody; b += RSB_LANES) {
+    const int jn = MDL.body_jntnum[b], ja = MDL.body_jntadr[b];
+    real p[3], q[4];
+    if (jn == 1 && MDL.jnt_type[ja] == RSB_JNT_FREE) {           /* free body: world pose straight from qpos (normalised in place) */
+      const int a = MDL.jnt_qadr[ja]; quatnorm(qpos + a + 3);
+      p[0] = qpos[a]; p[1] = qpos[a + 1]; p[2] = qpos[a + 2]; q[0] = qpos[a + 3]; q[1] = qpos[a + 4]; q[2] = qpos[a + 5]; q[3] = qpos[a + 6];
+    } else {
+      const real *bp = (b == MDL.override_body) ? s + MDL.o_bpose : MDL.body_pos + 3 * b;
+      const real *bq = (b == MDL.override_body) ? s + MDL.o_bpose + 3 : MDL.body_quat + 4 * b;
+      p[0] = bp[0]; p[1] = bp[1]; p[2] = bp[2]; q[0] = bq[0]; q[1] = bq[1]; q[2] = bq[2]; q[3] = bq[3];
+      for (int k = 0; k < jn; k++) {
+        const int j = ja + k; const real dq = qpos[MDL.jnt_qadr[j]] - MDL.qpos0[MDL.jnt_qadr[j]]; real t3[3];
+        if (MDL.jnt_type[j] == RSB_JNT_SLIDE) { quatrot(t3, q, MDL.jnt_axis + 3 * j); p[0] += t3[0] * dq; p[1] += t3[1] * dq; p[2] += t3[2] * dq; }
+        else {                                                     /* hinge: rotate about the anchor, which stays fixed */
+          real sn, cs; rsb_sincos(0.5f * dq, &sn, &cs);
+          real jq4[4] = {cs, sn * MDL.jnt_axis[3 * j], sn * MDL.jnt_axis[3 * j + 1], sn * MDL.jnt_axis[3 * j + 2]}, qn[4], a3[3];
+          quatrot(a3, q, MDL.jnt_pos + 3 * j); quatmul(qn, q, jq4); quatrot(t3, qn, MDL.jnt_pos + 3 * j);
+          p[0] += a3[0] - t3[0]; p[1] += a3[1] - t3[1]; p[2] += a3[2] - t3[2]; q[0] = qn[0]; q[1] = qn[1]; q[2] = qn[2]; q[3] = qn[3];
         }
       }
-      quatnorm(quat);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) lt[7 * b + k] = p[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) lt[7 * b + 3 + k] = q[k];
+  }
+  gsync(g);
+  /* phase B: compose down the tree (inherently sequential; one lane, ~45 instructions per body) */
+  if (g.lane == 0) {
+    xpos[0] = xpos[1] = xpos[2] = 0; xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
+    for (int b = 1; b < MDL.nbody; b++) {
+      const int p = MDL.body_parent[b], jn = MDL.body_jntnum[b]; real pos[3], quat[4];
+      if (jn == 1 && MDL.jnt_type[MDL.body_jntadr[b]] == RSB_JNT_FREE) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) pos[k] = lt[7 * b + k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) quat[k] = lt[7 * b + 3 + k];
+      } else {
+        real t3[3]; quatrot(t3, xquat + 4 * p, lt + 7 * b);
+        pos[0] = xpos[3 * p] + t3[0]; pos[1] = xpos[3 * p + 1] + t3[1]; pos[2] = xpos[3 * p + 2] + t3[2];
+        quatmul(quat, xquat + 4 * p, lt + 7 * b + 3); quatnorm(quat);
+      }
       xpos[3 * b] = pos[0]; xpos[3 * b + 1] = pos[1]; xpos[3 * b + 2] = pos[2];
       xquat[4 * b] = quat[0]; xquat[4 * b + 1] = quat[1]; xquat[4 * b + 2] = quat[2]; xquat[4 * b + 3] = quat[3];
-      real R[9]; quat2mat(R, quat);
-#pragma unroll
-      for (int k = 0; k < 9; k++) xmat[9 * b + k] = R[k];
     }
+  }
+  gsync(g);
+  /* phase C, lane per body: rotation matrices; lane per joint: world anchors and axes (frame of the body BEFORE the joint moves it) */
+  for (int b = g.lane; b < MDL.nbody; b += RSB_LANES) { real R[9]; quat2mat(R, xquat + 4 * b);
+#pragma unroll
+    for (int k = 0; k < 9; k++) xmat[9 * b + k] = R[k]; }
+  for (int j = g.lane; j < MDL.njnt; j += RSB_LANES) {
+    const int b = MDL.jnt_body[j], p = MDL.body_parent[b], ja = MDL.body_jntadr[b]; real anchor[3], axis[3];
+    if (MDL.jnt_type[j] == RSB_JNT_FREE) { anchor[0] = xpos[3 * b]; anchor[1] = xpos[3 * b + 1]; anchor[2] = xpos[3 * b + 2]; axis[0] = 0; axis[1] = 0; axis[2] = 1; }
+    else {
+      const real *bp = (b == MDL.override_body) ? s + MDL.o_bpose : MDL.body_pos + 3 * b;
+      const real *bq = (b == MDL.override_body) ? s + MDL.o_bpose + 3 : MDL.body_quat + 4 * b;
+      real pl[3] = {bp[0], bp[1], bp[2]}, ql[4] = {bq[0], bq[1], bq[2], bq[3]}, t3[3];
+      for (int jj = ja; jj < j; jj++) {                           /* earlier joints of the same body (rare): replay their local motion */
+        const real dq = qpos[MDL.jnt_qadr[jj]] - MDL.qpos0[MDL.jnt_qadr[jj]];
+        if (MDL.jnt_type[jj] == RSB_JNT_SLIDE) { quatrot(t3, ql, MDL.jnt_axis + 3 * jj); pl[0] += t3[0] * dq; pl[1] += t3[1] * dq; pl[2] += t3[2] * dq; }
+        else { real sn, cs; rsb_sincos(0.5f * dq, &sn, &cs);
+          real jq4[4] = {cs, sn * MDL.jnt_axis[3 * jj], sn * MDL.jnt_axis[3 * jj + 1], sn * MDL.jnt_axis[3 * jj + 2]}, qn[4], a3[3];
+          quatrot(a3, ql, MDL.jnt_pos + 3 * jj); quatmul(qn, ql, jq4); quatrot(t3, qn, MDL.jnt_pos + 3 * jj);
+          pl[0] += a3[0] - t3[0]; pl[1] += a3[1] - t3[1]; pl[2] += a3[2] - t3[2]; ql[0] = qn[0]; ql[1] = qn[1]; ql[2] = qn[2]; ql[3] = qn[3]; }
+      }
+      real al[3], xl[3]; quatrot(t3, ql, MDL.jnt_pos + 3 * j); al[0] = pl[0] + t3[0]; al[1] = pl[1] + t3[1]; al[2] = pl[2] + t3[2];
+      quatrot(xl, ql, MDL.jnt_axis + 3 * j);
+      quatrot(t3, xquat + 4 * p, al); anchor[0] = xpos[3 * p] + t3[0]; anchor[1] = xpos[3 * p + 1] + t3[1]; anchor[2] = xpos[3 * p + 2] + t3[2];
+      quatrot(axis, xquat + 4 * p, xl);
+    }
+    xanchor[3 * j] = anchor[0]; xanchor[3 * j + 1] = anchor[1]; xanchor[3 * j + 2] = anchor[2];
+    xaxis[3 * j] = axis[0]; xaxis[3 * j + 1] = axis[1]; xaxis[3 * j + 2] = axis[2];
   }
   gsync(g);
   /* geoms and sites, lane-parallel */
@@ -331,8 +374,9 @@ RSB_DN void st_bias(int so, Grp g) { real *s = RSB_SMEM + so;
   real *cvel = s + MDL.o_cvel, *cacc = s + MDL.o_cacc, *cdd = s + MDL.o_cdofdot, *bias = s + MDL.o_bias, *passive = s + MDL.o_passive;
   /* body velocities: sum over the dof chain (all dofs of a tree share the reference point) */
   for (int b = g.lane; b < MDL.nbody; b += RSB_LANES) {
-    real v[6] = {0, 0, 0, 0, 0, 0};
-    for (int d = MDL.body_lastdof[b]; d >= 0; d = MDL.dof_parent[d]) { real q = qvel[d];
+    real v[6] = {0, 0, 0, 0, 0, 0}; const unsigned mask = (unsigned)MDL.body_dofmask[b];
+#pragma unroll 4
+    for (int d = 0; d < MDL.nv; d++) { real q = ((mask >> d) & 1u) ? qvel[d] : 0.0f;      /* predicated, no pointer chasing up the chain */
 #pragma unroll
       for (int k = 0; k < 6; k++) v[k] += cdof[6 * d + k] * q; }
 #pragma unroll
@@ -342,8 +386,9 @@ RSB_DN void st_bias(int so, Grp g) { real *s = RSB_SMEM + so;
   for (int d = g.lane; d < MDL.nv; d += RSB_LANES) {
     real o[6] = {0, 0, 0, 0, 0, 0}; int st = MDL.dof_velstart[d];
     if (st != -2) {
-      real v[6] = {0, 0, 0, 0, 0, 0};
-      for (int e = st; e >= 0; e = MDL.dof_parent[e]) { real q = qvel[e];
+      real v[6] = {0, 0, 0, 0, 0, 0}; const unsigned mask = (unsigned)MDL.dof_velmask[d];
+#pragma unroll 4
+      for (int e = 0; e < MDL.nv; e++) { real q = ((mask >> e) & 1u) ? qvel[e] : 0.0f;
 #pragma unroll
         for (int k = 0; k < 6; k++) v[k] += cdof[6 * e + k] * q; }
       crossm(o, v, cdof + 6 * d);
@@ -354,8 +399,9 @@ RSB_DN void st_bias(int so, Grp g) { real *s = RSB_SMEM + so;
   gsync(g);
   /* body accelerations (acc = 0, gravity as base acceleration) and body forces */
   for (int b = g.lane; b < MDL.nbody; b += RSB_LANES) {
-    real a[6] = {0, 0, 0, -MDL.gravity[0], -MDL.gravity[1], -MDL.gravity[2]};
-    for (int d = MDL.body_lastdof[b]; d >= 0; d = MDL.dof_parent[d]) { real q = qvel[d];
+    real a[6] = {0, 0, 0, -MDL.gravity[0], -MDL.gravity[1], -MDL.gravity[2]}; const unsigned mask = (unsigned)MDL.body_dofmask[b];
+#pragma unroll 4
+    for (int d = 0; d < MDL.nv; d++) { real q = ((mask >> d) & 1u) ? qvel[d] : 0.0f;
 #pragma unroll
       for (int k = 0; k < 6; k++) a[k] += cdd[6 * d + k] * q; }
     real f[6] = {0, 0, 0, 0, 0, 0};
@@ -654,15 +700,17 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
   gsync(g);
   const int nefc = misc[MISC_NEFC];
   /* scalar rows of J */
-  for (int i = g.lane; i < nscalar * nv; i += RSB_LANES) {
-    int r = i / nv, d = i - r * nv; real v = 0;
+  const int nvp = 1 << MDL.nvsh;                                 /* items are (row, dof) with dof = item & (nvp - 1): no integer division */
+  for (int i = g.lane; i < nscalar * nvp; i += RSB_LANES) {
+    int r = i >> MDL.nvsh, d = i & (nvp - 1); real v = 0; if (d >= nv) continue;
     if (etype[r] == EFC_FRICTION) v = (eid[r] == d) ? 1.0f : 0.0f;
     else v = (MDL.jnt_dadr[eid[r]] == d) ? efloss[r] : 0.0f;
     J[r * ldj + d] = v;
   }
   /* contact rows of J: item = (contact, dof) */
-  for (int i = g.lane; i < ncon * nv; i += RSB_LANES) {
-    int c = i / nv, d = i - c * nv; const real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr;
+  for (int i = g.lane; i < ncon * nvp; i += RSB_LANES) {
+    int c = i >> MDL.nvsh, d = i & (nvp - 1); if (d >= nv) continue;
+    const real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr;
     int adr = ci[CON_ADR]; if (adr < 0) continue;
     int dim = ci[CON_DIM], b1 = MDL.geom_body[ci[CON_G1]], b2 = MDL.geom_body[ci[CON_G2]];
     int sgn = ((MDL.body_dofmask[b2] >> d) & 1) - ((MDL.body_dofmask[b1] >> d) & 1);
@@ -698,7 +746,7 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
     if (type == EFC_FRICTION || type == EFC_CONTACT_FRICTION) K = 0;
     real imp = impedance_fn(solimp, epos[r], emargin[r]);
     real Rr = fmaxf((1 - imp) / imp * diag, RSB_MINVAL); eR[r] = Rr;
-    real vel = 0; for (int d = 0; d < nv; d++) vel += J[r * ldj + d] * qvel[d];
+    real vel = sdot(J + r * ldj, qvel, nv);
     earef[r] = -B * vel - K * imp * (epos[r] - emargin[r]);
   }
   gsync(g);
@@ -716,38 +764,48 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
   gsync(g);
 }
 
-/* ================================================================== dense Cholesky, lane per row (n <= 2*RSB_LANES) */
-/* In-place lower factor of the symmetric matrix A (only the lower triangle is read).  Pivots below `floor_` are treated as
-   dropped directions (pinv-like): the column is zeroed and the pivot set to +inf so solves return 0 along it. */
-RSB_DN void chol_factor(int ao, int n, int ld, Grp g) { real *A = RSB_SMEM + ao;
-  for (int j = 0; j < n; j++) {
-    real sj = 0, s0 = 0, s1 = 0; int i0 = g.lane, i1 = g.lane + RSB_LANES;
-    if (i0 >= j && i0 < n) { s0 = A[i0 * ld + j]; for (int k = 0; k < j; k++) s0 -= A[i0 * ld + k] * A[j * ld + k]; }
-    if (i1 >= j && i1 < n) { s1 = A[i1 * ld + j]; for (int k = 0; k < j; k++) s1 -= A[i1 * ld + k] * A[j * ld + k]; }
-    sj = gshfl(g, (j < RSB_LANES) ? s0 : s1, j % RSB_LANES);
-    real inv = sj > 1e-30f ? rsb_rsqrt(sj) : 0.0f, diag = sj > 1e-30f ? sj * inv : 1e30f;
-    if (i0 >= j && i0 < n) A[i0 * ld + j] = (i0 == j) ? diag : s0 * inv;
-    if (i1 >= j && i1 < n) A[i1 * ld + j] = (i1 == j) ? diag : s1 * inv;
-    gsync(g);
+/* ================================================================== dense Cholesky, one matrix row per lane (n <= RSB_LANES) */
+/* Right-looking factorisation with the row held in REGISTERS: lane i owns row i of the lower triangle; column j is scaled by the
+   broadcast pivot, then every trailing entry gets its rank-1 update from one shuffle + one FMA.  N(N+1)/2 shuffles, no shared-memory
+   traffic and no barriers until the factor is written back.  The factor is stored in place with the INVERSE pivots on the diagonal
+   (the solves only ever divide by them).  Pivots <= 1e-30 are dropped directions (pinv-like): inverse pivot 0. */
+template <int N> RSB_D void chol_factor_t(real *A, int n, int ld, Grp g) {
+  const int i = g.lane; real a[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) a[k] = (i < n && k <= i) ? A[i * ld + k] : 0.0f;
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    if (j < n) {
+      real sj = gshfl(g, a[j], j);
+      real inv = sj > 1e-30f ? rsb_rsqrt(sj) : 0.0f;
+      real lij = (i == j) ? inv : a[j] * inv;                     /* lane j keeps 1/L_jj, lanes i > j keep L_ij */
+      a[j] = lij;
+#pragma unroll
+      for (int k = j + 1; k < N; k++) if (k < n) { real lkj = gshfl(g, a[j], k); a[k] -= lij * lkj; }   /* lane k supplies L_kj; rows i >= k use it */
+    }
   }
+#pragma unroll
+  for (int k = 0; k < N; k++) if (i < n && k <= i) A[i * ld + k] = a[k];
+  gsync(g);
 }
-/* x <- A^-1 x with A = L L^T; x is a shared-memory vector of length n; result visible to all lanes on return */
+RSB_DN void chol_factor(int ao, int n, int ld, Grp g) { real *A = RSB_SMEM + ao;
+  if (n <= 8) chol_factor_t<8>(A, n, ld, g);
+  else if (n <= 16) chol_factor_t<16>(A, n, ld, g);
+  else chol_factor_t<32>(A, n, ld, g);
+}
+/* x <- A^-1 x with the factor of chol_factor (inverse pivots on the diagonal); x is a shared-memory vector of length n */
 RSB_DN void chol_solve(int lo_, int n, int ld, int xo, Grp g) { const real *L = RSB_SMEM + lo_; real *x = RSB_SMEM + xo;
-  int i0 = g.lane, i1 = g.lane + RSB_LANES;
-  real b0 = i0 < n ? x[i0] : 0, b1 = i1 < n ? x[i1] : 0;
-  for (int k = 0; k < n; k++) {
-    real mine = (k < RSB_LANES) ? b0 : b1; real xk = gshfl(g, mine, k % RSB_LANES) / L[k * ld + k];
-    if (i0 == k) b0 = xk; if (i1 == k) b1 = xk;
-    if (i0 > k && i0 < n) b0 -= L[i0 * ld + k] * xk;
-    if (i1 > k && i1 < n) b1 -= L[i1 * ld + k] * xk;
+  const int i = g.lane; const bool act = i < n;
+  real b = act ? x[i] : 0.0f; const real dinv = act ? L[i * ld + i] : 0.0f;
+  for (int k = 0; k < n; k++) {                                   /* forward: L y = b, column oriented */
+    real xk = gshfl(g, b * dinv, k);
+    if (i == k) b = xk; else if (i > k && act) b -= L[i * ld + k] * xk;
   }
-  for (int k = n - 1; k >= 0; k--) {
-    real mine = (k < RSB_LANES) ? b0 : b1; real xk = gshfl(g, mine, k % RSB_LANES) / L[k * ld + k];
-    if (i0 == k) b0 = xk; if (i1 == k) b1 = xk;
-    if (i0 < k) b0 -= L[k * ld + i0] * xk;
-    if (i1 < k) b1 -= L[k * ld + i1] * xk;
+  for (int k = n - 1; k >= 0; k--) {                              /* backward: L^T x = y */
+    real xk = gshfl(g, b * dinv, k);
+    if (i == k) b = xk; else if (i < k) b -= L[k * ld + i] * xk;
   }
-  if (i0 < n) x[i0] = b0; if (i1 < n) x[i1] = b1;
+  if (act) x[i] = b;
   gsync(g);
 }
 
@@ -808,16 +866,16 @@ RSB_DN void ctrl_set_goal(int so, Grp g) { real *s = RSB_SMEM + so;
   gsync(g);
 }
 
-/* serial 7x7 triangular solves on one lane (fully unrolled: x stays in registers) */
+/* serial 7x7 triangular solves on one lane (fully unrolled: x stays in registers); L carries inverse pivots on its diagonal */
 RSB_D void chol7_solve_reg(const real *L, real *x) {
 #pragma unroll
   for (int i = 0; i < 7; i++) { real v = x[i];
 #pragma unroll
-    for (int k = 0; k < i; k++) v -= L[i * 7 + k] * x[k]; x[i] = v / L[i * 7 + i]; }
+    for (int k = 0; k < i; k++) v -= L[i * 7 + k] * x[k]; x[i] = v * L[i * 7 + i]; }
 #pragma unroll
   for (int i = 6; i >= 0; i--) { real v = x[i];
 #pragma unroll
-    for (int k = i + 1; k < 7; k++) v -= L[k * 7 + i] * x[k]; x[i] = v / L[i * 7 + i]; }
+    for (int k = i + 1; k < 7; k++) v -= L[k * 7 + i] * x[k]; x[i] = v * L[i * 7 + i]; }
 }
 /* solve the symmetric 3x3 system A x = b (A given with leading dim ld); x = 0 when A is singular */
 RSB_D void sym3_solve(const real *A, int ld, const real *b, real *x) {
@@ -1014,9 +1072,12 @@ RSB_DN LsAcc efc_eval(int so, Grp g, int nefc, real alpha, int mode) { real *s =
 /* jar = J qacc - aref (lane per row); returns the total cost (Gauss + constraint), identical on all lanes */
 RSB_DN real solver_cost(int so, Grp g, int nefc, int qo) { real *s = RSB_SMEM + so; const real *qacc = RSB_SMEM + qo;
   const real *J = s + MDL.o_J, *earef = s + MDL.o_earef, *M = s + MDL.o_M, *qas = s + MDL.o_qacc_smooth; real *jar = s + MDL.o_ejar;
-  for (int r = g.lane; r < nefc; r += RSB_LANES) { real a = -earef[r]; for (int d = 0; d < MDL.nv; d++) a += J[r * MDL.ldj + d] * qacc[d]; jar[r] = a; }
+  for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] = sdot(J + r * MDL.ldj, qacc, MDL.nv) - earef[r];
   real gs = 0;
-  for (int i = g.lane; i < MDL.nv; i += RSB_LANES) { real md = 0; for (int j = 0; j < MDL.nv; j++) md += M[i * MDL.ldm + j] * (qacc[j] - qas[j]); gs += 0.5f * (qacc[i] - qas[i]) * md; }
+  real *dq = s + MDL.o_tmpv;                                       /* qacc - qacc_smooth */
+  for (int i = g.lane; i < MDL.nv; i += RSB_LANES) dq[i] = qacc[i] - qas[i];
+  gsync(g);
+  for (int i = g.lane; i < MDL.nv; i += RSB_LANES) gs += 0.5f * dq[i] * sdot(M + i * MDL.ldm, dq, MDL.nv);
   gsync(g);
   LsAcc a = efc_eval(so, g, nefc, 0.0f, 0);
   return gsum(g, gs + a.cost);
@@ -1041,15 +1102,17 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
   int iter = 0;
   for (; iter < MDL.solver_iters; iter++) {
     /* residual rows, forces, Hessian weights */
-    for (int r = g.lane; r < nefc; r += RSB_LANES) { real a = -(s + MDL.o_earef)[r]; for (int d = 0; d < nv; d++) a += J[r * ldj + d] * qacc[d]; jar[r] = a; }
+    for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] = sdot(J + r * ldj, qacc, nv) - (s + MDL.o_earef)[r];
     gsync(g);
     efc_eval(so, g, nefc, 0.0f, 1);
     gsync(g);
-    /* gradient = M qacc - M qacc_smooth - J^T f  (lane per dof) */
+    /* gradient = M (qacc - qacc_smooth) - J^T f  (lane per dof) */
+    for (int d = g.lane; d < nv; d += RSB_LANES) tmpv[d] = qacc[d] - qas[d];
+    gsync(g);
     real gn = 0;
     for (int d = g.lane; d < nv; d += RSB_LANES) {
-      real a = 0; for (int j = 0; j < nv; j++) a += M[d * ldm + j] * (qacc[j] - qas[j]);    /* difference first: exact 0 on unconstrained dofs */
-      real f = 0; for (int r = 0; r < nefc; r++) f += J[r * ldj + d] * force[r];
+      real a = sdot(M + d * ldm, tmpv, nv);                         /* tmpv = qacc - qacc_smooth: difference first, exact 0 on unconstrained dofs */
+      real f = sdot_strided(J + d, ldj, force, nefc);
       a -= f; grad[d] = a; qfc[d] = f; gn += a * a;
     }
     gn = gsum(g, gn);
@@ -1057,23 +1120,23 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
     if (g.lane == 0) printf("  it %d scaled|grad| %.3e\n", iter, scale * sqrtf(gn));
 #endif
     if (scale * sqrtf(gn) < MDL.solver_tol) break;
-    /* H = M + J^T W J (+ cone blocks), lower triangle, lanes over entries */
-    for (int e = g.lane; e < nv * nv; e += RSB_LANES) {
-      int i = e / nv, j = e - i * nv; if (j > i) continue;
+    /* H = M + J^T W J (+ cone blocks), lower triangle only, one lane per entry (table tri_ij) */
+    const int ncon_ = misc[MISC_NCON];
+    for (int e = g.lane; e < MDL.ntri; e += RSB_LANES) {
+      const int ij = MDL.tri_ij[e], i = ij >> 8, j = ij & 255;
       real h = M[i * ldm + j];
-      for (int r = 0; r < nefc; r++) { real wv = ew[r]; if (wv > 0) h += wv * J[r * ldj + i] * J[r * ldj + j]; }
-      H[i * ldm + j] = h;
-    }
-    gsync(g);
-    for (int c = 0; c < misc[MISC_NCON]; c++) {
-      const int *ci = (const int *)(con + c * RSB_CONW); int adr = ci[CON_ADR]; if (adr < 0 || !(ew[adr] < 0)) continue;
-      int dim = ci[CON_DIM]; const real *hc = Hc + c * 16;
-      for (int e = g.lane; e < nv * nv; e += RSB_LANES) {
-        int i = e / nv, j = e - i * nv; if (j > i) continue;
-        real h = 0;
+      { real h1 = 0, h2 = 0, h3 = 0; int r = 0; const real *Ji = J + i, *Jj = J + j;      /* cone rows carry ew < 0: clamped to 0 here */
+        for (; r + 4 <= nefc; r += 4) { real w0 = fmaxf(ew[r], 0.0f), w1 = fmaxf(ew[r + 1], 0.0f), w2 = fmaxf(ew[r + 2], 0.0f), w3 = fmaxf(ew[r + 3], 0.0f);
+          real a0 = Ji[r * ldj], a1 = Ji[(r + 1) * ldj], a2 = Ji[(r + 2) * ldj], a3 = Ji[(r + 3) * ldj], b0 = Jj[r * ldj], b1 = Jj[(r + 1) * ldj], b2 = Jj[(r + 2) * ldj], b3 = Jj[(r + 3) * ldj];
+          h += w0 * a0 * b0; h1 += w1 * a1 * b1; h2 += w2 * a2 * b2; h3 += w3 * a3 * b3; }
+        for (; r < nefc; r++) h += fmaxf(ew[r], 0.0f) * Ji[r * ldj] * Jj[r * ldj];
+        h += (h1 + h2) + h3; }
+      for (int c = 0; c < ncon_; c++) {                            /* sliding contacts: dim x dim cone block instead of the diagonal weights */
+        const int *ci = (const int *)(con + c * RSB_CONW); const int adr = ci[CON_ADR]; if (adr < 0 || !(ew[adr] < 0)) continue;
+        const int dim = ci[CON_DIM]; const real *hc = Hc + c * 16;
         for (int a = 0; a < dim; a++) { real ja = J[(adr + a) * ldj + i]; if (ja != 0) for (int b = 0; b < dim; b++) h += hc[a * 4 + b] * ja * J[(adr + b) * ldj + j]; }
-        H[i * ldm + j] += h;
       }
+      H[i * ldm + j] = h;
     }
     gsync(g);
     chol_factor(so + MDL.o_L, nv, ldm, g);
@@ -1082,8 +1145,8 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
     chol_solve(so + MDL.o_L, nv, ldm, so + MDL.o_search, g);
     /* directional quantities */
     real gq1 = 0, gq2 = 0;
-    for (int d = g.lane; d < nv; d += RSB_LANES) { real a = 0; for (int j = 0; j < nv; j++) a += M[d * ldm + j] * search[j]; Mv[d] = a; gq2 += search[d] * a; gq1 += search[d] * (grad[d] + qfc[d]); }
-    for (int r = g.lane; r < nefc; r += RSB_LANES) { real a = 0; for (int d = 0; d < nv; d++) a += J[r * ldj + d] * search[d]; Jv[r] = a; }
+    for (int d = g.lane; d < nv; d += RSB_LANES) { real a = sdot(M + d * ldm, search, nv); Mv[d] = a; gq2 += search[d] * a; gq1 += search[d] * (grad[d] + qfc[d]); }
+    for (int r = g.lane; r < nefc; r += RSB_LANES) Jv[r] = sdot(J + r * ldj, search, nv);
     gq1 = gsum(g, gq1); gq2 = gsum(g, gq2);           /* gq1 = s.(M a - M a_s): slope of the Gauss term at alpha = 0 */
     gsync(g);
     /* exact line search on the convex 1-D cost: safeguarded Newton on its derivative */
@@ -1109,11 +1172,11 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
     gsync(g);
   }
   if (iter == MDL.solver_iters) {                       /* forces must correspond to the final qacc */
-    for (int r = g.lane; r < nefc; r += RSB_LANES) { real a = -(s + MDL.o_earef)[r]; for (int d = 0; d < nv; d++) a += J[r * ldj + d] * qacc[d]; jar[r] = a; }
+    for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] = sdot(J + r * ldj, qacc, nv) - (s + MDL.o_earef)[r];
     gsync(g);
     efc_eval(so, g, nefc, 0.0f, 1);
     gsync(g);
-    for (int d = g.lane; d < nv; d += RSB_LANES) { real f = 0; for (int r = 0; r < nefc; r++) f += J[r * ldj + d] * force[r]; qfc[d] = f; }
+    for (int d = g.lane; d < nv; d += RSB_LANES) qfc[d] = sdot_strided(J + d, ldj, force, nefc);
   }
   if (g.lane == 0) misc[MISC_ITER] = iter;
   gsync(g);

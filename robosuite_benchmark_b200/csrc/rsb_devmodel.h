@@ -20,8 +20,8 @@
 #define RSB_DM_INT_ARRAYS(X) \
   X(body_parent) X(body_root) X(body_jntadr) X(body_jntnum) X(body_dofadr) X(body_dofnum) X(body_lastdof) X(body_dofmask) \
   X(jnt_type) X(jnt_qadr) X(jnt_dadr) X(jnt_body) \
-  X(dof_body) X(dof_jnt) X(dof_parent) X(dof_kind) X(dof_velstart) X(dof_root) \
-  X(mpair_i) X(mpair_j) \
+  X(dof_body) X(dof_jnt) X(dof_parent) X(dof_kind) X(dof_velstart) X(dof_velmask) X(dof_root) \
+  X(mpair_i) X(mpair_j) X(tri_ij) \
   X(geom_type) X(geom_body) X(site_body) \
   X(pair_g1) X(pair_g2) X(pair_dim) \
   X(act_dof) X(act_climited) X(act_flimited) \
@@ -58,6 +58,7 @@ typedef struct DevModel {
   /* sizes */
   int nq, nv, nu, nbody, njnt, ngeom, nsite, npair, nmpair, nfl, nlimj, ncon_max, nefc_max;
   int ldm, ldj;                /* leading dims of M/H (nv|1) and J (nv|1) */
+  int ntri, nvsh;              /* lower-triangle entry count nv(nv+1)/2 (table tri_ij = i<<8|j); log2 of the power of two >= nv */
   float timestep, gravity[3], impratio, meaninertia;
   int cone, any_damping, solver_iters, ls_iters;
   float solver_tol;
@@ -173,12 +174,16 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
     } else { dkind[(size_t)a] = m->jnt_type[j] == RSB_JNT_SLIDE ? RSB_DOF_SLIDE : RSB_DOF_HINGE; dvs[(size_t)a] = m->dof_parentid[a]; }
     if (m->jnt_limited[j] && m->jnt_type[j] != RSB_JNT_FREE) lim_jnt.push_back(j);
   }
+  std::vector<int> dvm((size_t)m->nv, 0);
+  for (int i = 0; i < m->nv; i++) { for (int k = dvs[(size_t)i]; k >= 0; k = m->dof_parentid[k]) dvm[(size_t)i] |= 1 << k; }
   for (int i = 0; i < m->nv; i++) {
     droot[(size_t)i] = m->body_rootid[m->dof_bodyid[i]];
     if (m->dof_frictionloss[i] > 0) fl_dof.push_back(i);
     if (m->dof_damping[i] > 0) d.any_damping = 1;
     for (int k = i; k >= 0; k = m->dof_parentid[k]) { mi.push_back(i); mj.push_back(k); }
   }
+  std::vector<int> tri; for (int i = 0; i < m->nv; i++) for (int j = 0; j <= i; j++) tri.push_back((i << 8) | j);
+  d.ntri = (int)tri.size(); d.nvsh = 0; while ((1 << d.nvsh) < m->nv) d.nvsh++;
   d.nfl = (int)fl_dof.size(); d.nlimj = (int)lim_jnt.size(); d.nmpair = (int)mi.size();
   std::vector<float> gmat((size_t)m->ngeom * 9), smat((size_t)m->nsite * 9);
   for (int g = 0; g < m->ngeom; g++) { double R[9]; q2m(m->geom_quat + 4 * g, R); for (int k = 0; k < 9; k++) gmat[(size_t)g * 9 + k] = (float)R[k]; }
@@ -193,7 +198,7 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
   SETI(jnt_type, vi(m->jnt_type, m->njnt)); SETI(jnt_qadr, vi(m->jnt_qposadr, m->njnt)); SETI(jnt_dadr, vi(m->jnt_dofadr, m->njnt));
   SETI(jnt_body, vi(m->jnt_bodyid, m->njnt));
   SETI(dof_body, vi(m->dof_bodyid, m->nv)); SETI(dof_jnt, vi(m->dof_jntid, m->nv)); SETI(dof_parent, vi(m->dof_parentid, m->nv));
-  SETI(dof_kind, dkind); SETI(dof_velstart, dvs); SETI(dof_root, droot); SETI(mpair_i, mi); SETI(mpair_j, mj);
+  SETI(dof_kind, dkind); SETI(dof_velstart, dvs); SETI(dof_velmask, dvm); SETI(dof_root, droot); SETI(mpair_i, mi); SETI(mpair_j, mj); SETI(tri_ij, tri);
   SETI(geom_type, vi(m->geom_type, m->ngeom)); SETI(geom_body, vi(m->geom_bodyid, m->ngeom)); SETI(site_body, vi(m->site_bodyid, m->nsite));
   SETI(pair_g1, vi(m->pair_geom1, m->npair)); SETI(pair_g2, vi(m->pair_geom2, m->npair)); SETI(pair_dim, vi(m->pair_condim, m->npair));
   SETI(act_dof, vi(m->act_dofid, m->nu)); SETI(act_climited, vi(m->act_ctrllimited, m->nu)); SETI(act_flimited, vi(m->act_forcelimited, m->nu));
@@ -254,7 +259,7 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
   int o = 0; int nb = d.nbody, nv = d.nv, nj = d.njnt, ne = nefc_max, nc = ncon_max;
 #define L(name, n) d.name = o; o += (n)
   L(o_qpos, d.nq); L(o_qvel, nv); L(o_warm, nv); L(o_ctrl, d.nu > 0 ? d.nu : 1); L(o_cs, d.nrobot * RSB_CS_WORDS + 1); L(o_act, d.act_dim + 1); L(o_bpose, 7);
-  L(o_xpos, 3 * nb); L(o_xquat, 4 * nb); L(o_xmat, 9 * nb); L(o_xanchor, 3 * nj + 1); L(o_xaxis, 3 * nj + 1); L(o_jq, 4 * nj + 1);
+  L(o_xpos, 3 * nb); L(o_xquat, 4 * nb); L(o_xmat, 9 * nb); L(o_xanchor, 3 * nj + 1); L(o_xaxis, 3 * nj + 1); L(o_jq, 7 * nb + 1);
   L(o_cinert, 10 * nb); L(o_crb, 10 * nb); L(o_cdof, 6 * nv); L(o_fi, 6 * nv); L(o_M, nv * d.ldm); L(o_L, nv * d.ldm);
   L(o_gxpos, 3 * d.ngeom + 1); L(o_gxmat, 9 * d.ngeom + 1); L(o_sxpos, 3 * d.nsite + 1); L(o_sxmat, 9 * d.nsite + 1);
   L(o_cvel, 6 * nb); L(o_cacc, 6 * nb); L(o_cdofdot, 6 * nv);
