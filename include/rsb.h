@@ -21,7 +21,7 @@ typedef struct rsb_batch rsb_batch;
 
 enum { RSB_INFO_NENVS = 0, RSB_INFO_OBS_DIM = 1, RSB_INFO_ACT_DIM = 2, RSB_INFO_STATE_WORDS = 3, RSB_INFO_SMEM_BYTES = 4,
        RSB_INFO_DBG_WORDS = 5, RSB_INFO_NQ = 6, RSB_INFO_NV = 7, RSB_INFO_ENVS_PER_BLOCK = 8, RSB_INFO_LAUNCHES = 9,
-       RSB_INFO_NCON_MAX = 10, RSB_INFO_NEFC_MAX = 11, RSB_INFO_REGS_STEP = 12, RSB_INFO_BLOCKS_PER_SM = 13 };
+       RSB_INFO_NCON_MAX = 10, RSB_INFO_NEFC_MAX = 11, RSB_INFO_REGS_STEP = 12, RSB_INFO_BLOCKS_PER_SM = 13, RSB_INFO_LANES = 14 };
 
 const char *rsb_last_error(void);
 int rsb_sizeof_model(void);

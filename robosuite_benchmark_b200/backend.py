@@ -21,11 +21,11 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 _LIB = None
 
 INFO = dict(nenvs=0, obs_dim=1, act_dim=2, state_words=3, smem_bytes=4, dbg_words=5, nq=6, nv=7, envs_per_block=8,
-            launches=9, ncon_max=10, nefc_max=11, regs_step=12, blocks_per_sm=13)
+            launches=9, ncon_max=10, nefc_max=11, regs_step=12, blocks_per_sm=13, lanes=14)
 
 
 def sources():
-    return [os.path.join(_CSRC, f) for f in ("rsb_cuda.cu", "rsb_sac.cu", "rsb_dev.h", "rsb_devmodel.h")] + \
+    return [os.path.join(_CSRC, f) for f in ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_kernels.inl", "rsb_ktable.h", "rsb_sac.cu", "rsb_dev.h", "rsb_devmodel.h")] + \
            [os.path.join(_HERE, "..", "include", f) for f in ("rsb.h", "rsb_sac.h", "rsb_model.h")]
 
 
@@ -33,7 +33,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/rsb_cuda.cu for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     stale = force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in sources())
     if stale:
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(_CSRC, "rsb_cuda.cu"), os.path.join(_CSRC, "rsb_sac.cu")]
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + [os.path.join(_CSRC, f) for f in ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_sac.cu")]
         subprocess.check_call(cmd)
     return LIB_PATH
 

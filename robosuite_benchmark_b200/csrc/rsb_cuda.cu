@@ -15,10 +15,9 @@
 
 #include "../../include/rsb.h"
 
-#define RSB_MAX_EPB 16         /* envs (warps) per CTA, chosen at create(): as many as fit shared memory, so that with lockstep
-                                  stages ONE CTA per SM shares a single instruction stream */
-#define RSB_LOCKSTEP 1
-#include "rsb_dev.h"
+#define RSB_LANES 32
+#define RSB_TABLE_NAME rsb_table_32
+#include "rsb_kernels.inl"     /* the 32-lane build of the kernels lives in this TU; rsb_cuda16.cu holds the 16-lane build */
 
 static thread_local std::string g_err;
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return 1; } } while (0)
@@ -28,6 +27,7 @@ struct rsb_batch {
   void *d_arena = nullptr;
   float *d_state = nullptr;
   int n = 0, device = 0, epb = 1;
+  const RsbKernelTable *kt = nullptr;
   uint64_t seed = 0, env_id_base = 0;
   size_t smem_bytes = 0;
   int64_t launches = 0;
@@ -38,51 +38,8 @@ struct rsb_batch {
   cudaStream_t stream = nullptr;
 };
 
-/* ------------------------------------------------------------------ kernels */
-__global__ void __launch_bounds__(RSB_MAX_EPB * 32)
-k_step(float *__restrict__ state, const float *__restrict__ actions, float *__restrict__ obs,
-       float *__restrict__ rew, unsigned char *__restrict__ done, int n) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, env = blockIdx.x * (blockDim.x >> 5) + w;
-  const bool commit = env < n; const int e = commit ? env : n - 1;          /* padding warps shadow the last env (no stores) */
-  Grp g{lane, 0xffffffffu};
-  env_step(w * c_model.smem_words, g, state + (size_t)e * c_model.st_words, actions + (size_t)e * c_model.act_dim,
-           obs + (size_t)e * c_model.obs_dim, rew + e, done + e, commit);
-}
-
-__global__ void __launch_bounds__(RSB_MAX_EPB * 32)
-k_reset(float *__restrict__ state, const unsigned char *__restrict__ mask, float *__restrict__ obs,
-        uint64_t seed, uint64_t env_id_base, int n) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, env = blockIdx.x * (blockDim.x >> 5) + w;
-  if (env >= n) return;
-  if (mask && !mask[env]) return;
-  Grp g{lane, 0xffffffffu};
-  env_reset(w * c_model.smem_words, g, state + (size_t)env * c_model.st_words, seed, env_id_base + (uint64_t)env, obs + (size_t)env * c_model.obs_dim);
-}
-
-__global__ void __launch_bounds__(RSB_MAX_EPB * 32)
-k_debug_substep(float *__restrict__ state, const float *__restrict__ actions, int policy_step,
-                float *__restrict__ dbg, int dbg_words, int n) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, env = blockIdx.x * (blockDim.x >> 5) + w;
-  const bool commit = env < n; const int e = commit ? env : n - 1;
-  const DevModel &m = c_model;
-  Grp g{lane, 0xffffffffu}; const int so = w * m.smem_words; float *s = rsb_smem + so; float *st = state + (size_t)e * m.st_words;
-  load_state(so, st, g);
-  for (int i = lane; i < m.act_dim; i += 32) s[m.o_act + i] = actions[(size_t)e * m.act_dim + i];
-  gsync(g);
-  substep(so, g, policy_step != 0);
-  if (!commit) return;
-  dump_debug(so, g, dbg + (size_t)e * dbg_words);
-  store_state(so, st, g);
-}
-
-__global__ void k_random_actions(uint64_t seed, uint64_t env_id_base, uint64_t step, int act_dim, float *__restrict__ actions, int n) {
-  const int nblk = (act_dim + 3) / 4; int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * nblk) return;
-  int env = i / nblk, blk = i - env * nblk;
-  random_action_block(seed, env_id_base + (uint64_t)env, step, blk, act_dim, actions + (size_t)env * act_dim);
-}
-
-static const rsb_batch *g_const_owner[64];
+static const rsb_batch *g_const_owner[64][2];     /* [device][lane-width variant]: which batch's model sits in constant memory */
+#define OWNER(b) g_const_owner[(b)->device][(b)->kt->lanes == 16]
 
 /* ------------------------------------------------------------------ C-ABI */
 extern "C" {
@@ -95,7 +52,7 @@ void rsb_destroy(rsb_batch *b) {
   if (!b) return;
   cudaSetDevice(b->device);
   cudaDeviceSynchronize();
-  if (b->device < 64 && g_const_owner[b->device] == b) g_const_owner[b->device] = nullptr;
+  if (b->device < 64 && b->kt && OWNER(b) == b) OWNER(b) = nullptr;
   cudaFree(b->d_arena); cudaFree(b->d_state); cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_done); cudaFree(b->d_mask);
   cudaFreeHost(b->p_act); cudaFreeHost(b->p_obs); cudaFreeHost(b->p_rew); cudaFreeHost(b->p_done);
   if (b->stream) cudaStreamDestroy(b->stream);
@@ -114,12 +71,15 @@ int rsb_create(const rsb_model *model, const rsb_task *task, int n_envs, int dev
   if (!rsb_build_host_model(model, task, ncon_max, nefc_max, hm)) { g_err = hm.error; return 4; }
   rsb_batch *b = new rsb_batch(); b->n = n_envs; b->device = device; b->seed = seed; b->env_id_base = env_id_base;
   b->dm = hm.dm;
+  /* lane-group width: 16 lanes (two envs per warp) when the model fits (nv <= 16), else one warp per env; RSB_LANES=32|16 overrides */
+  b->kt = (hm.dm.nv <= 16) ? &rsb_table_16 : &rsb_table_32;
+  if (const char *e = getenv("RSB_LANES")) { int v = atoi(e); if (v == 32) b->kt = &rsb_table_32; if (v == 16 && hm.dm.nv <= 16) b->kt = &rsb_table_16; }
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
   size_t per_env = (size_t)hm.dm.smem_words * 4;
-  int epb = (int)((size_t)prop.sharedMemPerBlockOptin / per_env); if (epb > RSB_MAX_EPB) epb = RSB_MAX_EPB;
+  int epb = (int)((size_t)prop.sharedMemPerBlockOptin / per_env); if (epb > b->kt->max_epb) epb = b->kt->max_epb;
   /* two CTAs per SM (each keeps its warps in lockstep) balance instruction-fetch sharing against barrier stalls and tail waves */
   { int half = (int)(((size_t)prop.sharedMemPerMultiprocessor / 2 - 1024) / per_env); if (half >= 4 && half < epb) epb = half; }
-  if (const char *e = getenv("RSB_EPB")) { int v = atoi(e); if (v > 0 && v < epb) epb = v; }
+  if (const char *e = getenv("RSB_EPB")) { int v = atoi(e); int cap = (int)((size_t)prop.sharedMemPerBlockOptin / per_env); if (v > 0) epb = v < cap ? v : cap; if (epb > b->kt->max_epb) epb = b->kt->max_epb; }
   if (epb < 1) { g_err = "per-env working set does not fit shared memory"; delete b; return 5; }
   b->epb = epb; b->smem_bytes = per_env * (size_t)epb;
   CK(cudaMalloc(&b->d_arena, hm.arena.size()));
@@ -127,11 +87,7 @@ int rsb_create(const rsb_model *model, const rsb_task *task, int n_envs, int dev
   rsb_fixup_pointers(b->dm, b->d_arena);
   CK(cudaMalloc(&b->d_state, (size_t)n_envs * b->dm.st_words * 4));
   CK(cudaMemset(b->d_state, 0, (size_t)n_envs * b->dm.st_words * 4));
-  CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
-  CK(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
-  CK(cudaFuncSetAttribute(k_debug_substep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
-  cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_step)); b->regs_step = fa.numRegs;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->blocks_per_sm, k_step, b->epb * 32, b->smem_bytes));
+  CK(b->kt->prepare(b->smem_bytes, b->epb, &b->regs_step, &b->blocks_per_sm));
   CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   *out = b; return 0;
 }
@@ -143,7 +99,7 @@ int64_t rsb_info(const rsb_batch *b, int what) {
     case RSB_INFO_DBG_WORDS: return RSB_DBG_WORDS(b->dm.nv, b->dm.ncon_max, b->dm.nefc_max); case RSB_INFO_NQ: return b->dm.nq; case RSB_INFO_NV: return b->dm.nv;
     case RSB_INFO_ENVS_PER_BLOCK: return b->epb; case RSB_INFO_LAUNCHES: return b->launches;
     case RSB_INFO_NCON_MAX: return b->dm.ncon_max; case RSB_INFO_NEFC_MAX: return b->dm.nefc_max;
-    case RSB_INFO_REGS_STEP: return b->regs_step; case RSB_INFO_BLOCKS_PER_SM: return b->blocks_per_sm;
+    case RSB_INFO_REGS_STEP: return b->regs_step; case RSB_INFO_BLOCKS_PER_SM: return b->blocks_per_sm; case RSB_INFO_LANES: return b->kt->lanes;
   }
   return -1;
 }
@@ -153,24 +109,25 @@ static inline int nblocks(const rsb_batch *b) { return (b->n + b->epb - 1) / b->
 /* The kernels read the model from constant memory.  Several batches (e.g. exploration and evaluation envs) may coexist in
    one process: the constant copy is re-uploaded, stream-ordered, whenever another batch used it last. */
 static int bind_model(rsb_batch *b, cudaStream_t st) {
-  if (b->device < 64 && g_const_owner[b->device] == b) return 0;
-  if (b->device < 64 && g_const_owner[b->device] != nullptr) CK(cudaDeviceSynchronize());     /* kernels of the previous owner may be in flight */
-  CK(cudaMemcpyToSymbolAsync(c_model, &b->dm, sizeof(DevModel), 0, cudaMemcpyHostToDevice, st));
-  if (b->device < 64) g_const_owner[b->device] = b;
+  if (b->device >= 64) { g_err = "device index >= 64"; return 1; }
+  if (OWNER(b) == b) return 0;
+  if (OWNER(b) != nullptr) CK(cudaDeviceSynchronize());     /* kernels of the previous owner may be in flight */
+  CK(b->kt->bind(&b->dm, st));
+  OWNER(b) = b;
   return 0;
 }
 
 int rsb_reset(rsb_batch *b, const uint8_t *d_mask, float *d_obs, void *stream) {
   CK(cudaSetDevice(b->device));
   if (bind_model(b, (cudaStream_t)stream)) return 1;
-  k_reset<<<nblocks(b), b->epb * 32, b->smem_bytes, (cudaStream_t)stream>>>(b->d_state, d_mask, d_obs, b->seed, b->env_id_base, b->n);
+  b->kt->reset(nblocks(b), b->epb, b->smem_bytes, (cudaStream_t)stream, b->d_state, d_mask, d_obs, b->seed, b->env_id_base, b->n);
   b->launches++; CK(cudaGetLastError()); return 0;
 }
 
 int rsb_step(rsb_batch *b, const float *d_actions, float *d_obs, float *d_reward, uint8_t *d_done, void *stream) {
   CK(cudaSetDevice(b->device));
   if (bind_model(b, (cudaStream_t)stream)) return 1;
-  k_step<<<nblocks(b), b->epb * 32, b->smem_bytes, (cudaStream_t)stream>>>(b->d_state, d_actions, d_obs, d_reward, d_done, b->n);
+  b->kt->step(nblocks(b), b->epb, b->smem_bytes, (cudaStream_t)stream, b->d_state, d_actions, d_obs, d_reward, d_done, b->n);
   b->launches++; CK(cudaGetLastError()); return 0;
 }
 
@@ -178,14 +135,13 @@ int rsb_debug_substep(rsb_batch *b, const float *d_actions, int policy_step, flo
   CK(cudaSetDevice(b->device));
   int words = RSB_DBG_WORDS(b->dm.nv, b->dm.ncon_max, b->dm.nefc_max);
   if (bind_model(b, (cudaStream_t)stream)) return 1;
-  k_debug_substep<<<nblocks(b), b->epb * 32, b->smem_bytes, (cudaStream_t)stream>>>(b->d_state, d_actions, policy_step, d_dbg, words, b->n);
+  b->kt->debug(nblocks(b), b->epb, b->smem_bytes, (cudaStream_t)stream, b->d_state, d_actions, policy_step, d_dbg, words, b->n);
   b->launches++; CK(cudaGetLastError()); return 0;
 }
 
 int rsb_random_actions(rsb_batch *b, uint64_t step, float *d_actions, void *stream) {
   CK(cudaSetDevice(b->device));
-  int total = b->n * ((b->dm.act_dim + 3) / 4);
-  k_random_actions<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->seed, b->env_id_base, step, b->dm.act_dim, d_actions, b->n);
+  b->kt->random((cudaStream_t)stream, b->seed, b->env_id_base, step, b->dm.act_dim, d_actions, b->n);
   b->launches++; CK(cudaGetLastError()); return 0;
 }
 

@@ -57,11 +57,11 @@ RSB_D uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a 
 #include <stdint.h>
 struct Grp { int lane; unsigned mask; };
 #define RSB_D __device__ __forceinline__
-#define RSB_DN __device__ __noinline__
-#define RSB_DNOINL __device__ __noinline__
+#define RSB_DN static __device__ __noinline__
+#define RSB_DNOINL static __device__ __noinline__
 /* the compiled model lives in constant memory (set by the host before a launch); every env's working set is a slice of
    the CTA's dynamic shared memory, addressed by WORD OFFSET so that non-inlined stage functions still emit LDS/STS */
-__constant__ DevModel c_model;
+static __constant__ DevModel c_model;
 extern __shared__ float rsb_smem[];
 #define MDL c_model
 #define RSB_SMEM rsb_smem
@@ -585,15 +585,15 @@ RSB_DNOINL int col_box_box(const real *pa, const real *Ra, const real *ha, const
   return cnt;
 }
 
-/* contact record in shared memory (RSB_CONW words): pos3 frame9 dist includemargin mu | pair dim efc_address geom1 geom2 */
-#define CON_DIST 12
-#define CON_INC 13
-#define CON_MU 14
-#define CON_PAIR 15
-#define CON_DIM 16
-#define CON_ADR 17
-#define CON_G1 18
-#define CON_G2 19
+/* contact record in shared memory (RSB_CONW = 10 words): pos3 normal3 dist mu | pair efc_address.  Everything else is a function of
+   the candidate pair (condim, geoms, includemargin) or of the normal (the tangent frame, rebuilt where the Jacobian is formed). */
+#define CON_DIST 6
+#define CON_MU 7
+#define CON_PAIR 8
+#define CON_ADR 9
+#define CON_DIM_OF(ci) (MDL.pair_dim[(ci)[CON_PAIR]])
+#define CON_G1_OF(ci) (MDL.pair_g1[(ci)[CON_PAIR]])
+#define CON_G2_OF(ci) (MDL.pair_g2[(ci)[CON_PAIR]])
 #define MISC_NCON 0
 #define MISC_NEFC 1
 #define MISC_ITER 2
@@ -632,11 +632,8 @@ RSB_DN void st_collision(int so, Grp g) { real *s = RSB_SMEM + so;
       int c = off + k; if (c >= MDL.ncon_max) break;
       real *o = con + c * RSB_CONW; int *oi = (int *)o;
       o[0] = rc[k].pos[0]; o[1] = rc[k].pos[1]; o[2] = rc[k].pos[2];
-      real fr[9]; fr[0] = rc[k].normal[0]; fr[1] = rc[k].normal[1]; fr[2] = rc[k].normal[2]; make_frame(fr);
-#pragma unroll
-      for (int q = 0; q < 9; q++) o[3 + q] = fr[q];
-      o[CON_DIST] = rc[k].dist; o[CON_INC] = inc; o[CON_MU] = 0;
-      oi[CON_PAIR] = p; oi[CON_DIM] = MDL.pair_dim[p]; oi[CON_ADR] = -1; oi[CON_G1] = MDL.pair_g1[p]; oi[CON_G2] = MDL.pair_g2[p];
+      o[3] = rc[k].normal[0]; o[4] = rc[k].normal[1]; o[5] = rc[k].normal[2];
+      o[CON_DIST] = rc[k].dist; o[CON_MU] = 0; oi[CON_PAIR] = p; oi[CON_ADR] = -1;
     }
     base += gshfl_i(g, incl, RSB_LANES - 1);
   }
@@ -647,6 +644,11 @@ RSB_DN void st_collision(int so, Grp g) { real *s = RSB_SMEM + so;
 
 /* ================================================================== A.3.6 constraint rows */
 enum { EFC_FRICTION = 0, EFC_LIMIT = 1, EFC_CONTACT_NORMAL = 2, EFC_CONTACT_FRICTION = 3 };
+/* one word per constraint row: type in bits 0-1, 'upper limit' flag (J = -e_dof) in bit 2, id (dof / joint / contact) above */
+#define ET_PACK(type, neg, id) (((id) << 3) | ((neg) << 2) | (type))
+#define ET_TYPE(w) ((w) & 3)
+#define ET_NEG(w) (((w) >> 2) & 1)
+#define ET_ID(w) ((w) >> 3)
 
 RSB_D real impedance_fn(const real *si, real pos, real margin) {
   real d0 = si[0], d1 = si[1], w = si[2], mid = si[3], pw = si[4];
@@ -672,19 +674,19 @@ RSB_D void kb_fn(const real *solref, const real *solimp, real *K, real *B) {
 RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
   const real *qpos = s + MDL.o_qpos, *qvel = s + MDL.o_qvel, *cdof = s + MDL.o_cdof, *xpos = s + MDL.o_xpos;
   real *con = s + MDL.o_con, *J = s + MDL.o_J; int *misc = (int *)(s + MDL.o_misc);
-  real *epos = s + MDL.o_epos, *emargin = s + MDL.o_emargin, *eR = s + MDL.o_eR, *eD = s + MDL.o_eD, *earef = s + MDL.o_earef, *efloss = s + MDL.o_efloss;
-  int *etype = (int *)(s + MDL.o_etype), *eid = (int *)(s + MDL.o_eid);
+  real *epos = s + MDL.o_epos, *emargin = s + MDL.o_emargin, *eR = s + MDL.o_eR, *eD = s + MDL.o_eD, *earef = s + MDL.o_earef;
+  int *etid = (int *)(s + MDL.o_etype);
   const int ncon = misc[MISC_NCON], nv = MDL.nv, ldj = MDL.ldj;
   /* rows 0..nfl-1: dof friction loss (static) */
-  for (int k = g.lane; k < MDL.nfl; k += RSB_LANES) { etype[k] = EFC_FRICTION; eid[k] = MDL.fl_dof[k]; epos[k] = 0; emargin[k] = 0; efloss[k] = MDL.dof_floss[MDL.fl_dof[k]]; }
+  for (int k = g.lane; k < MDL.nfl; k += RSB_LANES) { etid[k] = ET_PACK(EFC_FRICTION, 0, MDL.fl_dof[k]); epos[k] = 0; emargin[k] = 0; }
   /* joint limits: ordered compaction (joint order, lower side before upper side) */
   int nrow = MDL.nfl;
   for (int k0 = 0; k0 < MDL.nlimj; k0 += RSB_LANES) {
     int k = k0 + g.lane, cnt = 0; real dlo = 0, dhi = 0, mg = 0; int j = 0;
     if (k < MDL.nlimj) { j = MDL.lim_jnt[k]; real q = qpos[MDL.jnt_qadr[j]]; mg = MDL.jnt_margin[j]; dlo = q - MDL.jnt_range[2 * j]; dhi = MDL.jnt_range[2 * j + 1] - q; cnt = (dlo < mg) + (dhi < mg); }
     int incl = gscan_incl(g, cnt), r = nrow + incl - cnt;
-    if (cnt && dlo < mg && r < MDL.nefc_max) { etype[r] = EFC_LIMIT; eid[r] = j; epos[r] = dlo; emargin[r] = mg; efloss[r] = 1.0f; r++; }   /* efloss doubles as the sign of J */
-    if (cnt && dhi < mg && r < MDL.nefc_max) { etype[r] = EFC_LIMIT; eid[r] = j; epos[r] = dhi; emargin[r] = mg; efloss[r] = -1.0f; }
+    if (cnt && dlo < mg && r < MDL.nefc_max) { etid[r] = ET_PACK(EFC_LIMIT, 0, j); epos[r] = dlo; emargin[r] = mg; r++; }
+    if (cnt && dhi < mg && r < MDL.nefc_max) { etid[r] = ET_PACK(EFC_LIMIT, 1, j); epos[r] = dhi; emargin[r] = mg; }
     nrow += gshfl_i(g, incl, RSB_LANES - 1);
   }
   if (nrow > MDL.nefc_max) nrow = MDL.nefc_max;
@@ -693,7 +695,7 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
   gsync(g);
   if (g.lane == 0) {
     int n = nscalar;
-    for (int c = 0; c < ncon; c++) { int *ci = (int *)(con + c * RSB_CONW); int dim = ci[CON_DIM];
+    for (int c = 0; c < ncon; c++) { int *ci = (int *)(con + c * RSB_CONW); int dim = CON_DIM_OF(ci);
       if (n + dim > MDL.nefc_max) ci[CON_ADR] = -1; else { ci[CON_ADR] = n; n += dim; } }
     misc[MISC_NEFC] = n;
   }
@@ -703,8 +705,9 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
   const int nvp = 1 << MDL.nvsh;                                 /* items are (row, dof) with dof = item & (nvp - 1): no integer division */
   for (int i = g.lane; i < nscalar * nvp; i += RSB_LANES) {
     int r = i >> MDL.nvsh, d = i & (nvp - 1); real v = 0; if (d >= nv) continue;
-    if (etype[r] == EFC_FRICTION) v = (eid[r] == d) ? 1.0f : 0.0f;
-    else v = (MDL.jnt_dadr[eid[r]] == d) ? efloss[r] : 0.0f;
+    const int w = etid[r];
+    if (ET_TYPE(w) == EFC_FRICTION) v = (ET_ID(w) == d) ? 1.0f : 0.0f;
+    else v = (MDL.jnt_dadr[ET_ID(w)] == d) ? (ET_NEG(w) ? -1.0f : 1.0f) : 0.0f;
     J[r * ldj + d] = v;
   }
   /* contact rows of J: item = (contact, dof) */
@@ -712,7 +715,8 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
     int c = i >> MDL.nvsh, d = i & (nvp - 1); if (d >= nv) continue;
     const real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr;
     int adr = ci[CON_ADR]; if (adr < 0) continue;
-    int dim = ci[CON_DIM], b1 = MDL.geom_body[ci[CON_G1]], b2 = MDL.geom_body[ci[CON_G2]];
+    int dim = CON_DIM_OF(ci), b1 = MDL.geom_body[CON_G1_OF(ci)], b2 = MDL.geom_body[CON_G2_OF(ci)];
+    real fr[9] = {cr[3], cr[4], cr[5], 0, 0, 0, 0, 0, 0}; make_frame(fr);
     int sgn = ((MDL.body_dofmask[b2] >> d) & 1) - ((MDL.body_dofmask[b1] >> d) & 1);
     real jp[3] = {0, 0, 0}, jr[3] = {0, 0, 0};
     if (sgn != 0) {
@@ -721,26 +725,27 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
       jp[0] = sg * (cdof[6 * d + 3] + t[0]); jp[1] = sg * (cdof[6 * d + 4] + t[1]); jp[2] = sg * (cdof[6 * d + 5] + t[2]);
       jr[0] = sg * cdof[6 * d]; jr[1] = sg * cdof[6 * d + 1]; jr[2] = sg * cdof[6 * d + 2];
     }
-    J[adr * ldj + d] = dot3(cr + 3, jp);
-    if (dim >= 3) { J[(adr + 1) * ldj + d] = dot3(cr + 6, jp); J[(adr + 2) * ldj + d] = dot3(cr + 9, jp); }
-    if (dim >= 4) J[(adr + 3) * ldj + d] = dot3(cr + 3, jr);
+    J[adr * ldj + d] = dot3(fr, jp);
+    if (dim >= 3) { J[(adr + 1) * ldj + d] = dot3(fr + 3, jp); J[(adr + 2) * ldj + d] = dot3(fr + 6, jp); }
+    if (dim >= 4) J[(adr + 3) * ldj + d] = dot3(fr, jr);
   }
   /* contact row bookkeeping */
   for (int c = g.lane; c < ncon; c += RSB_LANES) {
     const real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr; int adr = ci[CON_ADR]; if (adr < 0) continue;
-    for (int r = 0; r < ci[CON_DIM]; r++) { etype[adr + r] = r == 0 ? EFC_CONTACT_NORMAL : EFC_CONTACT_FRICTION; eid[adr + r] = c; efloss[adr + r] = 0;
-      epos[adr + r] = r == 0 ? cr[CON_DIST] : 0; emargin[adr + r] = r == 0 ? cr[CON_INC] : 0; }
+    const int pr = ci[CON_PAIR]; const real inc = MDL.pair_margin[pr] - MDL.pair_gap[pr];
+    for (int r = 0; r < CON_DIM_OF(ci); r++) { etid[adr + r] = ET_PACK(r == 0 ? EFC_CONTACT_NORMAL : EFC_CONTACT_FRICTION, 0, c);
+      epos[adr + r] = r == 0 ? cr[CON_DIST] : 0; emargin[adr + r] = r == 0 ? inc : 0; }
   }
   gsync(g);
   /* impedance, regulariser, reference acceleration (mj_makeImpedance), lane per row */
   for (int r = g.lane; r < nefc; r += RSB_LANES) {
-    const real *solref, *solimp; real diag; int type = etype[r], id = eid[r];
+    const real *solref, *solimp; real diag; int type = ET_TYPE(etid[r]), id = ET_ID(etid[r]);
     if (type == EFC_FRICTION) { solref = MDL.dof_solref + 2 * id; solimp = MDL.dof_solimp + 5 * id; diag = MDL.dof_invw[id]; }
     else if (type == EFC_LIMIT) { solref = MDL.jnt_solref + 2 * id; solimp = MDL.jnt_solimp + 5 * id; diag = MDL.dof_invw[MDL.jnt_dadr[id]]; }
     else {
       const int *ci = (const int *)(con + id * RSB_CONW); int p = ci[CON_PAIR], rr = r - ci[CON_ADR];
       solref = MDL.pair_solref + 2 * p; solimp = MDL.pair_solimp + 5 * p; int o = rr < 3 ? 0 : 1;
-      diag = MDL.body_invw[2 * MDL.geom_body[ci[CON_G1]] + o] + MDL.body_invw[2 * MDL.geom_body[ci[CON_G2]] + o];
+      diag = MDL.body_invw[2 * MDL.geom_body[CON_G1_OF(ci)] + o] + MDL.body_invw[2 * MDL.geom_body[CON_G2_OF(ci)] + o];
     }
     real K, B; kb_fn(solref, solimp, &K, &B);
     if (type == EFC_FRICTION || type == EFC_CONTACT_FRICTION) K = 0;
@@ -752,7 +757,7 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
   gsync(g);
   /* elliptic friction rows: R from the normal row and impratio; regularised cone slope mu */
   for (int c = g.lane; c < ncon; c += RSB_LANES) {
-    real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr; int i = ci[CON_ADR], dim = ci[CON_DIM]; const real *fr = MDL.pair_friction + 5 * ci[CON_PAIR];
+    real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr; int i = ci[CON_ADR], dim = CON_DIM_OF(ci); const real *fr = MDL.pair_friction + 5 * ci[CON_PAIR];
     if (i < 0) continue;
     if (dim < 2) { cr[CON_MU] = fr[0]; continue; }
     real ir = fmaxf(MDL.impratio, RSB_MINVAL);
@@ -790,8 +795,12 @@ template <int N> RSB_D void chol_factor_t(real *A, int n, int ld, Grp g) {
 }
 RSB_DN void chol_factor(int ao, int n, int ld, Grp g) { real *A = RSB_SMEM + ao;
   if (n <= 8) chol_factor_t<8>(A, n, ld, g);
+#if RSB_LANES >= 32
   else if (n <= 16) chol_factor_t<16>(A, n, ld, g);
   else chol_factor_t<32>(A, n, ld, g);
+#else
+  else chol_factor_t<16>(A, n, ld, g);                            /* 16-lane groups serve models with nv <= 16 only (checked at create) */
+#endif
 }
 /* x <- A^-1 x with the factor of chol_factor (inverse pivots on the diagonal); x is a shared-memory vector of length n */
 RSB_DN void chol_solve(int lo_, int n, int ld, int xo, Grp g) { const real *L = RSB_SMEM + lo_; real *x = RSB_SMEM + xo;
@@ -964,15 +973,15 @@ RSB_DN void ctrl_run(int so, Grp g) { real *s = RSB_SMEM + so;
     gsync(g);
     if (g.lane < RSB_ARM_DOF) { int k = g.lane; real t = clampf(tau[k], rb.tl_lo[k], rb.tl_hi[k]); tau[k] = t; ctrl[rb.arm_act[k]] = t; }
     /* gripper: integrate the binary open/close command (robosuite Gripper.format_action) */
-    if (rb.grip_action_dim > 0 && g.lane >= 16 && g.lane < 16 + rb.grip_ndof) {
-      int k = g.lane - 16; real ga = s[MDL.o_act + rb.act_off + rb.control_dim]; real sg = ga > 0 ? 1.0f : (ga < 0 ? -1.0f : 0.0f);
+    if (rb.grip_action_dim > 0 && g.lane >= 8 && g.lane < 8 + rb.grip_ndof) {
+      int k = g.lane - 8; real ga = s[MDL.o_act + rb.act_off + rb.control_dim]; real sg = ga > 0 ? 1.0f : (ga < 0 ? -1.0f : 0.0f);
       real v = clampf(cs[CS_GRIP + k] + rb.grip_sign[k] * rb.grip_speed * sg, -1.0f, 1.0f); cs[CS_GRIP + k] = v;
       int a = rb.grip_act[k]; real lo = MDL.act_crange[2 * a], hi = MDL.act_crange[2 * a + 1];
       ctrl[a] = 0.5f * (hi + lo) + 0.5f * (hi - lo) * v;
     }
     gsync(g);
     /* keep the last torques for debugging/parity: cscr[208 + 7*ri ...] */
-    if (g.lane < RSB_ARM_DOF) scr[208 + 7 * ri + g.lane] = tau[g.lane];
+    if (g.lane < RSB_ARM_DOF) s[MDL.o_tau + 7 * ri + g.lane] = tau[g.lane];
     gsync(g);
   }
 }
@@ -1004,21 +1013,21 @@ struct LsAcc { real cost, d1, d2; };
 /* Evaluate the constraint cost of this lane's rows at x = jar + alpha*Jv.
    mode 0: cost only; mode 1: cost + force + Hessian weights (ew, Hc); mode 2: cost + line-search derivatives. */
 RSB_DN LsAcc efc_eval(int so, Grp g, int nefc, real alpha, int mode) { real *s = RSB_SMEM + so;
-  const real *con = s + MDL.o_con, *eD = s + MDL.o_eD, *eR = s + MDL.o_eR, *efloss = s + MDL.o_efloss, *jar = s + MDL.o_ejar, *Jv = s + MDL.o_eJv;
-  real *force = s + MDL.o_eforce, *ew = s + MDL.o_ew, *Hc = s + MDL.o_Hc; const int *etype = (const int *)(s + MDL.o_etype), *eid = (const int *)(s + MDL.o_eid);
+  const real *con = s + MDL.o_con, *eD = s + MDL.o_eD, *jar = s + MDL.o_ejar, *Jv = s + MDL.o_eJv;
+  real *force = s + MDL.o_eforce, *ew = s + MDL.o_ew; const int *etid = (const int *)(s + MDL.o_etype);
   real cost = 0, d1 = 0, d2 = 0;
   for (int r = g.lane; r < nefc; r += RSB_LANES) {
-    int type = etype[r]; real D = eD[r];
+    const int wd = etid[r], type = ET_TYPE(wd); real D = eD[r];
     if (type == EFC_CONTACT_FRICTION) continue;
     real dx = (mode == 2) ? Jv[r] : 0, x = jar[r] + alpha * dx;
     if (type == EFC_FRICTION) {
-      real fl = efloss[r], rf = eR[r] * fl;
+      real fl = MDL.dof_floss[ET_ID(wd)], rf = fl / D;          /* R * frictionloss */
       if (x <= -rf) { cost += -0.5f * rf * fl - fl * x; d1 += -fl * dx; if (mode == 1) { force[r] = fl; ew[r] = 0; } }
       else if (x >= rf) { cost += -0.5f * rf * fl + fl * x; d1 += fl * dx; if (mode == 1) { force[r] = -fl; ew[r] = 0; } }
       else { cost += 0.5f * D * x * x; d1 += D * x * dx; d2 += D * dx * dx; if (mode == 1) { force[r] = -D * x; ew[r] = D; } }
       continue;
     }
-    const real *cr = con + eid[r] * RSB_CONW; int dim = (type == EFC_LIMIT) ? 1 : ((const int *)cr)[CON_DIM];
+    const real *cr = con + ET_ID(wd) * RSB_CONW; int dim = (type == EFC_LIMIT) ? 1 : CON_DIM_OF((const int *)cr);
     if (dim == 1) {
       if (x < 0) { cost += 0.5f * D * x * x; d1 += D * x * dx; d2 += D * dx * dx; if (mode == 1) { force[r] = -D * x; ew[r] = D; } }
       else if (mode == 1) { force[r] = 0; ew[r] = 0; }
@@ -1049,8 +1058,8 @@ RSB_DN LsAcc efc_eval(int so, Grp g, int nefc, real alpha, int mode) { real *s =
 #pragma unroll
       for (int j = 1; j < RSB_MAXDIM; j++) if (j < dim) gU[j] = -Dm * mu * NmT * U[j] / T;
       if (mode == 1) { for (int j = 0; j < dim; j++) { force[r + j] = -gU[j] * sc[j]; ew[r + j] = -1.0f; } }     /* ew < 0 marks "use the cone block" */
-      if (mode >= 1) {
-        real *hc = Hc + eid[r] * 16; real invT = 1.0f / T;
+      if (mode == 2) {
+        real invT = 1.0f / T;
 #pragma unroll
         for (int a = 0; a < RSB_MAXDIM; a++)
 #pragma unroll
@@ -1059,14 +1068,32 @@ RSB_DN LsAcc efc_eval(int so, Grp g, int nefc, real alpha, int mode) { real *s =
             if (a == 0 && b == 0) h = Dm;
             else if (a == 0 || b == 0) h = -Dm * mu * U[a + b] * invT;
             else h = Dm * mu * mu * U[a] * U[b] * invT * invT - Dm * mu * NmT * ((a == b ? invT : 0.0f) - U[a] * U[b] * invT * invT * invT);
-            if (mode == 1) hc[a * 4 + b] = h * sc[a] * sc[b];
-            else d2 += dU[a] * h * dU[b];
+            if (mode == 2) d2 += dU[a] * h * dU[b];
           }
         if (mode == 2) { for (int j = 0; j < dim; j++) d1 += gU[j] * dU[j]; }
       }
     }
   }
   LsAcc acc; acc.cost = cost; acc.d1 = d1; acc.d2 = d2; return acc;
+}
+
+/* dim x dim Hessian block (in constraint-row space) of the elliptic cone cost for a contact in its MIDDLE zone, from the residuals
+   jar of its rows.  Recomputed where the Newton Hessian is assembled instead of being stored per contact (256 words of shared memory). */
+RSB_D void cone_mid_block(const real *jar_c, real D, real mu, const real *fr, int dim, real *hc) {
+  real sc[RSB_MAXDIM], U[RSB_MAXDIM]; sc[0] = mu; real T2 = 0;
+#pragma unroll
+  for (int j = 0; j < RSB_MAXDIM; j++) if (j < dim) { if (j > 0) sc[j] = fr[j - 1]; U[j] = jar_c[j] * sc[j]; if (j > 0) T2 += U[j] * U[j]; }
+  const real T = sqrtf(T2), invT = 1.0f / T, Dm = D / (mu * mu * (1 + mu * mu)), NmT = U[0] - mu * T;
+#pragma unroll
+  for (int a = 0; a < RSB_MAXDIM; a++)
+#pragma unroll
+    for (int b = 0; b < RSB_MAXDIM; b++) if (a < dim && b < dim) {
+      real h;
+      if (a == 0 && b == 0) h = Dm;
+      else if (a == 0 || b == 0) h = -Dm * mu * U[a + b] * invT;
+      else h = Dm * mu * mu * U[a] * U[b] * invT * invT - Dm * mu * NmT * ((a == b ? invT : 0.0f) - U[a] * U[b] * invT * invT * invT);
+      hc[a * 4 + b] = h * sc[a] * sc[b];
+    }
 }
 
 /* jar = J qacc - aref (lane per row); returns the total cost (Gauss + constraint), identical on all lanes */
@@ -1086,7 +1113,7 @@ RSB_DN real solver_cost(int so, Grp g, int nefc, int qo) { real *s = RSB_SMEM + 
 RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
   int *misc = (int *)(s + MDL.o_misc); const int nefc = misc[MISC_NEFC], nv = MDL.nv, ldm = MDL.ldm, ldj = MDL.ldj;
   real *qacc = s + MDL.o_qacc, *qas = s + MDL.o_qacc_smooth, *warm = s + MDL.o_warm, *qfc = s + MDL.o_qfc, *grad = s + MDL.o_grad, *search = s + MDL.o_search, *Mv = s + MDL.o_Mv, *tmpv = s + MDL.o_tmpv;
-  const real *M = s + MDL.o_M, *J = s + MDL.o_J; real *H = s + MDL.o_L, *force = s + MDL.o_eforce, *ew = s + MDL.o_ew, *Jv = s + MDL.o_eJv, *jar = s + MDL.o_ejar, *Hc = s + MDL.o_Hc;
+  const real *M = s + MDL.o_M, *J = s + MDL.o_J; real *H = s + MDL.o_L, *force = s + MDL.o_eforce, *ew = s + MDL.o_ew, *Jv = s + MDL.o_eJv, *jar = s + MDL.o_ejar;
   const real *con = s + MDL.o_con;
   if (nefc == 0) {
     for (int d = g.lane; d < nv; d += RSB_LANES) { qacc[d] = qas[d]; qfc[d] = 0; }
@@ -1131,12 +1158,17 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
           h += w0 * a0 * b0; h1 += w1 * a1 * b1; h2 += w2 * a2 * b2; h3 += w3 * a3 * b3; }
         for (; r < nefc; r++) h += fmaxf(ew[r], 0.0f) * Ji[r * ldj] * Jj[r * ldj];
         h += (h1 + h2) + h3; }
-      for (int c = 0; c < ncon_; c++) {                            /* sliding contacts: dim x dim cone block instead of the diagonal weights */
-        const int *ci = (const int *)(con + c * RSB_CONW); const int adr = ci[CON_ADR]; if (adr < 0 || !(ew[adr] < 0)) continue;
-        const int dim = ci[CON_DIM]; const real *hc = Hc + c * 16;
-        for (int a = 0; a < dim; a++) { real ja = J[(adr + a) * ldj + i]; if (ja != 0) for (int b = 0; b < dim; b++) h += hc[a * 4 + b] * ja * J[(adr + b) * ldj + j]; }
-      }
       H[i * ldm + j] = h;
+    }
+    for (int c = 0; c < ncon_; c++) {                              /* sliding contacts (rare): add the dim x dim cone block, recomputed here */
+      const real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr; const int adr = ci[CON_ADR]; if (adr < 0 || !(ew[adr] < 0)) continue;
+      const int dim = CON_DIM_OF(ci); real hc[16];
+      cone_mid_block(jar + adr, (s + MDL.o_eD)[adr], cr[CON_MU], MDL.pair_friction + 5 * ci[CON_PAIR], dim, hc);
+      for (int e = g.lane; e < MDL.ntri; e += RSB_LANES) {
+        const int ij = MDL.tri_ij[e], i = ij >> 8, j = ij & 255; real h = 0;
+        for (int a = 0; a < dim; a++) { real ja = J[(adr + a) * ldj + i]; if (ja != 0) for (int b = 0; b < dim; b++) h += hc[a * 4 + b] * ja * J[(adr + b) * ldj + j]; }
+        H[i * ldm + j] += h;
+      }
     }
     gsync(g);
     chol_factor(so + MDL.o_L, nv, ldm, g);
@@ -1211,18 +1243,20 @@ RSB_DN void st_euler(int so, Grp g) { real *s = RSB_SMEM + so;
 /* Stage sequence of one physics substep.  RSB_CTA_SYNC() between stages keeps all warps of the CTA in the same stage
    (they then share instruction-cache lines: the whole step is far larger than the I-cache); it carries no data dependency. */
 RSB_D void substep(int so, Grp g, bool policy_step) {
+  /* order matters for the shared-memory overlays (rsb_devmodel.h): everything that reads the kinematics/dynamics temporaries runs
+     before the constraint rows are built, because the Jacobian overlays them */
   st_kinematics(so, g); RSB_CTA_SYNC(); st_inertia(so, g); st_crb(so, g); RSB_CTA_SYNC(); st_collision(so, g); RSB_CTA_SYNC();
-  st_bias(so, g); RSB_CTA_SYNC(); st_constraint(so, g); RSB_CTA_SYNC();
+  st_bias(so, g); RSB_CTA_SYNC();
   if (policy_step) ctrl_set_goal(so, g);
   ctrl_run(so, g); RSB_CTA_SYNC();
-  st_actuation(so, g); RSB_CTA_SYNC(); st_solve(so, g); RSB_CTA_SYNC(); st_euler(so, g); RSB_CTA_SYNC();
+  st_actuation(so, g); RSB_CTA_SYNC(); st_constraint(so, g); RSB_CTA_SYNC(); st_solve(so, g); RSB_CTA_SYNC(); st_euler(so, g); RSB_CTA_SYNC();
 }
 
 RSB_D bool geom_in(const int *set, int n, int gm) { for (int i = 0; i < n; i++) if (set[i] == gm) return true; return false; }
 RSB_D bool check_grasp(int so, int ri, int obj_geom) { const real *s = RSB_SMEM + so;
   const DevRobot &rb = MDL.robot[ri]; const real *con = s + MDL.o_con; int ncon = ((const int *)(s + MDL.o_misc))[MISC_NCON]; bool tl = false, tr = false;
   for (int c = 0; c < ncon; c++) {
-    const int *ci = (const int *)(con + c * RSB_CONW); int g1 = ci[CON_G1], g2 = ci[CON_G2];
+    const int *ci = (const int *)(con + c * RSB_CONW); int g1 = CON_G1_OF(ci), g2 = CON_G2_OF(ci);
     if ((geom_in(rb.lfg, rb.nlfg, g1) && g2 == obj_geom) || (geom_in(rb.lfg, rb.nlfg, g2) && g1 == obj_geom)) tl = true;
     if ((geom_in(rb.rfg, rb.nrfg, g1) && g2 == obj_geom) || (geom_in(rb.rfg, rb.nrfg, g2) && g1 == obj_geom)) tr = true;
   }
@@ -1250,7 +1284,7 @@ RSB_DN real task_reward(int so) { const real *s = RSB_SMEM + so;
     bool lifted = A[2] > MDL.table_height + 0.04f; real r_lift = lifted ? 1.0f : 0.0f;
     if (lifted) { real hd = sqrtf((A[0] - B[0]) * (A[0] - B[0]) + (A[1] - B[1]) * (A[1] - B[1])); r_lift += 0.5f * (1 - tanhf(hd)); }
     bool touch = false; const real *con = s + MDL.o_con; int ncon = ((const int *)(s + MDL.o_misc))[MISC_NCON];
-    for (int c = 0; c < ncon; c++) { const int *ci = (const int *)(con + c * RSB_CONW); int g1 = ci[CON_G1], g2 = ci[CON_G2];
+    for (int c = 0; c < ncon; c++) { const int *ci = (const int *)(con + c * RSB_CONW); int g1 = CON_G1_OF(ci), g2 = CON_G2_OF(ci);
       if ((g1 == MDL.obj_geom[0] && g2 == MDL.obj_geom[1]) || (g2 == MDL.obj_geom[0] && g1 == MDL.obj_geom[1])) touch = true; }
     real r_stack = (!grasp && r_lift > 0 && touch) ? 2.0f : 0.0f;
     if (MDL.reward_shaping) r = fmaxf(r_reach, fmaxf(r_lift, r_stack)); else r = r_stack > 0 ? 2.0f : 0.0f;
@@ -1440,14 +1474,15 @@ RSB_D void dump_debug(int so, Grp g, real *out) { const real *s = RSB_SMEM + so;
   const int vecs[8] = {MDL.o_bias, MDL.o_passive, MDL.o_actuator, MDL.o_qacc_smooth, MDL.o_qacc, MDL.o_qfc, MDL.o_smooth, MDL.o_warm};
   for (int k = 0; k < 8; k++) for (int i = g.lane; i < nv; i += RSB_LANES) o[k * nv + i] = s[vecs[k] + i];
   o += 8 * nv;
-  for (int i = g.lane; i < 14; i += RSB_LANES) o[i] = s[MDL.o_cscr + 208 + i];
+  for (int i = g.lane; i < 14; i += RSB_LANES) o[i] = s[MDL.o_tau + i];
   o += 14;
   for (int i = g.lane; i < nc * 16; i += RSB_LANES) { int c = i / 16, k = i % 16; const real *cr = s + MDL.o_con + c * RSB_CONW; const int *ci = (const int *)cr;
-    real v = 0; if (c < misc[MISC_NCON]) { if (k < 13) v = cr[k]; else if (k == 13) v = (real)ci[CON_G1]; else if (k == 14) v = (real)ci[CON_G2]; else v = cr[CON_MU]; } o[i] = v; }
+    real v = 0; if (c < misc[MISC_NCON]) { real fr[9] = {cr[3], cr[4], cr[5], 0, 0, 0, 0, 0, 0}; make_frame(fr);
+      if (k < 3) v = cr[k]; else if (k < 12) v = fr[k - 3]; else if (k == 12) v = cr[CON_DIST]; else if (k == 13) v = (real)CON_G1_OF(ci); else if (k == 14) v = (real)CON_G2_OF(ci); else v = cr[CON_MU]; } o[i] = v; }
   o += nc * 16;
-  const int ev[5] = {MDL.o_earef, MDL.o_eR, MDL.o_eforce, MDL.o_epos, MDL.o_ejar};
+  const int ev[5] = {MDL.o_earef, MDL.o_eD, MDL.o_eforce, MDL.o_earef, MDL.o_ejar};    /* slots 1 and 3 used to be R and pos: now D and aref again (temporaries are overlaid) */
   for (int k = 0; k < 5; k++) for (int i = g.lane; i < ne; i += RSB_LANES) o[k * ne + i] = i < misc[MISC_NEFC] ? s[ev[k] + i] : 0;
-  for (int i = g.lane; i < ne; i += RSB_LANES) o[5 * ne + i] = i < misc[MISC_NEFC] ? (real)((const int *)(s + MDL.o_etype))[i] : -1;
+  for (int i = g.lane; i < ne; i += RSB_LANES) o[5 * ne + i] = i < misc[MISC_NEFC] ? (real)ET_TYPE(((const int *)(s + MDL.o_etype))[i]) : -1;
   o += 6 * ne;
   for (int i = g.lane; i < ne * nv; i += RSB_LANES) { int r = i / nv, d = i % nv; o[i] = r < misc[MISC_NEFC] ? s[MDL.o_J + r * MDL.ldj + d] : 0; }
 }

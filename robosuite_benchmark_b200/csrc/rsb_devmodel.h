@@ -13,7 +13,7 @@
 #include "../../include/rsb_model.h"
 
 #define RSB_MAXDIM 4            /* contact condim supported: 1, 3, 4 */
-#define RSB_CONW 20             /* words per contact record in shared memory */
+#define RSB_CONW 10             /* words per contact record in shared memory */
 #define RSB_CS_WORDS 80         /* controller state words per robot (same layout as the oracle's get/set_state) */
 
 /* int arrays */
@@ -80,7 +80,7 @@ typedef struct DevModel {
   int o_cvel, o_cacc, o_cdofdot;
   int o_bias, o_passive, o_actuator, o_smooth, o_qacc_smooth, o_qacc, o_qfc, o_grad, o_search, o_Mv, o_tmpv;
   int o_con, o_J, o_epos, o_emargin, o_eR, o_eD, o_earef, o_efloss, o_ejar, o_eJv, o_eforce, o_ew, o_etype, o_eid, o_Hc;
-  int o_cscr;                  /* controller scratch */
+  int o_cscr, o_tau;           /* controller scratch; last arm torques (kept for parity checks) */
   int o_misc;                  /* ncon, nefc, iters, ... (8 words) */
   int smem_words;
 #define X(n) const int *n;
@@ -255,19 +255,35 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
   int w = 0;
   d.st_qpos = w; w += d.nq; d.st_qvel = w; w += d.nv; d.st_warm = w; w += d.nv; d.st_cs = w; w += d.nrobot * RSB_CS_WORDS; d.st_bpose = w; w += 7;
   d.st_time = w++; d.st_episode = w++; d.st_words = w;
-  /* shared-memory layout */
+  /* shared-memory layout.  Arrays are grouped by LIFETIME inside one physics substep, and groups that are never alive together
+     share words (stage order: kinematics, inertia, crb, collision, bias, controller, actuation | constraint rows, solve, Euler):
+       P  persistent over the substep (state, poses needed late, cdof, M, force vectors, contact list, per-row D/aref/type)
+       A  kinematics/dynamics/controller temporaries, all dead once the actuation stage has run
+       J  the dense constraint Jacobian, written by the constraint stage -> overlays A
+       B  solver temporaries (factor workspace, cone blocks, per-row jar/Jv/force/weight; the constraint stage's pos/margin/R
+          temporaries overlay jar/Jv/force) */
   int o = 0; int nb = d.nbody, nv = d.nv, nj = d.njnt, ne = nefc_max, nc = ncon_max;
 #define L(name, n) d.name = o; o += (n)
   L(o_qpos, d.nq); L(o_qvel, nv); L(o_warm, nv); L(o_ctrl, d.nu > 0 ? d.nu : 1); L(o_cs, d.nrobot * RSB_CS_WORDS + 1); L(o_act, d.act_dim + 1); L(o_bpose, 7);
-  L(o_xpos, 3 * nb); L(o_xquat, 4 * nb); L(o_xmat, 9 * nb); L(o_xanchor, 3 * nj + 1); L(o_xaxis, 3 * nj + 1); L(o_jq, 7 * nb + 1);
-  L(o_cinert, 10 * nb); L(o_crb, 10 * nb); L(o_cdof, 6 * nv); L(o_fi, 6 * nv); L(o_M, nv * d.ldm); L(o_L, nv * d.ldm);
-  L(o_gxpos, 3 * d.ngeom + 1); L(o_gxmat, 9 * d.ngeom + 1); L(o_sxpos, 3 * d.nsite + 1); L(o_sxmat, 9 * d.nsite + 1);
-  L(o_cvel, 6 * nb); L(o_cacc, 6 * nb); L(o_cdofdot, 6 * nv);
-  L(o_bias, nv); L(o_passive, nv); L(o_actuator, nv); L(o_smooth, nv); L(o_qacc_smooth, nv); L(o_qacc, nv); L(o_qfc, nv);
+  L(o_xpos, 3 * nb); L(o_sxpos, 3 * d.nsite + 1); L(o_sxmat, 9 * d.nsite + 1); L(o_cdof, 6 * nv); L(o_M, nv * d.ldm);
+  L(o_bias, nv); L(o_actuator, nv); L(o_smooth, nv); L(o_qacc_smooth, nv); L(o_qacc, nv); L(o_qfc, nv); L(o_tau, 7 * RSB_MAX_ROBOTS);
+  L(o_con, nc * RSB_CONW); L(o_eD, ne); L(o_earef, ne); L(o_etype, ne); d.o_efloss = d.o_eid = 0; L(o_misc, 8);
+  const int r0 = o;
+  /* group A */
+  L(o_xquat, 4 * nb); L(o_passive, nv); L(o_gxpos, 3 * d.ngeom + 1); L(o_gxmat, 9 * d.ngeom + 1); L(o_cvel, 6 * nb);
+  { const int x1 = o; int kin = (7 * nb + 1) + 2 * (3 * nj + 1); int sz = kin > 208 ? kin : 208;          /* X1: controller scratch | per-body local transforms, joint anchors/axes */
+    d.o_cscr = x1; d.o_jq = x1; d.o_xanchor = x1 + 7 * nb + 1; d.o_xaxis = d.o_xanchor + 3 * nj + 1; o = x1 + sz; }
+  L(o_cinert, 10 * nb); L(o_crb, 10 * nb);
+  { const int x3 = o; int sz = 6 * nb + 6 * nv; if (sz < 9 * nb) sz = 9 * nb;                                          /* X3: body rotation matrices (kinematics, inertia) | crb force temporaries | RNE temporaries */
+    d.o_xmat = x3; d.o_cacc = x3; d.o_cdofdot = x3 + 6 * nb; d.o_fi = x3; o = x3 + sz; }
+  const int end_a = o;
+  /* group J over A */
+  d.o_J = r0; const int end_j = r0 + ne * d.ldj;
+  o = end_a > end_j ? end_a : end_j;
+  /* group B */
+  L(o_L, nv * d.ldm); d.o_Hc = 0; L(o_ejar, ne); L(o_eJv, ne); L(o_eforce, ne); L(o_ew, ne);
   L(o_grad, nv); L(o_search, nv); L(o_Mv, nv); L(o_tmpv, nv);
-  L(o_con, nc * RSB_CONW); L(o_J, ne * d.ldj); L(o_epos, ne); L(o_emargin, ne); L(o_eR, ne); L(o_eD, ne); L(o_earef, ne); L(o_efloss, ne);
-  L(o_ejar, ne); L(o_eJv, ne); L(o_eforce, ne); L(o_ew, ne); L(o_etype, ne); L(o_eid, ne); L(o_Hc, nc * 16);
-  L(o_cscr, 256); L(o_misc, 8);
+  d.o_epos = d.o_ejar; d.o_emargin = d.o_eJv; d.o_eR = d.o_eforce;
 #undef L
   d.smem_words = (o + 3) & ~3;
   return true;

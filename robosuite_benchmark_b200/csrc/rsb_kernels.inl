@@ -1,0 +1,78 @@
+/*
+ * rsb_kernels.inl -- the env kernels for ONE lane-group width (RSB_LANES = 32: one env per warp; 16: two envs per warp).
+ * Included by rsb_cuda.cu (32) and rsb_cuda16.cu (16); everything is TU-local and exported through an RsbKernelTable.
+ * The 16-lane variant halves the instruction stream per environment (the kernel is instruction-fetch bound, profiles/) and is
+ * used for models with nv <= 16; the lane-cooperative code in rsb_dev.h is written against RSB_LANES throughout.
+ */
+#include <cuda_runtime.h>
+#include "rsb_ktable.h"
+#define RSB_LOCKSTEP 1
+#include "rsb_dev.h"
+
+namespace {
+#define GROUPS_PER_WARP (32 / RSB_LANES)
+__device__ __forceinline__ Grp make_group(int &slot) {
+  const int lane = threadIdx.x & (RSB_LANES - 1); slot = threadIdx.x / RSB_LANES;
+  const unsigned full = (RSB_LANES == 32) ? 0xffffffffu : ((1u << RSB_LANES) - 1u);
+  Grp g{lane, full << (RSB_LANES * (slot % GROUPS_PER_WARP) % 32)};
+  return g;
+}
+
+__global__ void __launch_bounds__(RSB_MAX_THREADS)
+k_step(float *__restrict__ state, const float *__restrict__ actions, float *__restrict__ obs, float *__restrict__ rew, unsigned char *__restrict__ done, int n) {
+  int w; Grp g = make_group(w); const int env = blockIdx.x * (blockDim.x / RSB_LANES) + w;
+  const bool commit = env < n; const int e = commit ? env : n - 1;          /* padding groups shadow the last env (no stores) */
+  env_step(w * c_model.smem_words, g, state + (size_t)e * c_model.st_words, actions + (size_t)e * c_model.act_dim,
+           obs + (size_t)e * c_model.obs_dim, rew + e, done + e, commit);
+}
+
+__global__ void __launch_bounds__(RSB_MAX_THREADS)
+k_reset(float *__restrict__ state, const unsigned char *__restrict__ mask, float *__restrict__ obs, uint64_t seed, uint64_t env_id_base, int n) {
+  int w; Grp g = make_group(w); const int env = blockIdx.x * (blockDim.x / RSB_LANES) + w;
+  if (env >= n) return;
+  if (mask && !mask[env]) return;
+  env_reset(w * c_model.smem_words, g, state + (size_t)env * c_model.st_words, seed, env_id_base + (uint64_t)env, obs + (size_t)env * c_model.obs_dim);
+}
+
+__global__ void __launch_bounds__(RSB_MAX_THREADS)
+k_debug_substep(float *__restrict__ state, const float *__restrict__ actions, int policy_step, float *__restrict__ dbg, int dbg_words, int n) {
+  int w; Grp g = make_group(w); const int env = blockIdx.x * (blockDim.x / RSB_LANES) + w;
+  const bool commit = env < n; const int e = commit ? env : n - 1;
+  const DevModel &m = c_model;
+  const int so = w * m.smem_words; float *s = rsb_smem + so; float *st = state + (size_t)e * m.st_words;
+  load_state(so, st, g);
+  for (int i = g.lane; i < m.act_dim; i += RSB_LANES) s[m.o_act + i] = actions[(size_t)e * m.act_dim + i];
+  gsync(g);
+  substep(so, g, policy_step != 0);
+  if (!commit) return;
+  dump_debug(so, g, dbg + (size_t)e * dbg_words);
+  store_state(so, st, g);
+}
+
+__global__ void k_random_actions(uint64_t seed, uint64_t env_id_base, uint64_t step, int act_dim, float *__restrict__ actions, int n) {
+  const int nblk = (act_dim + 3) / 4; int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * nblk) return;
+  int env = i / nblk, blk = i - env * nblk;
+  random_action_block(seed, env_id_base + (uint64_t)env, step, blk, act_dim, actions + (size_t)env * act_dim);
+}
+
+cudaError_t t_bind(const DevModel *dm, cudaStream_t st) { return cudaMemcpyToSymbolAsync(c_model, dm, sizeof(DevModel), 0, cudaMemcpyHostToDevice, st); }
+cudaError_t t_prepare(size_t smem_bytes, int epb, int *regs, int *blocks_per_sm) {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_debug_substep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
+  cudaFuncAttributes fa; if ((e = cudaFuncGetAttributes(&fa, k_step)) != cudaSuccess) return e; *regs = fa.numRegs;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_step, epb * RSB_LANES, smem_bytes);
+}
+void t_step(int blocks, int epb, size_t smem, cudaStream_t st, float *state, const float *a, float *o, float *r, unsigned char *d, int n) {
+  k_step<<<blocks, epb * RSB_LANES, smem, st>>>(state, a, o, r, d, n); }
+void t_reset(int blocks, int epb, size_t smem, cudaStream_t st, float *state, const unsigned char *mask, float *o, uint64_t seed, uint64_t base, int n) {
+  k_reset<<<blocks, epb * RSB_LANES, smem, st>>>(state, mask, o, seed, base, n); }
+void t_debug(int blocks, int epb, size_t smem, cudaStream_t st, float *state, const float *a, int ps, float *dbg, int words, int n) {
+  k_debug_substep<<<blocks, epb * RSB_LANES, smem, st>>>(state, a, ps, dbg, words, n); }
+void t_random(cudaStream_t st, uint64_t seed, uint64_t base, uint64_t step, int act_dim, float *a, int n) {
+  int total = n * ((act_dim + 3) / 4); k_random_actions<<<(total + 127) / 128, 128, 0, st>>>(seed, base, step, act_dim, a, n); }
+}  // namespace
+
+extern const RsbKernelTable RSB_TABLE_NAME = {RSB_LANES, RSB_MAX_THREADS / RSB_LANES, t_bind, t_prepare, t_step, t_reset, t_debug, t_random};

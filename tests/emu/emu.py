@@ -15,25 +15,27 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _LIB = None
 
 
-def build(force=False):
-    so = os.path.join(_HERE, "librsb_emu.so")
+def build(force=False, lanes=32):
+    so = os.path.join(_HERE, "librsb_emu.so" if lanes == 32 else f"librsb_emu{lanes}.so")
     srcs = [os.path.join(_HERE, "rsb_emu.cpp"), os.path.join(_ROOT, "robosuite_benchmark_b200", "csrc", "rsb_dev.h"),
             os.path.join(_ROOT, "robosuite_benchmark_b200", "csrc", "rsb_devmodel.h"), os.path.join(_ROOT, "include", "rsb_model.h")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-fno-strict-aliasing", "-Wall",
-                               "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-misleading-indentation",
-                               "-o", so, srcs[0]])
+                               "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable", "-Wno-misleading-indentation",
+                               f"-DRSB_LANES={lanes}", "-o", so, srcs[0]])
     return so
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        L = C.CDLL(build())
+_LIBS = {}
+
+
+def lib(lanes=32):
+    if lanes not in _LIBS:
+        L = C.CDLL(build(lanes=lanes))
         L.emu_create.restype = C.c_void_p
         L.emu_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
-        _LIB = L
-    return _LIB
+        _LIBS[lanes] = L
+    return _LIBS[lanes]
 
 
 def _p(a):
@@ -64,9 +66,9 @@ def split_debug(dbg, nv, ncon_max, nefc_max):
 
 
 class EmuEnv:
-    def __init__(self, model, task, ncon_max=16, nefc_max=64):
+    def __init__(self, model, task, ncon_max=16, nefc_max=64, lanes=32):
         from robosuite_benchmark_b200.model.cstruct import model_to_c, task_to_c
-        self.L = lib()
+        self.L = lib(lanes)
         self.model, self.task = model, task
         self._cm, self._keep = model_to_c(model)
         self._ct = task_to_c(task)

@@ -88,12 +88,12 @@ void emu_set_state(void *h, const float *in) { EmuEnv *e = (EmuEnv *)h; memcpy(e
 void emu_reset(void *h, uint64_t seed, uint64_t env_id, float *obs) {
   EmuEnv *e = (EmuEnv *)h;
   emu_model = e->dm; emu_smem = e->smem.data();
-  run_group([&](int lane) { Grp g{lane, 0xffffffffu}; env_reset(0, g, e->state.data(), seed, env_id, obs); });
+  run_group([&](int lane) { Grp g{lane, (RSB_LANES == 32) ? 0xffffffffu : ((1u << RSB_LANES) - 1u)}; env_reset(0, g, e->state.data(), seed, env_id, obs); });
 }
 int emu_step(void *h, const float *action, float *obs, float *reward) {
   EmuEnv *e = (EmuEnv *)h; unsigned char done = 0;
   emu_model = e->dm; emu_smem = e->smem.data();
-  run_group([&](int lane) { Grp g{lane, 0xffffffffu}; env_step(0, g, e->state.data(), action, obs, reward, &done, true); });
+  run_group([&](int lane) { Grp g{lane, (RSB_LANES == 32) ? 0xffffffffu : ((1u << RSB_LANES) - 1u)}; env_step(0, g, e->state.data(), action, obs, reward, &done, true); });
   return done;
 }
 /* one physics substep from the stored state, state written back, internals dumped */
@@ -101,7 +101,7 @@ void emu_debug_substep(void *h, const float *action, int policy_step, float *dbg
   EmuEnv *e = (EmuEnv *)h;
   emu_model = e->dm; emu_smem = e->smem.data();
   run_group([&](int lane) {
-    Grp g{lane, 0xffffffffu}; const DevModel &m = e->dm; float *s = e->smem.data();
+    Grp g{lane, (RSB_LANES == 32) ? 0xffffffffu : ((1u << RSB_LANES) - 1u)}; const DevModel &m = e->dm; float *s = e->smem.data();
     load_state(0, e->state.data(), g);
     for (int i = g.lane; i < m.act_dim; i += RSB_LANES) s[m.o_act + i] = action[i];
     gsync(g);
