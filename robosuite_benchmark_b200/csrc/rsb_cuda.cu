@@ -76,9 +76,19 @@ int rsb_create(const rsb_model *model, const rsb_task *task, int n_envs, int dev
   if (const char *e = getenv("RSB_LANES")) { int v = atoi(e); if (v == 32) b->kt = &rsb_table_32; if (v == 16 && hm.dm.nv <= 16) b->kt = &rsb_table_16; }
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
   size_t per_env = (size_t)hm.dm.smem_words * 4;
-  int epb = (int)((size_t)prop.sharedMemPerBlockOptin / per_env); if (epb > b->kt->max_epb) epb = b->kt->max_epb;
-  /* two CTAs per SM (each keeps its warps in lockstep) balance instruction-fetch sharing against barrier stalls and tail waves */
-  { int half = (int)(((size_t)prop.sharedMemPerMultiprocessor / 2 - 1024) / per_env); if (half >= 4 && half < epb) epb = half; }
+  /* Envs per CTA.  The kernel is latency-bound per warp, so what counts is (1) the number of WAVES the batch needs on this GPU and
+     (2) even work per SM.  Try two CTAs per SM (measured best: each CTA keeps its warps in lockstep) and one; take the fewest waves,
+     then the smallest envs-per-CTA that still needs that many waves (4096 Lift envs on 148 SMs -> 2 x 14 per SM, one wave). */
+  int epb = 0; long best_waves = 0;
+  for (int bps = 2; bps >= 1; bps--) {
+    size_t budget = (size_t)prop.sharedMemPerMultiprocessor / bps - (size_t)prop.reservedSharedMemPerBlock;
+    if (budget > (size_t)prop.sharedMemPerBlockOptin) budget = (size_t)prop.sharedMemPerBlockOptin;
+    int cap = (int)(budget / per_env); if (cap > b->kt->max_epb) cap = b->kt->max_epb;
+    if (cap < 1) continue;
+    long slots = (long)prop.multiProcessorCount * bps, waves = ((long)n_envs + slots * cap - 1) / (slots * cap);
+    int e = (int)(((long)n_envs + slots * waves - 1) / (slots * waves));            /* balanced: ceil(n / (waves * CTAs per wave)) */
+    if (epb == 0 || waves < best_waves) { epb = e; best_waves = waves; }
+  }
   if (const char *e = getenv("RSB_EPB")) { int v = atoi(e); int cap = (int)((size_t)prop.sharedMemPerBlockOptin / per_env); if (v > 0) epb = v < cap ? v : cap; if (epb > b->kt->max_epb) epb = b->kt->max_epb; }
   if (epb < 1) { g_err = "per-env working set does not fit shared memory"; delete b; return 5; }
   b->epb = epb; b->smem_bytes = per_env * (size_t)epb;

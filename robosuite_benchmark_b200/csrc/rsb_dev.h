@@ -50,6 +50,7 @@ RSB_D real gshfl_up(Grp g, real v, int d) { return emu_shfl_f(v, g.lane >= d ? g
 RSB_D int gshfl_up_i(Grp g, int v, int d) { return emu_shfl_i(v, g.lane >= d ? g.lane - d : g.lane); }
 RSB_D void rsb_sincos(real x, real *s, real *c) { *s = sinf(x); *c = cosf(x); }
 RSB_D real rsb_rsqrt(real x) { return 1.0f / sqrtf(x); }
+RSB_D bool wany(bool p) { return p; }                          /* the emulator runs one group at a time */
 RSB_D int f2i(real f) { int i; memcpy(&i, &f, 4); return i; }
 RSB_D real i2f(int i) { real f; memcpy(&f, &i, 4); return f; }
 RSB_D uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
@@ -70,15 +71,21 @@ extern __shared__ float rsb_smem[];
 #else
 #define RSB_CTA_SYNC() ((void)0)
 #endif
-RSB_D void gsync(Grp g) { __syncwarp(g.mask); }
-RSB_D real gshfl(Grp g, real v, int src) { return __shfl_sync(g.mask, v, src, RSB_LANES); }
-RSB_D int gshfl_i(Grp g, int v, int src) { return __shfl_sync(g.mask, v, src, RSB_LANES); }
-RSB_D real gshfl_xor(Grp g, real v, int x) { return __shfl_xor_sync(g.mask, v, x, RSB_LANES); }
-RSB_D int gshfl_xor_i(Grp g, int v, int x) { return __shfl_xor_sync(g.mask, v, x, RSB_LANES); }
-RSB_D real gshfl_up(Grp g, real v, int d) { return __shfl_up_sync(g.mask, v, d, RSB_LANES); }
-RSB_D int gshfl_up_i(Grp g, int v, int d) { return __shfl_up_sync(g.mask, v, d, RSB_LANES); }
+/* WARP-UNIFORM CONTROL FLOW: the groups of a warp (two 16-lane groups, or one 32-lane group) always execute every shuffle / warp
+   barrier together, so the member mask is the compile-time constant 0xffffffff and a shuffle is ONE instruction (a run-time mask costs
+   MATCH + REDUX + VOTE + branch per shuffle).  Data-dependent loops that contain shuffles run until no group of the warp is active
+   (`wany`), with the finished group's updates predicated off. */
+#define RSB_FULL 0xffffffffu
+RSB_D void gsync(Grp) { __syncwarp(); }
+RSB_D real gshfl(Grp, real v, int src) { return __shfl_sync(RSB_FULL, v, src, RSB_LANES); }
+RSB_D int gshfl_i(Grp, int v, int src) { return __shfl_sync(RSB_FULL, v, src, RSB_LANES); }
+RSB_D real gshfl_xor(Grp, real v, int x) { return __shfl_xor_sync(RSB_FULL, v, x, RSB_LANES); }
+RSB_D int gshfl_xor_i(Grp, int v, int x) { return __shfl_xor_sync(RSB_FULL, v, x, RSB_LANES); }
+RSB_D real gshfl_up(Grp, real v, int d) { return __shfl_up_sync(RSB_FULL, v, d, RSB_LANES); }
+RSB_D int gshfl_up_i(Grp, int v, int d) { return __shfl_up_sync(RSB_FULL, v, d, RSB_LANES); }
+RSB_D bool wany(bool p) { return __any_sync(RSB_FULL, p) != 0; }
 RSB_D void rsb_sincos(real x, real *s, real *c) { sincosf(x, s, c); }
-RSB_D real rsb_rsqrt(real x) { return rsqrtf(x); }
+RSB_D real rsb_rsqrt(real x) { real r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 RSB_D int f2i(real f) { return __float_as_int(f); }
 RSB_D real i2f(int i) { return __int_as_float(i); }
 RSB_D uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
@@ -173,6 +180,20 @@ RSB_D real sdot_strided(const real *a, int stride, const real *b, int n) {      
     s0 += a0 * b0; s1 += a1 * b1; s2 += a2 * b2; s3 += a3 * b3; }
   for (; k < n; k++) s0 += a[k * stride] * b[k];
   return (s0 + s1) + (s2 + s3);
+}
+
+/* M, the Newton Hessian and their factors are PACKED lower triangles: entry (i, j), j <= i, at i(i+1)/2 + j */
+RSB_D int tri_off(int i) { return (i * (i + 1)) >> 1; }
+RSB_D real msym(const real *P, int i, int j) { return i >= j ? P[tri_off(i) + j] : P[tri_off(j) + i]; }
+/* row i of (symmetric packed P) times v: one uniform loop over j, the index switches from row i to column i at the diagonal */
+RSB_D real symv_row(const real *P, int i, const real *v, int n) {
+  real s0 = 0, s1 = 0; const int ri = tri_off(i); int tj = 0, j = 0;                      /* tj = tri_off(j) */
+  for (; j + 2 <= n; j += 2) {
+    const int i0 = (j <= i) ? ri + j : tj + i, t1 = tj + j + 1, i1 = (j + 1 <= i) ? ri + j + 1 : t1 + i;
+    s0 += P[i0] * v[j]; s1 += P[i1] * v[j + 1]; tj = t1 + j + 2;
+  }
+  if (j < n) { const int i0 = (j <= i) ? ri + j : tj + i; s0 += P[i0] * v[j]; }
+  return s0 + s1;
 }
 
 /* ------------------------------------------------------------------ Philox4x32-10 (same counters/keys as the oracle) */
@@ -338,7 +359,7 @@ RSB_DN void st_inertia(int so, Grp g) { real *s = RSB_SMEM + so;
     }
     cdof[6 * d] = w[0]; cdof[6 * d + 1] = w[1]; cdof[6 * d + 2] = w[2]; cdof[6 * d + 3] = v[0]; cdof[6 * d + 4] = v[1]; cdof[6 * d + 5] = v[2];
   }
-  for (int i = g.lane; i < MDL.nv * MDL.ldm; i += RSB_LANES) M[i] = 0;
+  for (int i = g.lane; i < MDL.ntri; i += RSB_LANES) M[i] = 0;
   gsync(g);
 }
 
@@ -354,7 +375,7 @@ RSB_DN void st_crb(int so, Grp g) { real *s = RSB_SMEM + so;
   for (int p = g.lane; p < MDL.nmpair; p += RSB_LANES) {
     int i = MDL.mpair_i[p], j = MDL.mpair_j[p]; real v = dot6(cdof + 6 * j, fi + 6 * i);
     if (i == j) v += MDL.dof_armature[i];
-    M[i * MDL.ldm + j] = v; M[j * MDL.ldm + i] = v;
+    M[tri_off(i) + j] = v;                         /* mpair: j is i or one of its ancestors, j <= i */
   }
   gsync(g);
 }
@@ -775,47 +796,57 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
    traffic and no barriers until the factor is written back.  The factor is stored in place with the INVERSE pivots on the diagonal
    (the solves only ever divide by them).  Pivots <= 1e-30 are dropped directions (pinv-like): inverse pivot 0. */
 template <int N> RSB_D void chol_factor_t(real *A, int n, int ld, Grp g) {
-  const int i = g.lane; real a[N];
+  const int i = g.lane; real a[N]; real *Ai = A + (ld ? i * ld : tri_off(i));       /* ld == 0: packed lower triangle */
 #pragma unroll
-  for (int k = 0; k < N; k++) a[k] = (i < n && k <= i) ? A[i * ld + k] : 0.0f;
+  for (int k = 0; k < N; k++) a[k] = (i < n && k <= i) ? Ai[k] : ((k == i) ? 1.0f : 0.0f);   /* identity padding up to N: no size tests below */
 #pragma unroll
   for (int j = 0; j < N; j++) {
-    if (j < n) {
-      real sj = gshfl(g, a[j], j);
-      real inv = sj > 1e-30f ? rsb_rsqrt(sj) : 0.0f;
-      real lij = (i == j) ? inv : a[j] * inv;                     /* lane j keeps 1/L_jj, lanes i > j keep L_ij */
-      a[j] = lij;
+    real sj = gshfl(g, a[j], j);
+    real inv = sj > 1e-30f ? rsb_rsqrt(sj) : 0.0f;
+    real lij = (i == j) ? inv : a[j] * inv;                       /* lane j keeps 1/L_jj, lanes i > j keep L_ij */
+    a[j] = lij;
 #pragma unroll
-      for (int k = j + 1; k < N; k++) if (k < n) { real lkj = gshfl(g, a[j], k); a[k] -= lij * lkj; }   /* lane k supplies L_kj; rows i >= k use it */
-    }
+    for (int k = j + 1; k < N; k++) { real lkj = gshfl(g, a[j], k); a[k] -= lij * lkj; }   /* lane k supplies L_kj; rows i >= k use it */
   }
 #pragma unroll
-  for (int k = 0; k < N; k++) if (i < n && k <= i) A[i * ld + k] = a[k];
+  for (int k = 0; k < N; k++) if (i < n && k <= i) Ai[k] = a[k];
   gsync(g);
 }
 RSB_DN void chol_factor(int ao, int n, int ld, Grp g) { real *A = RSB_SMEM + ao;
   if (n <= 8) chol_factor_t<8>(A, n, ld, g);
+  else if (n <= 12) chol_factor_t<12>(A, n, ld, g);
 #if RSB_LANES >= 32
   else if (n <= 16) chol_factor_t<16>(A, n, ld, g);
+  else if (n <= 24) chol_factor_t<24>(A, n, ld, g);
   else chol_factor_t<32>(A, n, ld, g);
 #else
   else chol_factor_t<16>(A, n, ld, g);                            /* 16-lane groups serve models with nv <= 16 only (checked at create) */
 #endif
 }
-/* x <- A^-1 x with the factor of chol_factor (inverse pivots on the diagonal); x is a shared-memory vector of length n */
-RSB_DN void chol_solve(int lo_, int n, int ld, int xo, Grp g) { const real *L = RSB_SMEM + lo_; real *x = RSB_SMEM + xo;
-  const int i = g.lane; const bool act = i < n;
-  real b = act ? x[i] : 0.0f; const real dinv = act ? L[i * ld + i] : 0.0f;
-  for (int k = 0; k < n; k++) {                                   /* forward: L y = b, column oriented */
-    real xk = gshfl(g, b * dinv, k);
-    if (i == k) b = xk; else if (i > k && act) b -= L[i * ld + k] * xk;
-  }
-  for (int k = n - 1; k >= 0; k--) {                              /* backward: L^T x = y */
-    real xk = gshfl(g, b * dinv, k);
-    if (i == k) b = xk; else if (i < k) b -= L[k * ld + i] * xk;
-  }
+/* x <- A^-1 x with the factor of chol_factor (inverse pivots on the diagonal); x is a shared-memory vector of length n.  Lane i
+   preloads row i (forward sweep) and column i (backward sweep) of L, so the two dependent chains are shuffle + FMA only. */
+template <int N> RSB_D void chol_solve_t(const real *L, int n, int ld, real *x, Grp g) {
+  const int i = g.lane; const bool act = i < n; real row[N], col[N]; const real *Li = L + (ld ? i * ld : tri_off(i));
+#pragma unroll
+  for (int k = 0; k < N; k++) { row[k] = (act && k < i) ? Li[k] : 0.0f; col[k] = (act && k > i && k < n) ? L[(ld ? k * ld : (k * (k + 1)) / 2) + i] : 0.0f; }
+  real b = act ? x[i] : 0.0f; const real dinv = act ? Li[i] : 0.0f;
+#pragma unroll
+  for (int k = 0; k < N; k++) { real xk = gshfl(g, b * dinv, k); b = (i == k) ? xk : b - row[k] * xk; }          /* forward: L y = b */
+#pragma unroll
+  for (int k = N - 1; k >= 0; k--) { real xk = gshfl(g, b * dinv, k); b = (i == k) ? xk : b - col[k] * xk; }     /* backward: L^T x = y */
   if (act) x[i] = b;
   gsync(g);
+}
+RSB_DN void chol_solve(int lo_, int n, int ld, int xo, Grp g) { const real *L = RSB_SMEM + lo_; real *x = RSB_SMEM + xo;
+  if (n <= 8) chol_solve_t<8>(L, n, ld, x, g);
+  else if (n <= 12) chol_solve_t<12>(L, n, ld, x, g);
+#if RSB_LANES >= 32
+  else if (n <= 16) chol_solve_t<16>(L, n, ld, x, g);
+  else if (n <= 24) chol_solve_t<24>(L, n, ld, x, g);
+  else chol_solve_t<32>(L, n, ld, x, g);
+#else
+  else chol_solve_t<16>(L, n, ld, x, g);
+#endif
 }
 
 /* ================================================================== A.2 controllers */
@@ -842,8 +873,8 @@ RSB_D real scale_action(const DevRobot &rb, int k, real a) {
 RSB_DN void ctrl_reset(int so, Grp g) { real *s = RSB_SMEM + so;
   const real *qpos = s + MDL.o_qpos, *sxpos = s + MDL.o_sxpos, *sxmat = s + MDL.o_sxmat;
   for (int ri = 0; ri < MDL.nrobot; ri++) {
-    const DevRobot &rb = MDL.robot[ri]; real *cs = s + MDL.o_cs + ri * RSB_CS_WORDS;
-    for (int k = g.lane; k < RSB_CS_WORDS; k += RSB_LANES) {
+    const DevRobot &rb = MDL.robot[ri]; real *cs = s + MDL.o_cs + ri * MDL.cs_words;
+    for (int k = g.lane; k < MDL.cs_words; k += RSB_LANES) {
       real v = 0;
       if (k < 3) v = sxpos[3 * rb.eef_site + k];
       else if (k < 12) v = sxmat[9 * rb.eef_site + k - 3];
@@ -857,7 +888,7 @@ RSB_DN void ctrl_reset(int so, Grp g) { real *s = RSB_SMEM + so;
 RSB_DN void ctrl_set_goal(int so, Grp g) { real *s = RSB_SMEM + so;
   const real *act = s + MDL.o_act, *sxpos = s + MDL.o_sxpos, *sxmat = s + MDL.o_sxmat;
   if (g.lane < MDL.nrobot) {
-    int ri = g.lane; const DevRobot &rb = MDL.robot[ri]; real *cs = s + MDL.o_cs + ri * RSB_CS_WORDS; const real *a = act + rb.act_off;
+    int ri = g.lane; const DevRobot &rb = MDL.robot[ri]; real *cs = s + MDL.o_cs + ri * MDL.cs_words; const real *a = act + rb.act_off;
     if (rb.ctrl_type == RSB_CTRL_OSC_POSE || rb.ctrl_type == RSB_CTRL_OSC_POSITION) {
       real d[6] = {0, 0, 0, 0, 0, 0}; for (int k = 0; k < rb.control_dim; k++) d[k] = scale_action(rb, k, a[k]);
       if (rb.ctrl_type == RSB_CTRL_OSC_POSE && (d[3] != 0 || d[4] != 0 || d[5] != 0)) {
@@ -903,7 +934,7 @@ RSB_DN void ctrl_run(int so, Grp g) { real *s = RSB_SMEM + so;
   real *ctrl = s + MDL.o_ctrl; real *scr = s + MDL.o_cscr;
   real *Jee = scr, *Lm = scr + 42, *X = scr + 91, *A = scr + 133, *F = scr + 169, *pose = scr + 175, *y = scr + 182, *w = scr + 188, *v6 = scr + 194, *tau = scr + 200;
   for (int ri = 0; ri < MDL.nrobot; ri++) {
-    const DevRobot &rb = MDL.robot[ri]; real *cs = s + MDL.o_cs + ri * RSB_CS_WORDS;
+    const DevRobot &rb = MDL.robot[ri]; real *cs = s + MDL.o_cs + ri * MDL.cs_words;
     if (rb.ctrl_type == RSB_CTRL_OSC_POSE || rb.ctrl_type == RSB_CTRL_OSC_POSITION) {
       int sb = MDL.site_body[rb.eef_site], root = MDL.body_root[sb]; const real *ep = sxpos + 3 * rb.eef_site;
       real off[3] = {ep[0] - xpos[3 * root], ep[1] - xpos[3 * root + 1], ep[2] - xpos[3 * root + 2]};
@@ -913,7 +944,7 @@ RSB_DN void ctrl_run(int so, Grp g) { real *s = RSB_SMEM + so;
           lv[0] = cdof[6 * d + 3] + t[0]; lv[1] = cdof[6 * d + 4] + t[1]; lv[2] = cdof[6 * d + 5] + t[2]; }
         for (int r = 0; r < 3; r++) { Jee[r * 7 + c] = lv[r]; Jee[(3 + r) * 7 + c] = wv[r]; }
       }
-      for (int i = g.lane; i < 49; i += RSB_LANES) { int r = i / 7, c = i - 7 * r; Lm[i] = M[rb.arm_dadr[r] * MDL.ldm + rb.arm_dadr[c]]; }
+      for (int i = g.lane; i < 49; i += RSB_LANES) { int r = i / 7, c = i - 7 * r; Lm[i] = msym(M, rb.arm_dadr[r], rb.arm_dadr[c]); }
       if (g.lane == 8) {                             /* site velocity = full Jacobian x qvel = body twist moved to the site */
         const real *cv = cvel + 6 * sb; real t[3]; cross3(t, cv, off);
         v6[0] = cv[3] + t[0]; v6[1] = cv[4] + t[1]; v6[2] = cv[5] + t[2]; v6[3] = cv[0]; v6[4] = cv[1]; v6[5] = cv[2];
@@ -950,7 +981,7 @@ RSB_DN void ctrl_run(int so, Grp g) { real *s = RSB_SMEM + so;
       if (g.lane < RSB_ARM_DOF) {
         int c = g.lane; real t = bias[rb.arm_dadr[c]];
         for (int r = 0; r < 6; r++) t += Jee[r * 7 + c] * (w[r] - y[r]);
-        for (int k = 0; k < 7; k++) t += M[rb.arm_dadr[c] * MDL.ldm + rb.arm_dadr[k]] * pose[k];
+        for (int k = 0; k < 7; k++) t += msym(M, rb.arm_dadr[c], rb.arm_dadr[k]) * pose[k];
         tau[c] = t;
       }
     } else if (rb.ctrl_type == RSB_CTRL_JOINT_VELOCITY) {
@@ -988,8 +1019,8 @@ RSB_DN void ctrl_run(int so, Grp g) { real *s = RSB_SMEM + so;
 
 /* ================================================================== actuation + smooth acceleration */
 RSB_DN void st_actuation(int so, Grp g) { real *s = RSB_SMEM + so;
-  const real *qpos = s + MDL.o_qpos, *qvel = s + MDL.o_qvel, *ctrl = s + MDL.o_ctrl, *bias = s + MDL.o_bias, *passive = s + MDL.o_passive, *M = s + MDL.o_M;
-  real *actf = s + MDL.o_actuator, *smooth = s + MDL.o_smooth, *qas = s + MDL.o_qacc_smooth, *L = s + MDL.o_L;
+  const real *qpos = s + MDL.o_qpos, *qvel = s + MDL.o_qvel, *ctrl = s + MDL.o_ctrl, *bias = s + MDL.o_bias, *passive = s + MDL.o_passive;
+  real *actf = s + MDL.o_actuator, *smooth = s + MDL.o_smooth, *qas = s + MDL.o_qacc_smooth;
   for (int d = g.lane; d < MDL.nv; d += RSB_LANES) {
     real f = 0;
     for (int a = 0; a < MDL.nu; a++) if (MDL.act_dof[a] == d) {
@@ -1001,10 +1032,14 @@ RSB_DN void st_actuation(int so, Grp g) { real *s = RSB_SMEM + so;
     }
     actf[d] = f; real sm = passive[d] - bias[d] + f; smooth[d] = sm; qas[d] = sm;
   }
-  for (int i = g.lane; i < MDL.nv * MDL.ldm; i += RSB_LANES) L[i] = M[i];
   gsync(g);
-  chol_factor(so + MDL.o_L, MDL.nv, MDL.ldm, g);
-  chol_solve(so + MDL.o_L, MDL.nv, MDL.ldm, so + MDL.o_qacc_smooth, g);
+}
+/* qacc_smooth = M^-1 qfrc_smooth.  Runs AFTER the constraint stage: the factor workspace overlays the poses / cdof that stage reads. */
+RSB_DN void st_smooth_acc(int so, Grp g) { real *s = RSB_SMEM + so; const real *M = s + MDL.o_M; real *L = s + MDL.o_L;
+  for (int i = g.lane; i < MDL.ntri; i += RSB_LANES) L[i] = M[i];
+  gsync(g);
+  chol_factor(so + MDL.o_L, MDL.nv, 0, g);
+  chol_solve(so + MDL.o_L, MDL.nv, 0, so + MDL.o_qacc_smooth, g);
 }
 
 /* ================================================================== A.3.7 constraint solver (Newton, exact line search) */
@@ -1104,30 +1139,34 @@ RSB_DN real solver_cost(int so, Grp g, int nefc, int qo) { real *s = RSB_SMEM + 
   real *dq = s + MDL.o_tmpv;                                       /* qacc - qacc_smooth */
   for (int i = g.lane; i < MDL.nv; i += RSB_LANES) dq[i] = qacc[i] - qas[i];
   gsync(g);
-  for (int i = g.lane; i < MDL.nv; i += RSB_LANES) gs += 0.5f * dq[i] * sdot(M + i * MDL.ldm, dq, MDL.nv);
+  for (int i = g.lane; i < MDL.nv; i += RSB_LANES) gs += 0.5f * dq[i] * symv_row(M, i, dq, MDL.nv);
   gsync(g);
   LsAcc a = efc_eval(so, g, nefc, 0.0f, 0);
   return gsum(g, gs + a.cost);
 }
 
 RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
-  int *misc = (int *)(s + MDL.o_misc); const int nefc = misc[MISC_NEFC], nv = MDL.nv, ldm = MDL.ldm, ldj = MDL.ldj;
-  real *qacc = s + MDL.o_qacc, *qas = s + MDL.o_qacc_smooth, *warm = s + MDL.o_warm, *qfc = s + MDL.o_qfc, *grad = s + MDL.o_grad, *search = s + MDL.o_search, *Mv = s + MDL.o_Mv, *tmpv = s + MDL.o_tmpv;
+  int *misc = (int *)(s + MDL.o_misc); const int nefc = misc[MISC_NEFC], nv = MDL.nv, ldj = MDL.ldj;
+  real *qacc = s + MDL.o_qacc, *qas = s + MDL.o_qacc_smooth, *warm = s + MDL.o_warm, *qfc = s + MDL.o_qfc, *grad = s + MDL.o_grad, *search = s + MDL.o_search, *tmpv = s + MDL.o_tmpv;
   const real *M = s + MDL.o_M, *J = s + MDL.o_J; real *H = s + MDL.o_L, *force = s + MDL.o_eforce, *ew = s + MDL.o_ew, *Jv = s + MDL.o_eJv, *jar = s + MDL.o_ejar;
   const real *con = s + MDL.o_con;
-  if (nefc == 0) {
+  if (!wany(nefc != 0)) {                             /* no group of this warp has constraint rows */
     for (int d = g.lane; d < nv; d += RSB_LANES) { qacc[d] = qas[d]; qfc[d] = 0; }
     if (g.lane == 0) misc[MISC_ITER] = 0;
     gsync(g); return;
   }
+  /* (an unconstrained group next to a constrained one runs the loop with nefc = 0: it starts from qacc_smooth, its gradient is exactly
+     0 and it is inactive from iteration 0 on, with qfc = 0 -- the same result as the early exit) */
   /* warm start: the cheaper of qacc_warmstart and qacc_smooth */
   real cw = solver_cost(so, g, nefc, so + MDL.o_warm); gsync(g);
   real cs0 = solver_cost(so, g, nefc, so + MDL.o_qacc_smooth); gsync(g);
   for (int d = g.lane; d < nv; d += RSB_LANES) { qacc[d] = (cw < cs0) ? warm[d] : qas[d]; tmpv[d] = 0; }
   gsync(g);
   const real scale = 1.0f / (MDL.meaninertia * (real)(nv > 1 ? nv : 1));
-  int iter = 0;
-  for (; iter < MDL.solver_iters; iter++) {
+  /* `active` is uniform within a group; every branch that encloses a shuffle tests a warp vote, so the groups of a warp stay converged.
+     A finished group keeps executing the body (recomputing identical residuals/forces for its unchanged qacc) until its neighbour is done. */
+  int iter = 0; bool active = true;
+  for (int it = 0; it < MDL.solver_iters; it++) {
     /* residual rows, forces, Hessian weights */
     for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] = sdot(J + r * ldj, qacc, nv) - (s + MDL.o_earef)[r];
     gsync(g);
@@ -1138,7 +1177,7 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
     gsync(g);
     real gn = 0;
     for (int d = g.lane; d < nv; d += RSB_LANES) {
-      real a = sdot(M + d * ldm, tmpv, nv);                         /* tmpv = qacc - qacc_smooth: difference first, exact 0 on unconstrained dofs */
+      real a = symv_row(M, d, tmpv, nv);                            /* tmpv = qacc - qacc_smooth: difference first, exact 0 on unconstrained dofs */
       real f = sdot_strided(J + d, ldj, force, nefc);
       a -= f; grad[d] = a; qfc[d] = f; gn += a * a;
     }
@@ -1146,19 +1185,20 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
 #ifdef RSB_EMU_TRACE
     if (g.lane == 0) printf("  it %d scaled|grad| %.3e\n", iter, scale * sqrtf(gn));
 #endif
-    if (scale * sqrtf(gn) < MDL.solver_tol) break;
+    if (active && scale * sqrtf(gn) < MDL.solver_tol) active = false;
+    if (!wany(active)) break;
     /* H = M + J^T W J (+ cone blocks), lower triangle only, one lane per entry (table tri_ij) */
     const int ncon_ = misc[MISC_NCON];
     for (int e = g.lane; e < MDL.ntri; e += RSB_LANES) {
       const int ij = MDL.tri_ij[e], i = ij >> 8, j = ij & 255;
-      real h = M[i * ldm + j];
+      real h = M[e];
       { real h1 = 0, h2 = 0, h3 = 0; int r = 0; const real *Ji = J + i, *Jj = J + j;      /* cone rows carry ew < 0: clamped to 0 here */
         for (; r + 4 <= nefc; r += 4) { real w0 = fmaxf(ew[r], 0.0f), w1 = fmaxf(ew[r + 1], 0.0f), w2 = fmaxf(ew[r + 2], 0.0f), w3 = fmaxf(ew[r + 3], 0.0f);
           real a0 = Ji[r * ldj], a1 = Ji[(r + 1) * ldj], a2 = Ji[(r + 2) * ldj], a3 = Ji[(r + 3) * ldj], b0 = Jj[r * ldj], b1 = Jj[(r + 1) * ldj], b2 = Jj[(r + 2) * ldj], b3 = Jj[(r + 3) * ldj];
           h += w0 * a0 * b0; h1 += w1 * a1 * b1; h2 += w2 * a2 * b2; h3 += w3 * a3 * b3; }
         for (; r < nefc; r++) h += fmaxf(ew[r], 0.0f) * Ji[r * ldj] * Jj[r * ldj];
         h += (h1 + h2) + h3; }
-      H[i * ldm + j] = h;
+      H[e] = h;
     }
     for (int c = 0; c < ncon_; c++) {                              /* sliding contacts (rare): add the dim x dim cone block, recomputed here */
       const real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr; const int adr = ci[CON_ADR]; if (adr < 0 || !(ew[adr] < 0)) continue;
@@ -1167,43 +1207,48 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
       for (int e = g.lane; e < MDL.ntri; e += RSB_LANES) {
         const int ij = MDL.tri_ij[e], i = ij >> 8, j = ij & 255; real h = 0;
         for (int a = 0; a < dim; a++) { real ja = J[(adr + a) * ldj + i]; if (ja != 0) for (int b = 0; b < dim; b++) h += hc[a * 4 + b] * ja * J[(adr + b) * ldj + j]; }
-        H[i * ldm + j] += h;
+        H[e] += h;
       }
     }
     gsync(g);
-    chol_factor(so + MDL.o_L, nv, ldm, g);
+    chol_factor(so + MDL.o_L, nv, 0, g);
     for (int d = g.lane; d < nv; d += RSB_LANES) search[d] = -grad[d];
     gsync(g);
-    chol_solve(so + MDL.o_L, nv, ldm, so + MDL.o_search, g);
+    chol_solve(so + MDL.o_L, nv, 0, so + MDL.o_search, g);
     /* directional quantities */
     real gq1 = 0, gq2 = 0;
-    for (int d = g.lane; d < nv; d += RSB_LANES) { real a = sdot(M + d * ldm, search, nv); Mv[d] = a; gq2 += search[d] * a; gq1 += search[d] * (grad[d] + qfc[d]); }
+    for (int d = g.lane; d < nv; d += RSB_LANES) { real a = symv_row(M, d, search, nv); gq2 += search[d] * a; gq1 += search[d] * (grad[d] + qfc[d]); }
     for (int r = g.lane; r < nefc; r += RSB_LANES) Jv[r] = sdot(J + r * ldj, search, nv);
     gq1 = gsum(g, gq1); gq2 = gsum(g, gq2);           /* gq1 = s.(M a - M a_s): slope of the Gauss term at alpha = 0 */
     gsync(g);
     /* exact line search on the convex 1-D cost: safeguarded Newton on its derivative */
-    real lo = 0, hi = -1, alpha = 0, d1_0 = 0;
-    for (int it = 0; it < MDL.ls_iters; it++) {
+    real lo = 0, hi = -1, alpha = 0, d1_0 = 0; bool ls = active;
+    for (int lit = 0; lit < MDL.ls_iters; lit++) {
+      if (!wany(ls)) break;
       LsAcc v = efc_eval(so, g, nefc, alpha, 2);
       real d1 = gq1 + alpha * gq2 + gsum(g, v.d1), d2 = gq2 + gsum(g, v.d2);
-      if (it == 0) d1_0 = fabsf(d1);
+      if (ls) {
+        if (lit == 0) d1_0 = fabsf(d1);
 #ifdef RSB_EMU_TRACE
-      if (g.lane == 0) printf("    ls %d alpha %.6g d1 %.3e d2 %.3e\n", it, alpha, d1, d2);
+        if (g.lane == 0) printf("    ls %d alpha %.6g d1 %.3e d2 %.3e\n", lit, alpha, d1, d2);
 #endif
-      if (fabsf(d1) <= 1e-4f * d1_0 + 1e-30f && it > 0) break;
-      if (it == 0 && !(d1 < -1e-10f / scale)) break;  /* Newton decrement below tolerance (or fp32 noise): converged */
-      if (d1 < 0) lo = alpha; else hi = alpha;
-      real an = d2 > RSB_MINVAL ? alpha - d1 / d2 : alpha;
-      if (hi >= 0 && (an <= lo || an >= hi)) an = 0.5f * (lo + hi);
-      else if (hi < 0 && an <= lo) an = lo > 0 ? 2 * lo : 1.0f;
-      if (an == alpha) break;
-      alpha = an;
+        if (fabsf(d1) <= 1e-4f * d1_0 + 1e-30f && lit > 0) ls = false;
+        else if (lit == 0 && !(d1 < -1e-10f / scale)) ls = false;  /* Newton decrement below tolerance (or fp32 noise): converged */
+        else {
+          if (d1 < 0) lo = alpha; else hi = alpha;
+          real an = d2 > RSB_MINVAL ? alpha - d1 / d2 : alpha;
+          if (hi >= 0 && (an <= lo || an >= hi)) an = 0.5f * (lo + hi);
+          else if (hi < 0 && an <= lo) an = lo > 0 ? 2 * lo : 1.0f;
+          if (an == alpha) ls = false; else alpha = an;
+        }
+      }
     }
-    if (alpha == 0) break;
-    for (int d = g.lane; d < nv; d += RSB_LANES) qacc[d] += alpha * search[d];
+    if (active && alpha == 0) active = false;
+    if (active) { for (int d = g.lane; d < nv; d += RSB_LANES) qacc[d] += alpha * search[d]; iter++; }
     gsync(g);
+    if (!wany(active)) break;
   }
-  if (iter == MDL.solver_iters) {                       /* forces must correspond to the final qacc */
+  if (wany(active)) {                                   /* iteration limit hit: forces must correspond to the final qacc (a no-op recomputation for a converged neighbour) */
     for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] = sdot(J + r * ldj, qacc, nv) - (s + MDL.o_earef)[r];
     gsync(g);
     efc_eval(so, g, nefc, 0.0f, 1);
@@ -1219,11 +1264,11 @@ RSB_DN void st_euler(int so, Grp g) { real *s = RSB_SMEM + so;
   real *qpos = s + MDL.o_qpos, *qvel = s + MDL.o_qvel, *warm = s + MDL.o_warm, *L = s + MDL.o_L, *tmpv = s + MDL.o_tmpv;
   const real *M = s + MDL.o_M, *qacc = s + MDL.o_qacc, *smooth = s + MDL.o_smooth, *qfc = s + MDL.o_qfc; const real h = MDL.timestep;
   if (MDL.any_damping) {
-    for (int i = g.lane; i < MDL.nv * MDL.ldm; i += RSB_LANES) { int r = i / MDL.ldm, c = i - r * MDL.ldm; L[i] = M[i] + ((r == c) ? h * MDL.dof_damping[r] : 0.0f); }
+    for (int e = g.lane; e < MDL.ntri; e += RSB_LANES) { const int ij = MDL.tri_ij[e], r = ij >> 8, c = ij & 255; L[e] = M[e] + ((r == c) ? h * MDL.dof_damping[r] : 0.0f); }
     for (int d = g.lane; d < MDL.nv; d += RSB_LANES) tmpv[d] = smooth[d] + qfc[d];
     gsync(g);
-    chol_factor(so + MDL.o_L, MDL.nv, MDL.ldm, g);
-    chol_solve(so + MDL.o_L, MDL.nv, MDL.ldm, so + MDL.o_tmpv, g);
+    chol_factor(so + MDL.o_L, MDL.nv, 0, g);
+    chol_solve(so + MDL.o_L, MDL.nv, 0, so + MDL.o_tmpv, g);
   } else { for (int d = g.lane; d < MDL.nv; d += RSB_LANES) tmpv[d] = qacc[d]; gsync(g); }
   for (int d = g.lane; d < MDL.nv; d += RSB_LANES) { qvel[d] += h * tmpv[d]; warm[d] = qacc[d]; }
   gsync(g);
@@ -1249,7 +1294,7 @@ RSB_D void substep(int so, Grp g, bool policy_step) {
   st_bias(so, g); RSB_CTA_SYNC();
   if (policy_step) ctrl_set_goal(so, g);
   ctrl_run(so, g); RSB_CTA_SYNC();
-  st_actuation(so, g); RSB_CTA_SYNC(); st_constraint(so, g); RSB_CTA_SYNC(); st_solve(so, g); RSB_CTA_SYNC(); st_euler(so, g); RSB_CTA_SYNC();
+  st_actuation(so, g); RSB_CTA_SYNC(); st_constraint(so, g); RSB_CTA_SYNC(); st_smooth_acc(so, g); st_solve(so, g); RSB_CTA_SYNC(); st_euler(so, g); RSB_CTA_SYNC();
 }
 
 RSB_D bool geom_in(const int *set, int n, int gm) { for (int i = 0; i < n; i++) if (set[i] == gm) return true; return false; }
@@ -1376,7 +1421,7 @@ RSB_D real obs_element(int so, int i) { const real *s = RSB_SMEM + so;
 RSB_D void load_state(int so, const real *st, Grp g) { real *s = RSB_SMEM + so;
   for (int i = g.lane; i < MDL.nq; i += RSB_LANES) s[MDL.o_qpos + i] = st[MDL.st_qpos + i];
   for (int i = g.lane; i < MDL.nv; i += RSB_LANES) { s[MDL.o_qvel + i] = st[MDL.st_qvel + i]; s[MDL.o_warm + i] = st[MDL.st_warm + i]; }
-  for (int i = g.lane; i < MDL.nrobot * RSB_CS_WORDS; i += RSB_LANES) s[MDL.o_cs + i] = st[MDL.st_cs + i];
+  for (int ri = 0; ri < MDL.nrobot; ri++) for (int i = g.lane; i < MDL.cs_words; i += RSB_LANES) s[MDL.o_cs + ri * MDL.cs_words + i] = st[MDL.st_cs + ri * RSB_CS_WORDS + i];
   for (int i = g.lane; i < MDL.nu; i += RSB_LANES) s[MDL.o_ctrl + i] = 0;
   if (g.lane < 7) s[MDL.o_bpose + g.lane] = st[MDL.st_bpose + g.lane];
   gsync(g);
@@ -1384,7 +1429,7 @@ RSB_D void load_state(int so, const real *st, Grp g) { real *s = RSB_SMEM + so;
 RSB_D void store_state(int so, real *st, Grp g) { const real *s = RSB_SMEM + so;
   for (int i = g.lane; i < MDL.nq; i += RSB_LANES) st[MDL.st_qpos + i] = s[MDL.o_qpos + i];
   for (int i = g.lane; i < MDL.nv; i += RSB_LANES) { st[MDL.st_qvel + i] = s[MDL.o_qvel + i]; st[MDL.st_warm + i] = s[MDL.o_warm + i]; }
-  for (int i = g.lane; i < MDL.nrobot * RSB_CS_WORDS; i += RSB_LANES) st[MDL.st_cs + i] = s[MDL.o_cs + i];
+  for (int ri = 0; ri < MDL.nrobot; ri++) for (int i = g.lane; i < MDL.cs_words; i += RSB_LANES) st[MDL.st_cs + ri * RSB_CS_WORDS + i] = s[MDL.o_cs + ri * MDL.cs_words + i];
   if (g.lane < 7) st[MDL.st_bpose + g.lane] = s[MDL.o_bpose + g.lane];
 }
 
@@ -1409,7 +1454,7 @@ RSB_D void env_step(int so, Grp g, real *st, const real *action, real *obs, real
 
 /* robosuite MujocoEnv.reset (hard_reset = False): sim.reset, noisy arm init, object placement, new controller, forward, obs.
    Randomness: Philox keyed (seed, env_id), stream 0, counter = episode*8 + block -- identical to the oracle's orc_reset. */
-RSB_D void env_reset(int so, Grp g, real *st, uint64_t seed, uint64_t env_id, real *obs) { real *s = RSB_SMEM + so;
+RSB_D void env_reset(int so, Grp g, real *st, uint64_t seed, uint64_t env_id, real *obs, bool commit) { real *s = RSB_SMEM + so;
   int episode = f2i(st[MDL.st_episode]);
   real *qpos = s + MDL.o_qpos;
   for (int i = g.lane; i < MDL.nq; i += RSB_LANES) qpos[i] = MDL.qpos0[i];
@@ -1452,6 +1497,7 @@ RSB_D void env_reset(int so, Grp g, real *st, uint64_t seed, uint64_t env_id, re
   gsync(g);
   st_kinematics(so, g);
   ctrl_reset(so, g);
+  if (!commit) return;                                /* masked-off or padding group: ran only to keep the warp converged */
   for (int i = g.lane; i < MDL.obs_dim; i += RSB_LANES) obs[i] = obs_element(so, i);
   store_state(so, st, g);
   if (g.lane == 0) { st[MDL.st_time] = i2f(0); st[MDL.st_episode] = i2f(episode + 1); }
@@ -1469,12 +1515,12 @@ RSB_D void dump_debug(int so, Grp g, real *out) { const real *s = RSB_SMEM + so;
   const int *misc = (const int *)(s + MDL.o_misc); int nv = MDL.nv, nc = MDL.ncon_max, ne = MDL.nefc_max;
   if (g.lane == 0) { out[0] = (real)misc[MISC_NCON]; out[1] = (real)misc[MISC_NEFC]; out[2] = (real)misc[MISC_ITER]; }
   real *o = out + 8;
-  for (int i = g.lane; i < nv * nv; i += RSB_LANES) o[i] = s[MDL.o_M + (i / nv) * MDL.ldm + i % nv];
+  for (int i = g.lane; i < nv * nv; i += RSB_LANES) o[i] = msym(s + MDL.o_M, i / nv, i % nv);
   o += nv * nv;
   const int vecs[8] = {MDL.o_bias, MDL.o_passive, MDL.o_actuator, MDL.o_qacc_smooth, MDL.o_qacc, MDL.o_qfc, MDL.o_smooth, MDL.o_warm};
   for (int k = 0; k < 8; k++) for (int i = g.lane; i < nv; i += RSB_LANES) o[k * nv + i] = s[vecs[k] + i];
   o += 8 * nv;
-  for (int i = g.lane; i < 14; i += RSB_LANES) o[i] = s[MDL.o_tau + i];
+  for (int i = g.lane; i < 14; i += RSB_LANES) o[i] = i < 7 * MDL.nrobot ? s[MDL.o_tau + i] : 0.0f;
   o += 14;
   for (int i = g.lane; i < nc * 16; i += RSB_LANES) { int c = i / 16, k = i % 16; const real *cr = s + MDL.o_con + c * RSB_CONW; const int *ci = (const int *)cr;
     real v = 0; if (c < misc[MISC_NCON]) { real fr[9] = {cr[3], cr[4], cr[5], 0, 0, 0, 0, 0, 0}; make_frame(fr);

@@ -57,7 +57,8 @@ typedef struct DevRobot {
 typedef struct DevModel {
   /* sizes */
   int nq, nv, nu, nbody, njnt, ngeom, nsite, npair, nmpair, nfl, nlimj, ncon_max, nefc_max;
-  int ldm, ldj;                /* leading dims of M/H (nv|1) and J (nv|1) */
+  int ldm, ldj;                /* ldm: unused (M, H and the factor are PACKED lower triangles, entry (i,j), j<=i, at i(i+1)/2+j); ldj: row length of J (nv|1) */
+  int cs_words;                /* controller state words per robot held in shared memory (21 for OSC laws, RSB_CS_WORDS otherwise) */
   int ntri, nvsh;              /* lower-triangle entry count nv(nv+1)/2 (table tri_ij = i<<8|j); log2 of the power of two >= nv */
   float timestep, gravity[3], impratio, meaninertia;
   int cone, any_damping, solver_iters, ls_iters;
@@ -257,17 +258,27 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
   d.st_time = w++; d.st_episode = w++; d.st_words = w;
   /* shared-memory layout.  Arrays are grouped by LIFETIME inside one physics substep, and groups that are never alive together
      share words (stage order: kinematics, inertia, crb, collision, bias, controller, actuation | constraint rows, solve, Euler):
-       P  persistent over the substep (state, poses needed late, cdof, M, force vectors, contact list, per-row D/aref/type)
-       A  kinematics/dynamics/controller temporaries, all dead once the actuation stage has run
+       P  persistent over the substep (state, M, force vectors, contact list, per-row D/aref/type)
+       K  body/site poses and cdof: read up to the constraint stage -> overlaid by the factor workspace L and the gradient
+       A  kinematics/dynamics/controller temporaries, all dead once the smooth forces are known
        J  the dense constraint Jacobian, written by the constraint stage -> overlays A
-       B  solver temporaries (factor workspace, cone blocks, per-row jar/Jv/force/weight; the constraint stage's pos/margin/R
-          temporaries overlay jar/Jv/force) */
+       B  solver temporaries (per-row jar/Jv/force/weight; the constraint stage's pos/margin/R temporaries overlay jar/Jv/force)
+     The whole record is sized so that 28 Lift-Panda environments fit one SM (4096 envs = one wave on 148 SMs). */
   int o = 0; int nb = d.nbody, nv = d.nv, nj = d.njnt, ne = nefc_max, nc = ncon_max;
+  d.cs_words = 21;                                   /* goal_pos3 goal_ori9 initial_joint7 grip_cur2: all an OSC law keeps */
+  for (int r = 0; r < t->nrobot; r++) if (t->robot[r].ctrl_type != RSB_CTRL_OSC_POSE && t->robot[r].ctrl_type != RSB_CTRL_OSC_POSITION) d.cs_words = RSB_CS_WORDS;
 #define L(name, n) d.name = o; o += (n)
-  L(o_qpos, d.nq); L(o_qvel, nv); L(o_warm, nv); L(o_ctrl, d.nu > 0 ? d.nu : 1); L(o_cs, d.nrobot * RSB_CS_WORDS + 1); L(o_act, d.act_dim + 1); L(o_bpose, 7);
-  L(o_xpos, 3 * nb); L(o_sxpos, 3 * d.nsite + 1); L(o_sxmat, 9 * d.nsite + 1); L(o_cdof, 6 * nv); L(o_M, nv * d.ldm);
-  L(o_bias, nv); L(o_actuator, nv); L(o_smooth, nv); L(o_qacc_smooth, nv); L(o_qacc, nv); L(o_qfc, nv); L(o_tau, 7 * RSB_MAX_ROBOTS);
+  L(o_qpos, d.nq); L(o_qvel, nv); L(o_warm, nv); L(o_ctrl, d.nu > 0 ? d.nu : 1); L(o_cs, d.nrobot * d.cs_words); L(o_act, d.act_dim); L(o_bpose, 7);
+  L(o_M, d.ntri);
+  L(o_bias, nv); L(o_actuator, nv); L(o_smooth, nv); L(o_qacc_smooth, nv); L(o_qacc, nv); L(o_qfc, nv); L(o_tau, 7 * d.nrobot);
   L(o_con, nc * RSB_CONW); L(o_eD, ne); L(o_earef, ne); L(o_etype, ne); d.o_efloss = d.o_eid = 0; L(o_misc, 8);
+  /* group K: kinematic results the constraint stage still reads (contact Jacobian); dead afterwards, so the factor workspace and the
+     gradient (first written after the constraint stage) overlay them */
+  const int k0 = o;
+  L(o_xpos, 3 * nb); L(o_sxpos, 3 * d.nsite); L(o_sxmat, 9 * d.nsite); L(o_cdof, 6 * nv);
+  const int end_k = o;
+  o = k0; L(o_L, d.ntri); L(o_grad, nv);
+  if (o < end_k) o = end_k;
   const int r0 = o;
   /* group A */
   L(o_xquat, 4 * nb); L(o_passive, nv); L(o_gxpos, 3 * d.ngeom + 1); L(o_gxmat, 9 * d.ngeom + 1); L(o_cvel, 6 * nb);
@@ -281,8 +292,8 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
   d.o_J = r0; const int end_j = r0 + ne * d.ldj;
   o = end_a > end_j ? end_a : end_j;
   /* group B */
-  L(o_L, nv * d.ldm); d.o_Hc = 0; L(o_ejar, ne); L(o_eJv, ne); L(o_eforce, ne); L(o_ew, ne);
-  L(o_grad, nv); L(o_search, nv); L(o_Mv, nv); L(o_tmpv, nv);
+  d.o_Hc = 0; L(o_ejar, ne); L(o_eJv, ne); L(o_eforce, ne); L(o_ew, ne);
+  L(o_search, nv); L(o_tmpv, nv); d.o_Mv = d.o_tmpv;
   d.o_epos = d.o_ejar; d.o_emargin = d.o_eJv; d.o_eR = d.o_eforce;
 #undef L
   d.smem_words = (o + 3) & ~3;

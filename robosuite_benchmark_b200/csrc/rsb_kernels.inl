@@ -29,9 +29,9 @@ k_step(float *__restrict__ state, const float *__restrict__ actions, float *__re
 __global__ void __launch_bounds__(RSB_MAX_THREADS)
 k_reset(float *__restrict__ state, const unsigned char *__restrict__ mask, float *__restrict__ obs, uint64_t seed, uint64_t env_id_base, int n) {
   int w; Grp g = make_group(w); const int env = blockIdx.x * (blockDim.x / RSB_LANES) + w;
-  if (env >= n) return;
-  if (mask && !mask[env]) return;
-  env_reset(w * c_model.smem_words, g, state + (size_t)env * c_model.st_words, seed, env_id_base + (uint64_t)env, obs + (size_t)env * c_model.obs_dim);
+  const int e = env < n ? env : n - 1; const bool commit = env < n && (!mask || mask[e]);
+  if (!__any_sync(0xffffffffu, commit)) return;       /* whole warp idle; otherwise an idle group shadows its env without storing */
+  env_reset(w * c_model.smem_words, g, state + (size_t)e * c_model.st_words, seed, env_id_base + (uint64_t)e, obs + (size_t)e * c_model.obs_dim, commit);
 }
 
 __global__ void __launch_bounds__(RSB_MAX_THREADS)

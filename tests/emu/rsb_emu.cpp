@@ -88,7 +88,7 @@ void emu_set_state(void *h, const float *in) { EmuEnv *e = (EmuEnv *)h; memcpy(e
 void emu_reset(void *h, uint64_t seed, uint64_t env_id, float *obs) {
   EmuEnv *e = (EmuEnv *)h;
   emu_model = e->dm; emu_smem = e->smem.data();
-  run_group([&](int lane) { Grp g{lane, (RSB_LANES == 32) ? 0xffffffffu : ((1u << RSB_LANES) - 1u)}; env_reset(0, g, e->state.data(), seed, env_id, obs); });
+  run_group([&](int lane) { Grp g{lane, (RSB_LANES == 32) ? 0xffffffffu : ((1u << RSB_LANES) - 1u)}; env_reset(0, g, e->state.data(), seed, env_id, obs, true); });
 }
 int emu_step(void *h, const float *action, float *obs, float *reward) {
   EmuEnv *e = (EmuEnv *)h; unsigned char done = 0;
