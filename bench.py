@@ -218,16 +218,31 @@ def run_ours(args):
     ms_total = max_over_ranks(ms, dev)
     value = whole_job_rate(E * args.steps, world, ms_total / 1000.0)
 
-    # ---- end-to-end through the host-buffer C-ABI call (pinned host actions in; obs/reward/done out), every step
-    h_act = torch.empty(E, sim.act_dim, pin_memory=True)
-    h_act.copy_(act)
+    # ---- end-to-end through the host-buffer C-ABI call (pinned host actions in; obs/reward/done out), every step.
+    # The host action batches continue the same Philox stream as the device-timed region (a constant action would drive the arms
+    # into their limits and time a different workload); they are generated before the timed region and sit in pinned host memory.
     e2e_steps = max(5, min(args.steps, 50))
-    for _ in range(3):
-        sim.step_host(h_act.numpy())
+    h_acts = torch.empty(e2e_steps + 3, E, sim.act_dim, pin_memory=True)
+    for k in range(e2e_steps + 3):
+        sim.random_actions(step_idx + k, out=act)
+        h_acts[k].copy_(act)
+    torch.cuda.synchronize()
+    h_np = h_acts.numpy()
+
+    def host_step(k):
+        nonlocal step_idx
+        out = sim.step_host(h_np[k])
+        step_idx += 1
+        if step_idx % HORIZON == 0:
+            sim.reset(obs=obs)
+        return out
+
+    for k in range(3):
+        host_step(k)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        o_h, r_h, d_h = sim.step_host(h_act.numpy())
+    for k in range(e2e_steps):
+        o_h, r_h, d_h = host_step(3 + k)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_value = whole_job_rate(E * e2e_steps, world, max_over_ranks(e2e_s, dev))

@@ -40,7 +40,7 @@ extern DevModel emu_model;                 /* the harness sets these before runn
 extern float *emu_smem;
 #define MDL emu_model
 #define RSB_SMEM emu_smem
-#define RSB_CTA_SYNC() ((void)0)
+#define RSB_CTA_SYNC(k) ((void)0)
 RSB_D void gsync(Grp) { emu_sync(); }
 RSB_D real gshfl(Grp, real v, int src) { return emu_shfl_f(v, src); }
 RSB_D int gshfl_i(Grp, int v, int src) { return emu_shfl_i(v, src); }
@@ -51,6 +51,7 @@ RSB_D int gshfl_up_i(Grp g, int v, int d) { return emu_shfl_i(v, g.lane >= d ? g
 RSB_D void rsb_sincos(real x, real *s, real *c) { *s = sinf(x); *c = cosf(x); }
 RSB_D real rsb_rsqrt(real x) { return 1.0f / sqrtf(x); }
 RSB_D bool wany(bool p) { return p; }                          /* the emulator runs one group at a time */
+RSB_D bool sany(bool p) { return p; }
 RSB_D int f2i(real f) { int i; memcpy(&i, &f, 4); return i; }
 RSB_D real i2f(int i) { real f; memcpy(&f, &i, 4); return f; }
 RSB_D uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
@@ -67,9 +68,9 @@ extern __shared__ float rsb_smem[];
 #define MDL c_model
 #define RSB_SMEM rsb_smem
 #ifdef RSB_LOCKSTEP
-#define RSB_CTA_SYNC() __syncthreads()       /* keep the CTA's warps in the same stage: they share instruction fetches */
+#define RSB_CTA_SYNC(k) do { if (MDL.lockstep & (1 << (k))) __syncthreads(); } while (0)     /* keep the CTA's warps in the same stage: they share instruction fetches */
 #else
-#define RSB_CTA_SYNC() ((void)0)
+#define RSB_CTA_SYNC(k) ((void)0)
 #endif
 /* WARP-UNIFORM CONTROL FLOW: the groups of a warp (two 16-lane groups, or one 32-lane group) always execute every shuffle / warp
    barrier together, so the member mask is the compile-time constant 0xffffffff and a shuffle is ONE instruction (a run-time mask costs
@@ -84,6 +85,9 @@ RSB_D int gshfl_xor_i(Grp, int v, int x) { return __shfl_xor_sync(RSB_FULL, v, x
 RSB_D real gshfl_up(Grp, real v, int d) { return __shfl_up_sync(RSB_FULL, v, d, RSB_LANES); }
 RSB_D int gshfl_up_i(Grp, int v, int d) { return __shfl_up_sync(RSB_FULL, v, d, RSB_LANES); }
 RSB_D bool wany(bool p) { return __any_sync(RSB_FULL, p) != 0; }
+/* solver vote: with lockstep bit 9 the whole CTA iterates together (a finished warp would wait at the stage barrier anyway, and
+   iterating together keeps the CTA on one instruction stream); otherwise a warp vote */
+RSB_D bool sany(bool p) { return (c_model.lockstep & 512) ? (__syncthreads_or(p) != 0) : (__any_sync(RSB_FULL, p) != 0); }
 RSB_D void rsb_sincos(real x, real *s, real *c) { sincosf(x, s, c); }
 RSB_D real rsb_rsqrt(real x) { real r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 RSB_D int f2i(real f) { return __float_as_int(f); }
@@ -1150,7 +1154,7 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
   real *qacc = s + MDL.o_qacc, *qas = s + MDL.o_qacc_smooth, *warm = s + MDL.o_warm, *qfc = s + MDL.o_qfc, *grad = s + MDL.o_grad, *search = s + MDL.o_search, *tmpv = s + MDL.o_tmpv;
   const real *M = s + MDL.o_M, *J = s + MDL.o_J; real *H = s + MDL.o_L, *force = s + MDL.o_eforce, *ew = s + MDL.o_ew, *Jv = s + MDL.o_eJv, *jar = s + MDL.o_ejar;
   const real *con = s + MDL.o_con;
-  if (!wany(nefc != 0)) {                             /* no group of this warp has constraint rows */
+  if (!sany(nefc != 0)) {                             /* no group of this warp has constraint rows */
     for (int d = g.lane; d < nv; d += RSB_LANES) { qacc[d] = qas[d]; qfc[d] = 0; }
     if (g.lane == 0) misc[MISC_ITER] = 0;
     gsync(g); return;
@@ -1186,7 +1190,7 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
     if (g.lane == 0) printf("  it %d scaled|grad| %.3e\n", iter, scale * sqrtf(gn));
 #endif
     if (active && scale * sqrtf(gn) < MDL.solver_tol) active = false;
-    if (!wany(active)) break;
+    if (!sany(active)) break;
     /* H = M + J^T W J (+ cone blocks), lower triangle only, one lane per entry (table tri_ij) */
     const int ncon_ = misc[MISC_NCON];
     for (int e = g.lane; e < MDL.ntri; e += RSB_LANES) {
@@ -1224,7 +1228,7 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
     /* exact line search on the convex 1-D cost: safeguarded Newton on its derivative */
     real lo = 0, hi = -1, alpha = 0, d1_0 = 0; bool ls = active;
     for (int lit = 0; lit < MDL.ls_iters; lit++) {
-      if (!wany(ls)) break;
+      if (!sany(ls)) break;
       LsAcc v = efc_eval(so, g, nefc, alpha, 2);
       real d1 = gq1 + alpha * gq2 + gsum(g, v.d1), d2 = gq2 + gsum(g, v.d2);
       if (ls) {
@@ -1246,9 +1250,9 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
     if (active && alpha == 0) active = false;
     if (active) { for (int d = g.lane; d < nv; d += RSB_LANES) qacc[d] += alpha * search[d]; iter++; }
     gsync(g);
-    if (!wany(active)) break;
+    if (!sany(active)) break;
   }
-  if (wany(active)) {                                   /* iteration limit hit: forces must correspond to the final qacc (a no-op recomputation for a converged neighbour) */
+  if (sany(active)) {                                   /* iteration limit hit: forces must correspond to the final qacc (a no-op recomputation for a converged neighbour) */
     for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] = sdot(J + r * ldj, qacc, nv) - (s + MDL.o_earef)[r];
     gsync(g);
     efc_eval(so, g, nefc, 0.0f, 1);
@@ -1290,11 +1294,11 @@ RSB_DN void st_euler(int so, Grp g) { real *s = RSB_SMEM + so;
 RSB_D void substep(int so, Grp g, bool policy_step) {
   /* order matters for the shared-memory overlays (rsb_devmodel.h): everything that reads the kinematics/dynamics temporaries runs
      before the constraint rows are built, because the Jacobian overlays them */
-  st_kinematics(so, g); RSB_CTA_SYNC(); st_inertia(so, g); st_crb(so, g); RSB_CTA_SYNC(); st_collision(so, g); RSB_CTA_SYNC();
-  st_bias(so, g); RSB_CTA_SYNC();
+  st_kinematics(so, g); RSB_CTA_SYNC(0); st_inertia(so, g); st_crb(so, g); RSB_CTA_SYNC(1); st_collision(so, g); RSB_CTA_SYNC(2);
+  st_bias(so, g); RSB_CTA_SYNC(3);
   if (policy_step) ctrl_set_goal(so, g);
-  ctrl_run(so, g); RSB_CTA_SYNC();
-  st_actuation(so, g); RSB_CTA_SYNC(); st_constraint(so, g); RSB_CTA_SYNC(); st_smooth_acc(so, g); st_solve(so, g); RSB_CTA_SYNC(); st_euler(so, g); RSB_CTA_SYNC();
+  ctrl_run(so, g); RSB_CTA_SYNC(4);
+  st_actuation(so, g); RSB_CTA_SYNC(5); st_constraint(so, g); RSB_CTA_SYNC(6); st_smooth_acc(so, g); st_solve(so, g); RSB_CTA_SYNC(7); st_euler(so, g); RSB_CTA_SYNC(8);
 }
 
 RSB_D bool geom_in(const int *set, int n, int gm) { for (int i = 0; i < n; i++) if (set[i] == gm) return true; return false; }
@@ -1443,7 +1447,7 @@ RSB_D void env_step(int so, Grp g, real *st, const real *action, real *obs, real
   for (int i = g.lane; i < MDL.act_dim; i += RSB_LANES) s[MDL.o_act + i] = action[i];
   gsync(g);
   for (int k = 0; k < MDL.substeps; k++) substep(so, g, k == 0);
-  st_kinematics(so, g); RSB_CTA_SYNC(); st_collision(so, g);   /* observations / reward read the post-step kinematics and contacts */
+  st_kinematics(so, g); RSB_CTA_SYNC(0); st_collision(so, g);   /* observations / reward read the post-step kinematics and contacts */
   if (!commit) return;                               /* padding warp of the last CTA: ran only to reach the barriers */
   if (finished) { if (g.lane == 0) { *done = 2; *reward = 0; } return; }      /* state untouched; host raises ValueError */
   real r = task_reward(so);

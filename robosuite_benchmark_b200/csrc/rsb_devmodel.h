@@ -58,6 +58,7 @@ typedef struct DevModel {
   /* sizes */
   int nq, nv, nu, nbody, njnt, ngeom, nsite, npair, nmpair, nfl, nlimj, ncon_max, nefc_max;
   int ldm, ldj;                /* ldm: unused (M, H and the factor are PACKED lower triangles, entry (i,j), j<=i, at i(i+1)/2+j); ldj: row length of J (nv|1) */
+  int lockstep;                /* bit k: CTA barrier after stage k (all warps of a CTA fetch the same code together) */
   int cs_words;                /* controller state words per robot held in shared memory (21 for OSC laws, RSB_CS_WORDS otherwise) */
   int ntri, nvsh;              /* lower-triangle entry count nv(nv+1)/2 (table tri_ij = i<<8|j); log2 of the power of two >= nv */
   float timestep, gravity[3], impratio, meaninertia;
@@ -154,7 +155,7 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
   d.ncon_max = ncon_max; d.nefc_max = nefc_max; d.ldm = m->nv | 1; d.ldj = m->nv | 1;
   d.timestep = (float)m->timestep; for (int k = 0; k < 3; k++) d.gravity[k] = (float)m->gravity[k];
   d.impratio = (float)m->impratio; d.meaninertia = (float)m->meaninertia; d.cone = m->cone;
-  d.solver_iters = 12; d.ls_iters = 24; d.solver_tol = 1e-6f;
+  d.solver_iters = 12; d.ls_iters = 24; d.solver_tol = 1e-6f; d.lockstep = 0x1ff;
   /* bodies */
   std::vector<int> lastdof((size_t)m->nbody, -1), dofmask((size_t)m->nbody, 0);
   for (int b = 1; b < m->nbody; b++) {
