@@ -1169,7 +1169,7 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
   const real scale = 1.0f / (MDL.meaninertia * (real)(nv > 1 ? nv : 1));
   /* `active` is uniform within a group; every branch that encloses a shuffle tests a warp vote, so the groups of a warp stay converged.
      A finished group keeps executing the body (recomputing identical residuals/forces for its unchanged qacc) until its neighbour is done. */
-  int iter = 0; bool active = true;
+  int iter = 0; bool active = true, last = false;       /* last: the previous update improved the cost by less than the tolerance */
   for (int it = 0; it < MDL.solver_iters; it++) {
     /* residual rows, forces, Hessian weights */
     for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] = sdot(J + r * ldj, qacc, nv) - (s + MDL.o_earef)[r];
@@ -1189,7 +1189,7 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
 #ifdef RSB_EMU_TRACE
     if (g.lane == 0) printf("  it %d scaled|grad| %.3e\n", iter, scale * sqrtf(gn));
 #endif
-    if (active && scale * sqrtf(gn) < MDL.solver_tol) active = false;
+    if (active && (last || scale * sqrtf(gn) < MDL.solver_tol)) active = false;      /* mj_solNewton: stop on small gradient OR small improvement */
     if (!sany(active)) break;
     /* H = M + J^T W J (+ cone blocks), lower triangle only, one lane per entry (table tri_ij) */
     const int ncon_ = misc[MISC_NCON];
@@ -1240,6 +1240,7 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
         else if (lit == 0 && !(d1 < -1e-10f / scale)) ls = false;  /* Newton decrement below tolerance (or fp32 noise): converged */
         else {
           if (d1 < 0) lo = alpha; else hi = alpha;
+          if (hi >= 0 && hi - lo <= 1e-4f * hi) ls = false;         /* bracket at fp32 resolution of the derivative: the sign of d1 is noise from here on */
           real an = d2 > RSB_MINVAL ? alpha - d1 / d2 : alpha;
           if (hi >= 0 && (an <= lo || an >= hi)) an = 0.5f * (lo + hi);
           else if (hi < 0 && an <= lo) an = lo > 0 ? 2 * lo : 1.0f;
@@ -1248,7 +1249,8 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
       }
     }
     if (active && alpha == 0) active = false;
-    if (active) { for (int d = g.lane; d < nv; d += RSB_LANES) qacc[d] += alpha * search[d]; iter++; }
+    if (active) { for (int d = g.lane; d < nv; d += RSB_LANES) qacc[d] += alpha * search[d]; iter++;
+      last = scale * 0.5f * alpha * d1_0 < MDL.solver_tol; }       /* cost decrease of an exact line search on a (locally) quadratic cost: alpha |d1(0)| / 2 */
     gsync(g);
     if (!sany(active)) break;
   }
