@@ -795,62 +795,46 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
 }
 
 /* ================================================================== dense Cholesky, one matrix row per lane (n <= RSB_LANES) */
-/* Right-looking factorisation with the row held in REGISTERS: lane i owns row i of the lower triangle; column j is scaled by the
-   broadcast pivot, then every trailing entry gets its rank-1 update from one shuffle + one FMA.  N(N+1)/2 shuffles, no shared-memory
-   traffic and no barriers until the factor is written back.  The factor is stored in place with the INVERSE pivots on the diagonal
-   (the solves only ever divide by them).  Pivots <= 1e-30 are dropped directions (pinv-like): inverse pivot 0. */
-template <int N> RSB_D void chol_factor_t(real *A, int n, int ld, Grp g) {
-  const int i = g.lane; real a[N]; real *Ai = A + (ld ? i * ld : tri_off(i));       /* ld == 0: packed lower triangle */
-#pragma unroll
-  for (int k = 0; k < N; k++) a[k] = (i < n && k <= i) ? Ai[k] : ((k == i) ? 1.0f : 0.0f);   /* identity padding up to N: no size tests below */
-#pragma unroll
-  for (int j = 0; j < N; j++) {
-    real sj = gshfl(g, a[j], j);
-    real inv = sj > 1e-30f ? rsb_rsqrt(sj) : 0.0f;
-    real lij = (i == j) ? inv : a[j] * inv;                       /* lane j keeps 1/L_jj, lanes i > j keep L_ij */
-    a[j] = lij;
-#pragma unroll
-    for (int k = j + 1; k < N; k++) { real lkj = gshfl(g, a[j], k); a[k] -= lij * lkj; }   /* lane k supplies L_kj; rows i >= k use it */
-  }
-#pragma unroll
-  for (int k = 0; k < N; k++) if (i < n && k <= i) Ai[k] = a[k];
-  gsync(g);
-}
+/* COMPACT ON PURPOSE.  The step kernel is bound by instruction fetch (profiles/): straight-line code that does not fit the 32 KB
+   instruction cache streams from L2 at ~6 cycles per instruction, loops that fit run at issue rate.  A fully unrolled register-resident
+   factorisation (940 + 810 SASS instructions for n = 16, re-fetched at each of the 3-10 calls per substep) lost to these rolled loops
+   over shared memory (~150 instructions in total).
+   Left-looking (Cholesky-Crout): at column j lane i >= j forms s = A_ij - sum_{k<j} L_ik L_jk (a dot product of two rows: reads only),
+   lane j's value is the pivot.  The factor is stored in place with the INVERSE pivots on the diagonal (the solves only ever divide by
+   them); pivots <= 1e-30 are dropped directions (pinv-like): inverse pivot 0.  ld == 0 selects packed lower-triangular storage. */
 RSB_DN void chol_factor(int ao, int n, int ld, Grp g) { real *A = RSB_SMEM + ao;
-  if (n <= 8) chol_factor_t<8>(A, n, ld, g);
-  else if (n <= 12) chol_factor_t<12>(A, n, ld, g);
-#if RSB_LANES >= 32
-  else if (n <= 16) chol_factor_t<16>(A, n, ld, g);
-  else if (n <= 24) chol_factor_t<24>(A, n, ld, g);
-  else chol_factor_t<32>(A, n, ld, g);
-#else
-  else chol_factor_t<16>(A, n, ld, g);                            /* 16-lane groups serve models with nv <= 16 only (checked at create) */
-#endif
+  const int i = g.lane; real *Ai = A + (ld ? i * ld : tri_off(i)); const real *Aj = A;       /* Aj: row j */
+  for (int j = 0; j < n; j++) {
+    real s0 = 0, s1 = 0;
+    if (i >= j && i < n) {
+      s0 = Ai[j]; int k = 0;
+      for (; k + 2 <= j; k += 2) { s0 -= Ai[k] * Aj[k]; s1 -= Ai[k + 1] * Aj[k + 1]; }
+      if (k < j) s0 -= Ai[k] * Aj[k];
+      s0 += s1;
+    }
+    const real piv = gshfl(g, s0, j), inv = piv > 1e-30f ? rsb_rsqrt(piv) : 0.0f;
+    if (i >= j && i < n) Ai[j] = (i == j) ? inv : s0 * inv;
+    gsync(g);
+    Aj += ld ? ld : j + 1;
+  }
 }
-/* x <- A^-1 x with the factor of chol_factor (inverse pivots on the diagonal); x is a shared-memory vector of length n.  Lane i
-   preloads row i (forward sweep) and column i (backward sweep) of L, so the two dependent chains are shuffle + FMA only. */
-template <int N> RSB_D void chol_solve_t(const real *L, int n, int ld, real *x, Grp g) {
-  const int i = g.lane; const bool act = i < n; real row[N], col[N]; const real *Li = L + (ld ? i * ld : tri_off(i));
-#pragma unroll
-  for (int k = 0; k < N; k++) { row[k] = (act && k < i) ? Li[k] : 0.0f; col[k] = (act && k > i && k < n) ? L[(ld ? k * ld : (k * (k + 1)) / 2) + i] : 0.0f; }
+/* x <- A^-1 x with the factor of chol_factor; x is a shared-memory vector of length n.  Lane i walks row i (forward sweep) and column i
+   (backward sweep) of L; the dependent chain per step is one shuffle and one FMA. */
+RSB_DN void chol_solve(int lo_, int n, int ld, int xo, Grp g) { const real *L = RSB_SMEM + lo_; real *x = RSB_SMEM + xo;
+  const int i = g.lane; const bool act = i < n; const real *Li = L + (ld ? i * ld : tri_off(i));
   real b = act ? x[i] : 0.0f; const real dinv = act ? Li[i] : 0.0f;
-#pragma unroll
-  for (int k = 0; k < N; k++) { real xk = gshfl(g, b * dinv, k); b = (i == k) ? xk : b - row[k] * xk; }          /* forward: L y = b */
-#pragma unroll
-  for (int k = N - 1; k >= 0; k--) { real xk = gshfl(g, b * dinv, k); b = (i == k) ? xk : b - col[k] * xk; }     /* backward: L^T x = y */
+  for (int k = 0; k < n; k++) {                                   /* forward: L y = b */
+    const real lik = (act && k < i) ? Li[k] : 0.0f, xk = gshfl(g, b * dinv, k);
+    b = (i == k) ? xk : b - lik * xk;
+  }
+  const real *Lk = L + (ld ? (n - 1) * ld : tri_off(n - 1)) + i;  /* L[k][i], k = n-1 .. 0 */
+  for (int k = n - 1; k >= 0; k--) {                              /* backward: L^T x = y */
+    const real lki = (act && k > i) ? *Lk : 0.0f, xk = gshfl(g, b * dinv, k);
+    b = (i == k) ? xk : b - lki * xk;
+    Lk -= ld ? ld : k;
+  }
   if (act) x[i] = b;
   gsync(g);
-}
-RSB_DN void chol_solve(int lo_, int n, int ld, int xo, Grp g) { const real *L = RSB_SMEM + lo_; real *x = RSB_SMEM + xo;
-  if (n <= 8) chol_solve_t<8>(L, n, ld, x, g);
-  else if (n <= 12) chol_solve_t<12>(L, n, ld, x, g);
-#if RSB_LANES >= 32
-  else if (n <= 16) chol_solve_t<16>(L, n, ld, x, g);
-  else if (n <= 24) chol_solve_t<24>(L, n, ld, x, g);
-  else chol_solve_t<32>(L, n, ld, x, g);
-#else
-  else chol_solve_t<16>(L, n, ld, x, g);
-#endif
 }
 
 /* ================================================================== A.2 controllers */
@@ -1135,27 +1119,70 @@ RSB_D void cone_mid_block(const real *jar_c, real D, real mu, const real *fr, in
     }
 }
 
+/* ---- shared building blocks of the Newton solver.  Each is ONE non-inlined function: the solver loop then is ~1.5k instructions in
+   total and stays in the instruction cache across iterations (the envs that need 5-9 iterations are the kernel's critical path). */
+/* y[r] = J[r,:] . x (- aref[r]) for every constraint row (lane per row) */
+RSB_DN void efc_mulJ(int so, Grp g, int nefc, int xo, int yo, int sub_aref) { real *s = RSB_SMEM + so;
+  const real *J = s + MDL.o_J, *x = RSB_SMEM + xo, *earef = s + MDL.o_earef; real *y = RSB_SMEM + yo; const int nv = MDL.nv, ldj = MDL.ldj;
+#pragma unroll 1
+  for (int r = g.lane; r < nefc; r += RSB_LANES) { real v = sdot(J + r * ldj, x, nv); if (sub_aref) v -= earef[r]; y[r] = v; }
+  gsync(g);
+}
+/* lane d < nv: row d of the packed mass matrix times the shared-memory vector at vo (0 on the other lanes) */
+RSB_DN real mulM_lane(int so, Grp g, int vo) { const real *s = RSB_SMEM + so;
+  return g.lane < MDL.nv ? symv_row(s + MDL.o_M, g.lane, RSB_SMEM + vo, MDL.nv) : 0.0f;
+}
+/* lane d < nv: (J^T force)[d] */
+RSB_DN real mulJT_lane(int so, Grp g, int nefc) { const real *s = RSB_SMEM + so;
+  return g.lane < MDL.nv ? sdot_strided(s + MDL.o_J + g.lane, MDL.ldj, s + MDL.o_eforce, nefc) : 0.0f;
+}
+/* H = M + J^T W J (+ cone blocks) into the packed workspace at o_L, one lane per lower-triangle entry (table tri_ij) */
+RSB_DN void newton_hessian(int so, Grp g, int nefc) { real *s = RSB_SMEM + so;
+  const real *M = s + MDL.o_M, *J = s + MDL.o_J, *ew = s + MDL.o_ew, *con = s + MDL.o_con, *jar = s + MDL.o_ejar; real *H = s + MDL.o_L;
+  const int ldj = MDL.ldj, ncon = ((const int *)(s + MDL.o_misc))[MISC_NCON];
+#pragma unroll 1
+  for (int e = g.lane; e < MDL.ntri; e += RSB_LANES) {
+    const int ij = MDL.tri_ij[e], i = ij >> 8, j = ij & 255;
+    real h = M[e], h1 = 0; int r = 0; const real *Ji = J + i, *Jj = J + j;          /* cone rows carry ew < 0: clamped to 0 here */
+#pragma unroll 1
+    for (; r + 2 <= nefc; r += 2) { real w0 = fmaxf(ew[r], 0.0f), w1 = fmaxf(ew[r + 1], 0.0f);
+      h += w0 * Ji[r * ldj] * Jj[r * ldj]; h1 += w1 * Ji[(r + 1) * ldj] * Jj[(r + 1) * ldj]; }
+    if (r < nefc) h += fmaxf(ew[r], 0.0f) * Ji[r * ldj] * Jj[r * ldj];
+    H[e] = h + h1;
+  }
+#pragma unroll 1
+  for (int c = 0; c < ncon; c++) {                                /* sliding contacts (rare): add the dim x dim cone block, recomputed here */
+    const real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr; const int adr = ci[CON_ADR]; if (adr < 0 || !(ew[adr] < 0)) continue;
+    const int dim = CON_DIM_OF(ci); real hc[16];
+    cone_mid_block(jar + adr, (s + MDL.o_eD)[adr], cr[CON_MU], MDL.pair_friction + 5 * ci[CON_PAIR], dim, hc);
+#pragma unroll 1
+    for (int e = g.lane; e < MDL.ntri; e += RSB_LANES) {
+      const int ij = MDL.tri_ij[e], i = ij >> 8, j = ij & 255; real h = 0;
+      for (int a = 0; a < dim; a++) { real ja = J[(adr + a) * ldj + i]; if (ja != 0) for (int b = 0; b < dim; b++) h += hc[a * 4 + b] * ja * J[(adr + b) * ldj + j]; }
+      H[e] += h;
+    }
+  }
+  gsync(g);
+}
+
 /* jar = J qacc - aref (lane per row); returns the total cost (Gauss + constraint), identical on all lanes */
 RSB_DN real solver_cost(int so, Grp g, int nefc, int qo) { real *s = RSB_SMEM + so; const real *qacc = RSB_SMEM + qo;
-  const real *J = s + MDL.o_J, *earef = s + MDL.o_earef, *M = s + MDL.o_M, *qas = s + MDL.o_qacc_smooth; real *jar = s + MDL.o_ejar;
-  for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] = sdot(J + r * MDL.ldj, qacc, MDL.nv) - earef[r];
-  real gs = 0;
+  const real *qas = s + MDL.o_qacc_smooth;
+  efc_mulJ(so, g, nefc, qo, so + MDL.o_ejar, 1);
   real *dq = s + MDL.o_tmpv;                                       /* qacc - qacc_smooth */
-  for (int i = g.lane; i < MDL.nv; i += RSB_LANES) dq[i] = qacc[i] - qas[i];
+  if (g.lane < MDL.nv) dq[g.lane] = qacc[g.lane] - qas[g.lane];
   gsync(g);
-  for (int i = g.lane; i < MDL.nv; i += RSB_LANES) gs += 0.5f * dq[i] * symv_row(M, i, dq, MDL.nv);
+  real gs = mulM_lane(so, g, so + MDL.o_tmpv); if (g.lane < MDL.nv) gs *= 0.5f * dq[g.lane];
   gsync(g);
   LsAcc a = efc_eval(so, g, nefc, 0.0f, 0);
   return gsum(g, gs + a.cost);
 }
 
 RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
-  int *misc = (int *)(s + MDL.o_misc); const int nefc = misc[MISC_NEFC], nv = MDL.nv, ldj = MDL.ldj;
+  int *misc = (int *)(s + MDL.o_misc); const int nefc = misc[MISC_NEFC], nv = MDL.nv; const bool dl = g.lane < nv; const int d = g.lane;
   real *qacc = s + MDL.o_qacc, *qas = s + MDL.o_qacc_smooth, *warm = s + MDL.o_warm, *qfc = s + MDL.o_qfc, *grad = s + MDL.o_grad, *search = s + MDL.o_search, *tmpv = s + MDL.o_tmpv;
-  const real *M = s + MDL.o_M, *J = s + MDL.o_J; real *H = s + MDL.o_L, *force = s + MDL.o_eforce, *ew = s + MDL.o_ew, *Jv = s + MDL.o_eJv, *jar = s + MDL.o_ejar;
-  const real *con = s + MDL.o_con;
   if (!sany(nefc != 0)) {                             /* no group of this warp has constraint rows */
-    for (int d = g.lane; d < nv; d += RSB_LANES) { qacc[d] = qas[d]; qfc[d] = 0; }
+    if (dl) { qacc[d] = qas[d]; qfc[d] = 0; }
     if (g.lane == 0) misc[MISC_ITER] = 0;
     gsync(g); return;
   }
@@ -1164,103 +1191,71 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
   /* warm start: the cheaper of qacc_warmstart and qacc_smooth */
   real cw = solver_cost(so, g, nefc, so + MDL.o_warm); gsync(g);
   real cs0 = solver_cost(so, g, nefc, so + MDL.o_qacc_smooth); gsync(g);
-  for (int d = g.lane; d < nv; d += RSB_LANES) { qacc[d] = (cw < cs0) ? warm[d] : qas[d]; tmpv[d] = 0; }
+  if (dl) { qacc[d] = (cw < cs0) ? warm[d] : qas[d]; tmpv[d] = 0; }
   gsync(g);
   const real scale = 1.0f / (MDL.meaninertia * (real)(nv > 1 ? nv : 1));
   /* `active` is uniform within a group; every branch that encloses a shuffle tests a warp vote, so the groups of a warp stay converged.
      A finished group keeps executing the body (recomputing identical residuals/forces for its unchanged qacc) until its neighbour is done. */
-  int iter = 0; bool active = true, last = false;       /* last: the previous update improved the cost by less than the tolerance */
-  for (int it = 0; it < MDL.solver_iters; it++) {
+  int iter = 0; bool active = true, last = false;                  /* last: the previous update improved the cost by less than the tolerance */
+#pragma unroll 1
+  for (int it = 0; it <= MDL.solver_iters; it++) {
     /* residual rows, forces, Hessian weights */
-    for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] = sdot(J + r * ldj, qacc, nv) - (s + MDL.o_earef)[r];
-    gsync(g);
+    efc_mulJ(so, g, nefc, so + MDL.o_qacc, so + MDL.o_ejar, 1);
     efc_eval(so, g, nefc, 0.0f, 1);
+    if (dl) tmpv[d] = qacc[d] - qas[d];
     gsync(g);
-    /* gradient = M (qacc - qacc_smooth) - J^T f  (lane per dof) */
-    for (int d = g.lane; d < nv; d += RSB_LANES) tmpv[d] = qacc[d] - qas[d];
-    gsync(g);
-    real gn = 0;
-    for (int d = g.lane; d < nv; d += RSB_LANES) {
-      real a = symv_row(M, d, tmpv, nv);                            /* tmpv = qacc - qacc_smooth: difference first, exact 0 on unconstrained dofs */
-      real f = sdot_strided(J + d, ldj, force, nefc);
-      a -= f; grad[d] = a; qfc[d] = f; gn += a * a;
-    }
-    gn = gsum(g, gn);
+    /* gradient = M (qacc - qacc_smooth) - J^T f  (lane per dof; the difference first: exact 0 on unconstrained dofs) */
+    real a = mulM_lane(so, g, so + MDL.o_tmpv), f = mulJT_lane(so, g, nefc);
+    a -= f; if (dl) { grad[d] = a; qfc[d] = f; }
+    const real gn = gsum(g, a * a);
 #ifdef RSB_EMU_TRACE
     if (g.lane == 0) printf("  it %d scaled|grad| %.3e\n", iter, scale * sqrtf(gn));
 #endif
-    if (active && (last || scale * sqrtf(gn) < MDL.solver_tol)) active = false;      /* mj_solNewton: stop on small gradient OR small improvement */
+    if (active && (last || it == MDL.solver_iters || scale * sqrtf(gn) < MDL.solver_tol)) active = false;      /* mj_solNewton: stop on small gradient OR small improvement (or the iteration limit) */
     if (!sany(active)) break;
-    /* H = M + J^T W J (+ cone blocks), lower triangle only, one lane per entry (table tri_ij) */
-    const int ncon_ = misc[MISC_NCON];
-    for (int e = g.lane; e < MDL.ntri; e += RSB_LANES) {
-      const int ij = MDL.tri_ij[e], i = ij >> 8, j = ij & 255;
-      real h = M[e];
-      { real h1 = 0, h2 = 0, h3 = 0; int r = 0; const real *Ji = J + i, *Jj = J + j;      /* cone rows carry ew < 0: clamped to 0 here */
-        for (; r + 4 <= nefc; r += 4) { real w0 = fmaxf(ew[r], 0.0f), w1 = fmaxf(ew[r + 1], 0.0f), w2 = fmaxf(ew[r + 2], 0.0f), w3 = fmaxf(ew[r + 3], 0.0f);
-          real a0 = Ji[r * ldj], a1 = Ji[(r + 1) * ldj], a2 = Ji[(r + 2) * ldj], a3 = Ji[(r + 3) * ldj], b0 = Jj[r * ldj], b1 = Jj[(r + 1) * ldj], b2 = Jj[(r + 2) * ldj], b3 = Jj[(r + 3) * ldj];
-          h += w0 * a0 * b0; h1 += w1 * a1 * b1; h2 += w2 * a2 * b2; h3 += w3 * a3 * b3; }
-        for (; r < nefc; r++) h += fmaxf(ew[r], 0.0f) * Ji[r * ldj] * Jj[r * ldj];
-        h += (h1 + h2) + h3; }
-      H[e] = h;
-    }
-    for (int c = 0; c < ncon_; c++) {                              /* sliding contacts (rare): add the dim x dim cone block, recomputed here */
-      const real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr; const int adr = ci[CON_ADR]; if (adr < 0 || !(ew[adr] < 0)) continue;
-      const int dim = CON_DIM_OF(ci); real hc[16];
-      cone_mid_block(jar + adr, (s + MDL.o_eD)[adr], cr[CON_MU], MDL.pair_friction + 5 * ci[CON_PAIR], dim, hc);
-      for (int e = g.lane; e < MDL.ntri; e += RSB_LANES) {
-        const int ij = MDL.tri_ij[e], i = ij >> 8, j = ij & 255; real h = 0;
-        for (int a = 0; a < dim; a++) { real ja = J[(adr + a) * ldj + i]; if (ja != 0) for (int b = 0; b < dim; b++) h += hc[a * 4 + b] * ja * J[(adr + b) * ldj + j]; }
-        H[e] += h;
-      }
-    }
-    gsync(g);
+    newton_hessian(so, g, nefc);
     chol_factor(so + MDL.o_L, nv, 0, g);
-    for (int d = g.lane; d < nv; d += RSB_LANES) search[d] = -grad[d];
+    if (dl) search[d] = -grad[d];
     gsync(g);
     chol_solve(so + MDL.o_L, nv, 0, so + MDL.o_search, g);
     /* directional quantities */
-    real gq1 = 0, gq2 = 0;
-    for (int d = g.lane; d < nv; d += RSB_LANES) { real a = symv_row(M, d, search, nv); gq2 += search[d] * a; gq1 += search[d] * (grad[d] + qfc[d]); }
-    for (int r = g.lane; r < nefc; r += RSB_LANES) Jv[r] = sdot(J + r * ldj, search, nv);
-    gq1 = gsum(g, gq1); gq2 = gsum(g, gq2);           /* gq1 = s.(M a - M a_s): slope of the Gauss term at alpha = 0 */
-    gsync(g);
-    /* exact line search on the convex 1-D cost: safeguarded Newton on its derivative */
-    real lo = 0, hi = -1, alpha = 0, d1_0 = 0; bool ls = active;
-    for (int lit = 0; lit < MDL.ls_iters; lit++) {
+    real gq1 = 0, gq2 = 0, sg = 0;
+    { real ms = mulM_lane(so, g, so + MDL.o_search); if (dl) { gq2 = search[d] * ms; gq1 = search[d] * (grad[d] + qfc[d]); sg = search[d] * grad[d]; } }
+    efc_mulJ(so, g, nefc, so + MDL.o_search, so + MDL.o_eJv, 0);
+    gq1 = gsum(g, gq1); gq2 = gsum(g, gq2); sg = gsum(g, sg);   /* gq1 = s.(M a - M a_s): slope of the Gauss term at alpha = 0; sg: slope of the total cost */
+    /* exact line search on the convex 1-D cost: safeguarded Newton on its derivative.  At alpha = 0 the slope is search.grad and, for the
+       Newton direction, the curvature is its negative (H search = -grad): the first trial step is 1, no evaluation at 0 is needed. */
+    real lo = 0, hi = -1, alpha = 0; const real d1_0 = fabsf(sg);
+    bool ls = active && (sg < -1e-10f / scale);                   /* else: Newton decrement below tolerance (or fp32 noise): converged */
+    if (ls) alpha = 1.0f;
+#pragma unroll 1
+    for (int lit = 1; lit < MDL.ls_iters; lit++) {
       if (!sany(ls)) break;
       LsAcc v = efc_eval(so, g, nefc, alpha, 2);
       real d1 = gq1 + alpha * gq2 + gsum(g, v.d1), d2 = gq2 + gsum(g, v.d2);
       if (ls) {
-        if (lit == 0) d1_0 = fabsf(d1);
 #ifdef RSB_EMU_TRACE
-        if (g.lane == 0) printf("    ls %d alpha %.6g d1 %.3e d2 %.3e\n", lit, alpha, d1, d2);
+        if (g.lane == 0) printf("    ls %d alpha %.6g d1 %.3e d2 %.3e (d1_0 %.3e)\n", lit, alpha, d1, d2, d1_0);
 #endif
-        if (fabsf(d1) <= 1e-4f * d1_0 + 1e-30f && lit > 0) ls = false;
-        else if (lit == 0 && !(d1 < -1e-10f / scale)) ls = false;  /* Newton decrement below tolerance (or fp32 noise): converged */
+        if (fabsf(d1) <= 1e-4f * d1_0 + 1e-30f) ls = false;
         else {
           if (d1 < 0) lo = alpha; else hi = alpha;
           if (hi >= 0 && hi - lo <= 1e-4f * hi) ls = false;         /* bracket at fp32 resolution of the derivative: the sign of d1 is noise from here on */
           real an = d2 > RSB_MINVAL ? alpha - d1 / d2 : alpha;
           if (hi >= 0 && (an <= lo || an >= hi)) an = 0.5f * (lo + hi);
-          else if (hi < 0 && an <= lo) an = lo > 0 ? 2 * lo : 1.0f;
-          if (an == alpha) ls = false; else alpha = an;
+          else if (hi < 0 && an <= lo) an = 2 * lo;
+          if (an == alpha) ls = false; else if (ls) alpha = an;
         }
       }
     }
     if (active && alpha == 0) active = false;
-    if (active) { for (int d = g.lane; d < nv; d += RSB_LANES) qacc[d] += alpha * search[d]; iter++;
+    if (active) { if (dl) qacc[d] += alpha * search[d]; iter++;
       last = scale * 0.5f * alpha * d1_0 < MDL.solver_tol; }       /* cost decrease of an exact line search on a (locally) quadratic cost: alpha |d1(0)| / 2 */
     gsync(g);
     if (!sany(active)) break;
   }
-  if (sany(active)) {                                   /* iteration limit hit: forces must correspond to the final qacc (a no-op recomputation for a converged neighbour) */
-    for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] = sdot(J + r * ldj, qacc, nv) - (s + MDL.o_earef)[r];
-    gsync(g);
-    efc_eval(so, g, nefc, 0.0f, 1);
-    gsync(g);
-    for (int d = g.lane; d < nv; d += RSB_LANES) qfc[d] = sdot_strided(J + d, ldj, force, nefc);
-  }
+  /* The loop evaluates forces at its top, so on every exit the forces correspond to the final qacc: an update is always followed by
+     another pass of the top part (the loop runs to it == solver_iters, where a still-active group is stopped before its next update). */
   if (g.lane == 0) misc[MISC_ITER] = iter;
   gsync(g);
 }
