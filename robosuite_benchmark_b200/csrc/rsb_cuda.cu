@@ -72,6 +72,8 @@ int rsb_create(const rsb_model *model, const rsb_task *task, int n_envs, int dev
   rsb_batch *b = new rsb_batch(); b->n = n_envs; b->device = device; b->seed = seed; b->env_id_base = env_id_base;
   b->dm = hm.dm;
   if (const char *e = getenv("RSB_LOCKSTEP")) b->dm.lockstep = (int)strtol(e, nullptr, 0);
+  if (const char *e = getenv("RSB_SOLVER_ITERS")) b->dm.solver_iters = atoi(e);        /* developer knobs (tools/): timing experiments only */
+  if (const char *e = getenv("RSB_LS_ITERS")) b->dm.ls_iters = atoi(e);
   /* lane-group width: 16 lanes (two envs per warp) when the model fits (nv <= 16), else one warp per env; RSB_LANES=32|16 overrides */
   b->kt = (hm.dm.nv <= 16) ? &rsb_table_16 : &rsb_table_32;
   if (const char *e = getenv("RSB_LANES")) { int v = atoi(e); if (v == 32) b->kt = &rsb_table_32; if (v == 16 && hm.dm.nv <= 16) b->kt = &rsb_table_16; }

@@ -807,10 +807,16 @@ RSB_DN void chol_factor(int ao, int n, int ld, Grp g) { real *A = RSB_SMEM + ao;
   for (int j = 0; j < n; j++) {
     real s0 = 0, s1 = 0;
     if (i >= j && i < n) {
-      s0 = Ai[j]; int k = 0;
-      for (; k + 2 <= j; k += 2) { s0 -= Ai[k] * Aj[k]; s1 -= Ai[k + 1] * Aj[k + 1]; }
-      if (k < j) s0 -= Ai[k] * Aj[k];
-      s0 += s1;
+      s0 = Ai[j]; int k = 0; real s2 = 0, s3 = 0;
+#pragma unroll 1
+      for (; k + 4 <= j; k += 4) {                                /* eight independent loads in flight, four independent accumulators */
+        const real a0 = Ai[k], a1 = Ai[k + 1], a2 = Ai[k + 2], a3 = Ai[k + 3], b0 = Aj[k], b1 = Aj[k + 1], b2 = Aj[k + 2], b3 = Aj[k + 3];
+        s0 -= a0 * b0; s1 -= a1 * b1; s2 -= a2 * b2; s3 -= a3 * b3; }
+      if (k < j) {                                                /* tail of 1-3 terms, loads issued together */
+        const bool p1 = k + 1 < j, p2 = k + 2 < j;
+        const real a0 = Ai[k], b0 = Aj[k], a1 = p1 ? Ai[k + 1] : 0.0f, b1 = p1 ? Aj[k + 1] : 0.0f, a2 = p2 ? Ai[k + 2] : 0.0f, b2 = p2 ? Aj[k + 2] : 0.0f;
+        s1 -= a0 * b0; s2 -= a1 * b1; s3 -= a2 * b2; }
+      s0 = (s0 + s1) + (s2 + s3);
     }
     const real piv = gshfl(g, s0, j), inv = piv > 1e-30f ? rsb_rsqrt(piv) : 0.0f;
     if (i >= j && i < n) Ai[j] = (i == j) ? inv : s0 * inv;
@@ -1136,31 +1142,39 @@ RSB_DN real mulM_lane(int so, Grp g, int vo) { const real *s = RSB_SMEM + so;
 RSB_DN real mulJT_lane(int so, Grp g, int nefc) { const real *s = RSB_SMEM + so;
   return g.lane < MDL.nv ? sdot_strided(s + MDL.o_J + g.lane, MDL.ldj, s + MDL.o_eforce, nefc) : 0.0f;
 }
-/* H = M + J^T W J (+ cone blocks) into the packed workspace at o_L, one lane per lower-triangle entry (table tri_ij) */
+/* H = M + J^T W J (+ cone blocks) into the packed workspace at o_L.  Lane j owns COLUMN j and keeps h[i] = sum_r w_r J_ri J_rj for all
+   i in registers: per constraint row one own-column load, then nv broadcast loads + FMAs (a lane-per-entry loop costs 8 passes over all
+   rows at nv = 15).  A sliding contact (ew < 0 marks its rows) adds J_c^T Hc J_c: t_a = sum_b Hc_ab J_bj first, then h[i] += J_ai t_a. */
 RSB_DN void newton_hessian(int so, Grp g, int nefc) { real *s = RSB_SMEM + so;
   const real *M = s + MDL.o_M, *J = s + MDL.o_J, *ew = s + MDL.o_ew, *con = s + MDL.o_con, *jar = s + MDL.o_ejar; real *H = s + MDL.o_L;
-  const int ldj = MDL.ldj, ncon = ((const int *)(s + MDL.o_misc))[MISC_NCON];
+  const int ldj = MDL.ldj, nv = MDL.nv, j = g.lane < nv ? g.lane : 0; const int *etid = (const int *)(s + MDL.o_etype);
+  real h[RSB_LANES];
+#pragma unroll
+  for (int i = 0; i < RSB_LANES; i++) h[i] = 0.0f;
 #pragma unroll 1
-  for (int e = g.lane; e < MDL.ntri; e += RSB_LANES) {
-    const int ij = MDL.tri_ij[e], i = ij >> 8, j = ij & 255;
-    real h = M[e], h1 = 0; int r = 0; const real *Ji = J + i, *Jj = J + j;          /* cone rows carry ew < 0: clamped to 0 here */
-#pragma unroll 1
-    for (; r + 2 <= nefc; r += 2) { real w0 = fmaxf(ew[r], 0.0f), w1 = fmaxf(ew[r + 1], 0.0f);
-      h += w0 * Ji[r * ldj] * Jj[r * ldj]; h1 += w1 * Ji[(r + 1) * ldj] * Jj[(r + 1) * ldj]; }
-    if (r < nefc) h += fmaxf(ew[r], 0.0f) * Ji[r * ldj] * Jj[r * ldj];
-    H[e] = h + h1;
-  }
-#pragma unroll 1
-  for (int c = 0; c < ncon; c++) {                                /* sliding contacts (rare): add the dim x dim cone block, recomputed here */
-    const real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr; const int adr = ci[CON_ADR]; if (adr < 0 || !(ew[adr] < 0)) continue;
-    const int dim = CON_DIM_OF(ci); real hc[16];
-    cone_mid_block(jar + adr, (s + MDL.o_eD)[adr], cr[CON_MU], MDL.pair_friction + 5 * ci[CON_PAIR], dim, hc);
-#pragma unroll 1
-    for (int e = g.lane; e < MDL.ntri; e += RSB_LANES) {
-      const int ij = MDL.tri_ij[e], i = ij >> 8, j = ij & 255; real h = 0;
-      for (int a = 0; a < dim; a++) { real ja = J[(adr + a) * ldj + i]; if (ja != 0) for (int b = 0; b < dim; b++) h += hc[a * 4 + b] * ja * J[(adr + b) * ldj + j]; }
-      H[e] += h;
+  for (int r = 0; r < nefc; r++) {
+    const real w = ew[r]; const real *Jr = J + r * ldj;
+    if (w > 0) {
+      const real t = w * Jr[j];
+#pragma unroll
+      for (int i = 0; i < RSB_LANES; i++) if (i < nv) h[i] += Jr[i] * t;
+    } else if (w < 0 && ET_TYPE(etid[r]) == EFC_CONTACT_NORMAL) {   /* first row of a contact in the middle zone of its cone */
+      const real *cr = con + ET_ID(etid[r]) * RSB_CONW; const int *ci = (const int *)cr; const int dim = CON_DIM_OF(ci); real hc[16], t[RSB_MAXDIM];
+      cone_mid_block(jar + r, (s + MDL.o_eD)[r], cr[CON_MU], MDL.pair_friction + 5 * ci[CON_PAIR], dim, hc);
+#pragma unroll
+      for (int a = 0; a < RSB_MAXDIM; a++) { real acc = 0;
+#pragma unroll
+        for (int b = 0; b < RSB_MAXDIM; b++) if (a < dim && b < dim) acc += hc[a * 4 + b] * Jr[b * ldj + j];
+        t[a] = acc; }
+#pragma unroll
+      for (int a = 0; a < RSB_MAXDIM; a++) if (a < dim) { const real *Ja = Jr + a * ldj;
+#pragma unroll
+        for (int i = 0; i < RSB_LANES; i++) if (i < nv) h[i] += Ja[i] * t[a]; }
     }
+  }
+  if (g.lane < nv) {
+#pragma unroll
+    for (int i = 0; i < RSB_LANES; i++) if (i < nv && i >= j) { const int e = tri_off(i) + j; H[e] = M[e] + h[i]; }
   }
   gsync(g);
 }
@@ -1237,7 +1251,7 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
 #ifdef RSB_EMU_TRACE
         if (g.lane == 0) printf("    ls %d alpha %.6g d1 %.3e d2 %.3e (d1_0 %.3e)\n", lit, alpha, d1, d2, d1_0);
 #endif
-        if (fabsf(d1) <= 1e-4f * d1_0 + 1e-30f) ls = false;
+        if (fabsf(d1) <= MDL.ls_tol * d1_0 + 1e-30f) ls = false;
         else {
           if (d1 < 0) lo = alpha; else hi = alpha;
           if (hi >= 0 && hi - lo <= 1e-4f * hi) ls = false;         /* bracket at fp32 resolution of the derivative: the sign of d1 is noise from here on */
@@ -1288,14 +1302,25 @@ RSB_DN void st_euler(int so, Grp g) { real *s = RSB_SMEM + so;
 /* ================================================================== one physics substep, the control step, reward, observation */
 /* Stage sequence of one physics substep.  RSB_CTA_SYNC() between stages keeps all warps of the CTA in the same stage
    (they then share instruction-cache lines: the whole step is far larger than the I-cache); it carries no data dependency. */
-RSB_D void substep(int so, Grp g, bool policy_step) {
+/* developer build (-DRSB_PROFILE, tools/stage_profile.py): cycles per stage and per barrier wait, accumulated per warp */
+#if defined(RSB_PROFILE) && !defined(RSB_EMU)
+#define RSB_PROF_SLOTS 16
+__device__ unsigned long long g_prof[8192 * RSB_PROF_SLOTS];
+#define PROF(k) do { long long n_ = clock64(); if ((threadIdx.x & 31) == 0) g_prof[(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RSB_PROF_SLOTS + (k)] += (unsigned long long)(n_ - pt_); pt_ = n_; } while (0)
+#define PROF_DECL long long pt_ = clock64()
+#else
+#define PROF(k) ((void)0)
+#define PROF_DECL long long pt_ = 0; (void)pt_
+#endif
+#define STAGE_SYNC(k) do { PROF(k); RSB_CTA_SYNC(k); PROF(15); } while (0)
+RSB_D void substep(int so, Grp g, bool policy_step, long long &pt_) {
   /* order matters for the shared-memory overlays (rsb_devmodel.h): everything that reads the kinematics/dynamics temporaries runs
      before the constraint rows are built, because the Jacobian overlays them */
-  st_kinematics(so, g); RSB_CTA_SYNC(0); st_inertia(so, g); st_crb(so, g); RSB_CTA_SYNC(1); st_collision(so, g); RSB_CTA_SYNC(2);
-  st_bias(so, g); RSB_CTA_SYNC(3);
+  st_kinematics(so, g); STAGE_SYNC(0); st_inertia(so, g); st_crb(so, g); STAGE_SYNC(1); st_collision(so, g); STAGE_SYNC(2);
+  st_bias(so, g); STAGE_SYNC(3);
   if (policy_step) ctrl_set_goal(so, g);
-  ctrl_run(so, g); RSB_CTA_SYNC(4);
-  st_actuation(so, g); RSB_CTA_SYNC(5); st_constraint(so, g); RSB_CTA_SYNC(6); st_smooth_acc(so, g); st_solve(so, g); RSB_CTA_SYNC(7); st_euler(so, g); RSB_CTA_SYNC(8);
+  ctrl_run(so, g); STAGE_SYNC(4);
+  st_actuation(so, g); STAGE_SYNC(5); st_constraint(so, g); STAGE_SYNC(6); st_smooth_acc(so, g); PROF(9); st_solve(so, g); STAGE_SYNC(7); st_euler(so, g); STAGE_SYNC(8);
 }
 
 RSB_D bool geom_in(const int *set, int n, int gm) { for (int i = 0; i < n; i++) if (set[i] == gm) return true; return false; }
@@ -1443,7 +1468,8 @@ RSB_D void env_step(int so, Grp g, real *st, const real *action, real *obs, real
   load_state(so, st, g);
   for (int i = g.lane; i < MDL.act_dim; i += RSB_LANES) s[MDL.o_act + i] = action[i];
   gsync(g);
-  for (int k = 0; k < MDL.substeps; k++) substep(so, g, k == 0);
+  PROF_DECL;
+  for (int k = 0; k < MDL.substeps; k++) substep(so, g, k == 0, pt_);
   st_kinematics(so, g); RSB_CTA_SYNC(0); st_collision(so, g);   /* observations / reward read the post-step kinematics and contacts */
   if (!commit) return;                               /* padding warp of the last CTA: ran only to reach the barriers */
   if (finished) { if (g.lane == 0) { *done = 2; *reward = 0; } return; }      /* state untouched; host raises ValueError */

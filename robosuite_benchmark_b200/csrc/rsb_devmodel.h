@@ -63,7 +63,7 @@ typedef struct DevModel {
   int ntri, nvsh;              /* lower-triangle entry count nv(nv+1)/2 (table tri_ij = i<<8|j); log2 of the power of two >= nv */
   float timestep, gravity[3], impratio, meaninertia;
   int cone, any_damping, solver_iters, ls_iters;
-  float solver_tol;
+  float solver_tol, ls_tol;     /* Newton: scaled gradient / improvement tolerance; line search: |slope| <= ls_tol * |slope at 0| */
   /* task */
   int task_id, nrobot, horizon, substeps, ignore_done, reward_shaping, obs_dim, act_dim;
   float reward_scale, init_noise, table_height;
@@ -155,7 +155,7 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
   d.ncon_max = ncon_max; d.nefc_max = nefc_max; d.ldm = m->nv | 1; d.ldj = m->nv | 1;
   d.timestep = (float)m->timestep; for (int k = 0; k < 3; k++) d.gravity[k] = (float)m->gravity[k];
   d.impratio = (float)m->impratio; d.meaninertia = (float)m->meaninertia; d.cone = m->cone;
-  d.solver_iters = 12; d.ls_iters = 24; d.solver_tol = 1e-6f; d.lockstep = 0x1ff;
+  d.solver_iters = 12; d.ls_iters = 24; d.solver_tol = 1e-6f; d.ls_tol = 1e-2f;   /* MuJoCo ls_tolerance default */ d.lockstep = 0x1ff;
   /* bodies */
   std::vector<int> lastdof((size_t)m->nbody, -1), dofmask((size_t)m->nbody, 0);
   for (int b = 1; b < m->nbody; b++) {

@@ -43,7 +43,8 @@ k_debug_substep(float *__restrict__ state, const float *__restrict__ actions, in
   load_state(so, st, g);
   for (int i = g.lane; i < m.act_dim; i += RSB_LANES) s[m.o_act + i] = actions[(size_t)e * m.act_dim + i];
   gsync(g);
-  substep(so, g, policy_step != 0);
+  PROF_DECL;
+  substep(so, g, policy_step != 0, pt_);
   if (!commit) return;
   dump_debug(so, g, dbg + (size_t)e * dbg_words);
   store_state(so, st, g);
@@ -76,3 +77,9 @@ void t_random(cudaStream_t st, uint64_t seed, uint64_t base, uint64_t step, int 
 }  // namespace
 
 extern const RsbKernelTable RSB_TABLE_NAME = {RSB_LANES, RSB_MAX_THREADS / RSB_LANES, t_bind, t_prepare, t_step, t_reset, t_debug, t_random};
+
+#if defined(RSB_PROFILE) && RSB_LANES == 16
+/* developer build only: read / clear the per-warp stage cycle counters */
+extern "C" int rsb_prof_read(unsigned long long *host_out, int nwords) { return (int)cudaMemcpyFromSymbol(host_out, g_prof, (size_t)nwords * 8); }
+extern "C" int rsb_prof_reset(void) { void *p; cudaGetSymbolAddress(&p, g_prof); return (int)cudaMemset(p, 0, sizeof(g_prof)); }
+#endif

@@ -80,6 +80,7 @@ void emu_set_order(int order) { S.order = order; }
 int emu_smem_words(void *h) { return ((EmuEnv *)h)->dm.smem_words; }
 int emu_state_words(void *h) { return ((EmuEnv *)h)->dm.st_words; }
 int emu_dbg_words(void *h) { return (int)((EmuEnv *)h)->dbg.size(); }
+void emu_set_ls_tol(void *h, float tol) { ((EmuEnv *)h)->dm.ls_tol = tol; }
 void emu_set_solver(void *h, int iters, int ls_iters, float tol) { EmuEnv *e = (EmuEnv *)h; e->dm.solver_iters = iters; e->dm.ls_iters = ls_iters; e->dm.solver_tol = tol; }
 
 void emu_get_state(void *h, float *out) { EmuEnv *e = (EmuEnv *)h; memcpy(out, e->state.data(), e->state.size() * 4); }
@@ -105,7 +106,7 @@ void emu_debug_substep(void *h, const float *action, int policy_step, float *dbg
     load_state(0, e->state.data(), g);
     for (int i = g.lane; i < m.act_dim; i += RSB_LANES) s[m.o_act + i] = action[i];
     gsync(g);
-    substep(0, g, policy_step != 0);
+    long long pt_ = 0; substep(0, g, policy_step != 0, pt_);
     dump_debug(0, g, dbg);
     store_state(0, e->state.data(), g);
   });

@@ -23,4 +23,5 @@ ms = [a.elapsed_time(b) for a, b in ev]
 for w in range(0, steps, 50):
     seg = ms[w:w + 50]
     print(f"steps {w:4d}-{w+len(seg)-1:4d}: mean {sum(seg)/len(seg):.3f} ms  min {min(seg):.3f} max {max(seg):.3f}  reward {rews[w//50] if w//50 < len(rews) else float('nan'):.4f}")
+print(f"steady (steps 100+) mean {sum(ms[100:])/max(1,len(ms[100:])):.3f} ms")
 print(f"overall mean {sum(ms)/len(ms):.3f} ms -> {E/(sum(ms)/len(ms))*1000:.0f} control-steps/s")

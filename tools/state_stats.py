@@ -21,7 +21,7 @@ for k in range(301):
         print("   iters hist", np.bincount(it.astype(int), minlength=13).tolist())
         print("   ncon hist", np.bincount(ncon.astype(int), minlength=17).tolist())
         if k == 150:
-            hard = np.nonzero(it >= 5)[0]
+            hard = np.nonzero(it >= 8)[0]
             np.savez("gpurun_out/stragglers.npz", idx=hard, state=st.cpu().numpy()[hard], act=act.cpu().numpy()[hard], iters=it[hard], ncon=ncon[hard], nefc=nefc[hard])
         sim.set_state(st)
     sim.step(act, obs, rew, done)
