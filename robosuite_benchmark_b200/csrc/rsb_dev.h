@@ -527,7 +527,10 @@ RSB_D int col_capsule_box(const real *cp, const real *cm, const real *cs, const 
 
 /* box-box: separating-axis test over 15 axes, then reference-face clipping (face case, <= 8 contacts) or the closest
    points of the two supporting edges (edge case, 1 contact).  Same contact generation rules as DESIGN.md "box-box". */
-RSB_DNOINL int col_box_box(const real *pa, const real *Ra, const real *ha, const real *pb, const real *Rb, const real *hb, real margin, RawCon *out) {
+/* `scr`: 48 words of scratch for the clipped polygon (two buffers of 8 vertices).  The caller passes a slice of shared memory when it
+   has one (a generic pointer): thread-local arrays with run-time indices live in local memory, which at 448 threads x 230 KB of shared
+   memory per SM no longer fits L1 and costs an L2 round trip per access (60% of this function's stall samples, profiles/). */
+RSB_DNOINL int col_box_box(const real *pa, const real *Ra, const real *ha, const real *pb, const real *Rb, const real *hb, real margin, RawCon *out, real *scr) {
   real R[9], Q[9], t[3], d[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { real v = Ra[i] * Rb[j] + Ra[3 + i] * Rb[3 + j] + Ra[6 + i] * Rb[6 + j]; R[3 * i + j] = v; Q[3 * i + j] = fabsf(v) + 1e-9f; }
   matTvec3(t, Ra, d);
@@ -579,31 +582,34 @@ RSB_DNOINL int col_box_box(const real *pa, const real *Ra, const real *ha, const
   real nl[3]; matTvec3(nl, Ri, nr); int ia = 0; real am = fabsf(nl[0]);
   for (int k = 1; k < 3; k++) if (fabsf(nl[k]) > am) { am = fabsf(nl[k]); ia = k; }
   real isg = nl[ia] > 0 ? -1.0f : 1.0f; int u = (ia + 1) % 3, v = (ia + 2) % 3;
-  real poly[16][3], tmp[16][3]; int np = 4;
+  real *poly = scr, *tmp = scr + 24; int np = 4;               /* a quad clipped by four half-planes has at most 8 vertices */
   for (int c = 0; c < 4; c++) {
-    real su = (c == 0 || c == 3) ? -1.0f : 1.0f, sv = (c < 2) ? -1.0f : 1.0f; real wv[3];
+    real su = (c == 0 || c == 3) ? -1.0f : 1.0f, sv = (c < 2) ? -1.0f : 1.0f; real wv[3], pv[3];
     for (int k = 0; k < 3; k++) wv[k] = pi[k] + isg * hi[ia] * Ri[3 * k + ia] + su * hi[u] * Ri[3 * k + u] + sv * hi[v] * Ri[3 * k + v] - pr[k];
-    matTvec3(poly[c], Rr, wv);
+    matTvec3(pv, Rr, wv); poly[3 * c] = pv[0]; poly[3 * c + 1] = pv[1]; poly[3 * c + 2] = pv[2];
   }
   int ru = (ax + 1) % 3, rv = (ax + 2) % 3;
   for (int side = 0; side < 4; side++) {
     int k = side < 2 ? ru : rv; real sg = (side & 1) ? -1.0f : 1.0f, lim = hr[k];
     int nn = 0;
     for (int c = 0; c < np; c++) {
-      const real *P = poly[c], *Qp = poly[(c + 1) % np];
-      real dp = sg * P[k] - lim, dq = sg * Qp[k] - lim;
-      if (dp <= 0) { tmp[nn][0] = P[0]; tmp[nn][1] = P[1]; tmp[nn][2] = P[2]; nn++; }
-      if ((dp < 0 && dq > 0) || (dp > 0 && dq < 0)) { real f = dp / (dp - dq); for (int x = 0; x < 3; x++) tmp[nn][x] = P[x] + f * (Qp[x] - P[x]); nn++; }
+      const int c1 = (c + 1 == np) ? 0 : c + 1;
+      const real P0 = poly[3 * c], P1 = poly[3 * c + 1], P2 = poly[3 * c + 2], Q0 = poly[3 * c1], Q1 = poly[3 * c1 + 1], Q2 = poly[3 * c1 + 2];
+      const real Pk = k == 0 ? P0 : (k == 1 ? P1 : P2), Qk = k == 0 ? Q0 : (k == 1 ? Q1 : Q2);
+      real dp = sg * Pk - lim, dq = sg * Qk - lim;
+      if (dp <= 0 && nn < 8) { tmp[3 * nn] = P0; tmp[3 * nn + 1] = P1; tmp[3 * nn + 2] = P2; nn++; }
+      if (((dp < 0 && dq > 0) || (dp > 0 && dq < 0)) && nn < 8) { real f = dp / (dp - dq); tmp[3 * nn] = P0 + f * (Q0 - P0); tmp[3 * nn + 1] = P1 + f * (Q1 - P1); tmp[3 * nn + 2] = P2 + f * (Q2 - P2); nn++; }
     }
-    np = nn; for (int c = 0; c < np; c++) { poly[c][0] = tmp[c][0]; poly[c][1] = tmp[c][1]; poly[c][2] = tmp[c][2]; }
+    np = nn; { real *t_ = poly; poly = tmp; tmp = t_; }            /* swap the buffers instead of copying back */
     if (np == 0) return 0;
   }
   int cnt = 0;
   real nout[3]; for (int k = 0; k < 3; k++) nout[k] = (code < 3) ? nr[k] : -nr[k];
   for (int c = 0; c < np && cnt < 8; c++) {
-    real depth = nsign * poly[c][ax] - hr[ax];
+    real pl[3] = {poly[3 * c], poly[3 * c + 1], poly[3 * c + 2]};
+    real depth = nsign * pl[ax] - hr[ax];
     if (depth > margin) continue;
-    real pl[3] = {poly[c][0], poly[c][1], poly[c][2]}; pl[ax] -= nsign * 0.5f * depth;
+    pl[ax] -= nsign * 0.5f * depth;
     RawCon *o = &out[cnt++]; real w[3]; matvec3(w, Rr, pl);
     o->dist = depth; for (int k = 0; k < 3; k++) { o->pos[k] = pr[k] + w[k]; o->normal[k] = nout[k]; }
   }
@@ -624,11 +630,32 @@ RSB_DNOINL int col_box_box(const real *pa, const real *Ra, const real *ha, const
 #define MISC_ITER 2
 #define MISC_NLIMROW 3
 
+/* Conservative box-pair cull (after the bounding spheres): the bounding sphere of one box against the other box itself, both ways.
+   A flat table has a bounding sphere of 0.57 m that every gripper geom is always inside; its slab is what matters. */
+RSB_D bool sphere_box_apart(const real *c, real r, const real *bp, const real *bm, const real *h, real margin) {
+  real d[3] = {c[0] - bp[0], c[1] - bp[1], c[2] - bp[2]}, l[3]; matTvec3(l, bm, d);
+  real ex = fmaxf(fabsf(l[0]) - h[0], 0.0f), ey = fmaxf(fabsf(l[1]) - h[1], 0.0f), ez = fmaxf(fabsf(l[2]) - h[2], 0.0f), rr = r + margin;
+  return ex * ex + ey * ey + ez * ez > rr * rr;
+}
+RSB_D bool box_pair_separated(const real *p1, const real *R1, const real *h1, real r1, const real *p2, const real *R2, const real *h2, real r2, real margin) {
+  real dv[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]}, bound = r1 + r2 + margin;
+  if (dot3(dv, dv) > bound * bound) return true;
+  return sphere_box_apart(p2, r2, p1, R1, h1, margin) || sphere_box_apart(p1, r1, p2, R2, h2, margin);
+}
+#define RSB_BB_SLOTS 4
 RSB_DN void st_collision(int so, Grp g) { real *s = RSB_SMEM + so;
   const real *gxpos = s + MDL.o_gxpos, *gxmat = s + MDL.o_gxmat; real *con = s + MDL.o_con; int *misc = (int *)(s + MDL.o_misc);
   int base = 0;
   for (int p0 = 0; p0 < MDL.npair; p0 += RSB_LANES) {
-    int p = p0 + g.lane; RawCon rc[9]; int n = 0; real inc = 0;
+    int p = p0 + g.lane; RawCon rc[9]; int n = 0; real inc = 0; bool bb = false;
+    /* broad phase first, for every lane, so that the box-box candidates can be handed shared-memory scratch by rank */
+    if (p < MDL.npair) {
+      int g1 = MDL.pair_g1[p], g2 = MDL.pair_g2[p], t1 = MDL.geom_type[g1], t2 = MDL.geom_type[g2];
+      bb = (t1 == RSB_GEOM_BOX && t2 == RSB_GEOM_BOX) && !box_pair_separated(gxpos + 3 * g1, gxmat + 9 * g1, MDL.geom_size + 3 * g1, MDL.geom_rbound[g1],
+                                                                               gxpos + 3 * g2, gxmat + 9 * g2, MDL.geom_size + 3 * g2, MDL.geom_rbound[g2], MDL.pair_margin[p]);
+    }
+    const int rank = gscan_incl(g, bb ? 1 : 0) - 1;                /* rank among this group's box-box candidates */
+    real lscr[48]; real *scr = (bb && rank < RSB_BB_SLOTS) ? s + MDL.o_cscr + 48 * rank : lscr;       /* o_cscr is free between the inertia and the controller stages */
     if (p < MDL.npair) {
       int g1 = MDL.pair_g1[p], g2 = MDL.pair_g2[p], t1 = MDL.geom_type[g1], t2 = MDL.geom_type[g2];
       real margin = MDL.pair_margin[p]; const real *p1 = gxpos + 3 * g1, *p2 = gxpos + 3 * g2, *R1 = gxmat + 9 * g1, *R2 = gxmat + 9 * g2;
@@ -645,7 +672,7 @@ RSB_DN void st_collision(int so, Grp g) { real *s = RSB_SMEM + so;
         else if (t1 == RSB_GEOM_SPHERE && t2 == RSB_GEOM_BOX) n = col_sphere_box(p1, s1[0], p2, R2, s2, margin, rc);
         else if (t1 == RSB_GEOM_CAPSULE && t2 == RSB_GEOM_CAPSULE) n = col_capsule_capsule(p1, R1, s1, p2, R2, s2, margin, rc);
         else if (t1 == RSB_GEOM_CAPSULE && t2 == RSB_GEOM_BOX) n = col_capsule_box(p1, R1, s1, p2, R2, s2, margin, rc);
-        else if (t1 == RSB_GEOM_BOX && t2 == RSB_GEOM_BOX) n = col_box_box(p1, R1, s1, p2, R2, s2, margin, rc);
+        else if (bb) n = col_box_box(p1, R1, s1, p2, R2, s2, margin, rc, scr);
       }
       inc = margin - MDL.pair_gap[p];
       int keep = 0;                                 /* active contacts only: dist < includemargin; compact in place */
