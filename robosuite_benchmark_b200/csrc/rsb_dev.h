@@ -822,37 +822,58 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
 }
 
 /* ================================================================== dense Cholesky, one matrix row per lane (n <= RSB_LANES) */
-/* COMPACT ON PURPOSE.  The step kernel is bound by instruction fetch (profiles/): straight-line code that does not fit the 32 KB
-   instruction cache streams from L2 at ~6 cycles per instruction, loops that fit run at issue rate.  A fully unrolled register-resident
-   factorisation (940 + 810 SASS instructions for n = 16, re-fetched at each of the 3-10 calls per substep) lost to these rolled loops
-   over shared memory (~150 instructions in total).
-   Left-looking (Cholesky-Crout): at column j lane i >= j forms s = A_ij - sum_{k<j} L_ik L_jk (a dot product of two rows: reads only),
-   lane j's value is the pivot.  The factor is stored in place with the INVERSE pivots on the diagonal (the solves only ever divide by
-   them); pivots <= 1e-30 are dropped directions (pinv-like): inverse pivot 0.  ld == 0 selects packed lower-triangular storage. */
-RSB_DN void chol_factor(int ao, int n, int ld, Grp g) { real *A = RSB_SMEM + ao;
-  const int i = g.lane; real *Ai = A + (ld ? i * ld : tri_off(i)); const real *Aj = A;       /* Aj: row j */
-  for (int j = 0; j < n; j++) {
-    real s0 = 0, s1 = 0;
-    if (i >= j && i < n) {
-      s0 = Ai[j]; int k = 0; real s2 = 0, s3 = 0;
-#pragma unroll 1
-      for (; k + 4 <= j; k += 4) {                                /* eight independent loads in flight, four independent accumulators */
-        const real a0 = Ai[k], a1 = Ai[k + 1], a2 = Ai[k + 2], a3 = Ai[k + 3], b0 = Aj[k], b1 = Aj[k + 1], b2 = Aj[k + 2], b3 = Aj[k + 3];
-        s0 -= a0 * b0; s1 -= a1 * b1; s2 -= a2 * b2; s3 -= a3 * b3; }
-      if (k < j) {                                                /* tail of 1-3 terms, loads issued together */
-        const bool p1 = k + 1 < j, p2 = k + 2 < j;
-        const real a0 = Ai[k], b0 = Aj[k], a1 = p1 ? Ai[k + 1] : 0.0f, b1 = p1 ? Aj[k + 1] : 0.0f, a2 = p2 ? Ai[k + 2] : 0.0f, b2 = p2 ? Aj[k + 2] : 0.0f;
-        s1 -= a0 * b0; s2 -= a1 * b1; s3 -= a2 * b2; }
-      s0 = (s0 + s1) + (s2 + s3);
-    }
-    const real piv = gshfl(g, s0, j), inv = piv > 1e-30f ? rsb_rsqrt(piv) : 0.0f;
-    if (i >= j && i < n) Ai[j] = (i == j) ? inv : s0 * inv;
-    gsync(g);
-    Aj += ld ? ld : j + 1;
+/* Every factorisation of this kernel is followed by a solve with the fresh factor (qacc_smooth, the Newton direction, the implicit
+   Euler step, the task-space systems of the OSC law), and one such pair runs 5-13 times per physics substep on the critical path of an
+   environment: it is written for LATENCY.
+   chol_fs_t<N>: FUSED factor + solve with the matrix row in REGISTERS.  Lane i owns row i (identity-padded to N, so no size tests).
+     factor  (right-looking): at column j the pivot is broadcast by one shuffle, every trailing entry takes one shuffle + one FMA;
+             dependent chain per column = shuffle -> rsqrt -> mul -> (shuffle, FMA): ~110 cycles, no shared-memory traffic.
+     forward sweep straight from the row registers; the factor is then stored (inverse pivots on the diagonal) because the backward
+     sweep needs COLUMN i of L on lane i (loaded up front, off the dependent chain); each sweep step is one shuffle + one FMA.
+   Measured against a rolled shared-memory variant (150 instructions, dot-product loops): 4x fewer cycles per call, which outweighs the
+   larger footprint in the instruction cache (profiles/, stage profile of round 1).
+   Pivots <= 1e-30 are dropped directions (pinv-like): inverse pivot 0.  ld == 0 selects packed lower-triangular storage.  xo < 0:
+   factor only (the factor is still stored). */
+template <int N> RSB_D void chol_fs_t(real *A, int n, int ld, real *x, bool solve, Grp g) {
+  const int i = g.lane; real a[N]; real *Ai = A + (ld ? i * ld : tri_off(i)); const bool act = i < n;
+#pragma unroll
+  for (int k = 0; k < N; k++) a[k] = (act && k <= i) ? Ai[k] : ((k == i) ? 1.0f : 0.0f);
+  real b = (solve && act) ? x[i] : 0.0f, dinv = 0.0f;
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    const real sj = gshfl(g, a[j], j), inv = sj > 1e-30f ? rsb_rsqrt(sj) : 0.0f;
+    const real lij = (i == j) ? inv : a[j] * inv;                 /* lane j keeps 1/L_jj, lanes i > j keep L_ij */
+    a[j] = lij; if (i == j) dinv = inv;
+#pragma unroll
+    for (int k = j + 1; k < N; k++) { const real lkj = gshfl(g, a[j], k); a[k] -= lij * lkj; }   /* lane k supplies L_kj; rows i >= k use it */
   }
+#pragma unroll
+  for (int k = 0; k < N; k++) if (act && k <= i) Ai[k] = a[k];
+  gsync(g);
+  if (!solve) return;
+  real col[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) col[k] = (act && k > i && k < n) ? A[(ld ? k * ld : (k * (k + 1)) / 2) + i] : 0.0f;
+#pragma unroll
+  for (int k = 0; k < N; k++) { const real xk = gshfl(g, b * dinv, k); b = (i == k) ? xk : ((k < i) ? b - a[k] * xk : b); }      /* forward: L y = b */
+#pragma unroll
+  for (int k = N - 1; k >= 0; k--) { const real xk = gshfl(g, b * dinv, k); b = (i == k) ? xk : b - col[k] * xk; }               /* backward: L^T x = y */
+  if (act) x[i] = b;
+  gsync(g);
 }
-/* x <- A^-1 x with the factor of chol_factor; x is a shared-memory vector of length n.  Lane i walks row i (forward sweep) and column i
-   (backward sweep) of L; the dependent chain per step is one shuffle and one FMA. */
+/* A <- chol(A), then (xo >= 0) x <- A^-1 x */
+RSB_DN void chol_factor_solve(int ao, int n, int ld, int xo, Grp g) { real *A = RSB_SMEM + ao; real *x = RSB_SMEM + (xo < 0 ? 0 : xo); const bool sv = xo >= 0;
+  if (n <= 8) chol_fs_t<8>(A, n, ld, x, sv, g);
+  else if (n <= 12) chol_fs_t<12>(A, n, ld, x, sv, g);
+#if RSB_LANES >= 32
+  else if (n <= 16) chol_fs_t<16>(A, n, ld, x, sv, g);
+  else if (n <= 24) chol_fs_t<24>(A, n, ld, x, sv, g);
+  else chol_fs_t<32>(A, n, ld, x, sv, g);
+#else
+  else chol_fs_t<16>(A, n, ld, x, sv, g);                         /* 16-lane groups serve models with nv <= 16 only (checked at create) */
+#endif
+}
+/* x <- A^-1 x with an already stored factor (a second right-hand side: rare).  Rolled: lane i walks row i, then column i. */
 RSB_DN void chol_solve(int lo_, int n, int ld, int xo, Grp g) { const real *L = RSB_SMEM + lo_; real *x = RSB_SMEM + xo;
   const int i = g.lane; const bool act = i < n; const real *Li = L + (ld ? i * ld : tri_off(i));
   real b = act ? x[i] : 0.0f; const real dinv = act ? Li[i] : 0.0f;
@@ -972,7 +993,7 @@ RSB_DN void ctrl_run(int so, Grp g) { real *s = RSB_SMEM + so;
       }
       if (g.lane >= 9 && g.lane < 16) { int k = g.lane - 9; real kn = rb.null_kp; pose[k] = kn * (cs[CS_INITJ + k] - qpos[rb.arm_qadr[k]]) - 2 * sqrtf(kn) * qvel[rb.arm_dadr[k]]; }
       gsync(g);
-      chol_factor(SOFF(Lm), 7, 7, g);
+      chol_factor_solve(SOFF(Lm), 7, 7, -1, g);
       if (g.lane < 6) {                              /* X[r][:] = M^-1 J[r][:]^T */
         real x[7];
 #pragma unroll
@@ -996,8 +1017,7 @@ RSB_DN void ctrl_run(int so, Grp g) { real *s = RSB_SMEM + so;
         if (rb.uncouple) { sym3_solve(A, 6, F, w); sym3_solve(A + 21, 6, F + 3, w + 3); }
       }
       gsync(g);
-      chol_factor(SOFF(A), 6, 6, g);
-      chol_solve(SOFF(A), 6, 6, SOFF(y), g);                     /* y = Lambda_full J pose */
+      chol_factor_solve(SOFF(A), 6, 6, SOFF(y), g);              /* y = Lambda_full J pose */
       if (!rb.uncouple) { chol_solve(SOFF(A), 6, 6, SOFF(F), g); if (g.lane < 6) w[g.lane] = F[g.lane]; gsync(g); }
       if (g.lane < RSB_ARM_DOF) {
         int c = g.lane; real t = bias[rb.arm_dadr[c]];
@@ -1059,8 +1079,7 @@ RSB_DN void st_actuation(int so, Grp g) { real *s = RSB_SMEM + so;
 RSB_DN void st_smooth_acc(int so, Grp g) { real *s = RSB_SMEM + so; const real *M = s + MDL.o_M; real *L = s + MDL.o_L;
   for (int i = g.lane; i < MDL.ntri; i += RSB_LANES) L[i] = M[i];
   gsync(g);
-  chol_factor(so + MDL.o_L, MDL.nv, 0, g);
-  chol_solve(so + MDL.o_L, MDL.nv, 0, so + MDL.o_qacc_smooth, g);
+  chol_factor_solve(so + MDL.o_L, MDL.nv, 0, so + MDL.o_qacc_smooth, g);
 }
 
 /* ================================================================== A.3.7 constraint solver (Newton, exact line search) */
@@ -1255,10 +1274,9 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
     if (active && (last || it == MDL.solver_iters || scale * sqrtf(gn) < MDL.solver_tol)) active = false;      /* mj_solNewton: stop on small gradient OR small improvement (or the iteration limit) */
     if (!sany(active)) break;
     newton_hessian(so, g, nefc);
-    chol_factor(so + MDL.o_L, nv, 0, g);
     if (dl) search[d] = -grad[d];
     gsync(g);
-    chol_solve(so + MDL.o_L, nv, 0, so + MDL.o_search, g);
+    chol_factor_solve(so + MDL.o_L, nv, 0, so + MDL.o_search, g);
     /* directional quantities */
     real gq1 = 0, gq2 = 0, sg = 0;
     { real ms = mulM_lane(so, g, so + MDL.o_search); if (dl) { gq2 = search[d] * ms; gq1 = search[d] * (grad[d] + qfc[d]); sg = search[d] * grad[d]; } }
@@ -1309,8 +1327,7 @@ RSB_DN void st_euler(int so, Grp g) { real *s = RSB_SMEM + so;
     for (int e = g.lane; e < MDL.ntri; e += RSB_LANES) { const int ij = MDL.tri_ij[e], r = ij >> 8, c = ij & 255; L[e] = M[e] + ((r == c) ? h * MDL.dof_damping[r] : 0.0f); }
     for (int d = g.lane; d < MDL.nv; d += RSB_LANES) tmpv[d] = smooth[d] + qfc[d];
     gsync(g);
-    chol_factor(so + MDL.o_L, MDL.nv, 0, g);
-    chol_solve(so + MDL.o_L, MDL.nv, 0, so + MDL.o_tmpv, g);
+    chol_factor_solve(so + MDL.o_L, MDL.nv, 0, so + MDL.o_tmpv, g);
   } else { for (int d = g.lane; d < MDL.nv; d += RSB_LANES) tmpv[d] = qacc[d]; gsync(g); }
   for (int d = g.lane; d < MDL.nv; d += RSB_LANES) { qvel[d] += h * tmpv[d]; warm[d] = qacc[d]; }
   gsync(g);

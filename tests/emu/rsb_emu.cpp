@@ -13,6 +13,7 @@
 #include <cstring>
 #include <vector>
 #include <functional>
+#include <algorithm>
 
 #include "../../robosuite_benchmark_b200/csrc/rsb_dev.h"
 
@@ -77,6 +78,9 @@ void *emu_create(const rsb_model *m, const rsb_task *t, int ncon_max, int nefc_m
 }
 void emu_destroy(void *h) { delete (EmuEnv *)h; }
 void emu_set_order(int order) { S.order = order; }
+static float g_fill = 0.0f; static int g_do_fill = 0;
+/* fill the shared-memory image with a garbage value before every call: a read of a word the step has not written shows up */
+void emu_set_fill(float v, int on) { g_fill = v; g_do_fill = on; }
 int emu_smem_words(void *h) { return ((EmuEnv *)h)->dm.smem_words; }
 int emu_state_words(void *h) { return ((EmuEnv *)h)->dm.st_words; }
 int emu_dbg_words(void *h) { return (int)((EmuEnv *)h)->dbg.size(); }
@@ -93,6 +97,7 @@ void emu_reset(void *h, uint64_t seed, uint64_t env_id, float *obs) {
 }
 int emu_step(void *h, const float *action, float *obs, float *reward) {
   EmuEnv *e = (EmuEnv *)h; unsigned char done = 0;
+  if (g_do_fill) std::fill(e->smem.begin(), e->smem.end(), g_fill);
   emu_model = e->dm; emu_smem = e->smem.data();
   run_group([&](int lane) { Grp g{lane, (RSB_LANES == 32) ? 0xffffffffu : ((1u << RSB_LANES) - 1u)}; env_step(0, g, e->state.data(), action, obs, reward, &done, true); });
   return done;
