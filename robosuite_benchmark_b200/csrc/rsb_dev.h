@@ -743,6 +743,7 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
   }
   if (nrow > MDL.nefc_max) nrow = MDL.nefc_max;
   const int nscalar = nrow;
+  if (g.lane == 0) misc[MISC_NLIMROW] = nscalar;                 /* number of scalar rows (friction loss + limits): they precede the contact rows */
   /* contact row addresses: serial rule of the reference (a contact that does not fit is skipped, later ones may fit) */
   gsync(g);
   if (g.lane == 0) {
@@ -1091,9 +1092,13 @@ RSB_DN LsAcc efc_eval(int so, Grp g, int nefc, real alpha, int mode) { real *s =
   const real *con = s + MDL.o_con, *eD = s + MDL.o_eD, *jar = s + MDL.o_ejar, *Jv = s + MDL.o_eJv;
   real *force = s + MDL.o_eforce, *ew = s + MDL.o_ew; const int *etid = (const int *)(s + MDL.o_etype);
   real cost = 0, d1 = 0, d2 = 0;
-  for (int r = g.lane; r < nefc; r += RSB_LANES) {
+  /* work ITEMS, one per lane: the scalar rows (they come first) and the contacts (a contact's rows are handled from its first row).
+     A lane-per-row loop would leave the friction rows' lanes idle and need two passes from 17 rows on. */
+  const int *misc = (const int *)(s + MDL.o_misc); const int nscalar = misc[MISC_NLIMROW], nitem = nscalar + misc[MISC_NCON];
+  for (int it = g.lane; it < nitem; it += RSB_LANES) {
+    const int r = it < nscalar ? it : ((const int *)(con + (it - nscalar) * RSB_CONW))[CON_ADR];
+    if (r < 0) continue;                                          /* contact without rows (row limit reached) */
     const int wd = etid[r], type = ET_TYPE(wd); real D = eD[r];
-    if (type == EFC_CONTACT_FRICTION) continue;
     real dx = (mode == 2) ? Jv[r] : 0, x = jar[r] + alpha * dx;
     if (type == EFC_FRICTION) {
       real fl = MDL.dof_floss[ET_ID(wd)], rf = fl / D;          /* R * frictionloss */
