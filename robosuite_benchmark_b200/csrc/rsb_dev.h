@@ -105,6 +105,15 @@ RSB_D real gsum(Grp g, real v) {
   for (int o = RSB_LANES / 2; o > 0; o >>= 1) v += gshfl_xor(g, v, o);
   return v;
 }
+/* two / three sums at once: the shuffles of one level are independent, so the latency is that of ONE reduction */
+RSB_D void gsum2(Grp g, real &a, real &b) {
+#pragma unroll
+  for (int o = RSB_LANES / 2; o > 0; o >>= 1) { real ta = gshfl_xor(g, a, o), tb = gshfl_xor(g, b, o); a += ta; b += tb; }
+}
+RSB_D void gsum3(Grp g, real &a, real &b, real &c) {
+#pragma unroll
+  for (int o = RSB_LANES / 2; o > 0; o >>= 1) { real ta = gshfl_xor(g, a, o), tb = gshfl_xor(g, b, o), tc = gshfl_xor(g, c, o); a += ta; b += tb; c += tc; }
+}
 RSB_D real gmaxf(Grp g, real v) {
 #pragma unroll
   for (int o = RSB_LANES / 2; o > 0; o >>= 1) v = fmaxf(v, gshfl_xor(g, v, o));
@@ -1113,18 +1122,23 @@ RSB_DN LsAcc efc_eval(int so, Grp g, int nefc, real alpha, int mode) { real *s =
       else if (mode == 1) { force[r] = 0; ew[r] = 0; }
       continue;
     }
-    /* elliptic cone, dim in {3, 4} */
-    const real *fr = MDL.pair_friction + 5 * ((const int *)cr)[CON_PAIR]; real mu = cr[CON_MU];
-    real sc[RSB_MAXDIM], U[RSB_MAXDIM], dU[RSB_MAXDIM], xs[RSB_MAXDIM], dxs[RSB_MAXDIM]; sc[0] = mu; real T2 = 0;
+    /* elliptic cone, dim in {3, 4}.  All per-row arrays are indexed by unrolled loops only (registers: a run-time index would put them in
+       local memory, an L2 round trip per access at this kernel's shared-memory footprint).  In the middle zone, with U = (N, t), T = |t|,
+       s = t.dt / T:   cost = Dm (N - mu T)^2 / 2,   d1 = Dm (N - mu T)(dN - mu s),   d2 = Dm (dN - mu s)^2 - Dm mu (N - mu T)(dt.dt - s^2) / T. */
+    const real *fr = MDL.pair_friction + 5 * ((const int *)cr)[CON_PAIR]; const real mu = cr[CON_MU];
+    real sc[RSB_MAXDIM], U[RSB_MAXDIM], xs[RSB_MAXDIM], dxs[RSB_MAXDIM]; real T2 = 0, tdt = 0, dtdt = 0;
 #pragma unroll
-    for (int j = 0; j < RSB_MAXDIM; j++) if (j < dim) {
-      if (j > 0) sc[j] = fr[j - 1];
-      real dxj = (mode == 2) ? Jv[r + j] : 0; dxs[j] = dxj; xs[j] = jar[r + j] + alpha * dxj; U[j] = xs[j] * sc[j]; dU[j] = dxj * sc[j];
-      if (j > 0) T2 += U[j] * U[j];
-    }
-    real N = U[0], T = sqrtf(T2);
+    for (int j = 0; j < RSB_MAXDIM; j++) { sc[j] = 0; U[j] = 0; xs[j] = 0; dxs[j] = 0;
+      if (j < dim) {
+        sc[j] = (j == 0) ? mu : fr[j - 1];
+        const real dxj = (mode == 2) ? Jv[r + j] : 0.0f, dUj = dxj * sc[j]; dxs[j] = dxj; xs[j] = jar[r + j] + alpha * dxj; U[j] = xs[j] * sc[j];
+        if (j > 0) { T2 += U[j] * U[j]; tdt += U[j] * dUj; dtdt += dUj * dUj; }
+      } }
+    const real N = U[0], dN = dxs[0] * mu, invT = T2 > 0 ? rsb_rsqrt(T2) : 0.0f, T = T2 * invT;
     if (N >= mu * T || (T <= 0 && N >= 0)) {                         /* top zone: separated / inside the dual cone */
-      if (mode == 1) { for (int j = 0; j < dim; j++) { force[r + j] = 0; ew[r + j] = 0; } }
+      if (mode == 1) {
+#pragma unroll
+        for (int j = 0; j < RSB_MAXDIM; j++) if (j < dim) { force[r + j] = 0; ew[r + j] = 0; } }
     } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {              /* bottom zone: plain quadratic */
 #pragma unroll
       for (int j = 0; j < RSB_MAXDIM; j++) if (j < dim) {
@@ -1132,50 +1146,33 @@ RSB_DN LsAcc efc_eval(int so, Grp g, int nefc, real alpha, int mode) { real *s =
         if (mode == 1) { force[r + j] = -Dj * xs[j]; ew[r + j] = Dj; }
       }
     } else {                                                         /* middle zone: cone surface */
-      real Dm = D / (mu * mu * (1 + mu * mu)), NmT = N - mu * T;
+      const real Dm = D / (mu * mu * (1 + mu * mu)), NmT = N - mu * T;
       cost += 0.5f * Dm * NmT * NmT;
-      real gU[RSB_MAXDIM]; gU[0] = Dm * NmT;
+      if (mode == 1) {                                               /* force = -dcost/dx; ew < 0 marks "use the cone block" */
+        const real gt = Dm * mu * NmT * invT;
 #pragma unroll
-      for (int j = 1; j < RSB_MAXDIM; j++) if (j < dim) gU[j] = -Dm * mu * NmT * U[j] / T;
-      if (mode == 1) { for (int j = 0; j < dim; j++) { force[r + j] = -gU[j] * sc[j]; ew[r + j] = -1.0f; } }     /* ew < 0 marks "use the cone block" */
-      if (mode == 2) {
-        real invT = 1.0f / T;
-#pragma unroll
-        for (int a = 0; a < RSB_MAXDIM; a++)
-#pragma unroll
-          for (int b = 0; b < RSB_MAXDIM; b++) if (a < dim && b < dim) {
-            real h;
-            if (a == 0 && b == 0) h = Dm;
-            else if (a == 0 || b == 0) h = -Dm * mu * U[a + b] * invT;
-            else h = Dm * mu * mu * U[a] * U[b] * invT * invT - Dm * mu * NmT * ((a == b ? invT : 0.0f) - U[a] * U[b] * invT * invT * invT);
-            if (mode == 2) d2 += dU[a] * h * dU[b];
-          }
-        if (mode == 2) { for (int j = 0; j < dim; j++) d1 += gU[j] * dU[j]; }
+        for (int j = 0; j < RSB_MAXDIM; j++) if (j < dim) { force[r + j] = (j == 0) ? -Dm * NmT * mu : gt * U[j] * sc[j]; ew[r + j] = -1.0f; }
       }
+      if (mode == 2) { const real sdt = tdt * invT, q = dN - mu * sdt; d1 += Dm * NmT * q; d2 += Dm * q * q - Dm * mu * NmT * (dtdt - sdt * sdt) * invT; }
     }
   }
   LsAcc acc; acc.cost = cost; acc.d1 = d1; acc.d2 = d2; return acc;
 }
 
-/* dim x dim Hessian block (in constraint-row space) of the elliptic cone cost for a contact in its MIDDLE zone, from the residuals
-   jar of its rows.  Recomputed where the Newton Hessian is assembled instead of being stored per contact (256 words of shared memory). */
-RSB_D void cone_mid_block(const real *jar_c, real D, real mu, const real *fr, int dim, real *hc) {
-  real sc[RSB_MAXDIM], U[RSB_MAXDIM]; sc[0] = mu; real T2 = 0;
-#pragma unroll
-  for (int j = 0; j < RSB_MAXDIM; j++) if (j < dim) { if (j > 0) sc[j] = fr[j - 1]; U[j] = jar_c[j] * sc[j]; if (j > 0) T2 += U[j] * U[j]; }
-  const real T = sqrtf(T2), invT = 1.0f / T, Dm = D / (mu * mu * (1 + mu * mu)), NmT = U[0] - mu * T;
-#pragma unroll
-  for (int a = 0; a < RSB_MAXDIM; a++)
-#pragma unroll
-    for (int b = 0; b < RSB_MAXDIM; b++) if (a < dim && b < dim) {
-      real h;
-      if (a == 0 && b == 0) h = Dm;
-      else if (a == 0 || b == 0) h = -Dm * mu * U[a + b] * invT;
-      else h = Dm * mu * mu * U[a] * U[b] * invT * invT - Dm * mu * NmT * ((a == b ? invT : 0.0f) - U[a] * U[b] * invT * invT * invT);
-      hc[a * 4 + b] = h * sc[a] * sc[b];
-    }
-}
-
+/* developer build (-DRSB_PROFILE, tools/stage_profile.py): cycles per stage and per barrier wait, accumulated per warp */
+#if defined(RSB_PROFILE) && !defined(RSB_EMU)
+#define RSB_PROF_SLOTS 16
+__device__ unsigned long long g_prof[8192 * RSB_PROF_SLOTS];
+#define PROF(k) do { long long n_ = clock64(); if ((threadIdx.x & 31) == 0) g_prof[(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RSB_PROF_SLOTS + (k)] += (unsigned long long)(n_ - pt_); pt_ = n_; } while (0)
+#define PROF_DECL long long pt_ = clock64()
+#define PROF_LOCAL long long pt_ = clock64()
+#define PROF_COUNT(k) do { if ((threadIdx.x & 31) == 0) g_prof[(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RSB_PROF_SLOTS + (k)] += (1ull << 40); } while (0)
+#else
+#define PROF(k) ((void)0)
+#define PROF_DECL long long pt_ = 0; (void)pt_
+#define PROF_LOCAL ((void)0)
+#define PROF_COUNT(k) ((void)0)
+#endif
 /* ---- shared building blocks of the Newton solver.  Each is ONE non-inlined function: the solver loop then is ~1.5k instructions in
    total and stays in the instruction cache across iterations (the envs that need 5-9 iterations are the kernel's critical path). */
 /* y[r] = J[r,:] . x (- aref[r]) for every constraint row (lane per row) */
@@ -1210,13 +1207,24 @@ RSB_DN void newton_hessian(int so, Grp g, int nefc) { real *s = RSB_SMEM + so;
 #pragma unroll
       for (int i = 0; i < RSB_LANES; i++) if (i < nv) h[i] += Jr[i] * t;
     } else if (w < 0 && ET_TYPE(etid[r]) == EFC_CONTACT_NORMAL) {   /* first row of a contact in the middle zone of its cone */
-      const real *cr = con + ET_ID(etid[r]) * RSB_CONW; const int *ci = (const int *)cr; const int dim = CON_DIM_OF(ci); real hc[16], t[RSB_MAXDIM];
-      cone_mid_block(jar + r, (s + MDL.o_eD)[r], cr[CON_MU], MDL.pair_friction + 5 * ci[CON_PAIR], dim, hc);
+      /* cone Hessian in scaled coordinates U = sc * x, U = (N, t), T = |t|, that = t / T:  Hu = Dm u u^T - kap (I_t - that that^T) with
+         u = (1, -mu that), kap = Dm mu (N - mu T) / T.  Applied to column j without forming the dim x dim block:
+         y = sc * J_c[:, j],  (Hu y)_a = Dm u_a (u.y) - kap (y_a - that_a (that.y)) [a >= 1],  t_a = sc_a (Hu y)_a. */
+      const real *cr = con + ET_ID(etid[r]) * RSB_CONW; const int *ci = (const int *)cr; const int dim = CON_DIM_OF(ci);
+      const real *fr = MDL.pair_friction + 5 * ci[CON_PAIR]; const real mu = cr[CON_MU], D = (s + MDL.o_eD)[r];
+      real sc[RSB_MAXDIM], u[RSB_MAXDIM], y[RSB_MAXDIM], t[RSB_MAXDIM]; real T2 = 0, N = 0;
 #pragma unroll
-      for (int a = 0; a < RSB_MAXDIM; a++) { real acc = 0;
+      for (int a = 0; a < RSB_MAXDIM; a++) { sc[a] = 0; u[a] = 0; y[a] = 0;
+        if (a < dim) { sc[a] = (a == 0) ? mu : fr[a - 1]; const real Ua = jar[r + a] * sc[a]; y[a] = sc[a] * Jr[a * ldj + j];
+          if (a == 0) N = Ua; else { u[a] = Ua; T2 += Ua * Ua; } } }
+      const real invT = rsb_rsqrt(T2), T = T2 * invT, Dm = D / (mu * mu * (1 + mu * mu)), kap = Dm * mu * (N - mu * T) * invT;     /* middle zone: T > 0 */
+      real uy = y[0], ty = 0;
 #pragma unroll
-        for (int b = 0; b < RSB_MAXDIM; b++) if (a < dim && b < dim) acc += hc[a * 4 + b] * Jr[b * ldj + j];
-        t[a] = acc; }
+      for (int a = 1; a < RSB_MAXDIM; a++) { u[a] *= invT; ty += u[a] * y[a]; }      /* u[a >= 1] holds that_a for now */
+      uy -= mu * ty;
+      t[0] = sc[0] * Dm * uy;
+#pragma unroll
+      for (int a = 1; a < RSB_MAXDIM; a++) t[a] = sc[a] * (-Dm * mu * u[a] * uy - kap * (y[a] - u[a] * ty));
 #pragma unroll
       for (int a = 0; a < RSB_MAXDIM; a++) if (a < dim) { const real *Ja = Jr + a * ldj;
 #pragma unroll
@@ -1254,11 +1262,13 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
   /* (an unconstrained group next to a constrained one runs the loop with nefc = 0: it starts from qacc_smooth, its gradient is exactly
      0 and it is inactive from iteration 0 on, with qfc = 0 -- the same result as the early exit) */
   /* warm start: the cheaper of qacc_warmstart and qacc_smooth */
+  PROF_LOCAL;
   real cw = solver_cost(so, g, nefc, so + MDL.o_warm); gsync(g);
   real cs0 = solver_cost(so, g, nefc, so + MDL.o_qacc_smooth); gsync(g);
   if (dl) { qacc[d] = (cw < cs0) ? warm[d] : qas[d]; tmpv[d] = 0; }
   gsync(g);
   const real scale = 1.0f / (MDL.meaninertia * (real)(nv > 1 ? nv : 1));
+  PROF(10);                                            /* warm-start selection */
   /* `active` is uniform within a group; every branch that encloses a shuffle tests a warp vote, so the groups of a warp stay converged.
      A finished group keeps executing the body (recomputing identical residuals/forces for its unchanged qacc) until its neighbour is done. */
   int iter = 0; bool active = true, last = false;                  /* last: the previous update improved the cost by less than the tolerance */
@@ -1272,21 +1282,21 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
     /* gradient = M (qacc - qacc_smooth) - J^T f  (lane per dof; the difference first: exact 0 on unconstrained dofs) */
     real a = mulM_lane(so, g, so + MDL.o_tmpv), f = mulJT_lane(so, g, nefc);
     a -= f; if (dl) { grad[d] = a; qfc[d] = f; }
-    const real gn = gsum(g, a * a);
+    const real gn = gsum(g, a * a); PROF(11);            /* residual, forces, gradient */
 #ifdef RSB_EMU_TRACE
     if (g.lane == 0) printf("  it %d scaled|grad| %.3e\n", iter, scale * sqrtf(gn));
 #endif
     if (active && (last || it == MDL.solver_iters || scale * sqrtf(gn) < MDL.solver_tol)) active = false;      /* mj_solNewton: stop on small gradient OR small improvement (or the iteration limit) */
     if (!sany(active)) break;
-    newton_hessian(so, g, nefc);
+    newton_hessian(so, g, nefc); PROF(12); PROF_COUNT(12);      /* (profile build: iteration count in the high bits) */
     if (dl) search[d] = -grad[d];
     gsync(g);
-    chol_factor_solve(so + MDL.o_L, nv, 0, so + MDL.o_search, g);
+    chol_factor_solve(so + MDL.o_L, nv, 0, so + MDL.o_search, g); PROF(13);
     /* directional quantities */
     real gq1 = 0, gq2 = 0, sg = 0;
     { real ms = mulM_lane(so, g, so + MDL.o_search); if (dl) { gq2 = search[d] * ms; gq1 = search[d] * (grad[d] + qfc[d]); sg = search[d] * grad[d]; } }
     efc_mulJ(so, g, nefc, so + MDL.o_search, so + MDL.o_eJv, 0);
-    gq1 = gsum(g, gq1); gq2 = gsum(g, gq2); sg = gsum(g, sg);   /* gq1 = s.(M a - M a_s): slope of the Gauss term at alpha = 0; sg: slope of the total cost */
+    gsum3(g, gq1, gq2, sg);                                     /* gq1 = s.(M a - M a_s): slope of the Gauss term at alpha = 0; sg: slope of the total cost */
     /* exact line search on the convex 1-D cost: safeguarded Newton on its derivative.  At alpha = 0 the slope is search.grad and, for the
        Newton direction, the curvature is its negative (H search = -grad): the first trial step is 1, no evaluation at 0 is needed. */
     real lo = 0, hi = -1, alpha = 0; const real d1_0 = fabsf(sg);
@@ -1295,8 +1305,9 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
 #pragma unroll 1
     for (int lit = 1; lit < MDL.ls_iters; lit++) {
       if (!sany(ls)) break;
-      LsAcc v = efc_eval(so, g, nefc, alpha, 2);
-      real d1 = gq1 + alpha * gq2 + gsum(g, v.d1), d2 = gq2 + gsum(g, v.d2);
+      LsAcc v = efc_eval(so, g, nefc, alpha, 2); PROF_COUNT(14);
+      gsum2(g, v.d1, v.d2);
+      real d1 = gq1 + alpha * gq2 + v.d1, d2 = gq2 + v.d2;
       if (ls) {
 #ifdef RSB_EMU_TRACE
         if (g.lane == 0) printf("    ls %d alpha %.6g d1 %.3e d2 %.3e (d1_0 %.3e)\n", lit, alpha, d1, d2, d1_0);
@@ -1312,6 +1323,7 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
         }
       }
     }
+    PROF(14);                                          /* directional quantities + line search */
     if (active && alpha == 0) active = false;
     if (active) { if (dl) qacc[d] += alpha * search[d]; iter++;
       last = scale * 0.5f * alpha * d1_0 < MDL.solver_tol; }       /* cost decrease of an exact line search on a (locally) quadratic cost: alpha |d1(0)| / 2 */
@@ -1351,16 +1363,6 @@ RSB_DN void st_euler(int so, Grp g) { real *s = RSB_SMEM + so;
 /* ================================================================== one physics substep, the control step, reward, observation */
 /* Stage sequence of one physics substep.  RSB_CTA_SYNC() between stages keeps all warps of the CTA in the same stage
    (they then share instruction-cache lines: the whole step is far larger than the I-cache); it carries no data dependency. */
-/* developer build (-DRSB_PROFILE, tools/stage_profile.py): cycles per stage and per barrier wait, accumulated per warp */
-#if defined(RSB_PROFILE) && !defined(RSB_EMU)
-#define RSB_PROF_SLOTS 16
-__device__ unsigned long long g_prof[8192 * RSB_PROF_SLOTS];
-#define PROF(k) do { long long n_ = clock64(); if ((threadIdx.x & 31) == 0) g_prof[(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RSB_PROF_SLOTS + (k)] += (unsigned long long)(n_ - pt_); pt_ = n_; } while (0)
-#define PROF_DECL long long pt_ = clock64()
-#else
-#define PROF(k) ((void)0)
-#define PROF_DECL long long pt_ = 0; (void)pt_
-#endif
 #define STAGE_SYNC(k) do { PROF(k); RSB_CTA_SYNC(k); PROF(15); } while (0)
 RSB_D void substep(int so, Grp g, bool policy_step, long long &pt_) {
   /* order matters for the shared-memory overlays (rsb_devmodel.h): everything that reads the kinematics/dynamics temporaries runs
