@@ -25,6 +25,8 @@ if ROOT not in sys.path:
 
 ENV_NAME, ROBOT, CONTROLLER, SEED, HORIZON = "Lift", "Panda", "OSC_POSE", 17, 500
 METRIC, UNIT = "Lift-Panda-OSC env control-steps/s", "control-steps/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch (4096 envs), ncu --set full capture of round 1 (profiles/r1_kstep_ncu_summary.md)
+KSTEP_DRAM_BYTES_PER_LAUNCH = 11844608 + 2194944
 PREROLL = 100          # untimed control steps after the initial reset (run_ours): the timed region sits on the steady-state part of the episode
 
 
@@ -281,9 +283,11 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * sim.act_dim * 4,
                         "d2h_bytes_per_step": E * (sim.obs_dim * 4 + 4 + 1)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "k_step", "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": bps,
+                             "traffic": KSTEP_DRAM_BYTES_PER_LAUNCH if E == 4096 else None, "kernel": "k_step", "kernel_ms": kernel_ms,
+                             "algorithmic_bytes_per_env_step": bps,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                             "note": "state stays in shared memory for the 25 substeps: the kernel is issue/latency-bound, not HBM-bound (DESIGN.md)"},
+                             "note": "state stays in shared memory for the 25 substeps: the kernel is bound by the dependent-instruction latency of its slowest "
+                                     "environment, not by HBM (DESIGN.md 4.2); traffic = dram read+write of one launch from profiles/r1_kstep_ncu_summary.md"},
                 "kernel_info": {"regs": sim.info("regs_step"), "smem_bytes_per_env": sim.info("smem_bytes"),
                                 "envs_per_block": sim.info("envs_per_block"), "blocks_per_sm": sim.info("blocks_per_sm")},
                 "sac": sac, "cpu_baseline": cpu}
