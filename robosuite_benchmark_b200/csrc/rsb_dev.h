@@ -541,14 +541,19 @@ RSB_D int col_capsule_box(const real *cp, const real *cm, const real *cs, const 
    memory per SM no longer fits L1 and costs an L2 round trip per access (60% of this function's stall samples, profiles/). */
 RSB_DNOINL int col_box_box(const real *pa, const real *Ra, const real *ha, const real *pb, const real *Rb, const real *hb, real margin, RawCon *out, real *scr) {
   real R[9], Q[9], t[3], d[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
-  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { real v = Ra[i] * Rb[j] + Ra[3 + i] * Rb[3 + j] + Ra[6 + i] * Rb[6 + j]; R[3 * i + j] = v; Q[3 * i + j] = fabsf(v) + 1e-9f; }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) { real v = Ra[i] * Rb[j] + Ra[3 + i] * Rb[3 + j] + Ra[6 + i] * Rb[6 + j]; R[3 * i + j] = v; Q[3 * i + j] = fabsf(v) + 1e-9f; }
   matTvec3(t, Ra, d);
   real best = -1e30f; int code = -1; real bsign = 1;
+#pragma unroll
   for (int i = 0; i < 3; i++) {
     real sp = fabsf(t[i]) - (ha[i] + hb[0] * Q[3 * i] + hb[1] * Q[3 * i + 1] + hb[2] * Q[3 * i + 2]);
     if (sp > margin) return 0;
     if (sp > best + 1e-6f) { best = sp; code = i; bsign = t[i] >= 0 ? 1.0f : -1.0f; }
   }
+#pragma unroll
   for (int j = 0; j < 3; j++) {
     real tb = t[0] * R[j] + t[1] * R[3 + j] + t[2] * R[6 + j];
     real sp = fabsf(tb) - (hb[j] + ha[0] * Q[j] + ha[1] * Q[3 + j] + ha[2] * Q[6 + j]);
@@ -556,18 +561,22 @@ RSB_DNOINL int col_box_box(const real *pa, const real *Ra, const real *ha, const
     if (sp > best + 1e-6f) { best = sp; code = 3 + j; bsign = tb >= 0 ? 1.0f : -1.0f; }
   }
   real en[3] = {0, 0, 0};
-  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
-    int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-    real L[3] = {0, 0, 0}; L[i1] = -R[3 * i2 + j]; L[i2] = R[3 * i1 + j];
-    real len = sqrtf(L[i1] * L[i1] + L[i2] * L[i2]);
-    if (len < 1e-6f) continue;
-    real tl = (t[i1] * L[i1] + t[i2] * L[i2]) / len;
-    real ra = (ha[i1] * Q[3 * i2 + j] + ha[i2] * Q[3 * i1 + j]) / len;
-    real rb = (hb[j1] * Q[3 * i + j2] + hb[j2] * Q[3 * i + j1]) / len;
-    real sp = fabsf(tl) - (ra + rb);
-    if (sp > margin) return 0;
-    if (sp > best + 1e-4f) { best = sp; code = 6 + 3 * i + j; bsign = tl >= 0 ? 1.0f : -1.0f; en[0] = L[0] / len; en[1] = L[1] / len; en[2] = L[2] / len; }
-  }
+  /* the nine edge-edge axes: fully unrolled (compile-time indices keep R, Q, t in registers), one reciprocal square root per axis */
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const real La = -R[3 * i2 + j], Lb = R[3 * i1 + j], len2 = La * La + Lb * Lb;        /* L[i1] = La, L[i2] = Lb, L[i] = 0 */
+      if (len2 < 1e-12f) continue;
+      const real inv = rsb_rsqrt(len2);
+      const real tl = (t[i1] * La + t[i2] * Lb) * inv;
+      const real ra = (ha[i1] * Q[3 * i2 + j] + ha[i2] * Q[3 * i1 + j]) * inv;
+      const real rb = (hb[j1] * Q[3 * i + j2] + hb[j2] * Q[3 * i + j1]) * inv;
+      const real sp = fabsf(tl) - (ra + rb);
+      if (sp > margin) return 0;
+      if (sp > best + 1e-4f) { best = sp; code = 6 + 3 * i + j; bsign = tl >= 0 ? 1.0f : -1.0f; en[i] = 0; en[i1] = La * inv; en[i2] = Lb * inv; }
+    }
   if (code < 0) return 0;
   if (code >= 6) {
     int i = (code - 6) / 3, j = (code - 6) % 3;
