@@ -164,7 +164,7 @@ RSB_D void quatmul(real *o, const real *a, const real *b) {
 }
 RSB_D void quatnorm(real *q) {
   real n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
-  if (n2 < 1e-30f) { q[0] = 1; q[1] = q[2] = q[3] = 0; } else { real r = 1.0f / sqrtf(n2); q[0] *= r; q[1] *= r; q[2] *= r; q[3] *= r; }
+  if (n2 < 1e-30f) { q[0] = 1; q[1] = q[2] = q[3] = 0; } else { real r = rsb_rsqrt(n2); r = r * (1.5f - 0.5f * n2 * r * r); q[0] *= r; q[1] *= r; q[2] *= r; q[3] *= r; }   /* MUFU.RSQ + one Newton step */
 }
 RSB_D void quat2mat(real *R, const real *q) {
   real w = q[0], x = q[1], y = q[2], z = q[3];
@@ -464,7 +464,7 @@ RSB_D void make_frame(real *frame) {              /* frame[0..2] = normal; fills
   real *x = frame, *y = frame + 3, *z = frame + 6;
   if (x[1] < 0.5f && x[1] > -0.5f) { y[0] = 0; y[1] = 1; y[2] = 0; } else { y[0] = 0; y[1] = 0; y[2] = 1; }
   real d = dot3(x, y); y[0] -= x[0] * d; y[1] -= x[1] * d; y[2] -= x[2] * d;
-  real n = sqrtf(dot3(y, y)); if (n < RSB_MINVAL) { y[0] = 1; y[1] = 0; y[2] = 0; } else { y[0] /= n; y[1] /= n; y[2] /= n; }
+  real n2 = dot3(y, y); if (n2 < RSB_MINVAL * RSB_MINVAL) { y[0] = 1; y[1] = 0; y[2] = 0; } else { real r = rsb_rsqrt(n2); r = r * (1.5f - 0.5f * n2 * r * r); y[0] *= r; y[1] *= r; y[2] *= r; }
   cross3(z, x, y);
 }
 
