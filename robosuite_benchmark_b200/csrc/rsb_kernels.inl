@@ -60,11 +60,15 @@ __global__ void k_random_actions(uint64_t seed, uint64_t env_id_base, uint64_t s
 cudaError_t t_bind(const DevModel *dm, cudaStream_t st) { return cudaMemcpyToSymbolAsync(c_model, dm, sizeof(DevModel), 0, cudaMemcpyHostToDevice, st); }
 cudaError_t t_prepare(size_t smem_bytes, int epb, int *regs, int *blocks_per_sm) {
   cudaError_t e;
+  /* the dynamic-shared-memory limit is a property of the FUNCTION (per device), shared by every batch of the process: it only ever grows
+     (an evaluation batch of a few envs must not shrink the limit under a 4096-env exploration batch) */
+  static size_t s_limit[64]; int dev = 0; cudaGetDevice(&dev); const size_t want = smem_bytes;
+  if (dev >= 0 && dev < 64) { if (s_limit[dev] > smem_bytes) smem_bytes = s_limit[dev]; else s_limit[dev] = smem_bytes; }
   if ((e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_debug_substep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
   cudaFuncAttributes fa; if ((e = cudaFuncGetAttributes(&fa, k_step)) != cudaSuccess) return e; *regs = fa.numRegs;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_step, epb * RSB_LANES, smem_bytes);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_step, epb * RSB_LANES, want);
 }
 void t_step(int blocks, int epb, size_t smem, cudaStream_t st, float *state, const float *a, float *o, float *r, unsigned char *d, int n) {
   k_step<<<blocks, epb * RSB_LANES, smem, st>>>(state, a, o, r, d, n); }

@@ -266,3 +266,39 @@ def test_single_env_protocol(torch_cuda):
     o2 = g2.reset()
     assert o2.shape == (42,)
     env.close()
+
+
+def test_full_size_batch_is_invariant_to_batching(lift_panda_osc, torch_cuda):
+    """BASELINE.json configs[1] at FULL size (4096 envs, one CTA of 28 envs per SM) through size-independent properties:
+    (1) an env's trajectory does not depend on the batch it runs in -- env i of the 4096-batch equals env i of a 64-batch BIT FOR BIT
+        (different CTA packing, different partner in the warp, padding groups);
+    (2) the host-buffer C-ABI call (rsb_step_host) returns exactly what the device-resident call computes;
+    (3) rewards / observations are finite and every env's contact list holds the cube-on-table contacts after 30 control steps."""
+    from robosuite_benchmark_b200.backend import BatchSim
+    torch = torch_cuda
+    m, t = lift_panda_osc
+    big = BatchSim(m, t, 4096, device="cuda:0", seed=17, ncon_max=NCON, nefc_max=NEFC)
+    small = BatchSim(m, t, 64, device="cuda:0", seed=17, ncon_max=NCON, nefc_max=NEFC)
+    assert big.info("envs_per_block") == 28 and big.info("lanes") == 16
+    ob, os_ = big.reset(), small.reset()
+    assert torch.equal(ob[:64], os_)
+    for k in range(30):
+        ab, as_ = big.random_actions(k), small.random_actions(k)
+        assert torch.equal(ab[:64], as_)
+        ob, rb, _ = big.step(ab)
+        os_, rs, _ = small.step(as_)
+    assert torch.equal(ob[:64], os_) and torch.equal(rb[:64], rs)
+    assert torch.equal(big.get_state()[:64], small.get_state())
+    assert bool(torch.isfinite(ob).all()) and bool(torch.isfinite(rb).all())
+    # (2) host path == device path from the same state
+    st = big.get_state().clone()
+    a = big.random_actions(30)
+    od, rd, dd = big.step(a)
+    od, rd = od.cpu().numpy().copy(), rd.cpu().numpy().copy()
+    big.set_state(st)
+    oh, rh, dh = big.step_host(a.cpu().numpy())
+    assert np.array_equal(oh, od) and np.array_equal(rh, rd)
+    # (3) the cube rests on the table in (nearly) every env: 4 cube-table contacts at least
+    ncon = big.debug_substep(a, True)[:, 0].cpu().numpy()
+    assert (ncon >= 3).mean() > 0.99 and ncon.max() <= NCON
+    big.close(); small.close()
