@@ -302,3 +302,31 @@ def test_full_size_batch_is_invariant_to_batching(lift_panda_osc, torch_cuda):
     ncon = big.debug_substep(a, True)[:, 0].cpu().numpy()
     assert (ncon >= 3).mean() > 0.99 and ncon.max() <= NCON
     big.close(); small.close()
+
+
+def test_masked_reset_touches_only_masked_envs(lift_panda_osc, torch_cuda):
+    """rsb_reset with a mask (auto-reset of finished envs): masked-off envs -- including the partner env in the same warp -- keep their
+    state and their observation row; masked envs restart with the NEXT episode's Philox draws (the oracle's second episode)."""
+    from robosuite_benchmark_b200.backend import BatchSim
+    torch = torch_cuda
+    m, t = lift_panda_osc
+    n = 61                                                              # odd: the last warp has a padding group
+    s = BatchSim(m, t, n, device="cuda:0", seed=17, ncon_max=NCON, nefc_max=NEFC)
+    obs = s.reset()
+    for k in range(3):
+        obs, _, _ = s.step(s.random_actions(k))
+    before, obs_before = s.get_state().clone(), obs.clone()
+    mask = torch.zeros(n, dtype=torch.uint8)
+    mask[[0, 3, 10, 11, 60]] = 1                                        # one of a pair, both of a pair, the last env
+    s.reset(mask=mask, obs=obs)
+    after = s.get_state()
+    keep = (mask == 0).to(after.device)
+    assert torch.equal(after[keep], before[keep]) and torch.equal(obs[keep], obs_before[keep])
+    st = s.unpack_state(after.cpu().numpy())
+    for i in (0, 3, 10, 11, 60):
+        orc = _oracle(lift_panda_osc)
+        orc.reset(seed=17, env_id=i, episode=0)
+        o = orc.reset(seed=17, env_id=i, episode=1)
+        assert st["episode"][i] == 2 and st["timestep"][i] == 0
+        assert np.abs(o - obs[i].cpu().numpy()).max() < 2e-6
+    s.close()
