@@ -1080,16 +1080,21 @@ RSB_DN void ctrl_run(int so, Grp g) { real *s = RSB_SMEM + so;
 /* ================================================================== actuation + smooth acceleration */
 RSB_DN void st_actuation(int so, Grp g) { real *s = RSB_SMEM + so;
   const real *qpos = s + MDL.o_qpos, *qvel = s + MDL.o_qvel, *ctrl = s + MDL.o_ctrl, *bias = s + MDL.o_bias, *passive = s + MDL.o_passive;
-  real *actf = s + MDL.o_actuator, *smooth = s + MDL.o_smooth, *qas = s + MDL.o_qacc_smooth;
+  real *actf = s + MDL.o_actuator, *smooth = s + MDL.o_smooth, *qas = s + MDL.o_qacc_smooth, *af = s + MDL.o_cscr;
+  /* lane per ACTUATOR: its ~12 model loads are independent (one latency), the force goes to scratch (the controller scratch is dead here);
+     then lane per dof sums the actuators attached to it in actuator order (deterministic) */
+  for (int a = g.lane; a < MDL.nu; a += RSB_LANES) {
+    const int d = MDL.act_dof[a], qa = MDL.jnt_qadr[MDL.dof_jnt[d]];
+    real c = ctrl[a]; if (MDL.act_climited[a]) c = clampf(c, MDL.act_crange[2 * a], MDL.act_crange[2 * a + 1]);
+    const real gear = MDL.act_gear[a], len = qpos[qa] * gear, vel = qvel[d] * gear;
+    real fa = MDL.act_gain[a] * c + MDL.act_bias[3 * a] + MDL.act_bias[3 * a + 1] * len + MDL.act_bias[3 * a + 2] * vel;
+    if (MDL.act_flimited[a]) fa = clampf(fa, MDL.act_frange[2 * a], MDL.act_frange[2 * a + 1]);
+    af[a] = gear * fa;
+  }
+  gsync(g);
   for (int d = g.lane; d < MDL.nv; d += RSB_LANES) {
     real f = 0;
-    for (int a = 0; a < MDL.nu; a++) if (MDL.act_dof[a] == d) {
-      real c = ctrl[a]; if (MDL.act_climited[a]) c = clampf(c, MDL.act_crange[2 * a], MDL.act_crange[2 * a + 1]);
-      int qa = MDL.jnt_qadr[MDL.dof_jnt[d]]; real gear = MDL.act_gear[a], len = qpos[qa] * gear, vel = qvel[d] * gear;
-      real fa = MDL.act_gain[a] * c + MDL.act_bias[3 * a] + MDL.act_bias[3 * a + 1] * len + MDL.act_bias[3 * a + 2] * vel;
-      if (MDL.act_flimited[a]) fa = clampf(fa, MDL.act_frange[2 * a], MDL.act_frange[2 * a + 1]);
-      f += gear * fa;
-    }
+    for (int a = 0; a < MDL.nu; a++) f += (MDL.act_dof[a] == d) ? af[a] : 0.0f;
     actf[d] = f; real sm = passive[d] - bias[d] + f; smooth[d] = sm; qas[d] = sm;
   }
   gsync(g);
