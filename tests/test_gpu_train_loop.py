@@ -45,3 +45,23 @@ def test_variant_json_trains_and_logs_reference_schema(tmp_path, num_envs):
                                    "exploration/policy", "evaluation/policy"])
     assert tuple(snap["trainer/policy"]["fc0.weight"].shape) == (256, 42) and tuple(snap["trainer/qf1"]["fc0.weight"].shape) == (256, 49)
     assert json.load(open(os.path.join(log_dir, "variant.json")))["trainer_kwargs"]["qf_lr"] == 0.0005
+
+
+@pytest.mark.gpu
+def test_rollout_cli_on_a_committed_variant(tmp_path):
+    """scripts/rollout.py on the batched backend: a run directory with the reference's variant.json and a snapshot written by this
+    package's own _get_snapshot layout (state dicts) -> deterministic-policy returns; the untrained policy scores the logged
+    epoch-0 level (Lift-Panda-OSC_POSE zero/untrained-policy return ~3-20 over 500 steps)."""
+    import json, os, pickle, shutil
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from robosuite_benchmark_b200.rollout import main
+    from robosuite_benchmark_b200.sac import ParamStore, TanhGaussianPolicy
+    here = os.path.dirname(__file__)
+    shutil.copy(os.path.join(here, "golden", "variant_Lift-Panda-OSC-POSE-SEED17.json"), tmp_path / "variant.json")
+    store = ParamStore(42, 7, torch.device("cuda", 0), seed=17)
+    with open(tmp_path / "params.pkl", "wb") as f:
+        pickle.dump({"evaluation/policy": TanhGaussianPolicy(store).state_dict()}, f)
+    rets = main(["--load_dir", str(tmp_path), "--num_episodes", "4", "--horizon", "100"])
+    assert rets.shape == (4,) and np.isfinite(rets).all() and 0.0 < rets.mean() < 20.0
