@@ -1252,6 +1252,82 @@ RSB_DN void newton_hessian(int so, Grp g, int nefc) { real *s = RSB_SMEM + so;
   gsync(g);
 }
 
+/* ---- exact line search with per-item polynomial data in REGISTERS.
+   Along the search line every row residual is x(alpha) = jar + alpha Jv.  What the slope / curvature of the constraint cost need per
+   work item (scalar row or contact) are a handful of numbers that do not depend on alpha: they are loaded ONCE per Newton iteration
+   (two items per lane; items beyond 2 x lanes are re-loaded on every evaluation), so that one evaluation is ~30 flops per lane plus one
+   fused reduction instead of a pass over shared memory (mj's line search precomputes its `quad` coefficients for the same reason).
+     friction loss : x0 dx D fl rf            unilateral (limit, condim 1) : x0 dx D
+     elliptic cone : N0 dN tt tdt dtdt (scaled coordinates U = sc x: N = N0 + a dN, T^2 = tt + 2 a tdt + a^2 dtdt), mu, Dm,
+                     B1 B2 (bottom zone: slope B1 + a B2, curvature B2) */
+struct LsItem { int type; real a0, a1, a2, a3, a4, a5, a6, a7, a8; };
+RSB_D void ls_load(int so, int it, int nscalar, int nitem, LsItem &I) { const real *s = RSB_SMEM + so;
+  const real *con = s + MDL.o_con, *eD = s + MDL.o_eD, *jar = s + MDL.o_ejar, *Jv = s + MDL.o_eJv; const int *etid = (const int *)(s + MDL.o_etype);
+  I.type = 0; I.a0 = I.a1 = I.a2 = I.a3 = I.a4 = I.a5 = I.a6 = I.a7 = I.a8 = 0;
+  if (it >= nitem) return;
+  const int r = it < nscalar ? it : ((const int *)(con + (it - nscalar) * RSB_CONW))[CON_ADR];
+  if (r < 0) return;
+  const int wd = etid[r], type = ET_TYPE(wd); const real D = eD[r];
+  I.a0 = jar[r]; I.a1 = Jv[r]; I.a2 = D;
+  if (type == EFC_FRICTION) { const real fl = MDL.dof_floss[ET_ID(wd)]; I.type = 1; I.a3 = fl; I.a4 = fl / D; return; }
+  const real *cr = con + ET_ID(wd) * RSB_CONW; const int dim = (type == EFC_LIMIT) ? 1 : CON_DIM_OF((const int *)cr);
+  if (dim == 1) { I.type = 2; return; }
+  const real *fr = MDL.pair_friction + 5 * ((const int *)cr)[CON_PAIR]; const real mu = cr[CON_MU];
+  real tt = 0, tdt = 0, dtdt = 0, B1 = D * I.a0 * I.a1, B2 = D * I.a1 * I.a1;
+#pragma unroll
+  for (int j = 1; j < RSB_MAXDIM; j++) if (j < dim) {
+    const real sc = fr[j - 1], xj = jar[r + j], dxj = Jv[r + j], Dj = eD[r + j], U = xj * sc, dU = dxj * sc;
+    tt += U * U; tdt += U * dU; dtdt += dU * dU; B1 += Dj * xj * dxj; B2 += Dj * dxj * dxj; }
+  I.type = 3; I.a0 *= mu; I.a1 *= mu;                               /* N0, dN */
+  I.a2 = tt; I.a3 = tdt; I.a4 = dtdt; I.a5 = mu; I.a6 = D / (mu * mu * (1 + mu * mu)); I.a7 = B1; I.a8 = B2;
+}
+RSB_D void ls_eval(const LsItem &I, real alpha, real &d1, real &d2) {
+  if (I.type == 0) return;
+  if (I.type == 1) { const real x = I.a0 + alpha * I.a1;
+    if (x <= -I.a4) d1 -= I.a3 * I.a1; else if (x >= I.a4) d1 += I.a3 * I.a1; else { d1 += I.a2 * x * I.a1; d2 += I.a2 * I.a1 * I.a1; }
+    return; }
+  if (I.type == 2) { const real x = I.a0 + alpha * I.a1; if (x < 0) { d1 += I.a2 * x * I.a1; d2 += I.a2 * I.a1 * I.a1; } return; }
+  const real N = I.a0 + alpha * I.a1, mu = I.a5; real T2 = I.a2 + alpha * (2 * I.a3 + alpha * I.a4); T2 = fmaxf(T2, 0.0f);
+  const real invT = T2 > 0 ? rsb_rsqrt(T2) : 0.0f, T = T2 * invT;
+  if (N >= mu * T || (T <= 0 && N >= 0)) return;                    /* top zone */
+  if (mu * N + T <= 0 || (T <= 0 && N < 0)) { d1 += I.a7 + alpha * I.a8; d2 += I.a8; return; }       /* bottom zone */
+  const real sdt = (I.a3 + alpha * I.a4) * invT, q = I.a1 - mu * sdt, NmT = N - mu * T, Dm = I.a6;
+  d1 += Dm * NmT * q; d2 += Dm * q * q - Dm * mu * NmT * (I.a4 - sdt * sdt) * invT;
+}
+/* returns the step (0: the Newton decrement is below tolerance -- converged -- or the group is not active).  gq1, gq2: slope at 0 and
+   curvature of the Gauss term along the line; sg = search.grad: slope of the total cost at 0 (its negative is the curvature there). */
+RSB_DN real newton_linesearch(int so, Grp g, real gq1, real gq2, real sg, real scale, bool active) { const real *s = RSB_SMEM + so;
+  const int *misc = (const int *)(s + MDL.o_misc); const int nscalar = misc[MISC_NLIMROW], nitem = nscalar + misc[MISC_NCON];
+  LsItem I0, I1; ls_load(so, g.lane, nscalar, nitem, I0); ls_load(so, g.lane + RSB_LANES, nscalar, nitem, I1);
+  real lo = 0, hi = -1, alpha = 0; const real d1_0 = fabsf(sg);
+  bool ls = active && (sg < -1e-10f / scale);                     /* else: Newton decrement below tolerance (or fp32 noise): converged */
+  if (ls) alpha = 1.0f;                                           /* the Newton step: slope and curvature at 0 are sg and -sg */
+#pragma unroll 1
+  for (int lit = 1; lit < MDL.ls_iters; lit++) {
+    if (!sany(ls)) break;
+    real e1 = 0, e2 = 0; ls_eval(I0, alpha, e1, e2); ls_eval(I1, alpha, e1, e2);
+#pragma unroll 1
+    for (int it = g.lane + 2 * RSB_LANES; it < nitem; it += RSB_LANES) { LsItem J; ls_load(so, it, nscalar, nitem, J); ls_eval(J, alpha, e1, e2); }
+    gsum2(g, e1, e2); PROF_COUNT(14);
+    const real d1 = gq1 + alpha * gq2 + e1, d2 = gq2 + e2;
+    if (ls) {
+#ifdef RSB_EMU_TRACE
+      if (g.lane == 0) printf("    ls %d alpha %.6g d1 %.3e d2 %.3e (d1_0 %.3e)\n", lit, alpha, d1, d2, d1_0);
+#endif
+      if (fabsf(d1) <= MDL.ls_tol * d1_0 + 1e-30f) ls = false;
+      else {
+        if (d1 < 0) lo = alpha; else hi = alpha;
+        if (hi >= 0 && hi - lo <= 1e-4f * hi) ls = false;           /* bracket at fp32 resolution of the derivative: the sign of d1 is noise from here on */
+        real an = d2 > RSB_MINVAL ? alpha - d1 / d2 : alpha;
+        if (hi >= 0 && (an <= lo || an >= hi)) an = 0.5f * (lo + hi);
+        else if (hi < 0 && an <= lo) an = 2 * lo;
+        if (an == alpha) ls = false; else if (ls) alpha = an;
+      }
+    }
+  }
+  return alpha;
+}
+
 /* jar = J qacc - aref (lane per row); returns the total cost (Gauss + constraint), identical on all lanes */
 RSB_DN real solver_cost(int so, Grp g, int nefc, int qo) { real *s = RSB_SMEM + so; const real *qacc = RSB_SMEM + qo;
   const real *qas = s + MDL.o_qacc_smooth;
@@ -1311,32 +1387,8 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
     { real ms = mulM_lane(so, g, so + MDL.o_search); if (dl) { gq2 = search[d] * ms; gq1 = search[d] * (grad[d] + qfc[d]); sg = search[d] * grad[d]; } }
     efc_mulJ(so, g, nefc, so + MDL.o_search, so + MDL.o_eJv, 0);
     gsum3(g, gq1, gq2, sg);                                     /* gq1 = s.(M a - M a_s): slope of the Gauss term at alpha = 0; sg: slope of the total cost */
-    /* exact line search on the convex 1-D cost: safeguarded Newton on its derivative.  At alpha = 0 the slope is search.grad and, for the
-       Newton direction, the curvature is its negative (H search = -grad): the first trial step is 1, no evaluation at 0 is needed. */
-    real lo = 0, hi = -1, alpha = 0; const real d1_0 = fabsf(sg);
-    bool ls = active && (sg < -1e-10f / scale);                   /* else: Newton decrement below tolerance (or fp32 noise): converged */
-    if (ls) alpha = 1.0f;
-#pragma unroll 1
-    for (int lit = 1; lit < MDL.ls_iters; lit++) {
-      if (!sany(ls)) break;
-      LsAcc v = efc_eval(so, g, nefc, alpha, 2); PROF_COUNT(14);
-      gsum2(g, v.d1, v.d2);
-      real d1 = gq1 + alpha * gq2 + v.d1, d2 = gq2 + v.d2;
-      if (ls) {
-#ifdef RSB_EMU_TRACE
-        if (g.lane == 0) printf("    ls %d alpha %.6g d1 %.3e d2 %.3e (d1_0 %.3e)\n", lit, alpha, d1, d2, d1_0);
-#endif
-        if (fabsf(d1) <= MDL.ls_tol * d1_0 + 1e-30f) ls = false;
-        else {
-          if (d1 < 0) lo = alpha; else hi = alpha;
-          if (hi >= 0 && hi - lo <= 1e-4f * hi) ls = false;         /* bracket at fp32 resolution of the derivative: the sign of d1 is noise from here on */
-          real an = d2 > RSB_MINVAL ? alpha - d1 / d2 : alpha;
-          if (hi >= 0 && (an <= lo || an >= hi)) an = 0.5f * (lo + hi);
-          else if (hi < 0 && an <= lo) an = 2 * lo;
-          if (an == alpha) ls = false; else if (ls) alpha = an;
-        }
-      }
-    }
+    /* exact line search on the convex 1-D cost: safeguarded Newton on its derivative, first trial step 1 (newton_linesearch) */
+    const real d1_0 = fabsf(sg), alpha = newton_linesearch(so, g, gq1, gq2, sg, scale, active);
     PROF(14);                                          /* directional quantities + line search */
     if (active && alpha == 0) active = false;
     if (active) { if (dl) qacc[d] += alpha * search[d]; iter++;
