@@ -1107,70 +1107,62 @@ RSB_DN void st_smooth_acc(int so, Grp g) { real *s = RSB_SMEM + so; const real *
 }
 
 /* ================================================================== A.3.7 constraint solver (Newton, exact line search) */
-struct LsAcc { real cost, d1, d2; };
-
-/* Evaluate the constraint cost of this lane's rows at x = jar + alpha*Jv.
-   mode 0: cost only; mode 1: cost + force + Hessian weights (ew, Hc); mode 2: cost + line-search derivatives. */
-RSB_DN LsAcc efc_eval(int so, Grp g, int nefc, real alpha, int mode) { real *s = RSB_SMEM + so;
-  const real *con = s + MDL.o_con, *eD = s + MDL.o_eD, *jar = s + MDL.o_ejar, *Jv = s + MDL.o_eJv;
+/* Constraint cost of this lane's work items at the residuals jar (x = J qacc - aref); with_forces: also the row forces and the Hessian
+   weights (ew = D on quadratic rows, 0 on inactive ones, < 0 on the rows of a contact in the middle zone of its cone).
+   Work ITEMS, one per lane: the scalar rows (they come first) and the contacts (a contact's rows are handled from its first row); a
+   lane-per-row loop would leave the friction rows' lanes idle and need two passes from 17 rows on.  The line search has its own
+   evaluator (newton_linesearch). */
+RSB_DN real efc_eval(int so, Grp g, bool with_forces) { real *s = RSB_SMEM + so;
+  const real *con = s + MDL.o_con, *eD = s + MDL.o_eD, *jar = s + MDL.o_ejar;
   real *force = s + MDL.o_eforce, *ew = s + MDL.o_ew; const int *etid = (const int *)(s + MDL.o_etype);
-  real cost = 0, d1 = 0, d2 = 0;
-  /* work ITEMS, one per lane: the scalar rows (they come first) and the contacts (a contact's rows are handled from its first row).
-     A lane-per-row loop would leave the friction rows' lanes idle and need two passes from 17 rows on. */
+  real cost = 0;
   const int *misc = (const int *)(s + MDL.o_misc); const int nscalar = misc[MISC_NLIMROW], nitem = nscalar + misc[MISC_NCON];
   for (int it = g.lane; it < nitem; it += RSB_LANES) {
     const int r = it < nscalar ? it : ((const int *)(con + (it - nscalar) * RSB_CONW))[CON_ADR];
     if (r < 0) continue;                                          /* contact without rows (row limit reached) */
-    const int wd = etid[r], type = ET_TYPE(wd); real D = eD[r];
-    real dx = (mode == 2) ? Jv[r] : 0, x = jar[r] + alpha * dx;
+    const int wd = etid[r], type = ET_TYPE(wd); const real D = eD[r], x = jar[r];
     if (type == EFC_FRICTION) {
-      real fl = MDL.dof_floss[ET_ID(wd)], rf = fl / D;          /* R * frictionloss */
-      if (x <= -rf) { cost += -0.5f * rf * fl - fl * x; d1 += -fl * dx; if (mode == 1) { force[r] = fl; ew[r] = 0; } }
-      else if (x >= rf) { cost += -0.5f * rf * fl + fl * x; d1 += fl * dx; if (mode == 1) { force[r] = -fl; ew[r] = 0; } }
-      else { cost += 0.5f * D * x * x; d1 += D * x * dx; d2 += D * dx * dx; if (mode == 1) { force[r] = -D * x; ew[r] = D; } }
+      const real fl = MDL.dof_floss[ET_ID(wd)], rf = fl / D;    /* R * frictionloss */
+      if (x <= -rf) { cost += -0.5f * rf * fl - fl * x; if (with_forces) { force[r] = fl; ew[r] = 0; } }
+      else if (x >= rf) { cost += -0.5f * rf * fl + fl * x; if (with_forces) { force[r] = -fl; ew[r] = 0; } }
+      else { cost += 0.5f * D * x * x; if (with_forces) { force[r] = -D * x; ew[r] = D; } }
       continue;
     }
-    const real *cr = con + ET_ID(wd) * RSB_CONW; int dim = (type == EFC_LIMIT) ? 1 : CON_DIM_OF((const int *)cr);
+    const real *cr = con + ET_ID(wd) * RSB_CONW; const int dim = (type == EFC_LIMIT) ? 1 : CON_DIM_OF((const int *)cr);
     if (dim == 1) {
-      if (x < 0) { cost += 0.5f * D * x * x; d1 += D * x * dx; d2 += D * dx * dx; if (mode == 1) { force[r] = -D * x; ew[r] = D; } }
-      else if (mode == 1) { force[r] = 0; ew[r] = 0; }
+      if (x < 0) { cost += 0.5f * D * x * x; if (with_forces) { force[r] = -D * x; ew[r] = D; } }
+      else if (with_forces) { force[r] = 0; ew[r] = 0; }
       continue;
     }
-    /* elliptic cone, dim in {3, 4}.  All per-row arrays are indexed by unrolled loops only (registers: a run-time index would put them in
-       local memory, an L2 round trip per access at this kernel's shared-memory footprint).  In the middle zone, with U = (N, t), T = |t|,
-       s = t.dt / T:   cost = Dm (N - mu T)^2 / 2,   d1 = Dm (N - mu T)(dN - mu s),   d2 = Dm (dN - mu s)^2 - Dm mu (N - mu T)(dt.dt - s^2) / T. */
+    /* elliptic cone, dim in {3, 4}; scaled coordinates U = sc x = (N, t), T = |t|.  All per-row arrays are indexed by unrolled loops only
+       (registers: a run-time index would put them in local memory, an L2 round trip per access at this kernel's shared-memory footprint) */
     const real *fr = MDL.pair_friction + 5 * ((const int *)cr)[CON_PAIR]; const real mu = cr[CON_MU];
-    real sc[RSB_MAXDIM], U[RSB_MAXDIM], xs[RSB_MAXDIM], dxs[RSB_MAXDIM]; real T2 = 0, tdt = 0, dtdt = 0;
+    real sc[RSB_MAXDIM], U[RSB_MAXDIM], xs[RSB_MAXDIM]; real T2 = 0;
 #pragma unroll
-    for (int j = 0; j < RSB_MAXDIM; j++) { sc[j] = 0; U[j] = 0; xs[j] = 0; dxs[j] = 0;
-      if (j < dim) {
-        sc[j] = (j == 0) ? mu : fr[j - 1];
-        const real dxj = (mode == 2) ? Jv[r + j] : 0.0f, dUj = dxj * sc[j]; dxs[j] = dxj; xs[j] = jar[r + j] + alpha * dxj; U[j] = xs[j] * sc[j];
-        if (j > 0) { T2 += U[j] * U[j]; tdt += U[j] * dUj; dtdt += dUj * dUj; }
-      } }
-    const real N = U[0], dN = dxs[0] * mu, invT = T2 > 0 ? rsb_rsqrt(T2) : 0.0f, T = T2 * invT;
+    for (int j = 0; j < RSB_MAXDIM; j++) { sc[j] = 0; U[j] = 0; xs[j] = 0;
+      if (j < dim) { sc[j] = (j == 0) ? mu : fr[j - 1]; xs[j] = jar[r + j]; U[j] = xs[j] * sc[j]; if (j > 0) T2 += U[j] * U[j]; } }
+    const real N = U[0], invT = T2 > 0 ? rsb_rsqrt(T2) : 0.0f, T = T2 * invT;
     if (N >= mu * T || (T <= 0 && N >= 0)) {                         /* top zone: separated / inside the dual cone */
-      if (mode == 1) {
+      if (with_forces) {
 #pragma unroll
         for (int j = 0; j < RSB_MAXDIM; j++) if (j < dim) { force[r + j] = 0; ew[r + j] = 0; } }
     } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {              /* bottom zone: plain quadratic */
 #pragma unroll
       for (int j = 0; j < RSB_MAXDIM; j++) if (j < dim) {
-        real Dj = eD[r + j], dxj = dxs[j]; cost += 0.5f * Dj * xs[j] * xs[j]; d1 += Dj * xs[j] * dxj; d2 += Dj * dxj * dxj;
-        if (mode == 1) { force[r + j] = -Dj * xs[j]; ew[r + j] = Dj; }
+        const real Dj = eD[r + j]; cost += 0.5f * Dj * xs[j] * xs[j];
+        if (with_forces) { force[r + j] = -Dj * xs[j]; ew[r + j] = Dj; }
       }
-    } else {                                                         /* middle zone: cone surface */
+    } else {                                                         /* middle zone: cone surface, cost = Dm (N - mu T)^2 / 2 */
       const real Dm = D / (mu * mu * (1 + mu * mu)), NmT = N - mu * T;
       cost += 0.5f * Dm * NmT * NmT;
-      if (mode == 1) {                                               /* force = -dcost/dx; ew < 0 marks "use the cone block" */
+      if (with_forces) {                                             /* force = -dcost/dx; ew < 0 marks "use the cone block" */
         const real gt = Dm * mu * NmT * invT;
 #pragma unroll
         for (int j = 0; j < RSB_MAXDIM; j++) if (j < dim) { force[r + j] = (j == 0) ? -Dm * NmT * mu : gt * U[j] * sc[j]; ew[r + j] = -1.0f; }
       }
-      if (mode == 2) { const real sdt = tdt * invT, q = dN - mu * sdt; d1 += Dm * NmT * q; d2 += Dm * q * q - Dm * mu * NmT * (dtdt - sdt * sdt) * invT; }
     }
   }
-  LsAcc acc; acc.cost = cost; acc.d1 = d1; acc.d2 = d2; return acc;
+  return cost;
 }
 
 /* developer build (-DRSB_PROFILE, tools/stage_profile.py): cycles per stage and per barrier wait, accumulated per warp */
@@ -1200,9 +1192,23 @@ RSB_DN void efc_mulJ(int so, Grp g, int nefc, int xo, int yo, int sub_aref) { re
 RSB_DN real mulM_lane(int so, Grp g, int vo) { const real *s = RSB_SMEM + so;
   return g.lane < MDL.nv ? symv_row(s + MDL.o_M, g.lane, RSB_SMEM + vo, MDL.nv) : 0.0f;
 }
-/* lane d < nv: (J^T force)[d] */
-RSB_DN real mulJT_lane(int so, Grp g, int nefc) { const real *s = RSB_SMEM + so;
-  return g.lane < MDL.nv ? sdot_strided(s + MDL.o_J + g.lane, MDL.ldj, s + MDL.o_eforce, nefc) : 0.0f;
+/* lane d < nv: row d of M times the vector at vo AND (J^T force)[d], as one function so that the two independent load/FMA chains
+   interleave (each alone waits on its own shared-memory latency) */
+struct GradTerms { real ma, jtf; };
+RSB_DN GradTerms grad_terms_lane(int so, Grp g, int vo, int nefc) { const real *s = RSB_SMEM + so; GradTerms o; o.ma = 0; o.jtf = 0;
+  if (g.lane >= MDL.nv) return o;
+  const real *P = s + MDL.o_M, *v = RSB_SMEM + vo, *Jc = s + MDL.o_J + g.lane, *f = s + MDL.o_eforce; const int n = MDL.nv, ldj = MDL.ldj, i = g.lane;
+  real s0 = 0, s1 = 0, t0 = 0, t1 = 0; const int ri = tri_off(i); int tj = 0, j = 0, r = 0;
+  for (; j + 2 <= n; j += 2, r += 2) {                             /* symv_row and sdot_strided, two terms of each per trip */
+    const int i0 = (j <= i) ? ri + j : tj + i, u1 = tj + j + 1, i1 = (j + 1 <= i) ? ri + j + 1 : u1 + i;
+    const bool p0 = r < nefc, p1 = r + 1 < nefc;
+    const real m0 = P[i0], m1 = P[i1], v0 = v[j], v1 = v[j + 1], a0 = p0 ? Jc[r * ldj] : 0.0f, a1 = p1 ? Jc[(r + 1) * ldj] : 0.0f, f0 = p0 ? f[r] : 0.0f, f1 = p1 ? f[r + 1] : 0.0f;
+    s0 += m0 * v0; s1 += m1 * v1; t0 += a0 * f0; t1 += a1 * f1; tj = u1 + j + 2;
+  }
+  if (j < n) { const int i0 = (j <= i) ? ri + j : tj + i; s0 += P[i0] * v[j]; }
+  for (; r + 2 <= nefc; r += 2) { const real a0 = Jc[r * ldj], a1 = Jc[(r + 1) * ldj], f0 = f[r], f1 = f[r + 1]; t0 += a0 * f0; t1 += a1 * f1; }
+  if (r < nefc) t0 += Jc[r * ldj] * f[r];
+  o.ma = s0 + s1; o.jtf = t0 + t1; return o;
 }
 /* H = M + J^T W J (+ cone blocks) into the packed workspace at o_L.  Lane j owns COLUMN j and keeps h[i] = sum_r w_r J_ri J_rj for all
    i in registers: per constraint row one own-column load, then nv broadcast loads + FMAs (a lane-per-entry loop costs 8 passes over all
@@ -1337,8 +1343,7 @@ RSB_DN real solver_cost(int so, Grp g, int nefc, int qo) { real *s = RSB_SMEM + 
   gsync(g);
   real gs = mulM_lane(so, g, so + MDL.o_tmpv); if (g.lane < MDL.nv) gs *= 0.5f * dq[g.lane];
   gsync(g);
-  LsAcc a = efc_eval(so, g, nefc, 0.0f, 0);
-  return gsum(g, gs + a.cost);
+  return gsum(g, gs + efc_eval(so, g, false));
 }
 
 RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
@@ -1366,11 +1371,12 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
   for (int it = 0; it <= MDL.solver_iters; it++) {
     /* residual rows, forces, Hessian weights */
     efc_mulJ(so, g, nefc, so + MDL.o_qacc, so + MDL.o_ejar, 1);
-    efc_eval(so, g, nefc, 0.0f, 1);
+    efc_eval(so, g, true);
     if (dl) tmpv[d] = qacc[d] - qas[d];
     gsync(g);
     /* gradient = M (qacc - qacc_smooth) - J^T f  (lane per dof; the difference first: exact 0 on unconstrained dofs) */
-    real a = mulM_lane(so, g, so + MDL.o_tmpv), f = mulJT_lane(so, g, nefc);
+    const GradTerms gt = grad_terms_lane(so, g, so + MDL.o_tmpv, nefc);
+    real a = gt.ma, f = gt.jtf;
     a -= f; if (dl) { grad[d] = a; qfc[d] = f; }
     const real gn = gsum(g, a * a); PROF(11);            /* residual, forces, gradient */
 #ifdef RSB_EMU_TRACE
