@@ -1215,22 +1215,28 @@ RSB_DN GradTerms grad_terms_lane(int so, Grp g, int vo, int nefc) { const real *
    rows at nv = 15).  A sliding contact (ew < 0 marks its rows) adds J_c^T Hc J_c: t_a = sum_b Hc_ab J_bj first, then h[i] += J_ai t_a. */
 RSB_DN void newton_hessian(int so, Grp g, int nefc) { real *s = RSB_SMEM + so;
   const real *M = s + MDL.o_M, *J = s + MDL.o_J, *ew = s + MDL.o_ew, *con = s + MDL.o_con, *jar = s + MDL.o_ejar; real *H = s + MDL.o_L;
-  const int ldj = MDL.ldj, nv = MDL.nv, j = g.lane < nv ? g.lane : 0; const int *etid = (const int *)(s + MDL.o_etype);
+  const int ldj = MDL.ldj, nv = MDL.nv, j = g.lane < nv ? g.lane : 0;
   real h[RSB_LANES];
 #pragma unroll
   for (int i = 0; i < RSB_LANES; i++) h[i] = 0.0f;
-#pragma unroll 1
+  /* pass A, branch-free: every row with its clamped weight (inactive rows and cone rows carry w <= 0 -> 0); two rows per trip so that
+     the loads of one row overlap the FMAs of the other */
+#pragma unroll 2
   for (int r = 0; r < nefc; r++) {
-    const real w = ew[r]; const real *Jr = J + r * ldj;
-    if (w > 0) {
-      const real t = w * Jr[j];
+    const real *Jr = J + r * ldj; const real t = fmaxf(ew[r], 0.0f) * Jr[j];
 #pragma unroll
-      for (int i = 0; i < RSB_LANES; i++) if (i < nv) h[i] += Jr[i] * t;
-    } else if (w < 0 && ET_TYPE(etid[r]) == EFC_CONTACT_NORMAL) {   /* first row of a contact in the middle zone of its cone */
+    for (int i = 0; i < RSB_LANES; i++) if (i < nv) h[i] += Jr[i] * t;
+  }
+  /* pass B: contacts in the middle zone of their cone (ew < 0 on their rows) */
+  const int ncon = ((const int *)(s + MDL.o_misc))[MISC_NCON];
+#pragma unroll 1
+  for (int c = 0; c < ncon; c++) {
+    const real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr; const int r = ci[CON_ADR];
+    if (r >= 0 && ew[r] < 0) { const real *Jr = J + r * ldj;
       /* cone Hessian in scaled coordinates U = sc * x, U = (N, t), T = |t|, that = t / T:  Hu = Dm u u^T - kap (I_t - that that^T) with
          u = (1, -mu that), kap = Dm mu (N - mu T) / T.  Applied to column j without forming the dim x dim block:
          y = sc * J_c[:, j],  (Hu y)_a = Dm u_a (u.y) - kap (y_a - that_a (that.y)) [a >= 1],  t_a = sc_a (Hu y)_a. */
-      const real *cr = con + ET_ID(etid[r]) * RSB_CONW; const int *ci = (const int *)cr; const int dim = CON_DIM_OF(ci);
+      const int dim = CON_DIM_OF(ci);
       const real *fr = MDL.pair_friction + 5 * ci[CON_PAIR]; const real mu = cr[CON_MU], D = (s + MDL.o_eD)[r];
       real sc[RSB_MAXDIM], u[RSB_MAXDIM], y[RSB_MAXDIM], t[RSB_MAXDIM]; real T2 = 0, N = 0;
 #pragma unroll
