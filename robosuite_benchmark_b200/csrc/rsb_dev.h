@@ -1213,6 +1213,15 @@ RSB_DN GradTerms grad_terms_lane(int so, Grp g, int vo, int nefc) { const real *
 /* H = M + J^T W J (+ cone blocks) into the packed workspace at o_L.  Lane j owns COLUMN j and keeps h[i] = sum_r w_r J_ri J_rj for all
    i in registers: per constraint row one own-column load, then nv broadcast loads + FMAs (a lane-per-entry loop costs 8 passes over all
    rows at nv = 15).  A sliding contact (ew < 0 marks its rows) adds J_c^T Hc J_c: t_a = sum_b Hc_ab J_bj first, then h[i] += J_ai t_a. */
+/* pass A of newton_hessian for a compile-time number of dofs (NV = 0: run-time nv with per-term predicates) */
+template <int NV> RSB_D void hess_rows(const real *J, const real *ew, int ldj, int nv, int nefc, int j, real (&h)[RSB_LANES]) {
+#pragma unroll 2
+  for (int r = 0; r < nefc; r++) {
+    const real *Jr = J + r * ldj; const real t = fmaxf(ew[r], 0.0f) * Jr[j];
+#pragma unroll
+    for (int i = 0; i < RSB_LANES; i++) if (NV ? (i < NV) : (i < nv)) h[i] += Jr[i] * t;
+  }
+}
 RSB_DN void newton_hessian(int so, Grp g, int nefc) { real *s = RSB_SMEM + so;
   const real *M = s + MDL.o_M, *J = s + MDL.o_J, *ew = s + MDL.o_ew, *con = s + MDL.o_con, *jar = s + MDL.o_ejar; real *H = s + MDL.o_L;
   const int ldj = MDL.ldj, nv = MDL.nv, j = g.lane < nv ? g.lane : 0;
@@ -1221,12 +1230,9 @@ RSB_DN void newton_hessian(int so, Grp g, int nefc) { real *s = RSB_SMEM + so;
   for (int i = 0; i < RSB_LANES; i++) h[i] = 0.0f;
   /* pass A, branch-free: every row with its clamped weight (inactive rows and cone rows carry w <= 0 -> 0); two rows per trip so that
      the loads of one row overlap the FMAs of the other */
-#pragma unroll 2
-  for (int r = 0; r < nefc; r++) {
-    const real *Jr = J + r * ldj; const real t = fmaxf(ew[r], 0.0f) * Jr[j];
-#pragma unroll
-    for (int i = 0; i < RSB_LANES; i++) if (i < nv) h[i] += Jr[i] * t;
-  }
+  if (nv == 15) hess_rows<15>(J, ew, ldj, nv, nefc, j, h);          /* Lift-Panda / Lift-Sawyer (7 + 2 + 6 dofs) */
+  else if (nv == 11) hess_rows<11>(J, ew, ldj, nv, nefc, j, h);     /* Door-Panda */
+  else hess_rows<0>(J, ew, ldj, nv, nefc, j, h);
   /* pass B: contacts in the middle zone of their cone (ew < 0 on their rows) */
   const int ncon = ((const int *)(s + MDL.o_misc))[MISC_NCON];
 #pragma unroll 1
