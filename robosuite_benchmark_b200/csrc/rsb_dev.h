@@ -1192,27 +1192,10 @@ RSB_DN void efc_mulJ(int so, Grp g, int nefc, int xo, int yo, int sub_aref) { re
 RSB_DN real mulM_lane(int so, Grp g, int vo) { const real *s = RSB_SMEM + so;
   return g.lane < MDL.nv ? symv_row(s + MDL.o_M, g.lane, RSB_SMEM + vo, MDL.nv) : 0.0f;
 }
-/* lane d < nv: row d of M times the vector at vo AND (J^T force)[d], as one function so that the two independent load/FMA chains
-   interleave (each alone waits on its own shared-memory latency) */
-struct GradTerms { real ma, jtf; };
-RSB_DN GradTerms grad_terms_lane(int so, Grp g, int vo, int nefc) { const real *s = RSB_SMEM + so; GradTerms o; o.ma = 0; o.jtf = 0;
-  if (g.lane >= MDL.nv) return o;
-  const real *P = s + MDL.o_M, *v = RSB_SMEM + vo, *Jc = s + MDL.o_J + g.lane, *f = s + MDL.o_eforce; const int n = MDL.nv, ldj = MDL.ldj, i = g.lane;
-  real s0 = 0, s1 = 0, t0 = 0, t1 = 0; const int ri = tri_off(i); int tj = 0, j = 0, r = 0;
-  for (; j + 2 <= n; j += 2, r += 2) {                             /* symv_row and sdot_strided, two terms of each per trip */
-    const int i0 = (j <= i) ? ri + j : tj + i, u1 = tj + j + 1, i1 = (j + 1 <= i) ? ri + j + 1 : u1 + i;
-    const bool p0 = r < nefc, p1 = r + 1 < nefc;
-    const real m0 = P[i0], m1 = P[i1], v0 = v[j], v1 = v[j + 1], a0 = p0 ? Jc[r * ldj] : 0.0f, a1 = p1 ? Jc[(r + 1) * ldj] : 0.0f, f0 = p0 ? f[r] : 0.0f, f1 = p1 ? f[r + 1] : 0.0f;
-    s0 += m0 * v0; s1 += m1 * v1; t0 += a0 * f0; t1 += a1 * f1; tj = u1 + j + 2;
-  }
-  if (j < n) { const int i0 = (j <= i) ? ri + j : tj + i; s0 += P[i0] * v[j]; }
-  for (; r + 2 <= nefc; r += 2) { const real a0 = Jc[r * ldj], a1 = Jc[(r + 1) * ldj], f0 = f[r], f1 = f[r + 1]; t0 += a0 * f0; t1 += a1 * f1; }
-  if (r < nefc) t0 += Jc[r * ldj] * f[r];
-  o.ma = s0 + s1; o.jtf = t0 + t1; return o;
+/* lane d < nv: (J^T force)[d] */
+RSB_DN real mulJT_lane(int so, Grp g, int nefc) { const real *s = RSB_SMEM + so;
+  return g.lane < MDL.nv ? sdot_strided(s + MDL.o_J + g.lane, MDL.ldj, s + MDL.o_eforce, nefc) : 0.0f;
 }
-/* H = M + J^T W J (+ cone blocks) into the packed workspace at o_L.  Lane j owns COLUMN j and keeps h[i] = sum_r w_r J_ri J_rj for all
-   i in registers: per constraint row one own-column load, then nv broadcast loads + FMAs (a lane-per-entry loop costs 8 passes over all
-   rows at nv = 15).  A sliding contact (ew < 0 marks its rows) adds J_c^T Hc J_c: t_a = sum_b Hc_ab J_bj first, then h[i] += J_ai t_a. */
 /* pass A of newton_hessian for a compile-time number of dofs (NV = 0: run-time nv with per-term predicates) */
 template <int NV> RSB_D void hess_rows(const real *J, const real *ew, int ldj, int nv, int nefc, int j, real (&h)[RSB_LANES]) {
 #pragma unroll 2
@@ -1370,10 +1353,15 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
      0 and it is inactive from iteration 0 on, with qfc = 0 -- the same result as the early exit) */
   /* warm start: the cheaper of qacc_warmstart and qacc_smooth */
   PROF_LOCAL;
-  real cw = solver_cost(so, g, nefc, so + MDL.o_warm); gsync(g);
   real cs0 = solver_cost(so, g, nefc, so + MDL.o_qacc_smooth); gsync(g);
-  if (dl) { qacc[d] = (cw < cs0) ? warm[d] : qas[d]; tmpv[d] = 0; }
+  real cw = solver_cost(so, g, nefc, so + MDL.o_warm); gsync(g);       /* evaluated last: jar = J warm - aref stays in place for the usual choice */
+  const bool use_warm = cw < cs0;
+  if (dl) { qacc[d] = use_warm ? warm[d] : qas[d]; tmpv[d] = qacc[d] - qas[d]; }
   gsync(g);
+  if (sany(!use_warm)) efc_mulJ(so, g, nefc, so + MDL.o_qacc, so + MDL.o_ejar, 1);       /* (a group that did pick warm recomputes the same values) */
+  /* As in mj_solNewton the residuals jar = J qacc - aref and Ma = M (qacc - qacc_smooth) are carried along the iterations and updated with
+     the step (jar += alpha Jv, Ma += alpha Mv) instead of being recomputed from qacc; lane d keeps Ma_d and Mv_d in registers. */
+  real ma = mulM_lane(so, g, so + MDL.o_tmpv);
   const real scale = 1.0f / (MDL.meaninertia * (real)(nv > 1 ? nv : 1));
   PROF(10);                                            /* warm-start selection */
   /* `active` is uniform within a group; every branch that encloses a shuffle tests a warp vote, so the groups of a warp stay converged.
@@ -1381,15 +1369,11 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
   int iter = 0; bool active = true, last = false;                  /* last: the previous update improved the cost by less than the tolerance */
 #pragma unroll 1
   for (int it = 0; it <= MDL.solver_iters; it++) {
-    /* residual rows, forces, Hessian weights */
-    efc_mulJ(so, g, nefc, so + MDL.o_qacc, so + MDL.o_ejar, 1);
+    /* forces and Hessian weights at the current residuals; gradient = M (qacc - qacc_smooth) - J^T f (lane per dof) */
     efc_eval(so, g, true);
-    if (dl) tmpv[d] = qacc[d] - qas[d];
     gsync(g);
-    /* gradient = M (qacc - qacc_smooth) - J^T f  (lane per dof; the difference first: exact 0 on unconstrained dofs) */
-    const GradTerms gt = grad_terms_lane(so, g, so + MDL.o_tmpv, nefc);
-    real a = gt.ma, f = gt.jtf;
-    a -= f; if (dl) { grad[d] = a; qfc[d] = f; }
+    const real f = mulJT_lane(so, g, nefc), a = ma - f;
+    if (dl) { grad[d] = a; qfc[d] = f; }
     const real gn = gsum(g, a * a); PROF(11);            /* residual, forces, gradient */
 #ifdef RSB_EMU_TRACE
     if (g.lane == 0) printf("  it %d scaled|grad| %.3e\n", iter, scale * sqrtf(gn));
@@ -1402,20 +1386,31 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
     chol_factor_solve(so + MDL.o_L, nv, 0, so + MDL.o_search, g); PROF(13);
     /* directional quantities */
     real gq1 = 0, gq2 = 0, sg = 0;
-    { real ms = mulM_lane(so, g, so + MDL.o_search); if (dl) { gq2 = search[d] * ms; gq1 = search[d] * (grad[d] + qfc[d]); sg = search[d] * grad[d]; } }
+    const real mv = mulM_lane(so, g, so + MDL.o_search);
+    if (dl) { gq2 = search[d] * mv; gq1 = search[d] * ma; sg = search[d] * grad[d]; }
     efc_mulJ(so, g, nefc, so + MDL.o_search, so + MDL.o_eJv, 0);
     gsum3(g, gq1, gq2, sg);                                     /* gq1 = s.(M a - M a_s): slope of the Gauss term at alpha = 0; sg: slope of the total cost */
     /* exact line search on the convex 1-D cost: safeguarded Newton on its derivative, first trial step 1 (newton_linesearch) */
     const real d1_0 = fabsf(sg), alpha = newton_linesearch(so, g, gq1, gq2, sg, scale, active);
     PROF(14);                                          /* directional quantities + line search */
     if (active && alpha == 0) active = false;
-    if (active) { if (dl) qacc[d] += alpha * search[d]; iter++;
+    if (active) { if (dl) qacc[d] += alpha * search[d]; ma += alpha * mv; iter++;
+      real *jar = s + MDL.o_ejar; const real *Jv = s + MDL.o_eJv;
+      for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] += alpha * Jv[r];
       last = scale * 0.5f * alpha * d1_0 < MDL.solver_tol; }       /* cost decrease of an exact line search on a (locally) quadratic cost: alpha |d1(0)| / 2 */
     gsync(g);
     if (!sany(active)) break;
   }
   /* The loop evaluates forces at its top, so on every exit the forces correspond to the final qacc: an update is always followed by
-     another pass of the top part (the loop runs to it == solver_iters, where a still-active group is stopped before its next update). */
+     another pass of the top part (the loop runs to it == solver_iters, where a still-active group is stopped before its next update).
+     Those forces come from the residuals carried along the iterations; the constraint force handed to the integrator is evaluated once
+     more from residuals recomputed at the final qacc, so that the round-off of the incremental updates does not reach the state. */
+  if (sany(iter > 0)) {
+    efc_mulJ(so, g, nefc, so + MDL.o_qacc, so + MDL.o_ejar, 1);
+    efc_eval(so, g, true);
+    gsync(g);
+    const real f = mulJT_lane(so, g, nefc); if (dl) qfc[d] = f;
+  }
   if (g.lane == 0) misc[MISC_ITER] = iter;
   gsync(g);
 }
