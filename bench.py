@@ -26,7 +26,7 @@ if ROOT not in sys.path:
 ENV_NAME, ROBOT, CONTROLLER, SEED, HORIZON = "Lift", "Panda", "OSC_POSE", 17, 500
 METRIC, UNIT = "Lift-Panda-OSC env control-steps/s", "control-steps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch (4096 envs), ncu --set full capture of round 1 (profiles/r1_kstep_ncu_summary.md)
-KSTEP_DRAM_BYTES_PER_LAUNCH = 10529024 + 1549312
+KSTEP_DRAM_BYTES_PER_LAUNCH = 10565120 + 1346816
 PREROLL = 100          # untimed control steps after the initial reset (run_ours): the timed region sits on the steady-state part of the episode
 
 
