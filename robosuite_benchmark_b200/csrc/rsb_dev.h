@@ -1112,8 +1112,8 @@ RSB_DN void st_smooth_acc(int so, Grp g) { real *s = RSB_SMEM + so; const real *
    Work ITEMS, one per lane: the scalar rows (they come first) and the contacts (a contact's rows are handled from its first row); a
    lane-per-row loop would leave the friction rows' lanes idle and need two passes from 17 rows on.  The line search has its own
    evaluator (newton_linesearch). */
-RSB_DN real efc_eval(int so, Grp g, bool with_forces) { real *s = RSB_SMEM + so;
-  const real *con = s + MDL.o_con, *eD = s + MDL.o_eD, *jar = s + MDL.o_ejar;
+RSB_DN real efc_eval(int so, Grp g, bool with_forces, int jo) { real *s = RSB_SMEM + so;
+  const real *con = s + MDL.o_con, *eD = s + MDL.o_eD, *jar = RSB_SMEM + jo;      /* jo: the residual vector to evaluate (o_ejar; o_eJv holds a second candidate during warm-start selection) */
   real *force = s + MDL.o_eforce, *ew = s + MDL.o_ew; const int *etid = (const int *)(s + MDL.o_etype);
   real cost = 0;
   const int *misc = (const int *)(s + MDL.o_misc); const int nscalar = misc[MISC_NLIMROW], nitem = nscalar + misc[MISC_NCON];
@@ -1329,16 +1329,18 @@ RSB_DN real newton_linesearch(int so, Grp g, real gq1, real gq2, real sg, real s
   return alpha;
 }
 
-/* jar = J qacc - aref (lane per row); returns the total cost (Gauss + constraint), identical on all lanes */
-RSB_DN real solver_cost(int so, Grp g, int nefc, int qo) { real *s = RSB_SMEM + so; const real *qacc = RSB_SMEM + qo;
-  const real *qas = s + MDL.o_qacc_smooth;
-  efc_mulJ(so, g, nefc, qo, so + MDL.o_ejar, 1);
-  real *dq = s + MDL.o_tmpv;                                       /* qacc - qacc_smooth */
-  if (g.lane < MDL.nv) dq[g.lane] = qacc[g.lane] - qas[g.lane];
+/* residuals of TWO candidate accelerations in one pass over J (warm-start selection): y1 = J x1 - aref, y2 = J x2 - aref */
+RSB_DN void efc_mulJ2(int so, Grp g, int nefc, int x1o, int y1o, int x2o, int y2o) { real *s = RSB_SMEM + so;
+  const real *J = s + MDL.o_J, *x1 = RSB_SMEM + x1o, *x2 = RSB_SMEM + x2o, *earef = s + MDL.o_earef; real *y1 = RSB_SMEM + y1o, *y2 = RSB_SMEM + y2o;
+  const int nv = MDL.nv, ldj = MDL.ldj;
+#pragma unroll 1
+  for (int r = g.lane; r < nefc; r += RSB_LANES) {
+    const real *Jr = J + r * ldj; real a0 = 0, a1 = 0, b0 = 0, b1 = 0; int k = 0;
+    for (; k + 2 <= nv; k += 2) { const real j0 = Jr[k], j1 = Jr[k + 1], p0 = x1[k], p1 = x1[k + 1], q0 = x2[k], q1 = x2[k + 1]; a0 += j0 * p0; a1 += j1 * p1; b0 += j0 * q0; b1 += j1 * q1; }
+    if (k < nv) { const real j0 = Jr[k]; a0 += j0 * x1[k]; b0 += j0 * x2[k]; }
+    const real ar = earef[r]; y1[r] = (a0 + a1) - ar; y2[r] = (b0 + b1) - ar;
+  }
   gsync(g);
-  real gs = mulM_lane(so, g, so + MDL.o_tmpv); if (g.lane < MDL.nv) gs *= 0.5f * dq[g.lane];
-  gsync(g);
-  return gsum(g, gs + efc_eval(so, g, false));
 }
 
 RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
@@ -1353,15 +1355,22 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
      0 and it is inactive from iteration 0 on, with qfc = 0 -- the same result as the early exit) */
   /* warm start: the cheaper of qacc_warmstart and qacc_smooth */
   PROF_LOCAL;
-  real cs0 = solver_cost(so, g, nefc, so + MDL.o_qacc_smooth); gsync(g);
-  real cw = solver_cost(so, g, nefc, so + MDL.o_warm); gsync(g);       /* evaluated last: jar = J warm - aref stays in place for the usual choice */
-  const bool use_warm = cw < cs0;
-  if (dl) { qacc[d] = use_warm ? warm[d] : qas[d]; tmpv[d] = qacc[d] - qas[d]; }
+  /* cost(a) = (a - a_s)^T M (a - a_s) / 2 + s(J a - aref): both candidates' residuals from one pass over J (warm -> jar, smooth -> the Jv
+     array, free until the first search direction); the Gauss term of qacc_smooth is zero */
+  real *jar = s + MDL.o_ejar, *jas = s + MDL.o_eJv;
+  efc_mulJ2(so, g, nefc, so + MDL.o_warm, so + MDL.o_ejar, so + MDL.o_qacc_smooth, so + MDL.o_eJv);
+  if (dl) tmpv[d] = warm[d] - qas[d];
   gsync(g);
-  if (sany(!use_warm)) efc_mulJ(so, g, nefc, so + MDL.o_qacc, so + MDL.o_ejar, 1);       /* (a group that did pick warm recomputes the same values) */
+  const real mw = mulM_lane(so, g, so + MDL.o_tmpv);                /* lane d: (M (warm - qacc_smooth))_d */
+  real cw = efc_eval(so, g, false, so + MDL.o_ejar) + (dl ? 0.5f * tmpv[d] * mw : 0.0f), cs0 = efc_eval(so, g, false, so + MDL.o_eJv);
+  gsum2(g, cw, cs0);
+  const bool use_warm = cw < cs0;
+  if (dl) qacc[d] = use_warm ? warm[d] : qas[d];
+  if (!use_warm) for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] = jas[r];
+  gsync(g);
   /* As in mj_solNewton the residuals jar = J qacc - aref and Ma = M (qacc - qacc_smooth) are carried along the iterations and updated with
      the step (jar += alpha Jv, Ma += alpha Mv) instead of being recomputed from qacc; lane d keeps Ma_d and Mv_d in registers. */
-  real ma = mulM_lane(so, g, so + MDL.o_tmpv);
+  real ma = use_warm ? mw : 0.0f;
   const real scale = 1.0f / (MDL.meaninertia * (real)(nv > 1 ? nv : 1));
   PROF(10);                                            /* warm-start selection */
   /* `active` is uniform within a group; every branch that encloses a shuffle tests a warp vote, so the groups of a warp stay converged.
@@ -1370,7 +1379,7 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
 #pragma unroll 1
   for (int it = 0; it <= MDL.solver_iters; it++) {
     /* forces and Hessian weights at the current residuals; gradient = M (qacc - qacc_smooth) - J^T f (lane per dof) */
-    efc_eval(so, g, true);
+    efc_eval(so, g, true, so + MDL.o_ejar);
     gsync(g);
     const real f = mulJT_lane(so, g, nefc), a = ma - f;
     if (dl) { grad[d] = a; qfc[d] = f; }
@@ -1395,8 +1404,7 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
     PROF(14);                                          /* directional quantities + line search */
     if (active && alpha == 0) active = false;
     if (active) { if (dl) qacc[d] += alpha * search[d]; ma += alpha * mv; iter++;
-      real *jar = s + MDL.o_ejar; const real *Jv = s + MDL.o_eJv;
-      for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] += alpha * Jv[r];
+      for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] += alpha * jas[r];        /* jas = o_eJv holds J search here */
       last = scale * 0.5f * alpha * d1_0 < MDL.solver_tol; }       /* cost decrease of an exact line search on a (locally) quadratic cost: alpha |d1(0)| / 2 */
     gsync(g);
     if (!sany(active)) break;
@@ -1407,7 +1415,7 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
      more from residuals recomputed at the final qacc, so that the round-off of the incremental updates does not reach the state. */
   if (sany(iter > 0)) {
     efc_mulJ(so, g, nefc, so + MDL.o_qacc, so + MDL.o_ejar, 1);
-    efc_eval(so, g, true);
+    efc_eval(so, g, true, so + MDL.o_ejar);
     gsync(g);
     const real f = mulJT_lane(so, g, nefc); if (dl) qfc[d] = f;
   }
