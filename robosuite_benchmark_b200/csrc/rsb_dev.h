@@ -601,13 +601,17 @@ RSB_DNOINL int col_box_box(const real *pa, const real *Ra, const real *ha, const
   for (int k = 1; k < 3; k++) if (fabsf(nl[k]) > am) { am = fabsf(nl[k]); ia = k; }
   real isg = nl[ia] > 0 ? -1.0f : 1.0f; int u = (ia + 1) % 3, v = (ia + 2) % 3;
   real *poly = scr, *tmp = scr + 24; int np = 4;               /* a quad clipped by four half-planes has at most 8 vertices */
+  const int ru = (ax + 1) % 3, rv = (ax + 2) % 3; bool inside = true;
   for (int c = 0; c < 4; c++) {
     real su = (c == 0 || c == 3) ? -1.0f : 1.0f, sv = (c < 2) ? -1.0f : 1.0f; real wv[3], pv[3];
     for (int k = 0; k < 3; k++) wv[k] = pi[k] + isg * hi[ia] * Ri[3 * k + ia] + su * hi[u] * Ri[3 * k + u] + sv * hi[v] * Ri[3 * k + v] - pr[k];
     matTvec3(pv, Rr, wv); poly[3 * c] = pv[0]; poly[3 * c + 1] = pv[1]; poly[3 * c + 2] = pv[2];
+    const real pu = ru == 0 ? pv[0] : (ru == 1 ? pv[1] : pv[2]), pw = rv == 0 ? pv[0] : (rv == 1 ? pv[1] : pv[2]);
+    inside = inside && fabsf(pu) <= hr[ru] && fabsf(pw) <= hr[rv];
   }
-  int ru = (ax + 1) % 3, rv = (ax + 2) % 3;
-  for (int side = 0; side < 4; side++) {
+  /* the incident face lies inside the reference face (a small box resting on a large one: every vertex passes all four half-planes, so the
+     clipping below would copy the quad unchanged four times) */
+  for (int side = 0; side < (inside ? 0 : 4); side++) {
     int k = side < 2 ? ru : rv; real sg = (side & 1) ? -1.0f : 1.0f, lim = hr[k];
     int nn = 0;
     for (int c = 0; c < np; c++) {
