@@ -322,6 +322,9 @@ class SACTrainer:
         self.alpha = torch.tensor([1.0, 0.0], **f32)                 # [alpha, log_alpha] (device copy read by the kernels)
         self._alloc(self.B)
         self._graphs = {}
+        # side streams: the target-Q forward and the weight-gradient GEMMs do not lie on the update's dependency chain; inside the captured
+        # graph they become parallel branches (the update is launch-latency bound: ~55 kernels of 2-4 us each)
+        self._sT, self._sW = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
 
     # -- buffers
     def _alloc(self, B):
@@ -384,33 +387,44 @@ class SACTrainer:
         t.mm(self.H2p, P["p_W2"], out=self.OUT); self._bias_relu(self.OUT, P["p_b2"], 0)
         _chk(L.rsb_head_fwd(_ptr(self.OUT), _ptr(self.eps), 2 * B, A, _ptr(self.a_store), _ptr(self.logpi),
                             C.c_void_p(self.XQ.data_ptr() + 4 * O), QI, 0, B, C.c_void_p(self.XT.data_ptr() + 4 * O), QI, B, 2 * B, st))
-        # twin Q forward (batched over the two networks) on [(obs,a_new); (obs,act)] and target twin Q on (next_obs, a')
+        # twin Q forward (batched over the two networks) on [(obs,a_new); (obs,act)]; target twin Q on (next_obs, a') on a side stream
         XQ2, XT2 = self.XQ.unsqueeze(0).expand(2, 2 * B, QI), self.XT.unsqueeze(0).expand(2, B, QI)
+        main, sT, sW = t.cuda.current_stream(self.device), self._sT, self._sW
+        sT.wait_stream(main)
+        with t.cuda.stream(sT):
+            t.bmm(XT2, T["q_W0"], out=self.H1t); self._bias_relu(self.H1t, T["q_b0"], 1, 2)
+            t.bmm(self.H1t, T["q_W1"], out=self.H2t); self._bias_relu(self.H2t, T["q_b1"], 1, 2)
+            t.bmm(self.H2t, T["q_W2"], out=self.qt); self._bias_relu(self.qt, T["q_b2"], 0, 2)
         t.bmm(XQ2, P["q_W0"], out=self.H1q); self._bias_relu(self.H1q, P["q_b0"], 1, 2)
         t.bmm(self.H1q, P["q_W1"], out=self.H2q); self._bias_relu(self.H2q, P["q_b1"], 1, 2)
         t.bmm(self.H2q, P["q_W2"], out=self.q); self._bias_relu(self.q, P["q_b2"], 0, 2)
-        t.bmm(XT2, T["q_W0"], out=self.H1t); self._bias_relu(self.H1t, T["q_b0"], 1, 2)
-        t.bmm(self.H1t, T["q_W1"], out=self.H2t); self._bias_relu(self.H2t, T["q_b1"], 1, 2)
-        t.bmm(self.H2t, T["q_W2"], out=self.qt); self._bias_relu(self.qt, T["q_b2"], 0, 2)
+        main.wait_stream(sT)
         # losses and their gradients w.r.t. the Q outputs / log_alpha
         _chk(L.rsb_sac_losses(_ptr(self.q), _ptr(self.qt), _ptr(self.logpi), _ptr(self.rew), _ptr(self.term), _ptr(self.alpha),
                               self.reward_scale, self.discount, self.target_entropy, B, _ptr(self.dq), _ptr(self.y), _ptr(self.sums),
                               _ptr(G["log_alpha"]), st))
-        # twin-Q backward: weight grads from the Bellman rows [B, 2B) only, input grads for the policy rows [0, B)
-        t.bmm(self.H2q[:, B:].transpose(1, 2), self.dq[:, B:], out=G["q_W2"]); self._colsum(self.dq, B, 2 * B, G["q_b2"], 2)
+        # twin-Q backward: weight grads from the Bellman rows [B, 2B) only, input grads for the policy rows [0, B).  The input-gradient
+        # chain (dq -> dH2q -> dH1q -> gX -> policy head -> dH2p -> dH1p) runs on the main stream; every weight/bias gradient only needs the
+        # activation gradient of its own layer and goes to the side stream as soon as that exists.
+        def weight_grads(fn):
+            sW.wait_stream(main)
+            with t.cuda.stream(sW):
+                fn()
+        weight_grads(lambda: (t.bmm(self.H2q[:, B:].transpose(1, 2), self.dq[:, B:], out=G["q_W2"]), self._colsum(self.dq, B, 2 * B, G["q_b2"], 2)))
         t.bmm(self.dq, P["q_W2"].transpose(1, 2), out=self.dH2q); self._relu_bwd(self.dH2q, self.H2q)
-        t.bmm(self.H1q[:, B:].transpose(1, 2), self.dH2q[:, B:], out=G["q_W1"]); self._colsum(self.dH2q, B, 2 * B, G["q_b1"], 2)
+        weight_grads(lambda: (t.bmm(self.H1q[:, B:].transpose(1, 2), self.dH2q[:, B:], out=G["q_W1"]), self._colsum(self.dH2q, B, 2 * B, G["q_b1"], 2)))
         t.bmm(self.dH2q, P["q_W1"].transpose(1, 2), out=self.dH1q); self._relu_bwd(self.dH1q, self.H1q)
-        t.bmm(XQ2[:, B:].transpose(1, 2), self.dH1q[:, B:], out=G["q_W0"]); self._colsum(self.dH1q, B, 2 * B, G["q_b0"], 2)
+        weight_grads(lambda: (t.bmm(XQ2[:, B:].transpose(1, 2), self.dH1q[:, B:], out=G["q_W0"]), self._colsum(self.dH1q, B, 2 * B, G["q_b0"], 2)))
         t.mm(self.dH1q[0, :B], P["q_W0"][0].t(), out=self.gX); self.gX.addmm_(self.dH1q[1, :B], P["q_W0"][1].t())
         # policy backward
         _chk(L.rsb_head_bwd(_ptr(self.OUT), _ptr(self.eps), _ptr(self.a_store), 2 * B, B, A, _ptr(self.alpha),
-                            C.c_void_p(self.gX.data_ptr() + 4 * O), QI, _ptr(self.dOUT), st))
-        t.mm(self.H2p[:B].t(), self.dOUT[:B], out=G["p_W2"]); self._colsum(self.dOUT, 0, B, G["p_b2"])
+                            C.c_void_p(self.gX.data_ptr() + 4 * O), QI, _ptr(self.dOUT), _stream(self.device)))
+        weight_grads(lambda: (t.mm(self.H2p[:B].t(), self.dOUT[:B], out=G["p_W2"]), self._colsum(self.dOUT, 0, B, G["p_b2"])))
         t.mm(self.dOUT[:B], P["p_W2"].t(), out=self.dH2p); self._relu_bwd(self.dH2p, self.H2p[:B])
-        t.mm(self.H1p[:B].t(), self.dH2p, out=G["p_W1"]); self._colsum(self.dH2p, 0, B, G["p_b1"])
+        weight_grads(lambda: (t.mm(self.H1p[:B].t(), self.dH2p, out=G["p_W1"]), self._colsum(self.dH2p, 0, B, G["p_b1"])))
         t.mm(self.dH2p, P["p_W1"].t(), out=self.dH1p); self._relu_bwd(self.dH1p, self.H1p[:B])
-        t.mm(self.Xp[:B].t(), self.dH1p, out=G["p_W0"]); self._colsum(self.dH1p, 0, B, G["p_b0"])
+        weight_grads(lambda: (t.mm(self.Xp[:B].t(), self.dH1p, out=G["p_W0"]), self._colsum(self.dH1p, 0, B, G["p_b0"])))
+        main.wait_stream(sW)
 
     def _apply(self, do_soft):
         s = self.store
