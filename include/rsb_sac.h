@@ -20,6 +20,9 @@ const char *rsb_sac_last_error(void);
    Row b of the batch takes ring row idx_b = mulhi32(Philox4x32-10(key=seed, ctr=(b, step_lo, step_hi, 0xB0FFE7)).word0, size). */
 int rsb_replay_sample(const float *d_obs, const float *d_act, const float *d_rew, const uint8_t *d_term, const float *d_next, int size, int obs_dim, int act_dim,
                       uint64_t seed, uint64_t step, int batch, float *b_obs, int ld_obs, float *b_act, float *b_rew, float *b_term, float *b_next, int ld_next, int *b_idx, void *stream);
+/* inputs of one update from the sampled batch (SACTrainer.train_from_torch's obs/actions/next_obs unpacking, util/rlkit_custom.py:238): Xp[2B,O] = [obs; next_obs],
+   act[B,A] -> XQ[2B,O+A] = [(obs, -); (obs, act)], XT[B,O+A] = (next_obs, -); clears the loss accumulators d_sums[nsums] and the log-alpha gradient */
+int rsb_sac_prepare(const float *d_xp, const float *d_act, float *d_xq, float *d_xt, float *d_sums, int nsums, float *d_g_log_alpha, int batch, int obs_dim, int act_dim, void *stream);
 int rsb_normal(uint64_t seed, uint64_t step, uint32_t stream_id, int n, float *d_out, void *stream);
 int rsb_bias_relu(float *d_x, const float *d_bias, int rows, int cols, int relu, int nmat, long mat_stride, int bias_stride, void *stream);
 int rsb_relu_bwd(float *d_dy, const float *d_y, long n, void *stream);

@@ -61,6 +61,7 @@ def lib():
         L.rsb_sac_last_error.restype = C.c_char_p
         V, I, F, U64, L_ = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_long
         L.rsb_replay_sample.argtypes = [V, V, V, V, V, I, I, I, U64, U64, I, V, I, V, V, V, V, I, V, V]
+        L.rsb_sac_prepare.argtypes = [V, V, V, V, V, I, V, I, I, I, V]
         L.rsb_normal.argtypes = [U64, U64, C.c_uint32, I, V, V]
         L.rsb_bias_relu.argtypes = [V, V, I, I, I, I, L_, I, V]
         L.rsb_relu_bwd.argtypes = [V, V, L_, V]
@@ -75,7 +76,7 @@ def lib():
 
 EXPORTS = ["rsb_last_error", "rsb_sizeof_model", "rsb_sizeof_task", "rsb_create", "rsb_destroy", "rsb_info", "rsb_reset",
            "rsb_step", "rsb_step_host", "rsb_reset_host", "rsb_random_actions", "rsb_get_state", "rsb_set_state",
-           "rsb_debug_substep", "rsb_sac_last_error", "rsb_replay_sample", "rsb_normal", "rsb_bias_relu", "rsb_relu_bwd",
+           "rsb_debug_substep", "rsb_sac_last_error", "rsb_sac_prepare", "rsb_replay_sample", "rsb_normal", "rsb_bias_relu", "rsb_relu_bwd",
            "rsb_colsum", "rsb_head_fwd", "rsb_head_bwd", "rsb_sac_losses", "rsb_adam_polyak"]
 
 

@@ -171,8 +171,26 @@ __global__ void k_adam_tick(double *__restrict__ bc, double b1, double b2) {
   double p1 = bc[2] * b1, p2 = bc[3] * b2; bc[2] = p1; bc[3] = p2; bc[0] = 1.0 - p1; bc[1] = sqrt(1.0 - p2);
 }
 
+/* Inputs of the update from the sampled batch, in one launch: XQ[2B, O+A] = [(obs, .) ; (obs, act)] (the first B action slots are filled by
+   the policy head later), XT[B, O+A] = (next_obs, .), and the loss accumulators cleared.  Xp[2B, O] = [obs ; next_obs] as sampled. */
+__global__ void k_sac_prepare(const float *__restrict__ Xp, const float *__restrict__ act, float *__restrict__ XQ, float *__restrict__ XT,
+                              float *__restrict__ sums, int nsums, float *__restrict__ g_log_alpha, int B, int O, int A) {
+  const int QI = O + A, i = blockIdx.x * blockDim.x + threadIdx.x, n = 2 * B * QI;
+  if (i < nsums) sums[i] = 0.0f;
+  if (i == 0) g_log_alpha[0] = 0.0f;
+  if (i >= n) return;
+  const int r = i / QI, c = i - r * QI;                          /* row of XQ */
+  const int b = r < B ? r : r - B;
+  if (c < O) { const float v = Xp[(size_t)b * O + c]; XQ[i] = v; if (r < B) XT[(size_t)b * QI + c] = Xp[(size_t)(B + b) * O + c]; }
+  else if (r >= B) XQ[i] = act[(size_t)b * A + (c - O)];
+}
+
 extern "C" {
 const char *rsb_sac_last_error(void) { return g_sac_err.c_str(); }
+int rsb_sac_prepare(const float *d_xp, const float *d_act, float *d_xq, float *d_xt, float *d_sums, int nsums, float *d_g_log_alpha, int batch, int obs_dim, int act_dim, void *stream) {
+  int n = 2 * batch * (obs_dim + act_dim); if (n < nsums) n = nsums;
+  k_sac_prepare<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_xp, d_act, d_xq, d_xt, d_sums, nsums, d_g_log_alpha, batch, obs_dim, act_dim); CKS(cudaGetLastError()); return 0;
+}
 
 int rsb_replay_sample(const float *d_obs, const float *d_act, const float *d_rew, const uint8_t *d_term, const float *d_next, int size, int obs_dim, int act_dim,
                       uint64_t seed, uint64_t step, int batch, float *b_obs, int ld_obs, float *b_act, float *b_rew, float *b_term, float *b_next, int ld_next, int *b_idx, void *stream) {

@@ -376,9 +376,7 @@ class SACTrainer:
         P, G, T = s.P, s.G, s.T
         st = _stream(self.device)
         # inputs
-        self.XQ[:B, :O].copy_(self.Xp[:B]); self.XQ[B:, :O].copy_(self.Xp[:B]); self.XQ[B:, O:].copy_(self.act)
-        self.XT[:, :O].copy_(self.Xp[B:])
-        self.sums.zero_(); G["log_alpha"].zero_()
+        _chk(L.rsb_sac_prepare(_ptr(self.Xp), _ptr(self.act), _ptr(self.XQ), _ptr(self.XT), _ptr(self.sums), self.sums.numel(), _ptr(G["log_alpha"]), B, O, A, st))
         if not external_eps:
             _chk(L.rsb_normal(C.c_uint64(self.seed), C.c_uint64(step_for_noise), 7, 2 * B * A, _ptr(self.eps), st))
         # policy forward on [obs; next_obs]
