@@ -61,9 +61,19 @@ void emu_sync() { int l = S.cur; swapcontext(&S.lane_ctx[l], &S.main_ctx); }
 float emu_shfl_f(float v, int src) { int l = S.cur; S.xf[l] = v; emu_sync(); float r = S.xf[src & (NL - 1)]; emu_sync(); return r; }
 int emu_shfl_i(int v, int src) { int l = S.cur; S.xi[l] = v; emu_sync(); int r = S.xi[src & (NL - 1)]; emu_sync(); return r; }
 
+/* the shared-memory image sits between two guard zones: a write outside the env's slice (which on the GPU would land in the neighbour
+   env's slice) trips check_guards() */
+constexpr int GUARD = 64;
+constexpr uint32_t GUARD_WORD = 0x7fc0dead;
 struct EmuEnv {
   RsbHostModel hm; DevModel dm;
   std::vector<float> smem, state, dbg;
+  float *slice() { return smem.data() + GUARD; }
+  void arm() { for (int i = 0; i < GUARD; i++) { memcpy(&smem[(size_t)i], &GUARD_WORD, 4); memcpy(&smem[smem.size() - 1 - (size_t)i], &GUARD_WORD, 4); } }
+  void check_guards() const {
+    for (int i = 0; i < GUARD; i++) { uint32_t a, b; memcpy(&a, &smem[(size_t)i], 4); memcpy(&b, &smem[smem.size() - 1 - (size_t)i], 4);
+      if (a != GUARD_WORD || b != GUARD_WORD) { fprintf(stderr, "rsb_emu: write outside the env's shared-memory slice (guard word %d)\n", i); abort(); } }
+  }
 };
 
 extern "C" {
@@ -72,7 +82,7 @@ void *emu_create(const rsb_model *m, const rsb_task *t, int ncon_max, int nefc_m
   EmuEnv *e = new EmuEnv();
   if (!rsb_build_host_model(m, t, ncon_max, nefc_max, e->hm)) { fprintf(stderr, "rsb_emu: %s\n", e->hm.error.c_str()); delete e; return nullptr; }
   e->dm = e->hm.dm; rsb_fixup_pointers(e->dm, e->hm.arena.data());
-  e->smem.assign((size_t)e->dm.smem_words, 0.0f); e->state.assign((size_t)e->dm.st_words, 0.0f);
+  e->smem.assign((size_t)e->dm.smem_words + 2 * GUARD, 0.0f); e->arm(); e->state.assign((size_t)e->dm.st_words, 0.0f);
   e->dbg.assign((size_t)RSB_DBG_WORDS(e->dm.nv, ncon_max, nefc_max), 0.0f);
   return e;
 }
@@ -92,22 +102,24 @@ void emu_set_state(void *h, const float *in) { EmuEnv *e = (EmuEnv *)h; memcpy(e
 
 void emu_reset(void *h, uint64_t seed, uint64_t env_id, float *obs) {
   EmuEnv *e = (EmuEnv *)h;
-  emu_model = e->dm; emu_smem = e->smem.data();
+  emu_model = e->dm; emu_smem = e->slice();
   run_group([&](int lane) { Grp g{lane, (RSB_LANES == 32) ? 0xffffffffu : ((1u << RSB_LANES) - 1u)}; env_reset(0, g, e->state.data(), seed, env_id, obs, true); });
+  e->check_guards();
 }
 int emu_step(void *h, const float *action, float *obs, float *reward) {
   EmuEnv *e = (EmuEnv *)h; unsigned char done = 0;
-  if (g_do_fill) std::fill(e->smem.begin(), e->smem.end(), g_fill);
-  emu_model = e->dm; emu_smem = e->smem.data();
+  if (g_do_fill) { std::fill(e->smem.begin(), e->smem.end(), g_fill); e->arm(); }
+  emu_model = e->dm; emu_smem = e->slice();
   run_group([&](int lane) { Grp g{lane, (RSB_LANES == 32) ? 0xffffffffu : ((1u << RSB_LANES) - 1u)}; env_step(0, g, e->state.data(), action, obs, reward, &done, true); });
+  e->check_guards();
   return done;
 }
 /* one physics substep from the stored state, state written back, internals dumped */
 void emu_debug_substep(void *h, const float *action, int policy_step, float *dbg) {
   EmuEnv *e = (EmuEnv *)h;
-  emu_model = e->dm; emu_smem = e->smem.data();
+  emu_model = e->dm; emu_smem = e->slice();
   run_group([&](int lane) {
-    Grp g{lane, (RSB_LANES == 32) ? 0xffffffffu : ((1u << RSB_LANES) - 1u)}; const DevModel &m = e->dm; float *s = e->smem.data();
+    Grp g{lane, (RSB_LANES == 32) ? 0xffffffffu : ((1u << RSB_LANES) - 1u)}; const DevModel &m = e->dm; float *s = e->slice();
     load_state(0, e->state.data(), g);
     for (int i = g.lane; i < m.act_dim; i += RSB_LANES) s[m.o_act + i] = action[i];
     gsync(g);
@@ -115,6 +127,7 @@ void emu_debug_substep(void *h, const float *action, int policy_step, float *dbg
     dump_debug(0, g, dbg);
     store_state(0, e->state.data(), g);
   });
+  e->check_guards();
 }
 void emu_random_action(void *h, uint64_t seed, uint64_t env_id, uint64_t step, float *action) {
   EmuEnv *e = (EmuEnv *)h; for (int blk = 0; 4 * blk < e->dm.act_dim; blk++) random_action_block(seed, env_id, step, blk, e->dm.act_dim, action);
