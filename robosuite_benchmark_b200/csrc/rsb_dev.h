@@ -742,15 +742,6 @@ RSB_D real impedance_fn(const real *si, real pos, real margin) {
   else y = 1 - powf(1 - x, pw) / powf(1 - mid, pw - 1);
   return d0 + y * (d1 - d0);
 }
-RSB_D void kb_fn(const real *solref, const real *solimp, real *K, real *B) {
-  real dmax = solimp[1];
-  if (solref[0] > 0) {
-    real tc = fmaxf(solref[0], 2 * MDL.timestep), dr = solref[1];
-    real k = dmax * dmax * tc * tc * dr * dr; *K = 1 / fmaxf(k, RSB_MINVAL);
-    *B = 2 / fmaxf(dmax * tc, RSB_MINVAL);
-  } else { *K = -solref[0] / fmaxf(dmax * dmax, RSB_MINVAL); *B = -solref[1] / fmaxf(dmax, RSB_MINVAL); }
-}
-
 RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
   const real *qpos = s + MDL.o_qpos, *qvel = s + MDL.o_qvel, *cdof = s + MDL.o_cdof, *xpos = s + MDL.o_xpos;
   real *con = s + MDL.o_con, *J = s + MDL.o_J; int *misc = (int *)(s + MDL.o_misc);
@@ -791,14 +782,23 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
     else v = (MDL.jnt_dadr[ET_ID(w)] == d) ? (ET_NEG(w) ? -1.0f : 1.0f) : 0.0f;
     J[r * ldj + d] = v;
   }
+  /* first tangent of every contact frame, once per contact (the item loop below would rebuild the frame for each of a contact's nv items);
+     kept in the Hessian-weight array, which the solver only writes later.  Needs 3 ncon_max <= nefc_max (checked at create). */
+  real *tcache = s + MDL.o_ew;
+  if (MDL.frame_cache) {
+    for (int c = g.lane; c < ncon; c += RSB_LANES) { const real *cr = con + c * RSB_CONW; real fr[9] = {cr[3], cr[4], cr[5], 0, 0, 0, 0, 0, 0}; make_frame(fr);
+      tcache[3 * c] = fr[3]; tcache[3 * c + 1] = fr[4]; tcache[3 * c + 2] = fr[5]; }
+    gsync(g);
+  }
   /* contact rows of J: item = (contact, dof) */
   for (int i = g.lane; i < ncon * nvp; i += RSB_LANES) {
     int c = i >> MDL.nvsh, d = i & (nvp - 1); if (d >= nv) continue;
     const real *cr = con + c * RSB_CONW; const int *ci = (const int *)cr;
     int adr = ci[CON_ADR]; if (adr < 0) continue;
-    int dim = CON_DIM_OF(ci), b1 = MDL.geom_body[CON_G1_OF(ci)], b2 = MDL.geom_body[CON_G2_OF(ci)];
-    real fr[9] = {cr[3], cr[4], cr[5], 0, 0, 0, 0, 0, 0}; make_frame(fr);
-    int sgn = ((MDL.body_dofmask[b2] >> d) & 1) - ((MDL.body_dofmask[b1] >> d) & 1);
+    const int pr_ = ci[CON_PAIR], dim = MDL.pair_dim[pr_];
+    real fr[9] = {cr[3], cr[4], cr[5], 0, 0, 0, 0, 0, 0};
+    if (MDL.frame_cache) { fr[3] = tcache[3 * c]; fr[4] = tcache[3 * c + 1]; fr[5] = tcache[3 * c + 2]; cross3(fr + 6, fr, fr + 3); } else make_frame(fr);
+    int sgn = ((MDL.pair_dm2[pr_] >> d) & 1) - ((MDL.pair_dm1[pr_] >> d) & 1);
     real jp[3] = {0, 0, 0}, jr[3] = {0, 0, 0};
     if (sgn != 0) {
       int r = MDL.dof_root[d]; real off[3] = {cr[0] - xpos[3 * r], cr[1] - xpos[3 * r + 1], cr[2] - xpos[3 * r + 2]}, t[3];
@@ -820,15 +820,14 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
   gsync(g);
   /* impedance, regulariser, reference acceleration (mj_makeImpedance), lane per row */
   for (int r = g.lane; r < nefc; r += RSB_LANES) {
-    const real *solref, *solimp; real diag; int type = ET_TYPE(etid[r]), id = ET_ID(etid[r]);
-    if (type == EFC_FRICTION) { solref = MDL.dof_solref + 2 * id; solimp = MDL.dof_solimp + 5 * id; diag = MDL.dof_invw[id]; }
-    else if (type == EFC_LIMIT) { solref = MDL.jnt_solref + 2 * id; solimp = MDL.jnt_solimp + 5 * id; diag = MDL.dof_invw[MDL.jnt_dadr[id]]; }
+    const real *solimp, *kb; real diag; int type = ET_TYPE(etid[r]), id = ET_ID(etid[r]);       /* (K, B) and the inverse weights are host-side tables */
+    if (type == EFC_FRICTION) { kb = MDL.dof_kb + 2 * id; solimp = MDL.dof_solimp + 5 * id; diag = MDL.dof_invw[id]; }
+    else if (type == EFC_LIMIT) { kb = MDL.jnt_kb + 2 * id; solimp = MDL.jnt_solimp + 5 * id; diag = MDL.dof_invw[MDL.jnt_dadr[id]]; }
     else {
       const int *ci = (const int *)(con + id * RSB_CONW); int p = ci[CON_PAIR], rr = r - ci[CON_ADR];
-      solref = MDL.pair_solref + 2 * p; solimp = MDL.pair_solimp + 5 * p; int o = rr < 3 ? 0 : 1;
-      diag = MDL.body_invw[2 * MDL.geom_body[CON_G1_OF(ci)] + o] + MDL.body_invw[2 * MDL.geom_body[CON_G2_OF(ci)] + o];
+      kb = MDL.pair_kb + 2 * p; solimp = MDL.pair_solimp + 5 * p; diag = MDL.pair_invw[2 * p + (rr < 3 ? 0 : 1)];
     }
-    real K, B; kb_fn(solref, solimp, &K, &B);
+    real K = kb[0]; const real B = kb[1];
     if (type == EFC_FRICTION || type == EFC_CONTACT_FRICTION) K = 0;
     real imp = impedance_fn(solimp, epos[r], emargin[r]);
     real Rr = fmaxf((1 - imp) / imp * diag, RSB_MINVAL); eR[r] = Rr;

@@ -23,7 +23,7 @@
   X(dof_body) X(dof_jnt) X(dof_parent) X(dof_kind) X(dof_velstart) X(dof_velmask) X(dof_root) \
   X(mpair_i) X(mpair_j) X(tri_ij) \
   X(geom_type) X(geom_body) X(site_body) \
-  X(pair_g1) X(pair_g2) X(pair_dim) \
+  X(pair_g1) X(pair_g2) X(pair_dim) X(pair_dm1) X(pair_dm2) \
   X(act_dof) X(act_climited) X(act_flimited) \
   X(fl_dof) X(lim_jnt)
 /* float arrays */
@@ -33,7 +33,7 @@
   X(dof_armature) X(dof_damping) X(dof_floss) X(dof_invw) X(dof_solref) X(dof_solimp) \
   X(qpos0) X(qpos_spring) \
   X(geom_size) X(geom_pos) X(geom_mat) X(geom_rbound) X(site_pos) X(site_mat) \
-  X(pair_friction) X(pair_solref) X(pair_solimp) X(pair_margin) X(pair_gap) \
+  X(pair_friction) X(pair_solref) X(pair_solimp) X(pair_margin) X(pair_gap) X(pair_invw) X(pair_kb) X(dof_kb) X(jnt_kb) \
   X(act_gain) X(act_bias) X(act_crange) X(act_frange) X(act_gear)
 
 enum { RSB_DOF_HINGE = 0, RSB_DOF_SLIDE = 1, RSB_DOF_FREE_T = 2, RSB_DOF_FREE_R = 3 };
@@ -58,6 +58,7 @@ typedef struct DevModel {
   /* sizes */
   int nq, nv, nu, nbody, njnt, ngeom, nsite, npair, nmpair, nfl, nlimj, ncon_max, nefc_max;
   int ldm, ldj;                /* ldm: unused (M, H and the factor are PACKED lower triangles, entry (i,j), j<=i, at i(i+1)/2+j); ldj: row length of J (nv|1) */
+  int frame_cache;             /* 1: contact tangents cached in the ew array during the constraint stage (3 ncon_max <= nefc_max) */
   int lockstep;                /* bit k: CTA barrier after stage k (all warps of a CTA fetch the same code together) */
   int cs_words;                /* controller state words per robot held in shared memory (21 for OSC laws, RSB_CS_WORDS otherwise) */
   int ntri, nvsh;              /* lower-triangle entry count nv(nv+1)/2 (table tri_ij = i<<8|j); log2 of the power of two >= nv */
@@ -152,7 +153,7 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
     if (!ok) { h.error = "unsupported geom type pair in candidate contact list"; return false; }
   }
   d.nq = m->nq; d.nv = m->nv; d.nu = m->nu; d.nbody = m->nbody; d.njnt = m->njnt; d.ngeom = m->ngeom; d.nsite = m->nsite; d.npair = m->npair;
-  d.ncon_max = ncon_max; d.nefc_max = nefc_max; d.ldm = m->nv | 1; d.ldj = m->nv | 1;
+  d.ncon_max = ncon_max; d.nefc_max = nefc_max; d.frame_cache = (3 * ncon_max <= nefc_max) ? 1 : 0; d.ldm = m->nv | 1; d.ldj = m->nv | 1;
   d.timestep = (float)m->timestep; for (int k = 0; k < 3; k++) d.gravity[k] = (float)m->gravity[k];
   d.impratio = (float)m->impratio; d.meaninertia = (float)m->meaninertia; d.cone = m->cone;
   d.solver_iters = 12; d.ls_iters = 24; d.solver_tol = 1e-6f; d.ls_tol = 1e-2f;   /* MuJoCo ls_tolerance default */ d.lockstep = 0x1ff;
@@ -203,6 +204,22 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
   SETI(dof_kind, dkind); SETI(dof_velstart, dvs); SETI(dof_velmask, dvm); SETI(dof_root, droot); SETI(mpair_i, mi); SETI(mpair_j, mj); SETI(tri_ij, tri);
   SETI(geom_type, vi(m->geom_type, m->ngeom)); SETI(geom_body, vi(m->geom_bodyid, m->ngeom)); SETI(site_body, vi(m->site_bodyid, m->nsite));
   SETI(pair_g1, vi(m->pair_geom1, m->npair)); SETI(pair_g2, vi(m->pair_geom2, m->npair)); SETI(pair_dim, vi(m->pair_condim, m->npair));
+  /* per-pair / per-dof / per-joint constants the constraint stage would otherwise chase through three dependent loads or recompute with
+     divisions every substep: the two bodies' ancestor-dof masks, the summed inverse weights (translation, rotation), and (K, B) of the
+     reference acceleration (mj_makeImpedance: functions of solref, solimp[1] and the timestep only) */
+  std::vector<int> pdm1((size_t)m->npair), pdm2((size_t)m->npair); std::vector<float> pinvw((size_t)m->npair * 2), pkb((size_t)m->npair * 2), dkb((size_t)m->nv * 2), jkb((size_t)m->njnt * 2);
+  auto kb = [&](const double *solref, const double *solimp, float *out) {
+    float dmax = (float)solimp[1], K, B, minval = 1e-15f;
+    if ((float)solref[0] > 0) { float tc = fmaxf((float)solref[0], 2 * (float)m->timestep), dr = (float)solref[1]; float k = dmax * dmax * tc * tc * dr * dr; K = 1 / fmaxf(k, minval); B = 2 / fmaxf(dmax * tc, minval); }
+    else { K = -(float)solref[0] / fmaxf(dmax * dmax, minval); B = -(float)solref[1] / fmaxf(dmax, minval); }
+    out[0] = K; out[1] = B; };
+  for (int p = 0; p < m->npair; p++) { int b1 = m->geom_bodyid[m->pair_geom1[p]], b2 = m->geom_bodyid[m->pair_geom2[p]];
+    pdm1[(size_t)p] = dofmask[(size_t)b1]; pdm2[(size_t)p] = dofmask[(size_t)b2];
+    for (int o = 0; o < 2; o++) pinvw[(size_t)p * 2 + o] = (float)m->body_invweight0[2 * b1 + o] + (float)m->body_invweight0[2 * b2 + o];
+    kb(m->pair_solref + 2 * p, m->pair_solimp + 5 * p, &pkb[(size_t)p * 2]); }
+  for (int i = 0; i < m->nv; i++) kb(m->dof_solref + 2 * i, m->dof_solimp + 5 * i, &dkb[(size_t)i * 2]);
+  for (int j = 0; j < m->njnt; j++) kb(m->jnt_solref + 2 * j, m->jnt_solimp + 5 * j, &jkb[(size_t)j * 2]);
+  SETI(pair_dm1, pdm1); SETI(pair_dm2, pdm2);
   SETI(act_dof, vi(m->act_dofid, m->nu)); SETI(act_climited, vi(m->act_ctrllimited, m->nu)); SETI(act_flimited, vi(m->act_forcelimited, m->nu));
   SETI(fl_dof, fl_dof); SETI(lim_jnt, lim_jnt);
   SETF(body_pos, vf(m->body_pos, 3 * m->nbody)); SETF(body_quat, vf(m->body_quat, 4 * m->nbody)); SETF(body_ipos, vf(m->body_ipos, 3 * m->nbody));
@@ -218,6 +235,7 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
   SETF(geom_rbound, vf(m->geom_rbound, m->ngeom)); SETF(site_pos, vf(m->site_pos, 3 * m->nsite)); SETF(site_mat, smat);
   SETF(pair_friction, vf(m->pair_friction, 5 * m->npair)); SETF(pair_solref, vf(m->pair_solref, 2 * m->npair));
   SETF(pair_solimp, vf(m->pair_solimp, 5 * m->npair)); SETF(pair_margin, vf(m->pair_margin, m->npair)); SETF(pair_gap, vf(m->pair_gap, m->npair));
+  SETF(pair_invw, pinvw); SETF(pair_kb, pkb); SETF(dof_kb, dkb); SETF(jnt_kb, jkb);
   SETF(act_gain, vf(m->act_gain, m->nu)); SETF(act_bias, vf(m->act_bias, 3 * m->nu)); SETF(act_crange, vf(m->act_ctrlrange, 2 * m->nu));
   SETF(act_frange, vf(m->act_forcerange, 2 * m->nu)); SETF(act_gear, vf(m->act_gear, m->nu));
 #undef SETI
