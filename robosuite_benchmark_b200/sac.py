@@ -296,7 +296,7 @@ class SACTrainer:
     def __init__(self, env=None, policy=None, qf1=None, qf2=None, target_qf1=None, target_qf2=None, *, store: ParamStore = None,
                  replay_buffer: EnvReplayBuffer = None, batch_size=128, discount=0.99, reward_scale=1.0, policy_lr=1e-3, qf_lr=1e-3,
                  soft_target_tau=1e-2, target_update_period=1, use_automatic_entropy_tuning=True, target_entropy=None,
-                 seed=0, tf32=True, use_graph=True, world_size=1):
+                 seed=0, tf32=True, use_graph=True, world_size=1, parallel_branches=True):
         import torch
         if store is None:
             store = policy.store
@@ -325,6 +325,7 @@ class SACTrainer:
         # side streams: the target-Q forward and the weight-gradient GEMMs do not lie on the update's dependency chain; inside the captured
         # graph they become parallel branches (the update is launch-latency bound: ~55 kernels of 2-4 us each)
         self._sT, self._sW = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        self.parallel_branches = bool(parallel_branches)          # False: everything on one stream (the reference order; tests compare the two)
 
     # -- buffers
     def _alloc(self, B):
@@ -387,7 +388,8 @@ class SACTrainer:
                             C.c_void_p(self.XQ.data_ptr() + 4 * O), QI, 0, B, C.c_void_p(self.XT.data_ptr() + 4 * O), QI, B, 2 * B, st))
         # twin Q forward (batched over the two networks) on [(obs,a_new); (obs,act)]; target twin Q on (next_obs, a') on a side stream
         XQ2, XT2 = self.XQ.unsqueeze(0).expand(2, 2 * B, QI), self.XT.unsqueeze(0).expand(2, B, QI)
-        main, sT, sW = t.cuda.current_stream(self.device), self._sT, self._sW
+        main = t.cuda.current_stream(self.device)
+        sT, sW = (self._sT, self._sW) if self.parallel_branches else (main, main)
         sT.wait_stream(main)
         with t.cuda.stream(sT):
             t.bmm(XT2, T["q_W0"], out=self.H1t); self._bias_relu(self.H1t, T["q_b0"], 1, 2)

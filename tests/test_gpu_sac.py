@@ -124,3 +124,24 @@ def test_tf32_graph_update_close_to_oracle_and_to_eager(torch_cuda):
         # relative Frobenius error of each gradient tensor <= 5 % (the fp32 mode of the same code is held to 2e-5 above)
         d = store3.G[k].cpu().numpy() - gr.numpy()
         assert np.linalg.norm(d) <= 5e-2 * max(np.linalg.norm(gr.numpy()), 1e-12), (k, np.linalg.norm(d) / np.linalg.norm(gr.numpy()))
+
+
+def test_parallel_graph_branches_equal_the_serial_order(torch_cuda):
+    """The update graph runs the target-Q forward and the weight-gradient GEMMs on side streams.  A missing dependency would be a timing-
+    dependent race: 300 graph-replayed updates with the branches must give the parameters of 300 eager updates on ONE stream."""
+    torch = torch_cuda
+    rb, _ = _ring(torch)
+    outs = []
+    for graph, par in ((True, True), (False, False), (True, True)):
+        from robosuite_benchmark_b200.sac import ParamStore, SACTrainer
+        store = ParamStore(O, A, "cuda:0", seed=3)
+        tr = SACTrainer(store=store, batch_size=B, tf32=True, use_graph=graph, seed=5, parallel_branches=par, discount=0.99, reward_scale=1.0,
+                        policy_lr=1e-3, qf_lr=5e-4, soft_target_tau=0.005, target_update_period=5)
+        tr.replay = rb
+        for _ in range(300):
+            tr.train_step()
+        torch.cuda.synchronize()
+        outs.append(store.flat.clone())
+    assert torch.equal(outs[0], outs[2]), "graph replay with parallel branches is not deterministic"
+    d = (outs[0] - outs[1]).abs().max().item()
+    assert d < 1e-5, d
