@@ -1,0 +1,33 @@
+/*
+ * rsb_gemm.h -- C-ABI of the tensor-core GEMM used by the SAC update (part of librsb_cuda.so; kernel in csrc/rsb_tc_gemm.cu).
+ *
+ * Reference interface replaced: the `torch.nn.Linear` forward/backward products inside rlkit's FlattenMlp / TanhGaussianPolicy as
+ * driven by SACTrainer.train_from_torch (un-vendored rlkit @ b7f97b2, reached from util/rlkit_custom.py:238).
+ *
+ *   C[b][m,n] = epilogue( sum_k A[b][m,k] * B[b][k,n] ),   b < batch
+ *
+ * A, B are fp32 in HBM with arbitrary ELEMENT strides (so X, X^T, W, W^T need no copies); the products run on the sm_100a tensor
+ * cores as TF32 x TF32 -> FP32 (`tcgen05.mma.kind::tf32`, accumulator in tensor memory).  C is row-major with row stride c_rs.
+ * epilogue: v += bias[b][n] (if bias); v = max(v, 0) (flag RELU); v = mask[b][m,n] > 0 ? v : 0 (if mask: the ReLU backward of a layer whose
+ * output is `mask`); v += C[b][m,n] (flag ACCUMULATE).  All pointers are DEVICE pointers; `stream` is a cudaStream_t as void*; the call
+ * is stream-ordered, non-blocking and CUDA-graph capturable.  Returns 0, or non-zero with rsb_sac_last_error() set.
+ */
+#ifndef RSB_GEMM_H
+#define RSB_GEMM_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+#define RSB_GEMM_RELU 1
+#define RSB_GEMM_ACCUMULATE 2
+/* n_tile: 0 = choose (16/32/64/128 output columns per CTA; one CTA owns a 128 x n_tile tile of C) */
+int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, const float *d_b, long b_ks, long b_ns, long b_bs, float *d_c, long c_rs, long c_bs,
+                  int m, int n, int k, int batch, const float *d_bias, long bias_bs, const float *d_mask, long mask_rs, long mask_bs, int flags, int n_tile,
+                  void *stream);
+/* device-side watchdog: number of mbarrier waits that gave up since the last call (0 on a healthy run); synchronises the device */
+int rsb_gemm_timeouts(void);
+/* diagnostic: exchange the two byte-offset fields of the shared-memory matrix descriptors (0 = as documented in csrc/rsb_tc_gemm.cu) */
+void rsb_gemm_debug_swap_offsets(int swap);
+#ifdef __cplusplus
+}
+#endif
+#endif

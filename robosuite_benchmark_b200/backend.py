@@ -25,15 +25,15 @@ INFO = dict(nenvs=0, obs_dim=1, act_dim=2, state_words=3, smem_bytes=4, dbg_word
 
 
 def sources():
-    return [os.path.join(_CSRC, f) for f in ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_kernels.inl", "rsb_ktable.h", "rsb_sac.cu", "rsb_dev.h", "rsb_devmodel.h")] + \
-           [os.path.join(_HERE, "..", "include", f) for f in ("rsb.h", "rsb_sac.h", "rsb_model.h")]
+    return [os.path.join(_CSRC, f) for f in ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_kernels.inl", "rsb_ktable.h", "rsb_sac.cu", "rsb_tc_gemm.cu", "rsb_dev.h", "rsb_devmodel.h")] + \
+           [os.path.join(_HERE, "..", "include", f) for f in ("rsb.h", "rsb_sac.h", "rsb_gemm.h", "rsb_model.h")]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/rsb_cuda.cu for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     stale = force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in sources())
     if stale:
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + [os.path.join(_CSRC, f) for f in ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_sac.cu")]
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + [os.path.join(_CSRC, f) for f in ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_sac.cu", "rsb_tc_gemm.cu")]
         subprocess.check_call(cmd)
     return LIB_PATH
 
@@ -70,6 +70,9 @@ def lib():
         L.rsb_head_bwd.argtypes = [V, V, V, I, I, I, V, V, I, V, V]
         L.rsb_sac_losses.argtypes = [V, V, V, V, V, V, F, F, F, I, V, V, V, V, V]
         L.rsb_adam_polyak.argtypes = [V, V, V, V, L_, C.c_double, C.c_double, F, F, F, V, V, L_, L_, F, I, V, L_, V]
+        L.rsb_gemm_tf32.argtypes = [V, L_, L_, L_, V, L_, L_, L_, V, L_, L_, I, I, I, I, V, L_, V, L_, L_, I, I, V]
+        L.rsb_gemm_debug_swap_offsets.argtypes = [I]
+        L.rsb_gemm_debug_swap_offsets.restype = None
         _LIB = L
     return _LIB
 
@@ -77,7 +80,8 @@ def lib():
 EXPORTS = ["rsb_last_error", "rsb_sizeof_model", "rsb_sizeof_task", "rsb_create", "rsb_destroy", "rsb_info", "rsb_reset",
            "rsb_step", "rsb_step_host", "rsb_reset_host", "rsb_random_actions", "rsb_get_state", "rsb_set_state",
            "rsb_debug_substep", "rsb_sac_last_error", "rsb_sac_prepare", "rsb_replay_sample", "rsb_normal", "rsb_bias_relu", "rsb_relu_bwd",
-           "rsb_colsum", "rsb_head_fwd", "rsb_head_bwd", "rsb_sac_losses", "rsb_adam_polyak"]
+           "rsb_colsum", "rsb_head_fwd", "rsb_head_bwd", "rsb_sac_losses", "rsb_adam_polyak", "rsb_gemm_tf32", "rsb_gemm_timeouts",
+           "rsb_gemm_debug_swap_offsets"]
 
 
 class RsbError(RuntimeError):

@@ -14,6 +14,7 @@
 #include "../../include/rsb_sac.h"
 
 static thread_local std::string g_sac_err;
+void rsb_sac_set_error(const char *msg) { g_sac_err = msg; }   /* shared with rsb_tc_gemm.cu */
 #define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_sac_err = std::string(#call) + ": " + cudaGetErrorString(e_); return 1; } } while (0)
 
 __device__ __forceinline__ void philox4(uint32_t c[4], uint32_t k0, uint32_t k1) {

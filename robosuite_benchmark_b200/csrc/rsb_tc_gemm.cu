@@ -1,0 +1,248 @@
+/*
+ * rsb_tc_gemm.cu -- the dense products of the SAC update on the sm_100a tensor cores (C-ABI: include/rsb_gemm.h).
+ *
+ * Stands behind the Linear layers of rlkit's FlattenMlp / TanhGaussianPolicy in SACTrainer.train_from_torch (reference call site
+ * util/rlkit_custom.py:238): forward X W + b (+ReLU), activation gradients dY W^T (masked by the ReLU), weight gradients X^T dY.
+ *
+ *   C[b][m,n] = epilogue( sum_k A[b][m,k] * B[b][k,n] )       fp32 in HBM, TF32 x TF32 -> FP32 on tcgen05, accumulator in tensor memory
+ *
+ * One CTA of 256 threads owns a 128 x n_tile tile of C (n_tile in {16,32,64,128}, chosen per launch so small-batch updates still spread
+ * over many SMs).  The contraction runs in chunks of 64:
+ *   - every thread stages its share of the A chunk (128 x 64) and the B chunk (n_tile x 64) with `cp.async` straight into the tensor
+ *     core's canonical K-major no-swizzle layout: core matrices of 8 rows x 16 bytes (4 fp32), 128 bytes each, the 16 core matrices of
+ *     one 8-row group back to back (so: byte offset of element (r, k) = (r/8)*2048 + (k/4)*128 + (r%8)*16 + (k%4)*4).  Because the
+ *     loader addresses elements by (row stride, column stride), transposed operands cost nothing extra: X^T and W^T are read in place.
+ *     A lane takes row (lane%8) and 16-byte column group (lane/8) of a 8 x 16 element patch, so a quarter-warp writes one whole core
+ *     matrix (128 contiguous bytes, conflict-free) and reads full 32-byte sectors; operands whose contraction index is contiguous and
+ *     16-byte aligned move as 16-byte copies, everything else as 4-byte copies; out-of-range rows/columns are zero-filled (src-size 0).
+ *   - two stages: the copies of chunk i+1 are in flight while chunk i is waited for; one elected thread then issues the chunk's
+ *     `tcgen05.mma.cta_group::1.kind::tf32` (M = 128, N = n_tile, K = 8 each: two core matrices along K, descriptor start address
+ *     advanced by 256 bytes) and `tcgen05.commit`s to the stage's mbarrier, which is what frees the stage for the loads two chunks on.
+ *   - epilogue: the 8 warps read the accumulator with `tcgen05.ld.32x32b.x16` (warp w owns tensor-memory lanes 32*(w%4).., the two warps
+ *     of a lane quarter split the columns), apply bias / ReLU / ReLU-mask / accumulate and store rows of C.
+ * Shared-memory matrix descriptor (64 bit): [0,14) start address >> 4, [16,30) leading byte offset >> 4 = distance between the two core
+ * matrices along K (128), [32,46) stride byte offset >> 4 = distance between 8-row groups (2048), [46,48) = 1 (sm_100), [61,64) = 0 (no swizzle).
+ * Instruction descriptor (32 bit): [4,6) D format 1 = F32, [7,10) A format 2 = TF32, [10,13) B format 2 = TF32, bits 15/16 = 0 (both K-major),
+ * [17,23) N >> 3, [24,29) M >> 4.
+ * Every mbarrier wait is bounded (a wait that gives up raises a device-side counter, rsb_gemm_timeouts()), so a protocol error shows up as a
+ * wrong result in the tests and never as a hung GPU.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/rsb_gemm.h"
+#include "../../include/rsb_sac.h"
+
+void rsb_sac_set_error(const char *msg);   /* rsb_sac.cu: the string rsb_sac_last_error() returns */
+
+#define BM 128
+#define KC 64
+#define BN_MAX 128
+#define NTHREADS 256
+#define A_BYTES (BM * KC * 4)
+#define B_BYTES (BN_MAX * KC * 4)
+#define STAGE_BYTES (A_BYTES + B_BYTES)
+#define SMEM_BYTES (2 * STAGE_BYTES + 64)
+#define TMEM_COLS 128
+
+struct GemmArgs {
+  const float *a, *b, *bias, *mask;
+  float *c;
+  long long a_rs, a_cs, a_bs, b_ks, b_ns, b_bs, c_rs, c_bs, bias_bs, mask_rs, mask_bs;
+  int m, n, k, flags, n_tile, lbo16, sbo16;
+};
+
+__device__ unsigned int g_gemm_timeouts;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, int bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+  for (int it = 0; it < (1 << 20); it++) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  atomicAdd(&g_gemm_timeouts, 1u);
+  return false;
+}
+
+/* stage `rows` x KC elements of an operand: element (r, k) of the tile lives at base + r*rs + k*cs; rows >= rvalid and columns >= kvalid are zero */
+__device__ __forceinline__ void load_tile(uint32_t dst, const float *base, long long rs, long long cs, int rows, int rvalid, int kvalid, bool vec16) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, rr = lane & 7, kq = lane >> 3;
+  if (vec16) {                                        /* task = (8-row group, group of 4 x 16-byte columns): lane -> row rr, 16-byte column 4*kg + kq */
+    const int ntask = (rows >> 3) * (KC / 16);
+    for (int t = warp; t < ntask; t += NTHREADS / 32) {
+      const int rg = t / (KC / 16), kg = t % (KC / 16), r = rg * 8 + rr, k = (kg * 4 + kq) * 4;
+      int bytes = (r < rvalid) ? min(16, max(0, (kvalid - k) * 4)) : 0;
+      const float *src = bytes ? base + (long long)r * rs + k : base;
+      cp_async16(dst + rg * 2048 + (kg * 4 + kq) * 128 + rr * 16, src, bytes);
+    }
+  } else {                                            /* task = (8-row group, 16-byte column k4): lane -> row rr, element 4*k4 + kq */
+    const int ntask = (rows >> 3) * (KC / 4);
+    for (int t = warp; t < ntask; t += NTHREADS / 32) {
+      const int rg = t / (KC / 4), k4 = t % (KC / 4), r = rg * 8 + rr, k = k4 * 4 + kq;
+      const bool ok = (r < rvalid) && (k < kvalid);
+      const float *src = ok ? base + (long long)r * rs + (long long)k * cs : base;
+      cp_async4(dst + rg * 2048 + k4 * 128 + rr * 16 + kq * 4, src, ok ? 4 : 0);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * g.n_tile, m0 = blockIdx.y * BM, bz = blockIdx.z;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + 2 * STAGE_BYTES, tslot = bar0 + 16;
+  volatile uint32_t *tslot_p = (volatile uint32_t *)(smem + 2 * STAGE_BYTES + 16);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tslot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (tid == 32) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0 + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = *tslot_p;
+
+  const float *A = g.a + (long long)bz * g.a_bs + (long long)m0 * g.a_rs;
+  const float *B = g.b + (long long)bz * g.b_bs + (long long)n0 * g.b_ns;
+  const bool a16 = g.a_cs == 1 && (g.a_rs & 3) == 0 && ((uintptr_t)A & 15) == 0;
+  const bool b16 = g.b_ks == 1 && (g.b_ns & 3) == 0 && ((uintptr_t)B & 15) == 0;
+  const int mvalid = g.m - m0, nvalid = g.n - n0, nchunks = (g.k + KC - 1) / KC;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const uint64_t desc_hi = ((uint64_t)g.lbo16 << 16) | ((uint64_t)g.sbo16 << 32) | (1ull << 46);
+
+  load_tile(sbase, A, g.a_rs, g.a_cs, BM, mvalid, g.k, a16);
+  load_tile(sbase + A_BYTES, B, g.b_ns, g.b_ks, g.n_tile, nvalid, g.k, b16);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  for (int i = 0; i < nchunks; i++) {
+    if (i + 1 < nchunks) {
+      const int s1 = (i + 1) & 1, k1 = (i + 1) * KC;
+      if (i + 1 >= 2) mbar_wait(bar0 + 8 * s1, ((i - 1) >> 1) & 1);          /* the products of chunk i-1 have read stage s1 */
+      load_tile(sbase + s1 * STAGE_BYTES, A + (long long)k1 * g.a_cs, g.a_rs, g.a_cs, BM, mvalid, g.k - k1, a16);
+      load_tile(sbase + s1 * STAGE_BYTES + A_BYTES, B + (long long)k1 * g.b_ks, g.b_ns, g.b_ks, g.n_tile, nvalid, g.k - k1, b16);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const int s = i & 1, kmma = (min(KC, g.k - i * KC) + 7) >> 3;
+      const uint32_t a_addr = sbase + s * STAGE_BYTES, b_addr = a_addr + A_BYTES;
+      for (int kk = 0; kk < kmma; kk++) {
+        const uint64_t da = desc_hi | (uint64_t)(((a_addr + kk * 256) >> 4) & 0x3FFF);
+        const uint64_t db = desc_hi | (uint64_t)(((b_addr + kk * 256) >> 4) & 0x3FFF);
+        const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                     ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar0 + 8 * s) : "memory");
+    }
+  }
+  const bool done = mbar_wait(bar0 + 8 * ((nchunks - 1) & 1), ((nchunks - 1) >> 1) & 1);
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+
+  /* epilogue: warp w reads lanes 32*(w%4) .. +31 (one row of C per thread); warps w and w+4 take alternate 16-column slabs */
+  {
+    const int q = warp & 3, half = warp >> 2, r = q * 32 + lane, m = m0 + r;
+    float *crow = g.c + (long long)bz * g.c_bs + (long long)m * g.c_rs + n0;
+    const float *mrow = g.mask ? g.mask + (long long)bz * g.mask_bs + (long long)m * g.mask_rs + n0 : nullptr;
+    const float *bias = g.bias ? g.bias + (long long)bz * g.bias_bs + n0 : nullptr;
+    const bool relu = g.flags & RSB_GEMM_RELU, accum = g.flags & RSB_GEMM_ACCUMULATE;
+    const bool st16 = ((g.c_rs & 3) == 0) && (((uintptr_t)(g.c + (long long)bz * g.c_bs + n0) & 15) == 0);
+    for (int c0 = half * 16; c0 < g.n_tile; c0 += 32) {
+      uint32_t v[16];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                     "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                   : "r"(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      if (m < g.m && done) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const int nn = c0 + j;
+          float x = __uint_as_float(v[j]);
+          if (nn < nvalid) {
+            if (bias) x += __ldg(bias + nn);
+            if (relu) x = fmaxf(x, 0.0f);
+            if (mrow) x = (mrow[nn] > 0.0f) ? x : 0.0f;
+            if (accum) x += crow[nn];
+          }
+          f[j] = x;
+        }
+        if (st16 && c0 + 16 <= nvalid) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(crow + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; j++) if (c0 + j < nvalid) crow[c0 + j] = f[j];
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+static int g_swap_offsets = 0;
+
+extern "C" void rsb_gemm_debug_swap_offsets(int swap) { g_swap_offsets = swap; }
+
+extern "C" int rsb_gemm_timeouts(void) {
+  unsigned int h = 0, z = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(&h, g_gemm_timeouts, sizeof(h)) != cudaSuccess) return -1;
+  cudaMemcpyToSymbol(g_gemm_timeouts, &z, sizeof(z));
+  return (int)h;
+}
+
+extern "C" int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, const float *d_b, long b_ks, long b_ns, long b_bs, float *d_c, long c_rs,
+                             long c_bs, int m, int n, int k, int batch, const float *d_bias, long bias_bs, const float *d_mask, long mask_rs, long mask_bs,
+                             int flags, int n_tile, void *stream) {
+  if (m < 1 || n < 1 || k < 1 || batch < 1 || !d_a || !d_b || !d_c) { rsb_sac_set_error("rsb_gemm_tf32: bad arguments"); return 1; }
+  const int mt = (m + BM - 1) / BM;
+  if (n_tile == 0) {                                  /* widest tile that still gives >= 32 CTAs; small outputs: the narrowest tile that covers n */
+    n_tile = 128;
+    while (n_tile > 16 && ((n + n_tile - 1) / n_tile) * mt * batch < 32) n_tile >>= 1;
+    while (n_tile > 16 && (n_tile >> 1) >= n) n_tile >>= 1;
+  }
+  if (n_tile != 16 && n_tile != 32 && n_tile != 64 && n_tile != 128) { rsb_sac_set_error("rsb_gemm_tf32: n_tile must be 16, 32, 64 or 128"); return 1; }
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess && dev < 64 && !attr_set[dev]) {
+    e = cudaFuncSetAttribute(k_gemm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_set[dev] = (e == cudaSuccess);
+  }
+  if (e != cudaSuccess) { rsb_sac_set_error(cudaGetErrorString(e)); return 1; }
+  GemmArgs g;
+  g.a = d_a; g.b = d_b; g.bias = d_bias; g.mask = d_mask; g.c = d_c;
+  g.a_rs = a_rs; g.a_cs = a_cs; g.a_bs = a_bs; g.b_ks = b_ks; g.b_ns = b_ns; g.b_bs = b_bs; g.c_rs = c_rs; g.c_bs = c_bs;
+  g.bias_bs = bias_bs; g.mask_rs = mask_rs; g.mask_bs = mask_bs;
+  g.m = m; g.n = n; g.k = k; g.flags = flags; g.n_tile = n_tile;
+  g.lbo16 = g_swap_offsets ? (2048 >> 4) : (128 >> 4);
+  g.sbo16 = g_swap_offsets ? (128 >> 4) : (2048 >> 4);
+  dim3 grid((n + n_tile - 1) / n_tile, mt, batch);
+  k_gemm_tf32<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(g);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { rsb_sac_set_error(cudaGetErrorString(e)); return 1; }
+  return 0;
+}

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     so = backend.build()
     out = subprocess.check_output(["nm", "-D", "--defined-only", so], text=True)
     exported = set(l.split()[-1] for l in out.splitlines() if l.strip())
-    declared = _declared("rsb.h") + _declared("rsb_sac.h")
+    declared = _declared("rsb.h") + _declared("rsb_sac.h") + _declared("rsb_gemm.h")
     assert len(declared) >= 20
     for name in declared:
         assert name in exported, name

@@ -1,0 +1,51 @@
+"""GPU parity of the tcgen05 TF32 GEMM (csrc/rsb_tc_gemm.cu, include/rsb_gemm.h) against fp64 on the SAC update's shapes and operand layouts.
+
+Tolerance: TF32 keeps 10 mantissa bits of each operand, so |C - C64| <= 2 * 2^-10 * (|A| @ |B|) elementwise (written below as 3e-3, with
+1e-3 absolute slack in the denominator); a wrong shared-memory layout or descriptor gives errors of order 1."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda:0")
+
+
+def test_tcgen05_gemm_matches_fp64_on_every_sac_shape(dev):
+    import diag_tc_gemm as d
+    from robosuite_benchmark_b200 import gemm
+    for c in d.cases():
+        for nt in (0, 16, 64):
+            err, *_ = d.run_case(c, dev, nt)
+            assert gemm.timeouts() == 0, c
+            assert err < 3e-3, (c, nt, err)
+
+
+def test_tcgen05_gemm_is_deterministic_and_graph_capturable(dev):
+    import torch
+    from robosuite_benchmark_b200 import gemm
+    a, b = torch.randn(2, 256, 256, device=dev), torch.randn(2, 256, 256, device=dev)
+    o1, o2 = torch.empty(2, 256, 256, device=dev), torch.empty(2, 256, 256, device=dev)
+    gemm.gemm_tf32(a, b, o1)
+    s = torch.cuda.Stream(dev)
+    s.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(s):
+        gemm.gemm_tf32(a, b, o2)
+    torch.cuda.current_stream(dev).wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        gemm.gemm_tf32(a, b, o2)
+    o2.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2)
+    assert gemm.timeouts() == 0
