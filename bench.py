@@ -309,11 +309,12 @@ def sac_bench(dev, obs_dim, act_dim, world, rank, updates=300):
         obs = torch.randn(m, obs_dim, device=dev, generator=g) * 0.5
         rb.add_batch(obs, torch.tanh(torch.randn(m, act_dim, device=dev, generator=g)), torch.rand(m, device=dev, generator=g) * 0.1,
                      torch.zeros(m, dtype=torch.uint8, device=dev), obs + 0.05 * torch.randn(m, obs_dim, device=dev, generator=g))
-    out = {"gemm": "cuBLAS TF32 (fp32 accumulate)", "ring_transitions": n, "world": world}
-    for B in (128, 4096):
+    out = {"gemm": "tcgen05 TF32, fp32 accumulate in tensor memory (csrc/rsb_tc_gemm.cu; bias/ReLU/ReLU-backward fused in the epilogue)",
+           "ring_transitions": n, "world": world}
+    for B, gemm in ((128, "tcgen05"), (4096, "tcgen05"), (128, "cublas"), (4096, "cublas")):
         store = ParamStore(obs_dim, act_dim, dev, seed=SEED)
         tr = SACTrainer(store=store, replay_buffer=rb, batch_size=B, discount=0.99, reward_scale=1.0, policy_lr=1e-3, qf_lr=5e-4,
-                        soft_target_tau=0.005, target_update_period=5, seed=SEED, tf32=True, use_graph=True, world_size=world)
+                        soft_target_tau=0.005, target_update_period=5, seed=SEED, tf32=True, use_graph=True, world_size=world, gemm=gemm)
         for _ in range(10):
             tr.train_step()
         torch.cuda.synchronize()
@@ -324,7 +325,7 @@ def sac_bench(dev, obs_dim, act_dim, world, rank, updates=300):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / updates
         fl = algorithmic_flops_per_update(obs_dim, act_dim, B)
-        out[f"b{B}"] = {"updates_per_s": 1000.0 / ms, "samples_per_s": world * B * 1000.0 / ms, "us_per_update": 1000.0 * ms,
+        out[f"b{B}" if gemm == "tcgen05" else f"b{B}_cublas_tf32"] = {"updates_per_s": 1000.0 / ms, "samples_per_s": world * B * 1000.0 / ms, "us_per_update": 1000.0 * ms,
                         "algorithmic_gflop_per_update": fl / 1e9, "achieved_tflops": fl / (ms / 1000.0) / 1e12}
         del tr, store
     return out

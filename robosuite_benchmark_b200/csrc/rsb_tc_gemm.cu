@@ -15,9 +15,10 @@
  *     A lane takes row (lane%8) and 16-byte column group (lane/8) of a 8 x 16 element patch, so a quarter-warp writes one whole core
  *     matrix (128 contiguous bytes, conflict-free) and reads full 32-byte sectors; operands whose contraction index is contiguous and
  *     16-byte aligned move as 16-byte copies, everything else as 4-byte copies; out-of-range rows/columns are zero-filled (src-size 0).
- *   - two stages: the copies of chunk i+1 are in flight while chunk i is waited for; one elected thread then issues the chunk's
- *     `tcgen05.mma.cta_group::1.kind::tf32` (M = 128, N = n_tile, K = 8 each: two core matrices along K, descriptor start address
- *     advanced by 256 bytes) and `tcgen05.commit`s to the stage's mbarrier, which is what frees the stage for the loads two chunks on.
+ *   - four stages (three at n_tile = 128): the copies of the first chunks leave before tensor memory is even allocated, so a K = 256 layer
+ *     has its whole operand set in flight at once; per chunk one elected thread issues `tcgen05.mma.cta_group::1.kind::tf32` (M = 128,
+ *     N = n_tile, K = 8 each: two core matrices along K, descriptor start address advanced by 256 bytes) and `tcgen05.commit`s to the
+ *     stage's mbarrier, which is what frees the stage for the chunk S further on.
  *   - epilogue: the 8 warps read the accumulator with `tcgen05.ld.32x32b.x16` (warp w owns tensor-memory lanes 32*(w%4).., the two warps
  *     of a lane quarter split the columns), apply bias / ReLU / ReLU-mask / accumulate and store rows of C.
  * Shared-memory matrix descriptor (64 bit): [0,14) start address >> 4, [16,30) leading byte offset >> 4 = distance between the two core
@@ -42,8 +43,8 @@ void rsb_sac_set_error(const char *msg);   /* rsb_sac.cu: the string rsb_sac_las
 #define NTHREADS 256
 #define A_BYTES (BM * KC * 4)
 #define B_BYTES (BN_MAX * KC * 4)
-#define STAGE_BYTES (A_BYTES + B_BYTES)
-#define SMEM_BYTES (2 * STAGE_BYTES + 64)
+#define CTRL_OFF (3 * (A_BYTES + B_BYTES))      /* = 4 x (32 KB + 64 x 256 B): control block (4 mbarriers, tensor-memory slot, bias row) behind the stages */
+#define SMEM_BYTES (CTRL_OFF + 64 + BN_MAX * 4)
 #define TMEM_COLS 128
 
 struct GemmArgs {
@@ -75,24 +76,31 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   return false;
 }
 
-/* stage `rows` x KC elements of an operand: element (r, k) of the tile lives at base + r*rs + k*cs; rows >= rvalid and columns >= kvalid are zero */
+/* stage `rows` x KC elements of an operand: element (r, k) of the tile lives at base + r*rs + k*cs; rows >= rvalid and columns >= kvalid are zero.
+   A thread keeps its (row in the core matrix, column) and walks down the 8-row groups with constant pointer increments. */
 __device__ __forceinline__ void load_tile(uint32_t dst, const float *base, long long rs, long long cs, int rows, int rvalid, int kvalid, bool vec16) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, rr = lane & 7, kq = lane >> 3;
-  if (vec16) {                                        /* task = (8-row group, group of 4 x 16-byte columns): lane -> row rr, 16-byte column 4*kg + kq */
-    const int ntask = (rows >> 3) * (KC / 16);
-    for (int t = warp; t < ntask; t += NTHREADS / 32) {
-      const int rg = t / (KC / 16), kg = t % (KC / 16), r = rg * 8 + rr, k = (kg * 4 + kq) * 4;
-      int bytes = (r < rvalid) ? min(16, max(0, (kvalid - k) * 4)) : 0;
-      const float *src = bytes ? base + (long long)r * rs + k : base;
-      cp_async16(dst + rg * 2048 + (kg * 4 + kq) * 128 + rr * 16, src, bytes);
+  if (vec16) {                                        /* lane -> row rr of the group, 16-byte column k4 = 4*(warp%4) + kq; warps 0-3 / 4-7 take even / odd groups */
+    const int k4 = (warp & 3) * 4 + kq, kb = min(16, max(0, (kvalid - k4 * 4) * 4));
+    int r = (warp >> 2) * 8 + rr;
+    const float *src = base + (long long)r * rs + k4 * 4;
+    uint32_t d = dst + (warp >> 2) * 2048 + k4 * 128 + rr * 16;
+    for (int j = 0; j < (rows >> 4); j++, r += 16, src += 16 * rs, d += 4096) {
+      const int bytes = (r < rvalid) ? kb : 0;
+      cp_async16(d, bytes ? src : base, bytes);
     }
-  } else {                                            /* task = (8-row group, 16-byte column k4): lane -> row rr, element 4*k4 + kq */
-    const int ntask = (rows >> 3) * (KC / 4);
-    for (int t = warp; t < ntask; t += NTHREADS / 32) {
-      const int rg = t / (KC / 4), k4 = t % (KC / 4), r = rg * 8 + rr, k = k4 * 4 + kq;
-      const bool ok = (r < rvalid) && (k < kvalid);
-      const float *src = ok ? base + (long long)r * rs + (long long)k * cs : base;
-      cp_async4(dst + rg * 2048 + k4 * 128 + rr * 16 + kq * 4, src, ok ? 4 : 0);
+  } else {                                            /* lane -> row rr, element kq of the 16-byte columns k4 = warp and warp + 8 */
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int k4 = warp + 8 * h, k = k4 * 4 + kq;
+      const bool okk = k < kvalid;
+      int r = rr;
+      const float *src = base + (long long)rr * rs + (long long)k * cs;
+      uint32_t d = dst + k4 * 128 + rr * 16 + kq * 4;
+      for (int rg = 0; rg < (rows >> 3); rg++, r += 8, src += 8 * rs, d += 2048) {
+        const bool ok = okk && (r < rvalid);
+        cp_async4(d, ok ? src : base, ok ? 4 : 0);
+      }
     }
   }
 }
@@ -102,49 +110,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * g.n_tile, m0 = blockIdx.y * BM, bz = blockIdx.z;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar0 = sbase + 2 * STAGE_BYTES, tslot = bar0 + 16;
-  volatile uint32_t *tslot_p = (volatile uint32_t *)(smem + 2 * STAGE_BYTES + 16);
-
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tslot), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-  }
-  if (tid == 32) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0 + 8) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const uint32_t tmem = *tslot_p;
+  const uint32_t bar0 = sbase + CTRL_OFF, tslot = bar0 + 32;
+  volatile uint32_t *tslot_p = (volatile uint32_t *)(smem + CTRL_OFF + 32);
+  float *sbias = (float *)(smem + CTRL_OFF + 64);
+  const int S = (g.n_tile == 128) ? 3 : 4;                      /* stages: 3 x 64 KB or 4 x (32 KB + n_tile x 256 B) */
+  const uint32_t stage_bytes = A_BYTES + (uint32_t)g.n_tile * (KC * 4);
 
   const float *A = g.a + (long long)bz * g.a_bs + (long long)m0 * g.a_rs;
   const float *B = g.b + (long long)bz * g.b_bs + (long long)n0 * g.b_ns;
   const bool a16 = g.a_cs == 1 && (g.a_rs & 3) == 0 && ((uintptr_t)A & 15) == 0;
   const bool b16 = g.b_ks == 1 && (g.b_ns & 3) == 0 && ((uintptr_t)B & 15) == 0;
   const int mvalid = g.m - m0, nvalid = g.n - n0, nchunks = (g.k + KC - 1) / KC;
+
+  /* the first S chunks go out before anything else: the copies fly while tensor memory is allocated and the barriers are set up */
+  for (int c = 0; c < S; c++) {
+    if (c < nchunks) {
+      load_tile(sbase + c * stage_bytes, A + (long long)(c * KC) * g.a_cs, g.a_rs, g.a_cs, BM, mvalid, g.k - c * KC, a16);
+      load_tile(sbase + c * stage_bytes + A_BYTES, B + (long long)(c * KC) * g.b_ks, g.b_ns, g.b_ks, g.n_tile, nvalid, g.k - c * KC, b16);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  if (tid < g.n_tile) sbias[tid] = (g.bias && tid < nvalid) ? __ldg(g.bias + (long long)bz * g.bias_bs + n0 + tid) : 0.0f;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tslot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (tid == 32) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0 + 8 * c) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = *tslot_p;
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   const uint64_t desc_hi = ((uint64_t)g.lbo16 << 16) | ((uint64_t)g.sbo16 << 32) | (1ull << 46);
 
-  load_tile(sbase, A, g.a_rs, g.a_cs, BM, mvalid, g.k, a16);
-  load_tile(sbase + A_BYTES, B, g.b_ns, g.b_ks, g.n_tile, nvalid, g.k, b16);
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  int st = 0, ph = 0;                                           /* stage and mbarrier phase of chunk i: i % S, (i / S) & 1 */
   for (int i = 0; i < nchunks; i++) {
-    if (i + 1 < nchunks) {
-      const int s1 = (i + 1) & 1, k1 = (i + 1) * KC;
-      if (i + 1 >= 2) mbar_wait(bar0 + 8 * s1, ((i - 1) >> 1) & 1);          /* the products of chunk i-1 have read stage s1 */
-      load_tile(sbase + s1 * STAGE_BYTES, A + (long long)k1 * g.a_cs, g.a_rs, g.a_cs, BM, mvalid, g.k - k1, a16);
-      load_tile(sbase + s1 * STAGE_BYTES + A_BYTES, B + (long long)k1 * g.b_ks, g.b_ns, g.b_ks, g.n_tile, nvalid, g.k - k1, b16);
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    if (S == 4) asm volatile("cp.async.wait_group 3;\n" ::: "memory");      /* exactly S-1 groups are younger than chunk i's */
+    else asm volatile("cp.async.wait_group 2;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const int s = i & 1, kmma = (min(KC, g.k - i * KC) + 7) >> 3;
-      const uint32_t a_addr = sbase + s * STAGE_BYTES, b_addr = a_addr + A_BYTES;
+      const int kmma = (min(KC, g.k - i * KC) + 7) >> 3;
+      const uint32_t a_addr = sbase + st * stage_bytes, b_addr = a_addr + A_BYTES;
       for (int kk = 0; kk < kmma; kk++) {
         const uint64_t da = desc_hi | (uint64_t)(((a_addr + kk * 256) >> 4) & 0x3FFF);
         const uint64_t db = desc_hi | (uint64_t)(((b_addr + kk * 256) >> 4) & 0x3FFF);
@@ -152,10 +164,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
                      ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar0 + 8 * s) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar0 + 8 * st) : "memory");
     }
+    if (i + S < nchunks) {                                      /* refill this stage once its products have read it */
+      const int k1 = (i + S) * KC;
+      mbar_wait(bar0 + 8 * st, ph);
+      load_tile(sbase + st * stage_bytes, A + (long long)k1 * g.a_cs, g.a_rs, g.a_cs, BM, mvalid, g.k - k1, a16);
+      load_tile(sbase + st * stage_bytes + A_BYTES, B + (long long)k1 * g.b_ks, g.b_ns, g.b_ks, g.n_tile, nvalid, g.k - k1, b16);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    if (i + 1 < nchunks && ++st == S) { st = 0; ph ^= 1; }
   }
-  const bool done = mbar_wait(bar0 + 8 * ((nchunks - 1) & 1), ((nchunks - 1) >> 1) & 1);
+  const bool done = mbar_wait(bar0 + 8 * st, ph);               /* the last commit covers every product issued before it */
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 
   /* epilogue: warp w reads lanes 32*(w%4) .. +31 (one row of C per thread); warps w and w+4 take alternate 16-column slabs */
@@ -163,7 +183,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
     const int q = warp & 3, half = warp >> 2, r = q * 32 + lane, m = m0 + r;
     float *crow = g.c + (long long)bz * g.c_bs + (long long)m * g.c_rs + n0;
     const float *mrow = g.mask ? g.mask + (long long)bz * g.mask_bs + (long long)m * g.mask_rs + n0 : nullptr;
-    const float *bias = g.bias ? g.bias + (long long)bz * g.bias_bs + n0 : nullptr;
     const bool relu = g.flags & RSB_GEMM_RELU, accum = g.flags & RSB_GEMM_ACCUMULATE;
     const bool st16 = ((g.c_rs & 3) == 0) && (((uintptr_t)(g.c + (long long)bz * g.c_bs + n0) & 15) == 0);
     for (int c0 = half * 16; c0 < g.n_tile; c0 += 32) {
@@ -180,7 +199,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
           const int nn = c0 + j;
           float x = __uint_as_float(v[j]);
           if (nn < nvalid) {
-            if (bias) x += __ldg(bias + nn);
+            x += sbias[nn];
             if (relu) x = fmaxf(x, 0.0f);
             if (mrow) x = (mrow[nn] > 0.0f) ? x : 0.0f;
             if (accum) x += crow[nn];

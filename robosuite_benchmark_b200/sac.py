@@ -16,6 +16,7 @@ from collections import OrderedDict
 import numpy as np
 
 from .backend import RsbError, lib
+from .gemm import gemm_tf32
 
 HID = 256
 
@@ -296,7 +297,7 @@ class SACTrainer:
     def __init__(self, env=None, policy=None, qf1=None, qf2=None, target_qf1=None, target_qf2=None, *, store: ParamStore = None,
                  replay_buffer: EnvReplayBuffer = None, batch_size=128, discount=0.99, reward_scale=1.0, policy_lr=1e-3, qf_lr=1e-3,
                  soft_target_tau=1e-2, target_update_period=1, use_automatic_entropy_tuning=True, target_entropy=None,
-                 seed=0, tf32=True, use_graph=True, world_size=1, parallel_branches=True):
+                 seed=0, tf32=True, use_graph=True, world_size=1, parallel_branches=True, gemm="tcgen05"):
         import torch
         if store is None:
             store = policy.store
@@ -312,6 +313,10 @@ class SACTrainer:
         A = store.A
         self.target_entropy = float(-A if target_entropy is None else target_entropy)   # -prod(action_space.shape)
         self.seed, self.tf32, self.use_graph, self.world = int(seed), bool(tf32), bool(use_graph), int(world_size)
+        if gemm not in ("tcgen05", "cublas"):
+            raise ValueError(f"gemm must be 'tcgen05' or 'cublas', got {gemm!r}")
+        # TF32 products: the hand-written tcgen05 kernel (csrc/rsb_tc_gemm.cu) unless cuBLAS is asked for; tf32=False = cuBLAS fp32 (strict-parity mode)
+        self.gemm = gemm if self.tf32 else "cublas"
         self._n_train_steps_total = 0
         self._need_to_update_eval_statistics = True
         self.eval_statistics = OrderedDict()
@@ -359,6 +364,24 @@ class SACTrainer:
         rows, cols = dy.shape[-2], dy.shape[-1]
         _chk(self.L.rsb_colsum(_ptr(dy), r0, r1, cols, _ptr(db), nmat, rows * cols, cols, _stream(self.device)))
 
+    def _mm(self, a, b, out, bias=None, relu=False, mask=None, accumulate=False):
+        """out = epilogue(a @ b) (2-D, or 3-D batched over the twin networks): ONE launch of the tcgen05 TF32 kernel with the bias / ReLU /
+        ReLU-backward mask / accumulation in its epilogue (gemm="tcgen05"), or the cuBLAS product followed by the elementwise kernels
+        (gemm="cublas": fp32 when tf32=False -- the mode the strict oracle-parity test runs in)."""
+        if self.gemm == "tcgen05":
+            return gemm_tf32(a, b, out, bias=bias, relu=relu, mask=mask, accumulate=accumulate)
+        t = self.torch
+        if accumulate:
+            out.addmm_(a, b)
+        elif a.dim() == 3:
+            t.bmm(a, b, out=out)
+        else:
+            t.mm(a, b, out=out)
+        if bias is not None:
+            self._bias_relu(out, bias, int(relu), out.shape[0] if out.dim() == 3 else 1)
+        if mask is not None:
+            self._relu_bwd(out, mask)
+
     def _sample(self, step):
         s = self.store
         B, O = self.B, s.O
@@ -381,9 +404,10 @@ class SACTrainer:
         if not external_eps:
             _chk(L.rsb_normal(C.c_uint64(self.seed), C.c_uint64(step_for_noise), 7, 2 * B * A, _ptr(self.eps), st))
         # policy forward on [obs; next_obs]
-        t.mm(self.Xp, P["p_W0"], out=self.H1p); self._bias_relu(self.H1p, P["p_b0"], 1)
-        t.mm(self.H1p, P["p_W1"], out=self.H2p); self._bias_relu(self.H2p, P["p_b1"], 1)
-        t.mm(self.H2p, P["p_W2"], out=self.OUT); self._bias_relu(self.OUT, P["p_b2"], 0)
+        mm = self._mm
+        mm(self.Xp, P["p_W0"], self.H1p, bias=P["p_b0"], relu=True)
+        mm(self.H1p, P["p_W1"], self.H2p, bias=P["p_b1"], relu=True)
+        mm(self.H2p, P["p_W2"], self.OUT, bias=P["p_b2"])
         _chk(L.rsb_head_fwd(_ptr(self.OUT), _ptr(self.eps), 2 * B, A, _ptr(self.a_store), _ptr(self.logpi),
                             C.c_void_p(self.XQ.data_ptr() + 4 * O), QI, 0, B, C.c_void_p(self.XT.data_ptr() + 4 * O), QI, B, 2 * B, st))
         # twin Q forward (batched over the two networks) on [(obs,a_new); (obs,act)]; target twin Q on (next_obs, a') on a side stream
@@ -392,12 +416,12 @@ class SACTrainer:
         sT, sW = (self._sT, self._sW) if self.parallel_branches else (main, main)
         sT.wait_stream(main)
         with t.cuda.stream(sT):
-            t.bmm(XT2, T["q_W0"], out=self.H1t); self._bias_relu(self.H1t, T["q_b0"], 1, 2)
-            t.bmm(self.H1t, T["q_W1"], out=self.H2t); self._bias_relu(self.H2t, T["q_b1"], 1, 2)
-            t.bmm(self.H2t, T["q_W2"], out=self.qt); self._bias_relu(self.qt, T["q_b2"], 0, 2)
-        t.bmm(XQ2, P["q_W0"], out=self.H1q); self._bias_relu(self.H1q, P["q_b0"], 1, 2)
-        t.bmm(self.H1q, P["q_W1"], out=self.H2q); self._bias_relu(self.H2q, P["q_b1"], 1, 2)
-        t.bmm(self.H2q, P["q_W2"], out=self.q); self._bias_relu(self.q, P["q_b2"], 0, 2)
+            mm(XT2, T["q_W0"], self.H1t, bias=T["q_b0"], relu=True)
+            mm(self.H1t, T["q_W1"], self.H2t, bias=T["q_b1"], relu=True)
+            mm(self.H2t, T["q_W2"], self.qt, bias=T["q_b2"])
+        mm(XQ2, P["q_W0"], self.H1q, bias=P["q_b0"], relu=True)
+        mm(self.H1q, P["q_W1"], self.H2q, bias=P["q_b1"], relu=True)
+        mm(self.H2q, P["q_W2"], self.q, bias=P["q_b2"])
         main.wait_stream(sT)
         # losses and their gradients w.r.t. the Q outputs / log_alpha
         _chk(L.rsb_sac_losses(_ptr(self.q), _ptr(self.qt), _ptr(self.logpi), _ptr(self.rew), _ptr(self.term), _ptr(self.alpha),
@@ -405,25 +429,26 @@ class SACTrainer:
                               _ptr(G["log_alpha"]), st))
         # twin-Q backward: weight grads from the Bellman rows [B, 2B) only, input grads for the policy rows [0, B).  The input-gradient
         # chain (dq -> dH2q -> dH1q -> gX -> policy head -> dH2p -> dH1p) runs on the main stream; every weight/bias gradient only needs the
-        # activation gradient of its own layer and goes to the side stream as soon as that exists.
+        # activation gradient of its own layer and goes to the side stream as soon as that exists.  `mask=` is the ReLU backward of the
+        # layer that produced the mask tensor, fused into the product's epilogue.
         def weight_grads(fn):
             sW.wait_stream(main)
             with t.cuda.stream(sW):
                 fn()
-        weight_grads(lambda: (t.bmm(self.H2q[:, B:].transpose(1, 2), self.dq[:, B:], out=G["q_W2"]), self._colsum(self.dq, B, 2 * B, G["q_b2"], 2)))
-        t.bmm(self.dq, P["q_W2"].transpose(1, 2), out=self.dH2q); self._relu_bwd(self.dH2q, self.H2q)
-        weight_grads(lambda: (t.bmm(self.H1q[:, B:].transpose(1, 2), self.dH2q[:, B:], out=G["q_W1"]), self._colsum(self.dH2q, B, 2 * B, G["q_b1"], 2)))
-        t.bmm(self.dH2q, P["q_W1"].transpose(1, 2), out=self.dH1q); self._relu_bwd(self.dH1q, self.H1q)
-        weight_grads(lambda: (t.bmm(XQ2[:, B:].transpose(1, 2), self.dH1q[:, B:], out=G["q_W0"]), self._colsum(self.dH1q, B, 2 * B, G["q_b0"], 2)))
-        t.mm(self.dH1q[0, :B], P["q_W0"][0].t(), out=self.gX); self.gX.addmm_(self.dH1q[1, :B], P["q_W0"][1].t())
+        weight_grads(lambda: (mm(self.H2q[:, B:].transpose(1, 2), self.dq[:, B:], G["q_W2"]), self._colsum(self.dq, B, 2 * B, G["q_b2"], 2)))
+        mm(self.dq, P["q_W2"].transpose(1, 2), self.dH2q, mask=self.H2q)
+        weight_grads(lambda: (mm(self.H1q[:, B:].transpose(1, 2), self.dH2q[:, B:], G["q_W1"]), self._colsum(self.dH2q, B, 2 * B, G["q_b1"], 2)))
+        mm(self.dH2q, P["q_W1"].transpose(1, 2), self.dH1q, mask=self.H1q)
+        weight_grads(lambda: (mm(XQ2[:, B:].transpose(1, 2), self.dH1q[:, B:], G["q_W0"]), self._colsum(self.dH1q, B, 2 * B, G["q_b0"], 2)))
+        mm(self.dH1q[0, :B], P["q_W0"][0].t(), self.gX); mm(self.dH1q[1, :B], P["q_W0"][1].t(), self.gX, accumulate=True)
         # policy backward
         _chk(L.rsb_head_bwd(_ptr(self.OUT), _ptr(self.eps), _ptr(self.a_store), 2 * B, B, A, _ptr(self.alpha),
                             C.c_void_p(self.gX.data_ptr() + 4 * O), QI, _ptr(self.dOUT), _stream(self.device)))
-        weight_grads(lambda: (t.mm(self.H2p[:B].t(), self.dOUT[:B], out=G["p_W2"]), self._colsum(self.dOUT, 0, B, G["p_b2"])))
-        t.mm(self.dOUT[:B], P["p_W2"].t(), out=self.dH2p); self._relu_bwd(self.dH2p, self.H2p[:B])
-        weight_grads(lambda: (t.mm(self.H1p[:B].t(), self.dH2p, out=G["p_W1"]), self._colsum(self.dH2p, 0, B, G["p_b1"])))
-        t.mm(self.dH2p, P["p_W1"].t(), out=self.dH1p); self._relu_bwd(self.dH1p, self.H1p[:B])
-        weight_grads(lambda: (t.mm(self.Xp[:B].t(), self.dH1p, out=G["p_W0"]), self._colsum(self.dH1p, 0, B, G["p_b0"])))
+        weight_grads(lambda: (mm(self.H2p[:B].t(), self.dOUT[:B], G["p_W2"]), self._colsum(self.dOUT, 0, B, G["p_b2"])))
+        mm(self.dOUT[:B], P["p_W2"].t(), self.dH2p, mask=self.H2p[:B])
+        weight_grads(lambda: (mm(self.H1p[:B].t(), self.dH2p, G["p_W1"]), self._colsum(self.dH2p, 0, B, G["p_b1"])))
+        mm(self.dH2p, P["p_W1"].t(), self.dH1p, mask=self.H1p[:B])
+        weight_grads(lambda: (mm(self.Xp[:B].t(), self.dH1p, G["p_W0"]), self._colsum(self.dH1p, 0, B, G["p_b0"])))
         main.wait_stream(sW)
 
     def _apply(self, do_soft):
