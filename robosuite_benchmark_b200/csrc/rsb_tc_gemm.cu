@@ -43,18 +43,20 @@ void rsb_sac_set_error(const char *msg);   /* rsb_sac.cu: the string rsb_sac_las
 #define NTHREADS 256
 #define A_BYTES (BM * KC * 4)
 #define B_BYTES (BN_MAX * KC * 4)
-#define CTRL_OFF (3 * (A_BYTES + B_BYTES))      /* = 4 x (32 KB + 64 x 256 B): control block (4 mbarriers, tensor-memory slot, bias row) behind the stages */
-#define SMEM_BYTES (CTRL_OFF + 64 + BN_MAX * 4)
+#define CTRL_BYTES 1024                         /* control block in front of the stages: 4 mbarriers, tensor-memory slot, bias row */
+#define SMEM_MAX 232448                         /* 227 KB: the most one CTA may ask for */
 #define TMEM_COLS 128
 
 struct GemmArgs {
   const float *a, *b, *bias, *mask;
   float *c;
   long long a_rs, a_cs, a_bs, b_ks, b_ns, b_bs, c_rs, c_bs, bias_bs, mask_rs, mask_bs;
-  int m, n, k, flags, n_tile, lbo16, sbo16;
+  int m, n, k, flags, n_tile, lbo16, sbo16, splits, cps, recv_off, stages;   /* splits: CTAs of one cluster sharing a C tile along K; cps: chunks per split */
 };
 
 __device__ unsigned int g_gemm_timeouts;
+__device__ long long g_gemm_clk[12];         /* phase clocks of CTA (0,0,0)'s thread 0 of the last launch (diagnostic, rsb_gemm_debug_clocks) */
+#define CLK(i) do { if (tid == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) g_gemm_clk[i] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -106,30 +108,34 @@ __device__ __forceinline__ void load_tile(uint32_t dst, const float *base, long 
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * g.n_tile, m0 = blockIdx.y * BM, bz = blockIdx.z;
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar0 = sbase + CTRL_OFF, tslot = bar0 + 32;
-  volatile uint32_t *tslot_p = (volatile uint32_t *)(smem + CTRL_OFF + 32);
-  float *sbias = (float *)(smem + CTRL_OFF + 64);
-  const int S = (g.n_tile == 128) ? 3 : 4;                      /* stages: 3 x 64 KB or 4 x (32 KB + n_tile x 256 B) */
+  const int rank = blockIdx.x % g.splits;                       /* = %cluster_ctarank: the cluster is (splits, 1, 1) */
+  const int n0 = (blockIdx.x / g.splits) * g.n_tile, m0 = blockIdx.y * BM, bz = blockIdx.z;
+  const uint32_t bar0 = smem_u32(smem), tslot = bar0 + 32, sbase = bar0 + CTRL_BYTES;
+  volatile uint32_t *tslot_p = (volatile uint32_t *)(smem + 32);
+  float *sbias = (float *)(smem + 64);
+  const int S = g.stages;                   /* stages: 3 x 64 KB or 4 x (32 KB + n_tile x 256 B) */
   const uint32_t stage_bytes = A_BYTES + (uint32_t)g.n_tile * (KC * 4);
 
-  const float *A = g.a + (long long)bz * g.a_bs + (long long)m0 * g.a_rs;
-  const float *B = g.b + (long long)bz * g.b_bs + (long long)n0 * g.b_ns;
+  const int kbeg = rank * g.cps * KC, klen = min(g.k, kbeg + g.cps * KC) - kbeg;        /* this CTA's slice of the contraction */
+  const float *A = g.a + (long long)bz * g.a_bs + (long long)m0 * g.a_rs + (long long)kbeg * g.a_cs;
+  const float *B = g.b + (long long)bz * g.b_bs + (long long)n0 * g.b_ns + (long long)kbeg * g.b_ks;
   const bool a16 = g.a_cs == 1 && (g.a_rs & 3) == 0 && ((uintptr_t)A & 15) == 0;
   const bool b16 = g.b_ks == 1 && (g.b_ns & 3) == 0 && ((uintptr_t)B & 15) == 0;
-  const int mvalid = g.m - m0, nvalid = g.n - n0, nchunks = (g.k + KC - 1) / KC;
+  const int mvalid = g.m - m0, nvalid = g.n - n0, nchunks = (klen + KC - 1) / KC;
 
+  CLK(0);
+  if (g.splits > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n" ::: "memory");   /* waited for just before the first remote store */
   /* the first S chunks go out before anything else: the copies fly while tensor memory is allocated and the barriers are set up */
   for (int c = 0; c < S; c++) {
     if (c < nchunks) {
-      load_tile(sbase + c * stage_bytes, A + (long long)(c * KC) * g.a_cs, g.a_rs, g.a_cs, BM, mvalid, g.k - c * KC, a16);
-      load_tile(sbase + c * stage_bytes + A_BYTES, B + (long long)(c * KC) * g.b_ks, g.b_ns, g.b_ks, g.n_tile, nvalid, g.k - c * KC, b16);
+      load_tile(sbase + c * stage_bytes, A + (long long)(c * KC) * g.a_cs, g.a_rs, g.a_cs, BM, mvalid, klen - c * KC, a16);
+      load_tile(sbase + c * stage_bytes + A_BYTES, B + (long long)(c * KC) * g.b_ks, g.b_ns, g.b_ks, g.n_tile, nvalid, klen - c * KC, b16);
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   }
+  CLK(1);
   if (tid < g.n_tile) sbias[tid] = (g.bias && tid < nvalid) ? __ldg(g.bias + (long long)bz * g.bias_bs + n0 + tid) : 0.0f;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tslot), "r"(TMEM_COLS) : "memory");
@@ -144,18 +150,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = *tslot_p;
+  CLK(2);
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   const uint64_t desc_hi = ((uint64_t)g.lbo16 << 16) | ((uint64_t)g.sbo16 << 32) | (1ull << 46);
 
   int st = 0, ph = 0;                                           /* stage and mbarrier phase of chunk i: i % S, (i / S) & 1 */
   for (int i = 0; i < nchunks; i++) {
     if (S == 4) asm volatile("cp.async.wait_group 3;\n" ::: "memory");      /* exactly S-1 groups are younger than chunk i's */
-    else asm volatile("cp.async.wait_group 2;\n" ::: "memory");
+    else if (S == 3) asm volatile("cp.async.wait_group 2;\n" ::: "memory");
+    else if (S == 2) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
+    if (i == 0) CLK(3);
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const int kmma = (min(KC, g.k - i * KC) + 7) >> 3;
+      const int kmma = (min(KC, klen - i * KC) + 7) >> 3;
       const uint32_t a_addr = sbase + st * stage_bytes, b_addr = a_addr + A_BYTES;
       for (int kk = 0; kk < kmma; kk++) {
         const uint64_t da = desc_hi | (uint64_t)(((a_addr + kk * 256) >> 4) & 0x3FFF);
@@ -169,22 +179,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
     if (i + S < nchunks) {                                      /* refill this stage once its products have read it */
       const int k1 = (i + S) * KC;
       mbar_wait(bar0 + 8 * st, ph);
-      load_tile(sbase + st * stage_bytes, A + (long long)k1 * g.a_cs, g.a_rs, g.a_cs, BM, mvalid, g.k - k1, a16);
-      load_tile(sbase + st * stage_bytes + A_BYTES, B + (long long)k1 * g.b_ks, g.b_ns, g.b_ks, g.n_tile, nvalid, g.k - k1, b16);
+      load_tile(sbase + st * stage_bytes, A + (long long)k1 * g.a_cs, g.a_rs, g.a_cs, BM, mvalid, klen - k1, a16);
+      load_tile(sbase + st * stage_bytes + A_BYTES, B + (long long)k1 * g.b_ks, g.b_ns, g.b_ks, g.n_tile, nvalid, klen - k1, b16);
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     if (i + 1 < nchunks && ++st == S) { st = 0; ph ^= 1; }
   }
+  CLK(4);
   const bool done = mbar_wait(bar0 + 8 * st, ph);               /* the last commit covers every product issued before it */
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 
-  /* epilogue: warp w reads lanes 32*(w%4) .. +31 (one row of C per thread); warps w and w+4 take alternate 16-column slabs */
+  CLK(5);
+  /* epilogue.  (1) every warp takes its share of the accumulator out of tensor memory (warp w reads lanes 32*(w%4).., one row of C per thread,
+     `tcgen05.ld.32x32b.x16`; warps w and w+4 take alternate 16-column slabs) and sends each group of 4 columns to the CTA that owns them:
+     CTA j of the cluster owns columns [j, j+1) * n_tile/splits of the tile and keeps one receive panel per sender (rows padded by 4 words).
+     Without split-K the panel is the CTA's own and lies over the (now free) stages; with split-K the panels lie behind the stages, because a
+     fast CTA may deliver while the owner's products still read its stages, and the stores go through distributed shared memory.
+     (2) ONE CTA / cluster barrier.  (3) the owner sums its panels in sender order (deterministic) and runs bias / ReLU / mask / accumulate;
+     a thread handles 4 consecutive columns of a row, so the lanes of a warp write contiguous pieces of C.  Nothing remote is touched after
+     the barrier, so the CTAs of a cluster retire independently. */
+  const int w = g.n_tile / g.splits, ldp = w + 4, wsh = 31 - __clz(w >> 2);       /* w/4 = 1 << wsh column groups per owner */
+  float *recv = (float *)(smem + CTRL_BYTES + (g.splits > 1 ? g.recv_off : 0));
+  if (g.splits > 1) asm volatile("barrier.cluster.wait.aligned;\n" ::: "memory");    /* (arrived at entry) every CTA of the cluster is running */
   {
-    const int q = warp & 3, half = warp >> 2, r = q * 32 + lane, m = m0 + r;
-    float *crow = g.c + (long long)bz * g.c_bs + (long long)m * g.c_rs + n0;
-    const float *mrow = g.mask ? g.mask + (long long)bz * g.mask_bs + (long long)m * g.mask_rs + n0 : nullptr;
-    const bool relu = g.flags & RSB_GEMM_RELU, accum = g.flags & RSB_GEMM_ACCUMULATE;
-    const bool st16 = ((g.c_rs & 3) == 0) && (((uintptr_t)(g.c + (long long)bz * g.c_bs + n0) & 15) == 0);
+    const int q = warp & 3, half = warp >> 2, r = q * 32 + lane;
+    const uint32_t mine = smem_u32(recv + (rank * BM + r) * ldp);
     for (int c0 = half * 16; c0 < g.n_tile; c0 += 32) {
       uint32_t v[16];
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -192,38 +211,75 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                    : "r"(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0) : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-      if (m < g.m && done) {
-        float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-          const int nn = c0 + j;
-          float x = __uint_as_float(v[j]);
+      for (int j = 0; j < 16; j += 4) {
+        const int c = c0 + j, owner = c >> (wsh + 2), cl = c & (w - 1);
+        uint32_t dst = mine + cl * 4;
+        if (g.splits > 1) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(dst) : "r"(mine + cl * 4), "r"(owner));
+        asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "r"(v[j]), "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3]) : "memory");
+      }
+    }
+  }
+  CLK(8);
+  if (g.splits == 1) __syncthreads();
+  else {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  }
+  CLK(9);
+  {
+    const bool relu = g.flags & RSB_GEMM_RELU, accum = g.flags & RSB_GEMM_ACCUMULATE;
+    const int cbase = rank * w;                                 /* first tile column this CTA owns */
+    float *cbase_p = g.c + (long long)bz * g.c_bs + n0;
+    const float *mbase_p = g.mask ? g.mask + (long long)bz * g.mask_bs + n0 : nullptr;
+    const bool st16 = ((g.c_rs & 3) == 0) && (((uintptr_t)cbase_p & 15) == 0);
+    for (int t = tid; t < (BM << wsh); t += NTHREADS) {
+      const int row = t >> wsh, cl = (t - (row << wsh)) * 4, c = cbase + cl, m = m0 + row;
+      const float *lp = recv + row * ldp + cl;
+      float4 x = *reinterpret_cast<const float4 *>(lp);
+      for (int sidx = 1; sidx < g.splits; sidx++) {
+        const float4 pv = *reinterpret_cast<const float4 *>(lp + sidx * BM * ldp);
+        x.x += pv.x; x.y += pv.y; x.z += pv.z; x.w += pv.w;
+      }
+      if (m < g.m && done && c < nvalid) {
+        float *crow = cbase_p + (long long)m * g.c_rs;
+        const float *mrow = mbase_p ? mbase_p + (long long)m * g.mask_rs : nullptr;
+        const float4 bv = *reinterpret_cast<const float4 *>(sbias + c);
+        float f[4] = {x.x + bv.x, x.y + bv.y, x.z + bv.z, x.w + bv.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int nn = c + j;
           if (nn < nvalid) {
-            x += sbias[nn];
-            if (relu) x = fmaxf(x, 0.0f);
-            if (mrow) x = (mrow[nn] > 0.0f) ? x : 0.0f;
-            if (accum) x += crow[nn];
+            if (relu) f[j] = fmaxf(f[j], 0.0f);
+            if (mrow) f[j] = (mrow[nn] > 0.0f) ? f[j] : 0.0f;
+            if (accum) f[j] += crow[nn];
           }
-          f[j] = x;
         }
-        if (st16 && c0 + 16 <= nvalid) {
+        if (st16 && c + 4 <= nvalid) *reinterpret_cast<float4 *>(crow + c) = make_float4(f[0], f[1], f[2], f[3]);
+        else {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(crow + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; j++) if (c0 + j < nvalid) crow[c0 + j] = f[j];
+          for (int j = 0; j < 4; j++) if (c + j < nvalid) crow[c + j] = f[j];
         }
       }
     }
   }
+  CLK(10);
+  CLK(6);
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  CLK(7);
 }
 
-static int g_swap_offsets = 0;
+static int g_swap_offsets = 0, g_force_splits = 0;
 
 extern "C" void rsb_gemm_debug_swap_offsets(int swap) { g_swap_offsets = swap; }
+extern "C" void rsb_gemm_debug_splits(int splits) { g_force_splits = splits; }
+
+extern "C" int rsb_gemm_debug_clocks(long long *host_out12) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+  return cudaMemcpyFromSymbol(host_out12, g_gemm_clk, 12 * sizeof(long long)) != cudaSuccess;
+}
 
 extern "C" int rsb_gemm_timeouts(void) {
   unsigned int h = 0, z = 0;
@@ -248,7 +304,7 @@ extern "C" int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, 
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess && dev < 64 && !attr_set[dev]) {
-    e = cudaFuncSetAttribute(k_gemm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    e = cudaFuncSetAttribute(k_gemm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     attr_set[dev] = (e == cudaSuccess);
   }
   if (e != cudaSuccess) { rsb_sac_set_error(cudaGetErrorString(e)); return 1; }
@@ -259,9 +315,37 @@ extern "C" int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, 
   g.m = m; g.n = n; g.k = k; g.flags = flags; g.n_tile = n_tile;
   g.lbo16 = g_swap_offsets ? (2048 >> 4) : (128 >> 4);
   g.sbo16 = g_swap_offsets ? (128 >> 4) : (2048 >> 4);
-  dim3 grid((n + n_tile - 1) / n_tile, mt, batch);
-  k_gemm_tf32<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(g);
-  e = cudaGetLastError();
+  /* split the contraction over a cluster of 2 or 4 CTAs while the launch still fits one wave: at the update's sizes the time of a product is
+     the time one SM needs to pull its operands in, so more SMs with less each is what helps */
+  const int ctas = ((n + n_tile - 1) / n_tile) * mt * batch, nchunks_all = (k + KC - 1) / KC;
+  int splits = g_force_splits;
+  if (splits == 0) { splits = 4; while (splits > 1 && (splits > nchunks_all || ctas * splits > 148)) splits >>= 1; }
+  if (splits != 1 && splits != 2 && splits != 4) { rsb_sac_set_error("rsb_gemm_tf32: splits must be 1, 2 or 4"); return 1; }
+  int cps = (nchunks_all + splits - 1) / splits;
+  while (splits > 1 && (splits - 1) * cps >= nchunks_all) { splits >>= 1; cps = (nchunks_all + splits - 1) / splits; }   /* no empty slice */
+  g.splits = splits; g.cps = cps;
+  dim3 grid(((n + n_tile - 1) / n_tile) * splits, mt, batch);
+  /* shared memory: the stages this launch can fill (4 x (32 KB + n_tile x 256 B); 3 at n_tile = 128, 2 if that tile is also split) and, with
+     split-K, the receive panels behind them; without split-K the single panel lies over the stages */
+  int stages = (n_tile == 128) ? (splits > 1 ? 2 : 3) : 4;
+  if (cps < stages) stages = cps;
+  const size_t panels = (size_t)splits * BM * (n_tile / splits + 4) * 4;
+  while (stages > 1 && CTRL_BYTES + (size_t)stages * (A_BYTES + (size_t)n_tile * KC * 4) + (splits > 1 ? panels : 0) > SMEM_MAX) stages--;
+  g.stages = stages; g.recv_off = (int)((size_t)stages * (A_BYTES + (size_t)n_tile * KC * 4));
+  size_t smem_bytes = CTRL_BYTES + (size_t)g.recv_off + (splits > 1 ? panels : 0);
+  if (smem_bytes < CTRL_BYTES + panels) smem_bytes = CTRL_BYTES + panels;
+  if (splits == 1) {
+    k_gemm_tf32<<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(g);
+    e = cudaGetLastError();
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(NTHREADS, 1, 1); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = splits; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, k_gemm_tf32, g);
+  }
   if (e != cudaSuccess) { rsb_sac_set_error(cudaGetErrorString(e)); return 1; }
   return 0;
 }

@@ -24,10 +24,11 @@ def test_tcgen05_gemm_matches_fp64_on_every_sac_shape(dev):
     import diag_tc_gemm as d
     from robosuite_benchmark_b200 import gemm
     for c in d.cases():
-        for nt in (0, 16, 64):
-            err, *_ = d.run_case(c, dev, nt)
+        for nt, splits in ((0, 0), (16, 1), (16, 4), (64, 2), (128, 4), (32, 1)):     # tile width x CTAs sharing a tile along K (0 = chosen)
+            err, *_ = d.run_case(c, dev, nt, splits)
             assert gemm.timeouts() == 0, c
-            assert err < 3e-3, (c, nt, err)
+            assert err < 3e-3, (c, nt, splits, err)
+    d.lib().rsb_gemm_debug_splits(0)
 
 
 def test_tcgen05_gemm_is_deterministic_and_graph_capturable(dev):
