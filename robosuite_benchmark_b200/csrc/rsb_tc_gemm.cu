@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = blockIdx.x % g.splits;                       /* = %cluster_ctarank: the cluster is (splits, 1, 1) */
   const int n0 = (blockIdx.x / g.splits) * g.n_tile, m0 = blockIdx.y * BM, bz = blockIdx.z;
-  const uint32_t bar0 = smem_u32(smem), tslot = bar0 + 32, sbase = bar0 + CTRL_BYTES;
+  const uint32_t bar0 = smem_u32(smem), tslot = bar0 + 32, rbar = bar0 + 40, sbase = bar0 + CTRL_BYTES;
   volatile uint32_t *tslot_p = (volatile uint32_t *)(smem + 32);
   float *sbias = (float *)(smem + 64);
   const int S = g.stages;                   /* stages: 3 x 64 KB or 4 x (32 KB + n_tile x 256 B) */
@@ -126,7 +126,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
   const int mvalid = g.m - m0, nvalid = g.n - n0, nchunks = (klen + KC - 1) / KC;
 
   CLK(0);
-  if (g.splits > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n" ::: "memory");   /* waited for just before the first remote store */
   /* the first S chunks go out before anything else: the copies fly while tensor memory is allocated and the barriers are set up */
   for (int c = 0; c < S; c++) {
     if (c < nchunks) {
@@ -144,12 +143,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
   if (tid == 32) {
 #pragma unroll
     for (int c = 0; c < 4; c++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0 + 8 * c) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(rbar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    /* split-K: this CTA will receive splits x 128 x (n_tile/splits) partial sums = 512 x n_tile bytes on `rbar` (one phase) */
+    if (g.splits > 1) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(rbar), "r"(512 * g.n_tile) : "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = *tslot_p;
+  /* split-K: tell the cluster that this CTA runs and its receive barrier is armed; waited for just before the first remote store */
+  if (g.splits > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
   CLK(2);
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   const uint64_t desc_hi = ((uint64_t)g.lbo16 << 16) | ((uint64_t)g.sbo16 << 32) | (1ull << 46);
@@ -195,12 +199,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
      CTA j of the cluster owns columns [j, j+1) * n_tile/splits of the tile and keeps one receive panel per sender (rows padded by 4 words).
      Without split-K the panel is the CTA's own and lies over the (now free) stages; with split-K the panels lie behind the stages, because a
      fast CTA may deliver while the owner's products still read its stages, and the stores go through distributed shared memory.
-     (2) ONE CTA / cluster barrier.  (3) the owner sums its panels in sender order (deterministic) and runs bias / ReLU / mask / accumulate;
+     The remote stores are `st.async` with mbarrier completion: the owner arms one receive barrier with the 512 x n_tile bytes it expects.
+     (2) CTA barrier, or wait on the receive barrier (no cluster-wide release fence on the critical path).  (3) the owner sums its panels in sender order (deterministic) and runs bias / ReLU / mask / accumulate;
      a thread handles 4 consecutive columns of a row, so the lanes of a warp write contiguous pieces of C.  Nothing remote is touched after
      the barrier, so the CTAs of a cluster retire independently. */
   const int w = g.n_tile / g.splits, ldp = w + 4, wsh = 31 - __clz(w >> 2);       /* w/4 = 1 << wsh column groups per owner */
   float *recv = (float *)(smem + CTRL_BYTES + (g.splits > 1 ? g.recv_off : 0));
-  if (g.splits > 1) asm volatile("barrier.cluster.wait.aligned;\n" ::: "memory");    /* (arrived at entry) every CTA of the cluster is running */
+  if (g.splits > 1) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");    /* every CTA of the cluster runs, receive barriers armed */
   {
     const int q = warp & 3, half = warp >> 2, r = q * 32 + lane;
     const uint32_t mine = smem_u32(recv + (rank * BM + r) * ldp);
@@ -214,18 +219,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
         const int c = c0 + j, owner = c >> (wsh + 2), cl = c & (w - 1);
-        uint32_t dst = mine + cl * 4;
-        if (g.splits > 1) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(dst) : "r"(mine + cl * 4), "r"(owner));
-        asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "r"(v[j]), "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3]) : "memory");
+        if (g.splits > 1) {                                     /* asynchronous remote store that reports its 16 bytes on the owner's receive barrier */
+          uint32_t dst, dbar;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(dst) : "r"(mine + cl * 4), "r"(owner));
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(dbar) : "r"(rbar), "r"(owner));
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n"
+                       ::"r"(dst), "r"(v[j]), "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3]), "r"(dbar) : "memory");
+        } else
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(mine + cl * 4), "r"(v[j]), "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3]) : "memory");
       }
     }
   }
   CLK(8);
+  bool got = true;
   if (g.splits == 1) __syncthreads();
-  else {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-  }
+  else got = mbar_wait(rbar, 0);                                /* every partial sum addressed to this CTA has landed */
   CLK(9);
   {
     const bool relu = g.flags & RSB_GEMM_RELU, accum = g.flags & RSB_GEMM_ACCUMULATE;
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
         const float4 pv = *reinterpret_cast<const float4 *>(lp + sidx * BM * ldp);
         x.x += pv.x; x.y += pv.y; x.z += pv.z; x.w += pv.w;
       }
-      if (m < g.m && done && c < nvalid) {
+      if (m < g.m && done && got && c < nvalid) {
         float *crow = cbase_p + (long long)m * g.c_rs;
         const float *mrow = mbase_p ? mbase_p + (long long)m * g.mask_rs : nullptr;
         const float4 bv = *reinterpret_cast<const float4 *>(sbias + c);
