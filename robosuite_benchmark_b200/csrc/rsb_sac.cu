@@ -73,12 +73,29 @@ __global__ void k_bias_relu(float *__restrict__ x, const float *__restrict__ bia
 __global__ void k_relu_bwd(float *__restrict__ dy, const float *__restrict__ y, long n) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dy[i] = y[i] > 0.0f ? dy[i] : 0.0f;
 }
-/* column sums of dY [rows, cols] rows in [r0, r1) -> db[cols] (one block per column group; small matrices) */
-__global__ void k_colsum(const float *__restrict__ dy, int r0, int r1, int cols, float *__restrict__ db, int nmat, long mat_stride, int db_stride) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x, mt = blockIdx.y; if (c >= cols || mt >= nmat) return;
-  float acc = 0; const float *p = dy + (long)mt * mat_stride;
-  for (int r = r0; r < r1; r++) acc += p[(long)r * cols + c];
-  db[mt * db_stride + c] = acc;
+/* column sums of dY [rows, cols] rows in [r0, r1) -> db[cols].  Block = 32 columns x 32 row slices: thread (x, y) adds rows r0+y, r0+y+32, ...
+   (independent coalesced loads, 4 in flight), the 32 slice sums of a column are added in slice order through shared memory (deterministic).
+   A thread per column walking all rows is a chain of (r1-r0) dependent-latency loads: 10-16 us at 128 rows, on the tail of every update. */
+__global__ void __launch_bounds__(1024) k_colsum(const float *__restrict__ dy, int r0, int r1, int cols, float *__restrict__ db, int nmat, long mat_stride, int db_stride) {
+  __shared__ float s[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, mt = blockIdx.y;
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+  if (c < cols) {
+    const float *p = dy + (long)mt * mat_stride + c;
+    int r = r0 + threadIdx.y;
+    for (; r + 96 < r1; r += 128) {
+      a0 += p[(long)r * cols]; a1 += p[(long)(r + 32) * cols]; a2 += p[(long)(r + 64) * cols]; a3 += p[(long)(r + 96) * cols];
+    }
+    for (; r < r1; r += 32) a0 += p[(long)r * cols];
+  }
+  s[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.0f;
+#pragma unroll
+    for (int y = 0; y < 32; y++) t += s[y][threadIdx.x];
+    db[mt * db_stride + c] = t;
+  }
 }
 
 /* ---------------------------------------------------------------- tanh-Gaussian head (rlkit TanhGaussianPolicy / TanhNormal)
@@ -208,7 +225,7 @@ int rsb_bias_relu(float *d_x, const float *d_bias, int rows, int cols, int relu,
 }
 int rsb_relu_bwd(float *d_dy, const float *d_y, long n, void *stream) { k_relu_bwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_dy, d_y, n); CKS(cudaGetLastError()); return 0; }
 int rsb_colsum(const float *d_dy, int r0, int r1, int cols, float *d_db, int nmat, long mat_stride, int db_stride, void *stream) {
-  dim3 grid((cols + 127) / 128, nmat); k_colsum<<<grid, 128, 0, (cudaStream_t)stream>>>(d_dy, r0, r1, cols, d_db, nmat, mat_stride, db_stride); CKS(cudaGetLastError()); return 0;
+  dim3 grid((cols + 31) / 32, nmat); k_colsum<<<grid, dim3(32, 32), 0, (cudaStream_t)stream>>>(d_dy, r0, r1, cols, d_db, nmat, mat_stride, db_stride); CKS(cudaGetLastError()); return 0;
 }
 int rsb_head_fwd(const float *d_out, const float *d_eps, int rows, int act_dim, float *d_a, float *d_logpi, float *dst0, int ld0, int r0lo, int r0hi, float *dst1, int ld1, int r1lo, int r1hi, void *stream) {
   k_head_fwd<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_out, d_eps, rows, act_dim, d_a, d_logpi, dst0, ld0, r0lo, r0hi, dst1, ld1, r1lo, r1hi); CKS(cudaGetLastError()); return 0;

@@ -30,6 +30,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string>
 
 #include "../../include/rsb_gemm.h"
@@ -327,7 +328,9 @@ extern "C" int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, 
      the time one SM needs to pull its operands in, so more SMs with less each is what helps */
   const int ctas = ((n + n_tile - 1) / n_tile) * mt * batch, nchunks_all = (k + KC - 1) / KC;
   int splits = g_force_splits;
-  if (splits == 0) { splits = 4; while (splits > 1 && (splits > nchunks_all || ctas * splits > 148)) splits >>= 1; }
+  static int max_ctas = 0;                                       /* developer knob RSB_GEMM_MAX_CTAS: CTAs one product may occupy */
+  if (max_ctas == 0) { const char *ev = getenv("RSB_GEMM_MAX_CTAS"); max_ctas = ev ? atoi(ev) : 148; if (max_ctas < 1) max_ctas = 148; }
+  if (splits == 0) { splits = 4; while (splits > 1 && (splits > nchunks_all || ctas * splits > max_ctas)) splits >>= 1; }
   if (splits != 1 && splits != 2 && splits != 4) { rsb_sac_set_error("rsb_gemm_tf32: splits must be 1, 2 or 4"); return 1; }
   int cps = (nchunks_all + splits - 1) / splits;
   while (splits > 1 && (splits - 1) * cps >= nchunks_all) { splits >>= 1; cps = (nchunks_all + splits - 1) / splits; }   /* no empty slice */
