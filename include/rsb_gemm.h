@@ -19,10 +19,13 @@ extern "C" {
 #endif
 #define RSB_GEMM_RELU 1
 #define RSB_GEMM_ACCUMULATE 2
-/* n_tile: 0 = choose (16/32/64/128 output columns per CTA; one CTA owns a 128 x n_tile tile of C) */
+/* n_tile: 0 = choose (16/32/64/128 output columns per CTA; one CTA owns a 128 x n_tile tile of C).
+   k_block > 0 (a multiple of 64): the contraction index runs over k / k_block blocks that lie a_kbs / b_kbs elements apart (A[m, k] at
+   a + (k / k_block) * a_kbs + m * a_rs + (k % k_block) * a_cs, likewise B) -- e.g. the twin Q networks' activation gradients side by side, so that
+   dX = dH_1 W_1^T + dH_2 W_2^T is ONE product; k_block = 0: plain strides. */
 int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, const float *d_b, long b_ks, long b_ns, long b_bs, float *d_c, long c_rs, long c_bs,
                   int m, int n, int k, int batch, const float *d_bias, long bias_bs, const float *d_mask, long mask_rs, long mask_bs, int flags, int n_tile,
-                  void *stream);
+                  int k_block, long a_kbs, long b_kbs, void *stream);
 /* device-side watchdog: number of mbarrier waits that gave up since the last call (0 on a healthy run); synchronises the device */
 int rsb_gemm_timeouts(void);
 /* diagnostic: exchange the two byte-offset fields of the shared-memory matrix descriptors (0 = as documented in csrc/rsb_tc_gemm.cu) */

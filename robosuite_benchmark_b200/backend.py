@@ -70,7 +70,7 @@ def lib():
         L.rsb_head_bwd.argtypes = [V, V, V, I, I, I, V, V, I, V, V]
         L.rsb_sac_losses.argtypes = [V, V, V, V, V, V, F, F, F, I, V, V, V, V, V]
         L.rsb_adam_polyak.argtypes = [V, V, V, V, L_, C.c_double, C.c_double, F, F, F, V, V, L_, L_, F, I, V, L_, V]
-        L.rsb_gemm_tf32.argtypes = [V, L_, L_, L_, V, L_, L_, L_, V, L_, L_, I, I, I, I, V, L_, V, L_, L_, I, I, V]
+        L.rsb_gemm_tf32.argtypes = [V, L_, L_, L_, V, L_, L_, L_, V, L_, L_, I, I, I, I, V, L_, V, L_, L_, I, I, I, L_, L_, V]
         L.rsb_gemm_debug_swap_offsets.argtypes = [I]
         L.rsb_gemm_debug_swap_offsets.restype = None
         L.rsb_gemm_debug_splits.argtypes = [I]

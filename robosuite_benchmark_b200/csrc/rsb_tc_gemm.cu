@@ -51,8 +51,8 @@ void rsb_sac_set_error(const char *msg);   /* rsb_sac.cu: the string rsb_sac_las
 struct GemmArgs {
   const float *a, *b, *bias, *mask;
   float *c;
-  long long a_rs, a_cs, a_bs, b_ks, b_ns, b_bs, c_rs, c_bs, bias_bs, mask_rs, mask_bs;
-  int m, n, k, flags, n_tile, lbo16, sbo16, splits, cps, recv_off, stages;   /* splits: CTAs of one cluster sharing a C tile along K; cps: chunks per split */
+  long long a_rs, a_cs, a_bs, b_ks, b_ns, b_bs, c_rs, c_bs, bias_bs, mask_rs, mask_bs, a_kbs, b_kbs;
+  int m, n, k, flags, n_tile, lbo16, sbo16, splits, cps, recv_off, stages, k_block;   /* splits: CTAs of one cluster sharing a C tile along K; cps: chunks per split */
 };
 
 __device__ unsigned int g_gemm_timeouts;
@@ -120,18 +120,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
   const uint32_t stage_bytes = A_BYTES + (uint32_t)g.n_tile * (KC * 4);
 
   const int kbeg = rank * g.cps * KC, klen = min(g.k, kbeg + g.cps * KC) - kbeg;        /* this CTA's slice of the contraction */
-  const float *A = g.a + (long long)bz * g.a_bs + (long long)m0 * g.a_rs + (long long)kbeg * g.a_cs;
-  const float *B = g.b + (long long)bz * g.b_bs + (long long)n0 * g.b_ns + (long long)kbeg * g.b_ks;
-  const bool a16 = g.a_cs == 1 && (g.a_rs & 3) == 0 && ((uintptr_t)A & 15) == 0;
-  const bool b16 = g.b_ks == 1 && (g.b_ns & 3) == 0 && ((uintptr_t)B & 15) == 0;
+  /* the contraction index may run over `k / k_block` separately strided blocks (two networks' activations side by side): chunk at absolute
+     k sits at block k / k_block, offset k % k_block; k_block is a multiple of the chunk, so a chunk never straddles blocks */
+  const float *A0 = g.a + (long long)bz * g.a_bs + (long long)m0 * g.a_rs;
+  const float *B0 = g.b + (long long)bz * g.b_bs + (long long)n0 * g.b_ns;
+  auto a_at = [&](int kabs) { const int blk = kabs / g.k_block; return A0 + (long long)blk * g.a_kbs + (long long)(kabs - blk * g.k_block) * g.a_cs; };
+  auto b_at = [&](int kabs) { const int blk = kabs / g.k_block; return B0 + (long long)blk * g.b_kbs + (long long)(kabs - blk * g.k_block) * g.b_ks; };
+  const float *A = a_at(kbeg), *B = b_at(kbeg);
+  const bool a16 = g.a_cs == 1 && (g.a_rs & 3) == 0 && (g.a_kbs & 3) == 0 && ((uintptr_t)A0 & 15) == 0;
+  const bool b16 = g.b_ks == 1 && (g.b_ns & 3) == 0 && (g.b_kbs & 3) == 0 && ((uintptr_t)B0 & 15) == 0;
   const int mvalid = g.m - m0, nvalid = g.n - n0, nchunks = (klen + KC - 1) / KC;
 
   CLK(0);
   /* the first S chunks go out before anything else: the copies fly while tensor memory is allocated and the barriers are set up */
   for (int c = 0; c < S; c++) {
     if (c < nchunks) {
-      load_tile(sbase + c * stage_bytes, A + (long long)(c * KC) * g.a_cs, g.a_rs, g.a_cs, BM, mvalid, klen - c * KC, a16);
-      load_tile(sbase + c * stage_bytes + A_BYTES, B + (long long)(c * KC) * g.b_ks, g.b_ns, g.b_ks, g.n_tile, nvalid, klen - c * KC, b16);
+      load_tile(sbase + c * stage_bytes, a_at(kbeg + c * KC), g.a_rs, g.a_cs, BM, mvalid, klen - c * KC, a16);
+      load_tile(sbase + c * stage_bytes + A_BYTES, b_at(kbeg + c * KC), g.b_ns, g.b_ks, g.n_tile, nvalid, klen - c * KC, b16);
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   }
@@ -184,8 +189,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
     if (i + S < nchunks) {                                      /* refill this stage once its products have read it */
       const int k1 = (i + S) * KC;
       mbar_wait(bar0 + 8 * st, ph);
-      load_tile(sbase + st * stage_bytes, A + (long long)k1 * g.a_cs, g.a_rs, g.a_cs, BM, mvalid, klen - k1, a16);
-      load_tile(sbase + st * stage_bytes + A_BYTES, B + (long long)k1 * g.b_ks, g.b_ns, g.b_ks, g.n_tile, nvalid, klen - k1, b16);
+      load_tile(sbase + st * stage_bytes, a_at(kbeg + k1), g.a_rs, g.a_cs, BM, mvalid, klen - k1, a16);
+      load_tile(sbase + st * stage_bytes + A_BYTES, b_at(kbeg + k1), g.b_ns, g.b_ks, g.n_tile, nvalid, klen - k1, b16);
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     if (i + 1 < nchunks && ++st == S) { st = 0; ph ^= 1; }
@@ -300,8 +305,10 @@ extern "C" int rsb_gemm_timeouts(void) {
 
 extern "C" int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, const float *d_b, long b_ks, long b_ns, long b_bs, float *d_c, long c_rs,
                              long c_bs, int m, int n, int k, int batch, const float *d_bias, long bias_bs, const float *d_mask, long mask_rs, long mask_bs,
-                             int flags, int n_tile, void *stream) {
+                             int flags, int n_tile, int k_block, long a_kbs, long b_kbs, void *stream) {
   if (m < 1 || n < 1 || k < 1 || batch < 1 || !d_a || !d_b || !d_c) { rsb_sac_set_error("rsb_gemm_tf32: bad arguments"); return 1; }
+  if (k_block <= 0) { k_block = ((k + KC - 1) / KC) * KC; a_kbs = b_kbs = 0; }
+  if (k_block % KC != 0) { rsb_sac_set_error("rsb_gemm_tf32: k_block must be a multiple of 64"); return 1; }
   const int mt = (m + BM - 1) / BM;
   if (n_tile == 0) {                                  /* widest tile that still gives >= 32 CTAs; small outputs: the narrowest tile that covers n */
     n_tile = 128;
@@ -321,7 +328,7 @@ extern "C" int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, 
   g.a = d_a; g.b = d_b; g.bias = d_bias; g.mask = d_mask; g.c = d_c;
   g.a_rs = a_rs; g.a_cs = a_cs; g.a_bs = a_bs; g.b_ks = b_ks; g.b_ns = b_ns; g.b_bs = b_bs; g.c_rs = c_rs; g.c_bs = c_bs;
   g.bias_bs = bias_bs; g.mask_rs = mask_rs; g.mask_bs = mask_bs;
-  g.m = m; g.n = n; g.k = k; g.flags = flags; g.n_tile = n_tile;
+  g.m = m; g.n = n; g.k = k; g.flags = flags; g.n_tile = n_tile; g.k_block = k_block; g.a_kbs = a_kbs; g.b_kbs = b_kbs;
   g.lbo16 = g_swap_offsets ? (2048 >> 4) : (128 >> 4);
   g.sbo16 = g_swap_offsets ? (128 >> 4) : (2048 >> 4);
   /* split the contraction over a cluster of 2 or 4 CTAs while the launch still fits one wave: at the update's sizes the time of a product is

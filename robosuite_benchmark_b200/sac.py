@@ -329,7 +329,7 @@ class SACTrainer:
         self._graphs = {}
         # side streams: the target-Q forward and the weight-gradient GEMMs do not lie on the update's dependency chain; inside the captured
         # graph they become parallel branches (the update is launch-latency bound: ~55 kernels of 2-4 us each)
-        self._sT, self._sW = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        self._sT, self._sW, self._sB = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
         self.parallel_branches = bool(parallel_branches)          # False: everything on one stream (the reference order; tests compare the two)
 
     # -- buffers
@@ -413,7 +413,7 @@ class SACTrainer:
         # twin Q forward (batched over the two networks) on [(obs,a_new); (obs,act)]; target twin Q on (next_obs, a') on a side stream
         XQ2, XT2 = self.XQ.unsqueeze(0).expand(2, 2 * B, QI), self.XT.unsqueeze(0).expand(2, B, QI)
         main = t.cuda.current_stream(self.device)
-        sT, sW = (self._sT, self._sW) if self.parallel_branches else (main, main)
+        sT, sW, sB = (self._sT, self._sW, self._sB) if self.parallel_branches else (main, main, main)
         sT.wait_stream(main)
         with t.cuda.stream(sT):
             mm(XT2, T["q_W0"], self.H1t, bias=T["q_b0"], relu=True)
@@ -431,25 +431,30 @@ class SACTrainer:
         # chain (dq -> dH2q -> dH1q -> gX -> policy head -> dH2p -> dH1p) runs on the main stream; every weight/bias gradient only needs the
         # activation gradient of its own layer and goes to the side stream as soon as that exists.  `mask=` is the ReLU backward of the
         # layer that produced the mask tensor, fused into the product's epilogue.
-        def weight_grads(fn):
-            sW.wait_stream(main)
+        def weight_grads(product, bias_sum):      # the weight-gradient product and the bias column sum of one layer: a side stream each
+            sW.wait_stream(main); sB.wait_stream(main)
             with t.cuda.stream(sW):
-                fn()
-        weight_grads(lambda: (mm(self.H2q[:, B:].transpose(1, 2), self.dq[:, B:], G["q_W2"]), self._colsum(self.dq, B, 2 * B, G["q_b2"], 2)))
+                product()
+            with t.cuda.stream(sB):
+                bias_sum()
+        weight_grads(lambda: mm(self.H2q[:, B:].transpose(1, 2), self.dq[:, B:], G["q_W2"]), lambda: self._colsum(self.dq, B, 2 * B, G["q_b2"], 2))
         mm(self.dq, P["q_W2"].transpose(1, 2), self.dH2q, mask=self.H2q)
-        weight_grads(lambda: (mm(self.H1q[:, B:].transpose(1, 2), self.dH2q[:, B:], G["q_W1"]), self._colsum(self.dH2q, B, 2 * B, G["q_b1"], 2)))
+        weight_grads(lambda: mm(self.H1q[:, B:].transpose(1, 2), self.dH2q[:, B:], G["q_W1"]), lambda: self._colsum(self.dH2q, B, 2 * B, G["q_b1"], 2))
         mm(self.dH2q, P["q_W1"].transpose(1, 2), self.dH1q, mask=self.H1q)
-        weight_grads(lambda: (mm(XQ2[:, B:].transpose(1, 2), self.dH1q[:, B:], G["q_W0"]), self._colsum(self.dH1q, B, 2 * B, G["q_b0"], 2)))
-        mm(self.dH1q[0, :B], P["q_W0"][0].t(), self.gX); mm(self.dH1q[1, :B], P["q_W0"][1].t(), self.gX, accumulate=True)
+        weight_grads(lambda: mm(XQ2[:, B:].transpose(1, 2), self.dH1q[:, B:], G["q_W0"]), lambda: self._colsum(self.dH1q, B, 2 * B, G["q_b0"], 2))
+        if self.gemm == "tcgen05":       # dX = dH_1 W_1^T + dH_2 W_2^T as ONE product: the two networks' blocks side by side along the contraction
+            gemm_tf32(self.dH1q[:, :B], P["q_W0"].transpose(1, 2), self.gX, stack_k=True)
+        else:
+            mm(self.dH1q[0, :B], P["q_W0"][0].t(), self.gX); mm(self.dH1q[1, :B], P["q_W0"][1].t(), self.gX, accumulate=True)
         # policy backward
         _chk(L.rsb_head_bwd(_ptr(self.OUT), _ptr(self.eps), _ptr(self.a_store), 2 * B, B, A, _ptr(self.alpha),
                             C.c_void_p(self.gX.data_ptr() + 4 * O), QI, _ptr(self.dOUT), _stream(self.device)))
-        weight_grads(lambda: (mm(self.H2p[:B].t(), self.dOUT[:B], G["p_W2"]), self._colsum(self.dOUT, 0, B, G["p_b2"])))
+        weight_grads(lambda: mm(self.H2p[:B].t(), self.dOUT[:B], G["p_W2"]), lambda: self._colsum(self.dOUT, 0, B, G["p_b2"]))
         mm(self.dOUT[:B], P["p_W2"].t(), self.dH2p, mask=self.H2p[:B])
-        weight_grads(lambda: (mm(self.H1p[:B].t(), self.dH2p, G["p_W1"]), self._colsum(self.dH2p, 0, B, G["p_b1"])))
+        weight_grads(lambda: mm(self.H1p[:B].t(), self.dH2p, G["p_W1"]), lambda: self._colsum(self.dH2p, 0, B, G["p_b1"]))
         mm(self.dH2p, P["p_W1"].t(), self.dH1p, mask=self.H1p[:B])
-        weight_grads(lambda: (mm(self.Xp[:B].t(), self.dH1p, G["p_W0"]), self._colsum(self.dH1p, 0, B, G["p_b0"])))
-        main.wait_stream(sW)
+        weight_grads(lambda: mm(self.Xp[:B].t(), self.dH1p, G["p_W0"]), lambda: self._colsum(self.dH1p, 0, B, G["p_b0"]))
+        main.wait_stream(sW); main.wait_stream(sB)
 
     def _apply(self, do_soft):
         s = self.store

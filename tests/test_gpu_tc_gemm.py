@@ -50,3 +50,17 @@ def test_tcgen05_gemm_is_deterministic_and_graph_capturable(dev):
     torch.cuda.synchronize()
     assert torch.equal(o1, o2)
     assert gemm.timeouts() == 0
+
+
+def test_contraction_over_strided_blocks_equals_the_sum_of_products(dev):
+    """stack_k: dX = dH_1 W_1^T + dH_2 W_2^T (the twin Q networks' input gradient) as one product over K = 2 x 256."""
+    import torch
+    from robosuite_benchmark_b200 import gemm
+    dH = torch.randn(2, 256, 256, device=dev)                     # [net, 2B, H]; the product reads rows [0, B)
+    W = torch.randn(2, 49, 256, device=dev)                       # [net, in, H]
+    out = torch.empty(128, 49, device=dev)
+    gemm.gemm_tf32(dH[:, :128], W.transpose(1, 2), out, stack_k=True)
+    ref = sum(dH[i, :128].double() @ W[i].double().t() for i in range(2))
+    bound = sum(dH[i, :128].abs().double() @ W[i].abs().double().t() for i in range(2))
+    assert gemm.timeouts() == 0
+    assert ((out.double() - ref).abs() / (bound + 1e-3)).max().item() < 3e-3
