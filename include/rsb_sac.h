@@ -6,7 +6,7 @@
  *   TanhGaussianPolicy.forward / TanhNormal.rsample   -> rsb_normal + rsb_head_fwd / rsb_head_bwd
  *   SACTrainer.train_from_torch (losses)              -> rsb_sac_losses
  *   torch.optim.Adam x4 + soft_update_from_to         -> rsb_adam_polyak
- * The dense GEMMs between these calls are issued by the host through cuBLAS.  All pointers are DEVICE pointers, `stream` is a
+ * The dense products between these calls are rsb_gemm_tf32 (include/rsb_gemm.h: tcgen05 TF32, bias / ReLU / ReLU-backward fused).  All pointers are DEVICE pointers, `stream` is a
  * cudaStream_t as void*; every call is stream-ordered, non-blocking and CUDA-graph capturable.  Returns 0 or an error code.
  */
 #ifndef RSB_SAC_H

@@ -2,8 +2,8 @@
  * rsb_sac.cu -- replay sampling/gather and the non-GEMM parts of the rlkit SAC update as sm_100a kernels (C-ABI: include/rsb_sac.h).
  *
  * Stands behind rlkit's EnvReplayBuffer.random_batch and SACTrainer.train_from_torch (reference call sites
- * util/rlkit_custom.py:235-238).  The dense GEMMs of the five 256x256 MLPs are issued by the host through
- * cuBLAS (tensor cores, TF32/FP32-accumulate); everything between them is fused here: Philox index draw + row gather,
+ * util/rlkit_custom.py:235-238).  The dense products of the five 256x256 MLPs run in rsb_tc_gemm.cu (tcgen05 TF32,
+ * FP32 accumulate in tensor memory, bias / ReLU / ReLU-backward in its epilogue); everything between them is fused here: Philox index draw + row gather,
  * tanh-Gaussian sampling / log-prob and its backward, TD targets and loss gradients, bias+ReLU, and ONE Adam + Polyak
  * kernel over the flat parameter buffer.  All calls are stream-ordered and capturable in a CUDA graph (no syncs, no allocs).
  */

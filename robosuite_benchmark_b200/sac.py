@@ -4,8 +4,9 @@ re-built on the CUDA library: `EnvReplayBuffer` (HBM-resident ring, Philox-index
 
 All trainable parameters live in ONE flat fp32 buffer  [policy | Q1,Q2 (stacked per layer) | log_alpha]  with a matching flat
 gradient buffer, so that (a) the twin Q networks run as batched GEMMs, (b) one kernel does the four Adam steps and the
-Polyak update, (c) data-parallel training all-reduces a single bucket.  Dense GEMMs go through cuBLAS (torch.mm / bmm with
-`out=`); everything else is the fused kernels of csrc/rsb_sac.cu.  One whole update is captured in a CUDA graph.
+Polyak update, (c) data-parallel training all-reduces a single bucket.  The dense products run on the hand-written tcgen05 TF32 kernel
+(csrc/rsb_tc_gemm.cu via gemm.gemm_tf32, bias / ReLU / ReLU-backward in its epilogue; `gemm="cublas"` keeps torch.mm / bmm as the
+comparison arm and as the fp32 strict-parity mode); everything else is the fused kernels of csrc/rsb_sac.cu.  One whole update is captured in a CUDA graph.
 There is no CPU path: constructing any of these without a CUDA device raises.
 """
 from __future__ import annotations
