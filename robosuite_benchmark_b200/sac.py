@@ -484,23 +484,35 @@ class SACTrainer:
                 self.eps.copy_(t.as_tensor(eps, dtype=t.float32, device=self.device).reshape(self.eps.shape))
             if self.use_graph and batch is None and eps is None:
                 # the replay `size` argument is baked into a captured launch: sampling stays outside the graphs
-                key = "noise+body"
-                if key not in self._graphs:
-                    self._warm(lambda: self._update_body(step, do_soft, False))
-                    g = t.cuda.CUDAGraph()
-                    with t.cuda.graph(g):
-                        self._update_body(0, do_soft, True)            # noise generated outside (its counter changes per step)
-                    ga, gb = t.cuda.CUDAGraph(), t.cuda.CUDAGraph()
-                    with t.cuda.graph(ga):
-                        self._apply(True)
-                    with t.cuda.graph(gb):
-                        self._apply(False)
-                    self._graphs[key] = (g, ga, gb)
-                g, ga, gb = self._graphs[key]
                 _chk(self.L.rsb_normal(C.c_uint64(self.seed), C.c_uint64(step), 7, self.eps.numel(), _ptr(self.eps), _stream(self.device)))
-                g.replay()
-                self._allreduce()
-                (ga if do_soft else gb).replay()
+                if self.world == 1:
+                    # no collective between the gradients and the optimizer: body + Adam/Polyak are ONE graph per Polyak flavour
+                    key = ("update", do_soft)
+                    if key not in self._graphs:
+                        self._warm(lambda: self._update_body(step, do_soft, True))
+                        g = t.cuda.CUDAGraph()
+                        with t.cuda.graph(g):
+                            self._update_body(0, do_soft, True)        # noise generated outside (its counter changes per step)
+                            self._apply(do_soft)
+                        self._graphs[key] = g
+                    self._graphs[key].replay()
+                else:
+                    key = "noise+body"
+                    if key not in self._graphs:
+                        self._warm(lambda: self._update_body(step, do_soft, True))
+                        g = t.cuda.CUDAGraph()
+                        with t.cuda.graph(g):
+                            self._update_body(0, do_soft, True)
+                        ga, gb = t.cuda.CUDAGraph(), t.cuda.CUDAGraph()
+                        with t.cuda.graph(ga):
+                            self._apply(True)
+                        with t.cuda.graph(gb):
+                            self._apply(False)
+                        self._graphs[key] = (g, ga, gb)
+                    g, ga, gb = self._graphs[key]
+                    g.replay()
+                    self._allreduce()
+                    (ga if do_soft else gb).replay()
             else:
                 self._update_body(step, do_soft, eps is not None)
                 self._allreduce()
