@@ -26,6 +26,9 @@ extern "C" {
 int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, const float *d_b, long b_ks, long b_ns, long b_bs, float *d_c, long c_rs, long c_bs,
                   int m, int n, int k, int batch, const float *d_bias, long bias_bs, const float *d_mask, long mask_rs, long mask_bs, int flags, int n_tile,
                   int k_block, long a_kbs, long b_kbs, void *stream);
+/* launch geometry rsb_gemm_tf32 would use (host arithmetic only, no device needed): plan[8] = {n_tile, splits (CTAs of a cluster sharing a tile along K),
+   64-wide chunks per split, pipeline stages, byte offset of the split-K receive panels, dynamic shared memory bytes, grid.x, total CTAs} */
+int rsb_gemm_plan(int m, int n, int k, int batch, int n_tile, int force_splits, int *plan);
 /* device-side watchdog: number of mbarrier waits that gave up since the last call (0 on a healthy run); synchronises the device */
 int rsb_gemm_timeouts(void);
 /* diagnostic: exchange the two byte-offset fields of the shared-memory matrix descriptors (0 = as documented in csrc/rsb_tc_gemm.cu) */

@@ -83,7 +83,7 @@ EXPORTS = ["rsb_last_error", "rsb_sizeof_model", "rsb_sizeof_task", "rsb_create"
            "rsb_step", "rsb_step_host", "rsb_reset_host", "rsb_random_actions", "rsb_get_state", "rsb_set_state",
            "rsb_debug_substep", "rsb_sac_last_error", "rsb_sac_prepare", "rsb_replay_sample", "rsb_normal", "rsb_bias_relu", "rsb_relu_bwd",
            "rsb_colsum", "rsb_head_fwd", "rsb_head_bwd", "rsb_sac_losses", "rsb_adam_polyak", "rsb_gemm_tf32", "rsb_gemm_timeouts",
-           "rsb_gemm_debug_swap_offsets", "rsb_gemm_debug_clocks", "rsb_gemm_debug_splits"]
+           "rsb_gemm_debug_swap_offsets", "rsb_gemm_debug_clocks", "rsb_gemm_debug_splits", "rsb_gemm_plan"]
 
 
 class RsbError(RuntimeError):

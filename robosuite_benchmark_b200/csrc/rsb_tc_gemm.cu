@@ -303,12 +303,10 @@ extern "C" int rsb_gemm_timeouts(void) {
   return (int)h;
 }
 
-extern "C" int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, const float *d_b, long b_ks, long b_ns, long b_bs, float *d_c, long c_rs,
-                             long c_bs, int m, int n, int k, int batch, const float *d_bias, long bias_bs, const float *d_mask, long mask_rs, long mask_bs,
-                             int flags, int n_tile, int k_block, long a_kbs, long b_kbs, void *stream) {
-  if (m < 1 || n < 1 || k < 1 || batch < 1 || !d_a || !d_b || !d_c) { rsb_sac_set_error("rsb_gemm_tf32: bad arguments"); return 1; }
-  if (k_block <= 0) { k_block = ((k + KC - 1) / KC) * KC; a_kbs = b_kbs = 0; }
-  if (k_block % KC != 0) { rsb_sac_set_error("rsb_gemm_tf32: k_block must be a multiple of 64"); return 1; }
+/* launch geometry of one product (pure host arithmetic; tests/test_abi.py checks its invariants without a GPU).
+   plan = {n_tile, splits, chunks per split, stages, byte offset of the receive panels behind the stages, dynamic shared memory, grid.x, CTAs} */
+extern "C" int rsb_gemm_plan(int m, int n, int k, int batch, int n_tile, int force_splits, int *plan) {
+  if (m < 1 || n < 1 || k < 1 || batch < 1 || !plan) { rsb_sac_set_error("rsb_gemm_plan: bad arguments"); return 1; }
   const int mt = (m + BM - 1) / BM;
   if (n_tile == 0) {                                  /* widest tile that still gives >= 32 CTAs; small outputs: the narrowest tile that covers n */
     n_tile = 128;
@@ -316,6 +314,40 @@ extern "C" int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, 
     while (n_tile > 16 && (n_tile >> 1) >= n) n_tile >>= 1;
   }
   if (n_tile != 16 && n_tile != 32 && n_tile != 64 && n_tile != 128) { rsb_sac_set_error("rsb_gemm_tf32: n_tile must be 16, 32, 64 or 128"); return 1; }
+  /* split the contraction over a cluster of 2 or 4 CTAs while the launch still fits one wave: at the update's sizes the time of a product is
+     the time one SM needs to pull its operands in, so more SMs with less each is what helps */
+  const int ctas = ((n + n_tile - 1) / n_tile) * mt * batch, nchunks_all = (k + KC - 1) / KC;
+  int splits = force_splits;
+  static int max_ctas = 0;                                       /* developer knob RSB_GEMM_MAX_CTAS: CTAs one product may occupy */
+  if (max_ctas == 0) { const char *ev = getenv("RSB_GEMM_MAX_CTAS"); max_ctas = ev ? atoi(ev) : 148; if (max_ctas < 1) max_ctas = 148; }
+  if (splits == 0) { splits = 4; while (splits > 1 && (splits > nchunks_all || ctas * splits > max_ctas)) splits >>= 1; }
+  if (splits != 1 && splits != 2 && splits != 4) { rsb_sac_set_error("rsb_gemm_tf32: splits must be 1, 2 or 4"); return 1; }
+  int cps = (nchunks_all + splits - 1) / splits;
+  while (splits > 1 && (splits - 1) * cps >= nchunks_all) { splits >>= 1; cps = (nchunks_all + splits - 1) / splits; }   /* no empty slice */
+  /* shared memory: the stages this launch can fill (4 x (32 KB + n_tile x 256 B); 3 at n_tile = 128, 2 if that tile is also split) and, with
+     split-K, the receive panels behind them; without split-K the single panel lies over the stages */
+  int stages = (n_tile == 128) ? (splits > 1 ? 2 : 3) : 4;
+  if (cps < stages) stages = cps;
+  const size_t stage_bytes = A_BYTES + (size_t)n_tile * KC * 4, panels = (size_t)splits * BM * (n_tile / splits + 4) * 4;
+  while (stages > 1 && CTRL_BYTES + (size_t)stages * stage_bytes + (splits > 1 ? panels : 0) > SMEM_MAX) stages--;
+  size_t smem_bytes = CTRL_BYTES + (size_t)stages * stage_bytes + (splits > 1 ? panels : 0);
+  if (smem_bytes < CTRL_BYTES + panels) smem_bytes = CTRL_BYTES + panels;
+  if (smem_bytes > SMEM_MAX) { rsb_sac_set_error("rsb_gemm_plan: shared memory"); return 1; }
+  plan[0] = n_tile; plan[1] = splits; plan[2] = cps; plan[3] = stages; plan[4] = (int)((size_t)stages * stage_bytes); plan[5] = (int)smem_bytes;
+  plan[6] = ((n + n_tile - 1) / n_tile) * splits; plan[7] = ctas * splits;
+  return 0;
+}
+
+extern "C" int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, const float *d_b, long b_ks, long b_ns, long b_bs, float *d_c, long c_rs,
+                             long c_bs, int m, int n, int k, int batch, const float *d_bias, long bias_bs, const float *d_mask, long mask_rs, long mask_bs,
+                             int flags, int n_tile, int k_block, long a_kbs, long b_kbs, void *stream) {
+  if (m < 1 || n < 1 || k < 1 || batch < 1 || !d_a || !d_b || !d_c) { rsb_sac_set_error("rsb_gemm_tf32: bad arguments"); return 1; }
+  if (k_block <= 0) { k_block = ((k + KC - 1) / KC) * KC; a_kbs = b_kbs = 0; }
+  if (k_block % KC != 0) { rsb_sac_set_error("rsb_gemm_tf32: k_block must be a multiple of 64"); return 1; }
+  int plan[8];
+  if (rsb_gemm_plan(m, n, k, batch, n_tile, g_force_splits, plan) != 0) return 1;
+  n_tile = plan[0];
+  const int splits = plan[1];
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -331,27 +363,9 @@ extern "C" int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, 
   g.m = m; g.n = n; g.k = k; g.flags = flags; g.n_tile = n_tile; g.k_block = k_block; g.a_kbs = a_kbs; g.b_kbs = b_kbs;
   g.lbo16 = g_swap_offsets ? (2048 >> 4) : (128 >> 4);
   g.sbo16 = g_swap_offsets ? (128 >> 4) : (2048 >> 4);
-  /* split the contraction over a cluster of 2 or 4 CTAs while the launch still fits one wave: at the update's sizes the time of a product is
-     the time one SM needs to pull its operands in, so more SMs with less each is what helps */
-  const int ctas = ((n + n_tile - 1) / n_tile) * mt * batch, nchunks_all = (k + KC - 1) / KC;
-  int splits = g_force_splits;
-  static int max_ctas = 0;                                       /* developer knob RSB_GEMM_MAX_CTAS: CTAs one product may occupy */
-  if (max_ctas == 0) { const char *ev = getenv("RSB_GEMM_MAX_CTAS"); max_ctas = ev ? atoi(ev) : 148; if (max_ctas < 1) max_ctas = 148; }
-  if (splits == 0) { splits = 4; while (splits > 1 && (splits > nchunks_all || ctas * splits > max_ctas)) splits >>= 1; }
-  if (splits != 1 && splits != 2 && splits != 4) { rsb_sac_set_error("rsb_gemm_tf32: splits must be 1, 2 or 4"); return 1; }
-  int cps = (nchunks_all + splits - 1) / splits;
-  while (splits > 1 && (splits - 1) * cps >= nchunks_all) { splits >>= 1; cps = (nchunks_all + splits - 1) / splits; }   /* no empty slice */
-  g.splits = splits; g.cps = cps;
-  dim3 grid(((n + n_tile - 1) / n_tile) * splits, mt, batch);
-  /* shared memory: the stages this launch can fill (4 x (32 KB + n_tile x 256 B); 3 at n_tile = 128, 2 if that tile is also split) and, with
-     split-K, the receive panels behind them; without split-K the single panel lies over the stages */
-  int stages = (n_tile == 128) ? (splits > 1 ? 2 : 3) : 4;
-  if (cps < stages) stages = cps;
-  const size_t panels = (size_t)splits * BM * (n_tile / splits + 4) * 4;
-  while (stages > 1 && CTRL_BYTES + (size_t)stages * (A_BYTES + (size_t)n_tile * KC * 4) + (splits > 1 ? panels : 0) > SMEM_MAX) stages--;
-  g.stages = stages; g.recv_off = (int)((size_t)stages * (A_BYTES + (size_t)n_tile * KC * 4));
-  size_t smem_bytes = CTRL_BYTES + (size_t)g.recv_off + (splits > 1 ? panels : 0);
-  if (smem_bytes < CTRL_BYTES + panels) smem_bytes = CTRL_BYTES + panels;
+  g.splits = splits; g.cps = plan[2]; g.stages = plan[3]; g.recv_off = plan[4];
+  const size_t smem_bytes = (size_t)plan[5];
+  dim3 grid(plan[6], (m + BM - 1) / BM, batch);
   if (splits == 1) {
     k_gemm_tf32<<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(g);
     e = cudaGetLastError();
