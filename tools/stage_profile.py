@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 from robosuite_benchmark_b200 import backend
 PROF = os.path.join(os.path.dirname(backend.LIB_PATH), "librsb_cuda_prof.so")
 def build():
-    srcs = [os.path.join(os.path.dirname(backend.LIB_PATH), f) for f in ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_sac.cu")]
+    srcs = [os.path.join(os.path.dirname(backend.LIB_PATH), f) for f in ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_sac.cu", "rsb_tc_gemm.cu")]
     if not os.path.exists(PROF) or os.path.getmtime(PROF) < max(os.path.getmtime(s) for s in backend.sources()):
         subprocess.check_call(["nvcc"] + backend.NVCC_FLAGS + ["-DRSB_PROFILE", "-o", PROF] + srcs)
 if len(sys.argv) > 1 and sys.argv[1] == "build":
