@@ -33,6 +33,24 @@ int rsb_sac_losses(const float *d_q, const float *d_qt, const float *d_logpi, co
                    float target_entropy, int batch, float *d_dq, float *d_y, float *d_sums, float *d_galpha, void *stream);
 int rsb_adam_polyak(float *d_p, const float *d_g, float *d_m, float *d_v, long n, double lr_pi, double lr_q, float b1, float b2, float eps, double *d_bc /* [4] = {0,0,1,1} at start */,
                     float *d_tgt, long tgt_begin, long tgt_end, float tau, int do_soft, float *d_alpha, long log_alpha_idx, void *stream);
+
+/* ---- collector (csrc/rsb_collect.cu): what rlkit's MdpPathCollector.collect_new_paths does per control step and per epoch
+   (util/rlkit_custom.py:202,215,223 -> rollout -> TanhGaussianPolicy.get_action; statistics: util/rlkit_custom.py:244-301,315-377) */
+
+/* TanhGaussianPolicy.get_action for n environments in one launch (MakeDeterministic when deterministic != 0):
+   obs row i = d_obs + row_i * obs_ld, action row i = d_act + row_i * act_ld with row_i = i (cap == 0) or (slot0 + i) mod cap (the replay
+   ring's observations / actions arrays: rsb_step_ring then reads the action where this call put it).  Weights [in, out] row-major,
+   hidden must be 256.  a = tanh(mean + exp(clamp(log_std, -20, 2)) eps); eps = Box-Muller of Philox4x32-10(key = seed,
+   counter = (env_id_base + i [64 bit], 2, step * 8 + d / 4)): four action dims per Philox block, independent of the sharding. */
+int rsb_policy_act(const float *d_W0, const float *d_b0, const float *d_W1, const float *d_b1, const float *d_W2, const float *d_b2,
+                   int obs_dim, int act_dim, int hidden, const float *d_obs, long obs_ld, float *d_act, long act_ld, int64_t slot0, int64_t cap, int n,
+                   int deterministic, uint64_t seed, uint64_t env_id_base, uint64_t step, void *stream);
+
+/* eval_util.get_generic_path_information / get_custom_generic_path_information reduced on the device from the ring segment a collection
+   round wrote (transition (env i, step t) at row (slot0 + t n + i) mod cap).  d_out holds rsb_path_stats_words(n) doubles; the first 16 are
+   {sum, sum of squares, max, min} of: rewards (all T n), path returns (n), returns over the first expl_len steps (n), action entries (T n A). */
+int rsb_path_stats_words(int n);
+int rsb_path_stats(const float *d_rewards, const float *d_actions, int64_t slot0, int64_t cap, int n, int T, int act_dim, int expl_len, double *d_out, void *stream);
 #ifdef __cplusplus
 }
 #endif

@@ -29,12 +29,87 @@ def replay_indices(seed, step, batch, size):
     return out
 
 
+def policy_noise(seed, env_ids, step, act_dim):
+    """The collector's exploration noise restated on the host (csrc/rsb_collect.cu k_policy_act): for env id e and action dims 4 blk .. 4 blk + 3,
+    Philox4x32-10(key = seed, counter = (e_lo, e_hi, 2, step * 8 + blk)) -> two Box-Muller pairs (arguments in double, result cast to fp32)."""
+    from robosuite_benchmark_b200.philox import philox4x32
+    out = np.zeros((len(env_ids), act_dim), np.float32)
+    key = [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF]
+    for i, e in enumerate(env_ids):
+        e = int(e)
+        for blk in range((act_dim + 3) // 4):
+            w = philox4x32([e & 0xFFFFFFFF, (e >> 32) & 0xFFFFFFFF, 2, (step * 8 + blk) & 0xFFFFFFFF], key)
+            z = []
+            for a, b in ((w[0], w[1]), (w[2], w[3])):
+                u1, u2 = (a + 0.5) / 4294967296.0, (b + 0.5) / 4294967296.0
+                rad, ang = np.sqrt(-2.0 * np.log(u1)), 2.0 * np.pi * u2
+                z += [rad * np.cos(ang), rad * np.sin(ang)]
+            for k in range(4):
+                if 4 * blk + k < act_dim:
+                    out[i, 4 * blk + k] = np.float32(z[k])
+    return out
+
+
+def policy_act(params, obs, seed=0, env_ids=None, step=0, deterministic=False):
+    """rlkit TanhGaussianPolicy.get_action for a batch of observations in fp64 numpy (weights [in, out] as in the ParamStore): the checker of
+    k_policy_act.  a = tanh(mean) (MakeDeterministic) or tanh(mean + exp(clamp(log_std, -20, 2)) * eps) with eps = policy_noise(...)."""
+    g = lambda k: np.asarray(params[k], np.float64)
+    x = np.asarray(obs, np.float64)
+    h = np.maximum(x @ g("p_W0") + g("p_b0"), 0.0)
+    h = np.maximum(h @ g("p_W1") + g("p_b1"), 0.0)
+    out = h @ g("p_W2") + g("p_b2")
+    A = out.shape[1] // 2
+    mean, log_std = out[:, :A], np.clip(out[:, A:], LOG_SIG_MIN, LOG_SIG_MAX)
+    if deterministic:
+        return np.tanh(mean)
+    env_ids = np.arange(len(x)) if env_ids is None else env_ids
+    return np.tanh(mean + np.exp(log_std) * policy_noise(seed, env_ids, step, A).astype(np.float64))
+
+
+def tf32_operand(x, mode):
+    """fp32 -> the value a TF32 tensor-core product uses for this operand: sign, 8 exponent bits, 10 mantissa bits.
+    "trunc": the low 13 mantissa bits are dropped (what `tcgen05.mma.kind::tf32` does with raw fp32 operands in shared memory);
+    "rna": round to nearest, ties away from zero (`cvt.rna.tf32.f32`, what cuBLAS applies before `mma.sync`)."""
+    i = x.detach().contiguous().view(torch.int32)
+    if mode == "rna":
+        i = i + 0x1000
+    elif mode != "trunc":
+        raise ValueError(mode)
+    return (i & ~0x1FFF).view(torch.float32)
+
+
+class _TF32MatMul(torch.autograd.Function):
+    """a @ b as the product path computes it: BOTH operands of EVERY product (forward, input gradient, weight gradient) are reduced to
+    TF32, products and sums are exact (fp64 here; fp32 accumulation on the device)."""
+
+    @staticmethod
+    def forward(ctx, a, b, mode):
+        ctx.save_for_backward(a, b)
+        ctx.mode = mode
+        return (tf32_operand(a, mode).double() @ tf32_operand(b, mode).double()).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        m = ctx.mode
+        gt = tf32_operand(g, m).double()
+        ga = (gt @ tf32_operand(b, m).double().transpose(-1, -2)).float()
+        gb = (tf32_operand(a, m).double().transpose(-1, -2) @ gt).float()
+        while gb.dim() > b.dim():
+            gb = gb.sum(0)
+        while ga.dim() > a.dim():
+            ga = ga.sum(0)
+        return ga, gb, None
+
+
 class SacOracle:
     """Parameters in the store's host layout (weights as [in, out]; twin Q stacked on a leading axis of 2)."""
 
     def __init__(self, params, targets, obs_dim, act_dim, discount=0.99, reward_scale=1.0, policy_lr=1e-3, qf_lr=1e-3,
-                 soft_target_tau=1e-2, target_update_period=1, target_entropy=None):
-        self.O, self.A = obs_dim, act_dim
+                 soft_target_tau=1e-2, target_update_period=1, target_entropy=None, tf32=None):
+        """tf32: None = plain fp32 products (rlkit on a CPU); "trunc" / "rna" = every product with TF32 operands (tf32_operand), the
+        arithmetic of the tensor-core product path -- used to hold that path to a tight tolerance instead of the loose TF32 error bound."""
+        self.O, self.A, self.tf32 = obs_dim, act_dim, tf32
         self.p = {k: torch.tensor(np.asarray(v, np.float32), requires_grad=True) for k, v in params.items()}
         self.t = {k: torch.tensor(np.asarray(v, np.float32)) for k, v in targets.items()}
         self.discount, self.reward_scale, self.tau, self.period = discount, reward_scale, soft_target_tau, target_update_period
@@ -46,21 +121,25 @@ class SacOracle:
         self.opt_alpha = torch.optim.Adam([self.p["log_alpha"]], lr=policy_lr)
         self.n_steps, self.stats = 0, {}
 
+    def mm(self, a, b):
+        if self.tf32 is None:
+            return a @ b
+        return _TF32MatMul.apply(a, b, self.tf32)
+
     def policy(self, obs, eps):
-        p, A = self.p, self.A
-        h = F.relu(obs @ p["p_W0"] + p["p_b0"]); h = F.relu(h @ p["p_W1"] + p["p_b1"]); out = h @ p["p_W2"] + p["p_b2"]
+        p, A, mm = self.p, self.A, self.mm
+        h = F.relu(mm(obs, p["p_W0"]) + p["p_b0"]); h = F.relu(mm(h, p["p_W1"]) + p["p_b1"]); out = mm(h, p["p_W2"]) + p["p_b2"]
         mean, log_std = out[:, :A], out[:, A:].clamp(LOG_SIG_MIN, LOG_SIG_MAX)
         z = mean + log_std.exp() * eps
         a = torch.tanh(z)
         logp = (-0.5 * eps ** 2 - log_std - 0.5 * np.log(2 * np.pi) - torch.log(1 - a * a + 1e-6)).sum(1, keepdim=True)
         return a, logp, mean, log_std
 
-    @staticmethod
-    def qpair(w, obs, act):
+    def qpair(self, w, obs, act):
         x = torch.cat([obs, act], 1)
-        h = F.relu(torch.einsum("bi,nio->nbo", x, w["q_W0"]) + w["q_b0"][:, None, :])
-        h = F.relu(torch.bmm(h, w["q_W1"]) + w["q_b1"][:, None, :])
-        return torch.bmm(h, w["q_W2"]) + w["q_b2"][:, None, :]                     # [2, B, 1]
+        h = F.relu(self.mm(x.unsqueeze(0).expand(2, -1, -1), w["q_W0"]) + w["q_b0"][:, None, :])
+        h = F.relu(self.mm(h, w["q_W1"]) + w["q_b1"][:, None, :])
+        return self.mm(h, w["q_W2"]) + w["q_b2"][:, None, :]                       # [2, B, 1]
 
     def train(self, batch, eps):
         """batch: dict of numpy arrays (rlkit keys); eps: [2B, A] -- rows [0,B) drive pi(obs), rows [B,2B) drive pi(next_obs)."""

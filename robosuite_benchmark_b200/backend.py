@@ -18,14 +18,16 @@ _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_CSRC, "librsb_cuda.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
+CU_SOURCES = ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_sac.cu", "rsb_collect.cu", "rsb_tc_gemm.cu")
 _LIB = None
 
 INFO = dict(nenvs=0, obs_dim=1, act_dim=2, state_words=3, smem_bytes=4, dbg_words=5, nq=6, nv=7, envs_per_block=8,
-            launches=9, ncon_max=10, nefc_max=11, regs_step=12, blocks_per_sm=13, lanes=14)
+            launches=9, ncon_max=10, nefc_max=11, regs_step=12, blocks_per_sm=13, lanes=14,
+            ncon_overflow=15, nefc_overflow=16, steps_after_done=17, solver_iterations=18, ls_iterations=19)
 
 
 def sources():
-    return [os.path.join(_CSRC, f) for f in ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_kernels.inl", "rsb_ktable.h", "rsb_sac.cu", "rsb_tc_gemm.cu", "rsb_dev.h", "rsb_devmodel.h")] + \
+    return [os.path.join(_CSRC, f) for f in ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_kernels.inl", "rsb_ktable.h", "rsb_sac.cu", "rsb_collect.cu", "rsb_tc_gemm.cu", "rsb_dev.h", "rsb_devmodel.h")] + \
            [os.path.join(_HERE, "..", "include", f) for f in ("rsb.h", "rsb_sac.h", "rsb_gemm.h", "rsb_model.h")]
 
 
@@ -33,7 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/rsb_cuda.cu for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     stale = force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in sources())
     if stale:
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + [os.path.join(_CSRC, f) for f in ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_sac.cu", "rsb_tc_gemm.cu")]
+        cmd = ["nvcc", "--threads", "0"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + [os.path.join(_CSRC, f) for f in CU_SOURCES]
         subprocess.check_call(cmd)
     return LIB_PATH
 
@@ -58,8 +60,16 @@ def lib():
         L.rsb_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rsb_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rsb_debug_substep.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.rsb_reset_ring.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.rsb_step_ring.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+        L.rsb_get_iters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rsb_get_option.argtypes = [C.c_void_p, C.c_void_p]
+        L.rsb_clear_counters.argtypes = [C.c_void_p, C.c_void_p]
         L.rsb_sac_last_error.restype = C.c_char_p
         V, I, F, U64, L_ = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_long
+        L.rsb_policy_act.argtypes = [V, V, V, V, V, V, I, I, I, V, L_, V, L_, C.c_int64, C.c_int64, I, I, U64, U64, U64, V]
+        L.rsb_path_stats_words.argtypes = [I]
+        L.rsb_path_stats.argtypes = [V, V, C.c_int64, C.c_int64, I, I, I, I, V, V]
         L.rsb_replay_sample.argtypes = [V, V, V, V, V, I, I, I, U64, U64, I, V, I, V, V, V, V, I, V, V]
         L.rsb_sac_prepare.argtypes = [V, V, V, V, V, I, V, I, I, I, V]
         L.rsb_normal.argtypes = [U64, U64, C.c_uint32, I, V, V]
@@ -81,13 +91,20 @@ def lib():
 
 EXPORTS = ["rsb_last_error", "rsb_sizeof_model", "rsb_sizeof_task", "rsb_create", "rsb_destroy", "rsb_info", "rsb_reset",
            "rsb_step", "rsb_step_host", "rsb_reset_host", "rsb_random_actions", "rsb_get_state", "rsb_set_state",
-           "rsb_debug_substep", "rsb_sac_last_error", "rsb_sac_prepare", "rsb_replay_sample", "rsb_normal", "rsb_bias_relu", "rsb_relu_bwd",
+           "rsb_debug_substep", "rsb_reset_ring", "rsb_step_ring", "rsb_get_iters", "rsb_get_option", "rsb_clear_counters",
+           "rsb_policy_act", "rsb_path_stats", "rsb_path_stats_words", "rsb_sac_last_error", "rsb_sac_prepare", "rsb_replay_sample", "rsb_normal", "rsb_bias_relu", "rsb_relu_bwd",
            "rsb_colsum", "rsb_head_fwd", "rsb_head_bwd", "rsb_sac_losses", "rsb_adam_polyak", "rsb_gemm_tf32", "rsb_gemm_timeouts",
            "rsb_gemm_debug_swap_offsets", "rsb_gemm_debug_clocks", "rsb_gemm_debug_splits", "rsb_gemm_plan"]
 
 
 class RsbError(RuntimeError):
     pass
+
+
+class RsbRing(C.Structure):
+    """include/rsb.h `rsb_ring`: the five arrays of rlkit's EnvReplayBuffer, resident in HBM."""
+    _fields_ = [("observations", C.c_void_p), ("actions", C.c_void_p), ("rewards", C.c_void_p), ("terminals", C.c_void_p),
+                ("next_obs", C.c_void_p), ("capacity", C.c_int64)]
 
 
 def _check(rc):
@@ -170,6 +187,33 @@ class BatchSim:
         _check(self.L.rsb_step(self.h, C.c_void_p(actions.data_ptr()), C.c_void_p(obs.data_ptr()), C.c_void_p(reward.data_ptr()),
                                C.c_void_p(done.data_ptr()), _stream_ptr(self.device)))
         return obs, reward, done
+
+    # -- ring mode: the env kernels read actions from / write transitions into the replay ring (include/rsb.h rsb_step_ring)
+    def reset_ring(self, ring: "RsbRing", slot0: int):
+        _check(self.L.rsb_reset_ring(self.h, C.byref(ring), C.c_int64(slot0), _stream_ptr(self.device)))
+
+    def step_ring(self, ring: "RsbRing", slot0: int, write_next_row: bool):
+        _check(self.L.rsb_step_ring(self.h, C.byref(ring), C.c_int64(slot0), int(bool(write_next_row)), _stream_ptr(self.device)))
+
+    def newton_iterations(self):
+        """Newton iterations every env spent in its last control step (uint32 device tensor stored as int32)."""
+        out = self.torch.empty(self.num_envs, dtype=self.torch.int32, device=self.device)
+        _check(self.L.rsb_get_iters(self.h, C.c_void_p(out.data_ptr()), _stream_ptr(self.device)))
+        return out
+
+    def solver_option(self):
+        """(iterations, tolerance, ls_iterations, ls_tolerance) the kernels run with: the model's <option>, as uploaded."""
+        out = (C.c_double * 4)()
+        _check(self.L.rsb_get_option(self.h, out))
+        return int(out[0]), float(out[1]), int(out[2]), float(out[3])
+
+    def counters(self):
+        """Event counters since creation / clear_counters (SYNCHRONISES): contact truncations, constraint-row truncations, steps asked of
+        terminated episodes.  Truncation is never silent: tests and bench assert the first two are 0."""
+        return dict(ncon_overflow=self.info("ncon_overflow"), nefc_overflow=self.info("nefc_overflow"), steps_after_done=self.info("steps_after_done"))
+
+    def clear_counters(self):
+        _check(self.L.rsb_clear_counters(self.h, _stream_ptr(self.device)))
 
     def step_host(self, actions: np.ndarray):
         """The reference-facing call with HOST buffers (numpy in, numpy out): H2D + step + D2H inside."""

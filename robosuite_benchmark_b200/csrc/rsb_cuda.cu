@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -32,6 +33,9 @@ struct rsb_batch {
   size_t smem_bytes = 0;
   int64_t launches = 0;
   int regs_step = 0, blocks_per_sm = 0;
+  unsigned int *d_counters = nullptr;   /* [8] event counters (DevModel::counters) */
+  unsigned int *d_iters = nullptr;      /* [n] Newton iterations of every env in its last control step */
+  cudaStream_t last_stream = nullptr; bool launched = false;   /* stream of the last launch that touched d_state (see order_after_previous) */
   /* staging for the host-buffer entry points */
   float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr; uint8_t *d_done = nullptr, *d_mask = nullptr;
   float *p_act = nullptr, *p_obs = nullptr, *p_rew = nullptr; uint8_t *p_done = nullptr;
@@ -39,6 +43,7 @@ struct rsb_batch {
 };
 
 static const rsb_batch *g_const_owner[64][2];     /* [device][lane-width variant]: which batch's model sits in constant memory */
+static std::mutex g_owner_mutex;                   /* the owner table is process-wide: bind + launch of one call are atomic against other host threads */
 #define OWNER(b) g_const_owner[(b)->device][(b)->kt->lanes == 16]
 
 /* ------------------------------------------------------------------ C-ABI */
@@ -53,7 +58,7 @@ void rsb_destroy(rsb_batch *b) {
   cudaSetDevice(b->device);
   cudaDeviceSynchronize();
   if (b->device < 64 && b->kt && OWNER(b) == b) OWNER(b) = nullptr;
-  cudaFree(b->d_arena); cudaFree(b->d_state); cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_done); cudaFree(b->d_mask);
+  cudaFree(b->d_arena); cudaFree(b->d_state); cudaFree(b->d_counters); cudaFree(b->d_iters); cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_done); cudaFree(b->d_mask);
   cudaFreeHost(b->p_act); cudaFreeHost(b->p_obs); cudaFreeHost(b->p_rew); cudaFreeHost(b->p_done);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -102,13 +107,24 @@ int rsb_create(const rsb_model *model, const rsb_task *task, int n_envs, int dev
   rsb_fixup_pointers(b->dm, b->d_arena);
   CK(cudaMalloc(&b->d_state, (size_t)n_envs * b->dm.st_words * 4));
   CK(cudaMemset(b->d_state, 0, (size_t)n_envs * b->dm.st_words * 4));
+  CK(cudaMalloc(&b->d_counters, 8 * sizeof(unsigned int))); CK(cudaMemset(b->d_counters, 0, 8 * sizeof(unsigned int)));
+  CK(cudaMalloc(&b->d_iters, (size_t)n_envs * sizeof(unsigned int))); CK(cudaMemset(b->d_iters, 0, (size_t)n_envs * sizeof(unsigned int)));
+  b->dm.counters = b->d_counters;
   CK(b->kt->prepare(b->smem_bytes, b->epb, &b->regs_step, &b->blocks_per_sm));
   CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   *out = b; return 0;
 }
 
+static int64_t read_counter(const rsb_batch *b, int k) {
+  unsigned int v = 0; cudaSetDevice(b->device);
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(&v, b->d_counters + k, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)v;
+}
+
 int64_t rsb_info(const rsb_batch *b, int what) {
   switch (what) {
+    case RSB_INFO_NCON_OVERFLOW: return read_counter(b, 0); case RSB_INFO_NEFC_OVERFLOW: return read_counter(b, 1); case RSB_INFO_STEPS_AFTER_DONE: return read_counter(b, 2);
+    case RSB_INFO_SOLVER_ITERATIONS: return b->dm.solver_iters; case RSB_INFO_LS_ITERATIONS: return b->dm.ls_iters;
     case RSB_INFO_NENVS: return b->n; case RSB_INFO_OBS_DIM: return b->dm.obs_dim; case RSB_INFO_ACT_DIM: return b->dm.act_dim;
     case RSB_INFO_STATE_WORDS: return b->dm.st_words; case RSB_INFO_SMEM_BYTES: return (int64_t)b->dm.smem_words * 4;
     case RSB_INFO_DBG_WORDS: return RSB_DBG_WORDS(b->dm.nv, b->dm.ncon_max, b->dm.nefc_max); case RSB_INFO_NQ: return b->dm.nq; case RSB_INFO_NV: return b->dm.nv;
@@ -131,25 +147,70 @@ static int bind_model(rsb_batch *b, cudaStream_t st) {
   OWNER(b) = b;
   return 0;
 }
+/* Launches of one batch are ordered by their stream.  The device-pointer entry points run on the caller's stream, the host-buffer entry
+   points on the batch's private stream; both touch the state records (and the constant-memory model), so when a call arrives on another
+   stream than the previous one, the previous stream is drained first (rare: only when the two families are mixed on one batch). */
+static int order_after_previous(rsb_batch *b, cudaStream_t st) {
+  if (b->launched && b->last_stream != st) CK(cudaStreamSynchronize(b->last_stream));
+  b->last_stream = st; b->launched = true; return 0;
+}
 
-int rsb_reset(rsb_batch *b, const uint8_t *d_mask, float *d_obs, void *stream) {
+static int launch_reset(rsb_batch *b, const uint8_t *d_mask, float *d_obs, long slot0, long cap, cudaStream_t st) {
   CK(cudaSetDevice(b->device));
-  if (bind_model(b, (cudaStream_t)stream)) return 1;
-  b->kt->reset(nblocks(b), b->epb, b->smem_bytes, (cudaStream_t)stream, b->d_state, d_mask, d_obs, b->seed, b->env_id_base, b->n);
+  std::lock_guard<std::mutex> lock(g_owner_mutex);
+  if (order_after_previous(b, st) || bind_model(b, st)) return 1;
+  b->kt->reset(nblocks(b), b->epb, b->smem_bytes, st, b->d_state, d_mask, d_obs, slot0, cap, b->seed, b->env_id_base, b->n);
+  b->launches++; CK(cudaGetLastError()); return 0;
+}
+static int launch_step(rsb_batch *b, RsbStepArgs &a, cudaStream_t st) {
+  CK(cudaSetDevice(b->device));
+  std::lock_guard<std::mutex> lock(g_owner_mutex);
+  if (order_after_previous(b, st) || bind_model(b, st)) return 1;
+  a.state = b->d_state; a.iters = b->d_iters; a.n = b->n;
+  b->kt->step(nblocks(b), b->epb, b->smem_bytes, st, &a);
   b->launches++; CK(cudaGetLastError()); return 0;
 }
 
+int rsb_reset(rsb_batch *b, const uint8_t *d_mask, float *d_obs, void *stream) { return launch_reset(b, d_mask, d_obs, 0, 0, (cudaStream_t)stream); }
+
 int rsb_step(rsb_batch *b, const float *d_actions, float *d_obs, float *d_reward, uint8_t *d_done, void *stream) {
+  RsbStepArgs a{}; a.actions = d_actions; a.obs = d_obs; a.obs2 = nullptr; a.rew = d_reward; a.done = d_done; a.slot0 = a.slot1 = a.cap = 0;
+  return launch_step(b, a, (cudaStream_t)stream);
+}
+
+static int check_ring(const rsb_batch *b, const rsb_ring *r, int64_t slot0) {
+  if (!r || !r->observations || !r->actions || !r->rewards || !r->terminals || !r->next_obs) { g_err = "ring: null array"; return 1; }
+  if (r->capacity < b->n) { g_err = "ring: capacity smaller than the env batch"; return 1; }
+  if (slot0 < 0 || slot0 >= r->capacity) { g_err = "ring: slot0 out of range"; return 1; }
+  return 0;
+}
+int rsb_reset_ring(rsb_batch *b, const rsb_ring *ring, int64_t slot0, void *stream) {
+  if (check_ring(b, ring, slot0)) return 6;
+  return launch_reset(b, nullptr, ring->observations, (long)slot0, (long)ring->capacity, (cudaStream_t)stream);
+}
+int rsb_step_ring(rsb_batch *b, const rsb_ring *ring, int64_t slot0, int write_next_row, void *stream) {
+  if (check_ring(b, ring, slot0)) return 6;
+  RsbStepArgs a{}; a.actions = ring->actions; a.obs = ring->next_obs; a.rew = ring->rewards; a.done = ring->terminals;
+  a.obs2 = write_next_row ? ring->observations : nullptr;
+  a.slot0 = (long)slot0; a.slot1 = (long)((slot0 + b->n) % ring->capacity); a.cap = (long)ring->capacity;
+  return launch_step(b, a, (cudaStream_t)stream);
+}
+int rsb_get_iters(rsb_batch *b, uint32_t *d_iters, void *stream) {
   CK(cudaSetDevice(b->device));
-  if (bind_model(b, (cudaStream_t)stream)) return 1;
-  b->kt->step(nblocks(b), b->epb, b->smem_bytes, (cudaStream_t)stream, b->d_state, d_actions, d_obs, d_reward, d_done, b->n);
-  b->launches++; CK(cudaGetLastError()); return 0;
+  CK(cudaMemcpyAsync(d_iters, b->d_iters, (size_t)b->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream)); return 0;
+}
+int rsb_get_option(const rsb_batch *b, double *out4) {
+  out4[0] = b->dm.solver_iters; out4[1] = b->dm.solver_tol; out4[2] = b->dm.ls_iters; out4[3] = b->dm.ls_tol; return 0;
+}
+int rsb_clear_counters(rsb_batch *b, void *stream) {
+  CK(cudaSetDevice(b->device)); CK(cudaMemsetAsync(b->d_counters, 0, 8 * sizeof(unsigned int), (cudaStream_t)stream)); return 0;
 }
 
 int rsb_debug_substep(rsb_batch *b, const float *d_actions, int policy_step, float *d_dbg, void *stream) {
   CK(cudaSetDevice(b->device));
   int words = RSB_DBG_WORDS(b->dm.nv, b->dm.ncon_max, b->dm.nefc_max);
-  if (bind_model(b, (cudaStream_t)stream)) return 1;
+  std::lock_guard<std::mutex> lock(g_owner_mutex);
+  if (order_after_previous(b, (cudaStream_t)stream) || bind_model(b, (cudaStream_t)stream)) return 1;
   b->kt->debug(nblocks(b), b->epb, b->smem_bytes, (cudaStream_t)stream, b->d_state, d_actions, policy_step, d_dbg, words, b->n);
   b->launches++; CK(cudaGetLastError()); return 0;
 }
@@ -161,11 +222,11 @@ int rsb_random_actions(rsb_batch *b, uint64_t step, float *d_actions, void *stre
 }
 
 int rsb_get_state(rsb_batch *b, float *d_state, void *stream) {
-  CK(cudaSetDevice(b->device));
+  CK(cudaSetDevice(b->device)); if (order_after_previous(b, (cudaStream_t)stream)) return 1;
   CK(cudaMemcpyAsync(d_state, b->d_state, (size_t)b->n * b->dm.st_words * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream)); return 0;
 }
 int rsb_set_state(rsb_batch *b, const float *d_state, void *stream) {
-  CK(cudaSetDevice(b->device));
+  CK(cudaSetDevice(b->device)); if (order_after_previous(b, (cudaStream_t)stream)) return 1;
   CK(cudaMemcpyAsync(b->d_state, d_state, (size_t)b->n * b->dm.st_words * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream)); return 0;
 }
 

@@ -61,6 +61,7 @@ RSB_D bool sany(bool p) { return p; }
 RSB_D int f2i(real f) { int i; memcpy(&i, &f, 4); return i; }
 RSB_D real i2f(int i) { real f; memcpy(&f, &i, 4); return f; }
 RSB_D uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+RSB_D void count_event(int k, unsigned int n) { if (MDL.counters) MDL.counters[k] += n; }
 #else
 #include <stdint.h>
 struct Grp { int lane; unsigned mask; };
@@ -99,6 +100,7 @@ RSB_D real rsb_rsqrt(real x) { real r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"
 RSB_D int f2i(real f) { return __float_as_int(f); }
 RSB_D real i2f(int i) { return __int_as_float(i); }
 RSB_D uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+RSB_D void count_event(int k, unsigned int n) { if (c_model.counters) atomicAdd(c_model.counters + k, n); }
 #endif
 
 #define SOFF(p) ((int)((p) - RSB_SMEM))
@@ -657,6 +659,8 @@ RSB_DNOINL int col_box_box(const real *pa, const real *Ra, const real *ha, const
 #define MISC_NEFC 1
 #define MISC_ITER 2
 #define MISC_NLIMROW 3
+#define MISC_OVF 4              /* sticky over the control step: bit 0 = a contact did not fit ncon_max, bit 1 = a constraint row did not fit nefc_max */
+#define MISC_ITERSUM 5          /* Newton iterations of this env summed over the substeps of the control step */
 
 /* Conservative box-pair cull (after the bounding spheres): the bounding sphere of one box against the other box itself, both ways.
    A flat table has a bounding sphere of 0.57 m that every gripper geom is always inside; its slab is what matters. */
@@ -717,7 +721,7 @@ RSB_DN void st_collision(int so, Grp g) { real *s = RSB_SMEM + so;
     }
     base += gshfl_i(g, incl, RSB_LANES - 1);
   }
-  if (base > MDL.ncon_max) base = MDL.ncon_max;
+  if (base > MDL.ncon_max) { base = MDL.ncon_max; if (g.lane == 0) misc[MISC_OVF] |= 1; }       /* truncation is counted, never silent (RSB_INFO_NCON_OVERFLOW) */
   if (g.lane == 0) misc[MISC_NCON] = base;
   gsync(g);
 }
@@ -760,7 +764,7 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
     if (cnt && dhi < mg && r < MDL.nefc_max) { etid[r] = ET_PACK(EFC_LIMIT, 1, j); epos[r] = dhi; emargin[r] = mg; }
     nrow += gshfl_i(g, incl, RSB_LANES - 1);
   }
-  if (nrow > MDL.nefc_max) nrow = MDL.nefc_max;
+  if (nrow > MDL.nefc_max) { nrow = MDL.nefc_max; if (g.lane == 0) misc[MISC_OVF] |= 2; }
   const int nscalar = nrow;
   if (g.lane == 0) misc[MISC_NLIMROW] = nscalar;                 /* number of scalar rows (friction loss + limits): they precede the contact rows */
   /* contact row addresses: serial rule of the reference (a contact that does not fit is skipped, later ones may fit) */
@@ -768,7 +772,7 @@ RSB_DN void st_constraint(int so, Grp g) { real *s = RSB_SMEM + so;
   if (g.lane == 0) {
     int n = nscalar;
     for (int c = 0; c < ncon; c++) { int *ci = (int *)(con + c * RSB_CONW); int dim = CON_DIM_OF(ci);
-      if (n + dim > MDL.nefc_max) ci[CON_ADR] = -1; else { ci[CON_ADR] = n; n += dim; } }
+      if (n + dim > MDL.nefc_max) { ci[CON_ADR] = -1; misc[MISC_OVF] |= 2; } else { ci[CON_ADR] = n; n += dim; } }
     misc[MISC_NEFC] = n;
   }
   gsync(g);
@@ -1428,7 +1432,7 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
     gsync(g);
     const real f = mulJT_lane(so, g, nefc); if (dl) qfc[d] = f;
   }
-  if (g.lane == 0) misc[MISC_ITER] = iter;
+  if (g.lane == 0) { misc[MISC_ITER] = iter; misc[MISC_ITERSUM] += iter; }
   gsync(g);
 }
 
@@ -1607,23 +1611,31 @@ RSB_D void store_state(int so, real *st, Grp g) { const real *s = RSB_SMEM + so;
 }
 
 /* One control step of one env (robosuite MujocoEnv.step): 25 x (forward, controller, mj_step), then reward + observation.
-   `st` = this env's state record, `action` = [act_dim], `obs` = [obs_dim] output row.  Returns via *reward, *done.
-   Stepping a finished episode leaves the state untouched and reports done = 2 (the host raises ValueError). */
-RSB_D void env_step(int so, Grp g, real *st, const real *action, real *obs, real *reward, unsigned char *done, bool commit) { real *s = RSB_SMEM + so;
+   `st` = this env's state record, `action` = [act_dim], `obs` = [obs_dim] output row; `obs2` (may be null) = a second destination of the
+   same observation row -- in ring mode `obs` is next_obs[slot] and `obs2` is observations[slot + N], the row the next control step's policy
+   forward reads (rlkit's EnvReplayBuffer keeps both arrays).  Returns via *reward, *done; `iters` (may be null) receives the env's Newton
+   iterations of this control step.  Stepping a finished episode leaves the state untouched, reports done = 2 and bumps counter 2 (the
+   host raises ValueError). */
+RSB_D void env_step(int so, Grp g, real *st, const real *action, real *obs, real *obs2, real *reward, unsigned char *done, unsigned int *iters, bool commit) { real *s = RSB_SMEM + so;
   int t = f2i(st[MDL.st_time]);
   const bool finished = (t >= MDL.horizon) && !MDL.ignore_done;
   load_state(so, st, g);
   for (int i = g.lane; i < MDL.act_dim; i += RSB_LANES) s[MDL.o_act + i] = action[i];
+  if (g.lane == 0) { int *misc = (int *)(s + MDL.o_misc); misc[MISC_OVF] = 0; misc[MISC_ITERSUM] = 0; }
   gsync(g);
   PROF_DECL;
   for (int k = 0; k < MDL.substeps; k++) substep(so, g, k == 0, pt_);
   st_kinematics(so, g); RSB_CTA_SYNC(0); st_collision(so, g);   /* observations / reward read the post-step kinematics and contacts */
   if (!commit) return;                               /* padding warp of the last CTA: ran only to reach the barriers */
-  if (finished) { if (g.lane == 0) { *done = 2; *reward = 0; } return; }      /* state untouched; host raises ValueError */
+  if (finished) { if (g.lane == 0) { *done = 2; *reward = 0; count_event(2, 1); } return; }      /* state untouched; host raises ValueError */
   real r = task_reward(so);
-  for (int i = g.lane; i < MDL.obs_dim; i += RSB_LANES) obs[i] = obs_element(so, i);
+  for (int i = g.lane; i < MDL.obs_dim; i += RSB_LANES) { const real v = obs_element(so, i); obs[i] = v; if (obs2) obs2[i] = v; }
   store_state(so, st, g);
-  if (g.lane == 0) { t++; st[MDL.st_time] = i2f(t); *reward = r; *done = ((t >= MDL.horizon) && !MDL.ignore_done) ? 1 : 0; }
+  if (g.lane == 0) { t++; st[MDL.st_time] = i2f(t); *reward = r; *done = ((t >= MDL.horizon) && !MDL.ignore_done) ? 1 : 0;
+    const int *misc = (const int *)(s + MDL.o_misc); const int ovf = misc[MISC_OVF];
+    if (ovf & 1) count_event(0, 1);
+    if (ovf & 2) count_event(1, 1);
+    if (iters) *iters = (unsigned int)misc[MISC_ITERSUM]; }
 }
 
 /* robosuite MujocoEnv.reset (hard_reset = False): sim.reset, noisy arm init, object placement, new controller, forward, obs.

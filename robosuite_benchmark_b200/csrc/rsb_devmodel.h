@@ -86,6 +86,8 @@ typedef struct DevModel {
   int o_cscr, o_tau;           /* controller scratch; last arm torques (kept for parity checks) */
   int o_misc;                  /* ncon, nefc, iters, ... (8 words) */
   int smem_words;
+  unsigned int *counters;      /* per-batch event counters in HBM (may be null): [0] control steps of an env that dropped a contact beyond ncon_max,
+                                  [1] ... that dropped a constraint row beyond nefc_max, [2] steps asked of a terminated episode */
 #define X(n) const int *n;
   RSB_DM_INT_ARRAYS(X)
 #undef X
@@ -156,7 +158,11 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
   d.ncon_max = ncon_max; d.nefc_max = nefc_max; d.frame_cache = (3 * ncon_max <= nefc_max) ? 1 : 0; d.ldm = m->nv | 1; d.ldj = m->nv | 1;
   d.timestep = (float)m->timestep; for (int k = 0; k < 3; k++) d.gravity[k] = (float)m->gravity[k];
   d.impratio = (float)m->impratio; d.meaninertia = (float)m->meaninertia; d.cone = m->cone;
-  d.solver_iters = 12; d.ls_iters = 24; d.solver_tol = 1e-6f; d.ls_tol = 1e-2f;   /* MuJoCo ls_tolerance default */ d.lockstep = 0x1ff;
+  /* <option iterations tolerance ls_iterations ls_tolerance> of the compiled model (MuJoCo's mjOption fields): never hard-coded here.  The fp32
+     working budget (12 Newton iterations, improvement tolerance 1e-6, 24 line-search steps) is an explicit override applied by the HOST to the
+     model it passes in (environments.py `solver=` argument, documented in DESIGN.md 4.1), not a property of this builder. */
+  if (m->iterations < 1 || m->ls_iterations < 1 || !(m->tolerance >= 0) || !(m->ls_tolerance > 0)) { h.error = "model option: iterations / ls_iterations / tolerance / ls_tolerance out of range"; return false; }
+  d.solver_iters = m->iterations; d.ls_iters = m->ls_iterations; d.solver_tol = (float)m->tolerance; d.ls_tol = (float)m->ls_tolerance; d.lockstep = 0x1ff;
   /* bodies */
   std::vector<int> lastdof((size_t)m->nbody, -1), dofmask((size_t)m->nbody, 0);
   for (int b = 1; b < m->nbody; b++) {

@@ -18,20 +18,26 @@ __device__ __forceinline__ Grp make_group(int &slot) {
   return g;
 }
 
+/* Row of env `e` in the caller's arrays: plain batches use row e; in ring mode (cap > 0) the arrays are the replay ring's and the
+   row is slot (slot0 + e) mod cap -- the transition lands where rlkit's EnvReplayBuffer.add_sample would have put it, with no copy. */
+__device__ __forceinline__ long ring_row(long slot0, long cap, int e) { if (cap <= 0) return e; long r = slot0 + e; return r >= cap ? r - cap : r; }
+
 __global__ void __launch_bounds__(RSB_MAX_THREADS)
-k_step(float *__restrict__ state, const float *__restrict__ actions, float *__restrict__ obs, float *__restrict__ rew, unsigned char *__restrict__ done, int n) {
+k_step(const RsbStepArgs a) {
   int w; Grp g = make_group(w); const int env = blockIdx.x * (blockDim.x / RSB_LANES) + w;
-  const bool commit = env < n; const int e = commit ? env : n - 1;          /* padding groups shadow the last env (no stores) */
-  env_step(w * c_model.smem_words, g, state + (size_t)e * c_model.st_words, actions + (size_t)e * c_model.act_dim,
-           obs + (size_t)e * c_model.obs_dim, rew + e, done + e, commit);
+  const bool commit = env < a.n; const int e = commit ? env : a.n - 1;          /* padding groups shadow the last env (no stores) */
+  const long r = ring_row(a.slot0, a.cap, e);
+  float *obs2 = a.obs2 ? a.obs2 + (size_t)ring_row(a.slot1, a.cap, e) * c_model.obs_dim : nullptr;
+  env_step(w * c_model.smem_words, g, a.state + (size_t)e * c_model.st_words, a.actions + (size_t)r * c_model.act_dim,
+           a.obs + (size_t)r * c_model.obs_dim, obs2, a.rew + r, a.done + r, a.iters ? a.iters + e : nullptr, commit);
 }
 
 __global__ void __launch_bounds__(RSB_MAX_THREADS)
-k_reset(float *__restrict__ state, const unsigned char *__restrict__ mask, float *__restrict__ obs, uint64_t seed, uint64_t env_id_base, int n) {
+k_reset(float *__restrict__ state, const unsigned char *__restrict__ mask, float *__restrict__ obs, long slot0, long cap, uint64_t seed, uint64_t env_id_base, int n) {
   int w; Grp g = make_group(w); const int env = blockIdx.x * (blockDim.x / RSB_LANES) + w;
   const int e = env < n ? env : n - 1; const bool commit = env < n && (!mask || mask[e]);
   if (!__any_sync(0xffffffffu, commit)) return;       /* whole warp idle; otherwise an idle group shadows its env without storing */
-  env_reset(w * c_model.smem_words, g, state + (size_t)e * c_model.st_words, seed, env_id_base + (uint64_t)e, obs + (size_t)e * c_model.obs_dim, commit);
+  env_reset(w * c_model.smem_words, g, state + (size_t)e * c_model.st_words, seed, env_id_base + (uint64_t)e, obs + (size_t)ring_row(slot0, cap, e) * c_model.obs_dim, commit);
 }
 
 __global__ void __launch_bounds__(RSB_MAX_THREADS)
@@ -70,10 +76,10 @@ cudaError_t t_prepare(size_t smem_bytes, int epb, int *regs, int *blocks_per_sm)
   cudaFuncAttributes fa; if ((e = cudaFuncGetAttributes(&fa, k_step)) != cudaSuccess) return e; *regs = fa.numRegs;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_step, epb * RSB_LANES, want);
 }
-void t_step(int blocks, int epb, size_t smem, cudaStream_t st, float *state, const float *a, float *o, float *r, unsigned char *d, int n) {
-  k_step<<<blocks, epb * RSB_LANES, smem, st>>>(state, a, o, r, d, n); }
-void t_reset(int blocks, int epb, size_t smem, cudaStream_t st, float *state, const unsigned char *mask, float *o, uint64_t seed, uint64_t base, int n) {
-  k_reset<<<blocks, epb * RSB_LANES, smem, st>>>(state, mask, o, seed, base, n); }
+void t_step(int blocks, int epb, size_t smem, cudaStream_t st, const RsbStepArgs *a) {
+  k_step<<<blocks, epb * RSB_LANES, smem, st>>>(*a); }
+void t_reset(int blocks, int epb, size_t smem, cudaStream_t st, float *state, const unsigned char *mask, float *o, long slot0, long cap, uint64_t seed, uint64_t base, int n) {
+  k_reset<<<blocks, epb * RSB_LANES, smem, st>>>(state, mask, o, slot0, cap, seed, base, n); }
 void t_debug(int blocks, int epb, size_t smem, cudaStream_t st, float *state, const float *a, int ps, float *dbg, int words, int n) {
   k_debug_substep<<<blocks, epb * RSB_LANES, smem, st>>>(state, a, ps, dbg, words, n); }
 void t_random(cudaStream_t st, uint64_t seed, uint64_t base, uint64_t step, int act_dim, float *a, int n) {

@@ -25,8 +25,9 @@
  * matrices along K (128), [32,46) stride byte offset >> 4 = distance between 8-row groups (2048), [46,48) = 1 (sm_100), [61,64) = 0 (no swizzle).
  * Instruction descriptor (32 bit): [4,6) D format 1 = F32, [7,10) A format 2 = TF32, [10,13) B format 2 = TF32, bits 15/16 = 0 (both K-major),
  * [17,23) N >> 3, [24,29) M >> 4.
- * Every mbarrier wait is bounded (a wait that gives up raises a device-side counter, rsb_gemm_timeouts()), so a protocol error shows up as a
- * wrong result in the tests and never as a hung GPU.
+ * Every mbarrier wait is bounded: a wait that gives up raises a device-side counter (rsb_gemm_timeouts(), checked by the training loop once
+ * per epoch and by the tests) AND the CTA writes NaN into its tile of C, so a protocol error reaches the losses and the parameters as NaN --
+ * never a hung GPU, never silently stale activations or gradients.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
         const float4 pv = *reinterpret_cast<const float4 *>(lp + sidx * BM * ldp);
         x.x += pv.x; x.y += pv.y; x.z += pv.z; x.w += pv.w;
       }
-      if (m < g.m && done && got && c < nvalid) {
+      if (m < g.m && c < nvalid) {
         float *crow = cbase_p + (long long)m * g.c_rs;
         const float *mrow = mbase_p ? mbase_p + (long long)m * g.mask_rs : nullptr;
         const float4 bv = *reinterpret_cast<const float4 *>(sbias + c);
@@ -269,6 +270,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
             if (accum) f[j] += crow[nn];
           }
         }
+        if (!(done && got)) f[0] = f[1] = f[2] = f[3] = __int_as_float(0x7fc00000);      /* a bounded wait gave up: the tile is poisoned with NaN so the failure
+                                                                                       reaches the losses / parameters instead of leaving last update's values in C */
         if (st16 && c + 4 <= nvalid) *reinterpret_cast<float4 *>(crow + c) = make_float4(f[0], f[1], f[2], f[3]);
         else {
 #pragma unroll

@@ -34,7 +34,7 @@ class _EnvBase:
                  reward_shaping=False, hard_reset=True, ignore_done=False, has_renderer=False,
                  has_offscreen_renderer=False, use_object_obs=True, use_camera_obs=False,
                  env_configuration="single-arm-opposed", num_envs=1, device="cuda:0", seed=0, env_id_base=0,
-                 ncon_max=0, nefc_max=0, gripper_types="default", initialization_noise="default", **unsupported):
+                 ncon_max=0, nefc_max=0, gripper_types="default", initialization_noise="default", solver="fp32", **unsupported):
         if has_renderer or has_offscreen_renderer or use_camera_obs:
             raise NotImplementedError("rendering / camera observations are outside the batched hot path")
         if not use_object_obs:
@@ -60,7 +60,7 @@ class _EnvBase:
         self.model, self.task = build_task(env_name, self.robot_names, controller_configs, horizon=horizon,
                                            control_freq=control_freq, reward_scale=1.0 if reward_scale is None else reward_scale,
                                            reward_shaping=reward_shaping, ignore_done=ignore_done,
-                                           env_configuration=env_configuration)
+                                           env_configuration=env_configuration, solver=solver)
         self.sim = BatchSim(self.model, self.task, num_envs, device=device, seed=seed, env_id_base=env_id_base,
                             ncon_max=ncon_max, nefc_max=nefc_max)
         self.num_envs = int(num_envs)

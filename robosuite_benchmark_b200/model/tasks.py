@@ -79,8 +79,13 @@ def _robot_desc(m: Model, pf: str, robot: str, cc: dict) -> dict:
 
 def build_task(env_name: str, robots: Sequence[str], controller_config: dict, horizon: int = 500,
                control_freq: float = 20, reward_scale: float = 1.0, reward_shaping: bool = True,
-               ignore_done: bool = False, env_configuration: str = "single-arm-opposed"):
-    """-> (Model, task dict).  `controller_config` is the dict from load_controller_config."""
+               ignore_done: bool = False, env_configuration: str = "single-arm-opposed", solver="fp32"):
+    """-> (Model, task dict).  `controller_config` is the dict from load_controller_config.
+
+    `solver`: the constraint solver runs with the compiled model's `<option iterations tolerance ls_iterations ls_tolerance>` -- the
+    kernels read those four fields of the model, nothing is hard-coded on the device.  "model" keeps what the MJCF says (MuJoCo's
+    defaults: 100 Newton iterations, tolerance 1e-8, 50 line-search steps); "fp32" (default) is the documented override for fp32
+    arithmetic, where improvements below ~1e-6 of the scaled cost are round-off (SOLVER_FP32 below); a dict overrides field by field."""
     if isinstance(robots, str):
         robots = [robots]
     if env_name not in TASK_IDS:
@@ -92,6 +97,7 @@ def build_task(env_name: str, robots: Sequence[str], controller_config: dict, ho
     builder = _BUILDERS[env_name]
     xml, objs = builder(robots, env_configuration)
     m = compile_mjcf(xml)
+    apply_solver_option(m, solver)
     substeps = int((1.0 / control_freq) / m.timestep)
     n_rob = len(robots)
     rdesc = [_robot_desc(m, f"robot{i}_", r, controller_config) for i, r in enumerate(robots)]
@@ -103,6 +109,21 @@ def build_task(env_name: str, robots: Sequence[str], controller_config: dict, ho
                 act_dim=act_dim, env_name=env_name, robots=list(robots), xml=xml, ncon_max=LIMITS[env_name][0], nefc_max=LIMITS[env_name][1])
     task.update(objs(m))
     return m, task
+
+
+SOLVER_FP32 = dict(iterations=12, tolerance=1e-6, ls_iterations=24, ls_tolerance=0.01)
+
+
+def apply_solver_option(m: Model, solver):
+    """Write the solver override into the model's option block (see build_task)."""
+    if solver in (None, "model"):
+        return m
+    over = SOLVER_FP32 if solver == "fp32" else dict(solver)
+    for k, v in over.items():
+        if k not in ("iterations", "tolerance", "ls_iterations", "ls_tolerance"):
+            raise ValueError(f"unknown solver option {k!r}")
+        m.opt[k] = type(SOLVER_FP32[k])(v)
+    return m
 
 
 def empty_task():

@@ -36,3 +36,21 @@ def max_over_ranks(value: float, device=None) -> float:
 def whole_job_rate(units_per_rank: int, world: int, seconds_max: float) -> float:
     """value = units all ranks processed / max-over-ranks time."""
     return world * units_per_rank / seconds_max
+
+
+def reduce_path_stats(acc, counts, device=None):
+    """Per-epoch collective of the logged statistics: `acc` holds {sum, sum of squares, max, min} x 4 quantities
+    (algorithm.batched_path_information), `counts` the sample counts; sums and counts add over the ranks, maxima / minima combine."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return acc, counts
+    acc = np.asarray(acc, np.float64)
+    sums = torch.tensor(np.concatenate([acc[0::4], acc[1::4], np.asarray(counts, np.float64)]), dtype=torch.float64, device=device)
+    mx = torch.tensor(acc[2::4], dtype=torch.float64, device=device)
+    mn = torch.tensor(acc[3::4], dtype=torch.float64, device=device)
+    dist.all_reduce(sums); dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+    sums, out = sums.cpu().numpy(), acc.copy()
+    out[0::4], out[1::4], out[2::4], out[3::4] = sums[0:4], sums[4:8], mx.cpu().numpy(), mn.cpu().numpy()
+    return out, sums[8:]

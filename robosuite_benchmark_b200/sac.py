@@ -42,12 +42,12 @@ class EnvReplayBuffer:
     resident in HBM.  `add_batch` appends N transitions written by the env kernels; `random_batch` draws indices with
     replacement from Philox keyed (seed, draw counter, row) -- the same integers the numpy oracle produces."""
 
-    def __init__(self, max_replay_buffer_size, env=None, obs_dim=None, action_dim=None, device="cuda:0", seed=0):
+    def __init__(self, max_replay_buffer_size, env=None, env_info_sizes=None, obs_dim=None, action_dim=None, device=None, seed=0):
         import torch
         if not torch.cuda.is_available():
             raise RsbError("the replay ring lives in HBM: no CUDA device visible")
         self.torch, self.L = torch, lib()
-        self.device = torch.device(device)
+        self.device = torch.device(device or default_device())
         if env is not None:
             obs_dim = env.observation_space.low.size
             action_dim = env.action_space.low.size
@@ -60,6 +60,21 @@ class EnvReplayBuffer:
         self._rewards = torch.zeros(self.capacity, **f32)
         self._terminals = torch.zeros(self.capacity, dtype=torch.uint8, device=self.device)
         self._top, self._size, self.seed, self.draws = 0, 0, int(seed), 0
+        from .backend import RsbRing
+        # the C-ABI view of the five arrays (include/rsb.h rsb_ring): in ring mode the env kernels are the producer of these rows
+        self.ring = RsbRing(self._observations.data_ptr(), self._actions.data_ptr(), self._rewards.data_ptr(), self._terminals.data_ptr(),
+                            self._next_obs.data_ptr(), self.capacity)
+
+    @property
+    def top(self):
+        return self._top
+
+    def commit(self, n):
+        """The n rows from `top` on were written in place by the env kernels (rsb_step_ring): advance the ring pointer, saturate the
+        size -- rlkit's add_sample bookkeeping (`_advance`) for n samples, with no data movement."""
+        if n > self.capacity:
+            raise ValueError("round larger than the ring")
+        self._advance(int(n))
 
     def _pieces(self, n):
         """Ring rows for the next n transitions as (ring_slice, batch_slice) pieces (two when the pointer wraps)."""
@@ -208,84 +223,231 @@ def init_host_params(O, A, H=HID, seed=0, policy_init_w=1e-3, qf_init_w=3e-3, b_
             "log_alpha": np.zeros(1, np.float32)}
 
 
-class FlattenMlp:
-    """Handle on one Q network of the store (rlkit FlattenMlp: cat(obs, act) -> 256 -> 256 -> 1)."""
+def default_device():
+    """cuda:LOCAL_RANK (one process per GPU under torchrun), cuda:0 otherwise."""
+    import os
+    return "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))
 
-    def __init__(self, store: ParamStore, index: int, target=False):
-        self.store, self.index, self.target = store, index, target
+
+def _fanin_uniform(shape, fan_in):
+    bound = 1.0 / np.sqrt(fan_in)
+    return np.random.uniform(-bound, bound, size=shape).astype(np.float32)
+
+
+class _Net:
+    """Common part of the network handles.  A handle is either BOUND to a ParamStore (its weights are views into the store's flat
+    buffer: the form the fused update needs) or UNBOUND (host numpy weights: what the reference's constructors produce before the
+    trainer exists, util/rlkit_utils.py:64-92, and what a snapshot unpickles to); SACTrainer binds unbound handles into one store."""
+    KEYS = ("W0", "b0", "W1", "b1", "W2", "b2")
+    store = None
+
+    def to(self, device=None):                       # rlkit: net.to(ptu.device) -- parameters already live where the store lives
+        return self
+
+    def cuda(self, device=None):
+        return self
+
+    def cpu(self):
+        return self
+
+    def train(self, mode=True):
+        return self
+
+    def eval(self):
+        return self
+
+    def host_params(self):
+        """name -> numpy [in, out] weights / [out] biases."""
+        if self.store is None:
+            return {k: v.copy() for k, v in self._host.items()}
+        return {k: v.detach().cpu().numpy().copy() for k, v in self.views().items()}
+
+    def _torch_state(self, host):
+        import torch
+        return OrderedDict((k, torch.from_numpy(np.ascontiguousarray(v))) for k, v in host.items())
+
+
+class FlattenMlp(_Net):
+    """rlkit FlattenMlp: cat(inputs, dim=1) -> 256 -> 256 -> output_size, with the reference's constructor
+    `FlattenMlp(input_size=obs_dim + action_dim, output_size=1, hidden_sizes=[256, 256])` (util/rlkit_utils.py:64-83).
+    rlkit init: hidden W ~ U(+-1/sqrt(fan_in)), hidden b = 0.1, last layer U(+-init_w), drawn from numpy's global generator."""
+
+    def __init__(self, hidden_sizes=(HID, HID), output_size=1, input_size=None, init_w=3e-3, b_init_value=0.1, **unsupported):
+        if unsupported:
+            raise NotImplementedError(f"FlattenMlp options {sorted(unsupported)} are not on the benchmark path")
+        if list(hidden_sizes) != [HID, HID] or output_size != 1 or input_size is None:
+            raise NotImplementedError("the fused update is built for the benchmark's Q networks: input -> 256 -> 256 -> 1")
+        self.input_size, self.output_size, self.hidden_sizes = int(input_size), 1, [HID, HID]
+        self.store, self.index, self.target = None, None, False
+        QI = self.input_size
+        self._host = {"W0": _fanin_uniform((QI, HID), QI), "b0": np.full(HID, b_init_value, np.float32),
+                      "W1": _fanin_uniform((HID, HID), HID), "b1": np.full(HID, b_init_value, np.float32),
+                      "W2": np.random.uniform(-init_w, init_w, (HID, 1)).astype(np.float32),
+                      "b2": np.random.uniform(-init_w, init_w, (1,)).astype(np.float32)}
+
+    @classmethod
+    def of(cls, store: "ParamStore", index: int, target=False):
+        """Handle on Q network `index` of an existing store (its target copy when target=True)."""
+        self = cls.__new__(cls)
+        self.store, self.index, self.target, self._host = store, int(index), bool(target), None
         self.input_size, self.output_size, self.hidden_sizes = store.O + store.A, 1, [store.H, store.H]
+        return self
 
     def views(self):
         src = self.store.T if self.target else self.store.P
-        return {k: src["q_" + k][self.index] for k in ("W0", "b0", "W1", "b1", "W2", "b2")}
+        return {k: src["q_" + k][self.index] for k in self.KEYS}
 
-    def __call__(self, obs, act):
+    def __call__(self, *inputs):
+        """Q(obs, act) on the device (diagnostics / tests; the update itself runs the batched twin-Q products of SACTrainer)."""
+        if self.store is None:
+            raise RsbError("this Q network is not bound to a trainer yet (SACTrainer(...) places it in the parameter store)")
         t = self.store.torch
-        v = self.views()
-        x = t.cat([obs, act], dim=1)
-        h = t.relu(x @ v["W0"] + v["b0"])
-        h = t.relu(h @ v["W1"] + v["b1"])
-        return h @ v["W2"] + v["b2"]
+        v, out = self.views(), None
+        x = t.cat([t.as_tensor(i, dtype=t.float32, device=self.store.device) for i in inputs], dim=1).contiguous()
+        h1 = t.empty(x.shape[0], HID, device=x.device); h2 = t.empty_like(h1); out = t.empty(x.shape[0], 1, device=x.device)
+        gemm_tf32(x, v["W0"], h1, bias=v["b0"], relu=True); gemm_tf32(h1, v["W1"], h2, bias=v["b1"], relu=True); gemm_tf32(h2, v["W2"], out, bias=v["b2"])
+        return out
 
     def state_dict(self):
-        v = self.views()
-        return OrderedDict([("fc0.weight", v["W0"].t().contiguous().cpu()), ("fc0.bias", v["b0"].cpu().clone()),
-                            ("fc1.weight", v["W1"].t().contiguous().cpu()), ("fc1.bias", v["b1"].cpu().clone()),
-                            ("last_fc.weight", v["W2"].t().contiguous().cpu()), ("last_fc.bias", v["b2"].cpu().clone())])
+        v = self.host_params()
+        return self._torch_state(OrderedDict([("fc0.weight", v["W0"].T), ("fc0.bias", v["b0"]), ("fc1.weight", v["W1"].T), ("fc1.bias", v["b1"]),
+                                              ("last_fc.weight", v["W2"].T), ("last_fc.bias", v["b2"])]))
+
+    def __getstate__(self):                          # snapshots hold the weights, not the store
+        return dict(input_size=self.input_size, params=self._torch_state(self.host_params()))
+
+    def __setstate__(self, st):
+        self.input_size, self.output_size, self.hidden_sizes = int(st["input_size"]), 1, [HID, HID]
+        self.store, self.index, self.target = None, None, False
+        self._host = {k: v.numpy().copy() for k, v in st["params"].items()}
 
 
-class TanhGaussianPolicy:
-    """rlkit TanhGaussianPolicy handle: obs -> 256 -> 256 -> (mean, log_std); a = tanh(mean + std * eps)."""
+class TanhGaussianPolicy(_Net):
+    """rlkit TanhGaussianPolicy: obs -> 256 -> 256 -> (mean, log_std); a = tanh(mean + std * eps), with the reference's constructor
+    `TanhGaussianPolicy(obs_dim=, action_dim=, hidden_sizes=[256, 256])` (util/rlkit_utils.py:88-92).  get_action / get_actions run
+    the hand-written batched forward kernel (csrc/rsb_collect.cu k_policy_act) -- there is no torch/cuBLAS forward and no CPU path."""
 
-    def __init__(self, store: ParamStore):
-        self.store = store
+    def __init__(self, hidden_sizes=(HID, HID), obs_dim=None, action_dim=None, std=None, init_w=1e-3, b_init_value=0.1, **unsupported):
+        if unsupported or std is not None:
+            raise NotImplementedError("TanhGaussianPolicy: only the learned-std form of the benchmark is implemented")
+        if list(hidden_sizes) != [HID, HID] or obs_dim is None or action_dim is None:
+            raise NotImplementedError("the policy kernels are built for the benchmark's policy: obs -> 256 -> 256 -> 2 * action_dim")
+        self.obs_dim, self.action_dim = int(obs_dim), int(action_dim)
+        self.input_size, self.output_size, self.hidden_sizes = self.obs_dim, self.action_dim, [HID, HID]
+        self.store, self._dev, self.seed, self.env_id_base, self._steps = None, None, 0, 0, 0
+        O, A = self.obs_dim, self.action_dim
+        self._host = {"W0": _fanin_uniform((O, HID), O), "b0": np.full(HID, b_init_value, np.float32),
+                      "W1": _fanin_uniform((HID, HID), HID), "b1": np.full(HID, b_init_value, np.float32),
+                      "W2": np.random.uniform(-init_w, init_w, (HID, 2 * A)).astype(np.float32),
+                      "b2": np.random.uniform(-init_w, init_w, (2 * A,)).astype(np.float32)}
+
+    @classmethod
+    def of(cls, store: "ParamStore", seed=0, env_id_base=0):
+        self = cls.__new__(cls)
+        self.store, self._host, self._dev = store, None, None
+        self.obs_dim, self.action_dim = store.O, store.A
         self.input_size, self.output_size, self.hidden_sizes = store.O, store.A, [store.H, store.H]
+        self.seed, self.env_id_base, self._steps = int(seed), int(env_id_base), 0
+        return self
 
-    def forward(self, obs, deterministic=False, eps=None):
-        t, P, A = self.store.torch, self.store.P, self.store.A
-        h = t.relu(obs @ P["p_W0"] + P["p_b0"])
-        h = t.relu(h @ P["p_W1"] + P["p_b1"])
-        out = h @ P["p_W2"] + P["p_b2"]
-        mean, log_std = out[:, :A], out[:, A:].clamp(-20.0, 2.0)
-        if deterministic:
-            return t.tanh(mean), mean, log_std
-        if eps is None:
-            eps = t.randn_like(mean)
-        return t.tanh(mean + log_std.exp() * eps), mean, log_std
+    def views(self):
+        return {k: self.store.P["p_" + k] for k in self.KEYS}
 
-    def get_actions(self, obs, deterministic=False):
-        """obs: torch tensor [N, O] on the device -> actions [N, A] (batched collectors)."""
-        with self.store.torch.no_grad():
-            return self.forward(obs, deterministic)[0]
+    # -- device weights for the forward kernel
+    def _weights(self):
+        if self.store is not None:
+            return self.views(), self.store.device
+        if self._dev is None:                        # an unbound policy (e.g. unpickled from params.pkl) uploads its weights on first use
+            import torch
+            if not torch.cuda.is_available():
+                raise RsbError("the policy forward runs on a CUDA device only (no CPU fallback)")
+            dev = torch.device(default_device())
+            self._dev = ({k: torch.as_tensor(v, device=dev).contiguous() for k, v in self._host.items()}, dev)
+        return self._dev
+
+    def act_into(self, obs, obs_ld, act, act_ld, n, slot0=0, cap=0, deterministic=False, step=None, stream_device=None):
+        """Launch k_policy_act on raw row-addressed arrays (the replay ring in ring mode).  `step` keys the exploration noise
+        (default: this policy's own call counter)."""
+        W, dev = self._weights()
+        if step is None:
+            step = self._steps
+            self._steps += 1
+        _chk(lib().rsb_policy_act(_ptr(W["W0"]), _ptr(W["b0"]), _ptr(W["W1"]), _ptr(W["b1"]), _ptr(W["W2"]), _ptr(W["b2"]),
+                                  self.obs_dim, self.action_dim, HID, obs, int(obs_ld), act, int(act_ld), C.c_int64(slot0), C.c_int64(cap), int(n),
+                                  int(bool(deterministic)), C.c_uint64(self.seed), C.c_uint64(self.env_id_base), C.c_uint64(step), _stream(dev)))
+
+    def get_actions(self, obs, deterministic=False, out=None, step=None):
+        """obs: fp32 CUDA tensor [N, obs_dim] -> actions [N, action_dim] (env i of the batch draws noise under global id env_id_base + i)."""
+        _, dev = self._weights()
+        import torch
+        obs = obs.to(device=dev, dtype=torch.float32)
+        if obs.stride(-1) != 1:
+            obs = obs.contiguous()
+        n = obs.shape[0]
+        out = torch.empty(n, self.action_dim, dtype=torch.float32, device=dev) if out is None else out
+        self.act_into(_ptr(obs), obs.stride(0), _ptr(out), out.stride(0), n, deterministic=deterministic, step=step)
+        return out
 
     def get_action(self, obs_np, deterministic=False):
-        t = self.store.torch
-        o = t.as_tensor(np.asarray(obs_np, np.float32)[None], device=self.store.device)
+        """rlkit Policy.get_action: one observation (numpy) -> (action float64 numpy, agent_info {})."""
+        import torch
+        _, dev = self._weights()
+        o = torch.as_tensor(np.asarray(obs_np, np.float32).reshape(1, -1), device=dev)
         return self.get_actions(o, deterministic)[0].cpu().numpy().astype(np.float64), {}
 
     def reset(self):
         pass
 
     def state_dict(self):
-        P, A = self.store.P, self.store.A
-        W2, b2 = P["p_W2"], P["p_b2"]
-        return OrderedDict([("fc0.weight", P["p_W0"].t().contiguous().cpu()), ("fc0.bias", P["p_b0"].cpu().clone()),
-                            ("fc1.weight", P["p_W1"].t().contiguous().cpu()), ("fc1.bias", P["p_b1"].cpu().clone()),
-                            ("last_fc.weight", W2[:, :A].t().contiguous().cpu()), ("last_fc.bias", b2[:A].cpu().clone()),
-                            ("last_fc_log_std.weight", W2[:, A:].t().contiguous().cpu()), ("last_fc_log_std.bias", b2[A:].cpu().clone())])
+        v, A = self.host_params(), self.action_dim
+        return self._torch_state(OrderedDict([("fc0.weight", v["W0"].T), ("fc0.bias", v["b0"]), ("fc1.weight", v["W1"].T), ("fc1.bias", v["b1"]),
+                                              ("last_fc.weight", v["W2"][:, :A].T), ("last_fc.bias", v["b2"][:A]),
+                                              ("last_fc_log_std.weight", v["W2"][:, A:].T), ("last_fc_log_std.bias", v["b2"][A:])]))
+
+    def __getstate__(self):
+        return dict(obs_dim=self.obs_dim, action_dim=self.action_dim, seed=self.seed, params=self._torch_state(self.host_params()))
+
+    def __setstate__(self, st):
+        self.obs_dim, self.action_dim = int(st["obs_dim"]), int(st["action_dim"])
+        self.input_size, self.output_size, self.hidden_sizes = self.obs_dim, self.action_dim, [HID, HID]
+        self.store, self._dev, self.seed, self.env_id_base, self._steps = None, None, int(st.get("seed", 0)), 0, 0
+        self._host = {k: v.numpy().copy() for k, v in st["params"].items()}
 
 
-class MakeDeterministic:
+class MakeDeterministic(_Net):
+    """rlkit MakeDeterministic: the evaluation policy, a = tanh(mean)."""
+
     def __init__(self, stochastic_policy):
         self.stochastic_policy = stochastic_policy
 
     def get_action(self, obs_np):
         return self.stochastic_policy.get_action(obs_np, deterministic=True)
 
-    def get_actions(self, obs):
-        return self.stochastic_policy.get_actions(obs, deterministic=True)
+    def get_actions(self, obs, deterministic=True, out=None, step=None):
+        return self.stochastic_policy.get_actions(obs, deterministic=True, out=out, step=step)
+
+    def act_into(self, *a, **k):
+        k["deterministic"] = True
+        return self.stochastic_policy.act_into(*a, **k)
 
     def reset(self):
+        pass
+
+    def state_dict(self):
+        return self.stochastic_policy.state_dict()
+
+    def cuda(self, device=None):
+        self.stochastic_policy.cuda(device)
+        return self
+
+
+def register_safe_globals():
+    """torch >= 2.6 unpickles with weights_only=True by default: allow-list the snapshot classes so that the reference's
+    `torch.load(params.pkl)['evaluation/policy']` (util/rlkit_utils.py:173-174,241-242) keeps working on snapshots written here."""
+    try:
+        import torch
+        torch.serialization.add_safe_globals([FlattenMlp, TanhGaussianPolicy, MakeDeterministic, OrderedDict])
+    except Exception:
         pass
 
 
@@ -295,43 +457,88 @@ class SACTrainer:
     all losses are built from the pre-update weights and the PRE-update alpha; Adam on policy / Q1 / Q2 / log_alpha;
     Polyak update when n_train_steps % target_update_period == 0 (so the very first step already updates)."""
 
-    def __init__(self, env=None, policy=None, qf1=None, qf2=None, target_qf1=None, target_qf2=None, *, store: ParamStore = None,
-                 replay_buffer: EnvReplayBuffer = None, batch_size=128, discount=0.99, reward_scale=1.0, policy_lr=1e-3, qf_lr=1e-3,
-                 soft_target_tau=1e-2, target_update_period=1, use_automatic_entropy_tuning=True, target_entropy=None,
-                 seed=0, tf32=True, use_graph=True, world_size=1, parallel_branches=True, gemm="tcgen05"):
+    def __init__(self, env=None, policy=None, qf1=None, qf2=None, target_qf1=None, target_qf2=None, discount=0.99, reward_scale=1.0,
+                 policy_lr=1e-3, qf_lr=1e-3, optimizer_class=None, soft_target_tau=1e-2, target_update_period=1, plotter=None,
+                 render_eval_paths=False, use_automatic_entropy_tuning=True, target_entropy=None, *, store: ParamStore = None,
+                 replay_buffer: EnvReplayBuffer = None, batch_size=None, seed=0, use_graph=True, world_size=1, rank=0,
+                 parallel_branches=True, gemm="tcgen05", device=None):
+        """Positional / keyword arguments up to `target_entropy` are rlkit's SACTrainer signature as the reference calls it
+        (util/rlkit_utils.py:98-106); the keyword-only ones belong to this backend.  Networks built with the reference's constructors
+        (unbound handles) are placed into ONE flat parameter store here; `store=` passes an existing one."""
         import torch
-        if store is None:
+        if optimizer_class is not None:
+            raise NotImplementedError("the fused optimizer kernel implements torch.optim.Adam (rlkit's default); optimizer_class is not supported")
+        if store is None and policy is not None and policy.store is not None:
             store = policy.store
+        if store is None:
+            if policy is None:
+                raise ValueError("SACTrainer needs a policy (or store=)")
+            O, A = policy.obs_dim, policy.action_dim
+            store = ParamStore(O, A, device or default_device(), seed=seed)
+            host, targets = {}, {}
+            for k, v in policy.host_params().items():
+                host["p_" + k] = v
+            q1, q2 = (qf1 or FlattenMlp(input_size=O + A)).host_params(), (qf2 or FlattenMlp(input_size=O + A)).host_params()
+            # rlkit's target networks are separately initialised modules (the reference builds four FlattenMlp's) and are NOT copied from
+            # the Q networks before training: keep that
+            t1 = (target_qf1 or FlattenMlp(input_size=O + A)).host_params()
+            t2 = (target_qf2 or FlattenMlp(input_size=O + A)).host_params()
+            for k in _Net.KEYS:
+                host["q_" + k] = np.stack([q1[k], q2[k]])
+                targets["q_" + k] = np.stack([t1[k], t2[k]])
+            store.load_host(host, targets)
+            for net, idx, tgt in ((qf1, 0, False), (qf2, 1, False), (target_qf1, 0, True), (target_qf2, 1, True)):
+                if net is not None:
+                    net.store, net.index, net.target, net._host = store, idx, tgt, None
+            policy.store, policy._host, policy._dev = store, None, None
         self.torch, self.L, self.store, self.device = torch, lib(), store, store.device
-        self.policy = policy or TanhGaussianPolicy(store)
-        self.qf1, self.qf2 = qf1 or FlattenMlp(store, 0), qf2 or FlattenMlp(store, 1)
-        self.target_qf1, self.target_qf2 = target_qf1 or FlattenMlp(store, 0, True), target_qf2 or FlattenMlp(store, 1, True)
-        self.replay, self.B = replay_buffer, int(batch_size)
+        self.policy = policy or TanhGaussianPolicy.of(store, seed=seed)
+        self.qf1, self.qf2 = qf1 or FlattenMlp.of(store, 0), qf2 or FlattenMlp.of(store, 1)
+        self.target_qf1, self.target_qf2 = target_qf1 or FlattenMlp.of(store, 0, True), target_qf2 or FlattenMlp.of(store, 1, True)
+        self.env, self.replay = env, replay_buffer
         self.discount, self.reward_scale = float(discount), float(reward_scale)
         self.tau, self.period = float(soft_target_tau), int(target_update_period)
         if not use_automatic_entropy_tuning:
             raise NotImplementedError("fixed-alpha SAC is not on the benchmark path (all committed variants use automatic entropy tuning)")
         A = store.A
         self.target_entropy = float(-A if target_entropy is None else target_entropy)   # -prod(action_space.shape)
-        self.seed, self.tf32, self.use_graph, self.world = int(seed), bool(tf32), bool(use_graph), int(world_size)
-        if gemm not in ("tcgen05", "cublas"):
-            raise ValueError(f"gemm must be 'tcgen05' or 'cublas', got {gemm!r}")
-        # TF32 products: the hand-written tcgen05 kernel (csrc/rsb_tc_gemm.cu) unless cuBLAS is asked for; tf32=False = cuBLAS fp32 (strict-parity mode)
-        self.gemm = gemm if self.tf32 else "cublas"
+        self.seed, self.use_graph, self.world, self.rank = int(seed), bool(use_graph), int(world_size), int(rank)
+        # GEMM back-end of the update, always explicit: "tcgen05" = the hand-written TF32 tensor-core kernel (csrc/rsb_tc_gemm.cu, the product
+        # path); "cublas" = torch.mm/bmm with TF32 (comparison arm); "cublas_fp32" = torch.mm/bmm in fp32 (reference arm of the parity tests)
+        if gemm not in ("tcgen05", "cublas", "cublas_fp32"):
+            raise ValueError(f"gemm must be 'tcgen05', 'cublas' or 'cublas_fp32', got {gemm!r}")
+        self.gemm, self.tf32 = gemm, gemm != "cublas_fp32"
+        # exploration-noise key of the update's reparameterised actions: the rank is folded in, so data-parallel ranks draw independent eps
+        self.noise_stream = 7 + 16 * self.rank
         self._n_train_steps_total = 0
         self._need_to_update_eval_statistics = True
         self.eval_statistics = OrderedDict()
         f32 = dict(dtype=torch.float32, device=self.device)
-        n = store.n
         self.policy_lr, self.qf_lr = float(policy_lr), float(qf_lr)
         self.bc = torch.tensor([0.0, 0.0, 1.0, 1.0], dtype=torch.float64, device=self.device)
         self.alpha = torch.tensor([1.0, 0.0], **f32)                 # [alpha, log_alpha] (device copy read by the kernels)
-        self._alloc(self.B)
+        self.refresh_alpha()
+        self.B = None
+        if batch_size is not None:
+            self.set_batch_size(batch_size)
         self._graphs = {}
         # side streams: the target-Q forward and the weight-gradient GEMMs do not lie on the update's dependency chain; inside the captured
         # graph they become parallel branches (the update is launch-latency bound: ~55 kernels of 2-4 us each)
         self._sT, self._sW, self._sB = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
         self.parallel_branches = bool(parallel_branches)          # False: everything on one stream (the reference order; tests compare the two)
+
+    def refresh_alpha(self):
+        """[alpha, log_alpha] device copy from the store's log_alpha (after load_host / a checkpoint restore)."""
+        la = self.store.P["log_alpha"]
+        self.alpha[1:2].copy_(la)
+        self.alpha[0:1].copy_(la.double().exp().float())
+
+    def set_batch_size(self, B):
+        """(Re)allocate the update's activation buffers for batches of B rows; captured graphs of another size are dropped."""
+        if self.B != int(B):
+            self.B = int(B)
+            self._alloc(self.B)
+            self._graphs = {}
 
     # -- buffers
     def _alloc(self, B):
@@ -390,7 +597,9 @@ class SACTrainer:
 
     def load_batch(self, batch):
         """Use an explicit batch (dict of tensors/arrays, rlkit keys) instead of sampling -- parity tests and `train(batch)`."""
-        t, B = self.torch, self.B
+        t = self.torch
+        self.set_batch_size(len(batch["rewards"]))
+        B = self.B
         g = lambda k: t.as_tensor(np.asarray(batch[k]) if not t.is_tensor(batch[k]) else batch[k], dtype=t.float32, device=self.device)
         self.Xp[:B].copy_(g("observations")); self.Xp[B:].copy_(g("next_observations"))
         self.act.copy_(g("actions")); self.rew.copy_(g("rewards").reshape(-1)); self.term.copy_(g("terminals").reshape(-1))
@@ -403,7 +612,7 @@ class SACTrainer:
         # inputs
         _chk(L.rsb_sac_prepare(_ptr(self.Xp), _ptr(self.act), _ptr(self.XQ), _ptr(self.XT), _ptr(self.sums), self.sums.numel(), _ptr(G["log_alpha"]), B, O, A, st))
         if not external_eps:
-            _chk(L.rsb_normal(C.c_uint64(self.seed), C.c_uint64(step_for_noise), 7, 2 * B * A, _ptr(self.eps), st))
+            _chk(L.rsb_normal(C.c_uint64(self.seed), C.c_uint64(step_for_noise), self.noise_stream, 2 * B * A, _ptr(self.eps), st))
         # policy forward on [obs; next_obs]
         mm = self._mm
         mm(self.Xp, P["p_W0"], self.H1p, bias=P["p_b0"], relu=True)
@@ -473,6 +682,8 @@ class SACTrainer:
         t = self.torch
         step = self._n_train_steps_total
         do_soft = (step % self.period) == 0
+        if self.B is None and batch is None:
+            raise RsbError("SACTrainer.train_step(): no batch size set (pass batch_size= or call set_batch_size)")
         old = t.backends.cuda.matmul.allow_tf32
         t.backends.cuda.matmul.allow_tf32 = self.tf32
         try:
@@ -484,7 +695,7 @@ class SACTrainer:
                 self.eps.copy_(t.as_tensor(eps, dtype=t.float32, device=self.device).reshape(self.eps.shape))
             if self.use_graph and batch is None and eps is None:
                 # the replay `size` argument is baked into a captured launch: sampling stays outside the graphs
-                _chk(self.L.rsb_normal(C.c_uint64(self.seed), C.c_uint64(step), 7, self.eps.numel(), _ptr(self.eps), _stream(self.device)))
+                _chk(self.L.rsb_normal(C.c_uint64(self.seed), C.c_uint64(step), self.noise_stream, self.eps.numel(), _ptr(self.eps), _stream(self.device)))
                 if self.world == 1:
                     # no collective between the gradients and the optimizer: body + Adam/Polyak are ONE graph per Polyak flavour
                     key = ("update", do_soft)

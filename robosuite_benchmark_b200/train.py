@@ -1,4 +1,6 @@
 """`python -m robosuite_benchmark_b200.train --variant V.json [--seed S] [--log_dir D] [--num_envs N]`
+`python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 -m robosuite_benchmark_b200.train --variant V.json --num_envs N`
+(data parallel: G ranks x N envs, one replay shard per rank, gradients averaged over the ranks every update; rank 0 logs)
 
 The reference's entry point (scripts/train.py:25-133) on the batched backend: same `--variant` JSON schema
 (scripts/train.py:53-77; runs/*/variant.json), same log-directory naming ("{env}_{robots}_{controller}_SEED{seed}"), same outputs
@@ -50,7 +52,8 @@ def build_parser():
     p.add_argument("--replay_buffer_size", type=int, default=int(1e6))
     # batched backend
     p.add_argument("--num_envs", type=int, default=1, help="environments stepped together on the GPU (1 = the reference's data flow)")
-    p.add_argument("--device", type=str, default="cuda:0")
+    p.add_argument("--device", type=str, default=None, help="default: cuda:LOCAL_RANK (one process per GPU under torchrun)")
+    p.add_argument("--gemm", type=str, default="tcgen05", choices=["tcgen05", "cublas", "cublas_fp32"], help="GEMM back-end of the SAC update")
     return p
 
 
@@ -87,13 +90,18 @@ def run_experiment(args):
     ek = variant["expl_environment_kwargs"]
     tmp_file_prefix = "{}_{}_{}_SEED{}".format(ek["env_name"], "".join(ek["robots"]), ek["controller"], args.seed)
     stamp = datetime.datetime.now().strftime("%Y_%m_%d_%H_%M_%S")
-    log_dir = os.path.join(args.log_dir, tmp_file_prefix, f"{tmp_file_prefix}_{stamp}_0000--s-0")
+    log_dir = os.path.join(args.log_dir, tmp_file_prefix, f"{tmp_file_prefix}_{stamp}_0000--s-0")     # written by rank 0 only
     np.random.seed(args.seed)                         # scripts/train.py:112-113 seeds from the flag, not from variant["seed"]
     import torch
     torch.manual_seed(args.seed)
-    return experiment(variant, agent=variant.get("algorithm", "SAC"), num_envs=args.num_envs, device=args.device, log_dir=log_dir, seed=args.seed), log_dir
+    return experiment(variant, agent=variant.get("algorithm", "SAC"), num_envs=args.num_envs, device=args.device, log_dir=log_dir, seed=args.seed,
+                      gemm=args.gemm), log_dir
 
 
 if __name__ == "__main__":
     algo, log_dir = run_experiment(build_parser().parse_args())
-    print("logs:", log_dir)
+    if algo.rank == 0:
+        print("logs:", log_dir)
+    if algo.world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()

@@ -94,6 +94,18 @@ class EmuEnv:
     def set_solver(self, iters, ls_iters, tol):
         self.L.emu_set_solver(C.c_void_p(self.h), int(iters), int(ls_iters), C.c_float(tol))
 
+    def solver_option(self):
+        """(iterations, tolerance, ls_iterations, ls_tolerance) the device code runs with -- read from the model's <option>."""
+        out = (C.c_double * 4)()
+        self.L.emu_get_solver(C.c_void_p(self.h), out)
+        return int(out[0]), float(out[1]), int(out[2]), float(out[3])
+
+    def counters(self):
+        """(ncon overflow, nefc overflow, steps after done) event counters of the device code since emu_create."""
+        out = (C.c_uint * 3)()
+        self.L.emu_counters(C.c_void_p(self.h), out)
+        return tuple(int(v) for v in out)
+
     def raw_state(self):
         st = np.zeros(self.st_words, np.float32)
         self.L.emu_get_state(C.c_void_p(self.h), _p(st))

@@ -76,12 +76,15 @@ struct EmuEnv {
   }
 };
 
+static unsigned int g_counters[8];
+
 extern "C" {
 
 void *emu_create(const rsb_model *m, const rsb_task *t, int ncon_max, int nefc_max) {
   EmuEnv *e = new EmuEnv();
   if (!rsb_build_host_model(m, t, ncon_max, nefc_max, e->hm)) { fprintf(stderr, "rsb_emu: %s\n", e->hm.error.c_str()); delete e; return nullptr; }
   e->dm = e->hm.dm; rsb_fixup_pointers(e->dm, e->hm.arena.data());
+  memset(g_counters, 0, sizeof g_counters); e->dm.counters = g_counters;
   e->smem.assign((size_t)e->dm.smem_words + 2 * GUARD, 0.0f); e->arm(); e->state.assign((size_t)e->dm.st_words, 0.0f);
   e->dbg.assign((size_t)RSB_DBG_WORDS(e->dm.nv, ncon_max, nefc_max), 0.0f);
   return e;
@@ -95,6 +98,9 @@ int emu_smem_words(void *h) { return ((EmuEnv *)h)->dm.smem_words; }
 int emu_state_words(void *h) { return ((EmuEnv *)h)->dm.st_words; }
 int emu_dbg_words(void *h) { return (int)((EmuEnv *)h)->dbg.size(); }
 void emu_set_ls_tol(void *h, float tol) { ((EmuEnv *)h)->dm.ls_tol = tol; }
+/* event counters of the device code (contact / constraint-row truncation, steps after done), cleared at emu_create */
+void emu_counters(void *h, unsigned int *out3) { (void)h; for (int k = 0; k < 3; k++) out3[k] = g_counters[k]; }
+void emu_get_solver(void *h, double *out4) { EmuEnv *e = (EmuEnv *)h; out4[0] = e->dm.solver_iters; out4[1] = e->dm.solver_tol; out4[2] = e->dm.ls_iters; out4[3] = e->dm.ls_tol; }
 void emu_set_solver(void *h, int iters, int ls_iters, float tol) { EmuEnv *e = (EmuEnv *)h; e->dm.solver_iters = iters; e->dm.ls_iters = ls_iters; e->dm.solver_tol = tol; }
 
 void emu_get_state(void *h, float *out) { EmuEnv *e = (EmuEnv *)h; memcpy(out, e->state.data(), e->state.size() * 4); }
@@ -110,7 +116,7 @@ int emu_step(void *h, const float *action, float *obs, float *reward) {
   EmuEnv *e = (EmuEnv *)h; unsigned char done = 0;
   if (g_do_fill) { std::fill(e->smem.begin(), e->smem.end(), g_fill); e->arm(); }
   emu_model = e->dm; emu_smem = e->slice();
-  run_group([&](int lane) { Grp g{lane, (RSB_LANES == 32) ? 0xffffffffu : ((1u << RSB_LANES) - 1u)}; env_step(0, g, e->state.data(), action, obs, reward, &done, true); });
+  run_group([&](int lane) { Grp g{lane, (RSB_LANES == 32) ? 0xffffffffu : ((1u << RSB_LANES) - 1u)}; env_step(0, g, e->state.data(), action, obs, nullptr, reward, &done, nullptr, true); });
   e->check_guards();
   return done;
 }

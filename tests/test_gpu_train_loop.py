@@ -40,28 +40,33 @@ def test_variant_json_trains_and_logs_reference_schema(tmp_path, num_envs):
     assert float(r0["exploration/num paths total"]) == 6.0 and float(r0["evaluation/num paths total"]) == 2.0
     assert np.float32(float(r0["trainer/Alpha"])) == np.float32(0.9990004897117615) and float(r0["trainer/Alpha Loss"]) == 0.0
     assert abs(float(r0["trainer/Log Pis Mean"]) + 0.67 * 7) < 0.6
-    snap = pickle.load(open(os.path.join(log_dir, "params.pkl"), "rb"))
+    from robosuite_benchmark_b200.sac import register_safe_globals
+    register_safe_globals()
+    snap = torch.load(os.path.join(log_dir, "params.pkl"))        # the reference's own way of reading it (util/rlkit_utils.py:173-174)
     assert sorted(snap) == sorted(["trainer/policy", "trainer/qf1", "trainer/qf2", "trainer/target_qf1", "trainer/target_qf2",
                                    "exploration/policy", "evaluation/policy"])
-    assert tuple(snap["trainer/policy"]["fc0.weight"].shape) == (256, 42) and tuple(snap["trainer/qf1"]["fc0.weight"].shape) == (256, 49)
+    assert tuple(snap["trainer/policy"].state_dict()["fc0.weight"].shape) == (256, 42) and tuple(snap["trainer/qf1"].state_dict()["fc0.weight"].shape) == (256, 49)
+    a, info = snap["evaluation/policy"].get_action(np.zeros(42))          # ... and of using it: a policy object with get_action
+    assert a.shape == (7,) and np.all(np.abs(a) <= 1.0) and info == {}
+    live = algo.trainer.policy.get_actions(torch.zeros(1, 42, device="cuda:0"), deterministic=True)[0].cpu().numpy()
+    assert np.abs(a - live).max() < 1e-6
     assert json.load(open(os.path.join(log_dir, "variant.json")))["trainer_kwargs"]["qf_lr"] == 0.0005
 
 
 @pytest.mark.gpu
 def test_rollout_cli_on_a_committed_variant(tmp_path):
     """scripts/rollout.py on the batched backend: a run directory with the reference's variant.json and a snapshot written by this
-    package's own _get_snapshot layout (state dicts) -> deterministic-policy returns; the untrained policy scores the logged
+    package's own _get_snapshot layout (torch-pickled network objects) -> deterministic-policy returns; the untrained policy scores the logged
     epoch-0 level (Lift-Panda-OSC_POSE zero/untrained-policy return ~3-20 over 500 steps)."""
     import json, os, pickle, shutil
     import torch
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
     from robosuite_benchmark_b200.rollout import main
-    from robosuite_benchmark_b200.sac import ParamStore, TanhGaussianPolicy
+    from robosuite_benchmark_b200.sac import MakeDeterministic, ParamStore, TanhGaussianPolicy
     here = os.path.dirname(__file__)
     shutil.copy(os.path.join(here, "golden", "variant_Lift-Panda-OSC-POSE-SEED17.json"), tmp_path / "variant.json")
     store = ParamStore(42, 7, torch.device("cuda", 0), seed=17)
-    with open(tmp_path / "params.pkl", "wb") as f:
-        pickle.dump({"evaluation/policy": TanhGaussianPolicy(store).state_dict()}, f)
+    torch.save({"evaluation/policy": MakeDeterministic(TanhGaussianPolicy.of(store))}, tmp_path / "params.pkl")
     rets = main(["--load_dir", str(tmp_path), "--num_episodes", "4", "--horizon", "100"])
     assert rets.shape == (4,) and np.isfinite(rets).all() and 0.0 < rets.mean() < 20.0

@@ -13,8 +13,8 @@ rb.add_batch(*(torch.as_tensor(x, device="cuda:0") for x in (rng.normal(size=(n,
              rng.uniform(0, 0.03, size=n).astype(np.float32), (rng.uniform(size=n) < 0.01).astype(np.uint8), rng.normal(size=(n, O)).astype(np.float32) * 0.5)))
 kw = dict(discount=0.99, reward_scale=1.0, policy_lr=1e-3, qf_lr=5e-4, soft_target_tau=0.005, target_update_period=5)
 sa, sb = ParamStore(O, A, "cuda:0", seed=3), ParamStore(O, A, "cuda:0", seed=3)
-ta = SACTrainer(store=sa, batch_size=B, tf32=True, use_graph=True, seed=5, parallel_branches=True, **kw); ta.replay = rb
-tb = SACTrainer(store=sb, batch_size=B, tf32=True, use_graph=False, seed=5, parallel_branches=False, **kw); tb.replay = rb
+ta = SACTrainer(store=sa, batch_size=B, gemm="tcgen05", use_graph=True, seed=5, parallel_branches=True, **kw); ta.replay = rb
+tb = SACTrainer(store=sb, batch_size=B, gemm="tcgen05", use_graph=False, seed=5, parallel_branches=False, **kw); tb.replay = rb
 worst = 0.0; bad = 0
 for step in range(int(sys.argv[1]) if len(sys.argv) > 1 else 600):
     for name in ("flat", "m", "v", "target"):
