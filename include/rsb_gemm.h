@@ -35,7 +35,7 @@ int rsb_gemm_timeouts(void);
 void rsb_gemm_debug_swap_offsets(int swap);
 /* diagnostic: force the number of CTAs (1, 2, 4) that share one tile of C along the contraction; 0 = choose */
 void rsb_gemm_debug_splits(int splits);
-/* diagnostic: SM clock of CTA (0,0,0) of the last launch at 12 points ([0] entry, [1] copies issued, [2] tensor memory ready, [3] first chunk landed,
+/* diagnostic: SM clock of CTA (0,0,0) of the last launch at 12 points ([0] entry, [1] tensor memory + barriers ready and the preceding kernel complete, [2] first copies issued, [3] first chunk landed,
    [4] products issued, [5] accumulator complete, [8] accumulator parked in shared memory, [9] CTA/cluster barrier passed, [10] C written, [6] cluster
    released, [7] exit; [11] unused); synchronises the device */
 int rsb_gemm_debug_clocks(long long *host_out12);

@@ -31,8 +31,38 @@ int rsb_head_fwd(const float *d_out, const float *d_eps, int rows, int act_dim, 
 int rsb_head_bwd(const float *d_out, const float *d_eps, const float *d_a, int rows, int batch, int act_dim, const float *d_alpha, const float *d_ga, int ld_ga, float *d_dout, void *stream);
 int rsb_sac_losses(const float *d_q, const float *d_qt, const float *d_logpi, const float *d_rew, const float *d_term, const float *d_alpha, float reward_scale, float discount,
                    float target_entropy, int batch, float *d_dq, float *d_y, float *d_sums, float *d_galpha, void *stream);
-int rsb_adam_polyak(float *d_p, const float *d_g, float *d_m, float *d_v, long n, double lr_pi, double lr_q, float b1, float b2, float eps, double *d_bc /* [4] = {0,0,1,1} at start */,
-                    float *d_tgt, long tgt_begin, long tgt_end, float tau, int do_soft, float *d_alpha, long log_alpha_idx, void *stream);
+/* Adam's bias corrections advance on the device (d_bc [4] = {1 - b1^t, sqrt(1 - b2^t), b1^t, b2^t}; {0,0,1,1} at start): rsb_adam_tick advances them by one
+   step (and, if given, increments the device-resident update counter); rsb_adam_polyak with tick != 0 does the tick itself first, with tick == 0 it
+   expects the caller to have ticked earlier in the same update (off the update's critical path). */
+int rsb_adam_tick(double *d_bc, float b1, float b2, int64_t *d_step_counter, void *stream);
+int rsb_adam_polyak(float *d_p, const float *d_g, float *d_m, float *d_v, long n, double lr_pi, double lr_q, float b1, float b2, float eps, double *d_bc,
+                    float *d_tgt, long tgt_begin, long tgt_end, float tau, int do_soft, float *d_alpha, long log_alpha_idx, int tick, void *stream);
+
+/* ---- fused narrow layers (csrc/rsb_sac_fused.cu): the policy's last layer, the Q networks' last layer and their input gradients are not
+   GEMM-shaped (2A <= 32 columns; one column); each is fused with the elementwise kernel next to it, exact fp32 on the CUDA cores.
+   d_h2 [rows, 256] hidden activations, d_w2 [256, 2A], d_b2 [2A]; the rest as rsb_head_fwd / rsb_head_bwd / rsb_sac_losses. */
+int rsb_policy_head_fwd(const float *d_h2, const float *d_w2, const float *d_b2, const float *d_eps, int rows, int act_dim, float *d_out, float *d_a, float *d_logpi,
+                        float *dst0, int ld0, int r0lo, int r0hi, float *dst1, int ld1, int r1lo, int r1hi, void *stream);
+/* d_h2q [2, 2B, 256] (rows [0,B): (obs, a_new); [B,2B): (obs, act)), d_wq2 [2, 256], d_bq2 [2]; d_h2t [2, B, 256], d_wt2 [2, 256], d_bt2 [2] (target nets);
+   writes q [2, 2B], qt [2, B], dq [2, 2B], dH2q [2, 2B, 256] = (dq w2^T) masked by H2q > 0, y [B], the loss sums and d alpha_loss / d log_alpha */
+int rsb_q_losses(const float *d_h2q, const float *d_wq2, const float *d_bq2, const float *d_h2t, const float *d_wt2, const float *d_bt2, const float *d_logpi,
+                 const float *d_rew, const float *d_term, const float *d_alpha, float reward_scale, float discount, float target_entropy, int batch,
+                 float *d_q, float *d_qt, float *d_dq, float *d_dh2q, float *d_y, float *d_sums, float *d_galpha, void *stream);
+/* rows [0, batch) only: d_dout [batch, 2A], d_dh2 [batch, 256] = (dOUT W2^T) masked by H2 > 0 */
+int rsb_policy_head_bwd(const float *d_out, const float *d_eps, const float *d_a, const float *d_h2, const float *d_w2, int batch, int act_dim, const float *d_alpha,
+                        const float *d_ga, int ld_ga, float *d_dout, float *d_dh2, void *stream);
+/* rsb_replay_sample / rsb_normal keyed by DEVICE-resident counters d_ctr = {filled ring rows, update counter} (int64 x 2): no argument of an update
+   changes on the host side, so sampling sits inside the captured graph of the update */
+int rsb_replay_sample_dev(const float *d_obs, const float *d_act, const float *d_rew, const uint8_t *d_term, const float *d_next, const int64_t *d_ctr, int obs_dim, int act_dim,
+                          uint64_t seed, int batch, float *b_obs, int ld_obs, float *b_act, float *b_rew, float *b_term, float *b_next, int ld_next, int *b_idx, void *stream);
+int rsb_normal_dev(uint64_t seed, const int64_t *d_ctr, uint32_t stream_id, int n, float *d_out, void *stream);
+int rsb_counter_add(int64_t *d_counter, int64_t delta, void *stream);
+/* the head of one update in ONE launch (= rsb_replay_sample_dev + rsb_normal_dev + rsb_sac_prepare): draws the batch from the ring (sample != 0; else the
+   batch already sits in d_xp / b_act / b_rew / b_term), lays it out as the update's inputs Xp [2B,O], XQ [2B,O+A], XT [B,O+A], clears the loss accumulators
+   and the log-alpha gradient, and draws the policy noise eps [2B, A] (noise != 0) under key (seed_noise, update counter, noise_stream) */
+int rsb_sac_begin(const float *d_obs, const float *d_act, const float *d_rew, const uint8_t *d_term, const float *d_next, const int64_t *d_ctr, int obs_dim, int act_dim,
+                  uint64_t seed_ring, int batch, int sample, float *d_xp, float *b_act, float *b_rew, float *b_term, int *b_idx, float *d_xq, float *d_xt,
+                  float *d_sums, int nsums, float *d_g_log_alpha, int noise, uint64_t seed_noise, uint32_t noise_stream, float *d_eps, void *stream);
 
 /* ---- collector (csrc/rsb_collect.cu): what rlkit's MdpPathCollector.collect_new_paths does per control step and per epoch
    (util/rlkit_custom.py:202,215,223 -> rollout -> TanhGaussianPolicy.get_action; statistics: util/rlkit_custom.py:244-301,315-377) */

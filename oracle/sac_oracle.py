@@ -79,27 +79,31 @@ def tf32_operand(x, mode):
 
 
 class _TF32MatMul(torch.autograd.Function):
-    """a @ b as the product path computes it: BOTH operands of EVERY product (forward, input gradient, weight gradient) are reduced to
-    TF32, products and sums are exact (fp64 here; fp32 accumulation on the device)."""
+    """a @ b as the product path computes it: the operands of a product that runs on the tensor cores are reduced to TF32, products and sums
+    are exact (fp64 here; fp32 accumulation on the device).  `which` = (forward, input gradient, weight gradient) says which of the three
+    products of this layer are tensor-core products: (True, True, True) for the 256-wide layers; (False, False, True) for the narrow last
+    layers, whose forward and input gradient run in exact fp32 inside the fused CUDA-core kernels (csrc/rsb_sac_fused.cu)."""
 
     @staticmethod
-    def forward(ctx, a, b, mode):
+    def forward(ctx, a, b, mode, which):
         ctx.save_for_backward(a, b)
-        ctx.mode = mode
-        return (tf32_operand(a, mode).double() @ tf32_operand(b, mode).double()).float()
+        ctx.mode, ctx.which = mode, which
+        r = (lambda x: tf32_operand(x, mode)) if which[0] else (lambda x: x.detach())
+        return (r(a).double() @ r(b).double()).float()
 
     @staticmethod
     def backward(ctx, g):
         a, b = ctx.saved_tensors
         m = ctx.mode
-        gt = tf32_operand(g, m).double()
-        ga = (gt @ tf32_operand(b, m).double().transpose(-1, -2)).float()
-        gb = (tf32_operand(a, m).double().transpose(-1, -2) @ gt).float()
+        ra = (lambda x: tf32_operand(x, m)) if ctx.which[1] else (lambda x: x.detach())
+        rb = (lambda x: tf32_operand(x, m)) if ctx.which[2] else (lambda x: x.detach())
+        ga = (ra(g).double() @ ra(b).double().transpose(-1, -2)).float()
+        gb = (rb(a).double().transpose(-1, -2) @ rb(g).double()).float()
         while gb.dim() > b.dim():
             gb = gb.sum(0)
         while ga.dim() > a.dim():
             ga = ga.sum(0)
-        return ga, gb, None
+        return ga, gb, None, None
 
 
 class SacOracle:
@@ -121,14 +125,15 @@ class SacOracle:
         self.opt_alpha = torch.optim.Adam([self.p["log_alpha"]], lr=policy_lr)
         self.n_steps, self.stats = 0, {}
 
-    def mm(self, a, b):
+    def mm(self, a, b, narrow=False):
+        """narrow: a last layer (256 -> 2A / 256 -> 1)."""
         if self.tf32 is None:
             return a @ b
-        return _TF32MatMul.apply(a, b, self.tf32)
+        return _TF32MatMul.apply(a, b, self.tf32, (False, False, True) if narrow else (True, True, True))
 
     def policy(self, obs, eps):
         p, A, mm = self.p, self.A, self.mm
-        h = F.relu(mm(obs, p["p_W0"]) + p["p_b0"]); h = F.relu(mm(h, p["p_W1"]) + p["p_b1"]); out = mm(h, p["p_W2"]) + p["p_b2"]
+        h = F.relu(mm(obs, p["p_W0"]) + p["p_b0"]); h = F.relu(mm(h, p["p_W1"]) + p["p_b1"]); out = mm(h, p["p_W2"], narrow=True) + p["p_b2"]
         mean, log_std = out[:, :A], out[:, A:].clamp(LOG_SIG_MIN, LOG_SIG_MAX)
         z = mean + log_std.exp() * eps
         a = torch.tanh(z)
@@ -139,7 +144,7 @@ class SacOracle:
         x = torch.cat([obs, act], 1)
         h = F.relu(self.mm(x.unsqueeze(0).expand(2, -1, -1), w["q_W0"]) + w["q_b0"][:, None, :])
         h = F.relu(self.mm(h, w["q_W1"]) + w["q_b1"][:, None, :])
-        return self.mm(h, w["q_W2"]) + w["q_b2"][:, None, :]                       # [2, B, 1]
+        return self.mm(h, w["q_W2"], narrow=True) + w["q_b2"][:, None, :]          # [2, B, 1]
 
     def train(self, batch, eps):
         """batch: dict of numpy arrays (rlkit keys); eps: [2B, A] -- rows [0,B) drive pi(obs), rows [B,2B) drive pi(next_obs)."""

@@ -87,8 +87,10 @@ class NormalizedBoxEnv:
         lb, ub = self._wrapped_env.action_space.low, self._wrapped_env.action_space.high
         if hasattr(action, "clamp"):                               # batched torch actions
             import torch
-            lo, hi = torch.as_tensor(lb, device=action.device), torch.as_tensor(ub, device=action.device)
-            scaled = torch.minimum(torch.maximum(lo + (action + 1.0) * 0.5 * (hi - lo), lo), hi).contiguous()
+            # in float64 like rlkit's numpy arithmetic: for robosuite's (-1, 1) bounds the map is then EXACTLY the identity on fp32 actions
+            # (in fp32, (a + 1) - 1 != a), which is what the fused collector assumes when it bypasses this wrapper
+            lo, hi = torch.as_tensor(lb, device=action.device, dtype=torch.float64), torch.as_tensor(ub, device=action.device, dtype=torch.float64)
+            scaled = torch.minimum(torch.maximum(lo + (action.double() + 1.0) * 0.5 * (hi - lo), lo), hi).float().contiguous()
         else:
             scaled = np.clip(lb + (np.asarray(action) + 1.0) * 0.5 * (ub - lb), lb, ub)
         o, r, d, info = self._wrapped_env.step(scaled)

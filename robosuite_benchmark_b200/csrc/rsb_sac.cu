@@ -12,6 +12,7 @@
 #include <string>
 
 #include "../../include/rsb_sac.h"
+#include "rsb_pdl.h"
 
 static thread_local std::string g_sac_err;
 void rsb_sac_set_error(const char *msg) { g_sac_err = msg; }   /* shared with rsb_tc_gemm.cu */
@@ -34,6 +35,7 @@ __global__ void k_replay_sample(const float *__restrict__ obs, const float *__re
                                 int size, int O, int A, uint64_t seed, uint64_t step, int B,
                                 float *__restrict__ b_obs, float *__restrict__ b_act, float *__restrict__ b_rew, float *__restrict__ b_term,
                                 float *__restrict__ b_next, int *__restrict__ b_idx, int ld_obs, int ld_next) {
+  pdl_wait(); pdl_trigger();                /* rsb_pdl.h: everything above is independent of earlier kernels */
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= B) return;
   uint32_t c[4] = {(uint32_t)row, (uint32_t)step, (uint32_t)(step >> 32), 0xB0FFE7u};
@@ -47,6 +49,7 @@ __global__ void k_replay_sample(const float *__restrict__ obs, const float *__re
 
 /* ---------------------------------------------------------------- N(0,1) noise, Philox keyed (seed, step, stream)  */
 __global__ void k_normal(uint64_t seed, uint64_t step, uint32_t stream, int n, float *__restrict__ out) {
+  pdl_wait(); pdl_trigger();                /* rsb_pdl.h: everything above is independent of earlier kernels */
   int i = blockIdx.x * blockDim.x + threadIdx.x;               /* one thread -> 4 values */
   if (4 * i >= n) return;
   uint32_t c[4] = {(uint32_t)i, (uint32_t)step, (uint32_t)(step >> 32), stream};
@@ -63,6 +66,7 @@ __global__ void k_normal(uint64_t seed, uint64_t step, uint32_t stream, int n, f
 
 /* ---------------------------------------------------------------- bias + ReLU (in place), row-major [rows, cols] */
 __global__ void k_bias_relu(float *__restrict__ x, const float *__restrict__ bias, int rows, int cols, int relu, int nmat, long mat_stride, int bias_stride) {
+  pdl_wait(); pdl_trigger();                /* rsb_pdl.h: everything above is independent of earlier kernels */
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x; long per = (long)rows * cols;
   if (i >= per * nmat) return;
   int mt = (int)(i / per); long r = i - (long)mt * per; int c = (int)(r % cols);
@@ -71,12 +75,14 @@ __global__ void k_bias_relu(float *__restrict__ x, const float *__restrict__ bia
 }
 /* dZ = dY * (Y > 0)  (in place on dY) */
 __global__ void k_relu_bwd(float *__restrict__ dy, const float *__restrict__ y, long n) {
+  pdl_wait(); pdl_trigger();                /* rsb_pdl.h: everything above is independent of earlier kernels */
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dy[i] = y[i] > 0.0f ? dy[i] : 0.0f;
 }
 /* column sums of dY [rows, cols] rows in [r0, r1) -> db[cols].  Block = 32 columns x 32 row slices: thread (x, y) adds rows r0+y, r0+y+32, ...
    (independent coalesced loads, 4 in flight), the 32 slice sums of a column are added in slice order through shared memory (deterministic).
    A thread per column walking all rows is a chain of (r1-r0) dependent-latency loads: 10-16 us at 128 rows, on the tail of every update. */
 __global__ void __launch_bounds__(1024) k_colsum(const float *__restrict__ dy, int r0, int r1, int cols, float *__restrict__ db, int nmat, long mat_stride, int db_stride) {
+  pdl_wait(); pdl_trigger();                /* rsb_pdl.h: everything above is independent of earlier kernels */
   __shared__ float s[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x, mt = blockIdx.y;
   float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
@@ -107,6 +113,7 @@ __global__ void __launch_bounds__(1024) k_colsum(const float *__restrict__ dy, i
 __global__ void k_head_fwd(const float *__restrict__ out, const float *__restrict__ eps, int R, int A,
                            float *__restrict__ a_store, float *__restrict__ logpi,
                            float *__restrict__ dst0, int ld0, int row0_lo, int row0_hi, float *__restrict__ dst1, int ld1, int row1_lo, int row1_hi) {
+  pdl_wait(); pdl_trigger();                /* rsb_pdl.h: everything above is independent of earlier kernels */
   int r = blockIdx.x * blockDim.x + threadIdx.x; if (r >= R) return;
   float lp = 0;
   for (int d = 0; d < A; d++) {
@@ -123,6 +130,7 @@ __global__ void k_head_fwd(const float *__restrict__ out, const float *__restric
    (the action columns of d(Q input)).  d_out [R, 2A] is fully written (rows >= B get zero: next_obs rows carry no gradient). */
 __global__ void k_head_bwd(const float *__restrict__ out, const float *__restrict__ eps, const float *__restrict__ a_store, int R, int B, int A,
                            const float *__restrict__ alpha, float inv_B, const float *__restrict__ g_a, int ld_ga, float *__restrict__ d_out) {
+  pdl_wait(); pdl_trigger();                /* rsb_pdl.h: everything above is independent of earlier kernels */
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= R * A) return;
   int r = i / A, d = i - r * A; float dmu = 0, dls = 0;
   if (r < B) {
@@ -144,6 +152,7 @@ __global__ void k_losses(const float *__restrict__ q, const float *__restrict__ 
                          const float *__restrict__ rew, const float *__restrict__ term, const float *__restrict__ alpha_logalpha /* [alpha, log_alpha] */,
                          float reward_scale, float discount, float target_entropy, int B, float *__restrict__ dq, float *__restrict__ ytarget,
                          float *__restrict__ sums, float *__restrict__ galpha) {
+  pdl_wait(); pdl_trigger();                /* rsb_pdl.h: everything above is independent of earlier kernels */
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l1 = 0, l2 = 0, lp = 0, la = 0, mlp = 0, my = 0, ga = 0;
   if (b < B) {
@@ -175,6 +184,7 @@ __global__ void k_adam_polyak(float *__restrict__ p, const float *__restrict__ g
                               double lr_pi, double lr_q, float b1, float b2, float eps, const double *__restrict__ bc /* [1-b1^t, sqrt(1-b2^t), b1^t, b2^t] */,
                               float *__restrict__ tgt, long tgt_begin, long tgt_end, float tau, int do_soft,
                               float *__restrict__ alpha_out /* [alpha, log_alpha] refreshed from p[log_alpha_idx] */, long log_alpha_idx) {
+  pdl_wait(); pdl_trigger();                /* rsb_pdl.h: everything above is independent of earlier kernels */
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
   const bool isq = i >= tgt_begin && i < tgt_end;
   /* torch.optim.Adam keeps step_size = lr / bias_correction1 and sqrt(bias_correction2) as Python doubles, cast to fp32 at use */
@@ -185,14 +195,17 @@ __global__ void k_adam_polyak(float *__restrict__ p, const float *__restrict__ g
   if (i == log_alpha_idx) { alpha_out[1] = pi; alpha_out[0] = (float)exp((double)pi); }      /* correctly rounded, like torch's CPU exp */
 }
 /* bias corrections advance on the device so the whole update is graph-replayable */
-__global__ void k_adam_tick(double *__restrict__ bc, double b1, double b2) {
+__global__ void k_adam_tick(double *__restrict__ bc, double b1, double b2, long long *__restrict__ step_counter) {
+  pdl_wait(); pdl_trigger();                /* rsb_pdl.h: everything above is independent of earlier kernels */
   double p1 = bc[2] * b1, p2 = bc[3] * b2; bc[2] = p1; bc[3] = p2; bc[0] = 1.0 - p1; bc[1] = sqrt(1.0 - p2);
+  if (step_counter) step_counter[0] += 1;    /* the update counter that keys the NEXT update's replay indices and policy noise (rsb_replay_sample_dev) */
 }
 
 /* Inputs of the update from the sampled batch, in one launch: XQ[2B, O+A] = [(obs, .) ; (obs, act)] (the first B action slots are filled by
    the policy head later), XT[B, O+A] = (next_obs, .), and the loss accumulators cleared.  Xp[2B, O] = [obs ; next_obs] as sampled. */
 __global__ void k_sac_prepare(const float *__restrict__ Xp, const float *__restrict__ act, float *__restrict__ XQ, float *__restrict__ XT,
                               float *__restrict__ sums, int nsums, float *__restrict__ g_log_alpha, int B, int O, int A) {
+  pdl_wait(); pdl_trigger();                /* rsb_pdl.h: everything above is independent of earlier kernels */
   const int QI = O + A, i = blockIdx.x * blockDim.x + threadIdx.x, n = 2 * B * QI;
   if (i < nsums) sums[i] = 0.0f;
   if (i == 0) g_log_alpha[0] = 0.0f;
@@ -207,40 +220,43 @@ extern "C" {
 const char *rsb_sac_last_error(void) { return g_sac_err.c_str(); }
 int rsb_sac_prepare(const float *d_xp, const float *d_act, float *d_xq, float *d_xt, float *d_sums, int nsums, float *d_g_log_alpha, int batch, int obs_dim, int act_dim, void *stream) {
   int n = 2 * batch * (obs_dim + act_dim); if (n < nsums) n = nsums;
-  k_sac_prepare<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_xp, d_act, d_xq, d_xt, d_sums, nsums, d_g_log_alpha, batch, obs_dim, act_dim); CKS(cudaGetLastError()); return 0;
+  CKS(rsb_launch_pdl(k_sac_prepare, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, 1, d_xp, d_act, d_xq, d_xt, d_sums, nsums, d_g_log_alpha, batch, obs_dim, act_dim)); return 0;
 }
 
 int rsb_replay_sample(const float *d_obs, const float *d_act, const float *d_rew, const uint8_t *d_term, const float *d_next, int size, int obs_dim, int act_dim,
                       uint64_t seed, uint64_t step, int batch, float *b_obs, int ld_obs, float *b_act, float *b_rew, float *b_term, float *b_next, int ld_next, int *b_idx, void *stream) {
   if (size <= 0 || batch <= 0) { g_sac_err = "replay_sample: empty buffer or batch"; return 2; }
   int threads = 128, blocks = (batch * 32 + threads - 1) / threads;
-  k_replay_sample<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_obs, d_act, d_rew, d_term, d_next, size, obs_dim, act_dim, seed, step, batch, b_obs, b_act, b_rew, b_term, b_next, b_idx, ld_obs, ld_next);
-  CKS(cudaGetLastError()); return 0;
+  CKS(rsb_launch_pdl(k_replay_sample, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, 1, d_obs, d_act, d_rew, d_term, d_next, size, obs_dim, act_dim, seed, step, batch, b_obs, b_act, b_rew, b_term, b_next, b_idx, ld_obs, ld_next));
+  return 0;
 }
 int rsb_normal(uint64_t seed, uint64_t step, uint32_t stream_id, int n, float *d_out, void *stream) {
-  int t = (n + 3) / 4; k_normal<<<(t + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, step, stream_id, n, d_out); CKS(cudaGetLastError()); return 0;
+  int t = (n + 3) / 4; CKS(rsb_launch_pdl(k_normal, dim3((t + 127) / 128), dim3(128), 0, (cudaStream_t)stream, 1, seed, step, stream_id, n, d_out)); return 0;
 }
 int rsb_bias_relu(float *d_x, const float *d_bias, int rows, int cols, int relu, int nmat, long mat_stride, int bias_stride, void *stream) {
-  long n = (long)rows * cols * nmat; k_bias_relu<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_bias, rows, cols, relu, nmat, mat_stride, bias_stride); CKS(cudaGetLastError()); return 0;
+  long n = (long)rows * cols * nmat; CKS(rsb_launch_pdl(k_bias_relu, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 1, d_x, d_bias, rows, cols, relu, nmat, mat_stride, bias_stride)); return 0;
 }
-int rsb_relu_bwd(float *d_dy, const float *d_y, long n, void *stream) { k_relu_bwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_dy, d_y, n); CKS(cudaGetLastError()); return 0; }
+int rsb_relu_bwd(float *d_dy, const float *d_y, long n, void *stream) { CKS(rsb_launch_pdl(k_relu_bwd, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 1, d_dy, d_y, n)); return 0; }
 int rsb_colsum(const float *d_dy, int r0, int r1, int cols, float *d_db, int nmat, long mat_stride, int db_stride, void *stream) {
-  dim3 grid((cols + 31) / 32, nmat); k_colsum<<<grid, dim3(32, 32), 0, (cudaStream_t)stream>>>(d_dy, r0, r1, cols, d_db, nmat, mat_stride, db_stride); CKS(cudaGetLastError()); return 0;
+  dim3 grid((cols + 31) / 32, nmat); CKS(rsb_launch_pdl(k_colsum, grid, dim3(32, 32), 0, (cudaStream_t)stream, 1, d_dy, r0, r1, cols, d_db, nmat, mat_stride, db_stride)); return 0;
 }
 int rsb_head_fwd(const float *d_out, const float *d_eps, int rows, int act_dim, float *d_a, float *d_logpi, float *dst0, int ld0, int r0lo, int r0hi, float *dst1, int ld1, int r1lo, int r1hi, void *stream) {
-  k_head_fwd<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_out, d_eps, rows, act_dim, d_a, d_logpi, dst0, ld0, r0lo, r0hi, dst1, ld1, r1lo, r1hi); CKS(cudaGetLastError()); return 0;
+  CKS(rsb_launch_pdl(k_head_fwd, dim3((rows + 127) / 128), dim3(128), 0, (cudaStream_t)stream, 1, d_out, d_eps, rows, act_dim, d_a, d_logpi, dst0, ld0, r0lo, r0hi, dst1, ld1, r1lo, r1hi)); return 0;
 }
 int rsb_head_bwd(const float *d_out, const float *d_eps, const float *d_a, int rows, int batch, int act_dim, const float *d_alpha, const float *d_ga, int ld_ga, float *d_dout, void *stream) {
-  int n = rows * act_dim; k_head_bwd<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_out, d_eps, d_a, rows, batch, act_dim, d_alpha, 1.0f / (float)batch, d_ga, ld_ga, d_dout); CKS(cudaGetLastError()); return 0;
+  int n = rows * act_dim; CKS(rsb_launch_pdl(k_head_bwd, dim3((n + 127) / 128), dim3(128), 0, (cudaStream_t)stream, 1, d_out, d_eps, d_a, rows, batch, act_dim, d_alpha, 1.0f / (float)batch, d_ga, ld_ga, d_dout)); return 0;
 }
 int rsb_sac_losses(const float *d_q, const float *d_qt, const float *d_logpi, const float *d_rew, const float *d_term, const float *d_alpha, float reward_scale, float discount,
                    float target_entropy, int batch, float *d_dq, float *d_y, float *d_sums, float *d_galpha, void *stream) {
-  k_losses<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_q, d_qt, d_logpi, d_rew, d_term, d_alpha, reward_scale, discount, target_entropy, batch, d_dq, d_y, d_sums, d_galpha); CKS(cudaGetLastError()); return 0;
+  CKS(rsb_launch_pdl(k_losses, dim3((batch + 127) / 128), dim3(128), 0, (cudaStream_t)stream, 1, d_q, d_qt, d_logpi, d_rew, d_term, d_alpha, reward_scale, discount, target_entropy, batch, d_dq, d_y, d_sums, d_galpha)); return 0;
+}
+int rsb_adam_tick(double *d_bc, float b1, float b2, int64_t *d_step_counter, void *stream) {
+  CKS(rsb_launch_pdl(k_adam_tick, dim3(1), dim3(1), 0, (cudaStream_t)stream, 1, d_bc, (double)b1, (double)b2, (long long *)d_step_counter)); return 0;
 }
 int rsb_adam_polyak(float *d_p, const float *d_g, float *d_m, float *d_v, long n, double lr_pi, double lr_q, float b1, float b2, float eps, double *d_bc,
-                    float *d_tgt, long tgt_begin, long tgt_end, float tau, int do_soft, float *d_alpha, long log_alpha_idx, void *stream) {
-  k_adam_tick<<<1, 1, 0, (cudaStream_t)stream>>>(d_bc, (double)b1, (double)b2);
-  k_adam_polyak<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_p, d_g, d_m, d_v, n, lr_pi, lr_q, b1, b2, eps, d_bc, d_tgt, tgt_begin, tgt_end, tau, do_soft, d_alpha, log_alpha_idx);
-  CKS(cudaGetLastError()); return 0;
+                    float *d_tgt, long tgt_begin, long tgt_end, float tau, int do_soft, float *d_alpha, long log_alpha_idx, int tick, void *stream) {
+  if (tick) CKS(rsb_launch_pdl(k_adam_tick, dim3(1), dim3(1), 0, (cudaStream_t)stream, 1, d_bc, (double)b1, (double)b2, (long long *)nullptr));
+  CKS(rsb_launch_pdl(k_adam_polyak, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 1, d_p, d_g, d_m, d_v, n, lr_pi, lr_q, b1, b2, eps, (const double *)d_bc, d_tgt, tgt_begin, tgt_end, tau, do_soft, d_alpha, log_alpha_idx));
+  return 0;
 }
 }

@@ -36,6 +36,7 @@
 
 #include "../../include/rsb_gemm.h"
 #include "../../include/rsb_sac.h"
+#include "rsb_pdl.h"
 
 void rsb_sac_set_error(const char *msg);   /* rsb_sac.cu: the string rsb_sac_last_error() returns */
 
@@ -133,16 +134,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
   const int mvalid = g.m - m0, nvalid = g.n - n0, nchunks = (klen + KC - 1) / KC;
 
   CLK(0);
-  /* the first S chunks go out before anything else: the copies fly while tensor memory is allocated and the barriers are set up */
-  for (int c = 0; c < S; c++) {
-    if (c < nchunks) {
-      load_tile(sbase + c * stage_bytes, a_at(kbeg + c * KC), g.a_rs, g.a_cs, BM, mvalid, klen - c * KC, a16);
-      load_tile(sbase + c * stage_bytes + A_BYTES, b_at(kbeg + c * KC), g.b_ns, g.b_ks, g.n_tile, nvalid, klen - c * KC, b16);
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-  }
-  CLK(1);
-  if (tid < g.n_tile) sbias[tid] = (g.bias && tid < nvalid) ? __ldg(g.bias + (long long)bz * g.bias_bs + n0 + tid) : 0.0f;
+  /* prologue that touches no data of an earlier kernel: tensor memory, barriers.  Launched with programmatic stream serialization
+     (rsb_pdl.h) this part runs while the PRECEDING kernel of the chain is still working. */
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tslot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
@@ -161,6 +154,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
   const uint32_t tmem = *tslot_p;
   /* split-K: tell the cluster that this CTA runs and its receive barrier is armed; waited for just before the first remote store */
   if (g.splits > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  pdl_wait();                                                   /* the producer of A / B / mask / C has completed */
+  pdl_trigger();
+  CLK(1);
+  /* the first S chunks */
+  for (int c = 0; c < S; c++) {
+    if (c < nchunks) {
+      load_tile(sbase + c * stage_bytes, a_at(kbeg + c * KC), g.a_rs, g.a_cs, BM, mvalid, klen - c * KC, a16);
+      load_tile(sbase + c * stage_bytes + A_BYTES, b_at(kbeg + c * KC), g.b_ns, g.b_ks, g.n_tile, nvalid, klen - c * KC, b16);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  if (tid < g.n_tile) sbias[tid] = (g.bias && tid < nvalid) ? __ldg(g.bias + (long long)bz * g.bias_bs + n0 + tid) : 0.0f;     /* read in the epilogue, after the chunk loop's CTA barriers */
   CLK(2);
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   const uint64_t desc_hi = ((uint64_t)g.lbo16 << 16) | ((uint64_t)g.sbo16 << 32) | (1ull << 46);
@@ -369,18 +374,7 @@ extern "C" int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, 
   g.splits = splits; g.cps = plan[2]; g.stages = plan[3]; g.recv_off = plan[4];
   const size_t smem_bytes = (size_t)plan[5];
   dim3 grid(plan[6], (m + BM - 1) / BM, batch);
-  if (splits == 1) {
-    k_gemm_tf32<<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(g);
-    e = cudaGetLastError();
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(NTHREADS, 1, 1); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = splits; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, k_gemm_tf32, g);
-  }
+  e = rsb_launch_pdl(k_gemm_tf32, grid, dim3(NTHREADS, 1, 1), smem_bytes, (cudaStream_t)stream, splits, g);
   if (e != cudaSuccess) { rsb_sac_set_error(cudaGetErrorString(e)); return 1; }
   return 0;
 }

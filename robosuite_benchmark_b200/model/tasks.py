@@ -21,7 +21,16 @@ OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89}
 #: default bounds of the per-env contact list / constraint-row list (shared-memory sizing; rsb_create ncon_max / nefc_max).
 #: Maxima seen over 300 random-action control steps x 2048 envs (tools/limits_stats.py): Stack 16 contacts / 54 rows, TwoArmLift 9 / 31,
 #: Door 4 / 18, Lift 9 / 29; TwoArmLift (24, 80) keeps 2.5x headroom and lets 14 envs share an SM (4096 envs = 2 waves instead of 3).
-LIMITS = {"Lift": (16, 64), "Door": (16, 64), "Stack": (24, 96), "TwoArmLift": (24, 80)}
+#: Round 2 (481 steps, limits 48 / 160, same tool): Lift-Sawyer reaches 20 contacts / 71 rows (the Rethink gripper's box fingers lie flat on
+#: the table) -- it gets its own entry; Lift-Panda 8 / 26, Stack-Sawyer 16 / 54, TwoArmLift 11 / 37, Door 4 / 17.  Truncation beyond these limits
+#: is COUNTED (RSB_INFO_NCON_OVERFLOW / NEFC_OVERFLOW): tests/test_gpu_collector.py asserts 0 events over a full random-action episode of 4096
+#: envs per family; a policy that presses the whole hand onto the table can exceed (16, 64) on Lift-Panda (measured: 6e-5 of the env-steps of
+#: an early training run) -- `suite.make(..., ncon_max=24, nefc_max=80)` removes that at the price of a second wave at 4096 envs per GPU.
+LIMITS = {"Lift": (16, 64), ("Lift", "Sawyer"): (24, 80), "Door": (16, 64), "Stack": (24, 96), "TwoArmLift": (24, 80)}
+
+
+def limits_for(env_name, robots):
+    return LIMITS.get((env_name, robots[0]), LIMITS[env_name])
 
 
 def _robot_desc(m: Model, pf: str, robot: str, cc: dict) -> dict:
@@ -106,7 +115,7 @@ def build_task(env_name: str, robots: Sequence[str], controller_config: dict, ho
                 ignore_done=int(bool(ignore_done)), reward_shaping=int(bool(reward_shaping)),
                 reward_scale=float(reward_scale), init_noise=0.02, table_height=A.TABLE_HEIGHT,
                 obs_dim=OBS_DIMS[env_name] if n_rob == (2 if env_name == "TwoArmLift" else 1) else None,
-                act_dim=act_dim, env_name=env_name, robots=list(robots), xml=xml, ncon_max=LIMITS[env_name][0], nefc_max=LIMITS[env_name][1])
+                act_dim=act_dim, env_name=env_name, robots=list(robots), xml=xml, ncon_max=limits_for(env_name, robots)[0], nefc_max=limits_for(env_name, robots)[1])
     task.update(objs(m))
     return m, task
 

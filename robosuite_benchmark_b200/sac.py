@@ -518,13 +518,16 @@ class SACTrainer:
         self.bc = torch.tensor([0.0, 0.0, 1.0, 1.0], dtype=torch.float64, device=self.device)
         self.alpha = torch.tensor([1.0, 0.0], **f32)                 # [alpha, log_alpha] (device copy read by the kernels)
         self.refresh_alpha()
+        self.ctr = torch.zeros(2, dtype=torch.int64, device=self.device)     # device-resident [filled ring rows, update counter]
+        self._ring_size_seen = -1
         self.B = None
         if batch_size is not None:
             self.set_batch_size(batch_size)
         self._graphs = {}
         # side streams: the target-Q forward and the weight-gradient GEMMs do not lie on the update's dependency chain; inside the captured
         # graph they become parallel branches (the update is launch-latency bound: ~55 kernels of 2-4 us each)
-        self._sT, self._sW, self._sB = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        self._sT, self._sB = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        self._sWs = [torch.cuda.Stream(self.device) for _ in range(3)]
         self.parallel_branches = bool(parallel_branches)          # False: everything on one stream (the reference order; tests compare the two)
 
     def refresh_alpha(self):
@@ -590,10 +593,21 @@ class SACTrainer:
         if mask is not None:
             self._relu_bwd(out, mask)
 
-    def _sample(self, step):
-        s = self.store
+    def _sync_ring_size(self):
+        """ctr[0] = filled rows of the replay ring (read by the in-graph sampling kernel); refreshed only when the ring grew."""
+        n = self.replay._size if self.replay is not None else 0
+        if n != self._ring_size_seen:
+            self.ctr[0:1].fill_(n)
+            self._ring_size_seen = n
+
+    def _sample(self):
+        """EnvReplayBuffer.random_batch (util/rlkit_custom.py:235) straight into the update's input buffers: row b takes ring row
+        mulhi(Philox(seed; b, update counter), size) -- size and counter are read from device memory (graph-capturable)."""
+        s, R = self.store, self.replay
         B, O = self.B, s.O
-        self.replay.sample_into(B, step, self.Xp, O, self.act, self.rew, self.term, self.Xp[B:], O, self.idx)
+        _chk(self.L.rsb_replay_sample_dev(_ptr(R._observations), _ptr(R._actions), _ptr(R._rewards), _ptr(R._terminals), _ptr(R._next_obs), _ptr(self.ctr),
+                                          R.obs_dim, R.action_dim, C.c_uint64(R.seed), B, _ptr(self.Xp), O, _ptr(self.act), _ptr(self.rew), _ptr(self.term),
+                                          C.c_void_p(self.Xp.data_ptr() + 4 * B * O), O, _ptr(self.idx), _stream(self.device)))
 
     def load_batch(self, batch):
         """Use an explicit batch (dict of tensors/arrays, rlkit keys) instead of sampling -- parity tests and `train(batch)`."""
@@ -604,51 +618,61 @@ class SACTrainer:
         self.Xp[:B].copy_(g("observations")); self.Xp[B:].copy_(g("next_observations"))
         self.act.copy_(g("actions")); self.rew.copy_(g("rewards").reshape(-1)); self.term.copy_(g("terminals").reshape(-1))
 
-    def _update_body(self, step_for_noise, do_soft, external_eps):
+    def _update_body(self, sample, noise, tick_early):
+        """Gradients of one update into the flat gradient buffer.  sample / noise: draw the batch / the policy noise here (device counters);
+        tick_early: advance Adam's bias corrections and the update counter on a side stream (the single-graph form: `_apply(tick=False)` follows)."""
         t, s, L, B = self.torch, self.store, self.L, self.B
         O, A, H, QI = s.O, s.A, s.H, s.O + s.A
         P, G, T = s.P, s.G, s.T
         st = _stream(self.device)
-        # inputs
-        _chk(L.rsb_sac_prepare(_ptr(self.Xp), _ptr(self.act), _ptr(self.XQ), _ptr(self.XT), _ptr(self.sums), self.sums.numel(), _ptr(G["log_alpha"]), B, O, A, st))
-        if not external_eps:
-            _chk(L.rsb_normal(C.c_uint64(self.seed), C.c_uint64(step_for_noise), self.noise_stream, 2 * B * A, _ptr(self.eps), st))
-        # policy forward on [obs; next_obs]
+        main = t.cuda.current_stream(self.device)
+        sT, sB = (self._sT, self._sB) if self.parallel_branches else (main, main)
+        sWs = self._sWs if self.parallel_branches else [main]
+        self._wi = 0
+        # head of the update in one kernel: batch rows from the ring (or the explicit batch already loaded), the update's input layout, cleared
+        # accumulators, policy noise -- all keyed by the device-resident counters
+        R = self.replay
+        ring = (_ptr(R._observations), _ptr(R._actions), _ptr(R._rewards), _ptr(R._terminals), _ptr(R._next_obs), C.c_uint64(R.seed)) if sample else (None,) * 5 + (C.c_uint64(0),)
+        _chk(L.rsb_sac_begin(ring[0], ring[1], ring[2], ring[3], ring[4], _ptr(self.ctr), O, A, ring[5], B, int(sample), _ptr(self.Xp), _ptr(self.act), _ptr(self.rew),
+                             _ptr(self.term), _ptr(self.idx), _ptr(self.XQ), _ptr(self.XT), _ptr(self.sums), self.sums.numel(), _ptr(G["log_alpha"]), int(noise),
+                             C.c_uint64(self.seed), self.noise_stream, _ptr(self.eps), st))
+        if tick_early:                               # after the kernel that reads the update counter; nothing else of the update reads what it writes before _apply
+            sB.wait_stream(main)
+            with t.cuda.stream(sB):
+                _chk(L.rsb_adam_tick(_ptr(self.bc), 0.9, 0.999, C.c_void_p(self.ctr.data_ptr() + 8), _stream(self.device)))
+        # policy forward on [obs; next_obs]: two tensor-core layers, then last layer + tanh-Gaussian head in one kernel; the actions go straight into
+        # the action columns of the Q inputs (rows [0, B) -> XQ, rows [B, 2B) -> XT)
         mm = self._mm
         mm(self.Xp, P["p_W0"], self.H1p, bias=P["p_b0"], relu=True)
         mm(self.H1p, P["p_W1"], self.H2p, bias=P["p_b1"], relu=True)
-        mm(self.H2p, P["p_W2"], self.OUT, bias=P["p_b2"])
-        _chk(L.rsb_head_fwd(_ptr(self.OUT), _ptr(self.eps), 2 * B, A, _ptr(self.a_store), _ptr(self.logpi),
-                            C.c_void_p(self.XQ.data_ptr() + 4 * O), QI, 0, B, C.c_void_p(self.XT.data_ptr() + 4 * O), QI, B, 2 * B, st))
-        # twin Q forward (batched over the two networks) on [(obs,a_new); (obs,act)]; target twin Q on (next_obs, a') on a side stream
+        _chk(L.rsb_policy_head_fwd(_ptr(self.H2p), _ptr(P["p_W2"]), _ptr(P["p_b2"]), _ptr(self.eps), 2 * B, A, _ptr(self.OUT), _ptr(self.a_store), _ptr(self.logpi),
+                                   C.c_void_p(self.XQ.data_ptr() + 4 * O), QI, 0, B, C.c_void_p(self.XT.data_ptr() + 4 * O), QI, B, 2 * B, st))
+        # twin Q hidden layers (batched over the two networks) on [(obs,a_new); (obs,act)]; the target nets' on (next_obs, a') on a side stream
         XQ2, XT2 = self.XQ.unsqueeze(0).expand(2, 2 * B, QI), self.XT.unsqueeze(0).expand(2, B, QI)
-        main = t.cuda.current_stream(self.device)
-        sT, sW, sB = (self._sT, self._sW, self._sB) if self.parallel_branches else (main, main, main)
         sT.wait_stream(main)
         with t.cuda.stream(sT):
             mm(XT2, T["q_W0"], self.H1t, bias=T["q_b0"], relu=True)
             mm(self.H1t, T["q_W1"], self.H2t, bias=T["q_b1"], relu=True)
-            mm(self.H2t, T["q_W2"], self.qt, bias=T["q_b2"])
         mm(XQ2, P["q_W0"], self.H1q, bias=P["q_b0"], relu=True)
         mm(self.H1q, P["q_W1"], self.H2q, bias=P["q_b1"], relu=True)
-        mm(self.H2q, P["q_W2"], self.q, bias=P["q_b2"])
         main.wait_stream(sT)
-        # losses and their gradients w.r.t. the Q outputs / log_alpha
-        _chk(L.rsb_sac_losses(_ptr(self.q), _ptr(self.qt), _ptr(self.logpi), _ptr(self.rew), _ptr(self.term), _ptr(self.alpha),
-                              self.reward_scale, self.discount, self.target_entropy, B, _ptr(self.dq), _ptr(self.y), _ptr(self.sums),
-                              _ptr(G["log_alpha"]), st))
+        # last Q layers (dot products), TD target, losses, dq and the gradient w.r.t. the second hidden layer: one kernel
+        _chk(L.rsb_q_losses(_ptr(self.H2q), _ptr(P["q_W2"]), _ptr(P["q_b2"]), _ptr(self.H2t), _ptr(T["q_W2"]), _ptr(T["q_b2"]), _ptr(self.logpi), _ptr(self.rew),
+                            _ptr(self.term), _ptr(self.alpha), self.reward_scale, self.discount, self.target_entropy, B, _ptr(self.q), _ptr(self.qt), _ptr(self.dq),
+                            _ptr(self.dH2q), _ptr(self.y), _ptr(self.sums), _ptr(G["log_alpha"]), st))
         # twin-Q backward: weight grads from the Bellman rows [B, 2B) only, input grads for the policy rows [0, B).  The input-gradient
-        # chain (dq -> dH2q -> dH1q -> gX -> policy head -> dH2p -> dH1p) runs on the main stream; every weight/bias gradient only needs the
-        # activation gradient of its own layer and goes to the side stream as soon as that exists.  `mask=` is the ReLU backward of the
+        # chain (dH2q -> dH1q -> gX -> policy head -> dH2p -> dH1p) runs on the main stream; every weight/bias gradient only needs the
+        # activation gradient of its own layer and goes to the side streams as soon as that exists.  `mask=` is the ReLU backward of the
         # layer that produced the mask tensor, fused into the product's epilogue.
-        def weight_grads(product, bias_sum):      # the weight-gradient product and the bias column sum of one layer: a side stream each
+        def weight_grads(product, bias_sum):      # the weight-gradient product and the bias column sum of one layer: off the chain, on side streams
+            sW = sWs[self._wi % len(sWs)]             # (the six products are independent of each other: round-robin over three streams, or the
+            self._wi += 1                             #  last ones queue up behind the first and end the update late)
             sW.wait_stream(main); sB.wait_stream(main)
             with t.cuda.stream(sW):
                 product()
             with t.cuda.stream(sB):
                 bias_sum()
         weight_grads(lambda: mm(self.H2q[:, B:].transpose(1, 2), self.dq[:, B:], G["q_W2"]), lambda: self._colsum(self.dq, B, 2 * B, G["q_b2"], 2))
-        mm(self.dq, P["q_W2"].transpose(1, 2), self.dH2q, mask=self.H2q)
         weight_grads(lambda: mm(self.H1q[:, B:].transpose(1, 2), self.dH2q[:, B:], G["q_W1"]), lambda: self._colsum(self.dH2q, B, 2 * B, G["q_b1"], 2))
         mm(self.dH2q, P["q_W1"].transpose(1, 2), self.dH1q, mask=self.H1q)
         weight_grads(lambda: mm(XQ2[:, B:].transpose(1, 2), self.dH1q[:, B:], G["q_W0"]), lambda: self._colsum(self.dH1q, B, 2 * B, G["q_b0"], 2))
@@ -656,21 +680,26 @@ class SACTrainer:
             gemm_tf32(self.dH1q[:, :B], P["q_W0"].transpose(1, 2), self.gX, stack_k=True)
         else:
             mm(self.dH1q[0, :B], P["q_W0"][0].t(), self.gX); mm(self.dH1q[1, :B], P["q_W0"][1].t(), self.gX, accumulate=True)
-        # policy backward
-        _chk(L.rsb_head_bwd(_ptr(self.OUT), _ptr(self.eps), _ptr(self.a_store), 2 * B, B, A, _ptr(self.alpha),
-                            C.c_void_p(self.gX.data_ptr() + 4 * O), QI, _ptr(self.dOUT), _stream(self.device)))
+        # policy backward: head backward + the last layer's input gradient in one kernel
+        _chk(L.rsb_policy_head_bwd(_ptr(self.OUT), _ptr(self.eps), _ptr(self.a_store), _ptr(self.H2p), _ptr(P["p_W2"]), B, A, _ptr(self.alpha),
+                                   C.c_void_p(self.gX.data_ptr() + 4 * O), QI, _ptr(self.dOUT), _ptr(self.dH2p), st))
         weight_grads(lambda: mm(self.H2p[:B].t(), self.dOUT[:B], G["p_W2"]), lambda: self._colsum(self.dOUT, 0, B, G["p_b2"]))
-        mm(self.dOUT[:B], P["p_W2"].t(), self.dH2p, mask=self.H2p[:B])
         weight_grads(lambda: mm(self.H1p[:B].t(), self.dH2p, G["p_W1"]), lambda: self._colsum(self.dH2p, 0, B, G["p_b1"]))
         mm(self.dH2p, P["p_W1"].t(), self.dH1p, mask=self.H1p[:B])
         weight_grads(lambda: mm(self.Xp[:B].t(), self.dH1p, G["p_W0"]), lambda: self._colsum(self.dH1p, 0, B, G["p_b0"]))
-        main.wait_stream(sW); main.wait_stream(sB)
+        for sW in sWs:
+            main.wait_stream(sW)
+        main.wait_stream(sB)
 
-    def _apply(self, do_soft):
+    def _apply(self, do_soft, tick=True, count=True):
+        """Adam on policy / Q1 / Q2 / log_alpha + Polyak in one kernel.  tick: advance the bias corrections first (unless `_update_body(tick_early=True)`
+        did); count: advance the device-resident update counter (the tick kernel does it in the tick_early form)."""
         s = self.store
         _chk(self.L.rsb_adam_polyak(_ptr(s.flat), _ptr(s.grad), _ptr(s.m), _ptr(s.v), s.n, self.policy_lr, self.qf_lr, 0.9, 0.999, 1e-8, _ptr(self.bc),
-                                    _ptr(s.target), s.q_begin, s.q_end, self.tau, int(do_soft), _ptr(self.alpha), s.offsets["log_alpha"],
+                                    _ptr(s.target), s.q_begin, s.q_end, self.tau, int(do_soft), _ptr(self.alpha), s.offsets["log_alpha"], int(tick),
                                     _stream(self.device)))
+        if count:
+            _chk(self.L.rsb_counter_add(C.c_void_p(self.ctr.data_ptr() + 8), 1, _stream(self.device)))
 
     def _allreduce(self):
         from .parallel import allreduce_mean_
@@ -678,7 +707,9 @@ class SACTrainer:
 
     # -- public
     def train_step(self, batch=None, eps=None):
-        """One SAC update.  batch=None samples from the replay ring with the Philox rule; `eps` overrides the policy noise."""
+        """One SAC update.  batch=None samples from the replay ring with the Philox rule; `eps` overrides the policy noise.
+        Without overrides the whole update -- sampling, noise, forward, backward, Adam, Polyak -- is ONE CUDA-graph replay (world size 1), or
+        graph / gradient all-reduce / graph (data parallel)."""
         t = self.torch
         step = self._n_train_steps_total
         do_soft = (step % self.period) == 0
@@ -687,45 +718,48 @@ class SACTrainer:
         old = t.backends.cuda.matmul.allow_tf32
         t.backends.cuda.matmul.allow_tf32 = self.tf32
         try:
+            sample = batch is None
             if batch is not None:
                 self.load_batch(batch)
             else:
-                self._sample(step)
+                self._sync_ring_size()
+                if self._ring_size_seen <= 0:
+                    raise RsbError("replay_sample: the replay ring is empty")
             if eps is not None:
                 self.eps.copy_(t.as_tensor(eps, dtype=t.float32, device=self.device).reshape(self.eps.shape))
-            if self.use_graph and batch is None and eps is None:
-                # the replay `size` argument is baked into a captured launch: sampling stays outside the graphs
-                _chk(self.L.rsb_normal(C.c_uint64(self.seed), C.c_uint64(step), self.noise_stream, self.eps.numel(), _ptr(self.eps), _stream(self.device)))
+            if self.use_graph and eps is None:
                 if self.world == 1:
                     # no collective between the gradients and the optimizer: body + Adam/Polyak are ONE graph per Polyak flavour
-                    key = ("update", do_soft)
+                    key = ("update", do_soft, sample)
                     if key not in self._graphs:
-                        self._warm(lambda: self._update_body(step, do_soft, True))
+                        self._warm(lambda: self._update_body(sample, True, False))
                         g = t.cuda.CUDAGraph()
                         with t.cuda.graph(g):
-                            self._update_body(0, do_soft, True)        # noise generated outside (its counter changes per step)
-                            self._apply(do_soft)
+                            self._update_body(sample, True, True)
+                            self._apply(do_soft, tick=False, count=False)
                         self._graphs[key] = g
                     self._graphs[key].replay()
                 else:
-                    key = "noise+body"
+                    key = ("body", sample)
                     if key not in self._graphs:
-                        self._warm(lambda: self._update_body(step, do_soft, True))
+                        self._warm(lambda: self._update_body(sample, True, False))
                         g = t.cuda.CUDAGraph()
                         with t.cuda.graph(g):
-                            self._update_body(0, do_soft, True)
+                            self._update_body(sample, True, False)
+                        self._graphs[key] = g
+                    if "apply" not in self._graphs:
                         ga, gb = t.cuda.CUDAGraph(), t.cuda.CUDAGraph()
                         with t.cuda.graph(ga):
                             self._apply(True)
                         with t.cuda.graph(gb):
                             self._apply(False)
-                        self._graphs[key] = (g, ga, gb)
-                    g, ga, gb = self._graphs[key]
-                    g.replay()
+                        self._graphs["apply"] = (ga, gb)
+                    self._graphs[key].replay()
                     self._allreduce()
+                    ga, gb = self._graphs["apply"]
                     (ga if do_soft else gb).replay()
             else:
-                self._update_body(step, do_soft, eps is not None)
+                self._update_body(sample, eps is None, False)
                 self._allreduce()
                 self._apply(do_soft)
         finally:

@@ -165,15 +165,16 @@ def test_reference_entry_point_resolves_on_compat_and_fails_loudly_without_a_gpu
     import json, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     from oracle import build_ref
-    refpy = build_ref.build() or os.path.join(root, "oracle", "_ref", "refpy")
-    if not os.path.exists(os.path.join(refpy, "scripts", "train.pyc")):
-        pytest.skip("neither /root/reference nor a built oracle/_ref/refpy here")
+    refpy = build_ref.build()
+    if not refpy or not os.path.exists(refpy):
+        pytest.skip("neither /root/reference nor a built oracle/_ref/refpy.bin here")
+    run_train = "import runpy; runpy.run_module('scripts.train', run_name='__main__', alter_sys=True)"
     if torch.cuda.is_available():
         pytest.skip("CUDA present: covered by the GPU drop-in test")
     v = json.load(open(os.path.join(root, "tests", "golden", "variant_Lift-Panda-OSC-POSE-SEED17.json")))
     json.dump(v, open(tmp_path / "v.json", "w"))
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "robosuite_benchmark_b200", "compat"), root, refpy]))
-    r = subprocess.run([sys.executable, os.path.join(refpy, "scripts", "train.pyc"), "--variant", str(tmp_path / "v.json"), "--seed", "17",
+    r = subprocess.run([sys.executable, "-c", run_train, "--variant", str(tmp_path / "v.json"), "--seed", "17",
                         "--log_dir", str(tmp_path / "log")], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "RsbError" in r.stderr and "CUDA device only" in r.stderr, r.stderr[-2000:]
     assert "ModuleNotFoundError" not in r.stderr and "ImportError" not in r.stderr

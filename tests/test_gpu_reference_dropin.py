@@ -3,8 +3,8 @@
 `scripts/train.py --variant V.json` of the reference -- unmodified, together with its unmodified util/rlkit_utils.py, util/rlkit_custom.py and
 util/arguments.py -- runs on this package: every `import robosuite / rlkit / gtimer` in those files resolves to
 robosuite_benchmark_b200/compat/, which re-exports the CUDA-backed implementation.  /root/reference does not exist on the GPU box, so the four
-files travel as byte-code built by oracle/build_ref.py into the git-ignored oracle/_ref/refpy/ (no reference source is copied into the repo);
-without that directory the test skips and says so.
+files travel as byte-code built by oracle/build_ref.py into the git-ignored archive oracle/_ref/refpy.bin (no reference source is copied into
+the repo); without that archive the test skips and says so.
 """
 import csv
 import glob
@@ -18,8 +18,11 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REFPY = os.path.join(ROOT, "oracle", "_ref", "refpy")
+REFPY = os.path.join(ROOT, "oracle", "_ref", "refpy.bin")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+RUN_TRAIN = "import runpy; runpy.run_module('scripts.train', run_name='__main__', alter_sys=True)"      # = python scripts/train.py, from the archive
 
 
 def _pythonpath():
@@ -30,8 +33,8 @@ def test_reference_train_script_runs_unmodified_on_this_backend(tmp_path):
     torch = pytest.importorskip("torch")
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
-    if not os.path.exists(os.path.join(REFPY, "scripts", "train.pyc")):
-        pytest.skip("oracle/_ref/refpy is absent (python oracle/build_ref.py builds it where /root/reference exists)")
+    if not os.path.exists(REFPY):
+        pytest.skip("oracle/_ref/refpy.bin is absent (python oracle/build_ref.py builds it where /root/reference exists)")
     v = json.load(open(os.path.join(GOLDEN, "variant_Lift-Panda-OSC-POSE-SEED17.json")))      # verbatim copy of the committed run's variant.json
     v["algorithm_kwargs"].update(num_epochs=2, num_eval_steps_per_epoch=40, num_expl_steps_per_train_loop=40, num_trains_per_train_loop=12,
                                  min_num_steps_before_training=80, expl_max_path_length=20, eval_max_path_length=20)
@@ -39,7 +42,7 @@ def test_reference_train_script_runs_unmodified_on_this_backend(tmp_path):
     vp = tmp_path / "variant.json"
     json.dump(v, open(vp, "w"))
     env = dict(os.environ, PYTHONPATH=_pythonpath())
-    r = subprocess.run([sys.executable, os.path.join(REFPY, "scripts", "train.pyc"), "--variant", str(vp), "--seed", "17", "--log_dir", str(tmp_path / "log")],
+    r = subprocess.run([sys.executable, "-c", RUN_TRAIN, "--variant", str(vp), "--seed", "17", "--log_dir", str(tmp_path / "log")],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "FINISHED TRAINING" in r.stdout and "Finished run!" in r.stdout            # util/rlkit_utils.py:165, scripts/train.py:133
