@@ -59,10 +59,12 @@ int rsb_normal_dev(uint64_t seed, const int64_t *d_ctr, uint32_t stream_id, int 
 int rsb_counter_add(int64_t *d_counter, int64_t delta, void *stream);
 /* the head of one update in ONE launch (= rsb_replay_sample_dev + rsb_normal_dev + rsb_sac_prepare): draws the batch from the ring (sample != 0; else the
    batch already sits in d_xp / b_act / b_rew / b_term), lays it out as the update's inputs Xp [2B,O], XQ [2B,O+A], XT [B,O+A], clears the loss accumulators
-   and the log-alpha gradient, and draws the policy noise eps [2B, A] (noise != 0) under key (seed_noise, update counter, noise_stream) */
+   and the log-alpha gradient, and draws the policy noise eps [2B, A] (noise != 0) under key (seed_noise, update counter, noise_stream).  nsums >= 8.
+   In data-parallel runs it is also where the rank waits until its peers have finished reading its gradient bucket of the previous update. */
 int rsb_sac_begin(const float *d_obs, const float *d_act, const float *d_rew, const uint8_t *d_term, const float *d_next, const int64_t *d_ctr, int obs_dim, int act_dim,
                   uint64_t seed_ring, int batch, int sample, float *d_xp, float *b_act, float *b_rew, float *b_term, int *b_idx, float *d_xq, float *d_xt,
-                  float *d_sums, int nsums, float *d_g_log_alpha, int noise, uint64_t seed_noise, uint32_t noise_stream, float *d_eps, void *stream);
+                  float *d_sums, int nsums, float *d_g_log_alpha, int noise, uint64_t seed_noise, uint32_t noise_stream, float *d_eps,
+                  uint32_t *const *d_dp_flags, const uint32_t *d_dp_local, int dp_rank, int dp_world /* data parallel (below); world <= 1: unused */, void *stream);
 
 /* ---- collector (csrc/rsb_collect.cu): what rlkit's MdpPathCollector.collect_new_paths does per control step and per epoch
    (util/rlkit_custom.py:202,215,223 -> rollout -> TanhGaussianPolicy.get_action; statistics: util/rlkit_custom.py:244-301,315-377) */
@@ -81,6 +83,17 @@ int rsb_policy_act(const float *d_W0, const float *d_b0, const float *d_W1, cons
    {sum, sum of squares, max, min} of: rewards (all T n), path returns (n), returns over the first expl_len steps (n), action entries (T n A). */
 int rsb_path_stats_words(int n);
 int rsb_path_stats(const float *d_rewards, const float *d_actions, int64_t slot0, int64_t cap, int n, int T, int act_dim, int expl_len, double *d_out, void *stream);
+
+/* ---- data parallel (csrc/rsb_dp.cu): the one collective of the path -- the mean of the flat gradient bucket over the ranks, once per update
+    -- fused into the optimizer kernel over NVLink peer memory.  d_peer_grads / d_peer_flags: DEVICE arrays [world] of device pointers to
+   every rank's gradient bucket / flag words (>= 32 uint32, zero at start) in symmetric memory (torch.distributed._symmetric_memory: buffer_ptrs_dev);
+   d_local: 4 private uint32 of this rank, zero at start.  All ranks must call these the same number of times.  Bounded waits: rsb_dp_timeouts()
+   returns (and clears) the number of waits that gave up -- 0 on a healthy run; it synchronises the device. */
+int rsb_dp_wait_peers_done(const float *const *d_peer_grads, uint32_t *const *d_peer_flags, uint32_t *d_local, int rank, int world, void *stream);
+int rsb_adam_polyak_allreduce(const float *const *d_peer_grads, uint32_t *const *d_peer_flags, uint32_t *d_local, int rank, int world,
+                              float *d_p, float *d_m, float *d_v, long n, double lr_pi, double lr_q, float b1, float b2, float eps, double *d_bc,
+                              float *d_tgt, long tgt_begin, long tgt_end, float tau, int do_soft, float *d_alpha, long log_alpha_idx, void *stream);
+int rsb_dp_timeouts(void);
 #ifdef __cplusplus
 }
 #endif

@@ -541,6 +541,9 @@ class BatchRLAlgorithm:
         n = gemm.timeouts()
         if n:
             raise RuntimeError(f"{n} mbarrier waits of the tcgen05 GEMM timed out during this epoch (results poisoned with NaN)")
+        n = self.trainer.dp_timeouts() if hasattr(self.trainer, "dp_timeouts") else 0
+        if n:
+            raise RuntimeError(f"{n} cross-rank waits of the fused gradient all-reduce timed out during this epoch (a rank is missing or stalled)")
         out = {}
         for name, env in (("exploration", self.expl_env), ("evaluation", self.eval_env)):
             sim = getattr(env, "sim", None)
@@ -624,7 +627,8 @@ def distributed_context():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def build_experiment(variant, agent="SAC", num_envs=1, device=None, log_dir=None, seed=None, gemm="tcgen05", rank=None, world_size=None, fused=True):
+def build_experiment(variant, agent="SAC", num_envs=1, device=None, log_dir=None, seed=None, gemm="tcgen05", rank=None, world_size=None, fused=True,
+                     allreduce="fused"):
     """util/rlkit_utils.py:31-165 on the batched backend -> the algorithm object, not yet run.
 
     num_envs = 1 reproduces the reference's single-env data flow (rlkit path dicts through the host entry points).  num_envs = N > 1 steps N
@@ -650,7 +654,7 @@ def build_experiment(variant, agent="SAC", num_envs=1, device=None, log_dir=None
     obs_dim, action_dim = expl_env.observation_space.low.size, expl_env.action_space.low.size
     assert list(variant["policy_kwargs"]["hidden_sizes"]) == [256, 256] and list(variant["qf_kwargs"]["hidden_sizes"]) == [256, 256], \
         "the fused update is built for the benchmark's 256x256 networks"
-    store = ParamStore(obs_dim, action_dim, device, seed=seed)                   # same seed on every rank: replicated parameters
+    store = ParamStore(obs_dim, action_dim, device, seed=seed, symmetric=world > 1 and allreduce == "fused")   # same seed on every rank: replicated parameters
     policy = TanhGaussianPolicy.of(store, seed=seed, env_id_base=rank * num_envs)
     eval_policy = TanhGaussianPolicy.of(store, seed=seed, env_id_base=(1 << 20) + rank * num_envs)
     replay = EnvReplayBuffer(max(1, variant["replay_buffer_size"] // world), expl_env, device=device, seed=seed + 7919 * rank)
@@ -659,7 +663,7 @@ def build_experiment(variant, agent="SAC", num_envs=1, device=None, log_dir=None
         for k in ("num_eval_steps_per_epoch", "num_expl_steps_per_train_loop", "min_num_steps_before_training"):
             ak[k] = -(-ak[k] // world)
     trainer = SACTrainer(env=eval_env, store=store, policy=policy, replay_buffer=replay, batch_size=ak["batch_size"], seed=seed, gemm=gemm,
-                         world_size=world, rank=rank, **variant["trainer_kwargs"])
+                         world_size=world, rank=rank, allreduce=allreduce, **variant["trainer_kwargs"])
     if num_envs == 1:
         expl_c, eval_c = MdpPathCollector(expl_env, policy), MdpPathCollector(eval_env, MakeDeterministic(eval_policy))
     elif fused:

@@ -18,7 +18,7 @@ _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_CSRC, "librsb_cuda.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
-CU_SOURCES = ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_sac.cu", "rsb_sac_fused.cu", "rsb_collect.cu", "rsb_tc_gemm.cu")
+CU_SOURCES = ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_sac.cu", "rsb_sac_fused.cu", "rsb_dp.cu", "rsb_collect.cu", "rsb_tc_gemm.cu")
 _LIB = None
 
 INFO = dict(nenvs=0, obs_dim=1, act_dim=2, state_words=3, smem_bytes=4, dbg_words=5, nq=6, nv=7, envs_per_block=8,
@@ -27,7 +27,7 @@ INFO = dict(nenvs=0, obs_dim=1, act_dim=2, state_words=3, smem_bytes=4, dbg_word
 
 
 def sources():
-    return [os.path.join(_CSRC, f) for f in ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_kernels.inl", "rsb_ktable.h", "rsb_sac.cu", "rsb_sac_fused.cu", "rsb_pdl.h", "rsb_collect.cu", "rsb_tc_gemm.cu", "rsb_dev.h", "rsb_devmodel.h")] + \
+    return [os.path.join(_CSRC, f) for f in ("rsb_cuda.cu", "rsb_cuda16.cu", "rsb_kernels.inl", "rsb_ktable.h", "rsb_sac.cu", "rsb_sac_fused.cu", "rsb_dp.cu", "rsb_pdl.h", "rsb_collect.cu", "rsb_tc_gemm.cu", "rsb_dev.h", "rsb_devmodel.h")] + \
            [os.path.join(_HERE, "..", "include", f) for f in ("rsb.h", "rsb_sac.h", "rsb_gemm.h", "rsb_model.h")]
 
 
@@ -87,7 +87,9 @@ def lib():
         L.rsb_replay_sample_dev.argtypes = [V, V, V, V, V, V, I, I, U64, I, V, I, V, V, V, V, I, V, V]
         L.rsb_normal_dev.argtypes = [U64, V, C.c_uint32, I, V, V]
         L.rsb_counter_add.argtypes = [V, C.c_int64, V]
-        L.rsb_sac_begin.argtypes = [V, V, V, V, V, V, I, I, U64, I, I, V, V, V, V, V, V, V, V, I, V, I, U64, C.c_uint32, V, V]
+        L.rsb_dp_wait_peers_done.argtypes = [V, V, V, I, I, V]
+        L.rsb_adam_polyak_allreduce.argtypes = [V, V, V, I, I, V, V, V, L_, C.c_double, C.c_double, F, F, F, V, V, L_, L_, F, I, V, L_, V]
+        L.rsb_sac_begin.argtypes = [V, V, V, V, V, V, I, I, U64, I, I, V, V, V, V, V, V, V, V, I, V, I, U64, C.c_uint32, V, V, V, I, I, V]
         L.rsb_gemm_tf32.argtypes = [V, L_, L_, L_, V, L_, L_, L_, V, L_, L_, I, I, I, I, V, L_, V, L_, L_, I, I, I, L_, L_, V]
         L.rsb_gemm_debug_swap_offsets.argtypes = [I]
         L.rsb_gemm_debug_swap_offsets.restype = None
@@ -102,7 +104,7 @@ EXPORTS = ["rsb_last_error", "rsb_sizeof_model", "rsb_sizeof_task", "rsb_create"
            "rsb_debug_substep", "rsb_reset_ring", "rsb_step_ring", "rsb_get_iters", "rsb_get_option", "rsb_clear_counters",
            "rsb_policy_act", "rsb_path_stats", "rsb_path_stats_words", "rsb_sac_last_error", "rsb_sac_prepare", "rsb_replay_sample", "rsb_normal", "rsb_bias_relu", "rsb_relu_bwd",
            "rsb_colsum", "rsb_head_fwd", "rsb_head_bwd", "rsb_sac_losses", "rsb_adam_polyak", "rsb_adam_tick", "rsb_policy_head_fwd", "rsb_q_losses",
-           "rsb_policy_head_bwd", "rsb_replay_sample_dev", "rsb_normal_dev", "rsb_counter_add", "rsb_sac_begin", "rsb_gemm_tf32", "rsb_gemm_timeouts",
+           "rsb_policy_head_bwd", "rsb_replay_sample_dev", "rsb_normal_dev", "rsb_counter_add", "rsb_sac_begin", "rsb_dp_wait_peers_done", "rsb_adam_polyak_allreduce", "rsb_dp_timeouts", "rsb_gemm_tf32", "rsb_gemm_timeouts",
            "rsb_gemm_debug_swap_offsets", "rsb_gemm_debug_clocks", "rsb_gemm_debug_splits", "rsb_gemm_plan"]
 
 

@@ -226,12 +226,26 @@ __global__ void k_sac_begin(const float *__restrict__ obs, const float *__restri
                             const float *__restrict__ next_obs, const long long *__restrict__ ctr, int O, int A, uint64_t seed_ring, int B, int sample,
                             float *__restrict__ Xp, float *__restrict__ act, float *__restrict__ rew, float *__restrict__ term, int *__restrict__ b_idx,
                             float *__restrict__ XQ, float *__restrict__ XT, float *__restrict__ sums, int nsums, float *__restrict__ g_log_alpha,
-                            int noise, uint64_t seed_noise, uint32_t noise_stream, float *__restrict__ eps) {
+                            int noise, uint64_t seed_noise, uint32_t noise_stream, float *__restrict__ eps,
+                            uint32_t *const *__restrict__ dp_flags, const uint32_t *__restrict__ dp_local, int dp_rank, int dp_world) {
   pdl_wait(); pdl_trigger();
   const int gid = blockIdx.x * blockDim.x + threadIdx.x, b = gid >> 5, lane = gid & 31, QI = O + A;
   const uint64_t step = (uint64_t)ctr[1];
   if (gid < nsums) sums[gid] = 0.0f;
-  if (gid == 0) g_log_alpha[0] = 0.0f;
+  if (gid == 0) {
+    /* data parallel (csrc/rsb_dp.cu): the gradient bucket -- g_log_alpha is its last word -- may be overwritten only after every peer has finished
+       reading it for the previous update; this is the first write of the new update, every other one comes in later kernels.  Flag word
+       [16 + r] of THIS rank's flags holds the last epoch rank r has finished reading; bounded wait. */
+    if (dp_world > 1) {
+      const uint32_t epoch = dp_local[0];
+      for (int r = 0; r < dp_world; r++) {
+        const uint32_t *f = dp_flags[dp_rank] + 16 + r; bool ok = false;
+        for (int it = 0; it < (1 << 24) && !ok; it++) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory"); ok = (int32_t)(v - epoch) >= 0; }
+        if (!ok) sums[7] = __int_as_float(0x7fc00000);             /* poisoned statistics word: a missing peer is visible in the log (and rsb_dp_timeouts of the optimizer kernel fires) */
+      }
+    }
+    g_log_alpha[0] = 0.0f;
+  }
   if (noise && 4 * gid < 2 * B * A) {                                   /* same arithmetic as k_normal */
     uint32_t c[4] = {(uint32_t)gid, (uint32_t)step, (uint32_t)(step >> 32), noise_stream};
     philox4(c, (uint32_t)seed_noise, (uint32_t)(seed_noise >> 32));
@@ -298,12 +312,15 @@ int rsb_normal_dev(uint64_t seed, const int64_t *d_ctr, uint32_t stream_id, int 
 }
 int rsb_sac_begin(const float *d_obs, const float *d_act, const float *d_rew, const uint8_t *d_term, const float *d_next, const int64_t *d_ctr, int obs_dim, int act_dim,
                   uint64_t seed_ring, int batch, int sample, float *d_xp, float *b_act, float *b_rew, float *b_term, int *b_idx, float *d_xq, float *d_xt,
-                  float *d_sums, int nsums, float *d_g_log_alpha, int noise, uint64_t seed_noise, uint32_t noise_stream, float *d_eps, void *stream) {
-  if (batch <= 0 || !d_ctr || nsums > 32 * batch) { rsb_sac_set_error("sac_begin: bad arguments"); return 2; }
+                  float *d_sums, int nsums, float *d_g_log_alpha, int noise, uint64_t seed_noise, uint32_t noise_stream, float *d_eps,
+                  uint32_t *const *d_dp_flags, const uint32_t *d_dp_local, int dp_rank, int dp_world, void *stream) {
+  if (batch <= 0 || !d_ctr || nsums > 32 * batch || nsums < 8) { rsb_sac_set_error("sac_begin: bad arguments"); return 2; }
+  if (dp_world > 1 && (!d_dp_flags || !d_dp_local || dp_rank < 0 || dp_rank >= dp_world)) { rsb_sac_set_error("sac_begin: bad data-parallel arguments"); return 2; }
   if (sample && (!d_obs || !d_act || !d_rew || !d_term || !d_next)) { rsb_sac_set_error("sac_begin: sampling needs the replay ring"); return 2; }
   const int threads = 128, blocks = (batch * 32 + threads - 1) / threads;       /* 32 B threads >= ceil(2 B A / 4) for A <= 64 */
   CKF(rsb_launch_pdl(k_sac_begin, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, 1, d_obs, d_act, d_rew, d_term, d_next, (const long long *)d_ctr, obs_dim, act_dim, seed_ring,
-                     batch, sample, d_xp, b_act, b_rew, b_term, b_idx, d_xq, d_xt, d_sums, nsums, d_g_log_alpha, noise, seed_noise, noise_stream, d_eps));
+                     batch, sample, d_xp, b_act, b_rew, b_term, b_idx, d_xq, d_xt, d_sums, nsums, d_g_log_alpha, noise, seed_noise, noise_stream, d_eps,
+                     d_dp_flags, d_dp_local, dp_rank, dp_world));
   return 0;
 }
 int rsb_counter_add(int64_t *d_counter, int64_t delta, void *stream) {

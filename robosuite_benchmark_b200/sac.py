@@ -159,9 +159,12 @@ def replay_indices_reference(seed, step, batch, size):
 class ParamStore:
     """Flat fp32 parameter / gradient / Adam-moment buffers and the views the GEMMs read."""
 
-    def __init__(self, obs_dim, act_dim, device, hidden=HID, seed=0, policy_init_w=1e-3, qf_init_w=3e-3, b_init=0.1):
+    def __init__(self, obs_dim, act_dim, device, hidden=HID, seed=0, policy_init_w=1e-3, qf_init_w=3e-3, b_init=0.1, symmetric=False):
+        """symmetric: allocate the gradient bucket in NVLink symmetric memory (data-parallel runs: every rank then reads every rank's bucket
+        directly, csrc/rsb_dp.cu); needs an initialised NCCL process group."""
         import torch
         self.torch, self.device = torch, torch.device(device)
+        self.symmetric = bool(symmetric)
         self.O, self.A, self.H = int(obs_dim), int(act_dim), int(hidden)
         O, A, H, QI = self.O, self.A, self.H, self.O + self.A
         shapes = OrderedDict([
@@ -175,7 +178,13 @@ class ParamStore:
         self.n = n
         self.q_begin, self.q_end = self.offsets["q_W0"], self.offsets["log_alpha"]
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.flat, self.grad = torch.zeros(n, **f32), torch.zeros(n, **f32)
+        self.flat = torch.zeros(n, **f32)
+        if self.symmetric:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.grad = symm_mem.empty(n, dtype=torch.float32, device=self.device)
+            self.grad.zero_()
+        else:
+            self.grad = torch.zeros(n, **f32)
         self.m, self.v = torch.zeros(n, **f32), torch.zeros(n, **f32)
         self.target = torch.zeros(self.q_end - self.q_begin, **f32)
         self.P, self.G, self.T = self._views(self.flat, 0), self._views(self.grad, 0), self._views(self.target, self.q_begin, only_q=True)
@@ -461,7 +470,7 @@ class SACTrainer:
                  policy_lr=1e-3, qf_lr=1e-3, optimizer_class=None, soft_target_tau=1e-2, target_update_period=1, plotter=None,
                  render_eval_paths=False, use_automatic_entropy_tuning=True, target_entropy=None, *, store: ParamStore = None,
                  replay_buffer: EnvReplayBuffer = None, batch_size=None, seed=0, use_graph=True, world_size=1, rank=0,
-                 parallel_branches=True, gemm="tcgen05", device=None):
+                 parallel_branches=True, gemm="tcgen05", device=None, allreduce="fused"):
         """Positional / keyword arguments up to `target_entropy` are rlkit's SACTrainer signature as the reference calls it
         (util/rlkit_utils.py:98-106); the keyword-only ones belong to this backend.  Networks built with the reference's constructors
         (unbound handles) are placed into ONE flat parameter store here; `store=` passes an existing one."""
@@ -510,6 +519,16 @@ class SACTrainer:
         self.gemm, self.tf32 = gemm, gemm != "cublas_fp32"
         # exploration-noise key of the update's reparameterised actions: the rank is folded in, so data-parallel ranks draw independent eps
         self.noise_stream = 7 + 16 * self.rank
+        # the one collective of the path (world > 1): "fused" = peer-memory reduction inside the optimizer kernel (csrc/rsb_dp.cu; the gradient bucket must
+        # be symmetric memory: ParamStore(symmetric=True)), "nccl" = dist.all_reduce between the gradient graph and the optimizer graph (comparison arm)
+        if allreduce not in ("fused", "nccl"):
+            raise ValueError(f"allreduce must be 'fused' or 'nccl', got {allreduce!r}")
+        self.allreduce = allreduce if self.world > 1 else "none"
+        self._dp = None
+        if self.allreduce == "fused":
+            if not getattr(store, "symmetric", False):
+                raise RsbError("allreduce='fused' needs ParamStore(symmetric=True) (gradient bucket in NVLink symmetric memory)")
+            self._dp = self._setup_dp()
         self._n_train_steps_total = 0
         self._need_to_update_eval_statistics = True
         self.eval_statistics = OrderedDict()
@@ -529,6 +548,27 @@ class SACTrainer:
         self._sT, self._sB = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
         self._sWs = [torch.cuda.Stream(self.device) for _ in range(3)]
         self.parallel_branches = bool(parallel_branches)          # False: everything on one stream (the reference order; tests compare the two)
+
+    def _setup_dp(self):
+        """Rendezvous of the symmetric buffers: every rank learns the device addresses of every rank's gradient bucket and flag words."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        try:
+            symm_mem.enable_symm_mem_for_group(dist.group.WORLD.group_name)      # needed on older torch; a no-op / deprecated on newer
+        except Exception:
+            pass
+        flags = symm_mem.empty(64, dtype=torch.int32, device=self.device)
+        flags.zero_()
+        hg = symm_mem.rendezvous(self.store.grad, dist.group.WORLD.group_name)
+        hf = symm_mem.rendezvous(flags, dist.group.WORLD.group_name)
+        local = torch.zeros(4, dtype=torch.int32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        dist.barrier()                                 # every rank's flag words are zero before anyone signals
+        return dict(flags=flags, hg=hg, hf=hf, local=local, grads_dev=C.c_void_p(hg.buffer_ptrs_dev), flags_dev=C.c_void_p(hf.buffer_ptrs_dev))
+
+    def dp_timeouts(self):
+        return int(self.L.rsb_dp_timeouts()) if self._dp is not None else 0
 
     def refresh_alpha(self):
         """[alpha, log_alpha] device copy from the store's log_alpha (after load_host / a checkpoint restore)."""
@@ -631,11 +671,12 @@ class SACTrainer:
         self._wi = 0
         # head of the update in one kernel: batch rows from the ring (or the explicit batch already loaded), the update's input layout, cleared
         # accumulators, policy noise -- all keyed by the device-resident counters
-        R = self.replay
+        R, dp = self.replay, self._dp                # (data parallel: this kernel also waits until the peers are done with the previous gradient bucket)
         ring = (_ptr(R._observations), _ptr(R._actions), _ptr(R._rewards), _ptr(R._terminals), _ptr(R._next_obs), C.c_uint64(R.seed)) if sample else (None,) * 5 + (C.c_uint64(0),)
         _chk(L.rsb_sac_begin(ring[0], ring[1], ring[2], ring[3], ring[4], _ptr(self.ctr), O, A, ring[5], B, int(sample), _ptr(self.Xp), _ptr(self.act), _ptr(self.rew),
                              _ptr(self.term), _ptr(self.idx), _ptr(self.XQ), _ptr(self.XT), _ptr(self.sums), self.sums.numel(), _ptr(G["log_alpha"]), int(noise),
-                             C.c_uint64(self.seed), self.noise_stream, _ptr(self.eps), st))
+                             C.c_uint64(self.seed), self.noise_stream, _ptr(self.eps),
+                             dp["flags_dev"] if dp else None, _ptr(dp["local"]) if dp else None, self.rank, self.world if dp else 0, st))
         if tick_early:                               # after the kernel that reads the update counter; nothing else of the update reads what it writes before _apply
             sB.wait_stream(main)
             with t.cuda.stream(sB):
@@ -701,6 +742,13 @@ class SACTrainer:
         if count:
             _chk(self.L.rsb_counter_add(C.c_void_p(self.ctr.data_ptr() + 8), 1, _stream(self.device)))
 
+    def _apply_allreduce(self, do_soft):
+        """Gradient mean over the ranks + Adam + Polyak in ONE kernel over NVLink peer memory (csrc/rsb_dp.cu); the caller ticked (tick_early)."""
+        s, d = self.store, self._dp
+        _chk(self.L.rsb_adam_polyak_allreduce(d["grads_dev"], d["flags_dev"], _ptr(d["local"]), self.rank, self.world, _ptr(s.flat), _ptr(s.m), _ptr(s.v), s.n,
+                                              self.policy_lr, self.qf_lr, 0.9, 0.999, 1e-8, _ptr(self.bc), _ptr(s.target), s.q_begin, s.q_end, self.tau, int(do_soft),
+                                              _ptr(self.alpha), s.offsets["log_alpha"], _stream(self.device)))
+
     def _allreduce(self):
         from .parallel import allreduce_mean_
         allreduce_mean_(self.store.grad, self.world)                # ONE flat bucket per update
@@ -728,15 +776,18 @@ class SACTrainer:
             if eps is not None:
                 self.eps.copy_(t.as_tensor(eps, dtype=t.float32, device=self.device).reshape(self.eps.shape))
             if self.use_graph and eps is None:
-                if self.world == 1:
-                    # no collective between the gradients and the optimizer: body + Adam/Polyak are ONE graph per Polyak flavour
+                if self.world == 1 or self._dp is not None:
+                    # no host-side collective between the gradients and the optimizer: body + (all-reduce +) Adam/Polyak are ONE graph per Polyak flavour
                     key = ("update", do_soft, sample)
                     if key not in self._graphs:
-                        self._warm(lambda: self._update_body(sample, True, False))
+                        self._warm(lambda: self._update_body(sample, True, False))       # (in data-parallel mode the body only READS peer flags: no rank waits here)
                         g = t.cuda.CUDAGraph()
                         with t.cuda.graph(g):
                             self._update_body(sample, True, True)
-                            self._apply(do_soft, tick=False, count=False)
+                            if self._dp is None:
+                                self._apply(do_soft, tick=False, count=False)
+                            else:
+                                self._apply_allreduce(do_soft)
                         self._graphs[key] = g
                     self._graphs[key].replay()
                 else:
@@ -758,6 +809,9 @@ class SACTrainer:
                     self._allreduce()
                     ga, gb = self._graphs["apply"]
                     (ga if do_soft else gb).replay()
+            elif self._dp is not None:
+                self._update_body(sample, eps is None, True)
+                self._apply_allreduce(do_soft)
             else:
                 self._update_body(sample, eps is None, False)
                 self._allreduce()

@@ -14,6 +14,15 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--updates", type=int, default=300)
     a = ap.parse_args()
-    out = bench.sac_bench(torch.device("cuda:0"), 42, 7, 1, 0, updates=a.updates)
-    for k, v in out.items():
-        print(k, json.dumps(v) if isinstance(v, dict) else v)
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    out = bench.sac_bench(dev, 42, 7, world, rank, updates=a.updates)
+    if rank == 0:
+        for k, v in out.items():
+            print(k, json.dumps(v) if isinstance(v, dict) else v)
+    if world > 1:
+        dist.destroy_process_group()
