@@ -33,6 +33,15 @@ int rsb_gemm_plan(int m, int n, int k, int batch, int n_tile, int force_splits, 
 int rsb_gemm_timeouts(void);
 /* diagnostic: exchange the two byte-offset fields of the shared-memory matrix descriptors (0 = as documented in csrc/rsb_tc_gemm.cu) */
 void rsb_gemm_debug_swap_offsets(int swap);
+/* diagnostic: operand staging.  An operand with one unit stride and every other stride a multiple of 16 bytes is staged by TMA (`cp.async.bulk.tensor`,
+   128-byte swizzle, one issuing thread): K-major when the contraction index is the contiguous one (activations, W^T), MN-major when the row / column index
+   is (X^T, weights stored [in, out]; needs a tile of >= 32 columns for B); anything else by the strided `cp.async` gather.  mode 0 forces the gather for
+   every operand, 1 / -1 = TMA where eligible (RSB_GEMM_TMA=0 in the environment also disables it); rsb_gemm_debug_last_tma: staging of the last launch,
+   A in bits 0-1, B in bits 2-3 (0 gather, 1 TMA K-major, 2 TMA MN-major).  All paths feed the same products in the same order: results are bit-identical
+   (tests/test_gpu_tc_gemm.py). */
+void rsb_gemm_debug_tma(int mode);
+void rsb_gemm_debug_mn_swap(int swap);    /* diagnostic: exchange the leading / stride byte offsets of the MN-major swizzled descriptor (0 = as documented in the kernel) */
+int rsb_gemm_debug_last_tma(void);
 /* diagnostic: force the number of CTAs (1, 2, 4) that share one tile of C along the contraction; 0 = choose */
 void rsb_gemm_debug_splits(int splits);
 /* diagnostic: SM clock of CTA (0,0,0) of the last launch at 12 points ([0] entry, [1] tensor memory + barriers ready and the preceding kernel complete, [2] first copies issued, [3] first chunk landed,

@@ -62,8 +62,8 @@ int rsb_counter_add(int64_t *d_counter, int64_t delta, void *stream);
    and the log-alpha gradient, and draws the policy noise eps [2B, A] (noise != 0) under key (seed_noise, update counter, noise_stream).  nsums >= 8.
    In data-parallel runs it is also where the rank waits until its peers have finished reading its gradient bucket of the previous update. */
 int rsb_sac_begin(const float *d_obs, const float *d_act, const float *d_rew, const uint8_t *d_term, const float *d_next, const int64_t *d_ctr, int obs_dim, int act_dim,
-                  uint64_t seed_ring, int batch, int sample, float *d_xp, float *b_act, float *b_rew, float *b_term, int *b_idx, float *d_xq, float *d_xt,
-                  float *d_sums, int nsums, float *d_g_log_alpha, int noise, uint64_t seed_noise, uint32_t noise_stream, float *d_eps,
+                  uint64_t seed_ring, int batch, int sample, float *d_xp, int ld_xp, float *b_act, float *b_rew, float *b_term, int *b_idx, float *d_xq, float *d_xt,
+                  int ld_xq /* row pitches of Xp and of XQ / XT in floats (>= O, >= O + A; multiples of 4 make them TMA-stageable GEMM operands) */, float *d_sums, int nsums, float *d_g_log_alpha, int noise, uint64_t seed_noise, uint32_t noise_stream, float *d_eps,
                   uint32_t *const *d_dp_flags, const uint32_t *d_dp_local, int dp_rank, int dp_world /* data parallel (below); world <= 1: unused */, void *stream);
 
 /* ---- collector (csrc/rsb_collect.cu): what rlkit's MdpPathCollector.collect_new_paths does per control step and per epoch

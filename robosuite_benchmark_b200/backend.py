@@ -89,12 +89,16 @@ def lib():
         L.rsb_counter_add.argtypes = [V, C.c_int64, V]
         L.rsb_dp_wait_peers_done.argtypes = [V, V, V, I, I, V]
         L.rsb_adam_polyak_allreduce.argtypes = [V, V, V, I, I, V, V, V, L_, C.c_double, C.c_double, F, F, F, V, V, L_, L_, F, I, V, L_, V]
-        L.rsb_sac_begin.argtypes = [V, V, V, V, V, V, I, I, U64, I, I, V, V, V, V, V, V, V, V, I, V, I, U64, C.c_uint32, V, V, V, I, I, V]
+        L.rsb_sac_begin.argtypes = [V, V, V, V, V, V, I, I, U64, I, I, V, I, V, V, V, V, V, V, I, V, I, V, I, U64, C.c_uint32, V, V, V, I, I, V]
         L.rsb_gemm_tf32.argtypes = [V, L_, L_, L_, V, L_, L_, L_, V, L_, L_, I, I, I, I, V, L_, V, L_, L_, I, I, I, L_, L_, V]
         L.rsb_gemm_debug_swap_offsets.argtypes = [I]
         L.rsb_gemm_debug_swap_offsets.restype = None
         L.rsb_gemm_debug_splits.argtypes = [I]
         L.rsb_gemm_debug_splits.restype = None
+        L.rsb_gemm_debug_tma.argtypes = [I]
+        L.rsb_gemm_debug_tma.restype = None
+        L.rsb_gemm_debug_mn_swap.argtypes = [I]
+        L.rsb_gemm_debug_mn_swap.restype = None
         _LIB = L
     return _LIB
 
@@ -105,7 +109,7 @@ EXPORTS = ["rsb_last_error", "rsb_sizeof_model", "rsb_sizeof_task", "rsb_create"
            "rsb_policy_act", "rsb_path_stats", "rsb_path_stats_words", "rsb_sac_last_error", "rsb_sac_prepare", "rsb_replay_sample", "rsb_normal", "rsb_bias_relu", "rsb_relu_bwd",
            "rsb_colsum", "rsb_head_fwd", "rsb_head_bwd", "rsb_sac_losses", "rsb_adam_polyak", "rsb_adam_tick", "rsb_policy_head_fwd", "rsb_q_losses",
            "rsb_policy_head_bwd", "rsb_replay_sample_dev", "rsb_normal_dev", "rsb_counter_add", "rsb_sac_begin", "rsb_dp_wait_peers_done", "rsb_adam_polyak_allreduce", "rsb_dp_timeouts", "rsb_gemm_tf32", "rsb_gemm_timeouts",
-           "rsb_gemm_debug_swap_offsets", "rsb_gemm_debug_clocks", "rsb_gemm_debug_splits", "rsb_gemm_plan"]
+           "rsb_gemm_debug_swap_offsets", "rsb_gemm_debug_clocks", "rsb_gemm_debug_splits", "rsb_gemm_plan", "rsb_gemm_debug_tma", "rsb_gemm_debug_last_tma", "rsb_gemm_debug_mn_swap"]
 
 
 class RsbError(RuntimeError):

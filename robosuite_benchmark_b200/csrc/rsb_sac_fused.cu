@@ -224,12 +224,12 @@ __global__ void k_counter_add(long long *__restrict__ p, long long delta) { pdl_
    thread gid < ceil(2 B A / 4) also draws four N(0,1) of the policy noise (noise != 0), thread gid < nsums clears a loss accumulator. */
 __global__ void k_sac_begin(const float *__restrict__ obs, const float *__restrict__ act_ring, const float *__restrict__ rew_ring, const unsigned char *__restrict__ term_ring,
                             const float *__restrict__ next_obs, const long long *__restrict__ ctr, int O, int A, uint64_t seed_ring, int B, int sample,
-                            float *__restrict__ Xp, float *__restrict__ act, float *__restrict__ rew, float *__restrict__ term, int *__restrict__ b_idx,
-                            float *__restrict__ XQ, float *__restrict__ XT, float *__restrict__ sums, int nsums, float *__restrict__ g_log_alpha,
+                            float *__restrict__ Xp, int ldp, float *__restrict__ act, float *__restrict__ rew, float *__restrict__ term, int *__restrict__ b_idx,
+                            float *__restrict__ XQ, float *__restrict__ XT, int ldq, float *__restrict__ sums, int nsums, float *__restrict__ g_log_alpha,
                             int noise, uint64_t seed_noise, uint32_t noise_stream, float *__restrict__ eps,
                             uint32_t *const *__restrict__ dp_flags, const uint32_t *__restrict__ dp_local, int dp_rank, int dp_world) {
   pdl_wait(); pdl_trigger();
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x, b = gid >> 5, lane = gid & 31, QI = O + A;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x, b = gid >> 5, lane = gid & 31;
   const uint64_t step = (uint64_t)ctr[1];
   if (gid < nsums) sums[gid] = 0.0f;
   if (gid == 0) {
@@ -266,13 +266,13 @@ __global__ void k_sac_begin(const float *__restrict__ obs, const float *__restri
     const int idx = (int)__umulhi(c[0], (uint32_t)ctr[0]);
     so = obs + (size_t)idx * O; sn_ = next_obs + (size_t)idx * O; sa = act_ring + (size_t)idx * A;
     if (lane == 0) { rew[b] = rew_ring[idx]; term[b] = (float)term_ring[idx]; if (b_idx) b_idx[b] = idx; }
-  } else { so = Xp + (size_t)b * O; sn_ = Xp + (size_t)(B + b) * O; sa = act + (size_t)b * A; }
-  for (int k = lane; k < O; k += 32) {
+  } else { so = Xp + (size_t)b * ldp; sn_ = Xp + (size_t)(B + b) * ldp; sa = act + (size_t)b * A; }
+  for (int k = lane; k < O; k += 32) {                                  /* ldp / ldq: row pitches of Xp and of XQ / XT (padded to 16 bytes: TMA-stageable) */
     const float v = so[k], w = sn_[k];
-    if (sample) { Xp[(size_t)b * O + k] = v; Xp[(size_t)(B + b) * O + k] = w; }
-    XQ[(size_t)b * QI + k] = v; XQ[(size_t)(B + b) * QI + k] = v; XT[(size_t)b * QI + k] = w;
+    if (sample) { Xp[(size_t)b * ldp + k] = v; Xp[(size_t)(B + b) * ldp + k] = w; }
+    XQ[(size_t)b * ldq + k] = v; XQ[(size_t)(B + b) * ldq + k] = v; XT[(size_t)b * ldq + k] = w;
   }
-  for (int k = lane; k < A; k += 32) { const float v = sa[k]; if (sample) act[(size_t)b * A + k] = v; XQ[(size_t)(B + b) * QI + O + k] = v; }
+  for (int k = lane; k < A; k += 32) { const float v = sa[k]; if (sample) act[(size_t)b * A + k] = v; XQ[(size_t)(B + b) * ldq + O + k] = v; }
 }
 }  // namespace
 
@@ -311,15 +311,15 @@ int rsb_normal_dev(uint64_t seed, const int64_t *d_ctr, uint32_t stream_id, int 
   int t = (n + 3) / 4; CKF(rsb_launch_pdl(k_normal_dev, dim3((t + 127) / 128), dim3(128), 0, (cudaStream_t)stream, 1, seed, (const long long *)d_ctr, stream_id, n, d_out)); return 0;
 }
 int rsb_sac_begin(const float *d_obs, const float *d_act, const float *d_rew, const uint8_t *d_term, const float *d_next, const int64_t *d_ctr, int obs_dim, int act_dim,
-                  uint64_t seed_ring, int batch, int sample, float *d_xp, float *b_act, float *b_rew, float *b_term, int *b_idx, float *d_xq, float *d_xt,
-                  float *d_sums, int nsums, float *d_g_log_alpha, int noise, uint64_t seed_noise, uint32_t noise_stream, float *d_eps,
+                  uint64_t seed_ring, int batch, int sample, float *d_xp, int ld_xp, float *b_act, float *b_rew, float *b_term, int *b_idx, float *d_xq, float *d_xt,
+                  int ld_xq, float *d_sums, int nsums, float *d_g_log_alpha, int noise, uint64_t seed_noise, uint32_t noise_stream, float *d_eps,
                   uint32_t *const *d_dp_flags, const uint32_t *d_dp_local, int dp_rank, int dp_world, void *stream) {
-  if (batch <= 0 || !d_ctr || nsums > 32 * batch || nsums < 8) { rsb_sac_set_error("sac_begin: bad arguments"); return 2; }
+  if (batch <= 0 || !d_ctr || nsums > 32 * batch || nsums < 8 || ld_xp < obs_dim || ld_xq < obs_dim + act_dim) { rsb_sac_set_error("sac_begin: bad arguments"); return 2; }
   if (dp_world > 1 && (!d_dp_flags || !d_dp_local || dp_rank < 0 || dp_rank >= dp_world)) { rsb_sac_set_error("sac_begin: bad data-parallel arguments"); return 2; }
   if (sample && (!d_obs || !d_act || !d_rew || !d_term || !d_next)) { rsb_sac_set_error("sac_begin: sampling needs the replay ring"); return 2; }
   const int threads = 128, blocks = (batch * 32 + threads - 1) / threads;       /* 32 B threads >= ceil(2 B A / 4) for A <= 64 */
   CKF(rsb_launch_pdl(k_sac_begin, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, 1, d_obs, d_act, d_rew, d_term, d_next, (const long long *)d_ctr, obs_dim, act_dim, seed_ring,
-                     batch, sample, d_xp, b_act, b_rew, b_term, b_idx, d_xq, d_xt, d_sums, nsums, d_g_log_alpha, noise, seed_noise, noise_stream, d_eps,
+                     batch, sample, d_xp, ld_xp, b_act, b_rew, b_term, b_idx, d_xq, d_xt, ld_xq, d_sums, nsums, d_g_log_alpha, noise, seed_noise, noise_stream, d_eps,
                      d_dp_flags, d_dp_local, dp_rank, dp_world));
   return 0;
 }

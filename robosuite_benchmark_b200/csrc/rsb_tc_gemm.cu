@@ -29,9 +29,11 @@
  * per epoch and by the tests) AND the CTA writes NaN into its tile of C, so a protocol error reaches the losses and the parameters as NaN --
  * never a hung GPU, never silently stale activations or gradients.
  */
+#include <cuda.h>                 /* CUtensorMap + enums only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint (no link against libcuda) */
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 #include <string>
 
 #include "../../include/rsb_gemm.h"
@@ -55,9 +57,15 @@ struct GemmArgs {
   float *c;
   long long a_rs, a_cs, a_bs, b_ks, b_ns, b_bs, c_rs, c_bs, bias_bs, mask_rs, mask_bs, a_kbs, b_kbs;
   int m, n, k, flags, n_tile, lbo16, sbo16, splits, cps, recv_off, stages, k_block;   /* splits: CTAs of one cluster sharing a C tile along K; cps: chunks per split */
+  int a_tma, b_tma;         /* operand staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) instead of the strided cp.async gather: 1 = K-major (contraction index contiguous
+                               in memory), 2 = MN-major (row / column index contiguous: transposed activations, weights stored [in, out]); 0 = gather.  16-byte strides needed. */
+  int z_is_block;           /* third TMA coordinate: 1 = the k-block index (stack_k), 0 = the batch index */
+  int a_zbcast, b_zbcast;   /* the operand is shared by all batch entries (batch stride 0: both Q networks read the same input): its map has one slice, z = 0 */
 };
+#define FBAR_OFF 640        /* four "stage full" mbarriers (TMA completion) inside the control block, behind the bias row */
 
 __device__ unsigned int g_gemm_timeouts;
+__device__ int g_mn_swap;                     /* diagnostic (rsb_gemm_debug_mn_swap): exchange the two byte-offset fields of the MN-major descriptor */
 __device__ long long g_gemm_clk[12];         /* phase clocks of CTA (0,0,0)'s thread 0 of the last launch (diagnostic, rsb_gemm_debug_clocks) */
 #define CLK(i) do { if (tid == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) g_gemm_clk[i] = clock64(); } while (0)
 
@@ -68,6 +76,12 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int by
 }
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, int bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
+/* one box of a 3-D tensor map (k, row, z) -> shared memory; completion is reported in bytes on the stage's "full" barrier */
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
@@ -110,7 +124,7 @@ __device__ __forceinline__ void load_tile(uint32_t dst, const float *base, long 
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g, const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = blockIdx.x % g.splits;                       /* = %cluster_ctarank: the cluster is (splits, 1, 1) */
@@ -144,6 +158,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
 #pragma unroll
     for (int c = 0; c < 4; c++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0 + 8 * c) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(rbar) : "memory");
+#pragma unroll
+    for (int c = 0; c < 4; c++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0 + FBAR_OFF + 8 * c) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     /* split-K: this CTA will receive splits x 128 x (n_tile/splits) partial sums = 512 x n_tile bytes on `rbar` (one phase) */
     if (g.splits > 1) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(rbar), "r"(512 * g.n_tile) : "memory");
@@ -157,18 +173,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
   pdl_wait();                                                   /* the producer of A / B / mask / C has completed */
   pdl_trigger();
   CLK(1);
+  /* TMA staging of a chunk (one elected thread): the chunk's 64 k-values are two 128-byte swizzle atoms [rows x 32 floats]; rows / k beyond the tensor are
+     zero-filled by the TMA unit.  Coordinates (k inside the block, row, z) with z = batch index or k-block index. */
+  const uint32_t tma_bytes = (g.a_tma ? (uint32_t)A_BYTES : 0u) + (g.b_tma ? (uint32_t)g.n_tile * (KC * 4) : 0u);
+  auto tma_chunk = [&](int stage, int krel) {                   /* krel: offset of the chunk inside this CTA's K slice */
+    const uint32_t fb = bar0 + FBAR_OFF + 8 * stage, a_dst = sbase + stage * stage_bytes, b_dst = a_dst + A_BYTES;
+    const int kabs = kbeg + krel, blk = kabs / g.k_block, kin = kabs - blk * g.k_block, z = g.z_is_block ? blk : bz;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(fb), "r"(tma_bytes) : "memory");
+    /* K-major: two atoms [rows x 32 k] (box 32 k x rows).  MN-major: rows/32 atoms [64 k x 32 rows] (box 32 rows x 64 k), 8 KB apart */
+    const int za = g.a_zbcast ? 0 : z, zb = g.b_zbcast ? 0 : z;
+    if (g.a_tma == 1) { tma_load_3d(a_dst, &tmap_a, kin, m0, za, fb); tma_load_3d(a_dst + BM * 128, &tmap_a, kin + 32, m0, za, fb); }
+    else if (g.a_tma == 2) { for (int j = 0; j < BM / 32; j++) tma_load_3d(a_dst + j * (KC * 128), &tmap_a, m0 + 32 * j, kin, za, fb); }
+    if (g.b_tma == 1) { tma_load_3d(b_dst, &tmap_b, kin, n0, zb, fb); tma_load_3d(b_dst + g.n_tile * 128, &tmap_b, kin + 32, n0, zb, fb); }
+    else if (g.b_tma == 2) { for (int j = 0; j < (g.n_tile >> 5); j++) tma_load_3d(b_dst + j * (KC * 128), &tmap_b, n0 + 32 * j, kin, zb, fb); }
+  };
+  const bool any_tma = (g.a_tma | g.b_tma) != 0;
   /* the first S chunks */
   for (int c = 0; c < S; c++) {
     if (c < nchunks) {
-      load_tile(sbase + c * stage_bytes, a_at(kbeg + c * KC), g.a_rs, g.a_cs, BM, mvalid, klen - c * KC, a16);
-      load_tile(sbase + c * stage_bytes + A_BYTES, b_at(kbeg + c * KC), g.b_ns, g.b_ks, g.n_tile, nvalid, klen - c * KC, b16);
+      if (any_tma && tid == 64) tma_chunk(c, c * KC);
+      if (!g.a_tma) load_tile(sbase + c * stage_bytes, a_at(kbeg + c * KC), g.a_rs, g.a_cs, BM, mvalid, klen - c * KC, a16);
+      if (!g.b_tma) load_tile(sbase + c * stage_bytes + A_BYTES, b_at(kbeg + c * KC), g.b_ns, g.b_ks, g.n_tile, nvalid, klen - c * KC, b16);
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   }
   if (tid < g.n_tile) sbias[tid] = (g.bias && tid < nvalid) ? __ldg(g.bias + (long long)bz * g.bias_bs + n0 + tid) : 0.0f;     /* read in the epilogue, after the chunk loop's CTA barriers */
   CLK(2);
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((g.a_tma == 2 ? 1u : 0u) << 15) | ((g.b_tma == 2 ? 1u : 0u) << 16) |      /* bits 15 / 16: A / B is MN-major */
+                         ((uint32_t)(g.n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   const uint64_t desc_hi = ((uint64_t)g.lbo16 << 16) | ((uint64_t)g.sbo16 << 32) | (1ull << 46);
+  /* TMA-staged operand: K-major, 128-byte swizzle -- layout type 2 in bits [61,64), stride byte offset = 8 rows x 128 B = 1024, leading byte offset unused (1);
+     the k-th product of a chunk reads atom k / 4 (rows x 128 B apart) at byte offset 32 (k % 4) inside the swizzled 128-byte rows */
+  const uint64_t desc_hi_sw = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+  /* TMA-staged MN-major operand.  For 32-bit operands the tensor core accepts exactly one MN-major layout: 128-byte swizzle with 32-BYTE atoms (descriptor
+     layout type 1; TMA swizzle CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): a 128-byte row holds 32 consecutive rows / columns of the operand for ONE k, the four
+     32-byte pieces of a row are XOR-ed with (k mod 4); the pattern repeats every 4 k.  Leading byte offset = distance between 32-wide atoms along the row
+     index (64 k x 128 B = 8192), stride byte offset = distance between 4-k groups (512); the k-th product of a chunk (8 k) starts 1024 k bytes in. */
+  const uint64_t desc_hi_mn = g_mn_swap ? (((uint64_t)(512 >> 4) << 16) | ((uint64_t)((KC * 128) >> 4) << 32) | (1ull << 46) | (1ull << 61))
+                                        : (((uint64_t)((KC * 128) >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61));
 
   int st = 0, ph = 0;                                           /* stage and mbarrier phase of chunk i: i % S, (i / S) & 1 */
   for (int i = 0; i < nchunks; i++) {
@@ -183,9 +225,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const int kmma = (min(KC, klen - i * KC) + 7) >> 3;
       const uint32_t a_addr = sbase + st * stage_bytes, b_addr = a_addr + A_BYTES;
+      if (any_tma) mbar_wait(bar0 + FBAR_OFF + 8 * st, ph);     /* the TMA boxes of this chunk have landed (same stage / phase sequence as the "free" barriers) */
       for (int kk = 0; kk < kmma; kk++) {
-        const uint64_t da = desc_hi | (uint64_t)(((a_addr + kk * 256) >> 4) & 0x3FFF);
-        const uint64_t db = desc_hi | (uint64_t)(((b_addr + kk * 256) >> 4) & 0x3FFF);
+        const uint64_t da = g.a_tma == 1 ? (desc_hi_sw | (uint64_t)(((a_addr + (kk >> 2) * (BM * 128) + (kk & 3) * 32) >> 4) & 0x3FFF))
+                          : g.a_tma == 2 ? (desc_hi_mn | (uint64_t)(((a_addr + kk * 1024) >> 4) & 0x3FFF))
+                                         : (desc_hi | (uint64_t)(((a_addr + kk * 256) >> 4) & 0x3FFF));
+        const uint64_t db = g.b_tma == 1 ? (desc_hi_sw | (uint64_t)(((b_addr + (kk >> 2) * (g.n_tile * 128) + (kk & 3) * 32) >> 4) & 0x3FFF))
+                          : g.b_tma == 2 ? (desc_hi_mn | (uint64_t)(((b_addr + kk * 1024) >> 4) & 0x3FFF))
+                                         : (desc_hi | (uint64_t)(((b_addr + kk * 256) >> 4) & 0x3FFF));
         const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
                      ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
@@ -195,8 +242,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
     if (i + S < nchunks) {                                      /* refill this stage once its products have read it */
       const int k1 = (i + S) * KC;
       mbar_wait(bar0 + 8 * st, ph);
-      load_tile(sbase + st * stage_bytes, a_at(kbeg + k1), g.a_rs, g.a_cs, BM, mvalid, klen - k1, a16);
-      load_tile(sbase + st * stage_bytes + A_BYTES, b_at(kbeg + k1), g.b_ns, g.b_ks, g.n_tile, nvalid, klen - k1, b16);
+      if (any_tma && tid == 64) tma_chunk(st, k1);
+      if (!g.a_tma) load_tile(sbase + st * stage_bytes, a_at(kbeg + k1), g.a_rs, g.a_cs, BM, mvalid, klen - k1, a16);
+      if (!g.b_tma) load_tile(sbase + st * stage_bytes + A_BYTES, b_at(kbeg + k1), g.b_ns, g.b_ks, g.n_tile, nvalid, klen - k1, b16);
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     if (i + 1 < nchunks && ++st == S) { st = 0; ph ^= 1; }
@@ -295,6 +343,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tf32(GemmArgs g) {
 
 static int g_swap_offsets = 0, g_force_splits = 0;
 
+/* ---- TMA descriptors.  An operand is TMA-eligible when its contraction index is contiguous in memory and every stride is a multiple of 16 bytes: then
+   a [rows x 64] chunk is two `cp.async.bulk.tensor` boxes issued by ONE thread (the strided cp.async gather costs 16-64 instructions per thread and chunk:
+   9.2 k of the 16.5 k cycles of a 128 x 256 x 256 product in round 1).  The map is 3-D (k, row, z) with z = batch or k-block index.  RSB_GEMM_TMA=0 disables. */
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int g_tma_mode = -1, g_last_tma = 0;     /* diagnostic: -1 = as RSB_GEMM_TMA says (default on), 0 = force the cp.async gather, 1 = on; staging mode of the last launch: A in bits 0-1, B in bits 2-3 (0 gather, 1 TMA K-major, 2 TMA MN-major) */
+extern "C" void rsb_gemm_debug_tma(int mode) { g_tma_mode = mode; }
+extern "C" void rsb_gemm_debug_mn_swap(int swap) { cudaMemcpyToSymbol(g_mn_swap, &swap, sizeof(int)); }
+extern "C" int rsb_gemm_debug_last_tma(void) { return g_last_tma; }
+static EncodeTiledFn encode_tiled() {
+  if (g_tma_mode == 0) return nullptr;
+  static EncodeTiledFn fn = nullptr; static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char *ev = getenv("RSB_GEMM_TMA");
+    if (!(ev && atoi(ev) == 0)) {
+      void *p = nullptr; cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+    }
+  }
+  return fn;
+}
+/* 3-D view of an operand: element (i, o, z) at base + z * zs + o * rs + i (floats), i = the index that is contiguous in memory (k for a K-major operand,
+   the row / column index for an MN-major one), o = the other one; box = 32 i x box_rows o */
+static bool make_map(CUtensorMap *map, const float *base, long k_ext, long rows, long nz, long rs, long zs, int box_rows, bool atom32 = false) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn || k_ext < 32 || (rs & 3) || (nz > 1 && (zs & 3)) || ((uintptr_t)base & 15) || rs < k_ext) return false;
+  if (nz <= 1) { nz = 1; zs = rows * rs; if (zs & 3) zs = (zs + 3) & ~3L; }
+  const cuuint64_t dims[3] = {(cuuint64_t)k_ext, (cuuint64_t)rows, (cuuint64_t)nz};
+  const cuuint64_t strides[2] = {(cuuint64_t)rs * 4, (cuuint64_t)zs * 4};
+  const cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1}, es[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 extern "C" void rsb_gemm_debug_swap_offsets(int swap) { g_swap_offsets = swap; }
 extern "C" void rsb_gemm_debug_splits(int splits) { g_force_splits = splits; }
 
@@ -372,9 +456,22 @@ extern "C" int rsb_gemm_tf32(const float *d_a, long a_rs, long a_cs, long a_bs, 
   g.lbo16 = g_swap_offsets ? (2048 >> 4) : (128 >> 4);
   g.sbo16 = g_swap_offsets ? (128 >> 4) : (2048 >> 4);
   g.splits = splits; g.cps = plan[2]; g.stages = plan[3]; g.recv_off = plan[4];
+  /* TMA staging where the operand allows it (K-contiguous, 16-byte strides); the third coordinate is the k-block (stack_k products) or the batch */
+  const int nblk = (k + k_block - 1) / k_block;
+  alignas(64) CUtensorMap ta, tb; memset(&ta, 0, sizeof ta); memset(&tb, 0, sizeof tb);
+  g.z_is_block = nblk > 1; g.a_tma = g.b_tma = 0;
+  g.a_zbcast = (nblk == 1 && batch > 1 && a_bs == 0); g.b_zbcast = (nblk == 1 && batch > 1 && b_bs == 0);
+  if (!(nblk > 1 && batch > 1)) {
+    const long k_ext = nblk > 1 ? k_block : k, nza = g.a_zbcast ? 1 : (nblk > 1 ? nblk : batch), nzb = g.b_zbcast ? 1 : (nblk > 1 ? nblk : batch);
+    if (a_cs == 1) g.a_tma = make_map(&ta, d_a, k_ext, m, nza, a_rs, nblk > 1 ? a_kbs : a_bs, BM) ? 1 : 0;
+    if (!g.a_tma && a_rs == 1 && nblk == 1) g.a_tma = make_map(&ta, d_a, m, k, nza, a_cs, a_bs, KC, true) ? 2 : 0;                         /* A^T in memory */
+    if (b_ks == 1) g.b_tma = make_map(&tb, d_b, k_ext, n, nzb, b_ns, nblk > 1 ? b_kbs : b_bs, n_tile) ? 1 : 0;
+    if (!g.b_tma && b_ns == 1 && nblk == 1 && n_tile >= 32) g.b_tma = make_map(&tb, d_b, n, k, nzb, b_ks, b_bs, KC, true) ? 2 : 0;         /* B stored [k, n] */
+  }
+  g_last_tma = g.a_tma | (g.b_tma << 2);
   const size_t smem_bytes = (size_t)plan[5];
   dim3 grid(plan[6], (m + BM - 1) / BM, batch);
-  e = rsb_launch_pdl(k_gemm_tf32, grid, dim3(NTHREADS, 1, 1), smem_bytes, (cudaStream_t)stream, splits, g);
+  e = rsb_launch_pdl(k_gemm_tf32, grid, dim3(NTHREADS, 1, 1), smem_bytes, (cudaStream_t)stream, splits, g, ta, tb);
   if (e != cudaSuccess) { rsb_sac_set_error(cudaGetErrorString(e)); return 1; }
   return 0;
 }

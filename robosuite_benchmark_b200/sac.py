@@ -173,9 +173,10 @@ class ParamStore:
             ("log_alpha", (1,))])
         self.shapes, self.offsets, n = shapes, OrderedDict(), 0
         for k, s in shapes.items():
+            n = (n + 3) & ~3                            # every tensor starts on a 16-byte boundary: TMA-stageable as a GEMM operand (the gaps stay zero)
             self.offsets[k] = n
             n += int(np.prod(s))
-        self.n = n
+        self.n = (n + 3) & ~3
         self.q_begin, self.q_end = self.offsets["q_W0"], self.offsets["log_alpha"]
         f32 = dict(dtype=torch.float32, device=self.device)
         self.flat = torch.zeros(n, **f32)
@@ -588,9 +589,11 @@ class SACTrainer:
         t, s = self.torch, self.store
         O, A, H, QI = s.O, s.A, s.H, s.O + s.A
         f32 = dict(dtype=t.float32, device=self.device)
-        self.Xp = t.zeros(2 * B, O, **f32)             # policy input: obs rows, then next_obs rows
-        self.XQ = t.zeros(2 * B, QI, **f32)            # Q input: (obs, a_new) rows, then (obs, act) rows
-        self.XT = t.zeros(B, QI, **f32)                # target-Q input: (next_obs, a')
+        Op, QIp = (O + 3) & ~3, (QI + 3) & ~3          # row pitches padded to 16 bytes: the first layers' inputs are TMA-stageable (csrc/rsb_tc_gemm.cu)
+        self.ldO, self.ldQ = Op, QIp
+        self.Xp = t.zeros(2 * B, Op, **f32)[:, :O]     # policy input: obs rows, then next_obs rows
+        self.XQ = t.zeros(2 * B, QIp, **f32)[:, :QI]   # Q input: (obs, a_new) rows, then (obs, act) rows
+        self.XT = t.zeros(B, QIp, **f32)[:, :QI]       # target-Q input: (next_obs, a')
         self.act, self.rew, self.term = t.zeros(B, A, **f32), t.zeros(B, **f32), t.zeros(B, **f32)
         self.idx = t.zeros(B, dtype=t.int32, device=self.device)
         self.eps = t.zeros(2 * B, A, **f32)
@@ -600,7 +603,7 @@ class SACTrainer:
         self.H1t, self.H2t, self.qt = t.zeros(2, B, H, **f32), t.zeros(2, B, H, **f32), t.zeros(2, B, 1, **f32)
         self.dq, self.y, self.sums = t.zeros(2, 2 * B, 1, **f32), t.zeros(B, **f32), t.zeros(8, **f32)
         self.dH2q, self.dH1q = t.zeros(2, 2 * B, H, **f32), t.zeros(2, 2 * B, H, **f32)
-        self.gX = t.zeros(B, QI, **f32)
+        self.gX = t.zeros(B, QIp, **f32)[:, :QI]
         self.dOUT, self.dH2p, self.dH1p = t.zeros(2 * B, 2 * A, **f32), t.zeros(B, H, **f32), t.zeros(B, H, **f32)
 
     # -- kernels
@@ -646,8 +649,8 @@ class SACTrainer:
         s, R = self.store, self.replay
         B, O = self.B, s.O
         _chk(self.L.rsb_replay_sample_dev(_ptr(R._observations), _ptr(R._actions), _ptr(R._rewards), _ptr(R._terminals), _ptr(R._next_obs), _ptr(self.ctr),
-                                          R.obs_dim, R.action_dim, C.c_uint64(R.seed), B, _ptr(self.Xp), O, _ptr(self.act), _ptr(self.rew), _ptr(self.term),
-                                          C.c_void_p(self.Xp.data_ptr() + 4 * B * O), O, _ptr(self.idx), _stream(self.device)))
+                                          R.obs_dim, R.action_dim, C.c_uint64(R.seed), B, _ptr(self.Xp), self.ldO, _ptr(self.act), _ptr(self.rew), _ptr(self.term),
+                                          C.c_void_p(self.Xp.data_ptr() + 4 * B * self.ldO), self.ldO, _ptr(self.idx), _stream(self.device)))
 
     def load_batch(self, batch):
         """Use an explicit batch (dict of tensors/arrays, rlkit keys) instead of sampling -- parity tests and `train(batch)`."""
@@ -673,8 +676,8 @@ class SACTrainer:
         # accumulators, policy noise -- all keyed by the device-resident counters
         R, dp = self.replay, self._dp                # (data parallel: this kernel also waits until the peers are done with the previous gradient bucket)
         ring = (_ptr(R._observations), _ptr(R._actions), _ptr(R._rewards), _ptr(R._terminals), _ptr(R._next_obs), C.c_uint64(R.seed)) if sample else (None,) * 5 + (C.c_uint64(0),)
-        _chk(L.rsb_sac_begin(ring[0], ring[1], ring[2], ring[3], ring[4], _ptr(self.ctr), O, A, ring[5], B, int(sample), _ptr(self.Xp), _ptr(self.act), _ptr(self.rew),
-                             _ptr(self.term), _ptr(self.idx), _ptr(self.XQ), _ptr(self.XT), _ptr(self.sums), self.sums.numel(), _ptr(G["log_alpha"]), int(noise),
+        _chk(L.rsb_sac_begin(ring[0], ring[1], ring[2], ring[3], ring[4], _ptr(self.ctr), O, A, ring[5], B, int(sample), _ptr(self.Xp), self.ldO, _ptr(self.act), _ptr(self.rew),
+                             _ptr(self.term), _ptr(self.idx), _ptr(self.XQ), _ptr(self.XT), self.ldQ, _ptr(self.sums), self.sums.numel(), _ptr(G["log_alpha"]), int(noise),
                              C.c_uint64(self.seed), self.noise_stream, _ptr(self.eps),
                              dp["flags_dev"] if dp else None, _ptr(dp["local"]) if dp else None, self.rank, self.world if dp else 0, st))
         if tick_early:                               # after the kernel that reads the update counter; nothing else of the update reads what it writes before _apply
@@ -687,7 +690,7 @@ class SACTrainer:
         mm(self.Xp, P["p_W0"], self.H1p, bias=P["p_b0"], relu=True)
         mm(self.H1p, P["p_W1"], self.H2p, bias=P["p_b1"], relu=True)
         _chk(L.rsb_policy_head_fwd(_ptr(self.H2p), _ptr(P["p_W2"]), _ptr(P["p_b2"]), _ptr(self.eps), 2 * B, A, _ptr(self.OUT), _ptr(self.a_store), _ptr(self.logpi),
-                                   C.c_void_p(self.XQ.data_ptr() + 4 * O), QI, 0, B, C.c_void_p(self.XT.data_ptr() + 4 * O), QI, B, 2 * B, st))
+                                   C.c_void_p(self.XQ.data_ptr() + 4 * O), self.ldQ, 0, B, C.c_void_p(self.XT.data_ptr() + 4 * O), self.ldQ, B, 2 * B, st))
         # twin Q hidden layers (batched over the two networks) on [(obs,a_new); (obs,act)]; the target nets' on (next_obs, a') on a side stream
         XQ2, XT2 = self.XQ.unsqueeze(0).expand(2, 2 * B, QI), self.XT.unsqueeze(0).expand(2, B, QI)
         sT.wait_stream(main)
@@ -723,7 +726,7 @@ class SACTrainer:
             mm(self.dH1q[0, :B], P["q_W0"][0].t(), self.gX); mm(self.dH1q[1, :B], P["q_W0"][1].t(), self.gX, accumulate=True)
         # policy backward: head backward + the last layer's input gradient in one kernel
         _chk(L.rsb_policy_head_bwd(_ptr(self.OUT), _ptr(self.eps), _ptr(self.a_store), _ptr(self.H2p), _ptr(P["p_W2"]), B, A, _ptr(self.alpha),
-                                   C.c_void_p(self.gX.data_ptr() + 4 * O), QI, _ptr(self.dOUT), _ptr(self.dH2p), st))
+                                   C.c_void_p(self.gX.data_ptr() + 4 * O), self.ldQ, _ptr(self.dOUT), _ptr(self.dH2p), st))
         weight_grads(lambda: mm(self.H2p[:B].t(), self.dOUT[:B], G["p_W2"]), lambda: self._colsum(self.dOUT, 0, B, G["p_b2"]))
         weight_grads(lambda: mm(self.H1p[:B].t(), self.dH2p, G["p_W1"]), lambda: self._colsum(self.dH2p, 0, B, G["p_b1"]))
         mm(self.dH2p, P["p_W1"].t(), self.dH1p, mask=self.H1p[:B])

@@ -97,7 +97,9 @@ def test_one_control_step_from_policy_rollout_states(sim, lift_panda_osc, torch_
     d.pop("logged")
     pol = DeterministicPolicy({k: v.astype(np.float64) for k, v in d.items()})
     n = sim.num_envs
-    rows, acts, envs = [], [], []
+    from tests.emu.emu import split_debug
+    m, _ = lift_panda_osc
+    rows, acts, envs, starts = [], [], [], []
     ncon_seen = 0
     for i in range(n):
         orc = _oracle(lift_panda_osc)
@@ -106,10 +108,12 @@ def test_one_control_step_from_policy_rollout_states(sim, lift_panda_osc, torch_
         for k in range(20 + 6 * i):                                   # 20 .. 206 policy steps: approach, table contact, pushing
             o, _, _ = orc.step(pol(np.asarray(o, np.float64)))
         qpos, qvel, warm, cs = orc.get_state()
+        starts.append((qpos.copy(), qvel.copy(), warm.copy(), cs.copy(), k + 1))
         rows.append(sim.pack_state(qpos, qvel, warm, cs, timestep=k + 1, episode=1)[0])
         acts.append(pol(np.asarray(o, np.float64)))
         envs.append(orc)
-    sim.set_state(torch.as_tensor(np.stack(rows)))
+    state0 = torch.as_tensor(np.stack(rows))
+    sim.set_state(state0)
     a = torch.as_tensor(np.stack(acts), dtype=torch.float32, device=sim.device)
     obs, rew, done = sim.step(a)
     st = sim.unpack_state(sim.get_state().cpu().numpy())
@@ -122,17 +126,50 @@ def test_one_control_step_from_policy_rollout_states(sim, lift_panda_osc, torch_
         dq[i], dv[i] = np.abs(qpos - st["qpos"][i]).max(), np.abs(qvel - st["qvel"][i]).max()
         do[i], dr[i] = np.abs(o - obs[i]).max(), abs(r - rew[i])
     assert ncon_seen > 4, "the policy rollouts should reach states with gripper contacts"
+    # The same control step once more, SUBSTEP BY SUBSTEP on both sides (rsb_debug_substep / orc.substep): per environment the first substep
+    # at which the two contact-pair lists differ (a contact switching on or off one substep apart in fp32 and fp64), and the state
+    # difference accumulated up to the substep before it.  This classifies EVERY state -- nothing is excluded by rank:
+    #   * contact sets identical through all 25 substeps  -> the whole step is held to the tolerances below;
+    #   * a contact-set switch at substep s               -> identical pair lists and tight agreement up to substep s - 1 are REQUIRED;
+    #     what follows is a discontinuity of the physics (one substep of a contact force more or less), bounded loosely.
+    sim.set_state(state0)
+    refs = []
+    for i in range(n):
+        o2 = _oracle(lift_panda_osc)
+        o2.reset(seed=17, env_id=i, episode=0)
+        o2.set_state(*starts[i][:4]); o2.set_timestep(starts[i][4])
+        refs.append(o2)
+    switch = [None] * n                                            # first substep with differing pair lists
+    dv_before = np.zeros(n)                                        # |dqvel| after the last substep before the switch (or after substep 24)
+    for sub in range(25):
+        dbg = sim.debug_substep(a, sub == 0).cpu().numpy()
+        stt = sim.unpack_state(sim.get_state().cpu().numpy())
+        for i in range(n):
+            if switch[i] is not None:
+                continue
+            refs[i].substep(acts[i], sub == 0)
+            d = split_debug(dbg[i], m.nv, NCON, NEFC)
+            if refs[i].get("contact_geoms").reshape(-1, 2).astype(int).tolist() != d["contact_geoms"].tolist():
+                switch[i] = sub
+                continue
+            dv_before[i] = np.abs(refs[i].get_state()[1] - stt["qvel"][i]).max()
+    same = np.array([s_ is None for s_ in switch])
     # Findings on these 32 contact-rich states (tools/diag_policy_parity.py, tools/diag_env_substeps.py; DESIGN.md "parity results"):
-    #  * 29 are within 5e-5 on qvel (north_star: 1e-4), qpos within 3e-6 everywhere;
-    #  * where the hand SQUEEZES the cube against the table (6 contacts) the cube's angular velocity differs by up to 2.5e-4 rad/s,
+    #  * qpos within 3e-6 everywhere; qvel within 5e-5 wherever the contact sets stay identical, except
+    #  * where the hand SQUEEZES the cube against the table (6 contacts): the cube's angular velocity differs by up to 2.5e-4 rad/s,
     #    independent of the solver tolerances (checked down to 1e-8 in the emulator): fp32 resolution of the net moment of large
     #    opposing contact forces on a 0.07 kg cube;
-    #  * one state has the hand GRAZING the table: the hand-table contact switches on and off every few substeps, and fp32 vs fp64 (and
-    #    FMA contraction, CUDA vs the x86 emulator) detect one of the switches a substep apart (same pair lists in 22 of 25 substeps);
-    #    the velocities then differ by 4e-2.  A discontinuity of the physics, not a tolerance: such states are excluded by rank.
-    assert np.sort(dq)[-1] <= 1e-4, dq.max()
-    assert np.sort(dv)[-3] <= 1e-4 and np.sort(dv)[-2] <= 5e-4, np.sort(dv)[-4:]
-    assert np.sort(do)[-2] <= 5e-4 and np.sort(dr)[-2] <= 1e-5, (np.sort(do)[-3:], np.sort(dr)[-3:])
+    #  * one state has the hand GRAZING the table: the hand-table contact switches on and off every few substeps, and fp32 vs fp64
+    #    detect one of the switches a substep apart; the velocities then differ by 4e-2.
+    assert dq.max() <= 1e-4, dq.max()
+    assert same.sum() >= n - 3, switch                            # contact-set switches inside the step are the exception
+    assert dv[same].max() <= 5e-4 and np.sort(dv[same])[-3] <= 1e-4, np.sort(dv[same])[-4:]          # identical contact sets: every state bounded
+    assert do[same].max() <= 5e-4 and dr[same].max() <= 1e-5, (do[same].max(), dr[same].max())
+    for i in np.nonzero(~same)[0]:
+        assert switch[i] >= 1 and dv_before[i] <= 5e-4, (i, switch[i], dv_before[i])                   # tight until the switch ...
+        assert dv[i] <= 0.2 and do[i] <= 0.05 and dr[i] <= 0.05, (i, switch[i], dv[i], do[i], dr[i])    # ... bounded after it
+    print(f"policy states: {int(same.sum())}/{n} with identical contact sets over the step (max dqvel {dv[same].max():.1e}); switches at substeps "
+          f"{[s_ for s_ in switch if s_ is not None]} (dqvel before {dv_before[~same].tolist()}, after the step {dv[~same].tolist()})")
 
 
 def test_substep_internals_contacts_bit_exact_torques_1e5(sim, lift_panda_osc, torch_cuda):

@@ -31,6 +31,34 @@ def test_tcgen05_gemm_matches_fp64_on_every_sac_shape(dev):
     d.lib().rsb_gemm_debug_splits(0)
 
 
+def test_tma_staging_is_bit_identical_to_the_cp_async_gather(dev):
+    """Operands with one unit stride and 16-byte multiples otherwise are staged by TMA with the 128-byte swizzle -- K-major (contraction index contiguous)
+    or MN-major (transposed activations, weights stored [in, out]) --, the rest by the strided cp.async gather into the no-swizzle K-major layout: three
+    shared-memory layouts / descriptor kinds feeding the SAME products in the same order -- the outputs must be bit-identical, for every shape / tile
+    width / split factor, and TMA must actually engage on the eligible operands (A in bits 0-1, B in bits 2-3; 1 = K-major, 2 = MN-major)."""
+    import torch
+    import diag_tc_gemm as d
+    from robosuite_benchmark_b200 import gemm
+    L = d.lib()
+    engaged = {}
+    for c in d.cases():
+        for nt, splits in ((0, 0), (16, 4), (64, 2), (128, 1), (32, 1)):
+            L.rsb_gemm_debug_tma(1)
+            err, a, b, out_tma = d.run_case(c, dev, nt, splits)
+            engaged[c[0]] = L.rsb_gemm_debug_last_tma()
+            L.rsb_gemm_debug_tma(0)
+            _, _, _, out_gather = d.run_case(c, dev, nt, splits)
+            assert L.rsb_gemm_debug_last_tma() == 0
+            assert gemm.timeouts() == 0, c
+            assert err < 3e-3, (c, nt, splits, err)
+            assert torch.equal(out_tma, out_gather), (c, nt, splits, (out_tma - out_gather).abs().max().item())
+    L.rsb_gemm_debug_tma(-1); L.rsb_gemm_debug_splits(0)
+    assert engaged["fwd 128x256x256"] == 1 | (2 << 2) and engaged["big 4096x256x256"] == 1 | (2 << 2)        # X K-major, W [in, out] MN-major
+    assert engaged["dX twin 256x256x256"] == 1 | (1 << 2)                                                     # dY and W^T: both K-major
+    assert engaged["dW twin 256x256x128"] == 2 | (2 << 2) and engaged["dW big 256x256x4096"] == 2 | (2 << 2)  # X^T and dY: both MN-major
+    assert engaged["odd 130x70x100"] == 1 and engaged["fwd twin 256x256x49"] == 2 << 2                        # 280-byte rows of B / 196-byte rows of A: gather
+
+
 def test_tcgen05_gemm_is_deterministic_and_graph_capturable(dev):
     import torch
     from robosuite_benchmark_b200 import gemm
