@@ -94,6 +94,9 @@ int rsb_adam_polyak_allreduce(const float *const *d_peer_grads, uint32_t *const 
                               float *d_p, float *d_m, float *d_v, long n, double lr_pi, double lr_q, float b1, float b2, float eps, double *d_bc,
                               float *d_tgt, long tgt_begin, long tgt_end, float tau, int do_soft, float *d_alpha, long log_alpha_idx, void *stream);
 int rsb_dp_timeouts(void);
+/* diagnostic: %globaltimer [ns] of CTA 0 of the last rsb_adam_polyak_allreduce launch at 7 points (entry, dependency satisfied, READY signalled, peers ready,
+   go flag set, reduction + Adam done, tail); synchronises the device */
+int rsb_dp_debug_clocks(unsigned long long *host_out8);
 #ifdef __cplusplus
 }
 #endif

@@ -108,7 +108,7 @@ EXPORTS = ["rsb_last_error", "rsb_sizeof_model", "rsb_sizeof_task", "rsb_create"
            "rsb_debug_substep", "rsb_reset_ring", "rsb_step_ring", "rsb_get_iters", "rsb_get_option", "rsb_clear_counters",
            "rsb_policy_act", "rsb_path_stats", "rsb_path_stats_words", "rsb_sac_last_error", "rsb_sac_prepare", "rsb_replay_sample", "rsb_normal", "rsb_bias_relu", "rsb_relu_bwd",
            "rsb_colsum", "rsb_head_fwd", "rsb_head_bwd", "rsb_sac_losses", "rsb_adam_polyak", "rsb_adam_tick", "rsb_policy_head_fwd", "rsb_q_losses",
-           "rsb_policy_head_bwd", "rsb_replay_sample_dev", "rsb_normal_dev", "rsb_counter_add", "rsb_sac_begin", "rsb_dp_wait_peers_done", "rsb_adam_polyak_allreduce", "rsb_dp_timeouts", "rsb_gemm_tf32", "rsb_gemm_timeouts",
+           "rsb_policy_head_bwd", "rsb_replay_sample_dev", "rsb_normal_dev", "rsb_counter_add", "rsb_sac_begin", "rsb_dp_wait_peers_done", "rsb_adam_polyak_allreduce", "rsb_dp_timeouts", "rsb_dp_debug_clocks", "rsb_gemm_tf32", "rsb_gemm_timeouts",
            "rsb_gemm_debug_swap_offsets", "rsb_gemm_debug_clocks", "rsb_gemm_debug_splits", "rsb_gemm_plan", "rsb_gemm_debug_tma", "rsb_gemm_debug_last_tma", "rsb_gemm_debug_mn_swap"]
 
 

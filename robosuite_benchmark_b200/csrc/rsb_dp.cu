@@ -31,10 +31,16 @@ void rsb_sac_set_error(const char *msg);
 #define DP_SPIN (1 << 24)
 
 __device__ unsigned int g_dp_timeouts;
+__device__ unsigned long long g_dp_clk[8];      /* diagnostic (rsb_dp_debug_clocks): %globaltimer [ns] of CTA 0 of the last launch at entry, dependency satisfied, READY signalled,
+                                                   peers ready, go flag set, own reduction + Adam done, kernel tail */
+#define DPCLK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_dp_clk[i] = t_; } } while (0)
 
 namespace {
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory"); return v; }
+/* flag stores without a release fence: what the flag announces was written by EARLIER KERNELS of this stream (the gradient bucket) or has been consumed by this
+   thread's own dependent arithmetic (the peers' buckets) -- both are globally performed when the store issues; a sys-scope release costs ~2 us here (measured) */
+__device__ __forceinline__ void st_relaxed_sys(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ float4 ld_peer4(const float *p) { float4 v; asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory"); return v; }
@@ -68,15 +74,20 @@ __global__ void __launch_bounds__(512) k_adam_polyak_allreduce(DpArgs a, float *
                                                                double lr_pi, double lr_q, float b1, float b2, float eps, const double *__restrict__ bc,
                                                                float *__restrict__ tgt, long tgt_begin, long tgt_end, float tau, int do_soft,
                                                                float *__restrict__ alpha_out, long log_alpha_idx) {
+  DPCLK(0);
   pdl_wait(); pdl_trigger();
+  DPCLK(1);
   const int tid = threadIdx.x;
   const uint32_t epoch = a.local[0] + 1u;
   /* ---- barrier: every rank's bucket is complete.  CTA 0 talks to the peers, the other CTAs wait for its go flag. */
   if (blockIdx.x == 0) {
-    if (tid < a.world) st_release_sys(a.peer_flags[tid] + DP_READY + a.rank, epoch);
+    if (tid < a.world) st_relaxed_sys(a.peer_flags[tid] + DP_READY + a.rank, epoch);
+    DPCLK(2);
     if (tid < a.world) wait_ge_sys(a.peer_flags[a.rank] + DP_READY + tid, epoch);
     __syncthreads();
+    DPCLK(3);
     if (tid == 0) st_release_gpu(a.local + 1, epoch);
+    DPCLK(4);
   } else {
     if (tid == 0) { for (int it = 0; it < DP_SPIN; it++) { if ((int32_t)(ld_acquire_gpu(a.local + 1) - epoch) >= 0) break; __nanosleep(20); } }
     __syncthreads();
@@ -103,13 +114,15 @@ __global__ void __launch_bounds__(512) k_adam_polyak_allreduce(DpArgs a, float *
   }
   /* ---- the last CTA to finish tells every peer that this rank no longer reads their buckets, and closes the epoch */
   __syncthreads();
+  DPCLK(5);
   __shared__ unsigned int last;
   if (tid == 0) { __threadfence(); last = (atomicAdd(a.local + 2, 1u) == gridDim.x - 1) ? 1u : 0u; }
   __syncthreads();
   if (last) {
-    if (tid < a.world) st_release_sys(a.peer_flags[tid] + DP_DONE + a.rank, epoch);
+    if (tid < a.world) st_relaxed_sys(a.peer_flags[tid] + DP_DONE + a.rank, epoch);      /* (every CTA passed a __threadfence() after its last peer load) */
     if (tid == 0) { a.local[2] = 0u; a.local[0] = epoch; }
   }
+  DPCLK(6);
 }
 
 /* the next update may overwrite this rank's bucket only after every peer has finished reading it (epoch = last completed update) */
@@ -121,6 +134,11 @@ __global__ void k_dp_wait_peers_done(DpArgs a) {
 }  // namespace
 
 extern "C" {
+
+int rsb_dp_debug_clocks(unsigned long long *host_out8) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+  return cudaMemcpyFromSymbol(host_out8, g_dp_clk, 8 * sizeof(unsigned long long)) != cudaSuccess;
+}
 
 int rsb_dp_timeouts(void) {
   unsigned int h = 0, z = 0;

@@ -232,20 +232,18 @@ __global__ void k_sac_begin(const float *__restrict__ obs, const float *__restri
   const int gid = blockIdx.x * blockDim.x + threadIdx.x, b = gid >> 5, lane = gid & 31;
   const uint64_t step = (uint64_t)ctr[1];
   if (gid < nsums) sums[gid] = 0.0f;
-  if (gid == 0) {
-    /* data parallel (csrc/rsb_dp.cu): the gradient bucket -- g_log_alpha is its last word -- may be overwritten only after every peer has finished
-       reading it for the previous update; this is the first write of the new update, every other one comes in later kernels.  Flag word
-       [16 + r] of THIS rank's flags holds the last epoch rank r has finished reading; bounded wait. */
-    if (dp_world > 1) {
-      const uint32_t epoch = dp_local[0];
-      for (int r = 0; r < dp_world; r++) {
-        const uint32_t *f = dp_flags[dp_rank] + 16 + r; bool ok = false;
-        for (int it = 0; it < (1 << 24) && !ok; it++) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory"); ok = (int32_t)(v - epoch) >= 0; }
-        if (!ok) sums[7] = __int_as_float(0x7fc00000);             /* poisoned statistics word: a missing peer is visible in the log (and rsb_dp_timeouts of the optimizer kernel fires) */
-      }
+  /* data parallel (csrc/rsb_dp.cu): the gradient bucket -- g_log_alpha is its last word -- may be overwritten only after every peer has finished reading it
+     for the previous update; the store below is the first write of the new update, every other one comes in later kernels.  Flag word [16 + r] of THIS
+     rank's flags holds the last epoch rank r has finished reading; thread r of CTA 0 polls it (bounded), all in parallel. */
+  if (blockIdx.x == 0 && dp_world > 1) {
+    if ((int)threadIdx.x < dp_world) {
+      const uint32_t epoch = dp_local[0]; const uint32_t *f = dp_flags[dp_rank] + 16 + threadIdx.x; bool ok = false;
+      for (int it = 0; it < (1 << 24) && !ok; it++) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory"); ok = (int32_t)(v - epoch) >= 0; }
+      if (!ok) sums[7] = __int_as_float(0x7fc00000);               /* poisoned statistics word: a missing peer is visible in the log (and rsb_dp_timeouts of the optimizer kernel fires) */
     }
-    g_log_alpha[0] = 0.0f;
+    __syncthreads();
   }
+  if (gid == 0) g_log_alpha[0] = 0.0f;
   if (noise && 4 * gid < 2 * B * A) {                                   /* same arithmetic as k_normal */
     uint32_t c[4] = {(uint32_t)gid, (uint32_t)step, (uint32_t)(step >> 32), noise_stream};
     philox4(c, (uint32_t)seed_noise, (uint32_t)(seed_noise >> 32));

@@ -8,12 +8,16 @@ from torch.profiler import profile, ProfilerActivity
 from robosuite_benchmark_b200.sac import EnvReplayBuffer, ParamStore, SACTrainer
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 gemm = sys.argv[2] if len(sys.argv) > 2 else "tcgen05"
-dev = torch.device("cuda:0"); O, A = 42, 7
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))); torch.cuda.set_device(dev); O, A = 42, 7
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
 rb = EnvReplayBuffer(200000, obs_dim=O, action_dim=A, device=dev, seed=1)
 g = torch.Generator(device=dev); g.manual_seed(1)
 obs = torch.randn(200000, O, device=dev, generator=g) * 0.5
 rb.add_batch(obs, torch.tanh(torch.randn(200000, A, device=dev, generator=g)), torch.rand(200000, device=dev, generator=g) * 0.1, torch.zeros(200000, dtype=torch.uint8, device=dev), obs)
-tr = SACTrainer(store=ParamStore(O, A, dev, seed=1), replay_buffer=rb, batch_size=B, discount=0.99, policy_lr=1e-3, qf_lr=5e-4, soft_target_tau=0.005, target_update_period=5, seed=1, gemm=gemm)
+tr = SACTrainer(store=ParamStore(O, A, dev, seed=1, symmetric=world > 1), world_size=world, rank=rank, replay_buffer=rb, batch_size=B, discount=0.99, policy_lr=1e-3, qf_lr=5e-4, soft_target_tau=0.005, target_update_period=5, seed=1, gemm=gemm)
 for _ in range(20):
     tr.train_step()
 torch.cuda.synchronize()
@@ -27,6 +31,11 @@ ev.sort(key=lambda e: e.time_range.start)
 starts = [i for i, e in enumerate(ev) if "k_sac_begin" in e.name or "replay_sample" in e.name]
 import collections
 print("kernel names:", dict(collections.Counter(e.name.replace("(anonymous namespace)::", "").split("(")[0][:28] for e in ev)))
+if rank != 0:
+    starts = []
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    sys.exit(0)
 if len(starts) >= 4:
     a, b = starts[2], starts[3]
     t0 = ev[a].time_range.start
@@ -36,3 +45,6 @@ if len(starts) >= 4:
         print(f"  +{e.time_range.start - t0:7.1f} us  dur {e.time_range.end - e.time_range.start:6.1f} us  end {e.time_range.end - t0:6.1f}  {nm}")
 else:
     print("could not split updates;", len(ev), "kernels")
+
+if world > 1:
+    dist.barrier(); dist.destroy_process_group()
