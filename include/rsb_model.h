@@ -24,6 +24,13 @@ enum { RSB_TASK_LIFT = 0, RSB_TASK_DOOR = 1, RSB_TASK_STACK = 2, RSB_TASK_TWOARM
 enum { RSB_CTRL_OSC_POSE = 0, RSB_CTRL_OSC_POSITION = 1, RSB_CTRL_JOINT_VELOCITY = 2,
        RSB_CTRL_JOINT_TORQUE = 3 };
 
+/* OSC_POSE goal orientation from the scaled rotation action d (3-vector):
+   EULER_T    : goal = euler2mat(d)^T R_ee, euler2mat as in mujoco-py / robosuite transform_utils (first order: rotation by -d).  This is the convention the
+                reference's committed 2020 policies were trained under: the committed Lift-Panda-OSC_POSE-SEED17 policy scores 328 +- 8 (logged 364, same maximum
+                487) with it and 21 with the axis-angle form (tools/diag_policy_transfer2.py).
+   AXIS_ANGLE : goal = quat2mat(axisangle2quat(d)) R_ee (robosuite >= 1.1: rotation by +d). */
+enum { RSB_ORI_DELTA_EULER_T = 0, RSB_ORI_DELTA_AXIS_ANGLE = 1 };
+
 #define RSB_MAX_ROBOTS 2
 #define RSB_ARM_DOF 7
 #define RSB_MAX_FINGER_GEOMS 4
@@ -88,6 +95,7 @@ typedef struct rsb_robot {
   double ki[RSB_ARM_DOF];                  /* JV integral gain (0 -> pure P law of robosuite v1.0) */
   double nullspace_kp;                     /* 10 */
   int uncouple_pos_ori;
+  int ori_delta_mode;                      /* OSC_POSE: how the scaled rotation action d sets the goal orientation (RSB_ORI_DELTA_*) */
   double torque_limit_lo[RSB_ARM_DOF], torque_limit_hi[RSB_ARM_DOF];
   double velocity_limit_lo[RSB_ARM_DOF], velocity_limit_hi[RSB_ARM_DOF];
   int has_velocity_limits;

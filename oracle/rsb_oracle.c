@@ -54,6 +54,8 @@ typedef struct {
   real goal_vel[7], summed_err[7], last_err[7], derr_buf[5][7];
   int derr_n, derr_ptr, saturated;
   real torques[7];
+  real osc_cond;                           /* condition number of J M^-1 J^T (6x6) at the last OSC evaluation: how much the torque law amplifies input round-off */
+  real torques_raw[7];                     /* the control law's output before the actuator torque limits clip it */
 } orc_ctrl;
 
 typedef struct orc_env {
@@ -877,9 +879,20 @@ static void controller_set_goal(orc_env *e, int ri, const real *action) {
   if (rb->ctrl_type == RSB_CTRL_OSC_POSE || rb->ctrl_type == RSB_CTRL_OSC_POSITION) {
     real d[6] = { 0 }; for (int k = 0; k < rb->control_dim; k++) d[k] = scale_action(rb, k, action[k]);
     if (rb->ctrl_type == RSB_CTRL_OSC_POSE && (d[3] != 0 || d[4] != 0 || d[5] != 0)) {
-      real ang = v3norm(d + 3), ax[3] = { d[3], d[4], d[5] }, q[4], Rm[9];
-      if (ang < 1e-15) { q[0] = 1; q[1] = q[2] = q[3] = 0; } else { v3normalize(ax); axisangle2q(q, ax, ang); }
-      q2mat(Rm, q); m3mul(c->goal_ori, Rm, e->site_xmat[rb->eef_site]);
+      real Rm[9];
+      if (rb->ori_delta_mode == RSB_ORI_DELTA_AXIS_ANGLE) {          /* robosuite >= 1.1: quat2mat(axisangle2quat(d)) */
+        real ang = v3norm(d + 3), ax[3] = { d[3], d[4], d[5] }, q[4];
+        if (ang < 1e-15) { q[0] = 1; q[1] = q[2] = q[3] = 0; } else { v3normalize(ax); axisangle2q(q, ax, ang); }
+        q2mat(Rm, q);
+      } else {
+        /* euler2mat(d)^T, euler2mat as in mujoco-py / robosuite transform_utils.  That function's closed form equals E = X(d0) Y(d1) Z(d2) (elementary
+           rotations about the fixed axes); composed here from the three transposed elementary rotations instead of the closed form the device code
+           uses: E^T = Z(d2)^T Y(d1)^T X(d0)^T. */
+        real cx = cos(d[3]), sx = sin(d[3]), cy = cos(d[4]), sy = sin(d[4]), cz = cos(d[5]), sz = sin(d[5]);
+        real Xt[9] = { 1, 0, 0, 0, cx, sx, 0, -sx, cx }, Yt[9] = { cy, 0, -sy, 0, 1, 0, sy, 0, cy }, Zt[9] = { cz, sz, 0, -sz, cz, 0, 0, 0, 1 }, ZY[9];
+        m3mul(ZY, Zt, Yt); m3mul(Rm, ZY, Xt);
+      }
+      m3mul(c->goal_ori, Rm, e->site_xmat[rb->eef_site]);
     }
     for (int k = 0; k < 3; k++) c->goal_pos[k] = e->site_xpos[rb->eef_site][k] + d[k];
   } else if (rb->ctrl_type == RSB_CTRL_JOINT_VELOCITY) {
@@ -904,6 +917,9 @@ static void controller_run(orc_env *e, int ri) {
     for (int r = 0; r < 6; r++) for (int cc = 0; cc < 7; cc++) { real s = 0; for (int k = 0; k < 7; k++) s += J[r * 7 + k] * Mi[k * 7 + cc]; JMi[r * 7 + cc] = s; }
     for (int r = 0; r < 6; r++) for (int cc = 0; cc < 6; cc++) { real s = 0; for (int k = 0; k < 7; k++) s += JMi[r * 7 + k] * J[cc * 7 + k]; Lfi[r * 6 + cc] = s; }
     sym_pinv(Lfi, Lf, 6);
+    { real E[36], V[36], lo = 1e300, hi = 0; memcpy(E, Lfi, sizeof E); jacobi_eig(E, V, 6);
+      for (int k = 0; k < 6; k++) { real l = fabs(E[k * 6 + k]); if (l < lo) lo = l; if (l > hi) hi = l; }
+      c->osc_cond = hi / (lo > 1e-300 ? lo : 1e-300); }
     for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) T3[r * 6 + cc] = Lfi[r * 6 + cc];
     sym_pinv(T3, Lp, 3);
     for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) T3[r * 6 + cc] = Lfi[(3 + r) * 6 + 3 + cc];
@@ -943,7 +959,7 @@ static void controller_run(orc_env *e, int ri) {
   }
   for (int k = 0; k < 7; k++) {
     real t = tau[k]; if (t < rb->torque_limit_lo[k]) t = rb->torque_limit_lo[k]; if (t > rb->torque_limit_hi[k]) t = rb->torque_limit_hi[k];
-    c->torques[k] = t; e->ctrl[rb->arm_act[k]] = t;
+    c->torques_raw[k] = tau[k]; c->torques[k] = t; e->ctrl[rb->arm_act[k]] = t;
   }
 }
 
@@ -1238,6 +1254,8 @@ int orc_get(orc_env *e, const char *name, double *out) {
   if (!strcmp(name, "contact_frame")) { for (int c = 0; c < e->ncon; c++) memcpy(out + 9 * c, e->con[c].frame, 9 * sizeof(double)); return 9 * e->ncon; }
   if (!strcmp(name, "contact_dist")) { for (int c = 0; c < e->ncon; c++) out[c] = e->con[c].dist; return e->ncon; }
   if (!strcmp(name, "contact_mu")) { for (int c = 0; c < e->ncon; c++) out[c] = e->con[c].mu; return e->ncon; }
+  if (!strcmp(name, "osc_cond")) { for (int ri = 0; ri < e->t.nrobot; ri++) out[ri] = e->rc[ri].osc_cond; return e->t.nrobot; }
+  if (!strcmp(name, "torques_raw")) { for (int ri = 0; ri < e->t.nrobot; ri++) memcpy(out + 7 * ri, e->rc[ri].torques_raw, 7 * sizeof(double)); return 7 * e->t.nrobot; }
   if (!strcmp(name, "torques")) { for (int ri = 0; ri < e->t.nrobot; ri++) memcpy(out + 7 * ri, e->rc[ri].torques, 7 * sizeof(double)); return 7 * e->t.nrobot; }
   if (!strcmp(name, "counts")) { out[0] = e->ncon; out[1] = e->nefc; out[2] = e->solver_iter; out[3] = e->timestep; return 4; }
   return -1;

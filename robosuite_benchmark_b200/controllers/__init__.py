@@ -19,6 +19,9 @@ _OSC_POSE = {
     "kp": 150, "damping_ratio": 1, "impedance_mode": "fixed", "kp_limits": [0, 300], "damping_ratio_limits": [0, 10],
     "position_limits": None, "orientation_limits": None, "uncouple_pos_ori": True, "control_delta": True,
     "interpolation": None, "ramp_ratio": 0.2,
+    # how a rotation action sets the goal orientation (include/rsb_model.h RSB_ORI_DELTA_*): "euler_transpose" = euler2mat(d)^T R_ee, the convention the
+    # reference's committed 2020 policies were trained under (evidence: DESIGN.md 2); "axis_angle" = robosuite >= 1.1
+    "orientation_delta": "euler_transpose",
 }
 _OSC_POSITION = dict(_OSC_POSE, type="OSC_POSITION", output_max=[0.05, 0.05, 0.05], output_min=[-0.05, -0.05, -0.05])
 _JOINT_VELOCITY = {

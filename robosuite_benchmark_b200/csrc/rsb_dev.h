@@ -966,10 +966,21 @@ RSB_DN void ctrl_set_goal(int so, Grp g) { real *s = RSB_SMEM + so;
     if (rb.ctrl_type == RSB_CTRL_OSC_POSE || rb.ctrl_type == RSB_CTRL_OSC_POSITION) {
       real d[6] = {0, 0, 0, 0, 0, 0}; for (int k = 0; k < rb.control_dim; k++) d[k] = scale_action(rb, k, a[k]);
       if (rb.ctrl_type == RSB_CTRL_OSC_POSE && (d[3] != 0 || d[4] != 0 || d[5] != 0)) {
-        real ang = sqrtf(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]), q[4], Rm[9], Rg[9];
-        if (ang < RSB_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
-        else { real sn, c; rsb_sincos(0.5f * ang, &sn, &c); real f = sn / ang; q[0] = c; q[1] = f * d[3]; q[2] = f * d[4]; q[3] = f * d[5]; }
-        quat2mat(Rm, q); matmul3(Rg, Rm, sxmat + 9 * rb.eef_site);
+        real Rm[9], Rg[9];
+        if (rb.ori_mode == RSB_ORI_DELTA_AXIS_ANGLE) {             /* robosuite >= 1.1: rotation by the axis-angle vector d */
+          real ang = sqrtf(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]), q[4];
+          if (ang < RSB_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
+          else { real sn, c; rsb_sincos(0.5f * ang, &sn, &c); real f = sn / ang; q[0] = c; q[1] = f * d[3]; q[2] = f * d[4]; q[3] = f * d[5]; }
+          quat2mat(Rm, q);
+        } else {                                                   /* euler2mat(d)^T with mujoco-py's euler2mat: the convention of the committed 2020 policies */
+          real si, ci, sj, cj, sk, ck; rsb_sincos(-d[5], &si, &ci); rsb_sincos(-d[4], &sj, &cj); rsb_sincos(-d[3], &sk, &ck);
+          const real cc = ci * ck, cs = ci * sk, sc = si * ck, ss = si * sk;
+          /* E[r][c] of euler2mat, stored transposed: Rm[c][r] = E[r][c] */
+          Rm[0] = cj * ci;  Rm[3] = cj * si;       Rm[6] = -sj;
+          Rm[1] = sj * cs - sc; Rm[4] = sj * ss + cc; Rm[7] = cj * sk;
+          Rm[2] = sj * cc + ss; Rm[5] = sj * sc - cs; Rm[8] = cj * ck;
+        }
+        matmul3(Rg, Rm, sxmat + 9 * rb.eef_site);
         for (int k = 0; k < 9; k++) cs[CS_GOALORI + k] = Rg[k];
       }
       for (int k = 0; k < 3; k++) cs[CS_GOALPOS + k] = sxpos[3 * rb.eef_site + k] + d[k];
@@ -1419,6 +1430,9 @@ RSB_DN void st_solve(int so, Grp g) { real *s = RSB_SMEM + so;
     if (active) { if (dl) qacc[d] += alpha * search[d]; ma += alpha * mv; iter++;
       for (int r = g.lane; r < nefc; r += RSB_LANES) jar[r] += alpha * jas[r];        /* jas = o_eJv holds J search here */
       last = scale * 0.5f * alpha * d1_0 < MDL.solver_tol; }       /* cost decrease of an exact line search on a (locally) quadratic cost: alpha |d1(0)| / 2 */
+#ifdef RSB_EMU_TRACE
+    if (g.lane == 0) printf("    scaled improvement %.3e (tolerance %.3e, scale %.3e)\n", scale * 0.5f * alpha * d1_0, MDL.solver_tol, scale);
+#endif
     gsync(g);
     if (!sany(active)) break;
   }

@@ -49,6 +49,7 @@ typedef struct DevRobot {
   float in_max[RSB_ARM_DOF], in_min[RSB_ARM_DOF], out_max[RSB_ARM_DOF], out_min[RSB_ARM_DOF];
   float kp[RSB_ARM_DOF], kd[RSB_ARM_DOF], ki[RSB_ARM_DOF], null_kp;
   int uncouple;
+  int ori_mode;                /* RSB_ORI_DELTA_* */
   float tl_lo[RSB_ARM_DOF], tl_hi[RSB_ARM_DOF], vl_lo[RSB_ARM_DOF], vl_hi[RSB_ARM_DOF];
   int has_vl;
   int act_off;                 /* offset of this robot's slice in the action vector */
@@ -273,7 +274,7 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
     q->eef_site = s->eef_site; q->eef_body = s->eef_body;
     q->nlfg = s->n_left_finger_geoms; q->nrfg = s->n_right_finger_geoms;
     for (int k = 0; k < RSB_MAX_FINGER_GEOMS; k++) { q->lfg[k] = s->left_finger_geoms[k]; q->rfg[k] = s->right_finger_geoms[k]; }
-    q->ctrl_type = s->ctrl_type; q->control_dim = s->control_dim; q->null_kp = (float)s->nullspace_kp; q->uncouple = s->uncouple_pos_ori; q->has_vl = s->has_velocity_limits;
+    q->ctrl_type = s->ctrl_type; q->control_dim = s->control_dim; q->null_kp = (float)s->nullspace_kp; q->uncouple = s->uncouple_pos_ori; q->ori_mode = s->ori_delta_mode; q->has_vl = s->has_velocity_limits;
     q->act_off = aoff; aoff += s->control_dim + s->grip_action_dim;
     if (s->grip_ndof > 2) { h.error = "gripper with more than 2 dofs unsupported"; return false; }
   }

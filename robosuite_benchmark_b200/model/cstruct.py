@@ -69,7 +69,7 @@ class RsbRobot(C.Structure):
         ("right_finger_geoms", I4), ("n_right_finger_geoms", C.c_int),
         ("ctrl_type", C.c_int), ("control_dim", C.c_int),
         ("input_max", A7), ("input_min", A7), ("output_max", A7), ("output_min", A7),
-        ("kp", A7), ("kd", A7), ("ki", A7), ("nullspace_kp", C.c_double), ("uncouple_pos_ori", C.c_int),
+        ("kp", A7), ("kd", A7), ("ki", A7), ("nullspace_kp", C.c_double), ("uncouple_pos_ori", C.c_int), ("ori_delta_mode", C.c_int),
         ("torque_limit_lo", A7), ("torque_limit_hi", A7), ("velocity_limit_lo", A7), ("velocity_limit_hi", A7),
         ("has_velocity_limits", C.c_int),
     ]

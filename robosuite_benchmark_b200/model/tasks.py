@@ -24,9 +24,11 @@ OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89}
 #: Round 2 (481 steps, limits 48 / 160, same tool): Lift-Sawyer reaches 20 contacts / 71 rows (the Rethink gripper's box fingers lie flat on
 #: the table) -- it gets its own entry; Lift-Panda 8 / 26, Stack-Sawyer 16 / 54, TwoArmLift 11 / 37, Door 4 / 17.  Truncation beyond these limits
 #: is COUNTED (RSB_INFO_NCON_OVERFLOW / NEFC_OVERFLOW): tests/test_gpu_collector.py asserts 0 events over a full random-action episode of 4096
-#: envs per family; a policy that presses the whole hand onto the table can exceed (16, 64) on Lift-Panda (measured: 6e-5 of the env-steps of
-#: an early training run) -- `suite.make(..., ncon_max=24, nefc_max=80)` removes that at the price of a second wave at 4096 envs per GPU.
-LIMITS = {"Lift": (16, 64), ("Lift", "Sawyer"): (24, 80), "Door": (16, 64), "Stack": (24, 96), "TwoArmLift": (24, 80)}
+#: envs per family.  Lift-Panda: (18, 62) costs the same shared memory as (16, 64) (28 envs per SM, 4096 envs = one wave) and has no event over a
+#: random-action episode where (16, 64) had one (17 contacts; tools/limits_sweep.py, profiles/r2_limits_sweep_lift.txt).  A TRAINED policy grasps: the
+#: committed Lift-Panda policy exceeds these limits in 1.4e-4 of its env-steps (pads + table + hand on the cube) --
+#: `suite.make(..., ncon_max=24, nefc_max=80)` removes that at the price of a second wave at 4096 envs per GPU.
+LIMITS = {"Lift": (18, 62), ("Lift", "Sawyer"): (24, 80), "Door": (16, 64), "Stack": (24, 96), "TwoArmLift": (24, 80)}
 
 
 def limits_for(env_name, robots):
@@ -78,6 +80,7 @@ def _robot_desc(m: Model, pf: str, robot: str, cc: dict) -> dict:
         input_max=vec(cc.get("input_max", 1.0), ndim), input_min=vec(cc.get("input_min", -1.0), ndim),
         output_max=vec(cc.get("output_max", 1.0), ndim), output_min=vec(cc.get("output_min", -1.0), ndim),
         kp=kp, kd=kd, ki=ki, nullspace_kp=10.0, uncouple_pos_ori=int(bool(cc.get("uncouple_pos_ori", True))),
+        ori_delta_mode={"euler_transpose": 0, "axis_angle": 1}[cc.get("orientation_delta", "euler_transpose")],
         torque_limit_lo=tl_lo, torque_limit_hi=tl_hi,
         velocity_limit_lo=vec(vl[0], 7) if vl is not None else np.zeros(7),
         velocity_limit_hi=vec(vl[1], 7) if vl is not None else np.zeros(7),

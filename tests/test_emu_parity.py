@@ -54,3 +54,38 @@ def test_done_protocol_and_terminated_episode():
     assert emu.step(np.zeros(7))[2] is True
     with pytest.raises(ValueError):
         emu.step(np.zeros(7))
+
+
+def _quat_xyzw_to_mat(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+@pytest.mark.parametrize("mode,sign", [("euler_transpose", -1.0), ("axis_angle", +1.0)])
+def test_orientation_delta_convention(mode, sign):
+    """OSC_POSE rotation actions (include/rsb_model.h RSB_ORI_DELTA_*): the shipped default turns the end effector by -d to first order (euler2mat(d)^T R_ee, the
+    convention the committed 2020 policies transfer under), "axis_angle" by +d; device code == oracle under both."""
+    cfg = load_controller_config(default_controller="OSC_POSE")
+    assert cfg["orientation_delta"] == "euler_transpose"
+    cfg["orientation_delta"] = mode
+    m, t = build_task("Lift", "Panda", cfg, ignore_done=True)
+    assert t["robot"][0]["ori_delta_mode"] == (0 if mode == "euler_transpose" else 1)
+    orc, emu = OracleEnv(m, t, ncon_max=t["ncon_max"], nefc_max=t["nefc_max"]), EmuEnv(m, t, t["ncon_max"], t["nefc_max"])
+    o0 = orc.reset(seed=3, env_id=0)
+    emu.reset(seed=3, env_id=0)
+    a = np.array([0.1, -0.2, 0.3, 0.7, -0.9, 1.0, 0.0])                # all three rotation components large: the two conventions differ at second order too
+    qp, qv, w, cs = orc.get_state()
+    emu.set_state(qp, qv, w, cs, timestep=0, bpose=orc.get_bpose())
+    o1, r1, _ = orc.step(a)
+    o2, r2, _ = emu.step(a)
+    assert np.abs(o1 - o2).max() <= 1e-4 and abs(r1 - r2) <= 1e-5
+    # direction: a pure +z rotation action for a few control steps
+    orc.reset(seed=3, env_id=0)
+    for _ in range(6):
+        o = orc.step(np.array([0, 0, 0, 0, 0, 1.0, 0]))[0]
+    R0, R1 = _quat_xyzw_to_mat(o0[24:28]), _quat_xyzw_to_mat(o[24:28])
+    D = R1 @ R0.T                                                       # world-frame rotation the end effector made
+    wz = 0.5 * (D[1, 0] - D[0, 1])                                      # sin(angle) * axis_z
+    assert sign * wz > 0.05, (mode, wz)

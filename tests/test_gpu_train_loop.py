@@ -70,3 +70,44 @@ def test_rollout_cli_on_a_committed_variant(tmp_path):
     torch.save({"evaluation/policy": MakeDeterministic(TanhGaussianPolicy.of(store))}, tmp_path / "params.pkl")
     rets = main(["--load_dir", str(tmp_path), "--num_episodes", "4", "--horizon", "100"])
     assert rets.shape == (4,) and np.isfinite(rets).all() and 0.0 < rets.mean() < 20.0
+
+
+@pytest.mark.gpu
+def test_committed_policy_transfers():
+    """The reference's committed Lift-Panda-OSC_POSE-SEED17 policy (trained in 2020 against real robosuite + MuJoCo; exported to
+    tests/golden/policy_*.npz by tools/eval_committed_policy.py) is rolled out deterministically in the CUDA env for full 500-step episodes.
+    Its logged evaluation return is 364 (last 50 epochs), maximum 486.4.  Here: 328 +- 8 over 512 episodes, maximum 487.6, the cube is lifted in 74 % of the
+    episodes (profiles/r2_policy_transfer.txt) -- with the axis-angle orientation convention the same policy scores 21.  This is the one check in this
+    repository that ties the physics + controller + observation layout to the real simulator the policy was trained in."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import robosuite_benchmark_b200 as suite
+    from robosuite_benchmark_b200.rollout import policy_from_state_dict
+    d = dict(np.load(os.path.join(GOLDEN, "policy_Lift-Panda-OSC-POSE-SEED17.npz")))
+    logged = d.pop("logged")
+    pol = policy_from_state_dict(d)
+    E, dev = 256, torch.device("cuda", 0)
+
+    def rollout(cfg):
+        env = suite.make("Lift", "Panda", controller_configs=cfg, num_envs=E, batched=True, device=dev, seed=17, horizon=500, control_freq=20,
+                         reward_shaping=True, ignore_done=True)
+        sim = env.sim
+        obs = sim.reset()
+        ret, lifted = torch.zeros(E, device=dev), torch.zeros(E, device=dev)
+        act, rew, done = torch.empty(E, 7, device=dev), torch.empty(E, device=dev), torch.empty(E, dtype=torch.uint8, device=dev)
+        for _ in range(500):
+            pol.get_actions(obs, deterministic=True, out=act)
+            sim.step(act, obs, rew, done)
+            ret += rew
+            lifted = torch.maximum(lifted, (obs[:, 34] > 0.84).float())          # object-state cube z above the table top + 4 cm
+        env.close()
+        return ret.cpu().numpy(), lifted.mean().item()
+
+    cfg = suite.load_controller_config(default_controller="OSC_POSE")
+    ret, lifted = rollout(cfg)
+    assert ret.mean() > 250.0 and lifted > 0.5, (ret.mean(), lifted)               # logged: 364; the untrained level is ~7-20
+    assert abs(ret.max() - logged.max()) < 25.0, (ret.max(), logged.max())         # best episode == best logged evaluation (486.4)
+    cfg["orientation_delta"] = "axis_angle"                                         # the robosuite >= 1.1 convention: the policy does not transfer
+    ret2, lifted2 = rollout(cfg)
+    assert ret2.mean() < 60.0 and lifted2 < 0.1, (ret2.mean(), lifted2)

@@ -11,6 +11,7 @@ d = dict(np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden"
 pol = policy_from_state_dict(d)
 E, dev = 128, torch.device("cuda", 0)
 cfg = suite.load_controller_config(default_controller="OSC_POSE")
+cfg["orientation_delta"] = "axis_angle"     # this study was run against the axis-angle controller; its finding (rotation sign) made "euler_transpose" the default
 
 def rollout(obs_fn=None, act_fn=None, steps=500, seed=17):
     env = suite.make("Lift", "Panda", controller_configs=cfg, num_envs=E, batched=True, device=dev, seed=seed, horizon=500, control_freq=20, reward_shaping=True, ignore_done=True)
