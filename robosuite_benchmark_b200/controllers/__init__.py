@@ -26,10 +26,11 @@ _OSC_POSE = {
 _OSC_POSITION = dict(_OSC_POSE, type="OSC_POSITION", output_max=[0.05, 0.05, 0.05], output_min=[-0.05, -0.05, -0.05])
 _JOINT_VELOCITY = {
     "type": "JOINT_VELOCITY", "input_max": 1, "input_min": -1, "output_max": 0.5, "output_min": -0.5,
-    "kp": 3.0, "velocity_limits": [-1, 1], "interpolation": None, "ramp_ratio": 0.2,
-    # robosuite's PID law: kp scaled by the actuator range, ki = 0.005 kp, kd = 0.001 kp.
-    # Set "ki_ratio"/"kd_ratio" to 0 and "kp_scale_by_actuator_range" to False for the v1.0 pure-P law.
-    "ki_ratio": 0.005, "kd_ratio": 0.001, "kp_scale_by_actuator_range": True,
+    # robosuite v1.0's law: torque = kv (goal_vel - qvel) + gravity/Coriolis compensation, kv = 4.  This is the law the reference's committed 2020 JOINT_VELOCITY
+    # policies were trained under: rolled out here they score 225 vs 226 logged (Lift-Panda, 5 seeds) and 21.4 vs 21.4 (Stack-Panda) with it, 23 and 7.8 with the
+    # PID law of robosuite >= 1.1 (profiles/r2_policy_transfer_jv.txt, COMPAT.md).  The later law stays available: give "kp" INSTEAD of "kv" (kp scaled by the
+    # actuator range unless "kp_scale_by_actuator_range" is false, ki = "ki_ratio" kp = 0.005 kp, kd = "kd_ratio" kp = 0.001 kp).
+    "kv": 4.0, "velocity_limits": [-1, 1], "interpolation": None, "ramp_ratio": 0.2,
 }
 _JOINT_TORQUE = {
     "type": "JOINT_TORQUE", "input_max": 1, "input_min": -1, "output_max": 0.1, "output_min": -0.1,

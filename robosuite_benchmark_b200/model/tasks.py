@@ -57,6 +57,11 @@ def _robot_desc(m: Model, pf: str, robot: str, cc: dict) -> dict:
         kp = vec(cc.get("kp", 150.0), 6)
         damping = vec(cc.get("damping_ratio", cc.get("damping", 1.0)), 6)
         kd = 2.0 * np.sqrt(kp) * damping
+    elif ctype == "JOINT_VELOCITY" and "kv" in cc:             # robosuite v1.0: pure proportional law with gain kv (controllers/__init__.py)
+        if "kp" in cc:
+            raise ValueError('JOINT_VELOCITY config holds both "kv" (v1.0 P law) and "kp" (>= 1.1 PID law): give one')
+        kp = vec(cc["kv"], 7)
+        ki, kd = np.zeros(7), np.zeros(7)
     elif ctype == "JOINT_VELOCITY":
         kp_in = cc.get("kp", 3.0)
         kp = vec(kp_in, 7)

@@ -89,3 +89,32 @@ def test_orientation_delta_convention(mode, sign):
     D = R1 @ R0.T                                                       # world-frame rotation the end effector made
     wz = 0.5 * (D[1, 0] - D[0, 1])                                      # sin(angle) * axis_z
     assert sign * wz > 0.05, (mode, wz)
+
+
+@pytest.mark.parametrize("law", ["kv", "kp"])
+def test_joint_velocity_laws(law):
+    """JOINT_VELOCITY: the default is robosuite v1.0's proportional law (kv = 4; the law the committed JV policies transfer under, COMPAT.md); a config with "kp"
+    instead of "kv" selects the PID law of robosuite >= 1.1 (integral with anti-windup, 5-sample derivative average).  Device code == oracle over several control
+    steps, so that the integrator / derivative state carried between steps is covered."""
+    cfg = load_controller_config(default_controller="JOINT_VELOCITY")
+    assert cfg["kv"] == 4.0 and "kp" not in cfg
+    if law == "kp":
+        del cfg["kv"]
+        cfg["kp"] = 3.0
+    m, t = build_task("Lift", "Panda", cfg, ignore_done=True)
+    rb = t["robot"][0]
+    if law == "kv":
+        assert np.allclose(rb["kp"], 4.0) and not np.any(rb["ki"]) and not np.any(rb["kd"])
+    else:
+        assert np.allclose(rb["kp"], 3.0 * (np.asarray(rb["torque_limit_hi"]) - np.asarray(rb["torque_limit_lo"]))) and np.allclose(rb["ki"], 0.005 * np.asarray(rb["kp"]))
+    with pytest.raises(ValueError):
+        build_task("Lift", "Panda", dict(cfg, kv=4.0, kp=3.0))
+    orc, emu = OracleEnv(m, t, ncon_max=t["ncon_max"], nefc_max=t["nefc_max"]), EmuEnv(m, t, t["ncon_max"], t["nefc_max"])
+    orc.reset(seed=9, env_id=2)
+    emu.reset(seed=9, env_id=2)
+    for k in range(4):
+        a = orc.random_action(9, 2, k)
+        o1, r1, _ = orc.step(a)
+        o2, r2, _ = emu.step(a)
+        # both sides run free (no re-synchronisation): the PID law's gains (3 x the actuator range = 522 N m s/rad on joints 1-4) amplify fp32 round-off of the velocities
+        assert np.abs(o1 - o2).max() <= (2e-4 if law == "kv" else 5e-3) and abs(r1 - r2) <= 1e-5, (k, np.abs(o1 - o2).max())
