@@ -59,9 +59,24 @@ def panda_gripper_actuators(pf: str) -> str:
             f'<position name="{pf}gripper_finger_joint2" joint="{pf}finger_joint2" kp="1000" ctrlrange="-0.04 0" forcerange="-20 20"/>')
 
 
+#: Rethink finger geometry, in the finger body's frame, for the finger on the +y side (mirrored for the other): (pos, half size) of the finger bar and of the pad.
+#: "narrow_tall" restates robosuite's rethink_gripper.xml collision boxes as recalled (finger bar 10 x 13.5 x 75 mm without friction, pad 7 x 8 x 33 mm under the
+#: fingertip; the fully open gripper clears 79 mm); "round1" is the stand-in of round 1 (16 x 3 x 16 mm pads, 63 mm clearance).  The committed Sawyer policies do
+#: not tell them apart (Lift 139 vs 144, Stack 23.5 vs 25.2 of 348 / 28 logged: profiles/r2_policy_transfer_sawyer.txt), so the shipped default stays "round1".
+RETHINK_FINGERS = {
+    "narrow_tall": dict(bar=((0, 0.01725, 0.04), (0.005, 0.00675, 0.0375)), pad=((0, 0.01255, 0.058), (0.0035, 0.004, 0.0165)), bar_friction="0 0 0"),
+    "round1": dict(bar=((0, 0.009, 0.035), (0.008, 0.006, 0.035)), pad=((0, 0.002, 0.062), (0.008, 0.0015, 0.008)), bar_friction=None),
+}
+RETHINK_FINGER_STYLE = "round1"
+
+
 def rethink_gripper(pf: str) -> str:
     """Rethink two-finger gripper for Sawyer: slide fingers along ±y."""
     pad = f'{ROBOT_COL} condim="4" friction="2 0.05 0.0001" solref="0.01 0.5"'
+    G = RETHINK_FINGERS[RETHINK_FINGER_STYLE]
+    bar = ROBOT_COL + (f' friction="{G["bar_friction"]}"' if G["bar_friction"] else "")
+    (bp, bs), (pp, ps) = G["bar"], G["pad"]
+    m = lambda v: (v[0], -v[1], v[2])
     return f'''
 <body name="{pf}right_hand" pos="0 0 0.0245" quat="0.7071068 0 0 0.7071068">
   <inertial pos="0 0 0.03" mass="0.3" diaginertia="0.001 0.001 0.001"/>
@@ -70,14 +85,14 @@ def rethink_gripper(pf: str) -> str:
   <body name="{pf}leftfinger" pos="0 0.01 0.0444">
     <inertial pos="0 0 0.03" mass="0.02" diaginertia="0.00001 0.00001 0.00001"/>
     <joint name="{pf}finger_joint1" type="slide" axis="0 1 0" range="-0.0115 0.020833" damping="100" armature="1.0" frictionloss="1.0"/>
-    <geom name="{pf}finger1_col" type="box" pos="0 0.009 0.035" size="0.008 0.006 0.035" {ROBOT_COL}/>
-    <geom name="{pf}finger1_pad" type="box" pos="0 0.002 0.062" size="0.008 0.0015 0.008" {pad}/>
+    <geom name="{pf}finger1_col" type="box" pos="{_f(bp)}" size="{_f(bs)}" {bar}/>
+    <geom name="{pf}finger1_pad" type="box" pos="{_f(pp)}" size="{_f(ps)}" {pad}/>
   </body>
   <body name="{pf}rightfinger" pos="0 -0.01 0.0444">
     <inertial pos="0 0 0.03" mass="0.02" diaginertia="0.00001 0.00001 0.00001"/>
     <joint name="{pf}finger_joint2" type="slide" axis="0 1 0" range="-0.020833 0.0115" damping="100" armature="1.0" frictionloss="1.0"/>
-    <geom name="{pf}finger2_col" type="box" pos="0 -0.009 0.035" size="0.008 0.006 0.035" {ROBOT_COL}/>
-    <geom name="{pf}finger2_pad" type="box" pos="0 -0.002 0.062" size="0.008 0.0015 0.008" {pad}/>
+    <geom name="{pf}finger2_col" type="box" pos="{_f(m(bp))}" size="{_f(bs)}" {bar}/>
+    <geom name="{pf}finger2_pad" type="box" pos="{_f(m(pp))}" size="{_f(ps)}" {pad}/>
   </body>
 </body>'''
 
@@ -153,7 +168,9 @@ def sawyer_actuators(pf: str) -> str:
 
 SAWYER_INIT_QPOS = [0, -1.18, 0.00, 2.18, 0.00, 0.57, 3.3161]
 SAWYER_GRIP_INIT = [0.020833, -0.020833]
-SAWYER_GRIP_SIGN = [1.0, -1.0]
+#: a positive gripper action CLOSES (robosuite: -1 open, +1 closed): finger 1 (on +y, open at +0.020833) moves to its lower limit.  Round 1 had the signs the other
+#: way round; the committed Lift-Sawyer policies never lifted the cube then (best episode 228 of 486) and do with these (best 485.7).
+SAWYER_GRIP_SIGN = [-1.0, 1.0]
 
 ROBOTS = {
     "Panda": dict(body=panda, act=panda_actuators, init_qpos=PANDA_INIT_QPOS, grip_init=PANDA_GRIP_INIT,

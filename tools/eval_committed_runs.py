@@ -33,6 +33,13 @@ if mode == "export":
 else:
     import torch
     from robosuite_benchmark_b200.rollout import evaluate_policy
+    from robosuite_benchmark_b200.model import assets as _A
+    for spec in filter(None, os.environ.get("RSB_EVAL_ASSET_MODULE", "").split(";")):         # e.g. "RETHINK_FINGER_STYLE=round1": module-level switches of model/assets.py
+        k, v = spec.split("=")
+        setattr(_A, k, v)
+    for spec in filter(None, os.environ.get("RSB_EVAL_ASSET_OVERRIDES", "").split(";")):      # e.g. "Sawyer.grip_sign=[-1,1]": patch model/assets.py ROBOTS entries (what-if studies)
+        k, v = spec.split("="); r, field = k.split(".")
+        _A.ROBOTS[r][field] = json.loads(v)
     episodes = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     filt = sys.argv[3] if len(sys.argv) > 3 else ""
     extra = json.loads(os.environ.get("RSB_EVAL_CONTROLLER_OVERRIDES", "{}"))          # e.g. '{"orientation_delta": "axis_angle"}' (applied through a temp controller json)
