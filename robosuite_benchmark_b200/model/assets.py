@@ -186,10 +186,10 @@ TABLE_FULL = (0.8, 0.8, 0.05)
 ROBOT_BASE_Z = 0.912
 
 
-def table_arena(full=TABLE_FULL, friction=(1, 0.005, 0.0001)) -> str:
+def table_arena(full=TABLE_FULL, friction=(1, 0.005, 0.0001), offset=(0.0, 0.0)) -> str:
     hx, hy, hz = full[0] / 2, full[1] / 2, full[2] / 2
     return (f'<geom name="floor" type="plane" pos="0 0 0" size="3 3 0.125" {WORLD_COL}/>'
-            f'<body name="table" pos="0 0 {TABLE_HEIGHT - hz}">'
+            f'<body name="table" pos="{offset[0]} {offset[1]} {TABLE_HEIGHT - hz}">'
             f'<geom name="table_collision" type="box" size="{hx} {hy} {hz}" friction="{_f(friction)}" {WORLD_COL}/>'
             f'</body>')
 
@@ -226,20 +226,79 @@ def door_object(pos=(0.12, -0.2, TABLE_HEIGHT), yaw=-PI / 2, hinge_damping=0.1, 
 </body>'''
 
 
+#: which door the Door task stands on its table: "robosuite_recalled" (door_object_recalled below, the default since round 2) or "round1" (door_object above, a
+#: half-size push door calibrated by the reset distance only).  Chosen by the transfer of the committed Door-Panda policies, mean return here / logged over 5 seeds
+#: (profiles/r2_policy_transfer_door.txt): round1 1.4 / 140 (JOINT_VELOCITY) and 52 / 368 (OSC_POSE); recalled, no bolt 110 / 140 and 116 / 368, best episodes
+#: 446 / 461 and 483 / 488.
+DOOR_STYLE = "robosuite_recalled"
+#: the Door task's table: robosuite's Door env uses a narrow table beside the robot (full size 0.8 x 0.3 x 0.05 at offset (-0.2, -0.35, 0.8)), as recalled
+DOOR_TABLE_FULL, DOOR_TABLE_OFFSET = (0.8, 0.3, 0.05), (-0.2, -0.35)
+#: latch handle: spring and friction as recalled; inertia = the physical estimate for a 0.1 kg handle (the recalled XML value 0.048 / 0.041 / 0.011 transfers worse:
+#: 83 vs 116); `bolt`: a box on the latch behind the free post that keeps the door shut until the handle is turned ~66 degrees.  robosuite's use_latch=True has such
+#: a lock, but its geometry is not recalled, and every bolt tried here makes the committed policies transfer WORSE (JV 40 vs 110, OSC 34 vs 116), so it is off.
+DOOR_LATCH = dict(stiffness=1.0, damping=0.0, frictionloss=0.1, inertia=(0.001, 0.001, 0.001), bolt=False,
+                  bolt_pos=(-0.065, 0.044, 0.0), bolt_size=(0.045, 0.01, 0.015))
+
+
+def door_object_recalled(pos=(-0.12, -0.35, TABLE_HEIGHT + 0.3), yaw=-PI / 2, hinge_damping=0.1, hinge_frictionloss=0.0) -> str:
+    """robosuite's DoorObject(lock=True) (objects/door_lock.xml) restated from memory with box primitives -- every number here is UPSTREAM RECALL, kept because the
+    committed Door policies transfer better with it than with the round-1 stand-in (COMPAT.md): a 0.44 x 0.04 x 0.58 m panel between two 0.6 m posts, hinged at one
+    post (range 0..0.4 rad, DoorObject(friction=0, damping=0.1)), opening TOWARDS the side the handle is on (the robot pulls); a spring-loaded latch handle
+    (stiffness 1, frictionloss 0.1, range -pi/2..0) sticking 0.10 m out of the panel with the `handle` site at the far end of its 0.15 m grip bar; a bolt on the
+    latch that sits behind the free post until the handle is turned by more than ~66 degrees.  The object's frame body (pos 0 0.22 0, yaw -90 deg in the object root)
+    is folded into the coordinates: frame-local (x, y) -> root (y, 0.22 - x).  Root origin = centre height of the door (bottom_offset -0.3)."""
+    q = f"{np.cos(yaw / 2):.10g} 0 0 {np.sin(yaw / 2):.10g}"
+    col = WORLD_COL + ' friction="1 1 1"'
+    L = DOOR_LATCH
+    bolt = f'<geom name="latch_bolt" type="box" pos="{_f(L["bolt_pos"])}" size="{_f(L["bolt_size"])}" {col}/>' if L["bolt"] else ""
+    return f'''
+<body name="door_root" pos="{_f(pos)}" quat="{q}">
+  <geom name="door_post_l" type="box" pos="0 0.175 0" size="0.03 0.021 0.3" {col}/>
+  <geom name="door_post_r" type="box" pos="0 -0.335 0" size="0.03 0.021 0.3" {col}/>
+  <body name="door" pos="0 -0.08 0" quat="0.7071068 0 0 -0.7071068">
+    <inertial pos="0.0296816 -0.00152345 0" mass="2.43455" diaginertia="0.0521615 0.0913751 0.043714"/>
+    <joint name="door_hinge" type="hinge" pos="0.255 0 0" axis="0 0 1" range="0 0.4" damping="{hinge_damping}" frictionloss="{hinge_frictionloss}"/>
+    <geom name="door_panel" type="box" size="0.22 0.02 0.29" {col}/>
+    <body name="latch" pos="-0.175 0 -0.025">
+      <inertial pos="-0.017762 0.0138544 0" mass="0.1" diaginertia="{_f(L["inertia"])}"/>
+      <joint name="latch_joint" type="hinge" axis="0 1 0" range="-1.57 0" damping="{L["damping"]}" frictionloss="{L["frictionloss"]}" stiffness="{L["stiffness"]}" springref="0"/>
+      <geom name="latch_stem" type="box" pos="0 -0.0625 0" size="0.02 0.0625 0.02" {col}/>
+      <geom name="latch_handle" type="box" pos="0.075 -0.10 0" size="0.075 0.015 0.02" {col}/>
+      {bolt}
+      <site name="door_handle" pos="0.125 -0.10 0"/>
+    </body>
+  </body>
+</body>'''
+
+
+#: TwoArmLift pot, robosuite's PotWithHandlesObject as recalled: body half size 0.07, wall thickness 0.025 (2.8 kg at density 1000), handle loops 9 cm out at
+#: z = 0.07 - 0.01 with a main bar of half length 0.045 + 0.01 and two side bars (half 0.01 x 0.045 x 0.01 at x = +-0.045) that collide.  Round 1 had 5 mm walls
+#: (1.1 kg), bars at z = 0.05 of half length 0.045 and visual-only side bars: POT = dict(thickness=0.005, handle_z=0.05, bar_half=0.045, side_bars=False).
+#: Transfer of the 5 committed TwoArmLift-PandaPanda policies (mean return here / logged 110; profiles/r2_policy_transfer_pot.txt): round-1 pot 52, recalled pot 61.
+POT = dict(thickness=0.025, handle_z=0.06, bar_half=0.055, side_bars=True)
+#: |y| of the two robot bases in TwoArmLift's single-arm-opposed layout: robosuite rotates base_xpos_offset["table"](0.8) = (-0.56, 0, 0) by +-90 degrees.
+#: Round 1 used 0.69 (fitted to the logged epoch-0 return); the committed policies say 0.56: 80 vs 52 with the round-1 pot, 86 vs 61 with the recalled one.
+TWO_ARM_BASE_Y = 0.56
+
+
 def pot_with_handles(name="pot", pos=(0, 0, TABLE_HEIGHT + 0.07), density=1000) -> str:
     """robosuite PotWithHandlesObject from boxes: hollow body (base + 4 walls, half size 0.07) and two handle grip bars 9 cm out along
-    -y / +y (the side bars of each handle loop are visual only)."""
+    -y / +y (geometry switches: POT above)."""
     col = WORLD_COL + f' density="{density}" friction="1 0.005 0.0001"'
-    h, t = 0.07, 0.005
-    g = [f'<geom name="{name}_base" type="box" pos="0 0 {-h + 0.01}" size="{h} {h} 0.01" {col}/>',
-         f'<geom name="{name}_wall_xp" type="box" pos="{h - t} 0 0.01" size="{t} {h} {h - 0.01}" {col}/>',
-         f'<geom name="{name}_wall_xn" type="box" pos="{-h + t} 0 0.01" size="{t} {h} {h - 0.01}" {col}/>',
-         f'<geom name="{name}_wall_yp" type="box" pos="0 {h - t} 0.01" size="{h - 2 * t} {t} {h - 0.01}" {col}/>',
-         f'<geom name="{name}_wall_yn" type="box" pos="0 {-h + t} 0.01" size="{h - 2 * t} {t} {h - 0.01}" {col}/>']
+    h, t = 0.07, POT["thickness"]
+    bt = max(0.01, t / 2)                                    # half thickness of the base slab
+    g = [f'<geom name="{name}_base" type="box" pos="0 0 {-h + bt}" size="{h} {h} {bt}" {col}/>',
+         f'<geom name="{name}_wall_xp" type="box" pos="{h - t} 0 {bt}" size="{t} {h} {h - bt}" {col}/>',
+         f'<geom name="{name}_wall_xn" type="box" pos="{-h + t} 0 {bt}" size="{t} {h} {h - bt}" {col}/>',
+         f'<geom name="{name}_wall_yp" type="box" pos="0 {h - t} {bt}" size="{h - 2 * t} {t} {h - bt}" {col}/>',
+         f'<geom name="{name}_wall_yn" type="box" pos="0 {-h + t} {bt}" size="{h - 2 * t} {t} {h - bt}" {col}/>']
     for k, sg in enumerate((-1, 1)):
         y = sg * (h + 0.09)
-        g.append(f'<geom name="{name}_handle{k}" type="box" pos="0 {y} 0.05" size="0.045 0.01 0.01" {col}/>')
-        g.append(f'<site name="{name}_handle{k}" pos="0 {y} 0.05"/>')
+        g.append(f'<geom name="{name}_handle{k}" type="box" pos="0 {y} {POT["handle_z"]}" size="{POT["bar_half"]} 0.01 0.01" {col}/>')
+        if POT["side_bars"]:
+            for sx in (-1, 1):
+                g.append(f'<geom name="{name}_handle{k}_s{(sx + 1) // 2}" type="box" pos="{sx * 0.045} {sg * (h + 0.045)} {POT["handle_z"]}" size="0.01 0.045 0.01" {col}/>')
+        g.append(f'<site name="{name}_handle{k}" pos="0 {y} {POT["handle_z"]}"/>')
     return f'<body name="{name}" pos="{_f(pos)}"><freejoint name="{name}_joint"/>' + "".join(g) + "</body>"
 
 

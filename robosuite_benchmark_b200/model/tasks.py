@@ -215,7 +215,11 @@ def _door(robots, env_configuration):
     """Door: hinged door with a latch handle standing on the table; the door root is re-placed at every reset."""
     assert len(robots) == 1, "Door takes one robot"
     body, act = _single_arm_world(robots[0])
-    world = A.table_arena() + body + A.door_object()
+    recalled = A.DOOR_STYLE == "robosuite_recalled"
+    if recalled:
+        world = A.table_arena(full=A.DOOR_TABLE_FULL, offset=A.DOOR_TABLE_OFFSET) + body + A.door_object_recalled()
+    else:
+        world = A.table_arena() + body + A.door_object()
     xml = A.scene(world, act)
 
     def objs(m: Model):
@@ -231,6 +235,9 @@ def _door(robots, env_configuration):
         o["place_x"][2], o["place_y"][2], o["place_yaw"][2] = [0.07, 0.09], [-0.01, 0.01], [-np.pi / 2 - 0.25, -np.pi / 2]
         o["place_z"][2] = A.TABLE_HEIGHT
         o["place_ref"] = np.array([0.04, -0.2, A.TABLE_HEIGHT])
+        if recalled:                                       # UniformRandomSampler about the table offset; the object's bottom (0.3 below its origin) on the table top
+            o["place_z"][2] = A.TABLE_HEIGHT + 0.3
+            o["place_ref"] = np.array([A.DOOR_TABLE_OFFSET[0], A.DOOR_TABLE_OFFSET[1], A.TABLE_HEIGHT])
         return o
 
     return xml, objs
@@ -242,7 +249,7 @@ def _two_arm_lift(robots, env_configuration):
     if env_configuration not in ("single-arm-opposed", "default", None):
         raise NotImplementedError(f"env_configuration {env_configuration!r} is not implemented (single-arm-opposed only)")
     bodies, acts = "", ""
-    for i, (r, yaw, y) in enumerate(zip(robots, (np.pi / 2, -np.pi / 2), (-0.69, 0.69))):
+    for i, (r, yaw, y) in enumerate(zip(robots, (np.pi / 2, -np.pi / 2), (-A.TWO_ARM_BASE_Y, A.TWO_ARM_BASE_Y))):
         R = A.ROBOTS[r]
         quat = (np.cos(yaw / 2), 0, 0, np.sin(yaw / 2))
         bodies += R["body"](f"robot{i}_", (0.0, y, A.ROBOT_BASE_Z), quat)

@@ -35,8 +35,11 @@ else:
     from robosuite_benchmark_b200.rollout import evaluate_policy
     from robosuite_benchmark_b200.model import assets as _A
     for spec in filter(None, os.environ.get("RSB_EVAL_ASSET_MODULE", "").split(";")):         # e.g. "RETHINK_FINGER_STYLE=round1": module-level switches of model/assets.py
-        k, v = spec.split("=")
-        setattr(_A, k, v)
+        k, v = spec.split("=", 1)
+        try: v = json.loads(v)
+        except ValueError: pass
+        if isinstance(v, dict) and isinstance(getattr(_A, k, None), dict): getattr(_A, k).update(v)
+        else: setattr(_A, k, v)
     for spec in filter(None, os.environ.get("RSB_EVAL_ASSET_OVERRIDES", "").split(";")):      # e.g. "Sawyer.grip_sign=[-1,1]": patch model/assets.py ROBOTS entries (what-if studies)
         k, v = spec.split("="); r, field = k.split(".")
         _A.ROBOTS[r][field] = json.loads(v)
