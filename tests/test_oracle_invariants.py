@@ -164,3 +164,27 @@ def test_box_box_face_and_edge():
     d = 0.1 * np.sqrt(2)
     c = box_box([0, 0, 0], Ra, [0.1] * 3, [2 * d - 0.005, 0, 0], Rb, [0.1] * 3)
     assert c.shape[0] == 1 and abs(c[0, 6] + 0.005) < 1e-9 and np.allclose(c[0, 3:6], [1, 0, 0], atol=1e-9)
+
+
+@pytest.mark.parametrize("switch,value,env,robots", [("DOOR_STYLE", "round1", "Door", ["Panda"]), ("DOOR_STYLE", "robosuite_recalled", "Door", ["Sawyer"]),
+                                                     ("RETHINK_FINGER_STYLE", "narrow_tall", "Lift", ["Sawyer"]),
+                                                     ("POT", dict(thickness=0.005, handle_z=0.05, bar_half=0.045, side_bars=False), "TwoArmLift", ["Panda", "Panda"])])
+def test_asset_switches_build_and_step(switch, value, env, robots):
+    """model/assets.py keeps the round-1 stand-ins selectable next to the variants the policy-transfer study chose (COMPAT.md): every switch must still compile
+    and step without NaN, the settled scene must stay settled (no initial penetration kicking things around)."""
+    from robosuite_benchmark_b200.model import assets as A
+    from robosuite_benchmark_b200.controllers import load_controller_config
+    from robosuite_benchmark_b200.model.tasks import build_task
+    from oracle.oracle import OracleEnv
+    old = getattr(A, switch)
+    try:
+        setattr(A, switch, dict(old, **value) if isinstance(value, dict) else value)
+        m, t = build_task(env, robots, load_controller_config(default_controller="OSC_POSE"), ignore_done=True)
+        orc = OracleEnv(m, t, ncon_max=t["ncon_max"], nefc_max=t["nefc_max"])
+        o = orc.reset(seed=3, env_id=0)
+        for _ in range(5):
+            o, r, _ = orc.step(np.zeros(t["act_dim"]))
+        qv = orc.get_state()[1]
+        assert np.isfinite(o).all() and np.isfinite(r) and np.abs(qv).max() < 0.5, np.abs(qv).max()
+    finally:
+        setattr(A, switch, old)
