@@ -11,7 +11,7 @@ states/actions resident in HBM (CUDA events around each step, L2 flushed between
 
 --config selects the other BASELINE.json configs (configs[2] Door-Panda-JOINT_VELOCITY x 16384, configs[3] Stack-Sawyer-OSC_POSE,
 configs[4] TwoArmLift-PandaPanda-OSC_POSE); the default (lift) line also carries a short steady-state measurement of each of them
-(`other_configs`), the mean over one whole 500-step episode (`full_episode`), the SAC updates/s legs (`sac`) and a short run of the
+(`other_configs`), the same batch under a trained policy's contact load (`trained_policy`), the mean over one whole 500-step episode (`full_episode`), the SAC updates/s legs (`sac`) and a short run of the
 end-to-end training loop (`train`).  --mode train makes the training loop the timed workload: one bench "step" = one epoch of the
 reference's loop (util/rlkit_custom.py:215-239: evaluation rollouts, exploration rollouts with per-step policy inference written
 straight into the replay ring, add_paths, SAC updates sampled from that ring), under torchrun with the gradient all-reduce.
@@ -238,6 +238,44 @@ def steady_state_rate(cfg, E, dev, env_id_base, steps, preroll=PREROLL, full_epi
     return out
 
 
+def trained_policy_rate(cfg, E, dev, env_id_base):
+    """The same Lift batch driven by a TRAINED policy instead of random actions: the reference's committed Lift-Panda-OSC_POSE-SEED17 policy (weights in
+    tests/golden, rolled out by the package's own policy kernel).  A policy that reaches, grasps and lifts keeps 10-20 contacts alive per env, so a control step
+    costs more than under random actions; this is the load a late-training collector sees.  One whole episode; k_step timed with CUDA events on steps 100-119."""
+    import numpy as np
+    import torch
+    from robosuite_benchmark_b200.rollout import policy_from_state_dict
+    path = os.path.join(ROOT, "tests", "golden", "policy_Lift-Panda-OSC-POSE-SEED17.npz")
+    if not os.path.exists(path):
+        return None
+    d = dict(np.load(path)); logged = d.pop("logged")
+    pol = policy_from_state_dict(d)
+    env = _make_env(cfg, E, dev, env_id_base)
+    sim = env.sim
+    obs = torch.zeros(E, sim.obs_dim, device=dev); rew = torch.zeros(E, device=dev); ret = torch.zeros(E, device=dev)
+    done = torch.zeros(E, dtype=torch.uint8, device=dev); act = torch.zeros(E, sim.act_dim, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sim.reset(obs=obs)
+    ev = []
+    for k in range(HORIZON):
+        pol.get_actions(obs, deterministic=True, out=act)
+        if 100 <= k < 120:
+            flush.zero_()
+            ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            ev[-1][0].record(); sim.step(act, obs, rew, done); ev[-1][1].record()
+        else:
+            sim.step(act, obs, rew, done)
+        ret += rew
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+    out = {"workload": f"{family(cfg)}, {E} batched envs, deterministic actions of the committed SEED17 policy", "kernel_ms": ms, "steps_per_s": E / ms * 1000.0,
+           "timed_steps": len(ev), "episode_return_mean": float(ret.mean().item()), "logged_return_last50_mean": float(logged[-50:].mean()),
+           "truncation": sim.counters()}
+    out["truncation"]["env_steps"] = E * HORIZON
+    env.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -355,6 +393,10 @@ def run_ours(args):
                 r["steps_per_s_all_gpus"] = whole_job_rate(c["envs"], world, max_over_ranks(r["kernel_ms"], dev) / 1000.0)
                 others[name] = r
             extras["other_configs"] = others
+            tp = trained_policy_rate(cfg, E, dev, env_id_base)
+            if tp is not None:
+                tp["steps_per_s_all_gpus"] = whole_job_rate(E, world, max_over_ranks(tp["kernel_ms"], dev) / 1000.0)
+                extras["trained_policy"] = tp
     sac = None
     if not args.no_sac:
         sac = sac_bench(dev, obs_dim, act_dim, world, rank)
