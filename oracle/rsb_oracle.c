@@ -11,7 +11,12 @@
  * mujoco-py>=2.0.2.9 -> MuJoCo 2.0 (requirements.txt:4, Dockerfile:47).  This file restates
  * their published algorithms as summarised in SURVEY.md Appendix A (each function cites the
  * paragraph it follows); it is validated by physics invariants (tests/test_oracle_*.py), not
- * by outputs of the real MuJoCo.
+ * by outputs of the real MuJoCo.  The one tie to the real simulator is statistical: the
+ * reference's committed 2020 policies (trained against robosuite + MuJoCo) are rolled out in
+ * the CUDA env that this oracle checks, and the Panda families reach 0.78-1.02 of their logged
+ * returns with equal best episodes (profiles/r2_policy_transfer_all.txt; the
+ * OSC orientation rule, the JOINT_VELOCITY law and several asset choices were selected by
+ * that transfer, COMPAT.md).  Numerically the parity stays unpinned.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  It deliberately uses different formulations from the CUDA kernels

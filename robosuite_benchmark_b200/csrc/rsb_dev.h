@@ -974,11 +974,11 @@ RSB_DN void ctrl_set_goal(int so, Grp g) { real *s = RSB_SMEM + so;
           quat2mat(Rm, q);
         } else {                                                   /* euler2mat(d)^T with mujoco-py's euler2mat: the convention of the committed 2020 policies */
           real si, ci, sj, cj, sk, ck; rsb_sincos(-d[5], &si, &ci); rsb_sincos(-d[4], &sj, &cj); rsb_sincos(-d[3], &sk, &ck);
-          const real cc = ci * ck, cs = ci * sk, sc = si * ck, ss = si * sk;
+          const real cick = ci * ck, cisk = ci * sk, sick = si * ck, sisk = si * sk;
           /* E[r][c] of euler2mat, stored transposed: Rm[c][r] = E[r][c] */
-          Rm[0] = cj * ci;  Rm[3] = cj * si;       Rm[6] = -sj;
-          Rm[1] = sj * cs - sc; Rm[4] = sj * ss + cc; Rm[7] = cj * sk;
-          Rm[2] = sj * cc + ss; Rm[5] = sj * sc - cs; Rm[8] = cj * ck;
+          Rm[0] = cj * ci;          Rm[3] = cj * si;          Rm[6] = -sj;
+          Rm[1] = sj * cisk - sick; Rm[4] = sj * sisk + cick; Rm[7] = cj * sk;
+          Rm[2] = sj * cick + sisk; Rm[5] = sj * sick - cisk; Rm[8] = cj * ck;
         }
         matmul3(Rg, Rm, sxmat + 9 * rb.eef_site);
         for (int k = 0; k < 9; k++) cs[CS_GOALORI + k] = Rg[k];
