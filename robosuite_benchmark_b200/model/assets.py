@@ -103,6 +103,10 @@ def rethink_gripper_actuators(pf: str) -> str:
 
 
 # ----------------------------------------------------------------------------- robots
+#: collide the Panda's arm links (capsule envelopes) with the scene, not only its hand and fingers
+ARM_LINK_CAPSULES = False
+
+
 def panda(pf: str, base_pos, base_quat=(1, 0, 0, 0)) -> str:
     """Franka Emika Panda, 7 hinge joints about local z (link frames: SURVEY.md A.5)."""
     lim = [(-2.8973, 2.8973), (-1.7628, 1.7628), (-2.8973, 2.8973), (-3.0718, -0.0698),
@@ -114,12 +118,18 @@ def panda(pf: str, base_pos, base_quat=(1, 0, 0, 0)) -> str:
     inert = [("0 0 -0.07", 3, 0.3), ("0 -0.1 0", 3, 0.3), ("0.04 0 -0.05", 2, 0.2), ("-0.04 0.05 0", 2, 0.2),
              ("0 0 -0.15", 2, 0.2), ("0.06 0 0", 1.5, 0.1), ("0 0 0.08", 0.5, 0.05)]
     damp = [0.1, 0.1, 0.1, 0.1, 0.1, 0.01, 0.01]
+    # arm-link collision capsules (robosuite collides the links' meshes): rough envelopes of the public link geometry, in the link frames above.  Off unless
+    # ARM_LINK_CAPSULES says so for the task being built (model/tasks.py): they cost collision pairs on every env, and only tasks where the arm itself touches
+    # the scene need them.
+    caps = {1: ("0 0 -0.15 0 0 0", 0.06), 2: ("0 0 0 0 -0.316 0", 0.06), 4: ("0 0 0 -0.0825 0.384 0", 0.06), 6: ("0 0 0 0.088 0 0", 0.05), 7: ("0 0 0 0 0 0.107", 0.04)}
     s = f'<body name="{pf}base" pos="{_f(base_pos)}" quat="{_f(base_quat)}">'
     s += f'<inertial pos="0 0 0.05" mass="4" diaginertia="0.4 0.4 0.4"/>'
     for i in range(7):
         s += (f'<body name="{pf}link{i + 1}" pos="{frames[i][0]}" quat="{frames[i][1]}">'
               f'<inertial pos="{inert[i][0]}" mass="{inert[i][1]}" diaginertia="{inert[i][2]} {inert[i][2]} {inert[i][2]}"/>'
               f'<joint name="{pf}joint{i + 1}" type="hinge" axis="0 0 1" range="{lim[i][0]} {lim[i][1]}" damping="{damp[i]}"/>')
+        if ARM_LINK_CAPSULES and (i + 1) in caps:
+            s += f'<geom name="{pf}link{i + 1}_col" type="capsule" fromto="{caps[i + 1][0]}" size="{caps[i + 1][1]}" {ROBOT_COL}/>'
     s += panda_gripper(pf)
     s += "</body>" * 8
     return s
@@ -227,41 +237,63 @@ def door_object(pos=(0.12, -0.2, TABLE_HEIGHT), yaw=-PI / 2, hinge_damping=0.1, 
 
 
 #: which door the Door task stands on its table: "robosuite_recalled" (door_object_recalled below, the default since round 2) or "round1" (door_object above, a
-#: half-size push door calibrated by the reset distance only).  Chosen by the transfer of the committed Door-Panda policies, mean return here / logged over 5 seeds
-#: (profiles/r2_policy_transfer_door.txt): round1 1.4 / 140 (JOINT_VELOCITY) and 52 / 368 (OSC_POSE); recalled, no bolt 110 / 140 and 116 / 368, best episodes
-#: 446 / 461 and 483 / 488.
-DOOR_STYLE = "robosuite_recalled"
+#: half-size door calibrated by the reset distance only).  Chosen by the transfer of the committed Door policies, mean return here / logged over 5 seeds:
+#: round1 1.4 / 140 (Panda JOINT_VELOCITY), 52 / 368 (Panda OSC_POSE), 0.5 / 96 and 47 / 267 (Sawyer); recalled door with the hinge / latch choices below 247 / 140,
+#: 216 / 368, 59 / 96 and 261 / 267 (profiles/r2_policy_transfer_all.txt, r2_door_fit_cpu.txt).
 #: the Door task's table: robosuite's Door env uses a narrow table beside the robot (full size 0.8 x 0.3 x 0.05 at offset (-0.2, -0.35, 0.8)), as recalled
 DOOR_TABLE_FULL, DOOR_TABLE_OFFSET = (0.8, 0.3, 0.05), (-0.2, -0.35)
-#: latch handle: spring and friction as recalled; inertia = the physical estimate for a 0.1 kg handle (the recalled XML value 0.048 / 0.041 / 0.011 transfers worse:
-#: 83 vs 116); `bolt`: a box on the latch behind the free post that keeps the door shut until the handle is turned ~66 degrees.  robosuite's use_latch=True has such
-#: a lock, but its geometry is not recalled, and every bolt tried here makes the committed policies transfer WORSE (JV 40 vs 110, OSC 34 vs 116), so it is off.
-DOOR_LATCH = dict(stiffness=1.0, damping=0.0, frictionloss=0.1, inertia=(0.001, 0.001, 0.001), bolt=False,
-                  bolt_pos=(-0.065, 0.044, 0.0), bolt_size=(0.045, 0.01, 0.015))
+#: latch handle: spring and friction as recalled; inertia = the physical estimate for a 0.1 kg handle (the recalled XML value 0.048 / 0.041 / 0.011 transfers no
+#: better); axis -y: the far end of the handle bar is pushed DOWN to turn it (with +y, as first restated, the policies hardly turn it).  `bolt`: robosuite's
+#: use_latch=True locks the door until the handle is turned, but that geometry is not recalled and every lock tried here -- a bolt behind the post (True) or a
+#: bolt / strike pair that collide only with each other and release at a chosen handle angle ("strike") -- makes the committed policies transfer WORSE (one OSC
+#: policy that logs 444 never touches the handle), so the door is unlocked (False).
+DOOR_LATCH = dict(stiffness=1.0, damping=0.0, frictionloss=0.1, inertia=(0.001, 0.001, 0.001), bolt=False, axis=(0, -1, 0),
+                  bolt_pos=(-0.065, 0.044, 0.0), bolt_size=(0.045, 0.01, 0.015), bolt_r=(0.03, 0.048), bolt_h=0.004, strike_h=0.006)
+
+
+#: hinge: axis -z = the panel swings AWAY from the side the handle is on (the robot pushes); damping / frictionloss 1 / 1 are the values of door_lock.xml as recalled.
+#: Both chosen by the committed Door-Panda policies (tools/fit_assets_cpu.py on the CPU oracle, profiles/r2_door_fit_cpu.txt): with +z (pull) the OSC policies that
+#: log 408-466 score 87-202, with -z 322-470; with the DoorObject(friction=0, damping=0.1) values recalled from door.py the JOINT_VELOCITY policies that FAIL in
+#: their own logs (14, 105) open the door here (347, 437) -- a velocity-controlled arm pushes with a few newtons, which a frictionloss of 1 N m holds back.
+DOOR_HINGE = dict(axis=(0, 0, -1), damping=1.0, frictionloss=1.0)
+DOOR_PANEL = dict(mass=2.43455)
 
 
 def door_object_recalled(pos=(-0.12, -0.35, TABLE_HEIGHT + 0.3), yaw=-PI / 2, hinge_damping=0.1, hinge_frictionloss=0.0) -> str:
     """robosuite's DoorObject(lock=True) (objects/door_lock.xml) restated from memory with box primitives -- every number here is UPSTREAM RECALL, kept because the
     committed Door policies transfer better with it than with the round-1 stand-in (COMPAT.md): a 0.44 x 0.04 x 0.58 m panel between two 0.6 m posts, hinged at one
-    post (range 0..0.4 rad, DoorObject(friction=0, damping=0.1)), opening TOWARDS the side the handle is on (the robot pulls); a spring-loaded latch handle
-    (stiffness 1, frictionloss 0.1, range -pi/2..0) sticking 0.10 m out of the panel with the `handle` site at the far end of its 0.15 m grip bar; a bolt on the
-    latch that sits behind the free post until the handle is turned by more than ~66 degrees.  The object's frame body (pos 0 0.22 0, yaw -90 deg in the object root)
+    post (range 0..0.4 rad; direction, damping and frictionloss: DOOR_HINGE); a spring-loaded latch handle
+    (stiffness 1, frictionloss 0.1, range -pi/2..0) sticking 0.10 m out of the panel with the `handle` site at the far end of its 0.15 m grip bar; optionally a
+    lock (DOOR_LATCH["bolt"]).  The object's frame body (pos 0 0.22 0, yaw -90 deg in the object root)
     is folded into the coordinates: frame-local (x, y) -> root (y, 0.22 - x).  Root origin = centre height of the door (bottom_offset -0.3)."""
     q = f"{np.cos(yaw / 2):.10g} 0 0 {np.sin(yaw / 2):.10g}"
     col = WORLD_COL + ' friction="1 1 1"'
     L = DOOR_LATCH
-    bolt = f'<geom name="latch_bolt" type="box" pos="{_f(L["bolt_pos"])}" size="{_f(L["bolt_size"])}" {col}/>' if L["bolt"] else ""
+    bolt = f'<geom name="latch_bolt" type="box" pos="{_f(L["bolt_pos"])}" size="{_f(L["bolt_size"])}" {col}/>' if L["bolt"] is True else ""
+    strike = ""
+    if L["bolt"] == "strike":
+        # A lock of our own making (robosuite's is not recalled): a short bolt on the latch, r0..r1 from the latch axis, and a strike plate on the frame that the bolt
+        # runs into when the door moves in its opening direction.  Both collide ONLY with each other (contype / conaffinity bit 2).  Turning the handle by more than
+        # atan((strike_h + bolt_h) / r0) lifts the bolt over the plate.
+        r0, r1 = L["bolt_r"]; bh, sh, yb = L["bolt_h"], L["strike_h"], 0.035
+        sgn = 1.0 if DOOR_HINGE["axis"][2] < 0 else -1.0                # the panel swings towards +y (door frame) for axis -z: the plate sits on that side of the bolt
+        bolt = f'<geom name="latch_bolt" type="box" pos="{-(r0 + r1) / 2} {yb} 0" size="{(r1 - r0) / 2} 0.006 {bh}" contype="0" conaffinity="2"/>'
+        xs0, xs1 = r0 + 0.005, r1 + 0.004                                 # plate extent along the bolt, in the latch frame (-x)
+        xf, yf = 0.125 - (xs0 + xs1) / 2, yb + sgn * 0.0125
+        strike = f'<geom name="door_strike" type="box" pos="{yf} {0.22 - xf} -0.025" size="0.006 {(xs1 - xs0) / 2} {sh}" contype="2" conaffinity="0"/>'
+
     return f'''
 <body name="door_root" pos="{_f(pos)}" quat="{q}">
   <geom name="door_post_l" type="box" pos="0 0.175 0" size="0.03 0.021 0.3" {col}/>
   <geom name="door_post_r" type="box" pos="0 -0.335 0" size="0.03 0.021 0.3" {col}/>
+  {strike}
   <body name="door" pos="0 -0.08 0" quat="0.7071068 0 0 -0.7071068">
-    <inertial pos="0.0296816 -0.00152345 0" mass="2.43455" diaginertia="0.0521615 0.0913751 0.043714"/>
-    <joint name="door_hinge" type="hinge" pos="0.255 0 0" axis="0 0 1" range="0 0.4" damping="{hinge_damping}" frictionloss="{hinge_frictionloss}"/>
+    <inertial pos="0.0296816 -0.00152345 0" mass="{DOOR_PANEL["mass"]}" diaginertia="{_f(np.array([0.0521615, 0.0913751, 0.043714]) * DOOR_PANEL["mass"] / 2.43455)}"/>
+    <joint name="door_hinge" type="hinge" pos="0.255 0 0" axis="{_f(DOOR_HINGE["axis"])}" range="0 0.4" damping="{DOOR_HINGE["damping"]}" frictionloss="{DOOR_HINGE["frictionloss"]}"/>
     <geom name="door_panel" type="box" size="0.22 0.02 0.29" {col}/>
     <body name="latch" pos="-0.175 0 -0.025">
       <inertial pos="-0.017762 0.0138544 0" mass="0.1" diaginertia="{_f(L["inertia"])}"/>
-      <joint name="latch_joint" type="hinge" axis="0 1 0" range="-1.57 0" damping="{L["damping"]}" frictionloss="{L["frictionloss"]}" stiffness="{L["stiffness"]}" springref="0"/>
+      <joint name="latch_joint" type="hinge" axis="{_f(L["axis"])}" range="-1.57 0" damping="{L["damping"]}" frictionloss="{L["frictionloss"]}" stiffness="{L["stiffness"]}" springref="0"/>
       <geom name="latch_stem" type="box" pos="0 -0.0625 0" size="0.02 0.0625 0.02" {col}/>
       <geom name="latch_handle" type="box" pos="0.075 -0.10 0" size="0.075 0.015 0.02" {col}/>
       {bolt}
