@@ -240,6 +240,7 @@ def door_object(pos=(0.12, -0.2, TABLE_HEIGHT), yaw=-PI / 2, hinge_damping=0.1, 
 #: half-size door calibrated by the reset distance only).  Chosen by the transfer of the committed Door policies, mean return here / logged over 5 seeds:
 #: round1 1.4 / 140 (Panda JOINT_VELOCITY), 52 / 368 (Panda OSC_POSE), 0.5 / 96 and 47 / 267 (Sawyer); recalled door with the hinge / latch choices below 247 / 140,
 #: 216 / 368, 59 / 96 and 261 / 267 (profiles/r2_policy_transfer_all.txt, r2_door_fit_cpu.txt).
+DOOR_STYLE = "robosuite_recalled"
 #: the Door task's table: robosuite's Door env uses a narrow table beside the robot (full size 0.8 x 0.3 x 0.05 at offset (-0.2, -0.35, 0.8)), as recalled
 DOOR_TABLE_FULL, DOOR_TABLE_OFFSET = (0.8, 0.3, 0.05), (-0.2, -0.35)
 #: latch handle: spring and friction as recalled; inertia = the physical estimate for a 0.1 kg handle (the recalled XML value 0.048 / 0.041 / 0.011 transfers no
