@@ -68,11 +68,12 @@ RETHINK_FINGERS = {
     "round1": dict(bar=((0, 0.009, 0.035), (0.008, 0.006, 0.035)), pad=((0, 0.002, 0.062), (0.008, 0.0015, 0.008)), bar_friction=None),
 }
 RETHINK_FINGER_STYLE = "round1"
+RETHINK = dict(kp=1000.0, force=20.0, pad_friction="2 0.05 0.0001", pad_solref="0.01 0.5", finger_damping=100.0, finger_armature=1.0, finger_frictionloss=1.0)
 
 
 def rethink_gripper(pf: str) -> str:
     """Rethink two-finger gripper for Sawyer: slide fingers along ±y."""
-    pad = f'{ROBOT_COL} condim="4" friction="2 0.05 0.0001" solref="0.01 0.5"'
+    pad = f'{ROBOT_COL} condim="4" friction="{RETHINK["pad_friction"]}" solref="{RETHINK["pad_solref"]}"'
     G = RETHINK_FINGERS[RETHINK_FINGER_STYLE]
     bar = ROBOT_COL + (f' friction="{G["bar_friction"]}"' if G["bar_friction"] else "")
     (bp, bs), (pp, ps) = G["bar"], G["pad"]
@@ -84,13 +85,13 @@ def rethink_gripper(pf: str) -> str:
   <site name="{pf}grip_site" pos="0 0 0.109"/>
   <body name="{pf}leftfinger" pos="0 0.01 0.0444">
     <inertial pos="0 0 0.03" mass="0.02" diaginertia="0.00001 0.00001 0.00001"/>
-    <joint name="{pf}finger_joint1" type="slide" axis="0 1 0" range="-0.0115 0.020833" damping="100" armature="1.0" frictionloss="1.0"/>
+    <joint name="{pf}finger_joint1" type="slide" axis="0 1 0" range="-0.0115 0.020833" damping="{RETHINK["finger_damping"]}" armature="{RETHINK["finger_armature"]}" frictionloss="{RETHINK["finger_frictionloss"]}"/>
     <geom name="{pf}finger1_col" type="box" pos="{_f(bp)}" size="{_f(bs)}" {bar}/>
     <geom name="{pf}finger1_pad" type="box" pos="{_f(pp)}" size="{_f(ps)}" {pad}/>
   </body>
   <body name="{pf}rightfinger" pos="0 -0.01 0.0444">
     <inertial pos="0 0 0.03" mass="0.02" diaginertia="0.00001 0.00001 0.00001"/>
-    <joint name="{pf}finger_joint2" type="slide" axis="0 1 0" range="-0.020833 0.0115" damping="100" armature="1.0" frictionloss="1.0"/>
+    <joint name="{pf}finger_joint2" type="slide" axis="0 1 0" range="-0.020833 0.0115" damping="{RETHINK["finger_damping"]}" armature="{RETHINK["finger_armature"]}" frictionloss="{RETHINK["finger_frictionloss"]}"/>
     <geom name="{pf}finger2_col" type="box" pos="{_f(m(bp))}" size="{_f(bs)}" {bar}/>
     <geom name="{pf}finger2_pad" type="box" pos="{_f(m(pp))}" size="{_f(ps)}" {pad}/>
   </body>
@@ -98,8 +99,9 @@ def rethink_gripper(pf: str) -> str:
 
 
 def rethink_gripper_actuators(pf: str) -> str:
-    return (f'<position name="{pf}gripper_finger_joint1" joint="{pf}finger_joint1" kp="1000" ctrlrange="-0.0115 0.020833" forcerange="-20 20"/>'
-            f'<position name="{pf}gripper_finger_joint2" joint="{pf}finger_joint2" kp="1000" ctrlrange="-0.020833 0.0115" forcerange="-20 20"/>')
+    kp, fr = RETHINK["kp"], RETHINK["force"]
+    return (f'<position name="{pf}gripper_finger_joint1" joint="{pf}finger_joint1" kp="{kp}" ctrlrange="-0.0115 0.020833" forcerange="{-fr} {fr}"/>'
+            f'<position name="{pf}gripper_finger_joint2" joint="{pf}finger_joint2" kp="{kp}" ctrlrange="-0.020833 0.0115" forcerange="{-fr} {fr}"/>')
 
 
 # ----------------------------------------------------------------------------- robots

@@ -48,7 +48,15 @@ def episode(job):
         if stats and cfg["env_name"] == "Door":
             extra_stats["min_handle_dist"] = min(extra_stats.get("min_handle_dist", 9), float(np.linalg.norm(o[-5:-2])))
             extra_stats["max_handle_q"] = max(extra_stats.get("max_handle_q", 0), abs(float(o[-1]))); extra_stats["max_hinge"] = max(extra_stats.get("max_hinge", 0), float(o[-2]))
+        if stats and cfg["env_name"] == "TwoArmLift":
+            extra_stats["max_pot_dz"] = max(extra_stats.get("max_pot_dz", -9), float(o[-23] - o0[-23]))
+            extra_stats["min_g0h0"] = min(extra_stats.get("min_g0h0", 9), float(np.linalg.norm(o[-6:-3]))); extra_stats["min_g1h1"] = min(extra_stats.get("min_g1h1", 9), float(np.linalg.norm(o[-3:])))
+            extra_stats["max_r"] = max(extra_stats.get("max_r", 0), r)
+            extra_stats["final_pot_dz"] = float(o[-23] - o0[-23])
+        if stats and cfg["env_name"] == "Stack":
+            extra_stats["min_gA"] = min(extra_stats.get("min_gA", 9), float(np.linalg.norm(o[-9:-6]))); extra_stats["max_A_dz"] = max(extra_stats.get("max_A_dz", -9), float(o[-21] - o0[-21])); extra_stats["max_r"] = max(extra_stats.get("max_r", 0), r)
         if stats and cfg["env_name"] == "Lift":
+            extra_stats["max_r"] = max(extra_stats.get("max_r", 0), r)
             extra_stats["min_cube_dist"] = min(extra_stats.get("min_cube_dist", 9), float(np.linalg.norm(o[-3:])))
             extra_stats["max_cube_dz"] = max(extra_stats.get("max_cube_dz", -9), float(o[-8] - o0[-8]))
     return os.path.basename(f)[:-4], ret, extra_stats
