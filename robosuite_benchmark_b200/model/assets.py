@@ -26,6 +26,10 @@ WORLD_COL = 'contype="1" conaffinity="1"'
 NO_COL = 'contype="0" conaffinity="0"'
 
 
+def _rotz(a, v):
+    return (np.cos(a) * v[0] - np.sin(a) * v[1], np.sin(a) * v[0] + np.cos(a) * v[1], v[2])
+
+
 def _f(v):
     return " ".join(f"{float(x):.10g}" for x in np.atleast_1d(v))
 
@@ -68,7 +72,7 @@ RETHINK_FINGERS = {
     "round1": dict(bar=((0, 0.009, 0.035), (0.008, 0.006, 0.035)), pad=((0, 0.002, 0.062), (0.008, 0.0015, 0.008)), bar_friction=None),
 }
 RETHINK_FINGER_STYLE = "round1"
-RETHINK = dict(kp=1000.0, force=20.0, pad_friction="2 0.05 0.0001", pad_solref="0.01 0.5", finger_damping=100.0, finger_armature=1.0, finger_frictionloss=1.0)
+RETHINK = dict(hand_yaw=0.0, kp=1000.0, force=20.0, pad_friction="2 0.05 0.0001", pad_solref="0.01 0.5", finger_damping=100.0, finger_armature=1.0, finger_frictionloss=1.0)
 
 
 def rethink_gripper(pf: str) -> str:
@@ -78,18 +82,22 @@ def rethink_gripper(pf: str) -> str:
     bar = ROBOT_COL + (f' friction="{G["bar_friction"]}"' if G["bar_friction"] else "")
     (bp, bs), (pp, ps) = G["bar"], G["pad"]
     m = lambda v: (v[0], -v[1], v[2])
+    # hand_yaw (degrees): extra rotation of the `right_hand` BODY FRAME about its z axis with the gripper counter-rotated inside it, i.e. the same physical hand
+    # with a differently oriented eef frame -- it changes only the eef_quat observation (the OSC law rotates in the world frame).
+    yaw = np.deg2rad(90.0 + RETHINK["hand_yaw"]); cy = np.deg2rad(-RETHINK["hand_yaw"])
+    qh, qc = f"{np.cos(yaw / 2):.10g} 0 0 {np.sin(yaw / 2):.10g}", f"{np.cos(cy / 2):.10g} 0 0 {np.sin(cy / 2):.10g}"
     return f'''
-<body name="{pf}right_hand" pos="0 0 0.0245" quat="0.7071068 0 0 0.7071068">
+<body name="{pf}right_hand" pos="0 0 0.0245" quat="{qh}">
   <inertial pos="0 0 0.03" mass="0.3" diaginertia="0.001 0.001 0.001"/>
-  <geom name="{pf}hand_col" type="box" pos="0 0 0.03" size="0.03 0.06 0.03" {ROBOT_COL}/>
+  <geom name="{pf}hand_col" type="box" pos="0 0 0.03" quat="{qc}" size="0.03 0.06 0.03" {ROBOT_COL}/>
   <site name="{pf}grip_site" pos="0 0 0.109"/>
-  <body name="{pf}leftfinger" pos="0 0.01 0.0444">
+  <body name="{pf}leftfinger" pos="{_f(_rotz(cy, (0, 0.01, 0.0444)))}" quat="{qc}">
     <inertial pos="0 0 0.03" mass="0.02" diaginertia="0.00001 0.00001 0.00001"/>
     <joint name="{pf}finger_joint1" type="slide" axis="0 1 0" range="-0.0115 0.020833" damping="{RETHINK["finger_damping"]}" armature="{RETHINK["finger_armature"]}" frictionloss="{RETHINK["finger_frictionloss"]}"/>
     <geom name="{pf}finger1_col" type="box" pos="{_f(bp)}" size="{_f(bs)}" {bar}/>
     <geom name="{pf}finger1_pad" type="box" pos="{_f(pp)}" size="{_f(ps)}" {pad}/>
   </body>
-  <body name="{pf}rightfinger" pos="0 -0.01 0.0444">
+  <body name="{pf}rightfinger" pos="{_f(_rotz(cy, (0, -0.01, 0.0444)))}" quat="{qc}">
     <inertial pos="0 0 0.03" mass="0.02" diaginertia="0.00001 0.00001 0.00001"/>
     <joint name="{pf}finger_joint2" type="slide" axis="0 1 0" range="-0.020833 0.0115" damping="{RETHINK["finger_damping"]}" armature="{RETHINK["finger_armature"]}" frictionloss="{RETHINK["finger_frictionloss"]}"/>
     <geom name="{pf}finger2_col" type="box" pos="{_f(m(bp))}" size="{_f(bs)}" {bar}/>
