@@ -72,7 +72,12 @@ RETHINK_FINGERS = {
     "round1": dict(bar=((0, 0.009, 0.035), (0.008, 0.006, 0.035)), pad=((0, 0.002, 0.062), (0.008, 0.0015, 0.008)), bar_friction=None),
 }
 RETHINK_FINGER_STYLE = "round1"
-RETHINK = dict(hand_yaw=0.0, kp=1000.0, force=20.0, pad_friction="2 0.05 0.0001", pad_solref="0.01 0.5", finger_damping=100.0, finger_armature=1.0, finger_frictionloss=1.0)
+#: finger_inertia: rotational inertia of each finger body, 0.01 kg m^2 as recalled from rethink_gripper.xml (an odd value for a 20 g part, but it is what gives the
+#: Sawyer's wrist joints enough inertia for the JOINT_VELOCITY law: with the 1e-5 of round 1 the last joint carried ~1.5e-3 kg m^2, below the dt kv / 2 = 4e-3 that
+#: explicit Euler needs for a velocity gain kv = 4 at dt = 2 ms, and the wrist chattered).  Committed Sawyer policies, per run here vs their last logged returns
+#: (profiles/r2_sawyer_fit_cpu.txt): Lift-Sawyer-JV 5 / 12 / 21 / 3 / 16 -> 88 / 58 / 23 / 22 / 50 against 84 / 53 / 20 / 12 / 49 logged; Stack-Sawyer (JV + OSC) log-return
+#: loss 0.148 -> 0.018; Lift-Sawyer-OSC mean 146 -> 185 of 348; Door-Sawyer loss 2.36 -> 1.02.
+RETHINK = dict(hand_yaw=0.0, finger_inertia=0.01, kp=1000.0, force=20.0, pad_friction="2 0.05 0.0001", pad_solref="0.01 0.5", finger_damping=100.0, finger_armature=1.0, finger_frictionloss=1.0)
 
 
 def rethink_gripper(pf: str) -> str:
@@ -92,13 +97,13 @@ def rethink_gripper(pf: str) -> str:
   <geom name="{pf}hand_col" type="box" pos="0 0 0.03" quat="{qc}" size="0.03 0.06 0.03" {ROBOT_COL}/>
   <site name="{pf}grip_site" pos="0 0 0.109"/>
   <body name="{pf}leftfinger" pos="{_f(_rotz(cy, (0, 0.01, 0.0444)))}" quat="{qc}">
-    <inertial pos="0 0 0.03" mass="0.02" diaginertia="0.00001 0.00001 0.00001"/>
+    <inertial pos="0 0 0.03" mass="0.02" diaginertia="{_f([RETHINK["finger_inertia"]] * 3)}"/>
     <joint name="{pf}finger_joint1" type="slide" axis="0 1 0" range="-0.0115 0.020833" damping="{RETHINK["finger_damping"]}" armature="{RETHINK["finger_armature"]}" frictionloss="{RETHINK["finger_frictionloss"]}"/>
     <geom name="{pf}finger1_col" type="box" pos="{_f(bp)}" size="{_f(bs)}" {bar}/>
     <geom name="{pf}finger1_pad" type="box" pos="{_f(pp)}" size="{_f(ps)}" {pad}/>
   </body>
   <body name="{pf}rightfinger" pos="{_f(_rotz(cy, (0, -0.01, 0.0444)))}" quat="{qc}">
-    <inertial pos="0 0 0.03" mass="0.02" diaginertia="0.00001 0.00001 0.00001"/>
+    <inertial pos="0 0 0.03" mass="0.02" diaginertia="{_f([RETHINK["finger_inertia"]] * 3)}"/>
     <joint name="{pf}finger_joint2" type="slide" axis="0 1 0" range="-0.020833 0.0115" damping="{RETHINK["finger_damping"]}" armature="{RETHINK["finger_armature"]}" frictionloss="{RETHINK["finger_frictionloss"]}"/>
     <geom name="{pf}finger2_col" type="box" pos="{_f(m(bp))}" size="{_f(bs)}" {bar}/>
     <geom name="{pf}finger2_pad" type="box" pos="{_f(m(pp))}" size="{_f(ps)}" {pad}/>
@@ -157,6 +162,9 @@ PANDA_GRIP_INIT = [0.020833, -0.020833]
 PANDA_GRIP_SIGN = [-1.0, 1.0]
 
 
+SAWYER = dict(damping=0.1, inertia_scale=1.0, armature=0.0, frictionloss=0.0)          # joint-space dynamics switches (what-if studies; defaults = round 1)
+
+
 def sawyer(pf: str, base_pos, base_quat=(1, 0, 0, 0)) -> str:
     """Rethink Sawyer, 7 hinge joints about local z (public URDF link frames)."""
     lim = [(-3.0503, 3.0503), (-3.8095, 2.2736), (-3.0426, 3.0426), (-3.0439, 3.0439),
@@ -172,8 +180,9 @@ def sawyer(pf: str, base_pos, base_quat=(1, 0, 0, 0)) -> str:
     s += f'<inertial pos="0 0 0.04" mass="2" diaginertia="0.02 0.02 0.02"/>'
     for i in range(7):
         s += (f'<body name="{pf}link{i + 1}" pos="{frames[i][0]}" quat="{frames[i][1]}">'
-              f'<inertial pos="{inert[i][0]}" mass="{inert[i][1]}" diaginertia="{inert[i][2]} {inert[i][2]} {inert[i][2]}"/>'
-              f'<joint name="{pf}joint{i + 1}" type="hinge" axis="0 0 1" range="{lim[i][0]} {lim[i][1]}" damping="0.1"/>')
+              f'<inertial pos="{inert[i][0]}" mass="{inert[i][1]}" diaginertia="{_f([inert[i][2] * SAWYER["inertia_scale"]] * 3)}"/>'
+              f'<joint name="{pf}joint{i + 1}" type="hinge" axis="0 0 1" range="{lim[i][0]} {lim[i][1]}" damping="{SAWYER["damping"]}" '
+              f'armature="{SAWYER["armature"]}" frictionloss="{SAWYER["frictionloss"]}"/>')
     s += rethink_gripper(pf)
     s += "</body>" * 8
     return s
