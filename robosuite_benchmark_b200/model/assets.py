@@ -35,22 +35,25 @@ def _f(v):
 
 
 # ----------------------------------------------------------------------------- grippers
+PANDA_GRIPPER = dict(finger_inertia=(0.0001, 0.0001, 0.0001), hand_inertia=(0.002, 0.002, 0.002), hand_mass=0.5)
+
+
 def panda_gripper(pf: str) -> str:
     """Franka hand: two slide fingers (±y), box pads with high friction."""
     pad = f'{ROBOT_COL} condim="4" friction="2 0.05 0.0001" solref="0.01 0.5"'
     return f'''
 <body name="{pf}right_hand" pos="0 0 0.107" quat="0.9238795 0 0 -0.3826834">
-  <inertial pos="0 0 0.03" mass="0.5" diaginertia="0.002 0.002 0.002"/>
+  <inertial pos="0 0 0.03" mass="{PANDA_GRIPPER["hand_mass"]}" diaginertia="{_f(PANDA_GRIPPER["hand_inertia"])}"/>
   <geom name="{pf}hand_col" type="box" pos="0 0 0.0333" size="0.0315 0.102 0.0333" {ROBOT_COL}/>
   <site name="{pf}grip_site" pos="0 0 0.1025"/>
   <body name="{pf}leftfinger" pos="0 0 0.0584">
-    <inertial pos="0 0.01 0.02" mass="0.1" diaginertia="0.0001 0.0001 0.0001"/>
+    <inertial pos="0 0.01 0.02" mass="0.1" diaginertia="{_f(PANDA_GRIPPER["finger_inertia"])}"/>
     <joint name="{pf}finger_joint1" type="slide" axis="0 1 0" range="0 0.04" damping="100" armature="1.0" frictionloss="1.0"/>
     <geom name="{pf}finger1_col" type="box" pos="0 0.0115 0.027" size="0.0105 0.0075 0.027" {ROBOT_COL}/>
     <geom name="{pf}finger1_pad" type="box" pos="0 0.0025 0.044" size="0.008 0.0015 0.008" {pad}/>
   </body>
   <body name="{pf}rightfinger" pos="0 0 0.0584">
-    <inertial pos="0 -0.01 0.02" mass="0.1" diaginertia="0.0001 0.0001 0.0001"/>
+    <inertial pos="0 -0.01 0.02" mass="0.1" diaginertia="{_f(PANDA_GRIPPER["finger_inertia"])}"/>
     <joint name="{pf}finger_joint2" type="slide" axis="0 1 0" range="-0.04 0" damping="100" armature="1.0" frictionloss="1.0"/>
     <geom name="{pf}finger2_col" type="box" pos="0 -0.0115 0.027" size="0.0105 0.0075 0.027" {ROBOT_COL}/>
     <geom name="{pf}finger2_pad" type="box" pos="0 -0.0025 0.044" size="0.008 0.0015 0.008" {pad}/>
