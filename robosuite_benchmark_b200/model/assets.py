@@ -334,6 +334,9 @@ POT = dict(thickness=0.025, handle_z=0.06, bar_half=0.055, side_bars=True)
 #: |y| of the two robot bases in TwoArmLift's single-arm-opposed layout: robosuite rotates base_xpos_offset["table"](0.8) = (-0.56, 0, 0) by +-90 degrees.
 #: Round 1 used 0.69 (fitted to the logged epoch-0 return); the committed policies say 0.56: 80 vs 52 with the round-1 pot, 86 vs 61 with the recalled one.
 TWO_ARM_BASE_Y = 0.56
+#: TwoArmLift pot yaw at reset: True = pi +- pi/3 with robot0's handle on the pot frame's +y side (robosuite's sampler as recalled: rotation=(pi - pi/3, pi + pi/3));
+#: False = +- pi/3 with robot0's handle on -y (round 1).  Same scene either way (the pot is symmetric); only the pot_quat observation differs by half a turn.
+TWO_ARM_POT_YAW_PI = False
 
 
 def pot_with_handles(name="pot", pos=(0, 0, TABLE_HEIGHT + 0.07), density=1000) -> str:

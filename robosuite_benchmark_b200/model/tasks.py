@@ -261,11 +261,13 @@ def _two_arm_lift(robots, env_configuration):
         o = _empty_objs()
         j = m.id("joint", "pot_joint")
         o["obj_body"][0] = m.id("body", "pot")
-        o["obj_geom"][0], o["obj_geom"][1] = m.id("geom", "pot_handle0"), m.id("geom", "pot_handle1")
-        o["obj_site"][0], o["obj_site"][1] = m.id("site", "pot_handle0"), m.id("site", "pot_handle1")
+        h0, h1 = ("pot_handle1", "pot_handle0") if A.TWO_ARM_POT_YAW_PI else ("pot_handle0", "pot_handle1")
+        o["obj_geom"][0], o["obj_geom"][1] = m.id("geom", h0), m.id("geom", h1)
+        o["obj_site"][0], o["obj_site"][1] = m.id("site", h0), m.id("site", h1)
         o["obj_qposadr"][0], o["obj_dofadr"][0] = int(m.jnt_qposadr[j]), int(m.jnt_dofadr[j])
         o["obj_half"][0] = [0.07, 0.07, 0.07]
-        o["place_x"][0], o["place_y"][0], o["place_yaw"][0] = [-0.03, 0.03], [-0.03, 0.03], [-np.pi / 3, np.pi / 3]
+        yaw0 = np.pi if A.TWO_ARM_POT_YAW_PI else 0.0
+        o["place_x"][0], o["place_y"][0], o["place_yaw"][0] = [-0.03, 0.03], [-0.03, 0.03], [yaw0 - np.pi / 3, yaw0 + np.pi / 3]
         o["place_z"][0] = A.TABLE_HEIGHT + 0.07 + 0.01
         o["place_ref"] = np.array([0.0, 0.0, A.TABLE_HEIGHT])
         return o
