@@ -20,7 +20,8 @@ enum { RSB_JNT_FREE = 0, RSB_JNT_SLIDE = 2, RSB_JNT_HINGE = 3 };           /* mj
 enum { RSB_GEOM_PLANE = 0, RSB_GEOM_SPHERE = 2, RSB_GEOM_CAPSULE = 3,
        RSB_GEOM_CYLINDER = 5, RSB_GEOM_BOX = 6 };                          /* mjtGeom values  */
 enum { RSB_CONE_PYRAMIDAL = 0, RSB_CONE_ELLIPTIC = 1 };
-enum { RSB_TASK_LIFT = 0, RSB_TASK_DOOR = 1, RSB_TASK_STACK = 2, RSB_TASK_TWOARMLIFT = 3 };
+enum { RSB_TASK_LIFT = 0, RSB_TASK_DOOR = 1, RSB_TASK_STACK = 2, RSB_TASK_TWOARMLIFT = 3,
+       RSB_TASK_PICKPLACE = 4 };   /* PickPlace in single-object mode (PickPlaceMilk / PickPlaceCan / ...): one object, bin 1 -> its quadrant of bin 2 */
 enum { RSB_CTRL_OSC_POSE = 0, RSB_CTRL_OSC_POSITION = 1, RSB_CTRL_JOINT_VELOCITY = 2,
        RSB_CTRL_JOINT_TORQUE = 3 };
 
@@ -35,6 +36,7 @@ enum { RSB_ORI_DELTA_EULER_T = 0, RSB_ORI_DELTA_AXIS_ANGLE = 1 };
 #define RSB_ARM_DOF 7
 #define RSB_MAX_FINGER_GEOMS 4
 #define RSB_MAX_OBJ 4
+#define RSB_TASK_NPAR 8
 
 typedef struct rsb_model {
   /* sizes */
@@ -114,7 +116,8 @@ typedef struct rsb_task {
      DOOR:  obj_body[0]=door, [1]=latch(handle), obj_site[0]=handle site,
             obj_qposadr[0]=hinge, [1]=latch hinge, obj_body[2]=door frame root (placed)
      STACK: cubeA=0, cubeB=1
-     TWOARMLIFT: obj_body[0]=pot, obj_site[0..1]=handle sites, obj_geom[0..1]=handle geoms */
+     TWOARMLIFT: obj_body[0]=pot, obj_site[0..1]=handle sites, obj_geom[0..1]=handle geoms
+     PICKPLACE: obj_body[0]=the object, obj_geom[0]=its collision geom, obj_qposadr[0]=free joint; task_par below */
   int obj_body[RSB_MAX_OBJ], obj_geom[RSB_MAX_OBJ], obj_site[RSB_MAX_OBJ];
   int obj_qposadr[RSB_MAX_OBJ], obj_dofadr[RSB_MAX_OBJ];
   double obj_half[RSB_MAX_OBJ][3];         /* box half sizes for placement z / overlap tests */
@@ -125,6 +128,10 @@ typedef struct rsb_task {
   /* place_body[o] >= 0: object o is a FIXED body (no free joint; robosuite writes model.body_pos/body_quat at reset, e.g. the
      Door): the sampled pose (place_ref + xy, place_z, yaw about z) overrides that body's pos/quat for this env.  At most one. */
   int place_body[RSB_MAX_OBJ];
+  /* task constants, meaning by task_id (0 where unused)
+     PICKPLACE: [0..1] = xy of the object's target placement in bin 2 (centre of its quadrant), [2] = bin-2 z (bin2_pos[2]),
+                [3..4] = bin_size xy (the quadrant check is |obj - target| < bin_size / 4 per axis), [5] = lift target height above bin-2 z (0.25) */
+  double task_par[RSB_TASK_NPAR];
 } rsb_task;
 
 #ifdef __cplusplus

@@ -1062,6 +1062,26 @@ static real task_reward(const orc_env *e) {
     }
     return r * t->reward_scale / 3.0;
   }
+  if (t->task_id == RSB_TASK_PICKPLACE) {
+    /* robosuite v1.0 PickPlace.reward / staged_rewards / not_in_bin in single-object mode (the other three objects sit cleared away at x = 10 and contribute nothing):
+       success (object inside its bin-2 quadrant, 0 < z - bin2_z < 0.1, and the gripper away: 1 - tanh(10 d) < 0.6) -> 1; otherwise, when shaping, the maximum of
+       reach 0.1 (1 - tanh(10 d)), grasp 0.35 (both fingers touch), lift 0.35 + 0.15 (1 - tanh(15 max(z_target - z, 0))) while grasped, and hover
+       (0.5 when above the quadrant, else the lift reward) + 0.2 (1 - tanh(10 |xy - target|)).  The constants are pinned by the committed PickPlace runs' logs:
+       reward plateaus at 0.35 and 0.5, maxima 0.63 and exactly 1.0.  Not divided by 4: single-object mode. */
+    const real *obj = e->xpos[t->obj_body[0]], *eef = e->site_xpos[t->robot[0].eef_site], *tp = t->task_par;
+    real d[3]; v3sub(d, eef, obj); real reach = 1 - tanh(10.0 * v3norm(d));
+    int above = fabs(obj[0] - tp[0]) < tp[3] / 4 && fabs(obj[1] - tp[1]) < tp[4] / 4;
+    int in_bin = above && obj[2] > tp[2] && obj[2] < tp[2] + 0.1;
+    if (in_bin && reach < 0.6) r = 1.0;
+    else if (t->reward_shaping) {
+      real r_reach = 0.1 * reach, r_grasp = check_grasp(e, 0, t->obj_geom[0]) ? 0.35 : 0.0, r_lift = 0;
+      if (r_grasp > 0) { real zd = tp[2] + tp[5] - obj[2]; if (zd < 0) zd = 0; r_lift = 0.35 + (1 - tanh(15.0 * zd)) * 0.15; }
+      real hd = sqrt((obj[0] - tp[0]) * (obj[0] - tp[0]) + (obj[1] - tp[1]) * (obj[1] - tp[1]));
+      real r_hover = (above ? 0.5 : r_lift) + (1 - tanh(10.0 * hd)) * 0.2;
+      r = r_reach; if (r_grasp > r) r = r_grasp; if (r_lift > r) r = r_lift; if (r_hover > r) r = r_hover;
+    }
+    return r * t->reward_scale;
+  }
   return 0;
 }
 
@@ -1112,6 +1132,17 @@ static void observation(const orc_env *e, real *obs) {
     for (int k = 0; k < 3; k++) obs[n++] = h1[k];
     for (int k = 0; k < 3; k++) obs[n++] = h0[k] - e0[k];
     for (int k = 0; k < 3; k++) obs[n++] = h1[k] - e1[k];
+  } else if (t->task_id == RSB_TASK_PICKPLACE) {
+    /* object-state of robosuite v1.0 PickPlace._get_observation, single-object mode: {obj}_pos, {obj}_quat (xyzw), then the object's pose in the gripper frame
+       (pose_inv(eef pose) * object pose: {obj}_to_eef_pos = R_eef^T (p_obj - p_eef), {obj}_to_eef_quat = mat2quat(R_eef^T R_obj), xyzw with w >= 0) */
+    const real *obj = e->xpos[t->obj_body[0]], *qe = e->xquat[t->robot[0].eef_body], *qo = e->xquat[t->obj_body[0]];
+    for (int k = 0; k < 3; k++) obs[n++] = obj[k];
+    put_quat_xyzw(obs + n, qo); n += 4;
+    real d[3], Re[9], rel[3]; v3sub(d, obj, eef); q2mat(Re, qe); m3Tmulv(rel, Re, d);
+    for (int k = 0; k < 3; k++) obs[n++] = rel[k];
+    real qc[4] = {qe[0], -qe[1], -qe[2], -qe[3]}, qr[4]; qmul(qr, qc, qo); qnormalize(qr);
+    if (qr[0] < 0) for (int k = 0; k < 4; k++) qr[k] = -qr[k];
+    put_quat_xyzw(obs + n, qr); n += 4;
   }
 }
 

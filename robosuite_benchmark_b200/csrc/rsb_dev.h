@@ -1549,7 +1549,34 @@ RSB_DN real task_reward(int so) { const real *s = RSB_SMEM + so;
     }
     return r * MDL.reward_scale / 3.0f;
   }
+  if (MDL.task_id == RSB_TASK_PICKPLACE) {          /* single-object PickPlace: success 1, else max(reach, grasp, lift, hover) -- see the oracle's task_reward */
+    const real *obj = xpos + 3 * MDL.obj_body[0], *tp = MDL.task_par;
+    real d[3] = {eef[0] - obj[0], eef[1] - obj[1], eef[2] - obj[2]}; const real reach = 1 - tanhf(10.0f * sqrtf(dot3(d, d)));
+    const bool above = fabsf(obj[0] - tp[0]) < 0.25f * tp[3] && fabsf(obj[1] - tp[1]) < 0.25f * tp[4];
+    const bool in_bin = above && obj[2] > tp[2] && obj[2] < tp[2] + 0.1f;
+    if (in_bin && reach < 0.6f) r = 1.0f;
+    else if (MDL.reward_shaping) {
+      const real r_grasp = check_grasp(so, 0, MDL.obj_geom[0]) ? 0.35f : 0.0f; real r_lift = 0;
+      if (r_grasp > 0) r_lift = 0.35f + (1 - tanhf(15.0f * fmaxf(tp[2] + tp[5] - obj[2], 0.0f))) * 0.15f;
+      const real hx = obj[0] - tp[0], hy = obj[1] - tp[1];
+      const real r_hover = (above ? 0.5f : r_lift) + (1 - tanhf(10.0f * sqrtf(hx * hx + hy * hy))) * 0.2f;
+      r = fmaxf(fmaxf(0.1f * reach, r_grasp), fmaxf(r_lift, r_hover));
+    }
+    return r * MDL.reward_scale;
+  }
   return 0;
+}
+
+/* PickPlace object-state (element i of 14): obj pos, quat (xyzw), then the object's pose in the gripper frame: R_eef^T (p_obj - p_eef), conj(q_eef) q_obj with w >= 0.
+   Not inlined: its quaternion temporaries stay out of the step kernel's own stack frame. */
+RSB_DN real obs_pickplace(int so, int i) { const real *s = RSB_SMEM + so;
+  const real *xpos = s + MDL.o_xpos, *xquat = s + MDL.o_xquat, *eef = s + MDL.o_sxpos + 3 * MDL.robot[0].eef_site;
+  const real *obj = xpos + 3 * MDL.obj_body[0], *qo = xquat + 4 * MDL.obj_body[0], *qe = xquat + 4 * MDL.robot[0].eef_body;
+  if (i < 3) return obj[i];
+  if (i < 7) { int k = i - 3; return qo[k == 3 ? 0 : k + 1]; }
+  if (i < 10) { real Re[9], d[3] = {obj[0] - eef[0], obj[1] - eef[1], obj[2] - eef[2]}, rel[3]; quat2mat(Re, qe); matTvec3(rel, Re, d); return rel[i - 7]; }
+  real qc[4] = {qe[0], -qe[1], -qe[2], -qe[3]}, qr[4]; quatmul(qr, qc, qo); quatnorm(qr);
+  const real sg = qr[0] < 0 ? -1.0f : 1.0f; int k = i - 10; return sg * qr[k == 3 ? 0 : k + 1];
 }
 
 /* A.1.4 observation vector, robosuite v1.0 order: per robot [sin q, cos q, qd, eef_pos, eef_quat(xyzw), grip q, grip qd], then object-state.
@@ -1605,6 +1632,7 @@ RSB_D real obs_element(int so, int i) { const real *s = RSB_SMEM + so;
     if (i < 22) return h0[i - 19] - e0[i - 19];
     return h1[i - 22] - e1[i - 22];
   }
+  if (MDL.task_id == RSB_TASK_PICKPLACE) return obs_pickplace(so, i);
   return 0;
 }
 

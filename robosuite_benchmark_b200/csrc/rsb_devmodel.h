@@ -71,7 +71,7 @@ typedef struct DevModel {
   float reward_scale, init_noise, table_height;
   int obj_body[RSB_MAX_OBJ], obj_geom[RSB_MAX_OBJ], obj_site[RSB_MAX_OBJ], obj_qadr[RSB_MAX_OBJ], obj_dadr[RSB_MAX_OBJ];
   float obj_half[RSB_MAX_OBJ][3], place_x[RSB_MAX_OBJ][2], place_y[RSB_MAX_OBJ][2], place_yaw[RSB_MAX_OBJ][2];
-  float place_z[RSB_MAX_OBJ], place_ref[3];
+  float place_z[RSB_MAX_OBJ], place_ref[3], task_par[RSB_TASK_NPAR];
   int place_body[RSB_MAX_OBJ], override_body;       /* fixed body whose pose is a per-env quantity (Door), -1 if none */
   DevRobot robot[RSB_MAX_ROBOTS];
   /* per-env persistent state record in HBM (words): qpos, qvel, warm, cs[nrobot*RSB_CS_WORDS], bpose[7], timestep, episode */
@@ -259,6 +259,7 @@ inline bool rsb_build_host_model(const rsb_model *m, const rsb_task *t, int ncon
     d.place_z[o] = (float)t->place_z[o]; d.place_body[o] = t->place_body[o]; if (t->place_body[o] >= 0) d.override_body = t->place_body[o];
   }
   for (int k = 0; k < 3; k++) d.place_ref[k] = (float)t->place_ref[k];
+  for (int k = 0; k < RSB_TASK_NPAR; k++) d.task_par[k] = (float)t->task_par[k];
   int aoff = 0;
   for (int r = 0; r < t->nrobot; r++) {
     const rsb_robot *s = &t->robot[r]; DevRobot *q = &d.robot[r];

@@ -360,5 +360,44 @@ def pot_with_handles(name="pot", pos=(0, 0, TABLE_HEIGHT + 0.07), density=1000) 
     return f'<body name="{name}" pos="{_f(pos)}"><freejoint name="{name}_joint"/>' + "".join(g) + "</body>"
 
 
+# ----------------------------------------------------------------------------- PickPlace: bins arena and the pick objects
+#: robosuite's BinsArena (arenas/bins_arena.xml) as recalled: two open bins side by side, each a 0.4 x 0.5 m floor slab of half thickness 0.02 centred at the
+#: bin position (top surface at z = 0.82 = table_full_size[2] of the PickPlace env) with four 0.1 m walls.  The bin-2 partition lines and the legs are visual.
+BIN1_POS, BIN2_POS = (0.1, -0.25, 0.8), (0.1, 0.28, 0.8)
+BIN_SIZE = (0.39, 0.49, 0.82)                  # PickPlace's table_full_size: the sampler's and the reward's bin extent
+BIN_FLOOR_HALF = (0.2, 0.25, 0.02)
+#: base_xpos_offset["bins"] of robosuite's Panda and Sawyer models
+BINS_ROBOT_BASE = (-0.5, -0.1)
+#: the pick objects are meshes upstream (collision = the mesh's convex hull); here each is ONE box of the hull's extents -- half sizes from the objects' bottom / top /
+#: horizontal-radius sites as recalled; density 100, friction (0.95, 0.3, 0.1), solref (0.001, 1), solimp (0.998, 0.998, 0.001) as in the object XMLs.
+#: `bin_id` is the object's index in robosuite's item list [Milk, Bread, Cereal, Can] (its target quadrant of bin 2).  The can is a cylinder upstream: a square
+#: prism of the same width stands and is grasped like it but does not roll (no cylinder narrow phase in the kernels).
+PICK_OBJECTS = {
+    "Milk": dict(half=(0.0225, 0.0225, 0.08), bin_id=0),
+    "Bread": dict(half=(0.02, 0.04, 0.0225), bin_id=1),
+    "Cereal": dict(half=(0.02, 0.05, 0.1), bin_id=2),
+    "Can": dict(half=(0.03, 0.03, 0.06), bin_id=3),
+}
+
+
+def bins_arena(friction=(1, 0.005, 0.0001)) -> str:
+    s = f'<geom name="floor" type="plane" pos="0 0 0" size="3 3 0.125" {WORLD_COL}/>'
+    hx, hy, hz = BIN_FLOOR_HALF
+    for name, pos in (("bin1", BIN1_POS), ("bin2", BIN2_POS)):
+        col = f'friction="{_f(friction)}" {WORLD_COL}'
+        s += (f'<body name="{name}" pos="{_f(pos)}">'
+              f'<geom name="{name}_floor" type="box" size="{hx} {hy} {hz}" {col}/>'
+              f'<geom name="{name}_wall_yp" type="box" pos="0 {hy} 0.05" size="{hx + 0.01} 0.01 0.05" {col}/>'
+              f'<geom name="{name}_wall_yn" type="box" pos="0 {-hy} 0.05" size="{hx + 0.01} 0.01 0.05" {col}/>'
+              f'<geom name="{name}_wall_xp" type="box" pos="{hx} 0 0.05" size="0.01 {hy} 0.05" {col}/>'
+              f'<geom name="{name}_wall_xn" type="box" pos="{-hx} 0 0.05" size="0.01 {hy} 0.05" {col}/>'
+              f'</body>')
+    return s
+
+
+def pick_object(kind: str, pos) -> str:
+    return box_object(kind, PICK_OBJECTS[kind]["half"], pos, density=100, friction=(0.95, 0.3, 0.1), solref=(0.001, 1.0), solimp=(0.998, 0.998, 0.001))
+
+
 def scene(world: str, actuators: str, extra: str = "") -> str:
     return f'<mujoco model="rsb">{BASE_OPTION}<worldbody>{world}</worldbody><actuator>{actuators}</actuator>{extra}</mujoco>'

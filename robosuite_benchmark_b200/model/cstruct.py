@@ -85,6 +85,7 @@ class RsbTask(C.Structure):
         ("obj_half", (C.c_double * 3) * 4),
         ("place_x", D2 * 4), ("place_y", D2 * 4), ("place_yaw", D2 * 4), ("place_z", C.c_double * 4),
         ("place_ref", C.c_double * 3), ("place_body", I4),
+        ("task_par", C.c_double * 8),
     ]
 
 
@@ -131,6 +132,7 @@ def task_to_c(task: dict) -> RsbTask:
     for k in ("obj_body", "obj_geom", "obj_site", "obj_qposadr", "obj_dofadr", "obj_half", "place_x", "place_y",
               "place_yaw", "place_z", "place_ref", "place_body"):
         _fill(getattr(t, k), task[k])
+    _fill(t.task_par, np.concatenate([np.asarray(task.get("task_par", []), float), np.zeros(8)])[:8])
     for ri, rd in enumerate(task["robot"]):
         r = t.robot[ri]
         for name, typ in RsbRobot._fields_:

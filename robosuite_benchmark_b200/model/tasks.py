@@ -14,10 +14,10 @@ import numpy as np
 from . import assets as A
 from .mjcf import Model, compile_mjcf
 
-TASK_IDS = {"Lift": 0, "Door": 1, "Stack": 2, "TwoArmLift": 3}
+TASK_IDS = {"Lift": 0, "Door": 1, "Stack": 2, "TwoArmLift": 3, "PickPlaceMilk": 4, "PickPlaceBread": 4, "PickPlaceCereal": 4, "PickPlaceCan": 4}
 CTRL_IDS = {"OSC_POSE": 0, "OSC_POSITION": 1, "JOINT_VELOCITY": 2, "JOINT_TORQUE": 3}
 
-OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89}
+OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89, "PickPlaceMilk": 46, "PickPlaceBread": 46, "PickPlaceCereal": 46, "PickPlaceCan": 46}
 #: default bounds of the per-env contact list / constraint-row list (shared-memory sizing; rsb_create ncon_max / nefc_max).
 #: Maxima seen over 300 random-action control steps x 2048 envs (tools/limits_stats.py): Stack 16 contacts / 54 rows, TwoArmLift 9 / 31,
 #: Door 4 / 18, Lift 9 / 29; TwoArmLift (24, 80) keeps 2.5x headroom and lets 14 envs share an SM (4096 envs = 2 waves instead of 3).
@@ -28,7 +28,9 @@ OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89}
 #: random-action episode where (16, 64) had one (17 contacts; tools/limits_sweep.py, profiles/r2_limits_sweep_lift.txt).  A TRAINED policy grasps: the
 #: committed Lift-Panda policy exceeds these limits in 1.4e-4 of its env-steps (pads + table + hand on the cube) --
 #: `suite.make(..., ncon_max=24, nefc_max=80)` removes that at the price of a second wave at 4096 envs per GPU.
-LIMITS = {"Lift": (18, 62), ("Lift", "Sawyer"): (24, 80), "Door": (16, 64), "Stack": (24, 96), "TwoArmLift": (24, 80)}
+LIMITS = {"Lift": (18, 62), ("Lift", "Sawyer"): (24, 80), "Door": (16, 64), "Stack": (24, 96), "TwoArmLift": (24, 80),
+          # PickPlace, committed policies on the CPU oracle (16 episodes each): Panda reaches 13 contacts / 49 rows while carrying the object, Sawyer 18 / 64
+          **{"PickPlace" + k: (18, 62) for k in ("Milk", "Bread", "Cereal", "Can")}, **{("PickPlace" + k, "Sawyer"): (24, 80) for k in ("Milk", "Bread", "Cereal", "Can")}}
 
 
 def limits_for(env_name, robots):
@@ -154,7 +156,7 @@ def empty_task():
 def _empty_objs():
     return dict(obj_body=[-1] * 4, obj_geom=[-1] * 4, obj_site=[-1] * 4, obj_qposadr=[-1] * 4, obj_dofadr=[-1] * 4,
                 obj_half=np.zeros((4, 3)), place_x=np.zeros((4, 2)), place_y=np.zeros((4, 2)),
-                place_yaw=np.zeros((4, 2)), place_z=np.zeros(4), place_ref=np.zeros(3), place_body=[-1] * 4)
+                place_yaw=np.zeros((4, 2)), place_z=np.zeros(4), place_ref=np.zeros(3), place_body=[-1] * 4, task_par=[0.0] * 8)
 
 
 def _single_arm_world(robot: str):
@@ -275,4 +277,42 @@ def _two_arm_lift(robots, env_configuration):
     return xml, objs
 
 
-_BUILDERS: Dict[str, callable] = {"Lift": _lift, "Stack": _stack, "Door": _door, "TwoArmLift": _two_arm_lift}
+def _pick_place(kind):
+    """PickPlace in single-object mode (robosuite's PickPlaceMilk / PickPlaceCan / ... = PickPlace(single_object_mode=2, object_type=kind)): the object starts at a
+    uniform pose in bin 1 and goes into its quadrant of bin 2.  The other three objects, which robosuite parks at x = 10, are not modelled."""
+
+    def build(robots, env_configuration):
+        assert len(robots) == 1, "PickPlace takes one robot"
+        R = A.ROBOTS[robots[0]]
+        body, act = R["body"]("robot0_", (A.BINS_ROBOT_BASE[0], A.BINS_ROBOT_BASE[1], A.ROBOT_BASE_Z)), R["act"]("robot0_")
+        P = A.PICK_OBJECTS[kind]
+        half, top = np.array(P["half"]), A.BIN1_POS[2] + A.BIN_FLOOR_HALF[2]
+        world = A.bins_arena() + body + A.pick_object(kind, [A.BIN1_POS[0], A.BIN1_POS[1], top + half[2]])
+        xml = A.scene(world, act)
+
+        def objs(m: Model):
+            o = _empty_objs()
+            j = m.id("joint", kind + "_joint")
+            o["obj_body"][0], o["obj_geom"][0] = m.id("body", kind), m.id("geom", kind + "_g0")
+            o["obj_qposadr"][0], o["obj_dofadr"][0] = int(m.jnt_qposadr[j]), int(m.jnt_dofadr[j])
+            o["obj_half"][0] = half
+            # robosuite's bin sampler: uniform over the bin minus the object's horizontal radius and a 5 cm border, any yaw, resting on the bin floor
+            rad = float(np.hypot(half[0], half[1]))
+            bx, by = A.BIN_SIZE[0] / 2 - rad - 0.05, A.BIN_SIZE[1] / 2 - rad - 0.05
+            o["place_x"][0], o["place_y"][0], o["place_yaw"][0] = [-bx, bx], [-by, by], [0.0, 2 * np.pi]
+            o["place_z"][0] = top + half[2] + 0.01            # dropped from 1 cm like the table tasks (an exact resting pose would leave the contact set to round-off)
+            o["place_ref"] = np.array([A.BIN1_POS[0], A.BIN1_POS[1], top])
+            # target placement: centre of quadrant bin_id of bin 2 (PickPlace._reset_internal: ids 0 / 2 on the low-x side, ids 0 / 1 on the low-y side)
+            b = P["bin_id"]
+            tx = A.BIN2_POS[0] - (A.BIN_SIZE[0] / 2 if b in (0, 2) else 0.0) + A.BIN_SIZE[0] / 4
+            ty = A.BIN2_POS[1] - (A.BIN_SIZE[1] / 2 if b < 2 else 0.0) + A.BIN_SIZE[1] / 4
+            o["task_par"] = [tx, ty, A.BIN2_POS[2], A.BIN_SIZE[0], A.BIN_SIZE[1], 0.25]
+            return o
+
+        return xml, objs
+
+    return build
+
+
+_BUILDERS: Dict[str, callable] = {"Lift": _lift, "Stack": _stack, "Door": _door, "TwoArmLift": _two_arm_lift,
+                                  **{"PickPlace" + k: _pick_place(k) for k in A.PICK_OBJECTS}}
