@@ -1011,6 +1011,16 @@ static int check_grasp(const orc_env *e, int ri, int obj_geom) {
   return tl && tr;
 }
 
+/* TwoArmPegInHole._compute_orientation: v = peg axis (the peg body's z), c = hole centre (plate origin + offset along the plate's x); t = (c - p) . v, the
+   signed distance of the centre along the axis from the peg's origin; d = |v x (p - c)|, the distance of the centre from the axis; cosn = |n . v| with n the plate's z */
+static void peg_hole_orientation(const orc_env *e, real *t_out, real *d_out, real *cos_out) {
+  const rsb_task *t = &e->t; const real *hp = e->xpos[t->obj_body[0]], *Rh = e->xmat[t->obj_body[0]], *pp = e->xpos[t->obj_body[1]], *Rp = e->xmat[t->obj_body[1]];
+  real v[3] = {Rp[2], Rp[5], Rp[8]}, n[3] = {Rh[2], Rh[5], Rh[8]}, c[3], pc[3], cp[3], x[3];
+  for (int k = 0; k < 3; k++) { c[k] = hp[k] + t->task_par[0] * Rh[3 * k]; cp[k] = c[k] - pp[k]; pc[k] = pp[k] - c[k]; }
+  v3cross(x, v, pc);
+  *t_out = v3dot(cp, v) / v3dot(v, v); *d_out = v3norm(x) / v3norm(v); *cos_out = fabs(v3dot(n, v) / v3norm(n) / v3norm(v));
+}
+
 static real task_reward(const orc_env *e) {
   const rsb_task *t = &e->t; real r = 0;
   if (t->task_id == RSB_TASK_LIFT) {
@@ -1082,6 +1092,18 @@ static real task_reward(const orc_env *e) {
     }
     return r * t->reward_scale;
   }
+  if (t->task_id == RSB_TASK_PEGINHOLE) {
+    /* robosuite v1.0 TwoArmPegInHole.reward: success (d < 0.06, -0.12 <= t <= 0.14, cos > 0.95) 1, plus, when shaping, 1 - tanh(|peg - plate origin|),
+       1 - tanh(d), 1 - tanh(|t|) and cos; sparse reward x 5; all scaled by reward_scale / 5.  The committed runs log a maximum of 0.98 = (1 + 0.9 + 3) / 5:
+       the peg's origin at the hole's centre is 0.1 from the plate's origin, 1 - tanh(0.1) = 0.9 */
+    real tt, d, cs; peg_hole_orientation(e, &tt, &d, &cs);
+    if (d < 0.06 && tt >= -0.12 && tt <= 0.14 && cs > 0.95) r = 1.0;
+    if (t->reward_shaping) {
+      real dv[3]; v3sub(dv, e->xpos[t->obj_body[1]], e->xpos[t->obj_body[0]]);
+      r += (1 - tanh(v3norm(dv))) + (1 - tanh(d)) + (1 - tanh(fabs(tt))) + cs;
+    } else r *= 5.0;
+    return r * t->reward_scale / 5.0;
+  }
   return 0;
 }
 
@@ -1143,6 +1165,15 @@ static void observation(const orc_env *e, real *obs) {
     real qc[4] = {qe[0], -qe[1], -qe[2], -qe[3]}, qr[4]; qmul(qr, qc, qo); qnormalize(qr);
     if (qr[0] < 0) for (int k = 0; k < 4; k++) qr[k] = -qr[k];
     put_quat_xyzw(obs + n, qr); n += 4;
+  } else if (t->task_id == RSB_TASK_PEGINHOLE) {
+    /* hole_pos, hole_quat, cyl_to_hole = peg - hole, cyl_quat, angle (= cos), t, d */
+    const real *hp = e->xpos[t->obj_body[0]], *pp = e->xpos[t->obj_body[1]];
+    for (int k = 0; k < 3; k++) obs[n++] = hp[k];
+    put_quat_xyzw(obs + n, e->xquat[t->obj_body[0]]); n += 4;
+    for (int k = 0; k < 3; k++) obs[n++] = pp[k] - hp[k];
+    put_quat_xyzw(obs + n, e->xquat[t->obj_body[1]]); n += 4;
+    real tt, d, cs; peg_hole_orientation(e, &tt, &d, &cs);
+    obs[n++] = cs; obs[n++] = tt; obs[n++] = d;
   }
 }
 

@@ -1499,6 +1499,16 @@ RSB_D bool check_grasp(int so, int ri, int obj_geom) { const real *s = RSB_SMEM 
   return tl && tr;
 }
 
+/* TwoArmPegInHole._compute_orientation (see the oracle's peg_hole_orientation): out = {t, d, cos} */
+RSB_DN void peg_hole_orientation(int so, real *out) { const real *s = RSB_SMEM + so;
+  const real *hp = s + MDL.o_xpos + 3 * MDL.obj_body[0], *Rh = s + MDL.o_xmat + 9 * MDL.obj_body[0], *pp = s + MDL.o_xpos + 3 * MDL.obj_body[1], *Rp = s + MDL.o_xmat + 9 * MDL.obj_body[1];
+  real v[3] = {Rp[2], Rp[5], Rp[8]}, n[3] = {Rh[2], Rh[5], Rh[8]}, cp[3], pc[3], x[3];
+  for (int k = 0; k < 3; k++) { cp[k] = hp[k] + MDL.task_par[0] * Rh[3 * k] - pp[k]; pc[k] = -cp[k]; }
+  cross3(x, v, pc);
+  const real vv = dot3(v, v);
+  out[0] = dot3(cp, v) / vv; out[1] = sqrtf(dot3(x, x) / vv); out[2] = fabsf(dot3(n, v)) / sqrtf(dot3(n, n) * vv);
+}
+
 /* A.6 staged task rewards (evaluated by every lane identically; cheap) */
 RSB_DN real task_reward(int so) { const real *s = RSB_SMEM + so;
   const real *xpos = s + MDL.o_xpos, *sxpos = s + MDL.o_sxpos, *qpos = s + MDL.o_qpos; real r = 0;
@@ -1564,6 +1574,15 @@ RSB_DN real task_reward(int so) { const real *s = RSB_SMEM + so;
     }
     return r * MDL.reward_scale;
   }
+  if (MDL.task_id == RSB_TASK_PEGINHOLE) {          /* success 1 + (reach, d, t, cos shaping terms), / 5 -- see the oracle's task_reward */
+    real o3[3]; peg_hole_orientation(so, o3);
+    if (o3[1] < 0.06f && o3[0] >= -0.12f && o3[0] <= 0.14f && o3[2] > 0.95f) r = 1.0f;
+    if (MDL.reward_shaping) {
+      const real *hp = xpos + 3 * MDL.obj_body[0], *pp = xpos + 3 * MDL.obj_body[1]; real dv[3] = {pp[0] - hp[0], pp[1] - hp[1], pp[2] - hp[2]};
+      r += (1 - tanhf(sqrtf(dot3(dv, dv)))) + (1 - tanhf(o3[1])) + (1 - tanhf(fabsf(o3[0]))) + o3[2];
+    } else r *= 5.0f;
+    return r * MDL.reward_scale / 5.0f;
+  }
   return 0;
 }
 
@@ -1577,6 +1596,16 @@ RSB_DN real obs_pickplace(int so, int i) { const real *s = RSB_SMEM + so;
   if (i < 10) { real Re[9], d[3] = {obj[0] - eef[0], obj[1] - eef[1], obj[2] - eef[2]}, rel[3]; quat2mat(Re, qe); matTvec3(rel, Re, d); return rel[i - 7]; }
   real qc[4] = {qe[0], -qe[1], -qe[2], -qe[3]}, qr[4]; quatmul(qr, qc, qo); quatnorm(qr);
   const real sg = qr[0] < 0 ? -1.0f : 1.0f; int k = i - 10; return sg * qr[k == 3 ? 0 : k + 1];
+}
+
+/* TwoArmPegInHole object-state (element i of 17): hole_pos, hole_quat, peg - hole, peg_quat, cos, t, d.  Not inlined, like obs_pickplace. */
+RSB_DN real obs_peginhole(int so, int i) { const real *s = RSB_SMEM + so;
+  const real *xpos = s + MDL.o_xpos, *xquat = s + MDL.o_xquat, *hp = xpos + 3 * MDL.obj_body[0], *pp = xpos + 3 * MDL.obj_body[1];
+  if (i < 3) return hp[i];
+  if (i < 7) { int k = i - 3; return xquat[4 * MDL.obj_body[0] + (k == 3 ? 0 : k + 1)]; }
+  if (i < 10) return pp[i - 7] - hp[i - 7];
+  if (i < 14) { int k = i - 10; return xquat[4 * MDL.obj_body[1] + (k == 3 ? 0 : k + 1)]; }
+  real o3[3]; peg_hole_orientation(so, o3); return i == 14 ? o3[2] : (i == 15 ? o3[0] : o3[1]);
 }
 
 /* A.1.4 observation vector, robosuite v1.0 order: per robot [sin q, cos q, qd, eef_pos, eef_quat(xyzw), grip q, grip qd], then object-state.
@@ -1633,6 +1662,7 @@ RSB_D real obs_element(int so, int i) { const real *s = RSB_SMEM + so;
     return h1[i - 22] - e1[i - 22];
   }
   if (MDL.task_id == RSB_TASK_PICKPLACE) return obs_pickplace(so, i);
+  if (MDL.task_id == RSB_TASK_PEGINHOLE) return obs_peginhole(so, i);
   return 0;
 }
 

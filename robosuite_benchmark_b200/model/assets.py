@@ -125,7 +125,15 @@ def rethink_gripper_actuators(pf: str) -> str:
 ARM_LINK_CAPSULES = False
 
 
-def panda(pf: str, base_pos, base_quat=(1, 0, 0, 0)) -> str:
+def null_gripper(pf: str, hand_pos: str, hand_quat: str, payload: str = "") -> str:
+    """robosuite's NullGripper (gripper_types=None, e.g. TwoArmPegInHole): the bare `right_hand` body with the `grip_site` at its origin; `payload` = bodies rigidly
+    attached to the hand (the peg / the plate with the hole)."""
+    return (f'<body name="{pf}right_hand" pos="{hand_pos}" quat="{hand_quat}">'
+            f'<inertial pos="0 0 0" mass="0.5" diaginertia="0.002 0.002 0.002"/>'
+            f'<site name="{pf}grip_site" pos="0 0 0"/>{payload}</body>')
+
+
+def panda(pf: str, base_pos, base_quat=(1, 0, 0, 0), gripper="default", payload: str = "") -> str:
     """Franka Emika Panda, 7 hinge joints about local z (link frames: SURVEY.md A.5)."""
     lim = [(-2.8973, 2.8973), (-1.7628, 1.7628), (-2.8973, 2.8973), (-3.0718, -0.0698),
            (-2.8973, 2.8973), (-0.0175, 3.7525), (-2.8973, 2.8973)]
@@ -148,16 +156,16 @@ def panda(pf: str, base_pos, base_quat=(1, 0, 0, 0)) -> str:
               f'<joint name="{pf}joint{i + 1}" type="hinge" axis="0 0 1" range="{lim[i][0]} {lim[i][1]}" damping="{damp[i]}"/>')
         if ARM_LINK_CAPSULES and (i + 1) in caps:
             s += f'<geom name="{pf}link{i + 1}_col" type="capsule" fromto="{caps[i + 1][0]}" size="{caps[i + 1][1]}" {ROBOT_COL}/>'
-    s += panda_gripper(pf)
+    s += panda_gripper(pf) if gripper == "default" else null_gripper(pf, "0 0 0.107", "0.9238795 0 0 -0.3826834", payload)
     s += "</body>" * 8
     return s
 
 
-def panda_actuators(pf: str) -> str:
+def panda_actuators(pf: str, gripper="default") -> str:
     tl = [80, 80, 80, 80, 12, 12, 12]
     s = "".join(f'<motor name="{pf}torq_j{i + 1}" joint="{pf}joint{i + 1}" ctrlrange="{-tl[i]} {tl[i]}" ctrllimited="true"/>'
                 for i in range(7))
-    return s + panda_gripper_actuators(pf)
+    return s + (panda_gripper_actuators(pf) if gripper == "default" else "")
 
 
 PANDA_INIT_QPOS = [0, PI / 16.0, 0.00, -PI / 2.0 - PI / 3.0, 0.00, PI - 0.2, PI / 4]
@@ -168,7 +176,7 @@ PANDA_GRIP_SIGN = [-1.0, 1.0]
 SAWYER = dict(damping=0.1, inertia_scale=1.0, armature=0.0, frictionloss=0.0)          # joint-space dynamics switches (what-if studies; defaults = round 1)
 
 
-def sawyer(pf: str, base_pos, base_quat=(1, 0, 0, 0)) -> str:
+def sawyer(pf: str, base_pos, base_quat=(1, 0, 0, 0), gripper="default", payload: str = "") -> str:
     """Rethink Sawyer, 7 hinge joints about local z (public URDF link frames)."""
     lim = [(-3.0503, 3.0503), (-3.8095, 2.2736), (-3.0426, 3.0426), (-3.0439, 3.0439),
            (-2.9761, 2.9761), (-2.9761, 2.9761), (-4.7124, 4.7124)]
@@ -186,16 +194,16 @@ def sawyer(pf: str, base_pos, base_quat=(1, 0, 0, 0)) -> str:
               f'<inertial pos="{inert[i][0]}" mass="{inert[i][1]}" diaginertia="{_f([inert[i][2] * SAWYER["inertia_scale"]] * 3)}"/>'
               f'<joint name="{pf}joint{i + 1}" type="hinge" axis="0 0 1" range="{lim[i][0]} {lim[i][1]}" damping="{SAWYER["damping"]}" '
               f'armature="{SAWYER["armature"]}" frictionloss="{SAWYER["frictionloss"]}"/>')
-    s += rethink_gripper(pf)
+    s += rethink_gripper(pf) if gripper == "default" else null_gripper(pf, "0 0 0.0245", "0.7071068 0 0 0.7071068", payload)
     s += "</body>" * 8
     return s
 
 
-def sawyer_actuators(pf: str) -> str:
+def sawyer_actuators(pf: str, gripper="default") -> str:
     tl = [80, 80, 40, 40, 9, 9, 9]
     s = "".join(f'<motor name="{pf}torq_j{i + 1}" joint="{pf}joint{i + 1}" ctrlrange="{-tl[i]} {tl[i]}" ctrllimited="true"/>'
                 for i in range(7))
-    return s + rethink_gripper_actuators(pf)
+    return s + (rethink_gripper_actuators(pf) if gripper == "default" else "")
 
 
 SAWYER_INIT_QPOS = [0, -1.18, 0.00, 2.18, 0.00, 0.57, 3.3161]
@@ -397,6 +405,40 @@ def bins_arena(friction=(1, 0.005, 0.0001)) -> str:
 
 def pick_object(kind: str, pos) -> str:
     return box_object(kind, PICK_OBJECTS[kind]["half"], pos, density=100, friction=(0.95, 0.3, 0.1), solref=(0.001, 1.0), solimp=(0.998, 0.998, 0.001))
+
+
+# ----------------------------------------------------------------------------- TwoArmPegInHole: peg and plate, rigidly attached to the two hands
+#: robosuite's TwoArmPegInHole as recalled: no grippers, no table (EmptyArena); robot 0 carries a cylinder peg at (0, 0, 0.15) of its hand (axis = the hand's z,
+#: half length 0.13, radius drawn once per model from U(0.015, 0.03): the mean here), robot 1 a plate with a hole at (0.11, 0, 0.17) / quat (0, 0, 0.707, 0.707) of
+#: its hand; the hole's centre is 0.1 along the plate body's x axis, its normal is the plate's z axis (TwoArmPegInHole._compute_orientation).  The plate's own
+#: geometry (plate-with-hole.xml) is NOT recalled: a 0.2 m square frame of four boxes around a square hole of half width `hole_half`, wide enough for the largest peg
+#: plus the success tolerance d < 0.06.  The peg is a capsule of the same radius and overall length (the kernels have no cylinder narrow phase; the side surface,
+#: which is what meets the hole's rim, is the same).  |y| of the bases: base_xpos_offset["empty"] = (-0.6, 0, 0) turned by +-90 degrees.
+PEG_IN_HOLE = dict(peg_radius=0.0225, peg_half_length=0.13, peg_pos=(0, 0, 0.15), hole_pos=(0.11, 0, 0.17), hole_quat=(0, 0, 0.7071068, 0.7071068),
+                   hole_center=0.1, hole_half=0.06, plate_half=0.1, plate_thickness=0.01, base_y=0.6, plate_density=500)
+
+
+def peg_payload(name="peg") -> str:
+    P = PEG_IN_HOLE
+    r, hl = P["peg_radius"], P["peg_half_length"]
+    return (f'<body name="{name}" pos="{_f(P["peg_pos"])}">'
+            f'<geom name="{name}_g0" type="capsule" fromto="0 0 {-(hl - r)} 0 0 {hl - r}" size="{r}" density="1000" friction="1 0.005 0.0001" {WORLD_COL}/></body>')
+
+
+def hole_payload(name="hole") -> str:
+    P = PEG_IN_HOLE
+    c, h, w, t = P["hole_center"], P["hole_half"], P["plate_half"], P["plate_thickness"]
+    col = f'density="{P["plate_density"]}" friction="1 0.005 0.0001" {WORLD_COL}'
+    bar = (w - h) / 2                                   # half width of the frame's bars
+    g = (f'<geom name="{name}_xp" type="box" pos="{c + h + bar} 0 0" size="{bar} {w} {t}" {col}/>'
+         f'<geom name="{name}_xn" type="box" pos="{c - h - bar} 0 0" size="{bar} {w} {t}" {col}/>'
+         f'<geom name="{name}_yp" type="box" pos="{c} {h + bar} 0" size="{h} {bar} {t}" {col}/>'
+         f'<geom name="{name}_yn" type="box" pos="{c} {-h - bar} 0" size="{h} {bar} {t}" {col}/>')
+    return f'<body name="{name}" pos="{_f(P["hole_pos"])}" quat="{_f(P["hole_quat"])}">{g}<site name="{name}_center" pos="{c} 0 0"/></body>'
+
+
+def empty_arena() -> str:
+    return f'<geom name="floor" type="plane" pos="0 0 0" size="3 3 0.125" {WORLD_COL}/>'
 
 
 def scene(world: str, actuators: str, extra: str = "") -> str:

@@ -14,10 +14,12 @@ import numpy as np
 from . import assets as A
 from .mjcf import Model, compile_mjcf
 
-TASK_IDS = {"Lift": 0, "Door": 1, "Stack": 2, "TwoArmLift": 3, "PickPlaceMilk": 4, "PickPlaceBread": 4, "PickPlaceCereal": 4, "PickPlaceCan": 4}
+TASK_IDS = {"Lift": 0, "Door": 1, "Stack": 2, "TwoArmLift": 3, "PickPlaceMilk": 4, "PickPlaceBread": 4, "PickPlaceCereal": 4, "PickPlaceCan": 4,
+            "TwoArmPegInHole": 5}
 CTRL_IDS = {"OSC_POSE": 0, "OSC_POSITION": 1, "JOINT_VELOCITY": 2, "JOINT_TORQUE": 3}
 
-OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89, "PickPlaceMilk": 46, "PickPlaceBread": 46, "PickPlaceCereal": 46, "PickPlaceCan": 46}
+OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89, "PickPlaceMilk": 46, "PickPlaceBread": 46, "PickPlaceCereal": 46, "PickPlaceCan": 46,
+            "TwoArmPegInHole": 73}
 #: default bounds of the per-env contact list / constraint-row list (shared-memory sizing; rsb_create ncon_max / nefc_max).
 #: Maxima seen over 300 random-action control steps x 2048 envs (tools/limits_stats.py): Stack 16 contacts / 54 rows, TwoArmLift 9 / 31,
 #: Door 4 / 18, Lift 9 / 29; TwoArmLift (24, 80) keeps 2.5x headroom and lets 14 envs share an SM (4096 envs = 2 waves instead of 3).
@@ -30,6 +32,7 @@ OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89, "PickPlaceMil
 #: `suite.make(..., ncon_max=24, nefc_max=80)` removes that at the price of a second wave at 4096 envs per GPU.
 LIMITS = {"Lift": (18, 62), ("Lift", "Sawyer"): (24, 80), "Door": (16, 64), "Stack": (24, 96), "TwoArmLift": (24, 80),
           # PickPlace, committed policies on the CPU oracle (16 episodes each): Panda reaches 13 contacts / 49 rows while carrying the object, Sawyer 18 / 64
+          "TwoArmPegInHole": (8, 40),          # committed policies on the CPU oracle: at most 3 contacts (peg on the rim of the hole) / 11 rows
           **{"PickPlace" + k: (18, 62) for k in ("Milk", "Bread", "Cereal", "Can")}, **{("PickPlace" + k, "Sawyer"): (24, 80) for k in ("Milk", "Bread", "Cereal", "Can")}}
 
 
@@ -37,12 +40,13 @@ def limits_for(env_name, robots):
     return LIMITS.get((env_name, robots[0]), LIMITS[env_name])
 
 
-def _robot_desc(m: Model, pf: str, robot: str, cc: dict) -> dict:
+def _robot_desc(m: Model, pf: str, robot: str, cc: dict, gripper="default") -> dict:
     R = A.ROBOTS[robot]
     jn = [m.id("joint", f"{pf}joint{i + 1}") for i in range(7)]
-    fj = [m.id("joint", f"{pf}finger_joint{i + 1}") for i in range(2)]
+    ng = 2 if gripper == "default" else 0                  # gripper_types=None (robosuite's NullGripper): no finger joints, no gripper action
+    fj = [m.id("joint", f"{pf}finger_joint{i + 1}") for i in range(ng)]
     act = [m.id("actuator", f"{pf}torq_j{i + 1}") for i in range(7)]
-    gact = [m.id("actuator", f"{pf}gripper_finger_joint{i + 1}") for i in range(2)]
+    gact = [m.id("actuator", f"{pf}gripper_finger_joint{i + 1}") for i in range(ng)]
     ctype = cc["type"]
     ndim = {"OSC_POSE": 6, "OSC_POSITION": 3, "JOINT_VELOCITY": 7, "JOINT_TORQUE": 7}[ctype]
 
@@ -76,13 +80,13 @@ def _robot_desc(m: Model, pf: str, robot: str, cc: dict) -> dict:
     vl = cc.get("velocity_limits")
     d = dict(
         arm_qposadr=[int(m.jnt_qposadr[j]) for j in jn], arm_dofadr=[int(m.jnt_dofadr[j]) for j in jn],
-        arm_act=act, grip_ndof=2, grip_qposadr=[int(m.jnt_qposadr[j]) for j in fj],
-        grip_dofadr=[int(m.jnt_dofadr[j]) for j in fj], grip_act=gact, grip_action_dim=1,
-        grip_sign=list(R["grip_sign"]), grip_speed=0.01, grip_init_qpos=list(R["grip_init"]),
+        arm_act=act, grip_ndof=ng, grip_qposadr=[int(m.jnt_qposadr[j]) for j in fj],
+        grip_dofadr=[int(m.jnt_dofadr[j]) for j in fj], grip_act=gact, grip_action_dim=1 if ng else 0,
+        grip_sign=list(R["grip_sign"])[:ng], grip_speed=0.01, grip_init_qpos=list(R["grip_init"])[:ng],
         eef_site=m.id("site", f"{pf}grip_site"), eef_body=m.id("body", f"{pf}right_hand"),
         init_qpos=list(R["init_qpos"]),
-        left_finger_geoms=[m.id("geom", f"{pf}finger1_col"), m.id("geom", f"{pf}finger1_pad")],
-        right_finger_geoms=[m.id("geom", f"{pf}finger2_col"), m.id("geom", f"{pf}finger2_pad")],
+        left_finger_geoms=[m.id("geom", f"{pf}finger1_col"), m.id("geom", f"{pf}finger1_pad")] if ng else [],
+        right_finger_geoms=[m.id("geom", f"{pf}finger2_col"), m.id("geom", f"{pf}finger2_pad")] if ng else [],
         ctrl_type=CTRL_IDS[ctype], control_dim=ndim,
         input_max=vec(cc.get("input_max", 1.0), ndim), input_min=vec(cc.get("input_min", -1.0), ndim),
         output_max=vec(cc.get("output_max", 1.0), ndim), output_min=vec(cc.get("output_min", -1.0), ndim),
@@ -119,16 +123,19 @@ def build_task(env_name: str, robots: Sequence[str], controller_config: dict, ho
     apply_solver_option(m, solver)
     substeps = int((1.0 / control_freq) / m.timestep)
     n_rob = len(robots)
-    rdesc = [_robot_desc(m, f"robot{i}_", r, controller_config) for i, r in enumerate(robots)]
+    rdesc = [_robot_desc(m, f"robot{i}_", r, controller_config, gripper=GRIPPERS.get(env_name, "default")) for i, r in enumerate(robots)]
     act_dim = sum(r["control_dim"] + r["grip_action_dim"] for r in rdesc)
     task = dict(task_id=TASK_IDS[env_name], nrobot=n_rob, robot=rdesc, horizon=int(horizon), substeps=substeps,
                 ignore_done=int(bool(ignore_done)), reward_shaping=int(bool(reward_shaping)),
                 reward_scale=float(reward_scale), init_noise=0.02, table_height=A.TABLE_HEIGHT,
-                obs_dim=OBS_DIMS[env_name] if n_rob == (2 if env_name == "TwoArmLift" else 1) else None,
+                obs_dim=OBS_DIMS[env_name] if n_rob == (2 if env_name.startswith("TwoArm") else 1) else None,
                 act_dim=act_dim, env_name=env_name, robots=list(robots), xml=xml, ncon_max=limits_for(env_name, robots)[0], nefc_max=limits_for(env_name, robots)[1])
     task.update(objs(m))
     return m, task
 
+
+#: tasks whose robots carry no gripper (robosuite: gripper_types=None)
+GRIPPERS = {"TwoArmPegInHole": None}
 
 SOLVER_FP32 = dict(iterations=12, tolerance=1e-6, ls_iterations=24, ls_tolerance=0.01)
 
@@ -314,5 +321,31 @@ def _pick_place(kind):
     return build
 
 
-_BUILDERS: Dict[str, callable] = {"Lift": _lift, "Stack": _stack, "Door": _door, "TwoArmLift": _two_arm_lift,
+def _two_arm_peg_in_hole(robots, env_configuration):
+    """TwoArmPegInHole, `single-arm-opposed`: two gripper-less arms facing each other over an empty floor; robot 0 holds the peg, robot 1 the plate with the hole
+    (both rigidly attached to the hands: no free bodies, nothing to place at reset)."""
+    assert len(robots) == 2, "TwoArmPegInHole takes two robots"
+    if env_configuration not in ("single-arm-opposed", "default", None):
+        raise NotImplementedError(f"env_configuration {env_configuration!r} is not implemented (single-arm-opposed only)")
+    bodies, acts = "", ""
+    by = A.PEG_IN_HOLE["base_y"]
+    for i, (r, yaw, y, payload) in enumerate(zip(robots, (np.pi / 2, -np.pi / 2), (-by, by), (A.peg_payload(), A.hole_payload()))):
+        R = A.ROBOTS[r]
+        quat = (np.cos(yaw / 2), 0, 0, np.sin(yaw / 2))
+        bodies += R["body"](f"robot{i}_", (0.0, y, A.ROBOT_BASE_Z), quat, gripper=None, payload=payload)
+        acts += R["act"](f"robot{i}_", gripper=None)
+    xml = A.scene(A.empty_arena() + bodies, acts)
+
+    def objs(m: Model):
+        o = _empty_objs()
+        o["obj_body"][0], o["obj_body"][1] = m.id("body", "hole"), m.id("body", "peg")
+        o["obj_geom"][0] = m.id("geom", "peg_g0")
+        o["obj_site"][0] = m.id("site", "hole_center")
+        o["task_par"] = [A.PEG_IN_HOLE["hole_center"]] + [0.0] * 7
+        return o
+
+    return xml, objs
+
+
+_BUILDERS: Dict[str, callable] = {"Lift": _lift, "Stack": _stack, "Door": _door, "TwoArmLift": _two_arm_lift, "TwoArmPegInHole": _two_arm_peg_in_hole,
                                   **{"PickPlace" + k: _pick_place(k) for k in A.PICK_OBJECTS}}

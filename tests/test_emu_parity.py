@@ -10,7 +10,8 @@ from tests.emu.emu import EmuEnv
 
 CONFIGS = [("Lift", ["Panda"], "OSC_POSE", 42, 7), ("Lift", ["Panda"], "JOINT_VELOCITY", 42, 8), ("Lift", ["Sawyer"], "OSC_POSITION", 42, 4),
            ("Door", ["Panda"], "JOINT_VELOCITY", 46, 8), ("Stack", ["Sawyer"], "OSC_POSE", 55, 7), ("TwoArmLift", ["Panda", "Panda"], "OSC_POSE", 89, 14),
-           ("PickPlaceCan", ["Panda"], "OSC_POSE", 46, 7), ("PickPlaceMilk", ["Sawyer"], "OSC_POSE", 46, 7)]
+           ("PickPlaceCan", ["Panda"], "OSC_POSE", 46, 7), ("PickPlaceMilk", ["Sawyer"], "OSC_POSE", 46, 7),
+           ("TwoArmPegInHole", ["Panda", "Sawyer"], "OSC_POSE", 73, 12)]
 
 
 @pytest.mark.parametrize("env_name,robots,ctrl,obs_dim,act_dim", CONFIGS)

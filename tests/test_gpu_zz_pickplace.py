@@ -1,4 +1,4 @@
-"""PickPlace (single-object mode: runs/PickPlace{Can,Milk}-{Panda,Sawyer}-OSC-POSE-*) on the CUDA kernels, through the C-ABI: the checks of tests/test_pickplace.py
+"""PickPlace (single-object mode: runs/PickPlace{Can,Milk}-{Panda,Sawyer}-OSC-POSE-*) and TwoArmPegInHole (runs/TwoArmPegInHole-*-OSC-POSE-*) on the CUDA kernels, through the C-ABI: the checks of tests/test_pickplace.py
 and of the other families' GPU tests, on the real kernels.  The file sorts after the other GPU tests on purpose: these families were added last."""
 import json
 import os
@@ -10,7 +10,8 @@ from tests.test_gpu_parity import test_other_config_families_one_control_step as
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-FAMILIES = [("PickPlaceCan", ["Panda"], "OSC_POSE"), ("PickPlaceMilk", ["Sawyer"], "OSC_POSE"), ("PickPlaceCan", ["Sawyer"], "OSC_POSE"), ("PickPlaceMilk", ["Panda"], "OSC_POSE")]
+FAMILIES = [("PickPlaceCan", ["Panda"], "OSC_POSE"), ("PickPlaceMilk", ["Sawyer"], "OSC_POSE"), ("PickPlaceCan", ["Sawyer"], "OSC_POSE"), ("PickPlaceMilk", ["Panda"], "OSC_POSE"),
+            ("TwoArmPegInHole", ["Panda", "Panda"], "OSC_POSE"), ("TwoArmPegInHole", ["Panda", "Sawyer"], "OSC_POSE"), ("TwoArmPegInHole", ["Sawyer", "Sawyer"], "OSC_POSE")]
 
 
 @pytest.mark.parametrize("env_name,robots,ctrl", FAMILIES)
@@ -19,7 +20,7 @@ def test_pickplace_one_control_step(env_name, robots, ctrl, torch_cuda):
     _one_control_step(env_name, robots, ctrl, torch_cuda)
 
 
-@pytest.mark.parametrize("env_name,robots", [("PickPlaceCan", "Panda"), ("PickPlaceMilk", "Sawyer")])
+@pytest.mark.parametrize("env_name,robots", [("PickPlaceCan", "Panda"), ("PickPlaceMilk", "Sawyer"), ("TwoArmPegInHole", ["Panda", "Sawyer"])])
 def test_pickplace_full_episode_no_truncation_and_reward_mean(env_name, robots, torch_cuda):
     """A full 500-step random-action episode of 2048 envs: no contact / row truncation, finite observations, and the episode reward mean within 1 % of the
     oracle's over the same (seed, env id) streams (north_star: random-action episode reward means match within 1 %)."""
@@ -30,7 +31,7 @@ def test_pickplace_full_episode_no_truncation_and_reward_mean(env_name, robots, 
     env = suite.make(env_name, robots, controller_configs=suite.load_controller_config(default_controller="OSC_POSE"), num_envs=n, device="cuda:0", seed=59,
                      horizon=500, control_freq=20, reward_shaping=True, ignore_done=True)
     sim = env.sim
-    assert (sim.obs_dim, sim.act_dim) == (46, 7)
+    assert (sim.obs_dim, sim.act_dim) == ((73, 12) if env_name == "TwoArmPegInHole" else (46, 7))
     obs = sim.reset()
     act = torch.empty(n, sim.act_dim, device="cuda:0"); rew = torch.empty(n, device="cuda:0"); done = torch.empty(n, dtype=torch.uint8, device="cuda:0")
     tot = torch.zeros(n, device="cuda:0")
