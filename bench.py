@@ -7,7 +7,7 @@ tanh(N(0,1)) actions from the Philox stream shared with the oracle, horizon 500 
 states/actions resident in HBM (CUDA events around each step, L2 flushed between steps); `e2e` goes through the host-buffer C-ABI call
 (pinned host actions in, obs/reward/done out) each step.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--config lift|door|stack|twoarmlift] [--mode step|train] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--config lift|door|stack|twoarmlift|pickplacecan|peginhole] [--mode step|train] [--impl ours|reference]
 
 --config selects the other BASELINE.json configs (configs[2] Door-Panda-JOINT_VELOCITY x 16384, configs[3] Stack-Sawyer-OSC_POSE,
 configs[4] TwoArmLift-PandaPanda-OSC_POSE); the default (lift) line also carries a short steady-state measurement of each of them
@@ -36,6 +36,10 @@ CONFIGS = {   # BASELINE.json configs[1..4]
     "door": dict(env="Door", robots=["Panda"], controller="JOINT_VELOCITY", envs=16384),
     "stack": dict(env="Stack", robots=["Sawyer"], controller="OSC_POSE", envs=4096),
     "twoarmlift": dict(env="TwoArmLift", robots=["Panda", "Panda"], controller="OSC_POSE", envs=4096),
+    # families of the reference's runs/ beyond BASELINE.json's configs, added last in round 2: parity-tested on the CPU emulator and by
+    # tests/test_gpu_zz_pickplace.py; their rates ride along in the default line as `more_families`
+    "pickplacecan": dict(env="PickPlaceCan", robots=["Panda"], controller="OSC_POSE", envs=4096),
+    "peginhole": dict(env="TwoArmPegInHole", robots=["Panda", "Sawyer"], controller="OSC_POSE", envs=4096),
 }
 UNIT = "control-steps/s"
 PREROLL = 100          # untimed control steps after the initial reset (run_ours): the timed region sits on the steady-state part of the episode
@@ -403,6 +407,16 @@ def run_ours(args):
     train = None
     if not args.no_train and not args.quick:
         train = train_loop_bench(cfg, dev, world, rank, envs=E, epochs=3, warm_epochs=1)
+    if not args.quick and args.config == "lift" and world == 1:
+        # the families added last (CONFIGS): measured after everything the headline line needs, single-GPU line only, and never allowed to take that line down
+        more = {}
+        for name in ("pickplacecan", "peginhole"):
+            c = CONFIGS[name]
+            try:
+                more[name] = steady_state_rate(c, c["envs"], dev, 0, steps=20)
+            except Exception as e:          # noqa: BLE001 -- reported in the line instead
+                more[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        extras["more_families"] = more
 
     if rank == 0:
         peaks = {}

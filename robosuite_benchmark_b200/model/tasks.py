@@ -31,9 +31,10 @@ OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89, "PickPlaceMil
 #: committed Lift-Panda policy exceeds these limits in 1.4e-4 of its env-steps (pads + table + hand on the cube) --
 #: `suite.make(..., ncon_max=24, nefc_max=80)` removes that at the price of a second wave at 4096 envs per GPU.
 LIMITS = {"Lift": (18, 62), ("Lift", "Sawyer"): (24, 80), "Door": (16, 64), "Stack": (24, 96), "TwoArmLift": (24, 80),
-          # PickPlace, committed policies on the CPU oracle (16 episodes each): Panda reaches 13 contacts / 49 rows while carrying the object, Sawyer 18 / 64
-          "TwoArmPegInHole": (8, 40),          # committed policies on the CPU oracle: at most 3 contacts (peg on the rim of the hole) / 11 rows
-          **{"PickPlace" + k: (18, 62) for k in ("Milk", "Bread", "Cereal", "Can")}, **{("PickPlace" + k, "Sawyer"): (24, 80) for k in ("Milk", "Bread", "Cereal", "Can")}}
+          "TwoArmPegInHole": (8, 40),          # committed policies and random actions on the CPU oracle: at most 3 contacts (peg on the rim of the hole) / 11 rows
+          # PickPlace on the CPU oracle.  Committed policies (16 episodes each): Panda reaches 13 contacts / 49 rows while carrying the object, Sawyer 18 / 64.
+          # Random actions (768 envs x 500 steps): Panda 14 / 46, Sawyer 21 / 74 (the Rethink gripper's box fingers flat on the bin floor against a wall).
+          **{"PickPlace" + k: (24, 80) for k in ("Milk", "Bread", "Cereal", "Can")}, **{("PickPlace" + k, "Sawyer"): (32, 104) for k in ("Milk", "Bread", "Cereal", "Can")}}
 
 
 def limits_for(env_name, robots):

@@ -15,11 +15,11 @@ CONFIGS = [("Lift", ["Panda"], "OSC_POSE", 42, 7), ("Lift", ["Panda"], "JOINT_VE
 
 
 @pytest.mark.parametrize("env_name,robots,ctrl,obs_dim,act_dim", CONFIGS)
-def test_control_step_matches_oracle(env_name, robots, ctrl, obs_dim, act_dim):
+def test_control_step_matches_oracle(env_name, robots, ctrl, obs_dim, act_dim, lanes=32):
     m, t = build_task(env_name, robots, load_controller_config(default_controller=ctrl), ignore_done=True)
     assert (t["obs_dim"], t["act_dim"]) == (obs_dim, act_dim)          # dims pinned by the committed networks
     nc, ne = t["ncon_max"], t["nefc_max"]
-    orc, emu = OracleEnv(m, t, ncon_max=nc, nefc_max=ne), EmuEnv(m, t, nc, ne)
+    orc, emu = OracleEnv(m, t, ncon_max=nc, nefc_max=ne), EmuEnv(m, t, nc, ne, lanes=lanes)
     o1, o2 = orc.reset(seed=17, env_id=3), emu.reset(seed=17, env_id=3)
     assert np.abs(o1 - o2).max() < 2e-6
     for k in range(2):
@@ -33,6 +33,12 @@ def test_control_step_matches_oracle(env_name, robots, ctrl, obs_dim, act_dim):
         qp2, qv2, _, _ = emu.get_state()
         assert np.abs(qp - qp2).max() <= 1e-4 and np.abs(qv - qv2).max() <= 1e-4      # north_star tolerance for one control step (fp32)
         assert np.abs(o1 - o2).max() <= 1e-4 and abs(r1 - r2) <= 1e-5
+
+
+@pytest.mark.parametrize("env_name,robots,ctrl,obs_dim,act_dim", [c for c in CONFIGS if c[0] in ("Lift", "Door", "PickPlaceCan", "PickPlaceMilk", "TwoArmPegInHole")])
+def test_control_step_matches_oracle_16_lane_groups(env_name, robots, ctrl, obs_dim, act_dim):
+    """Models with nv <= 16 run as 16-lane groups (two envs per warp) on the GPU (csrc/rsb_cuda.cu): the same check on the device code compiled for 16 lanes."""
+    test_control_step_matches_oracle(env_name, robots, ctrl, obs_dim, act_dim, lanes=16)
 
 
 def test_lane_order_independence():

@@ -94,7 +94,7 @@ def test_committed_policy_inserts_the_peg_and_device_code_follows_it():
     pol = DeterministicPolicy({k: v.astype(np.float64) for k, v in d.items()})
     m, t = build_task(cfg["env_name"], cfg["robots"], load_controller_config(default_controller=cfg["controller"]), horizon=cfg["horizon"], ignore_done=True)
     nc, ne = t["ncon_max"], t["nefc_max"]
-    orc, emu = OracleEnv(m, t, ncon_max=nc, nefc_max=ne), EmuEnv(m, t, nc, ne)
+    orc, emu = OracleEnv(m, t, ncon_max=nc, nefc_max=ne), EmuEnv(m, t, nc, ne, lanes=16)          # nv = 14: the GPU runs this model as 16-lane groups
     o = orc.reset(seed=17, env_id=0)
     emu.reset(seed=17, env_id=0)
     ret, best, worst = 0.0, 0.0, 0.0

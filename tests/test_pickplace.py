@@ -132,7 +132,7 @@ def test_device_code_matches_oracle_on_policy_states():
     pol, _, cfg = _policy("PickPlaceCan-Sawyer-OSC-POSE-SEED59")
     m, t = build_task(cfg["env_name"], cfg["robots"], load_controller_config(default_controller=cfg["controller"]), horizon=cfg["horizon"], ignore_done=True)
     nc, ne = 32, 112
-    orc, emu = OracleEnv(m, t, ncon_max=nc, nefc_max=ne), EmuEnv(m, t, nc, ne)
+    orc, emu = OracleEnv(m, t, ncon_max=nc, nefc_max=ne), EmuEnv(m, t, nc, ne, lanes=16)          # nv = 15: the GPU runs this model as 16-lane groups
     o = orc.reset(seed=17, env_id=1)
     emu.reset(seed=17, env_id=1)
     checked = grazing = in_contact = 0
