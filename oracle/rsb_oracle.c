@@ -1001,15 +1001,17 @@ static void substep(orc_env *e, const real *action, int policy_step) {
 
 /* ------------------------------------------------------------------ A.6 rewards, A.1.4 observations */
 static int geom_in(const int *set, int n, int g) { for (int i = 0; i < n; i++) if (set[i] == g) return 1; return 0; }
-static int check_grasp(const orc_env *e, int ri, int obj_geom) {
+/* both fingers of robot ri touch a geom of the object (geom ids lo..hi) */
+static int check_grasp_range(const orc_env *e, int ri, int lo, int hi) {
   const rsb_robot *rb = &e->t.robot[ri]; int tl = 0, tr = 0;
   for (int c = 0; c < e->ncon; c++) {
-    int g1 = e->con[c].geom1, g2 = e->con[c].geom2;
-    if ((geom_in(rb->left_finger_geoms, rb->n_left_finger_geoms, g1) && g2 == obj_geom) || (geom_in(rb->left_finger_geoms, rb->n_left_finger_geoms, g2) && g1 == obj_geom)) tl = 1;
-    if ((geom_in(rb->right_finger_geoms, rb->n_right_finger_geoms, g1) && g2 == obj_geom) || (geom_in(rb->right_finger_geoms, rb->n_right_finger_geoms, g2) && g1 == obj_geom)) tr = 1;
+    int g1 = e->con[c].geom1, g2 = e->con[c].geom2, o1 = g1 >= lo && g1 <= hi, o2 = g2 >= lo && g2 <= hi;
+    if ((geom_in(rb->left_finger_geoms, rb->n_left_finger_geoms, g1) && o2) || (geom_in(rb->left_finger_geoms, rb->n_left_finger_geoms, g2) && o1)) tl = 1;
+    if ((geom_in(rb->right_finger_geoms, rb->n_right_finger_geoms, g1) && o2) || (geom_in(rb->right_finger_geoms, rb->n_right_finger_geoms, g2) && o1)) tr = 1;
   }
   return tl && tr;
 }
+static int check_grasp(const orc_env *e, int ri, int obj_geom) { return check_grasp_range(e, ri, obj_geom, obj_geom); }
 
 /* TwoArmPegInHole._compute_orientation: v = peg axis (the peg body's z), c = hole centre (plate origin + offset along the plate's x); t = (c - p) . v, the
    signed distance of the centre along the axis from the peg's origin; d = |v x (p - c)|, the distance of the centre from the axis; cosn = |n . v| with n the plate's z */
@@ -1104,6 +1106,25 @@ static real task_reward(const orc_env *e) {
     } else r *= 5.0;
     return r * t->reward_scale / 5.0;
   }
+  if (t->task_id == RSB_TASK_NUTASSEMBLY) {
+    /* robosuite v1.0 NutAssembly.reward / staged_rewards / on_peg in single-object mode: success (nut centre within 0.03 of its peg in x and y, below table + 0.05,
+       gripper away: 1 - tanh(10 |eef - nut|) < 0.6) -> 1; otherwise, when shaping, the maximum of reach 0.1 (1 - tanh(10 |eef - handle geom|)), grasp 0.35 (both
+       fingers touch any geom of the nut), lift 0.35 + 0.15 (1 - tanh(15 max(z_target - z, 0))) while grasped, hover = lift + 0.2 (1 - tanh(10 |xy - peg|)).
+       Same plateaus in the committed NutAssemblyRound logs: 0.35, 0.5, up to 0.7, exactly 1.0. */
+    const real *nut = e->xpos[t->obj_body[0]], *eef = e->site_xpos[t->robot[0].eef_site], *handle = e->geom_xpos[t->obj_geom[1]], *tp = t->task_par;
+    real d[3]; v3sub(d, eef, nut);
+    int on_peg = fabs(nut[0] - tp[0]) < 0.03 && fabs(nut[1] - tp[1]) < 0.03 && nut[2] < tp[2] + 0.05;
+    if (on_peg && 1 - tanh(10.0 * v3norm(d)) < 0.6) r = 1.0;
+    else if (t->reward_shaping) {
+      v3sub(d, eef, handle);
+      real r_reach = 0.1 * (1 - tanh(10.0 * v3norm(d))), r_grasp = check_grasp_range(e, 0, t->obj_geom[0], t->obj_geom[1]) ? 0.35 : 0.0, r_lift = 0;
+      if (r_grasp > 0) { real zd = tp[3] - nut[2]; if (zd < 0) zd = 0; r_lift = 0.35 + (1 - tanh(15.0 * zd)) * 0.15; }
+      real hd = sqrt((nut[0] - tp[0]) * (nut[0] - tp[0]) + (nut[1] - tp[1]) * (nut[1] - tp[1]));
+      real r_hover = r_lift + (1 - tanh(10.0 * hd)) * 0.2;
+      r = r_reach; if (r_grasp > r) r = r_grasp; if (r_lift > r) r = r_lift; if (r_hover > r) r = r_hover;
+    }
+    return r * t->reward_scale;
+  }
   return 0;
 }
 
@@ -1154,7 +1175,7 @@ static void observation(const orc_env *e, real *obs) {
     for (int k = 0; k < 3; k++) obs[n++] = h1[k];
     for (int k = 0; k < 3; k++) obs[n++] = h0[k] - e0[k];
     for (int k = 0; k < 3; k++) obs[n++] = h1[k] - e1[k];
-  } else if (t->task_id == RSB_TASK_PICKPLACE) {
+  } else if (t->task_id == RSB_TASK_PICKPLACE || t->task_id == RSB_TASK_NUTASSEMBLY) {
     /* object-state of robosuite v1.0 PickPlace._get_observation, single-object mode: {obj}_pos, {obj}_quat (xyzw), then the object's pose in the gripper frame
        (pose_inv(eef pose) * object pose: {obj}_to_eef_pos = R_eef^T (p_obj - p_eef), {obj}_to_eef_quat = mat2quat(R_eef^T R_obj), xyzw with w >= 0) */
     const real *obj = e->xpos[t->obj_body[0]], *qe = e->xquat[t->robot[0].eef_body], *qo = e->xquat[t->obj_body[0]];

@@ -1489,15 +1489,16 @@ RSB_D void substep(int so, Grp g, bool policy_step, long long &pt_) {
 }
 
 RSB_D bool geom_in(const int *set, int n, int gm) { for (int i = 0; i < n; i++) if (set[i] == gm) return true; return false; }
-RSB_D bool check_grasp(int so, int ri, int obj_geom) { const real *s = RSB_SMEM + so;
+RSB_D bool check_grasp_range(int so, int ri, int lo, int hi) { const real *s = RSB_SMEM + so;       /* both fingers of robot ri touch a geom lo..hi of the object */
   const DevRobot &rb = MDL.robot[ri]; const real *con = s + MDL.o_con; int ncon = ((const int *)(s + MDL.o_misc))[MISC_NCON]; bool tl = false, tr = false;
   for (int c = 0; c < ncon; c++) {
-    const int *ci = (const int *)(con + c * RSB_CONW); int g1 = CON_G1_OF(ci), g2 = CON_G2_OF(ci);
-    if ((geom_in(rb.lfg, rb.nlfg, g1) && g2 == obj_geom) || (geom_in(rb.lfg, rb.nlfg, g2) && g1 == obj_geom)) tl = true;
-    if ((geom_in(rb.rfg, rb.nrfg, g1) && g2 == obj_geom) || (geom_in(rb.rfg, rb.nrfg, g2) && g1 == obj_geom)) tr = true;
+    const int *ci = (const int *)(con + c * RSB_CONW); int g1 = CON_G1_OF(ci), g2 = CON_G2_OF(ci); const bool o1 = g1 >= lo && g1 <= hi, o2 = g2 >= lo && g2 <= hi;
+    if ((geom_in(rb.lfg, rb.nlfg, g1) && o2) || (geom_in(rb.lfg, rb.nlfg, g2) && o1)) tl = true;
+    if ((geom_in(rb.rfg, rb.nrfg, g1) && o2) || (geom_in(rb.rfg, rb.nrfg, g2) && o1)) tr = true;
   }
   return tl && tr;
 }
+RSB_D bool check_grasp(int so, int ri, int obj_geom) { return check_grasp_range(so, ri, obj_geom, obj_geom); }
 
 /* TwoArmPegInHole._compute_orientation (see the oracle's peg_hole_orientation): out = {t, d, cos} */
 RSB_DN void peg_hole_orientation(int so, real *out) { const real *s = RSB_SMEM + so;
@@ -1571,6 +1572,21 @@ RSB_DN real task_reward(int so) { const real *s = RSB_SMEM + so;
       const real hx = obj[0] - tp[0], hy = obj[1] - tp[1];
       const real r_hover = (above ? 0.5f : r_lift) + (1 - tanhf(10.0f * sqrtf(hx * hx + hy * hy))) * 0.2f;
       r = fmaxf(fmaxf(0.1f * reach, r_grasp), fmaxf(r_lift, r_hover));
+    }
+    return r * MDL.reward_scale;
+  }
+  if (MDL.task_id == RSB_TASK_NUTASSEMBLY) {        /* single-object NutAssembly: success 1, else max(reach to the handle, grasp, lift, hover over the peg) -- see the oracle */
+    const real *nut = xpos + 3 * MDL.obj_body[0], *handle = s + MDL.o_gxpos + 3 * MDL.obj_geom[1], *tp = MDL.task_par;
+    real d[3] = {eef[0] - nut[0], eef[1] - nut[1], eef[2] - nut[2]};
+    const bool on_peg = fabsf(nut[0] - tp[0]) < 0.03f && fabsf(nut[1] - tp[1]) < 0.03f && nut[2] < tp[2] + 0.05f;
+    if (on_peg && 1 - tanhf(10.0f * sqrtf(dot3(d, d))) < 0.6f) r = 1.0f;
+    else if (MDL.reward_shaping) {
+      real dh[3] = {eef[0] - handle[0], eef[1] - handle[1], eef[2] - handle[2]};
+      const real r_reach = 0.1f * (1 - tanhf(10.0f * sqrtf(dot3(dh, dh)))), r_grasp = check_grasp_range(so, 0, MDL.obj_geom[0], MDL.obj_geom[1]) ? 0.35f : 0.0f; real r_lift = 0;
+      if (r_grasp > 0) r_lift = 0.35f + (1 - tanhf(15.0f * fmaxf(tp[3] - nut[2], 0.0f))) * 0.15f;
+      const real hx = nut[0] - tp[0], hy = nut[1] - tp[1];
+      const real r_hover = r_lift + (1 - tanhf(10.0f * sqrtf(hx * hx + hy * hy))) * 0.2f;
+      r = fmaxf(fmaxf(r_reach, r_grasp), fmaxf(r_lift, r_hover));
     }
     return r * MDL.reward_scale;
   }
@@ -1661,7 +1677,7 @@ RSB_D real obs_element(int so, int i) { const real *s = RSB_SMEM + so;
     if (i < 22) return h0[i - 19] - e0[i - 19];
     return h1[i - 22] - e1[i - 22];
   }
-  if (MDL.task_id == RSB_TASK_PICKPLACE) return obs_pickplace(so, i);
+  if (MDL.task_id == RSB_TASK_PICKPLACE || MDL.task_id == RSB_TASK_NUTASSEMBLY) return obs_pickplace(so, i);
   if (MDL.task_id == RSB_TASK_PEGINHOLE) return obs_peginhole(so, i);
   return 0;
 }

@@ -441,5 +441,43 @@ def empty_arena() -> str:
     return f'<geom name="floor" type="plane" pos="0 0 0" size="3 3 0.125" {WORLD_COL}/>'
 
 
+# ----------------------------------------------------------------------------- NutAssembly: pegs arena and the nuts
+#: robosuite's PegsArena / NutAssembly as recalled: table 0.45 x 0.69 m with its top at z = 0.82 (table_offset), the square peg (box, half 0.016 x 0.016 x 0.1) at
+#: (0.23, 0.1, 0.85) and the round peg (cylinder, radius 0.02, half height 0.1) at (0.23, -0.1, 0.85); nuts start at x in [-0.115, -0.11], y in [0.11, 0.225] (square) /
+#: [-0.225, -0.11] (round), any yaw, dropped from 2 cm.  The round peg is a CAPSULE of the same radius and height here (no cylinder narrow phase; same side
+#: surface).  The nut meshes' collision boxes (round-nut.xml / square-nut.xml) are NOT recalled: the round nut is an octagonal ring of eight boxes (inner apothem
+#: `ring_in`, radial half thickness `ring_t`) 4 cm high with a handle bar reaching out to `handle_out` along +x, the LAST geom (robosuite's reach reward aims at the
+#: nut's last geom).  Density 100, friction (0.95, 0.3, 0.1), solref (0.001, 1), solimp (0.998, 0.998, 0.001) as in robosuite's object XMLs.
+NUT_TABLE_FULL, NUT_TABLE_Z = (0.45, 0.69, 0.05), 0.82
+NUT_PEGS = {"Square": (0.23, 0.1), "Round": (0.23, -0.1)}
+NUT_PLACE = {"Square": dict(x=(-0.115, -0.11), y=(0.11, 0.225)), "Round": dict(x=(-0.115, -0.11), y=(-0.225, -0.11))}
+ROUND_NUT = dict(ring_in=0.028, ring_t=0.0075, half_h=0.02, handle_out=0.09, handle_half_w=0.01)
+
+
+def pegs_arena(friction=(1, 0.005, 0.0001)) -> str:
+    hx, hy, hz = NUT_TABLE_FULL[0] / 2, NUT_TABLE_FULL[1] / 2, NUT_TABLE_FULL[2] / 2
+    col = f'friction="{_f(friction)}" {WORLD_COL}'
+    (sx, sy), (rx, ry) = NUT_PEGS["Square"], NUT_PEGS["Round"]
+    return (f'<geom name="floor" type="plane" pos="0 0 0" size="3 3 0.125" {WORLD_COL}/>'
+            f'<body name="table" pos="0 0 {NUT_TABLE_Z - hz}"><geom name="table_collision" type="box" size="{hx} {hy} {hz}" {col}/></body>'
+            f'<body name="peg1" pos="{sx} {sy} 0.85"><geom name="peg1_col" type="box" size="0.016 0.016 0.1" {col}/></body>'
+            f'<body name="peg2" pos="{rx} {ry} 0.85"><geom name="peg2_col" type="capsule" fromto="0 0 -0.1 0 0 0.08" size="0.02" {col}/></body>')
+
+
+def round_nut(name, pos) -> str:
+    N = ROUND_NUT
+    a_in, t, hh = N["ring_in"], N["ring_t"], N["half_h"]
+    a_out = a_in + 2 * t
+    col = f'density="100" friction="0.95 0.3 0.1" solref="0.001 1" solimp="0.998 0.998 0.001" {WORLD_COL}'
+    g = ""
+    for k in range(8):
+        a = 2 * PI * k / 8
+        g += (f'<geom name="{name}_ring{k}" type="box" pos="{(a_in + t) * np.cos(a):.8g} {(a_in + t) * np.sin(a):.8g} 0" '
+              f'quat="{np.cos(a / 2):.8g} 0 0 {np.sin(a / 2):.8g}" size="{t} {a_out * np.tan(PI / 8):.8g} {hh}" {col}/>')
+    hl = (N["handle_out"] - a_out) / 2
+    g += f'<geom name="{name}_handle" type="box" pos="{a_out + hl} 0 0" size="{hl} {N["handle_half_w"]} {hh}" {col}/>'
+    return f'<body name="{name}" pos="{_f(pos)}"><freejoint name="{name}_joint"/>{g}</body>'
+
+
 def scene(world: str, actuators: str, extra: str = "") -> str:
     return f'<mujoco model="rsb">{BASE_OPTION}<worldbody>{world}</worldbody><actuator>{actuators}</actuator>{extra}</mujoco>'

@@ -15,11 +15,11 @@ from . import assets as A
 from .mjcf import Model, compile_mjcf
 
 TASK_IDS = {"Lift": 0, "Door": 1, "Stack": 2, "TwoArmLift": 3, "PickPlaceMilk": 4, "PickPlaceBread": 4, "PickPlaceCereal": 4, "PickPlaceCan": 4,
-            "TwoArmPegInHole": 5}
+            "TwoArmPegInHole": 5, "NutAssemblyRound": 6}
 CTRL_IDS = {"OSC_POSE": 0, "OSC_POSITION": 1, "JOINT_VELOCITY": 2, "JOINT_TORQUE": 3}
 
 OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89, "PickPlaceMilk": 46, "PickPlaceBread": 46, "PickPlaceCereal": 46, "PickPlaceCan": 46,
-            "TwoArmPegInHole": 73}
+            "TwoArmPegInHole": 73, "NutAssemblyRound": 46}
 #: default bounds of the per-env contact list / constraint-row list (shared-memory sizing; rsb_create ncon_max / nefc_max).
 #: Maxima seen over 300 random-action control steps x 2048 envs (tools/limits_stats.py): Stack 16 contacts / 54 rows, TwoArmLift 9 / 31,
 #: Door 4 / 18, Lift 9 / 29; TwoArmLift (24, 80) keeps 2.5x headroom and lets 14 envs share an SM (4096 envs = 2 waves instead of 3).
@@ -31,6 +31,7 @@ OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89, "PickPlaceMil
 #: committed Lift-Panda policy exceeds these limits in 1.4e-4 of its env-steps (pads + table + hand on the cube) --
 #: `suite.make(..., ncon_max=24, nefc_max=80)` removes that at the price of a second wave at 4096 envs per GPU.
 LIMITS = {"Lift": (18, 62), ("Lift", "Sawyer"): (24, 80), "Door": (16, 64), "Stack": (24, 96), "TwoArmLift": (24, 80),
+          "NutAssemblyRound": (56, 184),       # nine boxes resting on the table: 36 contacts / 110 rows before the gripper touches anything; random actions, 256 envs x 500 steps: 45 / 141
           "TwoArmPegInHole": (8, 40),          # committed policies and random actions on the CPU oracle: at most 3 contacts (peg on the rim of the hole) / 11 rows
           # PickPlace on the CPU oracle.  Committed policies (16 episodes each): Panda reaches 13 contacts / 49 rows while carrying the object, Sawyer 18 / 64.
           # Random actions (768 envs x 500 steps): Panda 14 / 46, Sawyer 21 / 74 (the Rethink gripper's box fingers flat on the bin floor against a wall).
@@ -322,6 +323,35 @@ def _pick_place(kind):
     return build
 
 
+def _nut_assembly_round(robots, env_configuration):
+    """NutAssemblyRound = NutAssembly(single_object_mode=2, nut_type="round"): the round nut starts on the table beside the robot and goes over the round peg.
+    The square nut, which robosuite parks away from the scene in this mode, is not modelled (its peg is: the arm can run into it)."""
+    assert len(robots) == 1, "NutAssembly takes one robot"
+    R = A.ROBOTS[robots[0]]
+    body, act = R["body"]("robot0_", (-0.16 - A.NUT_TABLE_FULL[0] / 2, 0.0, A.ROBOT_BASE_Z)), R["act"]("robot0_")
+    hh = A.ROUND_NUT["half_h"]
+    world = A.pegs_arena() + body + A.round_nut("RoundNut", [-0.1125, -0.17, A.NUT_TABLE_Z + hh])
+    xml = A.scene(world, act)
+
+    def objs(m: Model):
+        o = _empty_objs()
+        j = m.id("joint", "RoundNut_joint")
+        o["obj_body"][0] = m.id("body", "RoundNut")
+        o["obj_geom"][0], o["obj_geom"][1] = m.id("geom", "RoundNut_ring0"), m.id("geom", "RoundNut_handle")
+        assert o["obj_geom"][1] - o["obj_geom"][0] == 8                     # contiguous geom ids: the grasp check tests a range
+        o["obj_qposadr"][0], o["obj_dofadr"][0] = int(m.jnt_qposadr[j]), int(m.jnt_dofadr[j])
+        o["obj_half"][0] = [A.ROUND_NUT["handle_out"], A.ROUND_NUT["ring_in"] + 2 * A.ROUND_NUT["ring_t"], hh]
+        P = A.NUT_PLACE["Round"]
+        o["place_x"][0], o["place_y"][0], o["place_yaw"][0] = list(P["x"]), list(P["y"]), [0.0, 2 * np.pi]
+        o["place_z"][0] = A.NUT_TABLE_Z + hh + 0.02
+        o["place_ref"] = np.array([0.0, 0.0, A.NUT_TABLE_Z])
+        px, py = A.NUT_PEGS["Round"]
+        o["task_par"] = [px, py, A.NUT_TABLE_Z, A.NUT_TABLE_Z - A.NUT_TABLE_FULL[2] / 2 + 0.2]       # lift target: the table BODY's z (its centre) + 0.2
+        return o
+
+    return xml, objs
+
+
 def _two_arm_peg_in_hole(robots, env_configuration):
     """TwoArmPegInHole, `single-arm-opposed`: two gripper-less arms facing each other over an empty floor; robot 0 holds the peg, robot 1 the plate with the hole
     (both rigidly attached to the hands: no free bodies, nothing to place at reset)."""
@@ -348,5 +378,5 @@ def _two_arm_peg_in_hole(robots, env_configuration):
     return xml, objs
 
 
-_BUILDERS: Dict[str, callable] = {"Lift": _lift, "Stack": _stack, "Door": _door, "TwoArmLift": _two_arm_lift, "TwoArmPegInHole": _two_arm_peg_in_hole,
+_BUILDERS: Dict[str, callable] = {"Lift": _lift, "Stack": _stack, "Door": _door, "TwoArmLift": _two_arm_lift, "TwoArmPegInHole": _two_arm_peg_in_hole, "NutAssemblyRound": _nut_assembly_round,
                                   **{"PickPlace" + k: _pick_place(k) for k in A.PICK_OBJECTS}}

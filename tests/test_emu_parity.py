@@ -11,7 +11,7 @@ from tests.emu.emu import EmuEnv
 CONFIGS = [("Lift", ["Panda"], "OSC_POSE", 42, 7), ("Lift", ["Panda"], "JOINT_VELOCITY", 42, 8), ("Lift", ["Sawyer"], "OSC_POSITION", 42, 4),
            ("Door", ["Panda"], "JOINT_VELOCITY", 46, 8), ("Stack", ["Sawyer"], "OSC_POSE", 55, 7), ("TwoArmLift", ["Panda", "Panda"], "OSC_POSE", 89, 14),
            ("PickPlaceCan", ["Panda"], "OSC_POSE", 46, 7), ("PickPlaceMilk", ["Sawyer"], "OSC_POSE", 46, 7),
-           ("TwoArmPegInHole", ["Panda", "Sawyer"], "OSC_POSE", 73, 12)]
+           ("TwoArmPegInHole", ["Panda", "Sawyer"], "OSC_POSE", 73, 12), ("NutAssemblyRound", ["Panda"], "OSC_POSE", 46, 7)]
 
 
 @pytest.mark.parametrize("env_name,robots,ctrl,obs_dim,act_dim", CONFIGS)
@@ -35,7 +35,7 @@ def test_control_step_matches_oracle(env_name, robots, ctrl, obs_dim, act_dim, l
         assert np.abs(o1 - o2).max() <= 1e-4 and abs(r1 - r2) <= 1e-5
 
 
-@pytest.mark.parametrize("env_name,robots,ctrl,obs_dim,act_dim", [c for c in CONFIGS if c[0] in ("Lift", "Door", "PickPlaceCan", "PickPlaceMilk", "TwoArmPegInHole")])
+@pytest.mark.parametrize("env_name,robots,ctrl,obs_dim,act_dim", [c for c in CONFIGS if c[0] in ("Lift", "Door", "PickPlaceCan", "PickPlaceMilk", "TwoArmPegInHole", "NutAssemblyRound")])
 def test_control_step_matches_oracle_16_lane_groups(env_name, robots, ctrl, obs_dim, act_dim):
     """Models with nv <= 16 run as 16-lane groups (two envs per warp) on the GPU (csrc/rsb_cuda.cu): the same check on the device code compiled for 16 lanes."""
     test_control_step_matches_oracle(env_name, robots, ctrl, obs_dim, act_dim, lanes=16)
@@ -126,3 +126,39 @@ def test_joint_velocity_laws(law):
         o2, r2, _ = emu.step(a)
         # both sides run free (no re-synchronisation): the PID law's gains (3 x the actuator range = 522 N m s/rad on joints 1-4) amplify fp32 round-off of the velocities
         assert np.abs(o1 - o2).max() <= (2e-4 if law == "kv" else 5e-3) and abs(r1 - r2) <= 1e-5, (k, np.abs(o1 - o2).max())
+
+
+NEW_FAMILIES = [("PickPlaceCan", ["Panda"]), ("PickPlaceMilk", ["Sawyer"]), ("PickPlaceCan", ["Sawyer"]), ("PickPlaceMilk", ["Panda"]), ("TwoArmPegInHole", ["Panda", "Panda"]),
+                ("TwoArmPegInHole", ["Panda", "Sawyer"]), ("TwoArmPegInHole", ["Sawyer", "Sawyer"]), ("NutAssemblyRound", ["Panda"]), ("NutAssemblyRound", ["Sawyer"])]
+
+
+@pytest.mark.parametrize("env_name,robots", NEW_FAMILIES)
+def test_emulator_twin_of_the_gpu_one_control_step_test(env_name, robots):
+    """tests/test_gpu_parity.py::test_other_config_families_one_control_step (which tests/test_gpu_zz_pickplace.py runs for the families added last) with the
+    emulator standing where the CUDA library stands: same seed, same six environments 0 .. 5 control steps into their episodes, same assertions -- contact-pair
+    lists bit-exact and torques 1e-5 relative after the first substep, 1e-4 on qpos / qvel / observation and 1e-5 on the reward after the control step."""
+    m, t = build_task(env_name, robots, load_controller_config(default_controller="OSC_POSE"), ignore_done=True)
+    nc, ne = t["ncon_max"], t["nefc_max"]
+    for i in range(6):
+        orc, emu = OracleEnv(m, t, ncon_max=nc, nefc_max=ne), EmuEnv(m, t, nc, ne, lanes=16 if m.nv <= 16 else 32)
+        o = orc.reset(seed=83, env_id=i, episode=0)
+        assert np.abs(o - emu.reset(seed=83, env_id=i, episode=0)).max() < 2e-6
+        for k in range(i):
+            orc.step(orc.random_action(83, i, k))
+        qpos, qvel, warm, cs = orc.get_state()
+        a = orc.random_action(83, i, i)
+        emu.set_state(qpos, qvel, warm, cs, timestep=i, episode=1, bpose=orc.get_bpose())
+        d = emu.debug_substep(a, True)
+        orc.substep(a, True)
+        assert orc.get("contact_geoms").reshape(-1, 2).astype(int).tolist() == d["contact_geoms"].tolist()
+        tau = orc.get("torques")[:7 * len(robots)]
+        assert np.abs(tau - d["torques"][:7 * len(robots)]).max() <= 1e-5 * max(1.0, np.abs(tau).max())
+        orc.set_state(qpos, qvel, warm, cs); orc.set_timestep(i)
+        emu.set_state(qpos, qvel, warm, cs, timestep=i, episode=1, bpose=orc.get_bpose())
+        o1, r1, _ = orc.step(a)
+        o2, r2, _ = emu.step(a)
+        qp1, qv1, _, _ = orc.get_state()
+        qp2, qv2, _, _ = emu.get_state()
+        assert np.abs(qp1 - qp2).max() <= 1e-4 and np.abs(qv1 - qv2).max() <= 1e-4, (i, np.abs(qv1 - qv2).max())
+        assert np.abs(o1 - o2).max() <= 1e-4 and abs(r1 - r2) <= 1e-5
+    assert emu.counters() == (0, 0, 0)

@@ -1,4 +1,4 @@
-"""PickPlace (single-object mode: runs/PickPlace{Can,Milk}-{Panda,Sawyer}-OSC-POSE-*) and TwoArmPegInHole (runs/TwoArmPegInHole-*-OSC-POSE-*) on the CUDA kernels, through the C-ABI: the checks of tests/test_pickplace.py
+"""PickPlace (single-object mode: runs/PickPlace{Can,Milk}-{Panda,Sawyer}-OSC-POSE-*) TwoArmPegInHole (runs/TwoArmPegInHole-*-OSC-POSE-*) and NutAssemblyRound (runs/NutAssemblyRound-*-OSC-POSE-*) on the CUDA kernels, through the C-ABI: the checks of tests/test_pickplace.py
 and of the other families' GPU tests, on the real kernels.  The file sorts after the other GPU tests on purpose: these families were added last."""
 import json
 import os
@@ -20,7 +20,8 @@ def torch_cuda():
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 FAMILIES = [("PickPlaceCan", ["Panda"], "OSC_POSE"), ("PickPlaceMilk", ["Sawyer"], "OSC_POSE"), ("PickPlaceCan", ["Sawyer"], "OSC_POSE"), ("PickPlaceMilk", ["Panda"], "OSC_POSE"),
-            ("TwoArmPegInHole", ["Panda", "Panda"], "OSC_POSE"), ("TwoArmPegInHole", ["Panda", "Sawyer"], "OSC_POSE"), ("TwoArmPegInHole", ["Sawyer", "Sawyer"], "OSC_POSE")]
+            ("TwoArmPegInHole", ["Panda", "Panda"], "OSC_POSE"), ("TwoArmPegInHole", ["Panda", "Sawyer"], "OSC_POSE"), ("TwoArmPegInHole", ["Sawyer", "Sawyer"], "OSC_POSE"),
+            ("NutAssemblyRound", ["Panda"], "OSC_POSE"), ("NutAssemblyRound", ["Sawyer"], "OSC_POSE")]
 
 
 @pytest.mark.parametrize("env_name,robots,ctrl", FAMILIES)
