@@ -451,7 +451,7 @@ def empty_arena() -> str:
 NUT_TABLE_FULL, NUT_TABLE_Z = (0.45, 0.69, 0.05), 0.82
 NUT_PEGS = {"Square": (0.23, 0.1), "Round": (0.23, -0.1)}
 NUT_PLACE = {"Square": dict(x=(-0.115, -0.11), y=(0.11, 0.225)), "Round": dict(x=(-0.115, -0.11), y=(-0.225, -0.11))}
-ROUND_NUT = dict(ring_in=0.028, ring_t=0.0075, half_h=0.02, handle_out=0.09, handle_half_w=0.01)
+ROUND_NUT = dict(ring_in=0.028, ring_t=0.0075, half_h=0.02, handle_out=0.09, handle_half_w=0.01, handle_dir=0.0)      # handle_dir: direction of the handle bar in the nut frame (degrees from +x)
 
 
 def pegs_arena(friction=(1, 0.005, 0.0001)) -> str:
@@ -475,7 +475,9 @@ def round_nut(name, pos) -> str:
         g += (f'<geom name="{name}_ring{k}" type="box" pos="{(a_in + t) * np.cos(a):.8g} {(a_in + t) * np.sin(a):.8g} 0" '
               f'quat="{np.cos(a / 2):.8g} 0 0 {np.sin(a / 2):.8g}" size="{t} {a_out * np.tan(PI / 8):.8g} {hh}" {col}/>')
     hl = (N["handle_out"] - a_out) / 2
-    g += f'<geom name="{name}_handle" type="box" pos="{a_out + hl} 0 0" size="{hl} {N["handle_half_w"]} {hh}" {col}/>'
+    hd = np.deg2rad(N["handle_dir"])
+    g += (f'<geom name="{name}_handle" type="box" pos="{(a_out + hl) * np.cos(hd):.8g} {(a_out + hl) * np.sin(hd):.8g} 0" quat="{np.cos(hd / 2):.8g} 0 0 {np.sin(hd / 2):.8g}" '
+          f'size="{hl} {N["handle_half_w"]} {hh}" {col}/>')
     return f'<body name="{name}" pos="{_f(pos)}"><freejoint name="{name}_joint"/>{g}</body>'
 
 
