@@ -16,15 +16,17 @@ from .backend import BatchSim
 from .controllers import load_controller_config, validate
 from .model.tasks import TASK_IDS, build_task
 
-ROBOT_STATE_DIM = 32
+ROBOT_STATE_DIM = 32        # sin q, cos q, qd (3 x 7), eef_pos (3), eef_quat (4), and 2 x 2 gripper joint values with the two-finger grippers
 
 
 def _obs_slices(task):
-    """name -> slice into the flat observation row (robosuite v1.0 order: robot blocks, then object-state)."""
+    """name -> slice into the flat observation row (robosuite v1.0 order: robot blocks, then object-state).  A robot without a gripper (TwoArmPegInHole) has a
+    28-wide block: the width follows the robot's gripper dofs, as in rsb_dev.h obs_element."""
     sl, o = OrderedDict(), 0
     for i in range(task["nrobot"]):
-        sl[f"robot{i}_robot-state"] = slice(o, o + ROBOT_STATE_DIM)
-        o += ROBOT_STATE_DIM
+        w = 28 + 2 * int(task["robot"][i]["grip_ndof"])
+        sl[f"robot{i}_robot-state"] = slice(o, o + w)
+        o += w
     sl["object-state"] = slice(o, task["obs_dim"])
     return sl
 
@@ -39,6 +41,9 @@ class _EnvBase:
             raise NotImplementedError("rendering / camera observations are outside the batched hot path")
         if not use_object_obs:
             raise NotImplementedError("use_object_obs=False is not supported")
+        from .model.tasks import GRIPPERS
+        if gripper_types not in ("default", GRIPPERS.get(env_name, "default")):
+            raise NotImplementedError(f"gripper_types={gripper_types!r} is not supported for {env_name} (the task's own default gripper only)")
         for k, v in unsupported.items():
             if k in ("render_camera", "render_collision_mesh", "render_visual_mesh", "camera_names", "camera_heights",
                      "camera_widths", "camera_depths", "placement_initializer", "use_indicator_object", "prehensile") and not v:

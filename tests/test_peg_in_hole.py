@@ -114,3 +114,20 @@ def test_committed_policy_inserts_the_peg_and_device_code_follows_it():
         ret += r; best = max(best, r)
     assert ret > 330.0 and best > 0.9 and ret < 1.02 * logged.max(), (ret, best, logged[-50:].mean())
     assert emu.counters() == (0, 0, 0)
+
+
+def test_observation_slices_follow_the_gripper_dofs():
+    """Host side of the obs-dict contract (environments._obs_slices, what GymWrapper(keys=...) and the single-env OrderedDict use): a gripper-less robot's
+    robot-state block is 28 wide, not 32, and the blocks tile the row exactly for every implemented family."""
+    from robosuite_benchmark_b200.environments import _obs_slices
+    from robosuite_benchmark_b200.model.tasks import _BUILDERS
+    two_arm = ("TwoArmLift", "TwoArmPegInHole")
+    for env_name in _BUILDERS:
+        robots = ["Panda", "Sawyer"] if env_name in two_arm else ["Sawyer"]
+        m, t = build_task(env_name, robots, load_controller_config(default_controller="OSC_POSE"))
+        sl = _obs_slices(t)
+        edges = [(v.start, v.stop) for v in sl.values()]
+        assert edges[0][0] == 0 and edges[-1][1] == t["obs_dim"] and all(a[1] == b[0] for a, b in zip(edges, edges[1:])), (env_name, edges)
+        assert list(sl)[-1] == "object-state" and len(sl) == len(robots) + 1
+        width = 28 if env_name == "TwoArmPegInHole" else 32
+        assert all(v.stop - v.start == width for k, v in sl.items() if k != "object-state")
