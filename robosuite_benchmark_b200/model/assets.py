@@ -415,7 +415,7 @@ def pick_object(kind: str, pos) -> str:
 #: plus the success tolerance d < 0.06.  The peg is a capsule of the same radius and overall length (the kernels have no cylinder narrow phase; the side surface,
 #: which is what meets the hole's rim, is the same).  |y| of the bases: base_xpos_offset["empty"] = (-0.6, 0, 0) turned by +-90 degrees.
 PEG_IN_HOLE = dict(peg_radius=0.0225, peg_half_length=0.13, peg_pos=(0, 0, 0.15), hole_pos=(0.11, 0, 0.17), hole_quat=(0, 0, 0.7071068, 0.7071068),
-                   hole_center=0.1, hole_half=0.06, plate_half=0.1, plate_thickness=0.01, base_y=0.6, plate_density=500)
+                   hole_center=0.1, hole_half=0.06, plate_half=0.1, plate_thickness=0.01, base_y=0.6, plate_density=500, collide=True)
 
 
 def peg_payload(name="peg") -> str:
@@ -428,7 +428,7 @@ def peg_payload(name="peg") -> str:
 def hole_payload(name="hole") -> str:
     P = PEG_IN_HOLE
     c, h, w, t = P["hole_center"], P["hole_half"], P["plate_half"], P["plate_thickness"]
-    col = f'density="{P["plate_density"]}" friction="1 0.005 0.0001" {WORLD_COL}'
+    col = f'density="{P["plate_density"]}" friction="1 0.005 0.0001" {WORLD_COL if P["collide"] else NO_COL}'
     bar = (w - h) / 2                                   # half width of the frame's bars
     g = (f'<geom name="{name}_xp" type="box" pos="{c + h + bar} 0 0" size="{bar} {w} {t}" {col}/>'
          f'<geom name="{name}_xn" type="box" pos="{c - h - bar} 0 0" size="{bar} {w} {t}" {col}/>'
