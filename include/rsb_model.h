@@ -25,7 +25,8 @@ enum { RSB_TASK_LIFT = 0, RSB_TASK_DOOR = 1, RSB_TASK_STACK = 2, RSB_TASK_TWOARM
        RSB_TASK_PEGINHOLE = 5,     /* TwoArmPegInHole: peg on robot 0's hand, plate with a hole on robot 1's hand */
        RSB_TASK_NUTASSEMBLY = 6 }; /* NutAssembly in single-object mode (NutAssemblyRound / NutAssemblySquare): one nut, table -> its peg */
 enum { RSB_CTRL_OSC_POSE = 0, RSB_CTRL_OSC_POSITION = 1, RSB_CTRL_JOINT_VELOCITY = 2,
-       RSB_CTRL_JOINT_TORQUE = 3 };
+       RSB_CTRL_JOINT_TORQUE = 3,
+       RSB_CTRL_JOINT_POSITION = 4 };   /* goal = q + scaled action at the policy step; torque = M_arm (kp (goal - q) - kd qd) + bias (kp, kd: 7 used) */
 
 /* OSC_POSE goal orientation from the scaled rotation action d (3-vector):
    EULER_T    : goal = euler2mat(d)^T R_ee, euler2mat as in mujoco-py / robosuite transform_utils (first order: rotation by -d).  This is the convention the

@@ -906,6 +906,8 @@ static void controller_set_goal(orc_env *e, int ri, const real *action) {
       if (rb->has_velocity_limits) { if (v < rb->velocity_limit_lo[k]) v = rb->velocity_limit_lo[k]; if (v > rb->velocity_limit_hi[k]) v = rb->velocity_limit_hi[k]; }
       c->goal_vel[k] = v;
     }
+  } else if (rb->ctrl_type == RSB_CTRL_JOINT_POSITION) {      /* robosuite JointPositionController.set_goal: goal_qpos = joint_pos + scaled delta (kept in goal_vel) */
+    for (int k = 0; k < 7; k++) c->goal_vel[k] = e->qpos[rb->arm_qposadr[k]] + scale_action(rb, k, action[k]);
   } else { for (int k = 0; k < 7; k++) c->goal_vel[k] = scale_action(rb, k, action[k]); }   /* JOINT_TORQUE: goal torque */
 }
 
@@ -959,6 +961,12 @@ static void controller_run(orc_env *e, int ri) {
       if (tau[k] != raw[k]) sat = 1;
     }
     c->saturated = sat;
+  } else if (rb->ctrl_type == RSB_CTRL_JOINT_POSITION) {
+    /* robosuite v1.0 JointPositionController.run_controller: desired = kp (goal_qpos - q) + kd (-qd); torques = mass_matrix . desired + torque_compensation,
+       mass_matrix = the arm's block of the joint-space inertia */
+    real des[7];
+    for (int k = 0; k < 7; k++) des[k] = rb->kp[k] * (c->goal_vel[k] - e->qpos[rb->arm_qposadr[k]]) - rb->kd[k] * e->qvel[rb->arm_dofadr[k]];
+    for (int k = 0; k < 7; k++) { real t = e->qfrc_bias[rb->arm_dofadr[k]]; for (int j = 0; j < 7; j++) t += e->M[rb->arm_dofadr[k] * e->m.nv + rb->arm_dofadr[j]] * des[j]; tau[k] = t; }
   } else {
     for (int k = 0; k < 7; k++) tau[k] = c->goal_vel[k] + e->qfrc_bias[rb->arm_dofadr[k]];
   }

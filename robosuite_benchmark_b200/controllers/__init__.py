@@ -36,8 +36,13 @@ _JOINT_TORQUE = {
     "type": "JOINT_TORQUE", "input_max": 1, "input_min": -1, "output_max": 0.1, "output_min": -0.1,
     "torque_limits": None, "interpolation": None, "ramp_ratio": 0.2,
 }
+_JOINT_POSITION = {
+    # robosuite v1.0 controllers/config/joint_position.json: goal_qpos = q + action * 0.05 at every policy step, torque = M (kp (goal - q) - kd qd) + compensation
+    "type": "JOINT_POSITION", "input_max": 1, "input_min": -1, "output_max": 0.05, "output_min": -0.05, "kp": 50, "damping_ratio": 1,
+    "impedance_mode": "fixed", "kp_limits": [0, 300], "damping_ratio_limits": [0, 10], "qpos_limits": None, "interpolation": None, "ramp_ratio": 0.2,
+}
 _DEFAULTS = {"OSC_POSE": _OSC_POSE, "OSC_POSITION": _OSC_POSITION, "JOINT_VELOCITY": _JOINT_VELOCITY,
-             "JOINT_TORQUE": _JOINT_TORQUE}
+             "JOINT_TORQUE": _JOINT_TORQUE, "JOINT_POSITION": _JOINT_POSITION}
 
 #: controllers with a batched CUDA implementation (the others are named by robosuite but not on this path)
 SUPPORTED_CONTROLLERS = tuple(_DEFAULTS)
@@ -72,7 +77,7 @@ def validate(cfg: dict) -> None:
         raise NotImplementedError("controller interpolation is not supported on the batched path")
     if cfg.get("impedance_mode", "fixed") != "fixed":
         raise NotImplementedError("only impedance_mode='fixed' is supported")
-    for k in ("position_limits", "orientation_limits"):
+    for k in ("position_limits", "orientation_limits", "qpos_limits"):
         if cfg.get(k) is not None:
             raise NotImplementedError(f"{k} is not supported on the batched path")
     if cfg.get("control_delta", True) is not True:

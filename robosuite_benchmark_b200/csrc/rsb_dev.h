@@ -986,6 +986,9 @@ RSB_DN void ctrl_set_goal(int so, Grp g) { real *s = RSB_SMEM + so;
       for (int k = 0; k < 3; k++) cs[CS_GOALPOS + k] = sxpos[3 * rb.eef_site + k] + d[k];
     } else if (rb.ctrl_type == RSB_CTRL_JOINT_VELOCITY) {
       for (int k = 0; k < RSB_ARM_DOF; k++) { real v = scale_action(rb, k, a[k]); if (rb.has_vl) v = clampf(v, rb.vl_lo[k], rb.vl_hi[k]); cs[CS_GOALVEL + k] = v; }
+    } else if (rb.ctrl_type == RSB_CTRL_JOINT_POSITION) {        /* robosuite JointPositionController.set_goal: goal_qpos = joint_pos + scaled delta (held in the goal-velocity slot) */
+      const real *qpos = s + MDL.o_qpos;
+      for (int k = 0; k < RSB_ARM_DOF; k++) cs[CS_GOALVEL + k] = qpos[rb.arm_qadr[k]] + scale_action(rb, k, a[k]);
     } else { for (int k = 0; k < RSB_ARM_DOF; k++) cs[CS_GOALVEL + k] = scale_action(rb, k, a[k]); }
   }
   gsync(g);
@@ -1013,6 +1016,18 @@ RSB_D void sym3_solve(const real *A, int ld, const real *b, real *x) {
 }
 
 /* scratch layout for the OSC law (floats, in o_cscr): Jee[42] Lm[49] X[42] A[36](ld 6) F[6] pose[7] y[6] w[6] v6[6] tau[7] */
+/* robosuite JointPositionController.run_controller for robot ri: torques = M_arm (kp (goal_qpos - q) - kd qd) + torque_compensation.  Its own function so that
+   the operational-space law's register allocation in ctrl_run does not change. */
+RSB_DN void ctrl_run_jpos(int so, Grp g, int ri) { real *s = RSB_SMEM + so;
+  const DevRobot &rb = MDL.robot[ri]; const real *cs = s + MDL.o_cs + ri * MDL.cs_words, *qpos = s + MDL.o_qpos, *qvel = s + MDL.o_qvel, *M = s + MDL.o_M, *bias = s + MDL.o_bias;
+  real *tau = s + MDL.o_cscr + 200;                    /* ctrl_run's raw-torque slot: its common tail clamps, writes ctrl and keeps the torques */
+  if (g.lane < RSB_ARM_DOF) {
+    const int c = g.lane; real t = bias[rb.arm_dadr[c]];
+    for (int k = 0; k < RSB_ARM_DOF; k++) t += msym(M, rb.arm_dadr[c], rb.arm_dadr[k]) * (rb.kp[k] * (cs[CS_GOALVEL + k] - qpos[rb.arm_qadr[k]]) - rb.kd[k] * qvel[rb.arm_dadr[k]]);
+    tau[c] = t;
+  }
+}
+
 RSB_DN void ctrl_run(int so, Grp g) { real *s = RSB_SMEM + so;
   const real *qpos = s + MDL.o_qpos, *qvel = s + MDL.o_qvel, *cdof = s + MDL.o_cdof, *M = s + MDL.o_M, *bias = s + MDL.o_bias;
   const real *sxpos = s + MDL.o_sxpos, *sxmat = s + MDL.o_sxmat, *xpos = s + MDL.o_xpos, *cvel = s + MDL.o_cvel;
@@ -1082,6 +1097,8 @@ RSB_DN void ctrl_run(int so, Grp g) { real *s = RSB_SMEM + so;
       sat = gsum_i(g, sat);
       gsync(g);
       if (g.lane == 0) { cs[CS_DERRPTR] = (real)((ptr + 1) % 5); cs[CS_DERRN] = (real)nn; cs[CS_SAT] = sat ? 1.0f : 0.0f; }
+    } else if (rb.ctrl_type == RSB_CTRL_JOINT_POSITION) {
+      ctrl_run_jpos(so, g, ri);
     } else {
       if (g.lane < RSB_ARM_DOF) tau[g.lane] = cs[CS_GOALVEL + g.lane] + bias[rb.arm_dadr[g.lane]];
     }

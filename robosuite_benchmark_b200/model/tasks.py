@@ -16,7 +16,7 @@ from .mjcf import Model, compile_mjcf
 
 TASK_IDS = {"Lift": 0, "Door": 1, "Stack": 2, "TwoArmLift": 3, "PickPlaceMilk": 4, "PickPlaceBread": 4, "PickPlaceCereal": 4, "PickPlaceCan": 4,
             "TwoArmPegInHole": 5, "NutAssemblyRound": 6}
-CTRL_IDS = {"OSC_POSE": 0, "OSC_POSITION": 1, "JOINT_VELOCITY": 2, "JOINT_TORQUE": 3}
+CTRL_IDS = {"OSC_POSE": 0, "OSC_POSITION": 1, "JOINT_VELOCITY": 2, "JOINT_TORQUE": 3, "JOINT_POSITION": 4}
 
 OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89, "PickPlaceMilk": 46, "PickPlaceBread": 46, "PickPlaceCereal": 46, "PickPlaceCan": 46,
             "TwoArmPegInHole": 73, "NutAssemblyRound": 46}
@@ -50,7 +50,7 @@ def _robot_desc(m: Model, pf: str, robot: str, cc: dict, gripper="default") -> d
     act = [m.id("actuator", f"{pf}torq_j{i + 1}") for i in range(7)]
     gact = [m.id("actuator", f"{pf}gripper_finger_joint{i + 1}") for i in range(ng)]
     ctype = cc["type"]
-    ndim = {"OSC_POSE": 6, "OSC_POSITION": 3, "JOINT_VELOCITY": 7, "JOINT_TORQUE": 7}[ctype]
+    ndim = {"OSC_POSE": 6, "OSC_POSITION": 3, "JOINT_VELOCITY": 7, "JOINT_TORQUE": 7, "JOINT_POSITION": 7}[ctype]
 
     def vec(x, n, fill=0.0):
         v = np.full(7, fill, float)
@@ -65,6 +65,9 @@ def _robot_desc(m: Model, pf: str, robot: str, cc: dict, gripper="default") -> d
         kp = vec(cc.get("kp", 150.0), 6)
         damping = vec(cc.get("damping_ratio", cc.get("damping", 1.0)), 6)
         kd = 2.0 * np.sqrt(kp) * damping
+    elif ctype == "JOINT_POSITION":                            # per-joint kp, kd = 2 sqrt(kp) damping_ratio (robosuite JointPositionController)
+        kp = vec(cc.get("kp", 50.0), 7)
+        kd = 2.0 * np.sqrt(kp) * vec(cc.get("damping_ratio", 1.0), 7)
     elif ctype == "JOINT_VELOCITY" and "kv" in cc:             # robosuite v1.0: pure proportional law with gain kv (controllers/__init__.py)
         if "kp" in cc:
             raise ValueError('JOINT_VELOCITY config holds both "kv" (v1.0 P law) and "kp" (>= 1.1 PID law): give one')

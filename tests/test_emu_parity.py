@@ -9,6 +9,7 @@ from robosuite_benchmark_b200.model.tasks import build_task
 from tests.emu.emu import EmuEnv
 
 CONFIGS = [("Lift", ["Panda"], "OSC_POSE", 42, 7), ("Lift", ["Panda"], "JOINT_VELOCITY", 42, 8), ("Lift", ["Sawyer"], "OSC_POSITION", 42, 4),
+           ("Lift", ["Panda"], "JOINT_POSITION", 42, 8), ("Lift", ["Sawyer"], "JOINT_TORQUE", 42, 8),
            ("Door", ["Panda"], "JOINT_VELOCITY", 46, 8), ("Stack", ["Sawyer"], "OSC_POSE", 55, 7), ("TwoArmLift", ["Panda", "Panda"], "OSC_POSE", 89, 14),
            ("PickPlaceCan", ["Panda"], "OSC_POSE", 46, 7), ("PickPlaceMilk", ["Sawyer"], "OSC_POSE", 46, 7),
            ("TwoArmPegInHole", ["Panda", "Sawyer"], "OSC_POSE", 73, 12), ("NutAssemblyRound", ["Panda"], "OSC_POSE", 46, 7)]
@@ -162,3 +163,30 @@ def test_emulator_twin_of_the_gpu_one_control_step_test(env_name, robots):
         assert np.abs(qp1 - qp2).max() <= 1e-4 and np.abs(qv1 - qv2).max() <= 1e-4, (i, np.abs(qv1 - qv2).max())
         assert np.abs(o1 - o2).max() <= 1e-4 and abs(r1 - r2) <= 1e-5
     assert emu.counters() == (0, 0, 0)
+
+
+def test_joint_position_law():
+    """JOINT_POSITION (robosuite v1.0 JointPositionController, the last joint-space controller of SURVEY 8f-3): the goal is re-based on the current joint angles at
+    every policy step (goal = q + 0.05 a), the torque is M_arm (kp (goal - q) - kd qd) + compensation with kp = 50, kd = 2 sqrt(kp).  Zero actions hold the pose;
+    a constant action moves exactly the commanded joints, in the commanded direction, by less than 0.05 rad per control step; device code == oracle while running free."""
+    cfg = load_controller_config(default_controller="JOINT_POSITION")
+    assert (cfg["kp"], cfg["damping_ratio"], cfg["output_max"]) == (50, 1, 0.05)
+    with pytest.raises(NotImplementedError):
+        from robosuite_benchmark_b200.controllers import validate
+        validate(dict(cfg, qpos_limits=[[-1] * 7, [1] * 7]))
+    m, t = build_task("Lift", "Panda", cfg, ignore_done=True)
+    rb = t["robot"][0]
+    assert rb["ctrl_type"] == 4 and np.allclose(rb["kp"], 50.0) and np.allclose(rb["kd"], 2 * np.sqrt(50.0))
+    orc, emu = OracleEnv(m, t, ncon_max=t["ncon_max"], nefc_max=t["nefc_max"]), EmuEnv(m, t, t["ncon_max"], t["nefc_max"], lanes=16)
+    orc.reset(seed=3, env_id=0); emu.reset(seed=3, env_id=0)
+    q0 = orc.get_state()[0][:7].copy()
+    for _ in range(10):
+        orc.step(np.zeros(8)); emu.step(np.zeros(8))
+    assert np.abs(orc.get_state()[0][:7] - q0).max() < 1e-6
+    a = np.zeros(8); a[1], a[3] = 1.0, -0.5
+    for k in range(10):
+        o1, r1, _ = orc.step(a)
+        o2, r2, _ = emu.step(a)
+        assert np.abs(o1 - o2).max() <= 2e-4 and abs(r1 - r2) <= 1e-5, (k, np.abs(o1 - o2).max())
+    dq = orc.get_state()[0][:7] - q0
+    assert 0.02 < dq[1] < 0.5 and -0.25 < dq[3] < -0.01 and abs(dq[3] / dq[1] + 0.5) < 0.05 and np.abs(dq[[0, 2, 4, 5, 6]]).max() < 2e-3, dq
