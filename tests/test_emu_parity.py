@@ -133,12 +133,12 @@ NEW_FAMILIES = [("PickPlaceCan", ["Panda"]), ("PickPlaceMilk", ["Sawyer"]), ("Pi
                 ("TwoArmPegInHole", ["Panda", "Sawyer"]), ("TwoArmPegInHole", ["Sawyer", "Sawyer"]), ("NutAssemblyRound", ["Panda"]), ("NutAssemblyRound", ["Sawyer"])]
 
 
-@pytest.mark.parametrize("env_name,robots", NEW_FAMILIES)
-def test_emulator_twin_of_the_gpu_one_control_step_test(env_name, robots):
+@pytest.mark.parametrize("env_name,robots,ctrl", [(e, r, "OSC_POSE") for e, r in NEW_FAMILIES] + [("Lift", ["Panda"], "JOINT_POSITION"), ("Stack", ["Sawyer"], "JOINT_TORQUE")])
+def test_emulator_twin_of_the_gpu_one_control_step_test(env_name, robots, ctrl):
     """tests/test_gpu_parity.py::test_other_config_families_one_control_step (which tests/test_gpu_zz_pickplace.py runs for the families added last) with the
     emulator standing where the CUDA library stands: same seed, same six environments 0 .. 5 control steps into their episodes, same assertions -- contact-pair
     lists bit-exact and torques 1e-5 relative after the first substep, 1e-4 on qpos / qvel / observation and 1e-5 on the reward after the control step."""
-    m, t = build_task(env_name, robots, load_controller_config(default_controller="OSC_POSE"), ignore_done=True)
+    m, t = build_task(env_name, robots, load_controller_config(default_controller=ctrl), ignore_done=True)
     nc, ne = t["ncon_max"], t["nefc_max"]
     for i in range(6):
         orc, emu = OracleEnv(m, t, ncon_max=nc, nefc_max=ne), EmuEnv(m, t, nc, ne, lanes=16 if m.nv <= 16 else 32)
