@@ -168,3 +168,34 @@ def test_device_code_matches_oracle_on_policy_states():
     # same tolerances as the Lift policy-state test on the CUDA kernels (tests/test_gpu_parity.py): qpos 1e-4 everywhere, velocities 1e-4 typically and 5e-4 where
     # the gripper squeezes the object (fp32 resolution of large opposing contact forces)
     assert checked == 15 and in_contact >= 3 and grazing <= 3 and np.median(dvs) <= 1e-4, (checked, in_contact, grazing, np.sort(dvs))
+
+
+#: the reference's 29 committed run families (runs/<family>-SEED*) with the observation / action sizes of their committed networks
+RUN_FAMILIES = {
+    **{f"{e}-{r}-{c}": (o, 7 if c == "OSC-POSE" else 8) for e, o in (("Lift", 42), ("Door", 46), ("Stack", 55)) for r in ("Panda", "Sawyer") for c in ("OSC-POSE", "JOINT-VELOCITY")},
+    **{f"{e}-{r}-OSC-POSE": (46, 7) for e in ("PickPlaceCan", "PickPlaceMilk", "NutAssemblyRound") for r in ("Panda", "Sawyer")},
+    **{f"TwoArmLift-{r}-OSC-POSE": (89, 14) for r in ("PandaPanda", "SawyerSawyer")},
+    **{f"TwoArmHandoff-{r}-OSC-POSE": (86, 14) for r in ("PandaPanda", "SawyerSawyer")},
+    **{f"TwoArmPegInHole-{r}-OSC-POSE": (73, 12) for r in ("PandaPanda", "PandaSawyer", "SawyerSawyer")},
+    **{f"Wipe-{r}-{c}": (379, 6 if c == "OSC-POSE" else 7) for r in ("Panda", "Sawyer") for c in ("OSC-POSE", "JOINT-VELOCITY")},
+}
+
+
+def test_every_committed_run_family_builds_with_its_networks_dims_or_refuses_loudly():
+    """SURVEY 8f-3 coverage, family by family: 23 of the 29 committed run families compile into a task whose observation / action sizes are those of the family's
+    committed policy and Q networks; the other six (TwoArmHandoff, Wipe) raise NotImplementedError -- never a silent stand-in."""
+    assert len(RUN_FAMILIES) == 29
+    built = 0
+    for fam, (obs_dim, act_dim) in RUN_FAMILIES.items():
+        env_name, robots, ctrl = fam.split("-", 2)
+        robots = {"PandaPanda": ["Panda", "Panda"], "SawyerSawyer": ["Sawyer", "Sawyer"], "PandaSawyer": ["Panda", "Sawyer"]}.get(robots, [robots])
+        cfg = load_controller_config(default_controller=ctrl.replace("-", "_"))
+        if env_name in ("TwoArmHandoff", "Wipe"):
+            with pytest.raises(NotImplementedError):
+                build_task(env_name, robots, cfg)
+            continue
+        m, t = build_task(env_name, robots, cfg, horizon=500, control_freq=20, reward_shaping=True, ignore_done=True)
+        assert (t["obs_dim"], t["act_dim"]) == (obs_dim, act_dim), (fam, t["obs_dim"], t["act_dim"])
+        assert t["substeps"] == 25 and m.nv <= 32
+        built += 1
+    assert built == 23
