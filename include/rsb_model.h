@@ -23,7 +23,8 @@ enum { RSB_CONE_PYRAMIDAL = 0, RSB_CONE_ELLIPTIC = 1 };
 enum { RSB_TASK_LIFT = 0, RSB_TASK_DOOR = 1, RSB_TASK_STACK = 2, RSB_TASK_TWOARMLIFT = 3,
        RSB_TASK_PICKPLACE = 4,     /* PickPlace in single-object mode (PickPlaceMilk / PickPlaceCan / ...): one object, bin 1 -> its quadrant of bin 2 */
        RSB_TASK_PEGINHOLE = 5,     /* TwoArmPegInHole: peg on robot 0's hand, plate with a hole on robot 1's hand */
-       RSB_TASK_NUTASSEMBLY = 6 }; /* NutAssembly in single-object mode (NutAssemblyRound / NutAssemblySquare): one nut, table -> its peg */
+       RSB_TASK_NUTASSEMBLY = 6,   /* NutAssembly in single-object mode (NutAssemblyRound / NutAssemblySquare): one nut, table -> its peg */
+       RSB_TASK_HANDOFF = 7 };     /* TwoArmHandoff: a hammer on a narrow table beside robot 0, to be picked up and handed to robot 1 */
 enum { RSB_CTRL_OSC_POSE = 0, RSB_CTRL_OSC_POSITION = 1, RSB_CTRL_JOINT_VELOCITY = 2,
        RSB_CTRL_JOINT_TORQUE = 3,
        RSB_CTRL_JOINT_POSITION = 4 };   /* goal = q + scaled action at the policy step; torque = M_arm (kp (goal - q) - kd qd) + bias (kp, kd: 7 used) */
@@ -122,6 +123,8 @@ typedef struct rsb_task {
      TWOARMLIFT: obj_body[0]=pot, obj_site[0..1]=handle sites, obj_geom[0..1]=handle geoms
      PICKPLACE: obj_body[0]=the object, obj_geom[0]=its collision geom, obj_qposadr[0]=free joint; task_par below
      PEGINHOLE: obj_body[0]=plate with the hole, obj_body[1]=peg; task_par below
+     HANDOFF: obj_body[0]=hammer, obj_geom[0]..obj_geom[1] = its (contiguous) geoms, the FIRST being the handle, obj_qposadr[0]=free joint; the placement angle
+              (place_yaw) turns the hammer about the world y axis (robosuite: rotation_axis='y'), not z
      NUTASSEMBLY: obj_body[0]=the nut, obj_geom[0]..obj_geom[1] = its (contiguous) collision geoms, the last one being the handle, obj_qposadr[0]=free joint */
   int obj_body[RSB_MAX_OBJ], obj_geom[RSB_MAX_OBJ], obj_site[RSB_MAX_OBJ];
   int obj_qposadr[RSB_MAX_OBJ], obj_dofadr[RSB_MAX_OBJ];
@@ -137,6 +140,7 @@ typedef struct rsb_task {
      PICKPLACE: [0..1] = xy of the object's target placement in bin 2 (centre of its quadrant), [2] = bin-2 z (bin2_pos[2]),
                 [3..4] = bin_size xy (the quadrant check is |obj - target| < bin_size / 4 per axis), [5] = lift target height above bin-2 z (0.25)
      PEGINHOLE: [0] = distance of the hole's centre from the plate body's origin along the plate's x axis (0.1)
+     HANDOFF: [0] = height above the table top (table_height) that counts as lifted (0.1), [1] = half thickness of the handle (its centre minus this is the hammer's height)
      NUTASSEMBLY: [0..1] = xy of the nut's peg, [2] = table top z (on-peg: |nut - peg| < 0.03 per axis and nut z < [2] + 0.05), [3] = lift target z */
   double task_par[RSB_TASK_NPAR];
 } rsb_task;

@@ -1133,6 +1133,24 @@ static real task_reward(const orc_env *e) {
     }
     return r * t->reward_scale;
   }
+  if (t->task_id == RSB_TASK_HANDOFF) {
+    /* robosuite v1.0 TwoArmHandoff.reward with the stage values the committed runs log (x 1/2: reach <= 0.125, plateau at exactly 0.25, 0.5 .. 0.625, 1.0): hammer not
+       lifted: arm 0 grasping any hammer geom -> 0.5, else 0.25 (1 - tanh |gripper0 - handle|); lifted (handle's underside > table + 0.1): arm 1 grasping the handle ->
+       2.0 once arm 0 has let go (1.5 while both hold: this value is NOT pinned, no run logs it), else 1.0 + 0.25 (1 - tanh |gripper1 - handle|).  Sparse: 2.0 on
+       success only.  All x reward_scale / 2. */
+    const real *handle = e->geom_xpos[t->obj_geom[0]], *e0 = e->site_xpos[t->robot[0].eef_site], *e1 = e->site_xpos[t->robot[1].eef_site];
+    int g0 = check_grasp_range(e, 0, t->obj_geom[0], t->obj_geom[1]), g1 = check_grasp(e, 1, t->obj_geom[0]);
+    int lifted = handle[2] - t->task_par[1] - t->table_height > t->task_par[0];
+    real d[3];
+    if (t->reward_shaping) {
+      if (lifted) {
+        if (g1) r = g0 ? 1.5 : 2.0;
+        else { v3sub(d, handle, e1); r = 1.0 + 0.25 * (1 - tanh(v3norm(d))); }
+      } else if (g0) r = 0.5;
+      else { v3sub(d, handle, e0); r = 0.25 * (1 - tanh(v3norm(d))); }
+    } else r = (lifted && g1 && !g0) ? 2.0 : 0.0;
+    return r * t->reward_scale / 2.0;
+  }
   return 0;
 }
 
@@ -1203,6 +1221,16 @@ static void observation(const orc_env *e, real *obs) {
     put_quat_xyzw(obs + n, e->xquat[t->obj_body[1]]); n += 4;
     real tt, d, cs; peg_hole_orientation(e, &tt, &d, &cs);
     obs[n++] = cs; obs[n++] = tt; obs[n++] = d;
+  } else if (t->task_id == RSB_TASK_HANDOFF) {
+    /* hammer_pos, hammer_quat, handle_xpos, robot0 eef_xpos, robot1 eef_xpos, gripper0_to_handle, gripper1_to_handle (handle - eef) */
+    const real *hp = e->xpos[t->obj_body[0]], *handle = e->geom_xpos[t->obj_geom[0]], *e0 = e->site_xpos[t->robot[0].eef_site], *e1 = e->site_xpos[t->robot[1].eef_site];
+    for (int k = 0; k < 3; k++) obs[n++] = hp[k];
+    put_quat_xyzw(obs + n, e->xquat[t->obj_body[0]]); n += 4;
+    for (int k = 0; k < 3; k++) obs[n++] = handle[k];
+    for (int k = 0; k < 3; k++) obs[n++] = e0[k];
+    for (int k = 0; k < 3; k++) obs[n++] = e1[k];
+    for (int k = 0; k < 3; k++) obs[n++] = handle[k] - e0[k];
+    for (int k = 0; k < 3; k++) obs[n++] = handle[k] - e1[k];
   }
 }
 
@@ -1258,6 +1286,7 @@ void orc_reset(orc_env *e, uint64_t seed, uint64_t env_id, uint64_t episode) {
     real *dst = t->place_body[o] >= 0 ? e->bpose : e->qpos + qa;
     dst[0] = t->place_ref[0] + x; dst[1] = t->place_ref[1] + y; dst[2] = t->place_z[o];
     dst[3] = cos(0.5 * yaw); dst[4] = 0; dst[5] = 0; dst[6] = sin(0.5 * yaw);
+    if (t->task_id == RSB_TASK_HANDOFF) { dst[5] = dst[6]; dst[6] = 0; }        /* the hammer is turned about y (robosuite: rotation_axis='y') */
   }
   orc_forward(e);
   for (int ri = 0; ri < t->nrobot; ri++) controller_reset(e, ri);

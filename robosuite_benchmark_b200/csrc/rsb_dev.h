@@ -1607,6 +1607,19 @@ RSB_DN real task_reward(int so) { const real *s = RSB_SMEM + so;
     }
     return r * MDL.reward_scale;
   }
+  if (MDL.task_id == RSB_TASK_HANDOFF) {            /* staged handoff reward (stage values as logged by the committed runs) -- see the oracle's task_reward */
+    const real *handle = s + MDL.o_gxpos + 3 * MDL.obj_geom[0], *e1 = sxpos + 3 * MDL.robot[1].eef_site;
+    const bool g0 = check_grasp_range(so, 0, MDL.obj_geom[0], MDL.obj_geom[1]), g1 = check_grasp(so, 1, MDL.obj_geom[0]);
+    const bool lifted = handle[2] - MDL.task_par[1] - MDL.table_height > MDL.task_par[0];
+    if (MDL.reward_shaping) {
+      if (lifted) {
+        if (g1) r = g0 ? 1.5f : 2.0f;
+        else { real d[3] = {handle[0] - e1[0], handle[1] - e1[1], handle[2] - e1[2]}; r = 1.0f + 0.25f * (1 - tanhf(sqrtf(dot3(d, d)))); }
+      } else if (g0) r = 0.5f;
+      else { real d[3] = {handle[0] - eef[0], handle[1] - eef[1], handle[2] - eef[2]}; r = 0.25f * (1 - tanhf(sqrtf(dot3(d, d)))); }
+    } else r = (lifted && g1 && !g0) ? 2.0f : 0.0f;
+    return r * MDL.reward_scale * 0.5f;
+  }
   if (MDL.task_id == RSB_TASK_PEGINHOLE) {          /* success 1 + (reach, d, t, cos shaping terms), / 5 -- see the oracle's task_reward */
     real o3[3]; peg_hole_orientation(so, o3);
     if (o3[1] < 0.06f && o3[0] >= -0.12f && o3[0] <= 0.14f && o3[2] > 0.95f) r = 1.0f;
@@ -1639,6 +1652,19 @@ RSB_DN real obs_peginhole(int so, int i) { const real *s = RSB_SMEM + so;
   if (i < 10) return pp[i - 7] - hp[i - 7];
   if (i < 14) { int k = i - 10; return xquat[4 * MDL.obj_body[1] + (k == 3 ? 0 : k + 1)]; }
   real o3[3]; peg_hole_orientation(so, o3); return i == 14 ? o3[2] : (i == 15 ? o3[0] : o3[1]);
+}
+
+/* TwoArmHandoff object-state (element i of 22): hammer_pos, hammer_quat, handle_xpos, eef0, eef1, handle - eef0, handle - eef1.  Not inlined, like obs_pickplace. */
+RSB_DN real obs_handoff(int so, int i) { const real *s = RSB_SMEM + so;
+  const real *hp = s + MDL.o_xpos + 3 * MDL.obj_body[0], *handle = s + MDL.o_gxpos + 3 * MDL.obj_geom[0];
+  const real *e0 = s + MDL.o_sxpos + 3 * MDL.robot[0].eef_site, *e1 = s + MDL.o_sxpos + 3 * MDL.robot[1].eef_site;
+  if (i < 3) return hp[i];
+  if (i < 7) { int k = i - 3; return s[MDL.o_xquat + 4 * MDL.obj_body[0] + (k == 3 ? 0 : k + 1)]; }
+  if (i < 10) return handle[i - 7];
+  if (i < 13) return e0[i - 10];
+  if (i < 16) return e1[i - 13];
+  if (i < 19) return handle[i - 16] - e0[i - 16];
+  return handle[i - 19] - e1[i - 19];
 }
 
 /* A.1.4 observation vector, robosuite v1.0 order: per robot [sin q, cos q, qd, eef_pos, eef_quat(xyzw), grip q, grip qd], then object-state.
@@ -1696,6 +1722,7 @@ RSB_D real obs_element(int so, int i) { const real *s = RSB_SMEM + so;
   }
   if (MDL.task_id == RSB_TASK_PICKPLACE || MDL.task_id == RSB_TASK_NUTASSEMBLY) return obs_pickplace(so, i);
   if (MDL.task_id == RSB_TASK_PEGINHOLE) return obs_peginhole(so, i);
+  if (MDL.task_id == RSB_TASK_HANDOFF) return obs_handoff(so, i);
   return 0;
 }
 
@@ -1783,6 +1810,7 @@ RSB_D void env_reset(int so, Grp g, real *st, uint64_t seed, uint64_t env_id, re
       real *dst = MDL.place_body[o] >= 0 ? s + MDL.o_bpose : qpos + qa;
       dst[0] = MDL.place_ref[0] + x; dst[1] = MDL.place_ref[1] + y; dst[2] = MDL.place_z[o];
       dst[3] = c; dst[4] = 0; dst[5] = 0; dst[6] = sn;
+      if (MDL.task_id == RSB_TASK_HANDOFF) { dst[5] = sn; dst[6] = 0; }        /* the hammer is turned about y (robosuite: rotation_axis='y') */
     }
   }
   gsync(g);

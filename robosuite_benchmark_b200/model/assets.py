@@ -481,5 +481,32 @@ def round_nut(name, pos) -> str:
     return f'<body name="{name}" pos="{_f(pos)}"><freejoint name="{name}_joint"/>{g}</body>'
 
 
+# ----------------------------------------------------------------------------- TwoArmHandoff: narrow table and the hammer
+#: robosuite's TwoArmHandoff as recalled: table_full_size (0.8, 1.2, 0.05) of which only a quarter of the width is real -- a 0.8 x 0.3 m table at
+#: (0, -0.45) with its top at 0.8, beside robot 0; the arms face each other along y.  `base_y`: where the bases stand; 0.76 = 0.16 + 1.2 / 2 is what the committed
+#: runs' epoch-0 reward level says (reach term 0.125 (1 - tanh d0): logged 0.094-0.100 for Panda, 0.079-0.094 for Sawyer; 0.096 / 0.090 here; with 0.56 it
+#: would be 0.079).  HammerObject (generated per model upstream with random sizes: handle radius U(0.015, 0.02), length U(0.1, 0.25), density U(100, 250), friction
+#: U(3, 5), head density x 2): the MEANS here; the neck / face cylinders are boxes of the same cross-section area.  The hammer starts lying along x on the table
+#: (robosuite samples a rotation about y and lets it fall; here: a quarter turn +- `tilt`).
+HANDOFF = dict(table_full=(0.8, 0.3, 0.05), table_offset=(0.0, -0.45), base_y=0.76, handle_radius=0.0175, handle_length=0.175, handle_density=175.0, handle_friction=4.0,
+               head_density_ratio=2.0, head_half_ratio=1.1, place_x=(-0.1, 0.1), place_y=(-0.05, 0.05), tilt=0.1, lift_height=0.1, head_dir=1.0)       # head_dir: +1 head towards +x, -1 towards -x
+
+
+def hammer(name, pos) -> str:
+    H = HANDOFF
+    r, hl = H["handle_radius"], H["handle_length"] / 2
+    h = r * H["head_half_ratio"]
+    zc = hl + h
+    sq = 0.8862269                                   # side / diameter of the square with a circle's area
+    col = lambda dens, fr: f'density="{dens}" friction="{fr} 0.005 0.0001" {WORLD_COL}'
+    hd = H["handle_density"] * H["head_density_ratio"]
+    g = (f'<geom name="{name}_handle" type="box" size="{r} {r} {hl}" {col(H["handle_density"], H["handle_friction"])}/>'
+         f'<geom name="{name}_head" type="box" pos="0 0 {zc}" size="{2 * h} {h} {h}" {col(hd, 1)}/>'
+         f'<geom name="{name}_neck" type="box" pos="{2.2 * h} 0 {zc}" size="{0.2 * h} {0.8 * h * sq} {0.8 * h * sq}" {col(hd, 1)}/>'
+         f'<geom name="{name}_face" type="box" pos="{2.8 * h} 0 {zc}" size="{0.4 * h} {h * sq} {h * sq}" {col(hd, 1)}/>'
+         f'<geom name="{name}_claw" type="box" pos="{-2 * h} 0 {zc}" quat="0.9238795 0 0.3826834 0" size="{0.7072 * h} {0.95 * h} {0.7072 * h}" {col(hd, 1)}/>')
+    return f'<body name="{name}" pos="{_f(pos)}"><freejoint name="{name}_joint"/>{g}</body>'
+
+
 def scene(world: str, actuators: str, extra: str = "") -> str:
     return f'<mujoco model="rsb">{BASE_OPTION}<worldbody>{world}</worldbody><actuator>{actuators}</actuator>{extra}</mujoco>'

@@ -15,11 +15,11 @@ from . import assets as A
 from .mjcf import Model, compile_mjcf
 
 TASK_IDS = {"Lift": 0, "Door": 1, "Stack": 2, "TwoArmLift": 3, "PickPlaceMilk": 4, "PickPlaceBread": 4, "PickPlaceCereal": 4, "PickPlaceCan": 4,
-            "TwoArmPegInHole": 5, "NutAssemblyRound": 6}
+            "TwoArmPegInHole": 5, "NutAssemblyRound": 6, "TwoArmHandoff": 7}
 CTRL_IDS = {"OSC_POSE": 0, "OSC_POSITION": 1, "JOINT_VELOCITY": 2, "JOINT_TORQUE": 3, "JOINT_POSITION": 4}
 
 OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89, "PickPlaceMilk": 46, "PickPlaceBread": 46, "PickPlaceCereal": 46, "PickPlaceCan": 46,
-            "TwoArmPegInHole": 73, "NutAssemblyRound": 46}
+            "TwoArmPegInHole": 73, "NutAssemblyRound": 46, "TwoArmHandoff": 86}
 #: default bounds of the per-env contact list / constraint-row list (shared-memory sizing; rsb_create ncon_max / nefc_max).
 #: Maxima seen over 300 random-action control steps x 2048 envs (tools/limits_stats.py): Stack 16 contacts / 54 rows, TwoArmLift 9 / 31,
 #: Door 4 / 18, Lift 9 / 29; TwoArmLift (24, 80) keeps 2.5x headroom and lets 14 envs share an SM (4096 envs = 2 waves instead of 3).
@@ -32,6 +32,7 @@ OBS_DIMS = {"Lift": 42, "Door": 46, "Stack": 55, "TwoArmLift": 89, "PickPlaceMil
 #: `suite.make(..., ncon_max=24, nefc_max=80)` removes that at the price of a second wave at 4096 envs per GPU.
 LIMITS = {"Lift": (18, 62), ("Lift", "Sawyer"): (24, 80), "Door": (16, 64), "Stack": (24, 96), "TwoArmLift": (24, 80),
           "NutAssemblyRound": (56, 184),       # nine boxes resting on the table: 36 contacts / 110 rows before the gripper touches anything; random actions, 256 envs x 500 steps: 45 / 141
+          "TwoArmHandoff": (40, 128),          # random actions on the CPU oracle, 256 envs x 500 steps: 27 contacts / 91 rows (Panda fingers and the hammer's five boxes on the table)
           "TwoArmPegInHole": (8, 40),          # committed policies and random actions on the CPU oracle: at most 3 contacts (peg on the rim of the hole) / 11 rows
           # PickPlace on the CPU oracle.  Committed policies (16 episodes each): Panda reaches 13 contacts / 49 rows while carrying the object, Sawyer 18 / 64.
           # Random actions (768 envs x 500 steps): Panda 14 / 46, Sawyer 21 / 74 (the Rethink gripper's box fingers flat on the bin floor against a wall).
@@ -355,6 +356,40 @@ def _nut_assembly_round(robots, env_configuration):
     return xml, objs
 
 
+def _two_arm_handoff(robots, env_configuration):
+    """TwoArmHandoff, `single-arm-opposed`, prehensile: the hammer lies on a narrow table beside robot 0, which picks it up and hands it to robot 1."""
+    assert len(robots) == 2, "TwoArmHandoff takes two robots"
+    if env_configuration not in ("single-arm-opposed", "default", None):
+        raise NotImplementedError(f"env_configuration {env_configuration!r} is not implemented (single-arm-opposed only)")
+    H = A.HANDOFF
+    bodies, acts = "", ""
+    for i, (r, yaw, y) in enumerate(zip(robots, (np.pi / 2, -np.pi / 2), (-H["base_y"], H["base_y"]))):
+        R = A.ROBOTS[r]
+        bodies += R["body"](f"robot{i}_", (0.0, y, A.ROBOT_BASE_Z), (np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)))
+        acts += R["act"](f"robot{i}_")
+    rad = H["handle_radius"]
+    world = A.table_arena(full=H["table_full"], offset=H["table_offset"]) + bodies + A.hammer("hammer", [H["table_offset"][0], H["table_offset"][1], A.TABLE_HEIGHT + 2 * rad])
+    xml = A.scene(world, acts)
+
+    def objs(m: Model):
+        o = _empty_objs()
+        j = m.id("joint", "hammer_joint")
+        o["obj_body"][0] = m.id("body", "hammer")
+        o["obj_geom"][0], o["obj_geom"][1] = m.id("geom", "hammer_handle"), m.id("geom", "hammer_claw")
+        assert o["obj_geom"][1] - o["obj_geom"][0] == 4                     # handle first, contiguous ids: the grasp checks test a range / the first geom
+        o["obj_qposadr"][0], o["obj_dofadr"][0] = int(m.jnt_qposadr[j]), int(m.jnt_dofadr[j])
+        o["obj_half"][0] = [H["handle_length"] / 2, rad, rad]
+        o["place_x"][0], o["place_y"][0] = list(H["place_x"]), list(H["place_y"])
+        q = H["head_dir"] * np.pi / 2
+        o["place_yaw"][0] = [q - H["tilt"], q + H["tilt"]]                        # about y: a quarter turn lays the handle (body z) along world x
+        o["place_z"][0] = A.TABLE_HEIGHT + 1.2 * rad * H["head_half_ratio"] + 0.01
+        o["place_ref"] = np.array([H["table_offset"][0], H["table_offset"][1], A.TABLE_HEIGHT])
+        o["task_par"] = [H["lift_height"], rad]
+        return o
+
+    return xml, objs
+
+
 def _two_arm_peg_in_hole(robots, env_configuration):
     """TwoArmPegInHole, `single-arm-opposed`: two gripper-less arms facing each other over an empty floor; robot 0 holds the peg, robot 1 the plate with the hole
     (both rigidly attached to the hands: no free bodies, nothing to place at reset)."""
@@ -381,5 +416,5 @@ def _two_arm_peg_in_hole(robots, env_configuration):
     return xml, objs
 
 
-_BUILDERS: Dict[str, callable] = {"Lift": _lift, "Stack": _stack, "Door": _door, "TwoArmLift": _two_arm_lift, "TwoArmPegInHole": _two_arm_peg_in_hole, "NutAssemblyRound": _nut_assembly_round,
+_BUILDERS: Dict[str, callable] = {"Lift": _lift, "Stack": _stack, "Door": _door, "TwoArmLift": _two_arm_lift, "TwoArmPegInHole": _two_arm_peg_in_hole, "NutAssemblyRound": _nut_assembly_round, "TwoArmHandoff": _two_arm_handoff,
                                   **{"PickPlace" + k: _pick_place(k) for k in A.PICK_OBJECTS}}

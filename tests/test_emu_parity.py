@@ -12,7 +12,8 @@ CONFIGS = [("Lift", ["Panda"], "OSC_POSE", 42, 7), ("Lift", ["Panda"], "JOINT_VE
            ("Lift", ["Panda"], "JOINT_POSITION", 42, 8), ("Lift", ["Sawyer"], "JOINT_TORQUE", 42, 8),
            ("Door", ["Panda"], "JOINT_VELOCITY", 46, 8), ("Stack", ["Sawyer"], "OSC_POSE", 55, 7), ("TwoArmLift", ["Panda", "Panda"], "OSC_POSE", 89, 14),
            ("PickPlaceCan", ["Panda"], "OSC_POSE", 46, 7), ("PickPlaceMilk", ["Sawyer"], "OSC_POSE", 46, 7),
-           ("TwoArmPegInHole", ["Panda", "Sawyer"], "OSC_POSE", 73, 12), ("NutAssemblyRound", ["Panda"], "OSC_POSE", 46, 7)]
+           ("TwoArmPegInHole", ["Panda", "Sawyer"], "OSC_POSE", 73, 12), ("NutAssemblyRound", ["Panda"], "OSC_POSE", 46, 7),
+           ("TwoArmHandoff", ["Panda", "Sawyer"], "OSC_POSE", 86, 14)]
 
 
 @pytest.mark.parametrize("env_name,robots,ctrl,obs_dim,act_dim", CONFIGS)
@@ -130,7 +131,8 @@ def test_joint_velocity_laws(law):
 
 
 NEW_FAMILIES = [("PickPlaceCan", ["Panda"]), ("PickPlaceMilk", ["Sawyer"]), ("PickPlaceCan", ["Sawyer"]), ("PickPlaceMilk", ["Panda"]), ("TwoArmPegInHole", ["Panda", "Panda"]),
-                ("TwoArmPegInHole", ["Panda", "Sawyer"]), ("TwoArmPegInHole", ["Sawyer", "Sawyer"]), ("NutAssemblyRound", ["Panda"]), ("NutAssemblyRound", ["Sawyer"])]
+                ("TwoArmPegInHole", ["Panda", "Sawyer"]), ("TwoArmPegInHole", ["Sawyer", "Sawyer"]), ("NutAssemblyRound", ["Panda"]), ("NutAssemblyRound", ["Sawyer"]),
+                ("TwoArmHandoff", ["Panda", "Panda"]), ("TwoArmHandoff", ["Sawyer", "Sawyer"])]
 
 
 @pytest.mark.parametrize("env_name,robots,ctrl", [(e, r, "OSC_POSE") for e, r in NEW_FAMILIES] + [("Lift", ["Panda"], "JOINT_POSITION"), ("Stack", ["Sawyer"], "JOINT_TORQUE")])

@@ -22,6 +22,7 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 FAMILIES = [("PickPlaceCan", ["Panda"], "OSC_POSE"), ("PickPlaceMilk", ["Sawyer"], "OSC_POSE"), ("PickPlaceCan", ["Sawyer"], "OSC_POSE"), ("PickPlaceMilk", ["Panda"], "OSC_POSE"),
             ("TwoArmPegInHole", ["Panda", "Panda"], "OSC_POSE"), ("TwoArmPegInHole", ["Panda", "Sawyer"], "OSC_POSE"), ("TwoArmPegInHole", ["Sawyer", "Sawyer"], "OSC_POSE"),
             ("NutAssemblyRound", ["Panda"], "OSC_POSE"), ("NutAssemblyRound", ["Sawyer"], "OSC_POSE"),
+            ("TwoArmHandoff", ["Panda", "Panda"], "OSC_POSE"), ("TwoArmHandoff", ["Sawyer", "Sawyer"], "OSC_POSE"),
             ("Lift", ["Panda"], "JOINT_POSITION"), ("Stack", ["Sawyer"], "JOINT_TORQUE")]            # the joint-space controllers the other GPU tests do not reach
 
 

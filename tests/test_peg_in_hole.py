@@ -121,7 +121,7 @@ def test_observation_slices_follow_the_gripper_dofs():
     robot-state block is 28 wide, not 32, and the blocks tile the row exactly for every implemented family."""
     from robosuite_benchmark_b200.environments import _obs_slices
     from robosuite_benchmark_b200.model.tasks import _BUILDERS
-    two_arm = ("TwoArmLift", "TwoArmPegInHole")
+    two_arm = ("TwoArmLift", "TwoArmPegInHole", "TwoArmHandoff")
     for env_name in _BUILDERS:
         robots = ["Panda", "Sawyer"] if env_name in two_arm else ["Sawyer"]
         m, t = build_task(env_name, robots, load_controller_config(default_controller="OSC_POSE"))

@@ -182,15 +182,15 @@ RUN_FAMILIES = {
 
 
 def test_every_committed_run_family_builds_with_its_networks_dims_or_refuses_loudly():
-    """SURVEY 8f-3 coverage, family by family: 23 of the 29 committed run families compile into a task whose observation / action sizes are those of the family's
-    committed policy and Q networks; the other six (TwoArmHandoff, Wipe) raise NotImplementedError -- never a silent stand-in."""
+    """SURVEY 8f-3 coverage, family by family: 25 of the 29 committed run families compile into a task whose observation / action sizes are those of the family's
+    committed policy and Q networks; the other four (Wipe) raise NotImplementedError -- never a silent stand-in."""
     assert len(RUN_FAMILIES) == 29
     built = 0
     for fam, (obs_dim, act_dim) in RUN_FAMILIES.items():
         env_name, robots, ctrl = fam.split("-", 2)
         robots = {"PandaPanda": ["Panda", "Panda"], "SawyerSawyer": ["Sawyer", "Sawyer"], "PandaSawyer": ["Panda", "Sawyer"]}.get(robots, [robots])
         cfg = load_controller_config(default_controller=ctrl.replace("-", "_"))
-        if env_name in ("TwoArmHandoff", "Wipe"):
+        if env_name == "Wipe":
             with pytest.raises(NotImplementedError):
                 build_task(env_name, robots, cfg)
             continue
@@ -198,4 +198,4 @@ def test_every_committed_run_family_builds_with_its_networks_dims_or_refuses_lou
         assert (t["obs_dim"], t["act_dim"]) == (obs_dim, act_dim), (fam, t["obs_dim"], t["act_dim"])
         assert t["substeps"] == 25 and m.nv <= 32
         built += 1
-    assert built == 23
+    assert built == 25

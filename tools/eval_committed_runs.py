@@ -9,7 +9,7 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
 import numpy as np
 OUT = os.path.join(ROOT, "oracle", "_ref", "policies")
-FAMILIES = ("Lift", "Door", "Stack", "TwoArmLift", "PickPlaceCan", "PickPlaceMilk", "TwoArmPegInHole", "NutAssemblyRound")
+FAMILIES = ("Lift", "Door", "Stack", "TwoArmLift", "PickPlaceCan", "PickPlaceMilk", "TwoArmPegInHole", "NutAssemblyRound", "TwoArmHandoff")
 mode = sys.argv[1] if len(sys.argv) > 1 else "export"
 if mode == "export":
     from robosuite_benchmark_b200.policy_io import load_params_pkl, mlp_weights

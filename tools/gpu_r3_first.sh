@@ -11,4 +11,5 @@ done
 python tools/eval_committed_runs.py run 256 PickPlace > gpurun_out/r3_policy_transfer_pickplace.txt 2>&1
 python tools/eval_committed_runs.py run 256 TwoArmPegInHole > gpurun_out/r3_policy_transfer_peginhole.txt 2>&1
 python tools/eval_committed_runs.py run 256 NutAssemblyRound > gpurun_out/r3_policy_transfer_nutassembly.txt 2>&1
+python tools/eval_committed_runs.py run 256 TwoArmHandoff > gpurun_out/r3_policy_transfer_handoff.txt 2>&1
 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/r3_all_gpu_tests.log 2>&1; tail -3 gpurun_out/r3_all_gpu_tests.log
