@@ -7,7 +7,7 @@ tanh(N(0,1)) actions from the Philox stream shared with the oracle, horizon 500 
 states/actions resident in HBM (CUDA events around each step, L2 flushed between steps); `e2e` goes through the host-buffer C-ABI call
 (pinned host actions in, obs/reward/done out) each step.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--config lift|door|stack|twoarmlift|pickplacecan|peginhole|nutassemblyround] [--mode step|train] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--config lift|door|stack|twoarmlift|pickplacecan|peginhole|nutassemblyround|handoff] [--mode step|train] [--impl ours|reference]
 
 --config selects the other BASELINE.json configs (configs[2] Door-Panda-JOINT_VELOCITY x 16384, configs[3] Stack-Sawyer-OSC_POSE,
 configs[4] TwoArmLift-PandaPanda-OSC_POSE); the default (lift) line also carries a short steady-state measurement of each of them
@@ -41,6 +41,7 @@ CONFIGS = {   # BASELINE.json configs[1..4]
     "pickplacecan": dict(env="PickPlaceCan", robots=["Panda"], controller="OSC_POSE", envs=4096),
     "peginhole": dict(env="TwoArmPegInHole", robots=["Panda", "Sawyer"], controller="OSC_POSE", envs=4096),
     "nutassemblyround": dict(env="NutAssemblyRound", robots=["Sawyer"], controller="OSC_POSE", envs=4096),
+    "handoff": dict(env="TwoArmHandoff", robots=["Panda", "Panda"], controller="OSC_POSE", envs=4096),
 }
 UNIT = "control-steps/s"
 PREROLL = 100          # untimed control steps after the initial reset (run_ours): the timed region sits on the steady-state part of the episode
@@ -411,7 +412,7 @@ def run_ours(args):
     if not args.quick and args.config == "lift" and world == 1:
         # the families added last (CONFIGS): measured after everything the headline line needs, single-GPU line only, and never allowed to take that line down
         more = {}
-        for name in ("pickplacecan", "peginhole", "nutassemblyround"):
+        for name in ("pickplacecan", "peginhole", "nutassemblyround", "handoff"):
             c = CONFIGS[name]
             try:
                 more[name] = steady_state_rate(c, c["envs"], dev, 0, steps=20)

@@ -5,7 +5,7 @@ set -x
 mkdir -p gpurun_out
 python -m pytest tests/test_gpu_zz_pickplace.py -q -p no:cacheprovider > gpurun_out/r3_newfam_tests.log 2>&1
 tail -5 gpurun_out/r3_newfam_tests.log
-for c in pickplacecan peginhole nutassemblyround; do
+for c in pickplacecan peginhole nutassemblyround handoff; do
   python bench.py --config $c --steps 20 --warmup 3 --no-sac --no-train --no-cpu > gpurun_out/r3_bench_$c.json 2> gpurun_out/r3_bench_$c.err
 done
 python tools/eval_committed_runs.py run 256 PickPlace > gpurun_out/r3_policy_transfer_pickplace.txt 2>&1
