@@ -124,7 +124,7 @@ typedef struct rsb_task {
      PICKPLACE: obj_body[0]=the object, obj_geom[0]=its collision geom, obj_qposadr[0]=free joint; task_par below
      PEGINHOLE: obj_body[0]=plate with the hole, obj_body[1]=peg; task_par below
      HANDOFF: obj_body[0]=hammer, obj_geom[0]..obj_geom[1] = its (contiguous) geoms, the FIRST being the handle, obj_qposadr[0]=free joint; the placement angle
-              (place_yaw) turns the hammer about the world y axis (robosuite: rotation_axis='y'), not z
+              (place_yaw) turns the hammer about the world x axis, with a random sign (head towards robot 0 or towards robot 1), not about z
      NUTASSEMBLY: obj_body[0]=the nut, obj_geom[0]..obj_geom[1] = its (contiguous) collision geoms, the last one being the handle, obj_qposadr[0]=free joint */
   int obj_body[RSB_MAX_OBJ], obj_geom[RSB_MAX_OBJ], obj_site[RSB_MAX_OBJ];
   int obj_qposadr[RSB_MAX_OBJ], obj_dofadr[RSB_MAX_OBJ];

@@ -1286,7 +1286,9 @@ void orc_reset(orc_env *e, uint64_t seed, uint64_t env_id, uint64_t episode) {
     real *dst = t->place_body[o] >= 0 ? e->bpose : e->qpos + qa;
     dst[0] = t->place_ref[0] + x; dst[1] = t->place_ref[1] + y; dst[2] = t->place_z[o];
     dst[3] = cos(0.5 * yaw); dst[4] = 0; dst[5] = 0; dst[6] = sin(0.5 * yaw);
-    if (t->task_id == RSB_TASK_HANDOFF) { dst[5] = dst[6]; dst[6] = 0; }        /* the hammer is turned about y (robosuite: rotation_axis='y') */
+    if (t->task_id == RSB_TASK_HANDOFF) {         /* the hammer is laid down by a quarter turn about the world x axis, head towards robot 0 or robot 1 (fourth word of the draw) */
+      real sg = (r[3] & 1u) ? -1.0 : 1.0; dst[4] = sg * dst[6]; dst[6] = 0;
+    }
   }
   orc_forward(e);
   for (int ri = 0; ri < t->nrobot; ri++) controller_reset(e, ri);

@@ -1810,7 +1810,7 @@ RSB_D void env_reset(int so, Grp g, real *st, uint64_t seed, uint64_t env_id, re
       real *dst = MDL.place_body[o] >= 0 ? s + MDL.o_bpose : qpos + qa;
       dst[0] = MDL.place_ref[0] + x; dst[1] = MDL.place_ref[1] + y; dst[2] = MDL.place_z[o];
       dst[3] = c; dst[4] = 0; dst[5] = 0; dst[6] = sn;
-      if (MDL.task_id == RSB_TASK_HANDOFF) { dst[5] = sn; dst[6] = 0; }        /* the hammer is turned about y (robosuite: rotation_axis='y') */
+      if (MDL.task_id == RSB_TASK_HANDOFF) { dst[4] = (r[3] & 1u) ? -sn : sn; dst[6] = 0; }        /* laid down by a quarter turn about the world x axis, head towards robot 0 or robot 1 */
     }
   }
   gsync(g);

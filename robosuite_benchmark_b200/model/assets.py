@@ -486,10 +486,12 @@ def round_nut(name, pos) -> str:
 #: (0, -0.45) with its top at 0.8, beside robot 0; the arms face each other along y.  `base_y`: where the bases stand; 0.76 = 0.16 + 1.2 / 2 is what the committed
 #: runs' epoch-0 reward level says (reach term 0.125 (1 - tanh d0): logged 0.094-0.100 for Panda, 0.079-0.094 for Sawyer; 0.096 / 0.090 here; with 0.56 it
 #: would be 0.079).  HammerObject (generated per model upstream with random sizes: handle radius U(0.015, 0.02), length U(0.1, 0.25), density U(100, 250), friction
-#: U(3, 5), head density x 2): the MEANS here; the neck / face cylinders are boxes of the same cross-section area.  The hammer starts lying along x on the table
-#: (robosuite samples a rotation about y and lets it fall; here: a quarter turn +- `tilt`).
+#: U(3, 5), head density x 2): the MEANS here; the neck / face cylinders are boxes of the same cross-section area.  The hammer starts lying along y on the table, its
+#: head towards robot 0 or robot 1 at random (a quarter turn about x, +- `tilt`).  Chosen by the committed policies: lying along x (a turn about y, as robosuite's
+#: sampler argument rotation_axis='y' was first read) none of them holds the hammer; lying along y the best ones grasp, lift and hold it for whole episodes
+#: (profiles/r2_policy_transfer_handoff_cpu.txt).
 HANDOFF = dict(table_full=(0.8, 0.3, 0.05), table_offset=(0.0, -0.45), base_y=0.76, handle_radius=0.0175, handle_length=0.175, handle_density=175.0, handle_friction=4.0,
-               head_density_ratio=2.0, head_half_ratio=1.1, place_x=(-0.1, 0.1), place_y=(-0.05, 0.05), tilt=0.1, lift_height=0.1, head_dir=1.0)       # head_dir: +1 head towards +x, -1 towards -x
+               head_density_ratio=2.0, head_half_ratio=1.1, place_x=(-0.1, 0.1), place_y=(-0.05, 0.05), tilt=0.1, lift_height=0.1)
 
 
 def hammer(name, pos) -> str:

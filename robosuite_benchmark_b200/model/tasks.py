@@ -380,8 +380,9 @@ def _two_arm_handoff(robots, env_configuration):
         o["obj_qposadr"][0], o["obj_dofadr"][0] = int(m.jnt_qposadr[j]), int(m.jnt_dofadr[j])
         o["obj_half"][0] = [H["handle_length"] / 2, rad, rad]
         o["place_x"][0], o["place_y"][0] = list(H["place_x"]), list(H["place_y"])
-        q = H["head_dir"] * np.pi / 2
-        o["place_yaw"][0] = [q - H["tilt"], q + H["tilt"]]                        # about y: a quarter turn lays the handle (body z) along world x
+        # a quarter turn about the world x axis lays the handle (body z) along world y, i.e. pointing from one robot to the other; the reset code draws the sign
+        # (head towards robot 0 or towards robot 1)
+        o["place_yaw"][0] = [np.pi / 2 - H["tilt"], np.pi / 2 + H["tilt"]]
         o["place_z"][0] = A.TABLE_HEIGHT + 1.2 * rad * H["head_half_ratio"] + 0.01
         o["place_ref"] = np.array([H["table_offset"][0], H["table_offset"][1], A.TABLE_HEIGHT])
         o["task_par"] = [H["lift_height"], rad]

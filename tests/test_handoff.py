@@ -6,8 +6,9 @@ What the reference pins (it ships no tests):
     0.25 (arm 0 holds the hammer), 0.5 .. 0.625 (lifted, arm 1 approaching), exactly 1.0 (handed over);
   * the epoch-0 evaluation reward level, i.e. 0.125 (1 - tanh |gripper 0 - handle|) after reset: 0.0974 (PandaPanda), 0.0917 (SawyerSawyer; mean of the seeds whose
     epoch-0 episodes stayed in the reach stage) -- it pins where the arms, the table and the hammer stand.
-What is NOT shown: transfer of the committed policies (they reach and touch the handle here but do not hold it; profiles/r2_policy_transfer_handoff_cpu.txt) -- the
-hammer is generated with random sizes upstream and is authored from the recalled means here (model/assets.py HANDOFF)."""
+Transfer of the committed policies is PARTIAL (profiles/r2_policy_transfer_handoff_cpu.txt): with the hammer lying along y the better policies grasp, lift and hold it
+for whole episodes, the others stay at the reach level; the hammer is generated with random sizes upstream and is authored from the recalled means here
+(model/assets.py HANDOFF)."""
 import numpy as np
 import pytest
 
@@ -45,7 +46,7 @@ def test_stage_values_are_the_logged_ones():
     c = np.sqrt(0.5)
 
     def rew(pos, fingers0=None):
-        q = qp.copy(); q[qa:qa + 3] = pos; q[qa + 3:qa + 7] = [c, 0, c, 0]                 # handle along x
+        q = qp.copy(); q[qa:qa + 3] = pos; q[qa + 3:qa + 7] = [c, 0, c, 0]                 # handle along x: across robot 0's closed fingers
         if fingers0 is not None:
             q[t["robot"][0]["grip_qposadr"][0]], q[t["robot"][0]["grip_qposadr"][1]] = fingers0, -fingers0
         orc.set_state(q, np.zeros_like(qv), w, cs)
